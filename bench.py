@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the render() hot path (BASELINE.json: rays/s for render() forward, 1200x680 image in
+1024-ray chunks, 64+64 samples, shipped network shapes, random-init synthetic model).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16|bf16x3]
+
+A "step" is one full-image render (816 000 rays) per GPU.  One JSON line is printed by rank 0:
+  value    -- rays/s with rays and uniform draws already resident in HBM (device-timed, max over ranks)
+  e2e      -- the same metric through VectorFieldNerf.render() the way evaluation/methods.py:516-530 calls
+              it: per 1024-ray chunk, pinned-host uv/pose/intrinsics -> device, CPU-generator draws -> device,
+              render, rgb/depth -> host; all inside the timed region
+  roofline -- the dominant kernel (VF MLP chain) timed alone with CUDA events, algorithmic FLOPs / time
+  cpu_baseline -- the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1)
+`--impl reference` times that CPU path alone (bounded: one 1024-ray chunk per step).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H, W_IMG, FOCAL = 680, 1200, 600.0
+N_COARSE, N_FINE = 64, 64
+F_VF, F_RN = 1_050_112, 542_720                    # algorithmic FLOP / point
+A_FWD = (N_COARSE + N_FINE) * (F_VF + F_RN)        # FLOP / ray, unique points only
+CASE = dict(seed=0, vf_hidden=(256,) * 8, feat=256, rn_hidden=(256,) * 4, n_coarse=N_COARSE, n_fine=N_FINE,
+            max_samples=100, perturb=False, near=0.0, far=6.0, fine_range=0.3, window=11,
+            dir_to_normal_th=-0.2, vf_gain=2.0)     # evaluation settings: evaluate.py:30,32
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("VFNERF_PRECISION", "fp32"))
+    ap.add_argument("--chunk", type=int, default=0, help="rays per render() call of the device-resident leg")
+    ap.add_argument("--rays", type=int, default=H * W_IMG, help="rays per step (default: the full image)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_pack():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import vfn_testutil as U
+    return U
+
+
+def cpu_reference_rays_per_s(n_steps, n_warm, threads=None):
+    """The reference's CPU path (oracle port, torch-CPU fp32 eager, all host threads): one 1024-ray chunk
+    per step, deterministic sampling -- the `--gpu cpu` configuration of BASELINE config 1."""
+    U = oracle_pack()
+    if threads:
+        torch.set_num_threads(threads)
+    st = U.S.synthetic_state(CASE["seed"], vf_gain=CASE["vf_gain"])
+    R = 1024
+    uv, pose, K = U.S.synthetic_rays(R, seed=0, start=0, stride=797)
+    _, _, U3 = U.S.synthetic_draws(R, N_COARSE, N_FINE, seed=1)
+    t_vals = torch.linspace(0., 1., N_COARSE)
+    cfg = U.oracle_cfg(CASE)
+    times = []
+    with torch.no_grad():
+        for i in range(n_warm + n_steps):
+            t0 = time.perf_counter()
+            U.O.render(st["vf_net"], st["rendering_net"], st["density"], cfg, uv, pose, K, t_vals, None, None, U3)
+            dt = time.perf_counter() - t0
+            if i >= n_warm:
+                times.append(dt)
+    med = statistics.median(times)
+    return R / med, med, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rps, med, threads = cpu_reference_rays_per_s(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "render_fwd_rays_per_sec", "value": rps, "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "render() forward, Replica-shaped 1200x680 image in 1024-ray chunks, 64+64 samples "
+                               "(reference arm: one 1024-ray chunk per step on the host CPU)",
+                   "rays_per_step": 1024, "n_coarse": N_COARSE, "n_fine": N_FINE},
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                         "sample": "one 1024-ray chunk per step, torch-CPU fp32 eager restatement of the reference "
+                                   "(oracle/render_oracle.py); the reference itself is Python and cannot travel"},
+        "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product has no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    U = oracle_pack()     # test helpers build the model; the oracle itself is only used by cpu_baseline
+    from vfnerf_b200 import _lib
+    _lib.build()
+    L = _lib.lib()
+    st = U.S.synthetic_state(CASE["seed"], vf_gain=CASE["vf_gain"])
+    model = U.make_model(CASE, st, dev, precision=args.precision)
+    model.return_ray_dirs = False       # the evaluation caller reads rgb/depth only (methods.py:529-530)
+    R = args.rays
+    chunk = args.chunk or (4096 if args.precision == "fp32" else 65536)
+
+    # ---- inputs: one synthetic camera per rank (weak scaling: every GPU renders a full image)
+    pose1, K1 = U.S.synthetic_camera(seed=rank, height=H, width=W_IMG, focal=FOCAL)
+    uv_h = U.S.pixel_grid(H, W_IMG)[:R].contiguous().pin_memory()
+    pose_h = pose1.repeat(R, 1, 1).contiguous().pin_memory()
+    K_h = K1.repeat(R, 1, 1).contiguous().pin_memory()
+    uv_d, pose_d, K_d = uv_h.to(dev), pose_h.to(dev), K_h.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    U3_d = torch.rand(R, N_FINE, device=dev, generator=gen)
+    rgb_img = torch.empty(R, 3, device=dev)
+    dep_img = torch.empty(R, 1, device=dev)
+
+    def step_resident():
+        with torch.no_grad():
+            for a in range(0, R, chunk):
+                b = min(R, a + chunk)
+                out = model.render(pose_d[a:b], uv_d[a:b], K_d[a:b], 0, draws=(None, None, U3_d[a:b]))
+                rgb_img[a:b] = out.coarse_rgb_values
+                dep_img[a:b] = out.coarse_depth_map
+        if world > 1:    # final gather of rgb+depth to rank 0 (16 B/ray), SURVEY.md §8e
+            both = torch.cat([rgb_img, dep_img], dim=1)
+            gl = [torch.empty_like(both) for _ in range(world)] if rank == 0 else None
+            dist.gather(both, gl, dst=0)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    sync_all()
+    clocks = ClockSampler(local)
+    clocks.start()
+    n0 = L.vfnerf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    sync_all()
+    launches = L.vfnerf_launch_count() - n0
+    clk = clocks.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    value = world * R * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: reference-facing call with host buffers, 1024-ray chunks (methods.py:516-530)
+    e2e = None
+    if not args.no_e2e:
+        ck = 1024
+        h2d = d2h = 0
+
+        def step_e2e(count):
+            nonlocal h2d, d2h
+            with torch.no_grad():
+                for a in range(0, R, ck):
+                    b = min(R, a + ck)
+                    px = uv_h[a:b].to(dev, non_blocking=True)
+                    po = pose_h[a:b].to(dev, non_blocking=True)
+                    ki = K_h[a:b].to(dev, non_blocking=True)
+                    out = model.render(po, px, ki, 0)          # draws U3 on the CPU generator + H2D, like the reference
+                    r_h = out.coarse_rgb_values.cpu()
+                    d_h = out.coarse_depth_map.cpu()
+                    if count:
+                        h2d += (px.numel() + po.numel() + ki.numel() + (b - a) * N_FINE + N_COARSE) * 4
+                        d2h += (r_h.numel() + d_h.numel()) * 4
+        step_e2e(False)
+        sync_all()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        step_e2e(True)
+        s1.record()
+        sync_all()
+        ms2 = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * R / (ms2.item() * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "chunk": ck}
+
+    # ---- roofline of the dominant kernel: the VF MLP chain on one chunk of merged points
+    from vfnerf_b200 import ops
+    pk, pk_src = peaks()
+    P = min(R, chunk) * (N_COARSE + N_FINE)
+    pts = (torch.rand(P, 3, device=dev) - 0.5) * 6
+    with torch.no_grad():
+        for _ in range(3):
+            ops.vf_query(model.vector_field_network, pts)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        r0.record()
+        for _ in range(reps):
+            ops.vf_query(model.vector_field_network, pts)
+        r1.record()
+        torch.cuda.synchronize()
+    t_vf = r0.elapsed_time(r1) * 1e-3 / reps
+    ach = F_VF * P / t_vf / 1e12
+    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": None, "kernel": "VF MLP chain over one chunk (%d points)" % P,
+                "algorithmic_flop_per_launch": F_VF * P, "ms_per_launch": t_vf * 1e3, "peak_source": pk_src,
+                "whole_path_frac": (A_FWD * value / world) / 1e12 / peak_tf}
+
+    line = {
+        "metric": "render_fwd_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3"}[args.precision], "data": "synthetic",
+        "config": {"workload": "render() forward, Replica-shaped 1200x680 image (816000 rays) per GPU, 64+64 samples, "
+                               "shipped VF(39-256x8-259)+colour(289-256x4-3) nets, deterministic sampling",
+                   "rays_per_step_per_gpu": R, "chunk_rays": chunk, "n_coarse": N_COARSE, "n_fine": N_FINE,
+                   "l2": "working set per step (workspace + outputs) exceeds the 126 MB L2 many times over; no explicit flush",
+                   "parallelism": f"rays sharded, {world} process(es), final gather to rank 0"},
+        "clocks": clk, "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rps, med, threads = cpu_reference_rays_per_s(3, 1)
+        line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                                "sample": "3 timed renders of one 1024-ray chunk (median) after 1 warm-up, oracle port on host cores"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,190 @@
+/* vfnerf_b200 -- C ABI of the B200-native VF-NeRF render() hot path.
+ *
+ * The reference (albertgassol1/vf-nerf) has no FFI: its "operator interface" for this path is the
+ * Python method VectorFieldNerf.render() (models/nerf/vector_field_nerf.py:216-338) and the bare
+ * nn.Module call VectorFieldNetwork.__call__ (models/vector_field/vector_field_network.py:140-208,
+ * used by evaluation/utils/mc_utils.py:88-104 and train/vector_field_nerf_train.py:191,203,215).
+ * The entry points below are what a ctypes binding of those two call sites needs (INTEGRATION.md
+ * shows the stub).  Conventions:
+ *   - every pointer is a DEVICE pointer to contiguous fp32 unless stated otherwise;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default);
+ *   - no hidden allocation: scratch memory is a caller-provided workspace whose size is queried first;
+ *   - return value 0 = ok, non-zero = error; vfnerf_last_error() returns a thread-local message;
+ *   - no exceptions cross the boundary, no torch types appear in any signature.
+ */
+#ifndef VFNERF_B200_H
+#define VFNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFNERF_MAX_LAYERS 16
+#define VFNERF_MAX_SAMPLES 256 /* samples per ray (coarse + fine) handled by one warp */
+
+/* precision of the two MLPs */
+#define VFNERF_PREC_FP32 0    /* CUDA-core fp32 (generic layer widths) -- parity path, 1e-3 contract      */
+#define VFNERF_PREC_BF16 1    /* tcgen05 bf16 x bf16 -> fp32 in TMEM (256-wide nets) -- 5e-3 contract       */
+#define VFNERF_PREC_BF16X3 2  /* tcgen05, hi/lo split operands, 3 MMAs per product -- fp32-class accuracy   */
+
+/* One MLP (Linear [+ BatchNorm1d in eval mode] per layer).  All parameters AND running statistics of
+ * the network live in one contiguous fp32 "arena"; the offsets below are in floats.  -1 = absent.
+ * Mirrors the state_dict of VectorFieldNetwork / RenderingNetwork: layers.{i}.0.{weight,bias},
+ * layers.{i}.1.{weight,bias,running_mean,running_var}, last layer layers.{n-1}.{weight,bias}.
+ * The gradient arena produced by the backward calls has the same layout (running-stat slots = 0). */
+typedef struct vfnerf_mlp_desc {
+  int32_t n_layers;
+  int32_t in_dim[VFNERF_MAX_LAYERS];
+  int32_t out_dim[VFNERF_MAX_LAYERS];
+  int64_t w_off[VFNERF_MAX_LAYERS];     /* Linear.weight [out,in] row-major                      */
+  int64_t b_off[VFNERF_MAX_LAYERS];     /* Linear.bias [out]                                     */
+  int64_t gamma_off[VFNERF_MAX_LAYERS]; /* BatchNorm1d.weight, -1 on layers without BN           */
+  int64_t beta_off[VFNERF_MAX_LAYERS];  /* BatchNorm1d.bias                                      */
+  int64_t mean_off[VFNERF_MAX_LAYERS];  /* running_mean                                          */
+  int64_t var_off[VFNERF_MAX_LAYERS];   /* running_var                                           */
+  int64_t arena_floats;
+} vfnerf_mlp_desc;
+
+/* Everything render() reads from the reference's config objects at call time
+ * (config_parser/vf_nerf_config.py:62-124, models/samplers/ray_sampler.py near/far/N_samples). */
+typedef struct vfnerf_render_cfg {
+  int32_t n_rays;
+  int32_t n_coarse;         /* ray_sampler.N_samples                                         */
+  int32_t n_fine;           /* min(fine_sampler.N_samples, fine_sampler.max_samples)         */
+  int32_t perturb;          /* 0: deterministic (eval)  1: stratified with U1/U2             */
+  int32_t pose_is_quat;     /* 0: pose [R,4,4]   1: pose [R,7] = (qr,qi,qj,qk,tx,ty,tz)      */
+  int32_t window;           /* len(cos_sim_weights), 11 in the shipped config                */
+  int32_t normalize;        /* normalize_rendering                                           */
+  int32_t multires;         /* VF embedder_multires (6)                                      */
+  int32_t multires_view;    /* rendering-net embedder_multires (4)                           */
+  int32_t skip_layer;       /* VF skip_connection_in[0], -1 = none                           */
+  int32_t precision;        /* VFNERF_PREC_*                                                 */
+  int32_t reserved;
+  double near_, far_, fine_range;   /* python floats of the samplers (kept in double: the reference
+                                       forms far-near and 2*range/(Nf-1) in double before rounding) */
+  float dir_to_normal_th;
+  float beta_lo, beta_hi, mean_lo, mean_hi, scale_min;   /* LaplaceDensity bounds                */
+  float bn_eps;
+} vfnerf_render_cfg;
+
+/* Outputs of render() == fields of NerfOutput (models/nerf/output.py:7-22) as filled at
+ * vector_field_nerf.py:331-338, plus optional intermediates (may be NULL). */
+typedef struct vfnerf_render_out {
+  float* points;        /* [R,N,3]  NerfOutput.points_coarse (merged coarse+fine points)          */
+  float* normals;       /* [R,N,3]  NerfOutput.coarse_normals (raw tanh VF vectors)               */
+  float* rgb;           /* [R,3]    NerfOutput.coarse_rgb_values                                  */
+  float* depth;         /* [R,1]    NerfOutput.coarse_depth_map                                   */
+  float* z_vals;        /* [R,N]    NerfOutput.z_vals                                             */
+  float* ray_dirs_rep;  /* [R*N,3]  NerfOutput.ray_dirs (unit dirs repeated per sample), nullable */
+  float* colors;        /* [R*N,3]  NerfOutput.coarse_colors                                      */
+  float* weights;       /* [R,N]    compositing weights (additive extra), nullable                */
+  float* z_coarse;      /* [R,Nc]   nullable                                                      */
+  float* weights_coarse;/* [R,Nc]   nullable                                                      */
+} vfnerf_render_out;
+
+int vfnerf_abi_version(void);
+const char* vfnerf_last_error(void);
+/* number of kernels this library has launched in this process (monotonic; for gpu_launches accounting) */
+long long vfnerf_launch_count(void);
+
+/* ---- whole path ------------------------------------------------------------------------------- */
+
+/* Bytes of workspace render_fwd needs for cfg->n_rays rays.  keep_for_backward != 0 reserves the
+ * activation stash that vfnerf_render_bwd consumes. */
+int64_t vfnerf_render_workspace_bytes(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf,
+                                      const vfnerf_mlp_desc* rn, int keep_for_backward);
+
+/* VectorFieldNerf.render(pose, pixels, intrinsics, epoch) in eval mode, rendering="volsdf"
+ * (vector_field_nerf.py:216-338).  uv [R,2]; pose [R,4,4] or [R,7]; intrinsics [R,4,4];
+ * t_vals [Nc] = torch.linspace(0,1,Nc) made by the host (ray_sampler.py:129);
+ * U1 [R,Nc], U2 [R,Nf] (read only when cfg->perturb), U3 [R,Nf] (always read) are the three
+ * uniform draws of ray_sampler.py:138,292,297.  z_override (nullable, [R,N]) replaces the merged z
+ * values of the second pass (parity protocol: the argmax that places fine samples is discontinuous).
+ * density_params = {beta, scale, mean} raw (unclamped) parameters on the device. */
+int vfnerf_render_fwd(const vfnerf_render_cfg* cfg,
+                      const vfnerf_mlp_desc* vf, const float* vf_arena,
+                      const vfnerf_mlp_desc* rn, const float* rn_arena,
+                      const float* density_params,
+                      const float* uv, const float* pose, const float* intrinsics,
+                      const float* t_vals, const float* U1, const float* U2, const float* U3,
+                      const float* z_override,
+                      const vfnerf_render_out* out,
+                      void* workspace, int64_t workspace_bytes, int keep_for_backward,
+                      void* stream);
+
+/* Backward of the second (merged) pass -- the autograd graph the reference builds at
+ * vector_field_nerf.py:281-323 (the coarse pass runs under no_grad, :252; sample positions carry
+ * no grad; normals are detached on the way into the colour net, rendering_network.py:76-77).
+ * d_rgb [R,3], d_depth [R,1], d_normals [R,N,3] (nullable), d_colors [R*N,3] (nullable).
+ * Gradients are WRITTEN (not accumulated) into grad arenas laid out like the parameter arenas and
+ * into d_density[3] = d(beta, scale, mean).  `workspace` must be the one render_fwd filled with
+ * keep_for_backward != 0 for the same cfg; `out` the same output block. */
+int vfnerf_render_bwd(const vfnerf_render_cfg* cfg,
+                      const vfnerf_mlp_desc* vf, const float* vf_arena,
+                      const vfnerf_mlp_desc* rn, const float* rn_arena,
+                      const float* density_params,
+                      const vfnerf_render_out* out,
+                      const float* d_rgb, const float* d_depth, const float* d_normals,
+                      const float* d_colors,
+                      float* vf_grad_arena, float* rn_grad_arena, float* d_density,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- VF-only query: VectorFieldNetwork.__call__ in eval mode -------------------------------- */
+/* (vector_field_network.py:177-208; the marching-cubes grid query of mc_utils.py:88-104 and the
+ * supervision-point queries of train/vector_field_nerf_train.py:191,203,215).
+ * points [P,3] -> out [P,out_ld] with the first n_out_cols columns of [v(3), feat(F)] written
+ * (n_out_cols = 3 for the grid query, 3+F for the module call). */
+int64_t vfnerf_vf_workspace_bytes(const vfnerf_mlp_desc* vf, int64_t n_points, int multires,
+                                  int keep_for_backward, int precision);
+int vfnerf_vf_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires, int skip_layer,
+                  float bn_eps, int precision, const float* points, int64_t n_points,
+                  float* out, int64_t out_ld, int n_out_cols,
+                  void* workspace, int64_t workspace_bytes, int keep_for_backward, void* stream);
+/* d_out [P,d_ld] holds dL/d(out[:, :n_out_cols]); grads are ACCUMULATED into vf_grad_arena when
+ * accumulate != 0 (the trainer sums the render() and supervision-point contributions). */
+int vfnerf_vf_bwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires, int skip_layer,
+                  float bn_eps, int precision, int64_t n_points,
+                  const float* out, int64_t out_ld, const float* d_out, int64_t d_ld, int n_out_cols,
+                  float* vf_grad_arena, int accumulate,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Same query with grid coordinates generated in-kernel (evaluation/methods.py:194-208): point i has
+ * integer coordinates (ix,iy,iz) = unravel(i0 + i, [res,res,res]) (z fastest) and position
+ * ((index * voxel + origin) + translation) + centroid per axis -- the reference's fp32 op order.
+ * origin/translation/centroid are 3 floats each in HOST memory.  out[i, 0:3] = v. */
+int vfnerf_vf_grid_query(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires, int skip_layer,
+                         float bn_eps, int precision, int res, int64_t i0, int64_t n_points,
+                         const float* origin3_host, const float* translation3_host,
+                         const float* centroid3_host, float voxel, float* out,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- stage entry points (one per SURVEY.md §8(a) row; used by the parity tests) ------------- */
+/* a1: get_ray_directions_and_cam_location, utils/rendering.py:12-60 */
+int vfnerf_ray_geometry(int n_rays, int pose_is_quat, const float* uv, const float* pose,
+                        const float* intrinsics, float* directions, float* ray_dirs, float* cam_loc,
+                        void* stream);
+/* a2: UniformSampler.get_z_vals + RaySampler.sample, ray_sampler.py:113-142, 49-80 */
+int vfnerf_coarse_sample(int n_rays, int n_coarse, double near_, double far_, int perturb,
+                         const float* t_vals, const float* U1, const float* directions,
+                         const float* cam_loc, float* z, float* points, void* stream);
+/* a7: RangeFineSampler.get_z_vals + sample, ray_sampler.py:264-302 */
+int vfnerf_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, double far_,
+                       double fine_range, int perturb, const float* z_coarse, const float* w_coarse,
+                       const float* U2, const float* U3, const float* directions, const float* cam_loc,
+                       float* z, float* points, void* stream);
+/* a4+a5+a6: window_cosine_similarity + get_density + volsdf_volume_rendering
+ * (functions.py:41-72, vector_field_nerf.py:442-474, rendering.py:122-148).
+ * normals [R,N,*] with row stride normals_ld floats per sample. */
+int vfnerf_density_weights(const vfnerf_render_cfg* cfg, int n_samples, const float* density_params,
+                           const float* normals, int64_t normals_ld, const float* ray_dirs,
+                           const float* z, float* cosw, float* sigma, float* weights, void* stream);
+/* a9: rgb = sum_j w_j c_j, depth = sum_j w_j z_j, vector_field_nerf.py:322-323 */
+int vfnerf_composite(int n_rays, int n_samples, const float* weights, const float* colors,
+                     const float* z, float* rgb, float* depth, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFNERF_B200_H */

@@ -1,0 +1,111 @@
+"""CPU: host-side mirror of the reference interface -- state_dict keys, parameter list quirks,
+draw order, error behaviour, and the refusal to run without CUDA."""
+import pytest
+import torch
+
+import vfn_testutil as U
+from vfnerf_b200 import VectorFieldNerf, VFNerfConfig
+from vfnerf_b200.samplers import RangeFineSampler, UniformSampler
+
+
+@pytest.fixture(scope="module")
+def model():
+    case, z = U.load_golden("full_det")
+    return U.make_model(case, U.case_state(case, z), "cpu")
+
+
+def test_state_dict_keys_match_reference(model):
+    # key pattern of the reference's checkpoints (SURVEY.md §5 "Checkpoint / resume")
+    want_vf = []
+    for i in range(8):
+        want_vf += [f"layers.{i}.0.weight", f"layers.{i}.0.bias", f"layers.{i}.1.weight", f"layers.{i}.1.bias",
+                    f"layers.{i}.1.running_mean", f"layers.{i}.1.running_var", f"layers.{i}.1.num_batches_tracked"]
+    want_vf += ["layers.8.weight", "layers.8.bias"]
+    assert list(model.vector_field_network.state_dict().keys()) == want_vf
+    rn = list(model.rendering_network.state_dict().keys())
+    assert rn[0] == "layers.0.0.weight" and rn[-2:] == ["layers.4.weight", "layers.4.bias"] and len(rn) == 30
+    assert sorted(model.density.state_dict().keys()) == ["beta", "mean", "scale"]
+    sd = model.vector_field_network.state_dict()
+    assert sd["layers.0.0.weight"].shape == (256, 39)
+    assert sd["layers.3.0.weight"].shape == (217, 256)      # narrowed before the skip layer
+    assert sd["layers.8.weight"].shape == (259, 256)
+    assert model.rendering_network.state_dict()["layers.0.0.weight"].shape == (256, 289)
+
+
+def test_parameter_list_has_the_reference_duplicates(model):
+    # 34 VF + 18 colour + 3 density + 34 VF again (vector_field_nerf.py:132-137)
+    assert len(model.parameters()) == 89
+    assert model.fine_vector_field_network is model.vector_field_network
+
+
+def test_arena_aliases_parameters_and_survives_to_and_load(model):
+    ar = model.vector_field_network.arena()
+    w = model.vector_field_network.layers[0][0].weight
+    assert w.data_ptr() == ar.flat.data_ptr() + 4 * ar.desc.w_off[0]
+    with torch.no_grad():
+        w[0, 0] = 123.0
+    assert ar.flat[ar.desc.w_off[0]].item() == 123.0
+    sd = {k: v.clone() for k, v in model.vector_field_network.state_dict().items()}
+    sd["layers.0.0.weight"][0, 0] = -7.0
+    model.vector_field_network.load_state_dict(sd)
+    ar = model.vector_field_network.arena()
+    assert ar.flat[ar.desc.w_off[0]].item() == -7.0
+    model.vector_field_network.double().float()              # storage replaced -> arena rebuilt
+    ar2 = model.vector_field_network.arena()
+    rm = model.vector_field_network.layers[0][1].running_mean
+    assert rm.data_ptr() == ar2.flat.data_ptr() + 4 * ar2.desc.mean_off[0]
+    assert ar2.flat[ar2.desc.w_off[0]].item() == -7.0
+    assert ar2.desc.in_dim[4] == 256 and ar2.desc.out_dim[3] == 217 and ar2.desc.n_layers == 9
+
+
+def test_no_cpu_fallback(model):
+    uv, pose, K = U.S.synthetic_rays(4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.render(pose, uv, K, 0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.vector_field_network(torch.zeros(4, 3))
+
+
+def test_reference_error_behaviour(model):
+    uv, pose, K = U.S.synthetic_rays(4)
+    with pytest.raises(UnboundLocalError):
+        model.render(pose, uv, K, 0, white=True)
+    with pytest.raises(ValueError):
+        VFNerfConfig(rendering="splat")
+    with pytest.raises(ValueError):
+        VFNerfConfig(cos_sim_weights_anneal="anneal_fine")
+    model.train()
+    try:
+        with pytest.raises(NotImplementedError):
+            model.vector_field_network(torch.zeros(4, 3))
+    finally:
+        model.eval()
+
+
+def test_draw_order_matches_reference_generator_consumption():
+    """U1 -> U2 -> U3 when perturbing; only U3 when deterministic (ray_sampler.py:138,292,297)."""
+    cs, fs = UniformSampler(8, 0.0, 1.0, deterministic=False), RangeFineSampler(6, 0.0, 1.0, False, 0.3, 100)
+    torch.manual_seed(7)
+    a1 = torch.rand([3, 8]); a2 = torch.rand([3, 6]); a3 = torch.rand((3, 6))
+    torch.manual_seed(7)
+    U1 = cs.draw(3); U2, U3 = fs.draw(3)
+    assert torch.equal(U1, a1) and torch.equal(U2, a2) and torch.equal(U3, a3)
+    cs.deterministic = fs.deterministic = True
+    torch.manual_seed(7)
+    b3 = torch.rand((3, 6))
+    torch.manual_seed(7)
+    assert cs.draw(3) is None
+    U2, U3 = fs.draw(3)
+    assert U2 is None and torch.equal(U3, b3)
+    fs.N_samples = 500
+    assert fs.n_fine() == 100                      # min(max_samples, N_samples), ray_sampler.py:276
+
+
+def test_sampler_attributes_are_read_at_call_time(model):
+    model.ray_sampler.near, model.ray_sampler.far = 0.5, 4.0
+    model.fine_sampler.N_samples = 70
+    cfg = model._render_cfg(16, False)
+    assert (cfg.near_, cfg.far_, cfg.n_fine, cfg.n_coarse) == (0.5, 4.0, 70, 64)
+    assert cfg.window == 11 and cfg.skip_layer == 4 and cfg.multires == 6 and cfg.multires_view == 4
+    model.ray_sampler.near, model.ray_sampler.far = 0.0, 6.0
+    model.fine_sampler.N_samples = 64

@@ -1,0 +1,91 @@
+"""CPU: the oracle restatement against the golden vectors generated from the live reference
+(tests/golden/make_golden.py).  This is what pins the oracle on machines without /root/reference."""
+import numpy as np
+import pytest
+import torch
+
+import vfn_testutil as U
+
+CASES = ["small_det", "small_perturb", "full_det", "full_perturb"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    case, z = U.load_golden(name)
+    st = U.case_state(case, z)
+    with torch.no_grad():
+        out = U.O.render(st["vf_net"], st["rendering_net"], st["density"], U.oracle_cfg(case),
+                         U.t(z, "uv"), U.t(z, "pose"), U.t(z, "K"), U.t(z, "t_vals"),
+                         U.t(z, "U1"), U.t(z, "U2"), U.t(z, "U3"))
+    # sample positions: bit-exact
+    assert torch.equal(out["z_vals"], U.t(z, "ref_z_vals"))
+    assert torch.equal(out["points"], U.t(z, "ref_points"))
+    # everything else: fp32 op-order noise only (tolerance 1e-4 abs, see make_golden.py)
+    for key, ref in (("normals", "ref_normals"), ("rgb", "ref_rgb"), ("depth", "ref_depth"),
+                     ("colors", "ref_colors"), ("rep_ray_dirs", "ref_ray_dirs")):
+        dev = (out[key] - U.t(z, ref)).abs().max().item()
+        assert dev <= 1e-4, (name, key, dev)
+    # the synthetic model must not be degenerate
+    assert (out["sigma"] > 0).float().mean().item() > 0.002
+    assert U.t(z, "ref_rgb").abs().max().item() > 0.05
+
+
+@pytest.mark.parametrize("name", ["small_det", "small_perturb"])
+def test_oracle_gradients_match_reference_golden(name):
+    case, z = U.load_golden(name)
+    st = U.case_state(case, z)
+    req = lambda sd: {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+                      for k, v in sd.items()}
+    vf, rn = req(st["vf_net"]), req(st["rendering_net"])
+    dn = {k: v.clone().requires_grad_(True) for k, v in st["density"].items()}
+    out = U.O.render(vf, rn, dn, U.oracle_cfg(case), U.t(z, "uv"), U.t(z, "pose"), U.t(z, "K"), U.t(z, "t_vals"),
+                     U.t(z, "U1"), U.t(z, "U2"), U.t(z, "U3"))
+    loss = U.O.vf_loss(out["rgb"], out["depth"], out["normals"].reshape(-1, 3), U.t(z, "rgb_gt"),
+                       U.t(z, "depth_gt"), U.LOSS_W, 0.5)
+    assert abs(loss.item() - float(z["ref_loss"])) < 1e-5
+    loss.backward()
+    for prefix, sd in (("g_vf.", vf), ("g_rn.", rn)):
+        for k, v in sd.items():
+            if isinstance(v, torch.Tensor) and v.requires_grad:
+                g = z[prefix + k]
+                rel = np.abs(v.grad.numpy() - g).max() / (np.abs(g).max() + 1e-12)
+                assert rel < 2e-3, (k, rel)
+    for k, v in dn.items():
+        g = float(z["g_density." + k])
+        assert abs(v.grad.item() - g) <= 2e-3 * abs(g) + 1e-7, (k, v.grad.item(), g)
+
+
+def test_fine_sampler_edge_cases():
+    """argmax ties / all-zero weights select the uniform z_add branch; rows are sorted; U3 is consumed
+    even when deterministic (ray_sampler.py:297)."""
+    R, Nc, Nf = 5, 16, 8
+    zc = torch.linspace(0, 6, Nc).repeat(R, 1)
+    w = torch.zeros(R, Nc)
+    w[1, 0] = 1.0          # argmax 0 -> z_add branch
+    w[2, 3] = 0.5
+    w[2, 9] = 0.5          # tie -> first index (3)
+    w[3, Nc - 1] = 1.0
+    w[4, 5] = 0.2
+    U3 = torch.rand(R, Nf)
+    z = U.O.fine_z_vals(zc, w, 0.0, 6.0, 0.3, Nf, False, None, U3)
+    assert z.shape == (R, Nc + Nf)
+    assert torch.all(z[:, 1:] >= z[:, :-1])
+    for r in (0, 1):       # all-zero row and argmax==0 row use U3*(far-near)+near
+        want = torch.sort(torch.cat([zc[r], U3[r] * 6.0 + 0.0]))[0]
+        assert torch.equal(z[r], want)
+    centre = zc[2, 3]
+    assert ((z[2] - centre).abs() <= 0.3 + 1e-6).sum().item() >= Nf
+
+
+def test_window_cosine_closed_form():
+    """c[j] for 7 <= j < N-1-7 is the mean over 5 back / 6 forward partners."""
+    torch.manual_seed(1)
+    n = torch.randn(3, 40, 3)
+    c = U.O.window_cosine(n, 11)
+    u = n / n.norm(dim=-1, keepdim=True)
+    j = 12
+    partners = list(range(j - 5, j)) + list(range(j + 1, j + 7))
+    want = sum((u[:, j] * u[:, k]).sum(-1) for k in partners) / 11.0
+    assert torch.allclose(c[:, j], want, atol=2e-6)
+    assert torch.allclose(c[:, 2], (u[:, 2] * u[:, 3]).sum(-1), atol=1e-6)
+    assert c.shape == (3, 39)

@@ -1,0 +1,519 @@
+// C-ABI entry points (include/vfnerf_b200.h) and the host-side orchestration of the render() path.
+//
+// Order of execution follows VectorFieldNerf.render() (vector_field_nerf.py:216-338):
+//   rays -> coarse z/points -> VF MLP (no grad) -> density -> weights -> fine z/points (merged, sorted)
+//   -> VF MLP on ALL merged points -> density -> weights -> colour MLP -> composite.
+// Everything is enqueued on the caller's stream; the only memory used is the caller's workspace.
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+
+#include "common.cuh"
+#include "mlp_tc.cuh"
+
+namespace vfn {
+
+static thread_local char g_err[1024] = "";
+long long g_launches = 0;
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace carving
+// ---------------------------------------------------------------------------------------------
+struct Carver {
+  char* base;
+  int64_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<char*>(p)) {}
+  float* f(int64_t n_floats) {
+    float* r = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += align_up(n_floats * (int64_t)sizeof(float), 256);
+    return r;
+  }
+};
+
+static int sum_out(const vfnerf_mlp_desc& d) {
+  int s = 0;
+  for (int l = 0; l < d.n_layers; ++l) s += d.out_dim[l];
+  return s;
+}
+static int max_dim(const vfnerf_mlp_desc& d) {
+  int m = 0;
+  for (int l = 0; l < d.n_layers; ++l) m = std::max(m, std::max(d.in_dim[l], d.out_dim[l]));
+  return m;
+}
+static int64_t max_wsize(const vfnerf_mlp_desc& d) {
+  int64_t m = 0;
+  for (int l = 0; l < d.n_layers; ++l) m = std::max<int64_t>(m, (int64_t)d.in_dim[l] * d.out_dim[l]);
+  return m;
+}
+
+// fp32-path buffers of one MLP evaluated on n points: the (post-activation) output of every hidden
+// layer l lives in act[l] with row stride in_dim[l+1] (so a skip layer finds its concatenated input
+// in place); `scale`/`shift` hold the folded BatchNorm affine of all layers.
+struct MlpBufs {
+  float* act[VFNERF_MAX_LAYERS];
+  float* scale;
+  float* shift;
+  int soff[VFNERF_MAX_LAYERS];
+};
+static void carve_mlp(Carver& c, const vfnerf_mlp_desc& d, int64_t n, MlpBufs& b) {
+  int so = 0;
+  for (int l = 0; l < d.n_layers; ++l) { b.soff[l] = so; so += d.out_dim[l]; }
+  b.scale = c.f(so);
+  b.shift = c.f(so);
+  for (int l = 0; l + 1 < d.n_layers; ++l) b.act[l] = c.f(n * d.in_dim[l + 1]);
+}
+
+struct BwdBufs {
+  float *dA, *dB, *G, *colsum;
+};
+static void carve_bwd(Carver& c, const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc& rn, int64_t n, BwdBufs& b) {
+  int w = std::max(max_dim(vf), max_dim(rn));
+  b.dA = c.f(n * w);
+  b.dB = c.f(n * w);
+  b.G = c.f(std::max(max_wsize(vf), max_wsize(rn)));
+  b.colsum = c.f(w);
+}
+
+static int validate_vf(const vfnerf_mlp_desc& vf, int multires, int skip_layer) {
+  const int E = 3 + 6 * multires;
+  VFN_REQUIRE(vf.n_layers >= 2 && vf.n_layers <= VFNERF_MAX_LAYERS, "VF net: n_layers=%d unsupported", vf.n_layers);
+  VFN_REQUIRE(vf.in_dim[0] == E, "VF net: in_dim[0]=%d but embedding width is %d", vf.in_dim[0], E);
+  for (int l = 1; l < vf.n_layers; ++l) {
+    int want = vf.out_dim[l - 1] + (l == skip_layer ? E : 0);
+    VFN_REQUIRE(vf.in_dim[l] == want, "VF net: in_dim[%d]=%d, expected %d", l, vf.in_dim[l], want);
+  }
+  VFN_REQUIRE(skip_layer != 0 && skip_layer < vf.n_layers, "VF net: skip_layer=%d unsupported", skip_layer);
+  VFN_REQUIRE(vf.out_dim[vf.n_layers - 1] >= 3, "VF net: output narrower than 3");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 MLP forward / backward (generic widths)
+// ---------------------------------------------------------------------------------------------
+static const float kSqrt2 = 1.41421354f;   // torch.sqrt(torch.tensor([2.]).float()), vector_field_network.py:193
+
+// VF MLP on n points.  x0 [n, in_dim[0]] = embedded input.  The last layer writes the first
+// n_out_cols columns of tanh(...) to out (row stride out_ld).
+static int vf_forward_fp32(const vfnerf_mlp_desc& d, const float* arena, const MlpBufs& b, int skip_layer,
+                           const float* x0, int64_t n, float* out, int64_t out_ld, int n_out_cols,
+                           cudaStream_t s) {
+  const float* x = x0;
+  int64_t x_ld = d.in_dim[0];
+  for (int l = 0; l < d.n_layers; ++l) {
+    const bool last = (l == d.n_layers - 1);
+    GemmArgs g{};
+    g.A = x; g.a_rs = x_ld; g.a_cs = 1; g.a_kscale = nullptr;
+    g.B = arena + d.w_off[l]; g.b_rs = 1; g.b_cs = d.in_dim[l];
+    g.M = n; g.K = d.in_dim[l];
+    g.scale = b.scale + b.soff[l]; g.shift = b.shift + b.soff[l];
+    g.split_k = 1; g.mask = nullptr; g.mask_rs = 0;
+    if (last) {
+      g.C = out; g.c_rs = out_ld; g.N = n_out_cols; g.act = ACT_TANH; g.post_div = 0.f;
+    } else {
+      g.C = b.act[l]; g.c_rs = d.in_dim[l + 1]; g.N = d.out_dim[l]; g.act = ACT_RELU;
+      g.post_div = (l + 1 == skip_layer) ? kSqrt2 : 0.f;
+    }
+    if (int e = launch_gemm(g, s)) return e;
+    x = b.act[l];
+    x_ld = last ? 0 : d.in_dim[l + 1];
+  }
+  return 0;
+}
+
+// writes the embedding of `points` to emb [n,E] and, if the net has a skip layer, emb/sqrt(2) into
+// the tail columns of the skip layer's input buffer.
+static int vf_embed_fp32(const vfnerf_mlp_desc& d, const MlpBufs& b, int multires, int skip_layer,
+                         const float* points, int64_t n, float* emb, cudaStream_t s) {
+  const int E = 3 + 6 * multires;
+  if (int e = launch_embed(points, 3, n, multires, 0.f, emb, E, s)) return e;
+  if (skip_layer > 0)
+    if (int e = launch_embed(points, 3, n, multires, kSqrt2, b.act[skip_layer - 1] + d.out_dim[skip_layer - 1],
+                             d.in_dim[skip_layer], s)) return e;
+  return 0;
+}
+
+// Generic MLP backward.  dY [n, out_dim[L-1]] (row stride dy_ld) is the gradient wrt the last layer's
+// pre-activation output.  x0 is the input of layer 0.  Hidden activations are ReLU; `skip_layer`'s
+// producer was divided by sqrt(2).  If d_in0 != NULL, the gradient wrt columns
+// [in0_col0, in0_col0 + in0_cols) of x0 is written there (row stride d_in0_ld).
+static int mlp_backward_fp32(const vfnerf_mlp_desc& d, const float* arena, const MlpBufs& b, int skip_layer,
+                             float bn_eps, const float* x0, int64_t x0_ld, int64_t n, const float* dY,
+                             int64_t dy_ld, const BwdBufs& w, float* grad_arena, int accumulate,
+                             float* d_in0, int64_t d_in0_ld, int in0_col0, int in0_cols, cudaStream_t s) {
+  const float* dy = dY;
+  int64_t ld = dy_ld;
+  float* pp[2] = {w.dA, w.dB};
+  int flip = 0;
+  const int split = (int)std::min<int64_t>(128, std::max<int64_t>(1, n / 1024));
+  for (int l = d.n_layers - 1; l >= 0; --l) {
+    const float* x = (l == 0) ? x0 : b.act[l - 1];
+    const int64_t x_ld = (l == 0) ? x0_ld : d.in_dim[l];
+    const int No = d.out_dim[l], Ki = d.in_dim[l];
+    if (int e = launch_colsum(dy, ld, n, No, nullptr, w.colsum, s)) return e;
+    VFN_CHECK_CUDA(cudaMemsetAsync(w.G, 0, sizeof(float) * (int64_t)No * Ki, s));
+    GemmArgs g{};
+    g.A = dy; g.a_rs = 1; g.a_cs = ld;            // A(m = out channel, k = point)
+    g.B = x; g.b_rs = x_ld; g.b_cs = 1;           // B(k = point, n = in channel)
+    g.C = w.G; g.c_rs = Ki; g.M = No; g.N = Ki; g.K = n; g.split_k = split;
+    if (int e = launch_gemm(g, s)) return e;
+    if (int e = launch_grad_finalize(d, l, arena, bn_eps, w.colsum, grad_arena, accumulate, w.G, s)) return e;
+    if (l > 0) {
+      // dX[:, :out_dim[l-1]] = ((dY * scale) W)[:, :out_dim[l-1]] masked by ReLU of the producer
+      GemmArgs h{};
+      h.A = dy; h.a_rs = ld; h.a_cs = 1; h.a_kscale = b.scale + b.soff[l];
+      h.B = arena + d.w_off[l]; h.b_rs = Ki; h.b_cs = 1;
+      h.C = pp[flip]; h.c_rs = d.out_dim[l - 1]; h.M = n; h.N = d.out_dim[l - 1]; h.K = No; h.split_k = 1;
+      h.post_div = (l == skip_layer) ? kSqrt2 : 0.f;
+      h.mask = b.act[l - 1]; h.mask_rs = d.in_dim[l];
+      if (int e = launch_gemm(h, s)) return e;
+      dy = pp[flip]; ld = d.out_dim[l - 1];
+      flip ^= 1;
+    } else if (d_in0) {
+      GemmArgs h{};
+      h.A = dy; h.a_rs = ld; h.a_cs = 1; h.a_kscale = b.scale + b.soff[0];
+      h.B = arena + d.w_off[0] + in0_col0; h.b_rs = Ki; h.b_cs = 1;
+      h.C = d_in0; h.c_rs = d_in0_ld; h.M = n; h.N = in0_cols; h.K = No; h.split_k = 1;
+      if (int e = launch_gemm(h, s)) return e;
+    }
+  }
+  return 0;
+}
+
+static int rn_forward_fp32(const vfnerf_mlp_desc& d, const float* arena, const MlpBufs& b, const float* cin,
+                           int64_t cin_ld, int64_t n, float* colors, cudaStream_t s) {
+  const float* x = cin;
+  int64_t x_ld = cin_ld;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const bool last = (l == d.n_layers - 1);
+    GemmArgs g{};
+    g.A = x; g.a_rs = x_ld; g.a_cs = 1;
+    g.B = arena + d.w_off[l]; g.b_rs = 1; g.b_cs = d.in_dim[l];
+    g.M = n; g.K = d.in_dim[l]; g.N = d.out_dim[l];
+    g.scale = b.scale + b.soff[l]; g.shift = b.shift + b.soff[l]; g.split_k = 1;
+    if (last) { g.C = colors; g.c_rs = d.out_dim[l]; g.act = ACT_SIGMOID; }
+    else { g.C = b.act[l]; g.c_rs = d.in_dim[l + 1]; g.act = ACT_RELU; }
+    if (int e = launch_gemm(g, s)) return e;
+    if (!last) { x = b.act[l]; x_ld = d.in_dim[l + 1]; }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// render plan
+// ---------------------------------------------------------------------------------------------
+struct RenderPlan {
+  int R, Nc, Nf, N, E, Ev, F, cin_ld;
+  int64_t P, Pc;
+  float *directions, *ray_dirs, *cam_loc, *z_c, *pts_c, *normals_c, *w_c, *emb, *cin, *weights;
+  MlpBufs vf, rn;
+  BwdBufs bw;
+  float* d_out;      // [P, 3+F]   gradient wrt the VF net's tanh outputs / pre-activations
+  float* d_colors;   // [P, 3]
+  TcPlan tc;         // tensor-core path buffers (mlp_tc.cu)
+  int64_t bytes;
+};
+
+static int make_plan(const vfnerf_render_cfg& cfg, const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc& rn,
+                     int keep, void* ws, RenderPlan& p) {
+  p.R = cfg.n_rays; p.Nc = cfg.n_coarse; p.Nf = cfg.n_fine; p.N = p.Nc + p.Nf;
+  p.P = (int64_t)p.R * p.N; p.Pc = (int64_t)p.R * p.Nc;
+  p.E = 3 + 6 * cfg.multires; p.Ev = 3 + 6 * cfg.multires_view;
+  p.F = vf.out_dim[vf.n_layers - 1] - 3;
+  p.cin_ld = 3 + p.Ev + 3 + p.F;
+  VFN_REQUIRE(p.R >= 0 && p.Nc >= 2, "render: n_rays=%d n_coarse=%d invalid", p.R, p.Nc);
+  VFN_REQUIRE(p.Nf >= 2, "render: n_fine=%d; the reference's render() needs fine sampling (n_importance > 0)", p.Nf);
+  VFN_REQUIRE(p.N <= VFNERF_MAX_SAMPLES, "render: %d samples per ray exceed %d", p.N, VFNERF_MAX_SAMPLES);
+  if (int e = validate_vf(vf, cfg.multires, cfg.skip_layer)) return e;
+  VFN_REQUIRE(rn.in_dim[0] == p.cin_ld, "colour net: in_dim[0]=%d, expected %d (mode 'idr')", rn.in_dim[0], p.cin_ld);
+  VFN_REQUIRE(rn.out_dim[rn.n_layers - 1] == 3, "colour net: output dim must be 3");
+  Carver c(ws);
+  p.directions = c.f(3 * p.R); p.ray_dirs = c.f(3 * p.R); p.cam_loc = c.f(3 * p.R);
+  p.z_c = c.f(p.Pc); p.pts_c = c.f(3 * p.Pc); p.normals_c = c.f(3 * p.Pc); p.w_c = c.f(p.Pc);
+  p.weights = c.f(p.P);
+  p.cin = c.f(p.P * p.cin_ld);
+  p.d_out = nullptr; p.d_colors = nullptr;
+  if (cfg.precision == VFNERF_PREC_FP32) {
+    p.emb = c.f(p.P * p.E);
+    carve_mlp(c, vf, p.P, p.vf);
+    carve_mlp(c, rn, p.P, p.rn);
+    if (keep) {
+      carve_bwd(c, vf, rn, p.P, p.bw);
+      p.d_out = c.f(p.P * (3 + p.F));
+      p.d_colors = c.f(3 * p.P);
+    }
+  } else {
+    if (int e = tc_carve(c.base, c.off, cfg, vf, rn, p.P, keep, p.tc)) return e;
+  }
+  p.bytes = c.off;
+  return 0;
+}
+
+static int check_precision(const vfnerf_render_cfg& cfg) {
+  VFN_REQUIRE(cfg.precision == VFNERF_PREC_FP32 || cfg.precision == VFNERF_PREC_BF16 ||
+              cfg.precision == VFNERF_PREC_BF16X3, "unknown precision %d", cfg.precision);
+  return 0;
+}
+
+}  // namespace vfn
+
+using namespace vfn;
+
+extern "C" {
+
+int vfnerf_abi_version(void) { return 1; }
+long long vfnerf_launch_count(void) { return g_launches; }
+const char* vfnerf_last_error(void) { return g_err; }
+
+int64_t vfnerf_render_workspace_bytes(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf,
+                                      const vfnerf_mlp_desc* rn, int keep_for_backward) {
+  if (!cfg || !vf || !rn) { set_error("null argument"); return -1; }
+  if (check_precision(*cfg)) return -1;
+  RenderPlan p;
+  if (make_plan(*cfg, *vf, *rn, keep_for_backward, nullptr, p)) return -1;
+  return p.bytes + 256;
+}
+
+int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, const float* vf_arena,
+                      const vfnerf_mlp_desc* rn, const float* rn_arena, const float* density_params,
+                      const float* uv, const float* pose, const float* intrinsics, const float* t_vals,
+                      const float* U1, const float* U2, const float* U3, const float* z_override,
+                      const vfnerf_render_out* out, void* workspace, int64_t workspace_bytes,
+                      int keep_for_backward, void* stream) {
+  VFN_REQUIRE(cfg && vf && rn && out, "render_fwd: null argument");
+  if (int e = check_precision(*cfg)) return e;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  RenderPlan p;
+  if (int e = make_plan(*cfg, *vf, *rn, keep_for_backward, workspace, p)) return e;
+  VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "render_fwd: workspace %lld B < required %lld B",
+              (long long)workspace_bytes, (long long)p.bytes);
+  VFN_REQUIRE(out->points && out->normals && out->rgb && out->depth && out->z_vals && out->colors,
+              "render_fwd: required output pointer is null");
+  if (p.R == 0) return 0;
+  float* weights = out->weights ? out->weights : p.weights;
+  float* z_c = out->z_coarse ? out->z_coarse : p.z_c;
+  float* w_c = out->weights_coarse ? out->weights_coarse : p.w_c;
+
+  if (int e = launch_ray_geometry(p.R, cfg->pose_is_quat, uv, pose, intrinsics, p.directions, p.ray_dirs, p.cam_loc, s)) return e;
+  if (int e = launch_coarse_sample(p.R, p.Nc, cfg->near_, cfg->far_, cfg->perturb, t_vals, U1, p.directions,
+                                   p.cam_loc, z_c, p.pts_c, s)) return e;
+
+  if (cfg->precision == VFNERF_PREC_FP32) {
+    if (int e = launch_fold_bn(*vf, vf_arena, cfg->bn_eps, p.vf.scale, p.vf.shift, s)) return e;
+    if (int e = launch_fold_bn(*rn, rn_arena, cfg->bn_eps, p.rn.scale, p.rn.shift, s)) return e;
+    // ---- coarse pass (vector_field_nerf.py:252-272), only the 3 vector outputs are needed
+    if (!z_override) {
+      if (int e = vf_embed_fp32(*vf, p.vf, cfg->multires, cfg->skip_layer, p.pts_c, p.Pc, p.emb, s)) return e;
+      if (int e = vf_forward_fp32(*vf, vf_arena, p.vf, cfg->skip_layer, p.emb, p.Pc, p.normals_c, 3, 3, s)) return e;
+    }
+  } else {
+    if (int e = tc_prepare(*cfg, *vf, vf_arena, *rn, rn_arena, p.tc, s)) return e;
+    if (!z_override)
+      if (int e = tc_vf_forward(*cfg, p.tc, p.pts_c, p.Pc, p.normals_c, 3, 3, nullptr, 0, s)) return e;
+  }
+  if (!z_override) {
+    if (int e = launch_density_weights(*cfg, p.R, p.Nc, density_params, p.normals_c, 3, p.ray_dirs, z_c,
+                                       nullptr, nullptr, w_c, s)) return e;
+  }
+  // ---- fine sampling: merged, sorted z values and points (vector_field_nerf.py:284-287)
+  if (int e = launch_fine_sample(p.R, p.Nc, p.Nf, cfg->near_, cfg->far_, cfg->fine_range, cfg->perturb, z_c, w_c,
+                                 U2, U3, z_override, p.directions, p.cam_loc, out->z_vals, out->points, s)) return e;
+  // ---- merged pass
+  if (int e = launch_color_input_head(out->points, p.ray_dirs, p.R, p.N, cfg->multires_view, p.cin, p.cin_ld,
+                                      out->ray_dirs_rep, s)) return e;
+  float* vf_out = p.cin + 3 + p.Ev;      // [v(3), feat(F)] written in place into the colour-net input
+  if (cfg->precision == VFNERF_PREC_FP32) {
+    if (int e = vf_embed_fp32(*vf, p.vf, cfg->multires, cfg->skip_layer, out->points, p.P, p.emb, s)) return e;
+    if (int e = vf_forward_fp32(*vf, vf_arena, p.vf, cfg->skip_layer, p.emb, p.P, vf_out, p.cin_ld, 3 + p.F, s)) return e;
+  } else {
+    if (int e = tc_vf_forward(*cfg, p.tc, out->points, p.P, vf_out, p.cin_ld, 3 + p.F, nullptr, keep_for_backward, s)) return e;
+  }
+  if (int e = launch_copy_cols(vf_out, p.cin_ld, out->normals, 3, p.P, 3, s)) return e;
+  if (int e = launch_density_weights(*cfg, p.R, p.N, density_params, vf_out, p.cin_ld, p.ray_dirs, out->z_vals,
+                                     nullptr, nullptr, weights, s)) return e;
+  if (cfg->precision == VFNERF_PREC_FP32) {
+    if (int e = rn_forward_fp32(*rn, rn_arena, p.rn, p.cin, p.cin_ld, p.P, out->colors, s)) return e;
+  } else {
+    if (int e = tc_rn_forward(*cfg, p.tc, p.cin, p.cin_ld, p.P, out->colors, keep_for_backward, s)) return e;
+  }
+  if (int e = launch_composite(p.R, p.N, weights, out->colors, out->z_vals, out->rgb, out->depth, s)) return e;
+  return 0;
+}
+
+int vfnerf_render_bwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, const float* vf_arena,
+                      const vfnerf_mlp_desc* rn, const float* rn_arena, const float* density_params,
+                      const vfnerf_render_out* out, const float* d_rgb, const float* d_depth,
+                      const float* d_normals, const float* d_colors, float* vf_grad_arena,
+                      float* rn_grad_arena, float* d_density, void* workspace, int64_t workspace_bytes,
+                      void* stream) {
+  VFN_REQUIRE(cfg && vf && rn && out && d_rgb && d_depth && vf_grad_arena && rn_grad_arena && d_density,
+              "render_bwd: null argument");
+  if (int e = check_precision(*cfg)) return e;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  RenderPlan p;
+  if (int e = make_plan(*cfg, *vf, *rn, 1, workspace, p)) return e;
+  VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "render_bwd: workspace %lld B < required %lld B",
+              (long long)workspace_bytes, (long long)p.bytes);
+  VFN_CHECK_CUDA(cudaMemsetAsync(d_density, 0, 3 * sizeof(float), s));
+  VFN_CHECK_CUDA(cudaMemsetAsync(vf_grad_arena, 0, sizeof(float) * vf->arena_floats, s));
+  VFN_CHECK_CUDA(cudaMemsetAsync(rn_grad_arena, 0, sizeof(float) * rn->arena_floats, s));
+  if (p.R == 0) return 0;
+  VFN_REQUIRE(cfg->precision == VFNERF_PREC_FP32, "render_bwd: only the fp32 path has a backward in this build");
+  const float* vf_out = p.cin + 3 + p.Ev;
+  const int Dv = 3 + p.F;
+  // a9..a4 fused: d_colors, dL/dv (into columns 0..2 of d_out), density parameter grads
+  if (int e = launch_render_tail_bwd(*cfg, p.R, p.N, density_params, vf_out, p.cin_ld, p.ray_dirs, out->z_vals,
+                                     out->colors, d_rgb, d_depth, d_normals, d_colors, p.d_colors, p.d_out, Dv,
+                                     d_density, s)) return e;
+  // colour net: sigmoid', then layers; only the feature columns of its input carry grad
+  // (points / view dirs have none, normals are detached: rendering_network.py:76-77)
+  if (int e = launch_act_bwd(out->colors, 3, p.d_colors, 3, p.P, 3, ACT_SIGMOID, p.d_colors, 3, s)) return e;
+  if (int e = mlp_backward_fp32(*rn, rn_arena, p.rn, -1, cfg->bn_eps, p.cin, p.cin_ld, p.P, p.d_colors, 3, p.bw,
+                                rn_grad_arena, 0, p.d_out + 3, Dv, 3 + p.Ev + 3, p.F, s)) return e;
+  // VF net: tanh' on [v, feat], then layers
+  if (int e = launch_act_bwd(vf_out, p.cin_ld, p.d_out, Dv, p.P, Dv, ACT_TANH, p.d_out, Dv, s)) return e;
+  if (int e = mlp_backward_fp32(*vf, vf_arena, p.vf, cfg->skip_layer, cfg->bn_eps, p.emb, p.E, p.P, p.d_out, Dv,
+                                p.bw, vf_grad_arena, 0, nullptr, 0, 0, 0, s)) return e;
+  return 0;
+}
+
+// ---- VF-only query -----------------------------------------------------------------------------
+struct VfPlan {
+  float* emb;
+  float* pts;     // grid query only
+  MlpBufs b;
+  BwdBufs bw;
+  float* d_pre;
+  int64_t bytes;
+};
+static void make_vf_plan(const vfnerf_mlp_desc& vf, int64_t n, int multires, int keep, int grid, void* ws, VfPlan& p) {
+  Carver c(ws);
+  p.emb = c.f(n * (3 + 6 * multires));
+  p.pts = grid ? c.f(3 * n) : nullptr;
+  carve_mlp(c, vf, n, p.b);
+  if (keep) {
+    vfnerf_mlp_desc none{};
+    carve_bwd(c, vf, none, n, p.bw);
+    p.d_pre = c.f(n * vf.out_dim[vf.n_layers - 1]);
+  }
+  p.bytes = c.off;
+}
+
+int64_t vfnerf_vf_workspace_bytes(const vfnerf_mlp_desc* vf, int64_t n_points, int multires,
+                                  int keep_for_backward, int precision) {
+  if (!vf) { set_error("null argument"); return -1; }
+  if (precision != VFNERF_PREC_FP32) return tc_vf_workspace_bytes(*vf, n_points, multires, keep_for_backward, precision);
+  VfPlan p;
+  make_vf_plan(*vf, n_points, multires, keep_for_backward, 1, nullptr, p);
+  return p.bytes + 256;
+}
+
+int vfnerf_vf_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires, int skip_layer, float bn_eps,
+                  int precision, const float* points, int64_t n_points, float* out, int64_t out_ld,
+                  int n_out_cols, void* workspace, int64_t workspace_bytes, int keep_for_backward,
+                  void* stream) {
+  VFN_REQUIRE(vf && vf_arena && out, "vf_fwd: null argument");
+  if (int e = validate_vf(*vf, multires, skip_layer)) return e;
+  VFN_REQUIRE(n_out_cols >= 1 && n_out_cols <= vf->out_dim[vf->n_layers - 1], "vf_fwd: n_out_cols=%d invalid", n_out_cols);
+  if (n_points == 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (precision != VFNERF_PREC_FP32)
+    return tc_vf_query(*vf, vf_arena, multires, skip_layer, bn_eps, precision, points, n_points, out, out_ld,
+                       n_out_cols, workspace, workspace_bytes, s);
+  VfPlan p;
+  make_vf_plan(*vf, n_points, multires, keep_for_backward, 1, workspace, p);
+  VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "vf_fwd: workspace %lld B < required %lld B",
+              (long long)workspace_bytes, (long long)p.bytes);
+  if (int e = launch_fold_bn(*vf, vf_arena, bn_eps, p.b.scale, p.b.shift, s)) return e;
+  if (int e = vf_embed_fp32(*vf, p.b, multires, skip_layer, points, n_points, p.emb, s)) return e;
+  return vf_forward_fp32(*vf, vf_arena, p.b, skip_layer, p.emb, n_points, out, out_ld, n_out_cols, s);
+}
+
+int vfnerf_vf_bwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires, int skip_layer, float bn_eps,
+                  int precision, int64_t n_points, const float* out, int64_t out_ld, const float* d_out,
+                  int64_t d_ld, int n_out_cols, float* vf_grad_arena, int accumulate, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+  VFN_REQUIRE(vf && vf_arena && out && d_out && vf_grad_arena, "vf_bwd: null argument");
+  VFN_REQUIRE(precision == VFNERF_PREC_FP32, "vf_bwd: only the fp32 path has a backward in this build");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int Do = vf->out_dim[vf->n_layers - 1];
+  VFN_REQUIRE(n_out_cols >= 1 && n_out_cols <= Do, "vf_bwd: n_out_cols invalid");
+  VfPlan p;
+  make_vf_plan(*vf, n_points, multires, 1, 1, workspace, p);
+  VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "vf_bwd: workspace too small");
+  if (!accumulate) VFN_CHECK_CUDA(cudaMemsetAsync(vf_grad_arena, 0, sizeof(float) * vf->arena_floats, s));
+  if (n_points == 0) return 0;
+  // d_pre = d_out * (1 - out^2) on the first n_out_cols columns, zero elsewhere
+  if (n_out_cols < Do) VFN_CHECK_CUDA(cudaMemsetAsync(p.d_pre, 0, sizeof(float) * n_points * Do, s));
+  if (int e = launch_act_bwd(out, out_ld, d_out, d_ld, n_points, n_out_cols, ACT_TANH, p.d_pre, Do, s)) return e;
+  return mlp_backward_fp32(*vf, vf_arena, p.b, skip_layer, bn_eps, p.emb, 3 + 6 * multires, n_points, p.d_pre, Do,
+                           p.bw, vf_grad_arena, 1, nullptr, 0, 0, 0, s);
+}
+
+int vfnerf_vf_grid_query(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires, int skip_layer,
+                         float bn_eps, int precision, int res, int64_t i0, int64_t n_points,
+                         const float* origin3_host, const float* translation3_host,
+                         const float* centroid3_host, float voxel, float* out, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+  VFN_REQUIRE(vf && vf_arena && out && origin3_host && translation3_host && centroid3_host, "grid_query: null argument");
+  if (int e = validate_vf(*vf, multires, skip_layer)) return e;
+  if (n_points == 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GridSpec gs;
+  for (int c = 0; c < 3; ++c) { gs.origin[c] = origin3_host[c]; gs.translation[c] = translation3_host[c]; gs.centroid[c] = centroid3_host[c]; }
+  gs.voxel = voxel;
+  if (precision != VFNERF_PREC_FP32)
+    return tc_vf_grid_query(*vf, vf_arena, multires, skip_layer, bn_eps, precision, res, i0, n_points, gs, out,
+                            workspace, workspace_bytes, s);
+  VfPlan p;
+  make_vf_plan(*vf, n_points, multires, 0, 1, workspace, p);
+  VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "grid_query: workspace %lld B < required %lld B",
+              (long long)workspace_bytes, (long long)p.bytes);
+  if (int e = launch_grid_points(res, i0, n_points, gs, p.pts, s)) return e;
+  if (int e = launch_fold_bn(*vf, vf_arena, bn_eps, p.b.scale, p.b.shift, s)) return e;
+  if (int e = vf_embed_fp32(*vf, p.b, multires, skip_layer, p.pts, n_points, p.emb, s)) return e;
+  return vf_forward_fp32(*vf, vf_arena, p.b, skip_layer, p.emb, n_points, out, 3, 3, s);
+}
+
+// ---- stage entry points ----------------------------------------------------------------------
+int vfnerf_ray_geometry(int n_rays, int pose_is_quat, const float* uv, const float* pose,
+                        const float* intrinsics, float* directions, float* ray_dirs, float* cam_loc,
+                        void* stream) {
+  return launch_ray_geometry(n_rays, pose_is_quat, uv, pose, intrinsics, directions, ray_dirs, cam_loc,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vfnerf_coarse_sample(int n_rays, int n_coarse, double near_, double far_, int perturb,
+                         const float* t_vals, const float* U1, const float* directions,
+                         const float* cam_loc, float* z, float* points, void* stream) {
+  return launch_coarse_sample(n_rays, n_coarse, near_, far_, perturb, t_vals, U1, directions, cam_loc, z, points,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vfnerf_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, double far_, double fine_range,
+                       int perturb, const float* z_coarse, const float* w_coarse, const float* U2,
+                       const float* U3, const float* directions, const float* cam_loc, float* z,
+                       float* points, void* stream) {
+  return launch_fine_sample(n_rays, n_coarse, n_fine, near_, far_, fine_range, perturb, z_coarse, w_coarse, U2, U3,
+                            nullptr, directions, cam_loc, z, points, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vfnerf_density_weights(const vfnerf_render_cfg* cfg, int n_samples, const float* density_params,
+                           const float* normals, int64_t normals_ld, const float* ray_dirs, const float* z,
+                           float* cosw, float* sigma, float* weights, void* stream) {
+  VFN_REQUIRE(cfg, "density_weights: null cfg");
+  return launch_density_weights(*cfg, cfg->n_rays, n_samples, density_params, normals, normals_ld, ray_dirs, z,
+                                cosw, sigma, weights, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vfnerf_composite(int n_rays, int n_samples, const float* weights, const float* colors, const float* z,
+                     float* rgb, float* depth, void* stream) {
+  return launch_composite(n_rays, n_samples, weights, colors, z, rgb, depth, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+// Density, transmittance and compositing and their fused backward.
+//
+// One warp owns one ray: N <= 256 samples, lane l holds samples l, l+32, ... (coalesced row access).
+// Unit VF vectors are staged in the warp's shared-memory slice so the 11-tap windowed cosine is a
+// shared-memory stencil; transmittance is a chunked warp scan; all sums are warp shuffles.
+// HBM-bound: forward reads 12N+4N bytes/ray and writes 4N..12N; nothing is re-read.
+#include "common.cuh"
+
+namespace vfn {
+
+constexpr int kRayWarps = 4;
+constexpr int kMaxPerLane = VFNERF_MAX_SAMPLES / 32;  // 8
+
+struct Laplace {
+  float beta, scale, mean;   // effective (clamped) parameters
+  float L0, Lp0, Lb0;        // cdf, d/dx and d/dbeta at the cutoff x0 = -0.5
+  __device__ __forceinline__ float cdf(float x) const {
+    float d = x - mean;
+    float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+    return scale * (0.5f + 0.5f * sg * (1.f - expf(-fabsf(d) / beta)));
+  }
+  __device__ __forceinline__ float dcdf_dx(float x) const {   // = -dcdf/dmean
+    return scale * 0.5f * expf(-fabsf(x - mean) / beta) / beta;
+  }
+  __device__ __forceinline__ float dcdf_dbeta(float x) const {
+    float d = x - mean, a = fabsf(d);
+    float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+    return scale * 0.5f * sg * (-expf(-a / beta) * a / (beta * beta));
+  }
+};
+
+// get_beta / get_scale / get_mean, density_functions.py:169-204; the cutoff is ALWAYS -0.5 because
+// Density.forward drops its cutoff argument (density_functions.py:20-34).
+__device__ __forceinline__ Laplace load_laplace(const vfnerf_render_cfg& cfg, const float* __restrict__ dp) {
+  Laplace l;
+  l.beta = fminf(fmaxf(dp[0], cfg.beta_lo), cfg.beta_hi);
+  l.scale = fmaxf(fabsf(dp[1]), cfg.scale_min);
+  l.mean = fminf(fmaxf(dp[2], cfg.mean_lo), cfg.mean_hi);
+  l.L0 = l.cdf(-0.5f);
+  l.Lp0 = l.dcdf_dx(-0.5f);
+  l.Lb0 = l.dcdf_dbeta(-0.5f);
+  return l;
+}
+
+struct Window {
+  int start, nb, lo, hi;     // band of centre indices j in [lo, hi) that get the full window
+  float coef;                // (1/W) / sum_i |1/W|, as the reference forms it in fp32
+};
+__device__ __forceinline__ Window make_window(int W, int N) {
+  Window w;
+  w.start = (W + 1) / 2 + 1;         // int((W + 1) / 2 + 1), functions.py:52
+  w.nb = w.start - 2;                // partners on each side besides j+1, functions.py:65
+  const int L = N - 1;
+  w.lo = w.start;
+  w.hi = L - w.start;
+  if (w.hi <= w.lo) { w.lo = 0; w.hi = 0; }
+  float wu = 1.0f / (float)W, nrm = 0.f;
+  for (int i = 0; i < W; ++i) nrm = __fadd_rn(nrm, wu);
+  w.coef = wu / nrm;
+  return w;
+}
+
+// Loads the N vectors of ray r, stores unit vectors (x / max(|x|, 1e-8), torch 2.x cosine_similarity)
+// and 1/max(|x|,1e-8) into shared memory.
+__device__ __forceinline__ void stage_unit_vectors(const float* __restrict__ nrm_row, int64_t ld, int N,
+                                                   int lane, float* su, float* sinv) {
+  for (int j = lane; j < N; j += 32) {
+    const float* p = nrm_row + (int64_t)j * ld;
+    float x = p[0], y = p[1], z = p[2];
+    float n = fmaxf(sqrtf(x * x + y * y + z * z), 1e-8f);
+    su[3 * j] = x / n; su[3 * j + 1] = y / n; su[3 * j + 2] = z / n;
+    if (sinv) sinv[j] = 1.f / n;
+  }
+}
+
+__device__ __forceinline__ float dot3(const float* a, const float* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+
+// windowed cosine c_j (functions.py:41-72 with the uniform weights of vector_field_nerf.py:453)
+__device__ __forceinline__ float window_cos(const float* su, int j, const Window& w) {
+  float base = dot3(su + 3 * j, su + 3 * (j + 1));
+  if (j < w.lo || j >= w.hi) return base;
+  float c = base * w.coef;
+  for (int i = 1; i <= w.nb; ++i) {
+    c = c + dot3(su + 3 * j, su + 3 * (j + 1 + i)) * w.coef;
+    c = c + dot3(su + 3 * j, su + 3 * (j - i)) * w.coef;
+  }
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: c, sigma, weights
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRayWarps * 32)
+density_weights_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __restrict__ dparams,
+                       const float* __restrict__ normals, int64_t ld, const float* __restrict__ ray_dirs,
+                       const float* __restrict__ z, float* __restrict__ cosw, float* __restrict__ sigma_out,
+                       float* __restrict__ weights) {
+  __shared__ float s_u[kRayWarps][3 * VFNERF_MAX_SAMPLES];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * kRayWarps + wid;
+  if (r >= n_rays) return;
+  float* su = s_u[wid];
+  const Laplace lap = load_laplace(cfg, dparams);
+  const Window win = make_window(cfg.window, N);
+  stage_unit_vectors(normals + (int64_t)r * N * ld, ld, N, lane, su, nullptr);
+  float d[3] = {ray_dirs[3 * (int64_t)r], ray_dirs[3 * (int64_t)r + 1], ray_dirs[3 * (int64_t)r + 2]};
+  {
+    float n = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-8f);
+    d[0] /= n; d[1] /= n; d[2] /= n;
+  }
+  __syncwarp();
+  const float* zr = z + (int64_t)r * N;
+  float carry = 0.f, wsum = 0.f;
+  float what[kMaxPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int j = lane + 32 * i;
+    float E = 0.f, sg = 0.f;
+    if (j < N - 1) {
+      float c = window_cos(su, j, win);
+      float cdir = dot3(su + 3 * j, d);
+      sg = fmaxf(lap.cdf(-c) - lap.L0, 0.f);
+      if (cdir < cfg.dir_to_normal_th && c < 0.f) sg = 0.f;
+      E = (zr[j + 1] - zr[j]) * sg;
+      if (cosw) cosw[(int64_t)r * (N - 1) + j] = c;
+    }
+    if (j < N && sigma_out) sigma_out[(int64_t)r * N + j] = sg;
+    // exclusive prefix of the free energy over this 32-sample chunk, plus the carry of earlier chunks
+    float inc = warp_inclusive_scan(E, lane);
+    float T = expf(-(carry + inc - E));
+    float a = 1.f - expf(-E);
+    what[i] = (j < N) ? a * T : 0.f;
+    wsum += what[i];
+    carry += __shfl_sync(kFull, inc, 31);
+  }
+  wsum = warp_sum(wsum);
+  const float inv = cfg.normalize ? 1.f / (wsum + 1e-5f) : 1.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int j = lane + 32 * i;
+    if (j < N) weights[(int64_t)r * N + j] = what[i] * inv;
+  }
+}
+
+int launch_density_weights(const vfnerf_render_cfg& cfg, int n_rays, int n_samples,
+                           const float* density_params, const float* normals, int64_t normals_ld,
+                           const float* ray_dirs, const float* z, float* cosw, float* sigma,
+                           float* weights, cudaStream_t s) {
+  if (n_rays <= 0) return 0;
+  VFN_REQUIRE(n_samples >= 2 && n_samples <= VFNERF_MAX_SAMPLES, "density_weights: n_samples=%d out of [2,%d]",
+              n_samples, VFNERF_MAX_SAMPLES);
+  VFN_REQUIRE(cfg.window >= 1 && cfg.window <= 63, "density_weights: window=%d unsupported", cfg.window);
+  density_weights_kernel<<<(n_rays + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, s>>>(
+      cfg, n_rays, n_samples, density_params, normals, normals_ld, ray_dirs, z, cosw, sigma, weights);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9: rgb = sum_j w_j c_j, depth = sum_j w_j z_j
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRayWarps * 32)
+composite_kernel(int n_rays, int N, const float* __restrict__ w, const float* __restrict__ colors,
+                 const float* __restrict__ z, float* __restrict__ rgb, float* __restrict__ depth) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * kRayWarps + wid;
+  if (r >= n_rays) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, ad = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    int64_t idx = (int64_t)r * N + j;
+    float wj = w[idx];
+    a0 += wj * colors[3 * idx]; a1 += wj * colors[3 * idx + 1]; a2 += wj * colors[3 * idx + 2];
+    ad += wj * z[idx];
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); ad = warp_sum(ad);
+  if (lane == 0) {
+    rgb[3 * (int64_t)r] = a0; rgb[3 * (int64_t)r + 1] = a1; rgb[3 * (int64_t)r + 2] = a2;
+    depth[r] = ad;
+  }
+}
+
+int launch_composite(int n_rays, int n_samples, const float* weights, const float* colors,
+                     const float* z, float* rgb, float* depth, cudaStream_t s) {
+  if (n_rays <= 0) return 0;
+  composite_kernel<<<(n_rays + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, s>>>(
+      n_rays, n_samples, weights, colors, z, rgb, depth);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused backward of rows a9 -> a6 -> a5 -> a4.  Recomputes the forward quantities from the VF
+// vectors (cheaper than stashing c / sigma / T) and produces
+//   d_colors [R*N,3] = w_j * d_rgb (+ upstream),   d_normals [R,N,ld] = dL/dv_j (+ upstream),
+//   d_density[3] += d(beta, scale, mean)   (atomicAdd of one value per ray; caller zeroes it).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRayWarps * 32)
+render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __restrict__ dparams,
+                       const float* __restrict__ normals, int64_t ld, const float* __restrict__ ray_dirs,
+                       const float* __restrict__ z, const float* __restrict__ colors,
+                       const float* __restrict__ d_rgb, const float* __restrict__ d_depth,
+                       const float* __restrict__ d_normals_up, const float* __restrict__ d_colors_up,
+                       float* __restrict__ d_colors, float* __restrict__ d_normals, int64_t dn_ld,
+                       float* __restrict__ d_density) {
+  __shared__ float s_u[kRayWarps][3 * VFNERF_MAX_SAMPLES];
+  __shared__ float s_inv[kRayWarps][VFNERF_MAX_SAMPLES];
+  __shared__ float s_dc[kRayWarps][VFNERF_MAX_SAMPLES];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * kRayWarps + wid;
+  if (r >= n_rays) return;
+  float* su = s_u[wid];
+  float* sinv = s_inv[wid];
+  float* sdc = s_dc[wid];
+  const Laplace lap = load_laplace(cfg, dparams);
+  const Window win = make_window(cfg.window, N);
+  stage_unit_vectors(normals + (int64_t)r * N * ld, ld, N, lane, su, sinv);
+  float d[3] = {ray_dirs[3 * (int64_t)r], ray_dirs[3 * (int64_t)r + 1], ray_dirs[3 * (int64_t)r + 2]};
+  {
+    float n = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-8f);
+    d[0] /= n; d[1] /= n; d[2] /= n;
+  }
+  __syncwarp();
+  const float* zr = z + (int64_t)r * N;
+  const float g0 = d_rgb[3 * (int64_t)r], g1 = d_rgb[3 * (int64_t)r + 1], g2 = d_rgb[3 * (int64_t)r + 2];
+  const float gd = d_depth[r];
+
+  // ---- forward recompute
+  float cj[kMaxPerLane], E[kMaxPerLane], T[kMaxPerLane], what[kMaxPerLane], dw[kMaxPerLane], delta[kMaxPerLane];
+  bool active[kMaxPerLane];
+  float carry = 0.f, wsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int j = lane + 32 * i;
+    float e = 0.f, c = 1.f, dl = 0.f;
+    bool act = false;
+    if (j < N - 1) {
+      c = window_cos(su, j, win);
+      float cdir = dot3(su + 3 * j, d);
+      float sg = lap.cdf(-c) - lap.L0;
+      act = sg > 0.f && !(cdir < cfg.dir_to_normal_th && c < 0.f);
+      sg = act ? sg : 0.f;
+      dl = zr[j + 1] - zr[j];
+      e = dl * sg;
+    }
+    cj[i] = c; E[i] = e; active[i] = act; delta[i] = dl;
+    float inc = warp_inclusive_scan(e, lane);
+    T[i] = expf(-(carry + inc - e));
+    what[i] = (j < N) ? (1.f - expf(-e)) * T[i] : 0.f;
+    wsum += what[i];
+    carry += __shfl_sync(kFull, inc, 31);
+  }
+  wsum = warp_sum(wsum);
+  const float inv = cfg.normalize ? 1.f / (wsum + 1e-5f) : 1.f;
+
+  // ---- composite backward: d_colors and dL/dw
+  float dot_dw_w = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int j = lane + 32 * i;
+    dw[i] = 0.f;
+    if (j < N) {
+      const int64_t idx = (int64_t)r * N + j;
+      const float w = what[i] * inv;
+      const float c0 = colors[3 * idx], c1 = colors[3 * idx + 1], c2 = colors[3 * idx + 2];
+      dw[i] = g0 * c0 + g1 * c1 + g2 * c2 + gd * zr[j];
+      float o0 = w * g0, o1 = w * g1, o2 = w * g2;
+      if (d_colors_up) { o0 += d_colors_up[3 * idx]; o1 += d_colors_up[3 * idx + 1]; o2 += d_colors_up[3 * idx + 2]; }
+      d_colors[3 * idx] = o0; d_colors[3 * idx + 1] = o1; d_colors[3 * idx + 2] = o2;
+      dot_dw_w += dw[i] * w;
+    }
+  }
+  dot_dw_w = warp_sum(dot_dw_w);
+  // w = what / (S + eps)  =>  d what_j = (dw_j - sum_i dw_i w_i) / (S + eps)
+  float q[kMaxPerLane], qtot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int j = lane + 32 * i;
+    float dwh = 0.f;
+    if (j < N) dwh = cfg.normalize ? (dw[i] - dot_dw_w) * inv : dw[i];
+    dw[i] = dwh;                 // now d/d what_j
+    q[i] = dwh * what[i];
+    qtot += q[i];
+  }
+  qtot = warp_sum(qtot);
+  // dE_j = d what_j * T_j * exp(-E_j) - sum_{i>j} d what_i * what_i
+  float ds_acc = 0.f, dm_acc = 0.f, db_acc = 0.f, qcarry = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int j = lane + 32 * i;
+    float inc = warp_inclusive_scan(q[i], lane);
+    float suffix = qtot - (qcarry + inc);            // sum over i > j
+    qcarry += __shfl_sync(kFull, inc, 31);
+    float dc = 0.f;
+    if (j < N - 1 && active[i]) {
+      float dE = dw[i] * T[i] * expf(-E[i]) - suffix;
+      float dsig = delta[i] * dE;
+      float x = -cj[i];
+      float lp = lap.dcdf_dx(x);
+      dc = -dsig * lp;
+      ds_acc += dsig * (lap.cdf(x) - lap.L0) / lap.scale;
+      dm_acc += dsig * (lap.Lp0 - lp);
+      db_acc += dsig * (lap.dcdf_dbeta(x) - lap.Lb0);
+    }
+    if (j < N) sdc[j] = dc;
+  }
+  __syncwarp();
+
+  // ---- windowed-cosine backward (gather form): for sample k collect every pair (k,m) in which
+  // k is the centre or the partner.  d cos(a,b)/da = (b^ - cos * a^)/|a|.
+  const int reach = win.nb + 1;
+  for (int k = lane; k < N; k += 32) {
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    const float* uk = su + 3 * k;
+    const bool k_band = (k >= win.lo && k < win.hi);
+    for (int m = max(0, k - reach); m <= min(N - 1, k + reach); ++m) {
+      if (m == k) continue;
+      float om = 0.f;
+      if (k < N - 1) {                                  // k is a centre
+        if (k_band) { if ((m - k >= 1 && m - k <= win.nb + 1) || (k - m >= 1 && k - m <= win.nb)) om += sdc[k] * win.coef; }
+        else if (m == k + 1) om += sdc[k];
+      }
+      if (m < N - 1) {                                  // m is a centre, k its partner
+        const bool m_band = (m >= win.lo && m < win.hi);
+        if (m_band) { if ((k - m >= 1 && k - m <= win.nb + 1) || (m - k >= 1 && m - k <= win.nb)) om += sdc[m] * win.coef; }
+        else if (k == m + 1) om += sdc[m];
+      }
+      if (om != 0.f) {
+        const float* um = su + 3 * m;
+        float cs = dot3(uk, um);
+        gx += om * (um[0] - cs * uk[0]); gy += om * (um[1] - cs * uk[1]); gz += om * (um[2] - cs * uk[2]);
+      }
+    }
+    const float iv = sinv[k];
+    gx *= iv; gy *= iv; gz *= iv;
+    const int64_t idx = (int64_t)r * N + k;
+    if (d_normals_up) { gx += d_normals_up[3 * idx]; gy += d_normals_up[3 * idx + 1]; gz += d_normals_up[3 * idx + 2]; }
+    float* o = d_normals + idx * dn_ld;
+    o[0] = gx; o[1] = gy; o[2] = gz;
+  }
+
+  // ---- density parameter grads through the clamps (density_functions.py:169-204)
+  ds_acc = warp_sum(ds_acc); dm_acc = warp_sum(dm_acc); db_acc = warp_sum(db_acc);
+  if (lane == 0) {
+    const float b = dparams[0], sc = dparams[1], mu = dparams[2];
+    if (b >= cfg.beta_lo && b <= cfg.beta_hi && db_acc != 0.f) atomicAdd(d_density + 0, db_acc);
+    float as = fabsf(sc);
+    float route = (as > cfg.scale_min) ? 1.f : ((as == cfg.scale_min) ? 0.5f : 0.f);
+    float sgn = (sc > 0.f) ? 1.f : ((sc < 0.f) ? -1.f : 0.f);
+    if (route != 0.f && ds_acc != 0.f) atomicAdd(d_density + 1, ds_acc * route * sgn);
+    if (mu >= cfg.mean_lo && mu <= cfg.mean_hi && dm_acc != 0.f) atomicAdd(d_density + 2, dm_acc);
+  }
+}
+
+int launch_render_tail_bwd(const vfnerf_render_cfg& cfg, int n_rays, int n_samples,
+                           const float* density_params, const float* normals, int64_t normals_ld,
+                           const float* ray_dirs, const float* z, const float* colors,
+                           const float* d_rgb, const float* d_depth, const float* d_normals_up,
+                           const float* d_colors_up, float* d_colors, float* d_normals,
+                           int64_t d_normals_ld, float* d_density, cudaStream_t s) {
+  if (n_rays <= 0) return 0;
+  VFN_REQUIRE(n_samples >= 2 && n_samples <= VFNERF_MAX_SAMPLES, "render_tail_bwd: n_samples=%d out of range", n_samples);
+  render_tail_bwd_kernel<<<(n_rays + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, s>>>(
+      cfg, n_rays, n_samples, density_params, normals, normals_ld, ray_dirs, z, colors, d_rgb, d_depth,
+      d_normals_up, d_colors_up, d_colors, d_normals, d_normals_ld, d_density);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vfn

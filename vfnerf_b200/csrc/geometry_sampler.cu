@@ -1,0 +1,226 @@
+// Ray generation and the two samplers.
+//
+// Contract: sample positions are BIT-EXACT with the reference given the same uniform draws.  The
+// reference evaluates every expression as separate fp32 tensor ops on the CPU, so every product and
+// sum here is an explicit round-to-nearest intrinsic (__fmul_rn/__fadd_rn/...): the compiler may not
+// contract them into FMAs.  HBM-bound byte work: one thread per output element, fully coalesced.
+#include "common.cuh"
+
+namespace vfn {
+
+// ---------------------------------------------------------------------------------------------
+// a1: utils/rendering.py:12-60 + utils/pinhole_model.py:9-63
+// ---------------------------------------------------------------------------------------------
+__global__ void ray_geometry_kernel(int n_rays, int pose_is_quat, const float* __restrict__ uv,
+                                    const float* __restrict__ pose, const float* __restrict__ K,
+                                    float* __restrict__ directions, float* __restrict__ ray_dirs,
+                                    float* __restrict__ cam_loc) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  float p[3][4];
+  if (pose_is_quat) {
+    const float* q7 = pose + (int64_t)r * 7;
+    float qr = q7[0], qi = q7[1], qj = q7[2], qk = q7[3];
+    float nq = fmaxf(sqrtf(qr * qr + qi * qi + qj * qj + qk * qk), 1e-12f);
+    qr /= nq; qi /= nq; qj /= nq; qk /= nq;
+    p[0][0] = 1.f - 2.f * (qj * qj + qk * qk); p[0][1] = 2.f * (qj * qi - qk * qr); p[0][2] = 2.f * (qi * qk + qr * qj);
+    p[1][0] = 2.f * (qj * qi + qk * qr); p[1][1] = 1.f - 2.f * (qi * qi + qk * qk); p[1][2] = 2.f * (qj * qk - qi * qr);
+    p[2][0] = 2.f * (qk * qi - qj * qr); p[2][1] = 2.f * (qj * qk + qi * qr); p[2][2] = 1.f - 2.f * (qi * qi + qj * qj);
+    p[0][3] = q7[4]; p[1][3] = q7[5]; p[2][3] = q7[6];
+  } else {
+    const float4* pm = reinterpret_cast<const float4*>(pose + (int64_t)r * 16);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float4 row = __ldg(pm + i);
+      p[i][0] = row.x; p[i][1] = row.y; p[i][2] = row.z; p[i][3] = row.w;
+    }
+  }
+  const float* Kr = K + (int64_t)r * 16;
+  float fx = Kr[0], skew = Kr[1], cx = Kr[2], fy = Kr[5], cy = Kr[6];
+  float k011 = __ldg(K + 5);                                   // intrinsics[0,1,1] of the FIRST ray
+  float zc = (k011 > 0.f) ? 1.f : ((k011 < 0.f) ? -1.f : 0.f);  // ones * sign(.)
+  float za = fabsf(zc);
+  float u = uv[2 * (int64_t)r], v = uv[2 * (int64_t)r + 1];
+  // x = (u - cx + cy*skew/fy - skew*v/fy) / fx * |z| ; y = (v - cy) / fy * |z|
+  float t = __fsub_rn(u, cx);
+  t = __fadd_rn(t, __fdiv_rn(__fmul_rn(cy, skew), fy));
+  t = __fsub_rn(t, __fdiv_rn(__fmul_rn(skew, v), fy));
+  float x = __fmul_rn(__fdiv_rn(t, fx), za);
+  float y = __fmul_rn(__fdiv_rn(__fsub_rn(v, cy), fy), za);
+  float d[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    // bmm row: ((p0*x + p1*y) + p2*z) + p3*1, unfused (matches torch CPU bmm bit for bit)
+    float acc = __fmul_rn(p[i][0], x);
+    acc = __fadd_rn(acc, __fmul_rn(p[i][1], y));
+    acc = __fadd_rn(acc, __fmul_rn(p[i][2], zc));
+    acc = __fadd_rn(acc, __fmul_rn(p[i][3], 1.f));
+    d[i] = __fsub_rn(acc, p[i][3]);
+  }
+  float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]))), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    directions[3 * (int64_t)r + i] = d[i];
+    ray_dirs[3 * (int64_t)r + i] = __fdiv_rn(d[i], nrm);
+    cam_loc[3 * (int64_t)r + i] = p[i][3];
+  }
+}
+
+int launch_ray_geometry(int n_rays, int pose_is_quat, const float* uv, const float* pose,
+                        const float* K, float* directions, float* ray_dirs, float* cam_loc,
+                        cudaStream_t s) {
+  if (n_rays <= 0) return 0;
+  ray_geometry_kernel<<<(n_rays + 127) / 128, 128, 0, s>>>(n_rays, pose_is_quat, uv, pose, K,
+                                                             directions, ray_dirs, cam_loc);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2: UniformSampler.get_z_vals (ray_sampler.py:113-142) + RaySampler.sample (:49-80)
+// ---------------------------------------------------------------------------------------------
+__global__ void coarse_sample_kernel(int64_t total, int n_coarse, float nearf, float farf, int perturb,
+                                     const float* __restrict__ t_vals, const float* __restrict__ U1,
+                                     const float* __restrict__ directions,
+                                     const float* __restrict__ cam_loc, float* __restrict__ z,
+                                     float* __restrict__ points) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int64_t r = idx / n_coarse;
+  int i = (int)(idx - r * n_coarse);
+  auto lin = [&](int k) {
+    float tk = __ldg(t_vals + k);
+    return __fadd_rn(__fmul_rn(nearf, __fsub_rn(1.f, tk)), __fmul_rn(farf, tk));
+  };
+  float zi = lin(i);
+  if (perturb) {
+    float lower = (i == 0) ? zi : __fmul_rn(0.5f, __fadd_rn(zi, lin(i - 1)));
+    float upper = (i == n_coarse - 1) ? zi : __fmul_rn(0.5f, __fadd_rn(lin(i + 1), zi));
+    zi = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), U1[idx]));
+  }
+  z[idx] = zi;
+  if (points) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      points[3 * idx + c] = __fadd_rn(__ldg(cam_loc + 3 * r + c), __fmul_rn(zi, __ldg(directions + 3 * r + c)));
+  }
+}
+
+int launch_coarse_sample(int n_rays, int n_coarse, double near_, double far_, int perturb,
+                         const float* t_vals, const float* U1, const float* directions,
+                         const float* cam_loc, float* z, float* points, cudaStream_t s) {
+  int64_t total = (int64_t)n_rays * n_coarse;
+  if (total <= 0) return 0;
+  VFN_REQUIRE(!perturb || U1 != nullptr, "coarse_sample: perturb=1 needs U1");
+  coarse_sample_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(
+      total, n_coarse, (float)near_, (float)far_, perturb, t_vals, U1, directions, cam_loc, z, points);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a7: RangeFineSampler.get_z_vals (ray_sampler.py:264-302) + sample.  One warp per ray:
+// warp argmax (first index on ties), candidate generation, bitonic sort of <= 256 values in the
+// warp's shared-memory slice (value-exact, so identical to torch.sort's values), point generation.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFineWarps = 4;
+
+__global__ void __launch_bounds__(kFineWarps * 32)
+fine_sample_kernel(int n_rays, int n_coarse, int n_fine, float nearf, float far_minus_near,
+                   float rangef, float stepf, int perturb, const float* __restrict__ z_coarse,
+                   const float* __restrict__ w_coarse, const float* __restrict__ U2,
+                   const float* __restrict__ U3, const float* __restrict__ z_override,
+                   const float* __restrict__ directions, const float* __restrict__ cam_loc,
+                   float* __restrict__ z_out, float* __restrict__ points) {
+  __shared__ float sbuf[kFineWarps][VFNERF_MAX_SAMPLES];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * kFineWarps + wid;
+  if (r >= n_rays) return;
+  float* s = sbuf[wid];
+  const int N = n_coarse + n_fine;
+  if (z_override) {
+    for (int j = lane; j < N; j += 32) s[j] = z_override[(int64_t)r * N + j];
+  } else {
+    // argmax of the coarse weights, first index on ties (torch.argmax)
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < n_coarse; j += 32) {
+      float w = w_coarse[(int64_t)r * n_coarse + j];
+      if (w > best) { best = w; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(kFull, best, o);
+      int oi = __shfl_xor_sync(kFull, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (bi == 0x7fffffff) bi = 0;  // all -inf / NaN rows: fall back to index 0 like an all-equal row
+    const float z_star = z_coarse[(int64_t)r * n_coarse + bi];
+    for (int j = lane; j < n_coarse; j += 32) s[j] = z_coarse[(int64_t)r * n_coarse + j];
+    const float base = __fsub_rn(z_star, rangef);
+    auto ramp = [&](int i) { return __fadd_rn(base, __fmul_rn(stepf, (float)i)); };
+    for (int i = lane; i < n_fine; i += 32) {
+      float v;
+      if (bi > 0) {
+        v = ramp(i);
+        if (perturb) {
+          float lower = (i == 0) ? v : __fmul_rn(0.5f, __fadd_rn(v, ramp(i - 1)));
+          float upper = (i == n_fine - 1) ? v : __fmul_rn(0.5f, __fadd_rn(ramp(i + 1), v));
+          v = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), U2[(int64_t)r * n_fine + i]));
+        }
+      } else {
+        v = __fadd_rn(__fmul_rn(U3[(int64_t)r * n_fine + i], far_minus_near), nearf);
+      }
+      s[n_coarse + i] = v;
+    }
+    int P2 = 32;
+    while (P2 < N) P2 <<= 1;
+    for (int j = N + lane; j < P2; j += 32) s[j] = INFINITY;
+    __syncwarp();
+    for (int k = 2; k <= P2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (P2 >> 1); t += 32) {
+          int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j cleared
+          int hi = lo | j;
+          bool asc = (lo & k) == 0;
+          float a = s[lo], b = s[hi];
+          if ((a > b) == asc) { s[lo] = b; s[hi] = a; }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncwarp();
+  const float dx = directions[3 * (int64_t)r], dy = directions[3 * (int64_t)r + 1], dz = directions[3 * (int64_t)r + 2];
+  const float ox = cam_loc[3 * (int64_t)r], oy = cam_loc[3 * (int64_t)r + 1], oz = cam_loc[3 * (int64_t)r + 2];
+  for (int j = lane; j < N; j += 32) z_out[(int64_t)r * N + j] = s[j];
+  if (points) {
+    float* pr = points + (int64_t)r * N * 3;
+    for (int e = lane; e < 3 * N; e += 32) {
+      int j = e / 3, c = e - 3 * j;
+      float d = (c == 0) ? dx : (c == 1 ? dy : dz);
+      float o = (c == 0) ? ox : (c == 1 ? oy : oz);
+      pr[e] = __fadd_rn(o, __fmul_rn(s[j], d));
+    }
+  }
+}
+
+int launch_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, double far_,
+                       double fine_range, int perturb, const float* z_coarse, const float* w_coarse,
+                       const float* U2, const float* U3, const float* z_override,
+                       const float* directions, const float* cam_loc, float* z, float* points,
+                       cudaStream_t s) {
+  if (n_rays <= 0) return 0;
+  VFN_REQUIRE(n_coarse + n_fine <= VFNERF_MAX_SAMPLES, "fine_sample: n_coarse+n_fine=%d exceeds %d",
+              n_coarse + n_fine, VFNERF_MAX_SAMPLES);
+  VFN_REQUIRE(n_fine >= 2, "fine_sample: n_fine must be >= 2 (the reference divides by n_fine-1)");
+  VFN_REQUIRE(z_override || (U3 && (!perturb || U2)), "fine_sample: missing uniform draws");
+  float stepf = (float)(2.0 * fine_range / (double)(n_fine - 1));   // python double, then fp32
+  fine_sample_kernel<<<(n_rays + kFineWarps - 1) / kFineWarps, kFineWarps * 32, 0, s>>>(
+      n_rays, n_coarse, n_fine, (float)near_, (float)(far_ - near_), (float)fine_range, stepf, perturb,
+      z_coarse, w_coarse, U2, U3, z_override, directions, cam_loc, z, points);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vfn

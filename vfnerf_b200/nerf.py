@@ -1,0 +1,202 @@
+"""VectorFieldNerf -- the drop-in boundary.
+
+Same constructor argument, attributes and methods as the reference facade
+(models/nerf/vector_field_nerf.py:23-338): ``render``, ``parameters``, ``train/eval``, ``load/save``,
+``to/cpu``, ``new_scheduler/reset_scheduler`` and the attributes callers touch (``ray_sampler``,
+``fine_sampler``, ``vector_field_network``, ``fine_vector_field_network``, ``rendering_network``,
+``density``, ``optimizer``, ``scheduler``, ``config``).  ``render()`` runs entirely in
+libvfnerf_b200.so; this file only marshals arguments.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+
+from . import _lib, ops
+from .networks import LaplaceDensity, RenderingNetwork, VectorFieldNetwork
+from .output import NerfOutput
+from .samplers import RangeFineSampler, UniformSampler
+
+
+class VectorFieldNerf:
+    def __init__(self, config, precision: str = "fp32") -> None:
+        """:param config: a VFNerfConfig (ours or the reference's own dataclass; only attributes are read).
+        :param precision: "fp32" | "bf16" | "bf16x3" -- arithmetic of the two MLPs (include/vfnerf_b200.h)."""
+        self.config = config
+        rs = config.ray_sampler_config
+        self.vector_field_network = VectorFieldNetwork(config.vf_net_config)
+        if rs.fine_sampling():
+            self.fine_vector_field_network = self.vector_field_network     # shared, vector_field_nerf.py:36
+        self.rendering_network = RenderingNetwork(config.rendering_net_config)
+        self.ray_sampler = UniformSampler(rs.n_samples, rs.near, rs.far, (not rs.perturb))
+        if rs.fine_sampling():
+            self.fine_sampler = RangeFineSampler(rs.n_importance, rs.near, rs.far, (not rs.perturb),
+                                                 range=rs.fine_range, max_samples=rs.max_samples)
+        self.density = LaplaceDensity(**config.density_config.todict())
+        self.set_precision(precision)
+
+        sc = config.scheduler_config
+        self.optimizer = torch.optim.Adam(self.parameters(), lr=sc.lr, weight_decay=sc.weight_decay)
+        self.scheduler = torch.optim.lr_scheduler.ExponentialLR(
+            self.optimizer, sc.lr_decay_factor ** (1. / sc.lr_decay_steps))
+        if getattr(config.cuda_config, "num_gpus", 1) > 1:
+            # The reference wraps the nets in nn.DataParallel here (:70-75), a path that cannot run as
+            # shipped.  Multi-GPU is one process per GPU: see vfnerf_b200.dist.
+            pass
+        self.to(config.cuda_config.device)
+        self.return_ray_dirs = True
+        self.last_extras: dict = {}
+
+    # ---- module plumbing (vector_field_nerf.py:84-214) ------------------------------------------
+    def set_precision(self, precision: str) -> None:
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
+        self.precision = precision
+        self.vector_field_network.precision = precision
+
+    def _modules(self):
+        return (self.vector_field_network, self.rendering_network, self.density)
+
+    def cpu(self) -> None:
+        for m in self._modules():
+            m.cpu()
+
+    def to(self, device: torch.device) -> None:
+        for m in self._modules():
+            m.to(device)
+
+    def _new_schedule(self, num_steps: int) -> None:
+        sc = self.config.scheduler_config
+        self.scheduler = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, sc.lr_decay_factor ** (1. / num_steps))
+        self.optimizer = torch.optim.Adam(self.parameters(), lr=sc.lr)
+
+    def new_scheduler(self, num_steps: int) -> None:
+        self._new_schedule(num_steps)
+
+    def reset_scheduler(self, num_steps: Optional[int] = None) -> None:
+        self._new_schedule(self.config.scheduler_config.lr_decay_steps if num_steps is None else num_steps)
+
+    def parameters(self) -> List[torch.nn.Parameter]:
+        # the VF parameters appear twice when fine sampling is on, exactly as in the reference (:132-137):
+        # clip_grad_norm_ and Adam then see the duplicate list the reference trainer sees.
+        params = list(self.vector_field_network.parameters()) + list(self.rendering_network.parameters()) + \
+            list(self.density.parameters())
+        if self.config.ray_sampler_config.fine_sampling():
+            params += list(self.fine_vector_field_network.parameters())
+        return params
+
+    def train(self) -> None:
+        if self.config.numerical_jacobian:
+            self.vector_field_network.eval()
+        else:
+            self.vector_field_network.train()
+        self.rendering_network.train()
+        self.density.train()
+
+    def eval(self) -> None:
+        for m in self._modules():
+            m.eval()
+
+    def load(self, path: str) -> int:
+        ckpt = torch.load(path, map_location=self.config.cuda_config.device)
+        self.vector_field_network.load_state_dict(ckpt["vf_net"])
+        self.rendering_network.load_state_dict(ckpt["rendering_net"])
+        self.density.load_state_dict(ckpt["density"])
+        epoch = ckpt["epoch"] + 1
+        self.optimizer.load_state_dict(ckpt["optimizer"])
+        self.scheduler.load_state_dict(ckpt["scheduler"])
+        if self.config.ray_sampler_config.fine_sampling() and "fine_vf_net" in ckpt:
+            self.fine_vector_field_network.load_state_dict(ckpt["fine_vf_net"])
+        return epoch
+
+    def save(self, epoch: int, path: str) -> None:
+        state = {"vf_net": self.vector_field_network.state_dict(),
+                 "rendering_net": self.rendering_network.state_dict(),
+                 "density": self.density.state_dict(), "epoch": epoch,
+                 "optimizer": self.optimizer.state_dict(), "scheduler": self.scheduler.state_dict()}
+        if self.config.ray_sampler_config.fine_sampling():
+            state["fine_vf_net"] = self.fine_vector_field_network.state_dict()
+        torch.save(state, os.path.join(path, f"{epoch}.pth"))
+        torch.save(state, os.path.join(path, "latest.pth"))
+
+    # ---- the hot path ---------------------------------------------------------------------------
+    def _render_cfg(self, n_rays: int, pose_is_quat: bool) -> _lib.RenderCfg:
+        c, d = self.config, self.density
+        if not c.ray_sampler_config.fine_sampling():
+            # the reference dies with UnboundLocalError at vector_field_nerf.py:331 in this configuration
+            raise UnboundLocalError("render() needs fine sampling (n_importance > 0), like the reference")
+        if c.rendering != "volsdf":
+            raise NotImplementedError('rendering="nerf" passes its arguments swapped in the reference '
+                                      "(SURVEY.md §8a); only \"volsdf\" is supported")
+        near, far = self.ray_sampler.near, self.ray_sampler.far
+        if not isinstance(far, (int, float)) or not isinstance(near, (int, float)):
+            near, far = float(near), float(far)
+        cfg = _lib.RenderCfg()
+        cfg.n_rays, cfg.n_coarse, cfg.n_fine = n_rays, self.ray_sampler.N_samples, self.fine_sampler.n_fine()
+        cfg.perturb = 0 if self.ray_sampler.deterministic else 1
+        cfg.pose_is_quat = 1 if pose_is_quat else 0
+        cfg.window = int(len(c.cos_sim_weights))
+        cfg.normalize = 1 if c.normalize_rendering else 0
+        cfg.multires = self.vector_field_network.multires
+        cfg.multires_view = self.rendering_network.multires_view
+        cfg.skip_layer = self.vector_field_network.skip_layer
+        cfg.precision = _lib.PRECISIONS[self.precision]
+        cfg.near_, cfg.far_, cfg.fine_range = float(near), float(far), float(self.fine_sampler.range)
+        cfg.dir_to_normal_th = float(c.dir_to_normal_th)
+        cfg.beta_lo, cfg.beta_hi = float(d.beta_bounds[0]), float(d.beta_bounds[1])
+        cfg.mean_lo, cfg.mean_hi = float(d.mean_bounds[0]), float(d.mean_bounds[1])
+        cfg.scale_min = float(d.scale_min)
+        cfg.bn_eps = 1e-5
+        return cfg
+
+    def render(self, pose: torch.Tensor, pixels: torch.Tensor, intrinsics: torch.Tensor, epoch: int,
+               white: bool = False, *, draws=None, z_vals_override: Optional[torch.Tensor] = None) -> NerfOutput:
+        """Same contract as vector_field_nerf.py:216-338.
+
+        :param pose: [R,4,4] camera-to-world matrices or [R,7] (quaternion, translation), on the GPU.
+        :param pixels: [R,2] (u, v).   :param intrinsics: [R,4,4].   :param epoch: unused on this path (the
+            annealed cos_sim_weights are only read for their length).
+        :param draws: optional (U1, U2, U3) uniform tensors replacing the CPU-generator draws (tests, and
+            multi-GPU ray sharding where each rank takes its slice of the global draws).
+        :param z_vals_override: optional [R,N] merged z values for the second pass (parity protocol).
+        """
+        if white:
+            # vector_field_nerf.py:274-277 reads rgb_values_coarse before assignment
+            raise UnboundLocalError("white=True is broken in the reference (SURVEY.md fact 2) and unsupported")
+        if self.vector_field_network.training:
+            raise NotImplementedError("render() with the VF net in train() mode (batch-stat BatchNorm + Jacobian) is "
+                                      "SURVEY.md §8(f) rank 1; call model.eval() as the reference trainer does")
+        pixels = ops._require_cuda("pixels", pixels)
+        pose = ops._require_cuda("pose", pose)
+        intrinsics = ops._require_cuda("intrinsics", intrinsics)
+        dev = pixels.device
+        R = pixels.shape[0]
+        if pose.shape[0] != R or intrinsics.shape[0] != R:
+            raise ValueError("pose, pixels and intrinsics must have one row per ray")
+        quat = pose.dim() == 2 and pose.shape[1] == 7
+        cfg = self._render_cfg(R, quat)
+        # host-side draws in the reference's order (ray_sampler.py:138, 292, 297), then H2D
+        if draws is None:
+            U1 = self.ray_sampler.draw(R)
+            U2, U3 = self.fine_sampler.draw(R)
+        else:
+            U1, U2, U3 = draws
+        t_vals = self.ray_sampler.t_vals()
+
+        def dev_(t):
+            return None if t is None else t.to(dev, non_blocking=True).float().contiguous()
+        call = ops.RenderCall(cfg, self.vector_field_network, self.rendering_network, self.density,
+                              pixels, pose, intrinsics, dev_(t_vals), dev_(U1), dev_(U2), dev_(U3),
+                              z_override=dev_(z_vals_override), want_extras=True,
+                              want_ray_dirs=self.return_ray_dirs)
+        res = ops.render_call(call)
+        rgb, depth, normals, colors, points, z_vals = res[:6]
+        ray_dirs = res[6] if len(res) > 6 else None
+        self.last_extras = call.extras
+        return NerfOutput(points_coarse=points, points_fine=None, coarse_normals=normals,
+                          coarse_rgb_values=rgb, coarse_depth_map=depth, fine_normals=None,
+                          fine_rgb_values=None, fine_depth_map=None, z_vals=z_vals,
+                          directional_derivtives=None, ray_dirs=ray_dirs, coarse_colors=colors,
+                          weights=call.extras.get("weights"))

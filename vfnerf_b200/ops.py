@@ -1,0 +1,195 @@
+"""torch.autograd bridges between the parameter owners (networks.py) and the C ABI (_lib.py).
+
+PyTorch is plumbing here: it owns device memory (outputs, workspaces, arenas), the current stream and
+the autograd tape.  All arithmetic happens in libvfnerf_b200.so.  Tensors handed to the library must
+be CUDA fp32; host tensors are rejected (no CPU path exists).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_NUM_LAUNCHES = {"count": 0}     # kernels enqueued by this process (bench.py reports it)
+
+
+def _require_cuda(name: str, t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: vfnerf_b200 has no CPU fallback "
+                           "(move inputs to the device first, like train/vector_field_nerf_train.py:172-174)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# VF-only query (VectorFieldNetwork.__call__)
+# ------------------------------------------------------------------------------------------------
+class _VFQuery(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, points, n_cols, need_bwd, *params):
+        L = _lib.lib()
+        ar = net.arena()
+        dev = points.device
+        P = points.shape[0]
+        Do = ar.desc.out_dim[ar.desc.n_layers - 1]
+        n_cols = Do if n_cols is None else int(n_cols)
+        prec = _lib.PRECISIONS[net.precision]
+        if need_bwd and prec != _lib.PREC_FP32:
+            prec = _lib.PREC_FP32
+        nbytes = L.vfnerf_vf_workspace_bytes(C.byref(ar.desc), P, net.multires, int(need_bwd), prec)
+        if nbytes < 0:
+            _lib.check(1, "vfnerf_vf_workspace_bytes")
+        ws = _workspace(nbytes, dev)
+        out = torch.empty(P, n_cols, dtype=torch.float32, device=dev)
+        _lib.check(L.vfnerf_vf_fwd(C.byref(ar.desc), ar.flat.data_ptr(), net.multires, net.skip_layer, 1e-5,
+                                   prec, points.data_ptr(), P, out.data_ptr(), n_cols, n_cols,
+                                   ws.data_ptr(), ws.numel(), int(need_bwd), _stream_ptr(dev)), "vfnerf_vf_fwd")
+        ctx.net, ctx.ws, ctx.P, ctx.n_cols = net, ws, P, n_cols
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        L = _lib.lib()
+        net = ctx.net
+        ar = net.arena()
+        (out,) = ctx.saved_tensors
+        dev = out.device
+        d_out = d_out.contiguous().float()
+        grad = torch.empty(ar.desc.arena_floats, dtype=torch.float32, device=dev)
+        _lib.check(L.vfnerf_vf_bwd(C.byref(ar.desc), ar.flat.data_ptr(), net.multires, net.skip_layer, 1e-5,
+                                   _lib.PREC_FP32, ctx.P, out.data_ptr(), ctx.n_cols, d_out.data_ptr(), ctx.n_cols,
+                                   ctx.n_cols, grad.data_ptr(), 0, ctx.ws.data_ptr(), ctx.ws.numel(),
+                                   _stream_ptr(dev)), "vfnerf_vf_bwd")
+        ctx.ws = None
+        return (None, None, None, None) + tuple(ar.grad_views(grad))
+
+
+def vf_query(net, points: torch.Tensor, n_cols: Optional[int] = None) -> torch.Tensor:
+    """tanh([v, feat]) of the VF MLP at ``points[P,3]`` (vector_field_network.py:177-208).  ``n_cols=3``
+    evaluates only the vector (the marching-cubes query keeps just [:, :3], mc_utils.py:99-101)."""
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise ValueError(f"points must be [P,3], got {tuple(points.shape)}")
+    points = _require_cuda("points", points.detach())
+    ar = net.arena()
+    if ar.flat.device != points.device:
+        raise RuntimeError(f"network parameters are on {ar.flat.device}, points on {points.device}")
+    params = ar.params()
+    need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _VFQuery.apply(net, points, n_cols, need_bwd, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# render()
+# ------------------------------------------------------------------------------------------------
+class RenderCall:
+    """Everything one render() call needs besides the parameters (built by nerf.VectorFieldNerf)."""
+
+    def __init__(self, cfg: _lib.RenderCfg, vf_net, rn_net, density, uv, pose, intrinsics, t_vals, U1, U2, U3,
+                 z_override=None, want_extras: bool = False, want_ray_dirs: bool = True):
+        self.cfg, self.vf_net, self.rn_net, self.density = cfg, vf_net, rn_net, density
+        self.uv, self.pose, self.intrinsics, self.t_vals = uv, pose, intrinsics, t_vals
+        self.U1, self.U2, self.U3, self.z_override = U1, U2, U3, z_override
+        self.want_extras, self.want_ray_dirs = want_extras, want_ray_dirs
+        self.extras = {}
+        self.need_bwd = False
+
+
+class _Render(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, call: RenderCall, *params):
+        L = _lib.lib()
+        cfg = call.cfg
+        vf_ar, rn_ar = call.vf_net.arena(), call.rn_net.arena()
+        dflat = call.density.flat()
+        dev = call.uv.device
+        R, N = cfg.n_rays, cfg.n_coarse + cfg.n_fine
+        need_bwd = call.need_bwd
+        if need_bwd and cfg.precision != _lib.PREC_FP32:
+            raise RuntimeError("training (backward) currently runs on precision='fp32' only")
+        nbytes = L.vfnerf_render_workspace_bytes(C.byref(cfg), C.byref(vf_ar.desc), C.byref(rn_ar.desc), int(need_bwd))
+        if nbytes < 0:
+            _lib.check(1, "vfnerf_render_workspace_bytes")
+        ws = _workspace(nbytes, dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        points = torch.empty(R, N, 3, **f32)
+        normals = torch.empty(R, N, 3, **f32)
+        rgb = torch.empty(R, 3, **f32)
+        depth = torch.empty(R, 1, **f32)
+        z_vals = torch.empty(R, N, **f32)
+        colors = torch.empty(R * N, 3, **f32)
+        ray_dirs = torch.empty(R * N, 3, **f32) if call.want_ray_dirs else None
+        weights = torch.empty(R, N, **f32)
+        z_c = torch.empty(R, cfg.n_coarse, **f32) if call.want_extras else None
+        w_c = torch.empty(R, cfg.n_coarse, **f32) if call.want_extras else None
+        out = _lib.RenderOut(points.data_ptr(), normals.data_ptr(), rgb.data_ptr(), depth.data_ptr(),
+                             z_vals.data_ptr(), _lib.ptr(ray_dirs), colors.data_ptr(), weights.data_ptr(),
+                             _lib.ptr(z_c), _lib.ptr(w_c))
+        _lib.check(L.vfnerf_render_fwd(
+            C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),
+            dflat.data_ptr(), call.uv.data_ptr(), call.pose.data_ptr(), call.intrinsics.data_ptr(),
+            call.t_vals.data_ptr(), _lib.ptr(call.U1), _lib.ptr(call.U2), _lib.ptr(call.U3),
+            _lib.ptr(call.z_override), C.byref(out), ws.data_ptr(), ws.numel(), int(need_bwd), _stream_ptr(dev)),
+            "vfnerf_render_fwd")
+        call.extras = dict(weights=weights, z_coarse=z_c, weights_coarse=w_c)
+        if need_bwd:
+            ctx.call, ctx.ws, ctx.out_struct = call, ws, out
+            ctx.keep = (points, z_vals, colors, normals, weights, ray_dirs, z_c, w_c)
+        if ray_dirs is not None:
+            ctx.mark_non_differentiable(points, z_vals, ray_dirs)
+            return rgb, depth, normals, colors, points, z_vals, ray_dirs
+        ctx.mark_non_differentiable(points, z_vals)
+        return rgb, depth, normals, colors, points, z_vals
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_depth, d_normals, d_colors, *_):
+        L = _lib.lib()
+        call = ctx.call
+        cfg = call.cfg
+        vf_ar, rn_ar = call.vf_net.arena(), call.rn_net.arena()
+        dflat = call.density.flat()
+        dev = call.uv.device
+        R, N = cfg.n_rays, cfg.n_coarse + cfg.n_fine
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        def prep(g, shape):
+            return None if g is None else g.contiguous().float().view(shape)
+        d_rgb = prep(d_rgb, (R, 3)) if d_rgb is not None else torch.zeros(R, 3, **f32)
+        d_depth = prep(d_depth, (R, 1)) if d_depth is not None else torch.zeros(R, 1, **f32)
+        d_normals = prep(d_normals, (R, N, 3))
+        d_colors = prep(d_colors, (R * N, 3))
+        g_vf = torch.empty(vf_ar.desc.arena_floats, **f32)
+        g_rn = torch.empty(rn_ar.desc.arena_floats, **f32)
+        g_d = torch.empty(3, **f32)
+        _lib.check(L.vfnerf_render_bwd(
+            C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),
+            dflat.data_ptr(), C.byref(ctx.out_struct), d_rgb.data_ptr(), d_depth.data_ptr(), _lib.ptr(d_normals),
+            _lib.ptr(d_colors), g_vf.data_ptr(), g_rn.data_ptr(), g_d.data_ptr(), ctx.ws.data_ptr(),
+            ctx.ws.numel(), _stream_ptr(dev)), "vfnerf_render_bwd")
+        ctx.ws = ctx.keep = None
+        grads = vf_ar.grad_views(g_vf) + rn_ar.grad_views(g_rn) + [g_d[0], g_d[1], g_d[2]]
+        return (None,) + tuple(grads)
+
+
+def render_params(vf_net, rn_net, density) -> List[torch.nn.Parameter]:
+    """Parameter order used by _Render (and by its backward's return value)."""
+    return vf_net.arena().params() + rn_net.arena().params() + [density.beta, density.scale, density.mean]
+
+
+def render_call(call: RenderCall) -> Tuple[torch.Tensor, ...]:
+    params = render_params(call.vf_net, call.rn_net, call.density)
+    call.density.flat()
+    call.need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _Render.apply(call, *params)
