@@ -184,6 +184,11 @@ int vfnerf_density_weights(const vfnerf_render_cfg* cfg, int n_samples, const fl
 int vfnerf_composite(int n_rays, int n_samples, const float* weights, const float* colors,
                      const float* z, float* rgb, float* depth, void* stream);
 
+/* ---- debug / regression -------------------------------------------------------------------- */
+/* One CTA: D[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T through tcgen05.mma + TMEM; pins the UMMA
+ * descriptor conventions of csrc/tc_common.cuh (variant 1 = LBO/SBO swapped, expected to be wrong). */
+int vfnerf_debug_umma_gemm(const float* A, const float* B, float* D, int N, int K, int variant, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,20 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+_ALIVE = []
+
+
+def keep(t):
+    """device copy of a host tensor that stays referenced until the test module is torn down (a
+    temporary would be freed -- and its memory reused -- before the asynchronous kernel reads it)"""
+    d = t.to(DEV).contiguous()
+    _ALIVE.append(d)
+    if len(_ALIVE) > 64:
+        torch.cuda.synchronize()
+        del _ALIVE[:32]
+    return d.data_ptr()
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -29,7 +43,7 @@ def test_a1_ray_geometry_bit_exact(built_lib, R):
     K = K.clone(); K[:, 0, 1] = 0.37            # exercise the skew terms
     d_ref, rd_ref, cam_ref = U.O.ray_geometry(uv, pose, K)
     d, rd, cam = (torch.empty(R, 3, device=DEV) for _ in range(3))
-    _lib.check(built_lib.vfnerf_ray_geometry(R, 0, uv.to(DEV).data_ptr(), pose.to(DEV).data_ptr(), K.to(DEV).data_ptr(),
+    _lib.check(built_lib.vfnerf_ray_geometry(R, 0, keep(uv), keep(pose), keep(K),
                                              d.data_ptr(), rd.data_ptr(), cam.data_ptr(), _stream()), "ray_geometry")
     assert torch.equal(d.cpu(), d_ref)               # feeds the bit-exact sample positions
     assert torch.equal(cam.cpu(), cam_ref)
@@ -44,7 +58,7 @@ def test_a1_quaternion_pose(built_lib):
     pose7 = torch.cat([q, t], dim=1)
     d_ref, rd_ref, cam_ref = U.O.ray_geometry(uv, pose7, K)
     d, rd, cam = (torch.empty(R, 3, device=DEV) for _ in range(3))
-    _lib.check(built_lib.vfnerf_ray_geometry(R, 1, uv.to(DEV).data_ptr(), pose7.to(DEV).data_ptr(), K.to(DEV).data_ptr(),
+    _lib.check(built_lib.vfnerf_ray_geometry(R, 1, keep(uv), keep(pose7), keep(K),
                                              d.data_ptr(), rd.data_ptr(), cam.data_ptr(), _stream()), "ray_geometry")
     # quat_to_rot is .cuda()-only in the reference (pinhole_model.py:22): tolerance, not bit-exact
     assert (d.cpu() - d_ref).abs().max().item() <= 1e-5
@@ -61,8 +75,8 @@ def test_a2_coarse_sampler_bit_exact(built_lib, perturb, R, Nc, near, far):
     z_ref = U.O.coarse_z_vals(R, near, far, t_vals, bool(perturb), U1)
     p_ref = U.O.sample_points(cam, z_ref, d)
     z = torch.empty(R, Nc, device=DEV); p = torch.empty(R, Nc, 3, device=DEV)
-    _lib.check(built_lib.vfnerf_coarse_sample(R, Nc, near, far, perturb, t_vals.to(DEV).data_ptr(), U1.to(DEV).data_ptr(),
-                                              d.to(DEV).data_ptr(), cam.to(DEV).data_ptr(), z.data_ptr(), p.data_ptr(),
+    _lib.check(built_lib.vfnerf_coarse_sample(R, Nc, near, far, perturb, keep(t_vals), keep(U1),
+                                              keep(d), keep(cam), z.data_ptr(), p.data_ptr(),
                                               _stream()), "coarse_sample")
     assert torch.equal(z.cpu(), z_ref)
     assert torch.equal(p.cpu(), p_ref)
@@ -86,9 +100,9 @@ def test_a7_fine_sampler_bit_exact(built_lib, perturb, R, Nc, Nf, near, far, rng
     z_ref = U.O.fine_z_vals(z_c, w_c, near, far, rng, Nf, bool(perturb), U2, U3)
     p_ref = U.O.sample_points(cam, z_ref, d)
     z = torch.empty(R, Nc + Nf, device=DEV); p = torch.empty(R, Nc + Nf, 3, device=DEV)
-    _lib.check(built_lib.vfnerf_fine_sample(R, Nc, Nf, near, far, rng, perturb, z_c.to(DEV).data_ptr(), w_c.to(DEV).data_ptr(),
-                                            U2.to(DEV).data_ptr(), U3.to(DEV).data_ptr(), d.to(DEV).data_ptr(),
-                                            cam.to(DEV).data_ptr(), z.data_ptr(), p.data_ptr(), _stream()), "fine_sample")
+    _lib.check(built_lib.vfnerf_fine_sample(R, Nc, Nf, near, far, rng, perturb, keep(z_c), keep(w_c),
+                                            keep(U2), keep(U3), keep(d),
+                                            keep(cam), z.data_ptr(), p.data_ptr(), _stream()), "fine_sample")
     assert torch.equal(z.cpu(), z_ref)
     assert torch.equal(p.cpu(), p_ref)
     assert torch.all(z[:, 1:] >= z[:, :-1])       # sortedness (size-independent property)
@@ -111,8 +125,8 @@ def test_a4_a5_a6_density_and_weights(built_lib, R, N, window, th):
     cfg = _cfg(R, window, th)
     dp = torch.stack([beta, scale, mean]).to(DEV)
     c = torch.empty(R, N - 1, device=DEV); sig = torch.empty(R, N, device=DEV); w = torch.empty(R, N, device=DEV)
-    _lib.check(built_lib.vfnerf_density_weights(C.byref(cfg), N, dp.data_ptr(), normals.to(DEV).data_ptr(), 3,
-                                                rd.to(DEV).data_ptr(), z.to(DEV).data_ptr(), c.data_ptr(), sig.data_ptr(),
+    _lib.check(built_lib.vfnerf_density_weights(C.byref(cfg), N, dp.data_ptr(), keep(normals), 3,
+                                                keep(rd), keep(z), c.data_ptr(), sig.data_ptr(),
                                                 w.data_ptr(), _stream()), "density_weights")
     assert (c.cpu() - c_ref).abs().max().item() <= 2e-6           # fp32 cosine arithmetic
     # sigma = 100 * laplace(c): 2e-6 in c is 2e-4 in sigma away from the mask discontinuity
@@ -129,7 +143,7 @@ def test_a9_composite(built_lib):
     w = torch.rand(R, N, generator=g); w = w / w.sum(1, keepdim=True)
     col = torch.rand(R * N, 3, generator=g); z = torch.rand(R, N, generator=g) * 6
     rgb = torch.empty(R, 3, device=DEV); dep = torch.empty(R, 1, device=DEV)
-    _lib.check(built_lib.vfnerf_composite(R, N, w.to(DEV).data_ptr(), col.to(DEV).data_ptr(), z.to(DEV).data_ptr(),
+    _lib.check(built_lib.vfnerf_composite(R, N, keep(w), keep(col), keep(z),
                                           rgb.data_ptr(), dep.data_ptr(), _stream()), "composite")
     rgb_ref = (w.unsqueeze(-1) * col.reshape(R, N, 3)).sum(1)
     dep_ref = (w * z).sum(1, keepdim=True)
