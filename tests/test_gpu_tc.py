@@ -22,3 +22,109 @@ def test_umma_descriptor_conventions(built_lib, N, K):
     err = (D - ref).abs().max().item()
     print(f"N={N} K={K}: max abs err {err:.3e} (ref magnitude {ref.abs().max().item():.1f})")
     assert err <= 1e-3 * max(1.0, ref.abs().max().item())      # fp32 accumulation-order noise only
+
+
+def _tame_state():
+    """A bf16-friendly model: default-like init (gain 1, no output centring).  Its density is degenerate
+     but the per-point MLP outputs are a meaningful bf16 parity target."""
+    return U.S.synthetic_state(0, vf_gain=1.0, center_output=False)
+
+
+@pytest.mark.parametrize("P", [1, 127, 128, 129, 5000, 300 * 128 + 17])
+def test_tc_vf_query_matches_fp32_path(built_lib, P):
+    """bf16 tcgen05 chain vs the fp32 CUDA-core chain on the same points (tail tiles, multi-tile CTAs)."""
+    case, z = U.load_golden("full_det")
+    model = U.make_model(case, _tame_state(), DEV)
+    g = torch.Generator().manual_seed(P)
+    pts = ((torch.rand(P, 3, generator=g) - 0.5) * 8).to(DEV)
+    with torch.no_grad():
+        ref = model.vector_field_network(pts)
+        model.set_precision("bf16")
+        out = model.vector_field_network(pts)
+        v3 = __import__("vfnerf_b200.ops", fromlist=["vf_query"]).vf_query(model.vector_field_network, pts, n_cols=3)
+    err = (out - ref).abs()
+    print(f"P={P}: bf16 vs fp32  v max {err[:, :3].max().item():.2e} mean {err[:, :3].mean().item():.2e} | "
+          f"feat max {err[:, 3:].max().item():.2e} mean {err[:, 3:].mean().item():.2e}")
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert torch.equal(v3, out[:, :3])                    # V_ONLY and VF_FULL programs agree on the vector
+    assert err.max().item() <= 5e-3                       # BASELINE.json north_star: 5e-3 abs on the bf16 path
+
+
+def test_tc_vf_query_on_the_bending_model(built_lib):
+    """On the centred (non-degenerate) synthetic model bf16 rounding is amplified by the output rescale;
+    this test documents the error instead of hiding it: mean stays small, the max is reported."""
+    case, z = U.load_golden("full_det")
+    model = U.make_model(case, U.case_state(case, z), DEV)
+    g = torch.Generator().manual_seed(5)
+    pts = ((torch.rand(20000, 3, generator=g) - 0.5) * 8).to(DEV)
+    with torch.no_grad():
+        ref = model.vector_field_network(pts)
+        model.set_precision("bf16")
+        out = model.vector_field_network(pts)
+    err = (out - ref).abs()
+    print(f"bending model: v max {err[:, :3].max().item():.2e} mean {err[:, :3].mean().item():.2e} | "
+          f"feat max {err[:, 3:].max().item():.2e} mean {err[:, 3:].mean().item():.2e}")
+    assert err[:, :3].mean().item() <= 3e-2 and err[:, 3:].mean().item() <= 1e-2
+
+
+def test_tc_render_matches_fp32_path(built_lib):
+    """Fused VF+colour tcgen05 launch inside render() vs the fp32 path, second pass conditioned on the same z."""
+    case, z = U.load_golden("full_perturb")
+    model = U.make_model(case, _tame_state(), DEV)
+    R = 512
+    uv, pose, K = U.S.synthetic_rays(R, seed=0, start=0, stride=797)
+    draws = U.S.synthetic_draws(R, 64, 64, seed=99)
+    a = (pose.to(DEV), uv.to(DEV), K.to(DEV), 0)
+    with torch.no_grad():
+        ref = model.render(*a, draws=draws)
+        model.set_precision("bf16")
+        out = model.render(*a, draws=draws, z_vals_override=ref.z_vals)
+        free = model.render(*a, draws=draws)
+    N = 128
+    dn = (out.coarse_normals - ref.coarse_normals).abs()
+    dc = (out.coarse_colors - ref.coarse_colors).abs()
+    print(f"render bf16 vs fp32: normals max {dn.max().item():.2e} mean {dn.mean().item():.2e} | colors max "
+          f"{dc.max().item():.2e} mean {dc.mean().item():.2e} | rgb max "
+          f"{(out.coarse_rgb_values - ref.coarse_rgb_values).abs().max().item():.2e} | depth max "
+          f"{(out.coarse_depth_map - ref.coarse_depth_map).abs().max().item():.2e}")
+    same = (free.z_vals == ref.z_vals).all(dim=1).float().mean().item()
+    print(f"fine-sample placement identical to the fp32 path on {100 * same:.1f}% of rays")
+    assert torch.equal(out.points_coarse, ref.points_coarse)
+    assert dn.max().item() <= 5e-3 and dc.max().item() <= 5e-3
+    assert (out.coarse_rgb_values - ref.coarse_rgb_values).abs().max().item() <= 5e-3
+    assert (out.coarse_depth_map - ref.coarse_depth_map).abs().max().item() <= 5e-3
+    assert out.ray_dirs.shape == (R * N, 3) and torch.equal(out.ray_dirs, ref.ray_dirs)
+
+
+def test_tc_render_on_the_bending_model_reports_errors(built_lib):
+    case, z = U.load_golden("full_perturb")
+    st = U.case_state(case, z)
+    model = U.make_model(case, st, DEV)
+    R = 512
+    uv, pose, K = U.S.synthetic_rays(R, seed=0, start=0, stride=797)
+    draws = U.S.synthetic_draws(R, 64, 64, seed=99)
+    a = (pose.to(DEV), uv.to(DEV), K.to(DEV), 0)
+    with torch.no_grad():
+        ref = model.render(*a, draws=draws)
+        model.set_precision("bf16")
+        out = model.render(*a, draws=draws, z_vals_override=ref.z_vals)
+    dr = (out.coarse_rgb_values - ref.coarse_rgb_values).abs()
+    dd = (out.coarse_depth_map - ref.coarse_depth_map).abs()
+    dn = (out.coarse_normals - ref.coarse_normals).abs()
+    print(f"bending model render bf16 vs fp32: normals mean {dn.mean().item():.2e} max {dn.max().item():.2e} | rgb median "
+          f"{dr.median().item():.2e} max {dr.max().item():.2e} | depth median {dd.median().item():.2e} max {dd.max().item():.2e}")
+    assert torch.isfinite(out.coarse_rgb_values).all() and dr.median().item() <= 5e-2
+
+
+def test_tc_grid_query_matches_fp32_grid_query(built_lib):
+    from vfnerf_b200.grid_query import grid_query
+    case, z = U.load_golden("full_det")
+    model = U.make_model(case, _tame_state(), DEV)
+    res = 40
+    tr, ce = torch.tensor([0.5, -0.5, 0.5]), torch.tensor([0.1, 0.0, -0.2])
+    ref = grid_query(model.vector_field_network, res, 1.0, tr, ce)
+    model.set_precision("bf16")
+    out = grid_query(model.vector_field_network, res, 1.0, tr, ce, chunk=10000)
+    slab = grid_query(model.vector_field_network, res, 1.0, tr, ce, i0=res * res * 7, n_points=res * res * 3)
+    assert (out - ref).abs().max().item() <= 5e-3
+    assert torch.equal(slab, out[res * res * 7: res * res * 10])      # z-slab partition == slice of the whole grid

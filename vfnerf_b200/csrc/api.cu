@@ -236,9 +236,10 @@ static int make_plan(const vfnerf_render_cfg& cfg, const vfnerf_mlp_desc& vf, co
   p.directions = c.f(3 * p.R); p.ray_dirs = c.f(3 * p.R); p.cam_loc = c.f(3 * p.R);
   p.z_c = c.f(p.Pc); p.pts_c = c.f(3 * p.Pc); p.normals_c = c.f(3 * p.Pc); p.w_c = c.f(p.Pc);
   p.weights = c.f(p.P);
-  p.cin = c.f(p.P * p.cin_ld);
+  p.cin = nullptr;
   p.d_out = nullptr; p.d_colors = nullptr;
   if (cfg.precision == VFNERF_PREC_FP32) {
+    p.cin = c.f(p.P * p.cin_ld);
     p.emb = c.f(p.P * p.E);
     carve_mlp(c, vf, p.P, p.vf);
     carve_mlp(c, rn, p.P, p.rn);
@@ -248,7 +249,9 @@ static int make_plan(const vfnerf_render_cfg& cfg, const vfnerf_mlp_desc& vf, co
       p.d_colors = c.f(3 * p.P);
     }
   } else {
-    if (int e = tc_carve(c.base, c.off, cfg, vf, rn, p.P, keep, p.tc)) return e;
+    VFN_REQUIRE(cfg.precision == VFNERF_PREC_BF16, "precision bf16x3 is not built yet; use fp32 or bf16");
+    VFN_REQUIRE(!keep, "the tensor-core path has no backward yet: train with precision fp32");
+    if (int e = tc_carve(c.base, c.off, cfg.multires, cfg.multires_view, cfg.skip_layer, vf, &rn, p.tc)) return e;
   }
   p.bytes = c.off;
   return 0;
@@ -312,9 +315,10 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
       if (int e = vf_forward_fp32(*vf, vf_arena, p.vf, cfg->skip_layer, p.emb, p.Pc, p.normals_c, 3, 3, s)) return e;
     }
   } else {
-    if (int e = tc_prepare(*cfg, *vf, vf_arena, *rn, rn_arena, p.tc, s)) return e;
+    if (int e = tc_prepare(*vf, vf_arena, rn, rn_arena, cfg->bn_eps, p.tc, s)) return e;
     if (!z_override)
-      if (int e = tc_vf_forward(*cfg, p.tc, p.pts_c, p.Pc, p.normals_c, 3, 3, nullptr, 0, s)) return e;
+      if (int e = tc_forward(p.tc, TC_MODE_V_ONLY, p.pts_c, nullptr, 0, 0, p.Pc, nullptr, 0, p.normals_c, 3,
+                             nullptr, 0, nullptr, s)) return e;
   }
   if (!z_override) {
     if (int e = launch_density_weights(*cfg, p.R, p.Nc, density_params, p.normals_c, 3, p.ray_dirs, z_c,
@@ -324,22 +328,25 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
   if (int e = launch_fine_sample(p.R, p.Nc, p.Nf, cfg->near_, cfg->far_, cfg->fine_range, cfg->perturb, z_c, w_c,
                                  U2, U3, z_override, p.directions, p.cam_loc, out->z_vals, out->points, s)) return e;
   // ---- merged pass
-  if (int e = launch_color_input_head(out->points, p.ray_dirs, p.R, p.N, cfg->multires_view, p.cin, p.cin_ld,
-                                      out->ray_dirs_rep, s)) return e;
-  float* vf_out = p.cin + 3 + p.Ev;      // [v(3), feat(F)] written in place into the colour-net input
   if (cfg->precision == VFNERF_PREC_FP32) {
+    if (int e = launch_color_input_head(out->points, p.ray_dirs, p.R, p.N, cfg->multires_view, p.cin, p.cin_ld,
+                                        out->ray_dirs_rep, s)) return e;
+    float* vf_out = p.cin + 3 + p.Ev;      // [v(3), feat(F)] written in place into the colour-net input
     if (int e = vf_embed_fp32(*vf, p.vf, cfg->multires, cfg->skip_layer, out->points, p.P, p.emb, s)) return e;
     if (int e = vf_forward_fp32(*vf, vf_arena, p.vf, cfg->skip_layer, p.emb, p.P, vf_out, p.cin_ld, 3 + p.F, s)) return e;
-  } else {
-    if (int e = tc_vf_forward(*cfg, p.tc, out->points, p.P, vf_out, p.cin_ld, 3 + p.F, nullptr, keep_for_backward, s)) return e;
-  }
-  if (int e = launch_copy_cols(vf_out, p.cin_ld, out->normals, 3, p.P, 3, s)) return e;
-  if (int e = launch_density_weights(*cfg, p.R, p.N, density_params, vf_out, p.cin_ld, p.ray_dirs, out->z_vals,
-                                     nullptr, nullptr, weights, s)) return e;
-  if (cfg->precision == VFNERF_PREC_FP32) {
+    if (int e = launch_copy_cols(vf_out, p.cin_ld, out->normals, 3, p.P, 3, s)) return e;
+    if (int e = launch_density_weights(*cfg, p.R, p.N, density_params, vf_out, p.cin_ld, p.ray_dirs, out->z_vals,
+                                       nullptr, nullptr, weights, s)) return e;
     if (int e = rn_forward_fp32(*rn, rn_arena, p.rn, p.cin, p.cin_ld, p.P, out->colors, s)) return e;
   } else {
-    if (int e = tc_rn_forward(*cfg, p.tc, p.cin, p.cin_ld, p.P, out->colors, keep_for_backward, s)) return e;
+    // one fused tcgen05 launch: VF MLP -> normals, colour MLP -> colours (features stay on chip)
+    if (out->ray_dirs_rep)
+      if (int e = launch_color_input_head(out->points, p.ray_dirs, p.R, p.N, cfg->multires_view, nullptr, 0,
+                                          out->ray_dirs_rep, s)) return e;
+    if (int e = tc_forward(p.tc, TC_MODE_RENDER, out->points, nullptr, 0, 0, p.P, p.ray_dirs, p.N, out->normals, 3,
+                           nullptr, 0, out->colors, s)) return e;
+    if (int e = launch_density_weights(*cfg, p.R, p.N, density_params, out->normals, 3, p.ray_dirs, out->z_vals,
+                                       nullptr, nullptr, weights, s)) return e;
   }
   if (int e = launch_composite(p.R, p.N, weights, out->colors, out->z_vals, out->rgb, out->depth, s)) return e;
   return 0;
@@ -404,10 +411,25 @@ static void make_vf_plan(const vfnerf_mlp_desc& vf, int64_t n, int multires, int
   p.bytes = c.off;
 }
 
+static int vf_tc_plan(const vfnerf_mlp_desc& vf, int multires, int skip_layer, void* ws, TcPlan& plan, int64_t& bytes) {
+  int64_t off = 0;
+  if (int e = tc_carve(reinterpret_cast<char*>(ws), off, multires, 0, skip_layer, vf, nullptr, plan)) return e;
+  bytes = off;
+  return 0;
+}
+
 int64_t vfnerf_vf_workspace_bytes(const vfnerf_mlp_desc* vf, int64_t n_points, int multires,
                                   int keep_for_backward, int precision) {
   if (!vf) { set_error("null argument"); return -1; }
-  if (precision != VFNERF_PREC_FP32) return tc_vf_workspace_bytes(*vf, n_points, multires, keep_for_backward, precision);
+  if (precision != VFNERF_PREC_FP32) {
+    if (precision != VFNERF_PREC_BF16 || keep_for_backward) { set_error("vf query: only fp32 (with backward) and bf16 (forward) are built"); return -1; }
+    TcPlan plan;
+    int64_t bytes = 0;
+    int skip = -1;
+    for (int l = 1; l < vf->n_layers; ++l) if (vf->in_dim[l] != vf->out_dim[l - 1]) skip = l;
+    if (vf_tc_plan(*vf, multires, skip, nullptr, plan, bytes)) return -1;
+    return bytes + 1024;
+  }
   VfPlan p;
   make_vf_plan(*vf, n_points, multires, keep_for_backward, 1, nullptr, p);
   return p.bytes + 256;
@@ -422,9 +444,18 @@ int vfnerf_vf_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
   VFN_REQUIRE(n_out_cols >= 1 && n_out_cols <= vf->out_dim[vf->n_layers - 1], "vf_fwd: n_out_cols=%d invalid", n_out_cols);
   if (n_points == 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (precision != VFNERF_PREC_FP32)
-    return tc_vf_query(*vf, vf_arena, multires, skip_layer, bn_eps, precision, points, n_points, out, out_ld,
-                       n_out_cols, workspace, workspace_bytes, s);
+  if (precision != VFNERF_PREC_FP32) {
+    VFN_REQUIRE(precision == VFNERF_PREC_BF16 && !keep_for_backward, "vf_fwd: only fp32 (with backward) and bf16 (forward) are built");
+    VFN_REQUIRE(n_out_cols == 3 || n_out_cols == vf->out_dim[vf->n_layers - 1], "vf_fwd(bf16): n_out_cols must be 3 or all");
+    TcPlan plan;
+    int64_t bytes = 0;
+    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes)) return e;
+    VFN_REQUIRE(workspace && workspace_bytes >= bytes, "vf_fwd: workspace too small");
+    if (int e = tc_prepare(*vf, vf_arena, nullptr, nullptr, bn_eps, plan, s)) return e;
+    const bool full = n_out_cols > 3;
+    return tc_forward(plan, full ? TC_MODE_VF_FULL : TC_MODE_V_ONLY, points, nullptr, 0, 0, n_points, nullptr, 0, out,
+                      out_ld, full ? out + 3 : nullptr, out_ld, nullptr, s);
+  }
   VfPlan p;
   make_vf_plan(*vf, n_points, multires, keep_for_backward, 1, workspace, p);
   VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "vf_fwd: workspace %lld B < required %lld B",
@@ -467,9 +498,15 @@ int vfnerf_vf_grid_query(const vfnerf_mlp_desc* vf, const float* vf_arena, int m
   GridSpec gs;
   for (int c = 0; c < 3; ++c) { gs.origin[c] = origin3_host[c]; gs.translation[c] = translation3_host[c]; gs.centroid[c] = centroid3_host[c]; }
   gs.voxel = voxel;
-  if (precision != VFNERF_PREC_FP32)
-    return tc_vf_grid_query(*vf, vf_arena, multires, skip_layer, bn_eps, precision, res, i0, n_points, gs, out,
-                            workspace, workspace_bytes, s);
+  if (precision != VFNERF_PREC_FP32) {
+    VFN_REQUIRE(precision == VFNERF_PREC_BF16, "grid_query: only fp32 and bf16 are built");
+    TcPlan plan;
+    int64_t bytes = 0;
+    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes)) return e;
+    VFN_REQUIRE(workspace && workspace_bytes >= bytes, "grid_query: workspace too small");
+    if (int e = tc_prepare(*vf, vf_arena, nullptr, nullptr, bn_eps, plan, s)) return e;
+    return tc_forward(plan, TC_MODE_V_ONLY, nullptr, &gs, res, i0, n_points, nullptr, 0, out, 3, nullptr, 0, nullptr, s);
+  }
   VfPlan p;
   make_vf_plan(*vf, n_points, multires, 0, 1, workspace, p);
   VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "grid_query: workspace %lld B < required %lld B",

@@ -185,14 +185,18 @@ __global__ void color_input_head_kernel(const float* __restrict__ points, const 
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int64_t r = i / N;
-  float* o = cin + i * ld;
   float d[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    o[c] = points[3 * i + c];
     d[c] = __ldg(ray_dirs + 3 * r + c);
-    o[3 + c] = d[c];
     if (rep) rep[3 * i + c] = d[c];
+  }
+  if (!cin) return;
+  float* o = cin + i * ld;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o[c] = points[3 * i + c];
+    o[3 + c] = d[c];
   }
   float f = 1.f;
   for (int k = 0; k < mv; ++k) {
