@@ -2,18 +2,21 @@
 // layers with skip -> tanh) and, in RENDER mode, the colour MLP (5 layers -> sigmoid) evaluated for a
 // tile of 128 points entirely on chip.  SURVEY.md §8 rows a3 + a8.
 //
-// Per CTA (192 threads, 2 CTAs per SM so one CTA's epilogue overlaps the other's MMAs):
-//   warp 0      weight producer: one lane streams pre-tiled bf16 weight chunks (<= 16 KiB) from L2 into a
-//               shared-memory ring with cp.async.bulk, completion on mbarriers            (SASS UBLKCP)
-//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N<=256, K=16, bf16 x bf16 -> fp32 in TMEM),
-//               tcgen05.commit releases ring slots and publishes the accumulator          (SASS UTCHMMA)
-//   warps 2..5  epilogue: tcgen05.ld the 128 x N fp32 accumulator (one row per thread), add the folded
-//               BatchNorm shift (the scale is folded into the weights), ReLU / tanh / sigmoid, convert to
-//               bf16 and write the NEXT layer's A operand straight into the activation tile in the K-slab
-//               UMMA layout (tc_common.cuh) -- activations never leave the SM.
-// Activation tile: 128 x 256 bf16 (64 KiB) [+ 48 aux columns holding the colour net's small inputs].
-// Weights: 1.1 MB (VF) + 0.6 MB (colour) bf16, L2 resident, re-streamed per tile: 128 KiB per 256x256
-// layer per tile = 64 B/clk/SM at full tensor rate (DESIGN.md discusses this limiter).
+// One CTA per SM, 320 threads:
+//   warp 0      weight producer: one lane streams pre-tiled bf16 weight chunks (<= 32 KiB) from L2 into a
+//               4-slot shared-memory ring with cp.async.bulk, completion on mbarriers      (SASS UBLKCP)
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N<=256, K=16, bf16 x bf16 -> fp32 in TMEM);
+//               tcgen05.commit releases ring slots and publishes the accumulator           (SASS UTCHMMA)
+//   warps 2..9  epilogue: tcgen05.ld the fp32 accumulator (one row per thread, 32 columns at a time),
+//               convert to bf16x2, ReLU / tanh on the packed pair, and write the NEXT layer's A operand
+//               straight into the activation tile in the K-slab UMMA layout -- activations never leave
+//               the SM.  The folded BatchNorm scale lives in the weights and the shift is a (hi, lo) bias
+//               row multiplied by a constant ones-column of A, so the epilogue has no per-channel operand.
+// Overlap inside the CTA: two 256-column TMEM accumulators (step s uses buffer s&1) and one "ready"
+// mbarrier per 32-column group of the activation tile; the MMAs of layer l+1 start on K chunk g as soon as
+// group g of layer l's output is in shared memory, so they trail the epilogue by about one chunk.
+// Weights: 1.1 MB (VF) + 0.6 MB (colour) bf16, L2 resident, re-streamed per tile.
+#include <cstdlib>
 #include "mlp_tc.cuh"
 #include "tc_common.cuh"
 
@@ -21,15 +24,17 @@ namespace vfn {
 using namespace tc;
 
 constexpr int kTileM = 128;
-constexpr int kStageBytes = 16384;
-constexpr int kTcThreads = 192;
+constexpr int kStageBytes = 32768;
+constexpr int kTcStages = 4;
+constexpr int kTcThreads = 320;
 constexpr int kAccCols = 256;
 constexpr float kInvSqrt2 = 0.70710678118654752f;
+// readiness barriers: 0..7 = 32-column groups of the main region, 8 = aux region, 9 = skip region
+constexpr int kGroups = 10, kBarAux = 8, kBarSkip = 9;
 
 struct TcParams {
   TcProgram prog;
   const uint8_t* wpack;
-  const float* affine;
   const float* points;
   int use_grid;
   GridSpec grid;
@@ -41,55 +46,55 @@ struct TcParams {
   float* out_v; long long v_ld;
   float* out_feat; long long feat_ld;
   float* colors;
+  long long* dbg_buf;   // VFNERF_TC_DBG=64: cycle counters of CTA 0 (MMA thread [0..2], epilogue warp 2 [8..12], warp 3 [16..20])
 };
 
 // ---------------------------------------------------------------------------------------------
-// weight packing: fp32 Linear weights (+ folded BatchNorm scale) -> bf16 K-slab images, one per step
+// weight packing: fp32 Linear weights (+ folded BatchNorm scale, + the bias row) -> bf16 K-slab images
 // ---------------------------------------------------------------------------------------------
 __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* __restrict__ vf_arena,
                                vfnerf_mlp_desc rn, const float* __restrict__ rn_arena, float eps,
-                               uint8_t* __restrict__ wpack, float* __restrict__ affine) {
+                               uint8_t* __restrict__ wpack) {
   const TcStep st = prog.s[blockIdx.y];
   const vfnerf_mlp_desc& d = st.net == 0 ? vf : rn;
   const float* arena = st.net == 0 ? vf_arena : rn_arena;
   const int l = st.layer, in_dim = d.in_dim[l];
   const bool bn = d.gamma_off[l] >= 0;
+  const int E = prog.emb_w, Epad = prog.emb_pad;
   const int total = st.N * st.K;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int n = e / st.K, k = e - n * st.K;
+    // locate (segment, column in segment) and the byte offset of the chunk that holds column k
+    int sg = 0, kin = k;
+    int64_t base = st.w_off;
+    while (kin >= st.seg_k[sg]) { kin -= st.seg_k[sg]; base += (int64_t)st.N * st.seg_k[sg] * 2; ++sg; }
+    const int64_t off = base + (int64_t)(kin / st.chunk_k) * st.N * st.chunk_k * 2 +
+                        (int64_t)((kin % st.chunk_k) / 8) * st.N * 16 + n * 16 + (kin & 7) * 2;
     float w = 0.f;
     if (n < st.n_valid) {
-      int src = -1;
-      if (st.colmap == 0) src = k;
-      else if (st.colmap == 1) src = (k < st.dup_w) ? k : k - st.dup_w;
-      else src = (k < 256) ? st.dup_w + k : k - 256;
-      if (st.colmap == 2 && k >= 256 && src >= st.dup_w) src = -1;
-      if (src >= 0 && src < in_dim) {
-        const int row = st.row0 + n;
-        float sc = 1.f;
-        if (bn) sc = arena[d.gamma_off[l] + row] / sqrtf(arena[d.var_off[l] + row] + eps);
-        w = arena[d.w_off[l] + (int64_t)row * in_dim + src] * sc * st.post_scale;
-      }
-    }
-    const int64_t off = st.w_off + (int64_t)(k / st.chunk_k) * st.N * st.chunk_k * 2 +
-                        (int64_t)((k % st.chunk_k) / 8) * st.N * 16 + n * 16 + (k & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(wpack + off) = __float2bfloat16(w);
-  }
-  if (blockIdx.x == 0) {
-    for (int n = threadIdx.x; n < 256; n += blockDim.x) {
-      float sh = 0.f;
-      if (n < st.n_valid) {
-        const int row = st.row0 + n;
-        const float b = arena[d.b_off[l] + row];
-        sh = b;
-        if (bn) {
-          const float sc = arena[d.gamma_off[l] + row] / sqrtf(arena[d.var_off[l] + row] + eps);
-          sh = arena[d.beta_off[l] + row] + (b - arena[d.mean_off[l] + row]) * sc;
+      const int row = st.row0 + n;
+      float sc = 1.f;
+      if (bn) sc = arena[d.gamma_off[l] + row] / sqrtf(arena[d.var_off[l] + row] + eps);
+      if (sg == st.n_seg - 1) {
+        // bias row: folded shift as a bf16 (hi, lo) pair in columns 0 and 1
+        if (kin < 2) {
+          const float b = arena[d.b_off[l] + row];
+          float sh = b;
+          if (bn) sh = arena[d.beta_off[l] + row] + (b - arena[d.mean_off[l] + row]) * sc;
+          sh *= st.post_scale;
+          const float hi = __bfloat162float(__float2bfloat16(sh));
+          w = kin == 0 ? hi : sh - hi;
         }
-        sh *= st.post_scale;
+      } else {
+        int src = -1;
+        if (st.colmap == 0) src = kin;
+        else if (st.colmap == 1) { src = kin < Epad ? kin : kin - Epad; if (src >= E) src = -1; }
+        else if (st.colmap == 2) src = sg == 0 ? st.src_split + kin : (kin < st.src_split ? kin : -1);
+        else src = sg == 0 ? (kin < st.src_split ? kin : -1) : (kin < E ? st.src_split + kin : -1);
+        if (src >= 0 && src < in_dim) w = arena[d.w_off[l] + (int64_t)row * in_dim + src] * sc * st.post_scale;
       }
-      affine[st.aff_off + n] = sh;
     }
+    *reinterpret_cast<__nv_bfloat16*>(wpack + off) = __float2bfloat16(w);
   }
 }
 
@@ -101,55 +106,106 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(y) : "r"(x), "r"(0u));
+  return y;
+}
 
 // 8 consecutive columns of one row -> one 16-byte store into slab `slab` of the activation tile
-__device__ __forceinline__ void store_slab(uint8_t* s_act, int slab, int row, const float* f) {
+__device__ __forceinline__ void store_slab_f(uint8_t* s_act, int slab, int row, const float* f) {
   uint4 u;
   u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
   u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
   *reinterpret_cast<uint4*>(s_act + slab * (kTileM * 16) + row * 16) = u;
 }
+__device__ __forceinline__ void store_slab_u(uint8_t* s_act, int slab, int row, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  *reinterpret_cast<uint4*>(s_act + slab * (kTileM * 16) + row * 16) = make_uint4(a, b, c, d);
+}
 
-// positional encoding of embedder.py:11-37 into e[0 .. 3+6*L)
+// positional encoding of embedder.py:11-37 into e[0 .. 3+6*L).  sin/cos of the base frequency come from
+// sincosf; the octaves above it use the double-angle recurrence (error doubles per octave: <= 4e-6 at 2^5,
+// far below the bf16 quantisation this path feeds).  Fully unrolled so e[] stays in registers.
+constexpr int kMaxRes = 7;
 __device__ __forceinline__ void embed3(const float* p, int L, float* e) {
-  e[0] = p[0]; e[1] = p[1]; e[2] = p[2];
-  float f = 1.f;
-  for (int k = 0; k < L; ++k) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float sv, cv;
-      sincosf(p[c] * f, &sv, &cv);
-      e[3 + 6 * k + c] = sv;
-      e[6 + 6 * k + c] = cv;
+  for (int c = 0; c < 3; ++c) {
+    e[c] = p[c];
+    float sv, cv;
+    sincosf(p[c], &sv, &cv);
+#pragma unroll
+    for (int k = 0; k < kMaxRes; ++k) {
+      if (k < L) {
+        e[3 + 6 * k + c] = sv;
+        e[6 + 6 * k + c] = cv;
+        const float s2 = 2.f * sv * cv, c2 = cv * cv - sv * sv;
+        sv = s2; cv = c2;
+      }
     }
-    f *= 2.f;
   }
 }
+
+__device__ __forceinline__ void load_point(const TcParams& p, long long pi, bool valid, float* pt) {
+  pt[0] = pt[1] = pt[2] = 0.f;
+  if (!valid) return;
+  if (p.use_grid) {
+    const long long g = p.grid_i0 + pi;
+    const long long res = p.grid_res;
+    const long long idx[3] = {(g / res / res) % res, (g / res) % res, g % res};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = __fadd_rn(__fmul_rn((float)idx[c], p.grid.voxel), p.grid.origin[c]);
+      v = __fadd_rn(v, p.grid.translation[c]);
+      pt[c] = __fadd_rn(v, p.grid.centroid[c]);
+    }
+  } else {
+    pt[0] = p.points[3 * pi]; pt[1] = p.points[3 * pi + 1]; pt[2] = p.points[3 * pi + 2];
+  }
+}
+
+// readiness barrier that guards activation-tile column `col` (-1: constant region, nothing to wait for)
+__device__ __forceinline__ int col_barrier(int col) {
+  return col < kColAux ? (col >> 5) : (col < kColSkip ? kBarAux : (col < kColOnes ? kBarSkip : -1));
+}
+
+#define TCK(acc_) do { if (prof) { long long t1_ = clock64(); acc_ += t1_ - t0; t0 = t1_; } } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
-template <int NSTAGE>
-__global__ void __launch_bounds__(kTcThreads, 2) mlp_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcProgram& prog = p.prog;
   uint8_t* s_act = smem;
-  uint8_t* s_stage = smem + prog.act_cols * (kTileM * 2);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + NSTAGE * kStageBytes);
+  uint8_t* s_stage = smem + kActCols * (kTileM * 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kTcStages * kStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + NSTAGE;
-  uint64_t* acc_full = bars + 2 * NSTAGE;
-  uint64_t* act_ready = acc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 1);
+  uint64_t* empty = bars + kTcStages;
+  uint64_t* acc_full = bars + 2 * kTcStages;
+  uint64_t* grp = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(grp + kGroups);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kTcStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(act_ready, 128);
+    for (int i = 0; i < kGroups; ++i) mbar_init(&grp[i], 128);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kAccCols>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kTileM) {
+    // constant ones-columns [1, 1, 0, ...] that pick up the bias row of every weight image
+    const int r = threadIdx.x - 64;
+    store_slab_u(s_act, kColOnes / 8, r, 0x3F803F80u, 0u, 0u, 0u);
+    store_slab_u(s_act, kColOnes / 8 + 1, r, 0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -164,14 +220,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) mlp_tc_kernel(const __grid_cons
         for (int si = 0; si < prog.n_steps; ++si) {
           const TcStep& st = prog.s[si];
           const uint8_t* src = p.wpack + st.w_off;
-          const int full_bytes = st.N * st.chunk_k * 2;
-          for (int c = 0; c < st.n_chunks; ++c) {
-            const int kc = min(st.chunk_k, st.K - c * st.chunk_k);
-            const uint32_t bytes = (uint32_t)(st.N * kc * 2);
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], bytes);
-            bulk_g2s(s_stage + stage * kStageBytes, src + (int64_t)c * full_bytes, bytes, &full[stage]);
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          for (int sg = 0; sg < st.n_seg; ++sg) {
+            for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
+              const int kc = min(st.chunk_k, st.seg_k[sg] - k0);
+              const uint32_t bytes = (uint32_t)(st.N * kc * 2);
+              mbar_wait(&empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full[stage], bytes);
+              bulk_g2s(s_stage + stage * kStageBytes, src, bytes, &full[stage]);
+              src += bytes;
+              if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -179,197 +237,281 @@ __global__ void __launch_bounds__(kTcThreads, 2) mlp_tc_kernel(const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int stage = 0, phase = 0, par_act = 0;
+      int stage = 0, phase = 0;
+      uint32_t grp_par = 0, gstep = 0;
+      long long t_grp = 0, t_full = 0, t_issue = 0, t0 = 0;
+      const bool prof = p.dbg_buf && blockIdx.x == 0;
+      if (prof) t0 = clock64();
       const uint32_t act_base = smem_u32(s_act), stage_base = smem_u32(s_stage);
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int si = 0; si < prog.n_steps; ++si) {
+      int tile_no = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_no) {
+        const bool tl = prof && tile_no == 2;
+        for (int si = 0; si < prog.n_steps; ++si, ++gstep) {
           const TcStep& st = prog.s[si];
+          bool first_mma = true;
           const uint32_t idesc = make_idesc_bf16(kTileM, st.N);
-          const uint32_t b_lbo = st.N * 16;
-          mbar_wait(act_ready, par_act);
-          par_act ^= 1;
-          tc_fence_after_sync();
+          // descriptor halves: only the start-address field of the low words changes between MMAs
+          const uint32_t desc_hi = (128u >> 4) | (1u << 14);                   // SBO = 128 B, version 1
+          const uint32_t a_lo0 = ((act_base >> 4) & 0x3FFF) | (((kTileM * 16u) >> 4) << 16);
+          const uint32_t b_lo0 = ((stage_base >> 4) & 0x3FFF) | ((((uint32_t)st.N * 16u) >> 4) << 16);
+          const uint32_t b_kstep = 2u * (uint32_t)st.N;                        // two K-slabs of the weight chunk, in 16-byte units
+          const uint32_t acc = tmem + (gstep & 1) * kAccCols;
+          uint32_t fresh = (uint32_t)st.fresh_mask;
           uint32_t accumulate = 0;
-          for (int c = 0; c < st.n_chunks; ++c) {
-            const int k0 = c * st.chunk_k;
-            const int kc = min(st.chunk_k, st.K - k0);
-            mbar_wait(&full[stage], phase);
-            tc_fence_after_sync();
-            for (int kk = 0; kk < kc; kk += 16) {
-              const uint32_t a_addr = act_base + ((st.a_col0 + k0 + kk) >> 3) * (kTileM * 16);
-              const uint32_t b_addr = stage_base + stage * kStageBytes + (kk >> 3) * b_lbo;
-              umma_bf16(tmem, make_smem_desc(a_addr, kTileM * 16, 128), make_smem_desc(b_addr, b_lbo, 128), idesc,
-                        accumulate);
-              accumulate = 1;
+          TCK(t_issue);
+          for (int g = 0; g < kGroups; ++g) {
+            if (st.pre_wait_mask & (1 << g)) {
+              mbar_wait(&grp[g], (grp_par >> g) & 1u);
+              grp_par ^= (1u << g);
             }
-            umma_commit(&empty[stage]);          // ring slot reusable once these MMAs have read it
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          umma_commit(acc_full);                 // accumulator complete -> epilogue
+          for (int sg = 0; sg < st.n_seg; ++sg) {
+            for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
+              const int kc = min(st.chunk_k, st.seg_k[sg] - k0);
+              const int col = st.seg_col0[sg] + k0;
+              // the A columns of this chunk must have been (re)written: wait for their readiness barriers
+              if (fresh) {
+                const int b0 = col_barrier(col), b1 = col_barrier(col + kc - 1);
+                for (int b = b0; b >= 0 && b <= b1; ++b) {
+                  if (fresh & (1u << b)) {
+                    mbar_wait(&grp[b], (grp_par >> b) & 1u);
+                    grp_par ^= (1u << b);
+                    fresh &= ~(1u << b);
+                  }
+                }
+              }
+              TCK(t_grp);
+              mbar_wait(&full[stage], phase);
+              TCK(t_full);
+              tc_fence_after_sync();
+              uint32_t a_lo = a_lo0 + (uint32_t)(col >> 3) * ((kTileM * 16u) >> 4);
+              uint32_t b_lo = b_lo0 + (uint32_t)stage * (kStageBytes >> 4);
+              if (tl && first_mma) { p.dbg_buf[64 + si * 8 + 0] = clock64(); first_mma = false; }
+              for (int kk = 0; kk < kc; kk += 16) {
+                umma_bf16_split(acc, a_lo, desc_hi, b_lo, desc_hi, idesc, accumulate);
+                accumulate = 1;
+                a_lo += 2u * ((kTileM * 16u) >> 4);
+                b_lo += b_kstep;
+              }
+              umma_commit(&empty[stage]);          // ring slot reusable once these MMAs have read it
+              if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          umma_commit(acc_full);                   // accumulator complete -> epilogue
+          if (tl) p.dbg_buf[64 + si * 8 + 1] = clock64();
         }
       }
+      TCK(t_issue);
+      if (prof) { p.dbg_buf[0] = t_grp; p.dbg_buf[1] = t_full; p.dbg_buf[2] = t_issue; }
     }
   } else {
-    // ===================== epilogue warps (one row per thread) =====================
-    const int q = warp & 3;
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access (hardware: warp % 4)
+    const int h = (warp - 2) >> 2;          // column-group parity: this warp owns groups g with g % 2 == h
     const int row = q * 32 + lane;
-    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int E = prog.emb_w, Epad = prog.emb_pad;
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const bool render = prog.render != 0;
+    uint32_t gstep = 0;
+    long long t_acc = 0, t_ld = 0, t_math = 0, t_sig = 0, t_other = 0, t0 = 0;
+    const bool prof = p.dbg_buf && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 3);
+    if (prof) t0 = clock64();
+
+    // A operand of step 0 (half-0 warps: bf16 hi/lo split of the embedding -> main columns [0, 2*Epad)) and the skip
+    // layer's extra input (half-1 warps: embedding / sqrt(2) -> skip columns).  Both are computed for the NEXT tile
+    // while this tile's MMAs run: half 1 stores right away (the skip columns are free once the skip step's MMAs
+    // are done), half 0 parks the packed values in registers and stores them during the last step.
+    uint32_t pk0[48];
+    auto embed_tile = [&](long long tile, float* emb) {
       const long long pi = tile * kTileM + row;
-      const bool valid = pi < p.n_points;
-      float pt[3] = {0.f, 0.f, 0.f};
-      if (valid) {
-        if (p.use_grid) {
-          const long long g = p.grid_i0 + pi;
-          const long long res = p.grid_res;
-          const long long idx[3] = {(g / res / res) % res, (g / res) % res, g % res};
+      float pt[3];
+      load_point(p, pi, pi < p.n_points, pt);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float v = __fadd_rn(__fmul_rn((float)idx[c], p.grid.voxel), p.grid.origin[c]);
-            v = __fadd_rn(v, p.grid.translation[c]);
-            pt[c] = __fadd_rn(v, p.grid.centroid[c]);
-          }
-        } else {
-          pt[0] = p.points[3 * pi]; pt[1] = p.points[3 * pi + 1]; pt[2] = p.points[3 * pi + 2];
-        }
-      }
-      // ---- prologue: positional encoding as a bf16 hi/lo pair -> A columns [0, 2*Epad)
-      float emb[48];
+      for (int i = 0; i < 48; ++i) emb[i] = 0.f;
       embed3(pt, prog.multires, emb);
-      for (int i = E; i < 48; ++i) emb[i] = 0.f;
-      {
-        const int nsl = Epad >> 3;
-        for (int sl = 0; sl < nsl; ++sl) {
-          float hi[8], lo[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float v = emb[sl * 8 + j];
-            hi[j] = __bfloat162float(__float2bfloat16(v));
-            lo[j] = v - hi[j];
-          }
-          store_slab(s_act, sl, row, hi);
-          store_slab(s_act, nsl + sl, row, lo);
+      for (int i = 0; i < 48; ++i)
+        if (i >= E) emb[i] = 0.f;
+    };
+    auto prologue_compute = [&](long long tile) {        // half 0
+      float emb[48];
+      embed_tile(tile, emb);
+#pragma unroll
+      for (int j = 0; j < 24; ++j) {
+        const float a = emb[2 * j], b = emb[2 * j + 1];
+        const float ah = __bfloat162float(__float2bfloat16(a)), bh = __bfloat162float(__float2bfloat16(b));
+        pk0[j] = pack_bf16x2(ah, bh);
+        pk0[24 + j] = pack_bf16x2(a - ah, b - bh);
+      }
+    };
+    auto prologue_store = [&]() {                        // half 0
+      const int nsl = Epad >> 3;
+#pragma unroll
+      for (int sl = 0; sl < 6; ++sl) {
+        if (sl < nsl) {
+          store_slab_u(s_act, sl, row, pk0[4 * sl], pk0[4 * sl + 1], pk0[4 * sl + 2], pk0[4 * sl + 3]);
+          store_slab_u(s_act, nsl + sl, row, pk0[24 + 4 * sl], pk0[25 + 4 * sl], pk0[26 + 4 * sl], pk0[27 + 4 * sl]);
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(act_ready);
+      const int ng = (2 * Epad + 31) >> 5;
+      for (int g = 0; g < ng; ++g) mbar_arrive(&grp[g]);
+    };
+    auto prologue_skip = [&](long long tile) {           // half 1
+      float emb[48];
+      embed_tile(tile, emb);
+#pragma unroll
+      for (int i = 0; i < 48; ++i) emb[i] *= kInvSqrt2;
+#pragma unroll
+      for (int sl = 0; sl < 6; ++sl) store_slab_f(s_act, kColSkip / 8 + sl, row, emb + 8 * sl);
+      fence_proxy_async_smem();
+      mbar_arrive(&grp[kBarSkip]);
+    };
 
-      for (int si = 0; si < prog.n_steps; ++si) {
+    if ((long long)blockIdx.x < num_tiles) {
+      if (h == 0) { prologue_compute(blockIdx.x); prologue_store(); }
+      else if (prog.skip_step >= 0) prologue_skip(blockIdx.x);
+    }
+
+    int tile_no = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_no) {
+      const long long pi = tile * kTileM + row;
+      const bool valid = pi < p.n_points;
+      const bool tl = prof && tile_no == 2;
+      for (int si = 0; si < prog.n_steps; ++si, ++gstep) {
         const TcStep& st = prog.s[si];
-        const float4* sh4 = reinterpret_cast<const float4*>(p.affine + st.aff_off);
-        mbar_wait(acc_full, it & 1);
-        ++it;
+        const uint32_t acc = tmem + (gstep & 1) * kAccCols + lane_off;
+        TCK(t_other);
+        mbar_wait(acc_full, gstep & 1);
+        TCK(t_acc);
+        if (tl) p.dbg_buf[64 + si * 8 + 2 + 3 * h] = clock64();
         tc_fence_after_sync();
-        if (st.epi == TC_EPI_RELU || st.epi == TC_EPI_RELU_SKIPFILL) {
-          const bool fill = st.epi == TC_EPI_RELU_SKIPFILL;
-          for (int g = 0; g < 8; ++g) {
-            const int c0 = g * 32;
-            if (c0 >= st.N && !fill) break;
-            float f[32];
-            if (c0 < st.N) {
-              uint32_t v[32];
-              tmem_ld32(t_lane + c0, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 s4 = __ldg(sh4 + (c0 >> 2) + j4);
-                f[4 * j4 + 0] = fmaxf(__uint_as_float(v[4 * j4 + 0]) + s4.x, 0.f);
-                f[4 * j4 + 1] = fmaxf(__uint_as_float(v[4 * j4 + 1]) + s4.y, 0.f);
-                f[4 * j4 + 2] = fmaxf(__uint_as_float(v[4 * j4 + 2]) + s4.z, 0.f);
-                f[4 * j4 + 3] = fmaxf(__uint_as_float(v[4 * j4 + 3]) + s4.w, 0.f);
-              }
-            }
-            if (fill) {
-              // skip connection: columns >= n_valid of the next layer's input are emb / sqrt(2)
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int col = c0 + j;
-                if (col >= st.n_valid) f[j] = (col - st.n_valid < E) ? emb[col - st.n_valid] * kInvSqrt2 : 0.f;
-              }
-            }
-#pragma unroll
-            for (int sl = 0; sl < 4; ++sl) store_slab(s_act, (c0 >> 3) + sl, row, f + 8 * sl);
-          }
-          fence_proxy_async_smem();
-        } else if (st.epi == TC_EPI_V) {
-          uint32_t v[16];
-          tmem_ld16(t_lane, v);
-          tmem_ld_wait();
-          float nv[3];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) nv[j] = tanhf(__uint_as_float(v[j]) + __ldg(p.affine + st.aff_off + j));
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) p.out_v[pi * p.v_ld + j] = nv[j];
-          }
-          if (prog.act_cols > 256) {
-            // colour-net small inputs [p(3), embed(view dir)(3+6*Lv), n(3), 0...] -> aux columns 256..303
-            float a[48];
-#pragma unroll
-            for (int j = 0; j < 48; ++j) a[j] = 0.f;
-            a[0] = pt[0]; a[1] = pt[1]; a[2] = pt[2];
-            float d[3] = {0.f, 0.f, 0.f};
-            if (valid) {
-              const long long r = pi / p.samples_per_ray;
-              d[0] = __ldg(p.ray_dirs + 3 * r); d[1] = __ldg(p.ray_dirs + 3 * r + 1); d[2] = __ldg(p.ray_dirs + 3 * r + 2);
-            }
-            embed3(d, prog.multires_view, a + 3);
-            const int ev = 3 + 6 * prog.multires_view;
-            a[3 + ev] = nv[0]; a[4 + ev] = nv[1]; a[5 + ev] = nv[2];
-#pragma unroll
-            for (int sl = 0; sl < 6; ++sl) store_slab(s_act, 32 + sl, row, a + 8 * sl);
-            fence_proxy_async_smem();
-          }
-        } else if (st.epi == TC_EPI_FEAT) {
-          const bool to_act = prog.act_cols > 256;
-          for (int g = 0; g < 8; ++g) {
-            const int c0 = g * 32;
-            uint32_t v[32];
-            tmem_ld32(t_lane + c0, v);
+        if (st.epi == TC_EPI_RELU || st.epi == TC_EPI_FEAT) {
+          const bool feat = st.epi == TC_EPI_FEAT;
+          const bool to_act = !feat || render;
+          uint32_t v[32];
+          if (h * 32 < st.N) tmem_ld32(acc + h * 32, v);
+#pragma unroll 1
+          for (int gi = 0; gi < 4; ++gi) {
+            const int g = 2 * gi + h, c0 = g * 32;
+            if (c0 >= st.N) break;
+            TCK(t_other);
             tmem_ld_wait();
-            float f[32];
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 s4 = __ldg(sh4 + (c0 >> 2) + j4);
-              f[4 * j4 + 0] = tanh_fast(__uint_as_float(v[4 * j4 + 0]) + s4.x);
-              f[4 * j4 + 1] = tanh_fast(__uint_as_float(v[4 * j4 + 1]) + s4.y);
-              f[4 * j4 + 2] = tanh_fast(__uint_as_float(v[4 * j4 + 2]) + s4.z);
-              f[4 * j4 + 3] = tanh_fast(__uint_as_float(v[4 * j4 + 3]) + s4.w);
-            }
+            TCK(t_ld);
             if (to_act) {
+              uint32_t pk[16];
 #pragma unroll
-              for (int sl = 0; sl < 4; ++sl) store_slab(s_act, (c0 >> 3) + sl, row, f + 8 * sl);
-            }
-            if (p.out_feat && valid) {
-              float* o = p.out_feat + pi * p.feat_ld + c0;
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t b2 = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                pk[j] = feat ? tanh_bf16x2(b2) : relu_bf16x2(b2);
+              }
+              if (c0 + 64 < st.N) tmem_ld32(acc + c0 + 64, v);        // next group in flight behind the stores
 #pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] = f[j];
+              for (int sl = 0; sl < 4; ++sl)
+                store_slab_u(s_act, (c0 >> 3) + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+              TCK(t_math);
+              fence_proxy_async_smem();
+              tc_fence_before_sync();
+              mbar_arrive(&grp[g]);
+              TCK(t_sig);
+              if (tl && gi == 0) p.dbg_buf[64 + si * 8 + 3 + 3 * h] = clock64();
+              if (tl) p.dbg_buf[64 + si * 8 + 4 + 3 * h] = clock64();
+            } else {
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = tanh_fast(__uint_as_float(v[j]));
+              if (c0 + 64 < st.N) tmem_ld32(acc + c0 + 64, v);
+              if (p.out_feat && valid) {
+                float* o = p.out_feat + pi * p.feat_ld + c0;
+                if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                  for (int j4 = 0; j4 < 8; ++j4)
+                    reinterpret_cast<float4*>(o)[j4] = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) o[j] = f[j];
+                }
+              }
+              TCK(t_math);
             }
           }
-          if (to_act) fence_proxy_async_smem();
-        } else {  // TC_EPI_RGB
-          uint32_t v[16];
-          tmem_ld16(t_lane, v);
-          tmem_ld_wait();
-          if (valid) {
+        } else if (st.epi == TC_EPI_V) {
+          if (h == 0) {
+            uint32_t v[16];
+            tmem_ld16(acc, v);
+            tmem_ld_wait();
+            float nv[3];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const float x = __uint_as_float(v[j]) + __ldg(p.affine + st.aff_off + j);
-              p.colors[3 * pi + j] = 1.f / (1.f + expf(-x));
+            for (int j = 0; j < 3; ++j) nv[j] = tanhf(__uint_as_float(v[j]));
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 3; ++j) p.out_v[pi * p.v_ld + j] = nv[j];
+            }
+            if (render) {
+              // colour-net small inputs [p(3), embed(view dir)(3+6*Lv), n(3), 0...] -> aux columns
+              float a[48];
+#pragma unroll
+              for (int j = 0; j < 48; ++j) a[j] = 0.f;
+              float pt[3], d[3] = {0.f, 0.f, 0.f};
+              load_point(p, pi, valid, pt);
+              if (valid) {
+                const long long r = pi / p.samples_per_ray;
+                d[0] = __ldg(p.ray_dirs + 3 * r); d[1] = __ldg(p.ray_dirs + 3 * r + 1); d[2] = __ldg(p.ray_dirs + 3 * r + 2);
+              }
+              embed3(d, prog.multires_view, a + 3);
+              const int ev = 3 + 6 * prog.multires_view;
+#pragma unroll
+              for (int j = 0; j < 48; ++j) {
+                if (j < 3) a[j] = pt[j];
+                if (j >= 3 + ev) a[j] = 0.f;
+                if (j == 3 + ev) a[j] = nv[0];
+                if (j == 4 + ev) a[j] = nv[1];
+                if (j == 5 + ev) a[j] = nv[2];
+              }
+#pragma unroll
+              for (int sl = 0; sl < 6; ++sl) store_slab_f(s_act, kColAux / 8 + sl, row, a + 8 * sl);
+              fence_proxy_async_smem();
+              tc_fence_before_sync();
+              mbar_arrive(&grp[kBarAux]);
+            } else if (si + 1 < prog.n_steps) {
+              // VF_FULL: the FEAT step's MMAs do not depend on any A rewrite; this arrival orders them (and through
+              // them the next tile's first MMA into this accumulator buffer) after the read above
+              tc_fence_before_sync();
+              mbar_arrive(&grp[kBarAux]);
+            }
+          }
+        } else {  // TC_EPI_RGB
+          if (h == 0) {
+            uint32_t v[16];
+            tmem_ld16(acc, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 3; ++j) p.colors[3 * pi + j] = 1.f / (1.f + expf(-__uint_as_float(v[j])));
             }
           }
         }
-        // accumulator drained (and the next A operand written): release the MMA issuer
+        // next tile's prologue, off the critical path (see above)
+        if (tile + gridDim.x < num_tiles) {
+          if (h == 0) {
+            if (si == 0) prologue_compute(tile + gridDim.x);
+            if (si == prog.n_steps - 1) prologue_store();      // this step's MMAs have finished reading the A tile
+          } else if (si == prog.skip_step) {
+            prologue_skip(tile + gridDim.x);                    // the skip step's MMAs (the only readers) are done
+          }
+        }
         tc_fence_before_sync();
-        if (si + 1 < prog.n_steps) mbar_arrive(act_ready);
       }
+    }
+    TCK(t_other);
+    if (prof) {
+      long long* o = p.dbg_buf + (warp == 2 ? 8 : 16);
+      o[0] = t_acc; o[1] = t_ld; o[2] = t_math; o[3] = t_sig; o[4] = t_other;
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<kAccCols>(tmem);
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -381,8 +523,9 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
                           const vfnerf_mlp_desc* rn, TcPlan& plan) {
   const int E = 3 + 6 * multires, Epad = round16(E);
   const int L = vf.n_layers;
-  VFN_REQUIRE(Epad <= 48, "tensor-core path: embedding width %d > 48", E);
+  VFN_REQUIRE(Epad <= 48 && multires <= kMaxRes && multires_view <= kMaxRes, "tensor-core path: embedding too wide");
   VFN_REQUIRE(L >= 3 && L + 1 + (rn ? rn->n_layers : 0) <= kTcMaxSteps, "tensor-core path: too many layers");
+  VFN_REQUIRE(skip_layer < 0 || (skip_layer >= 2 && skip_layer < L - 1), "tensor-core path: skip_layer=%d unsupported", skip_layer);
   for (int l = 0; l < L; ++l) {
     const int want_in = (l == 0) ? E : 256;
     const int want_out = (l == L - 1) ? 259 : ((l + 1 == skip_layer) ? 256 - E : 256);
@@ -393,25 +536,41 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   TcProgram pr{};
   pr.emb_w = E; pr.emb_pad = Epad; pr.multires = multires; pr.multires_view = multires_view;
   pr.small_w = 3 + (3 + 6 * multires_view) + 3;
+  pr.skip_step = skip_layer;
   int ns = 0;
   long long woff = 0;
-  auto add = [&](int K, int N, int n_valid, int chunk_k, int epi, int net, int layer, int row0, int colmap,
-                 int dup_w, float post) {
+  // appends a step; the bias (ones) segment is added automatically as the last segment
+  auto add = [&](int N, int n_valid, int nseg, const int* col0, const int* segk, int chunk_k, int epi, int fresh,
+                 int net, int layer, int row0, int colmap, int src_split, float post) {
     TcStep& s = pr.s[ns];
-    s.K = K; s.a_col0 = 0; s.N = N; s.n_valid = n_valid; s.chunk_k = chunk_k;
-    s.n_chunks = (K + chunk_k - 1) / chunk_k; s.epi = epi; s.aff_off = ns * 256; s.w_off = woff;
-    s.net = net; s.layer = layer; s.row0 = row0; s.colmap = colmap; s.dup_w = dup_w; s.post_scale = post;
-    woff += (long long)align_up((int64_t)N * K * 2, 128);
+    s.N = N; s.n_valid = n_valid; s.n_seg = nseg + 1; s.K = 0;
+    for (int i = 0; i < nseg; ++i) { s.seg_col0[i] = col0[i]; s.seg_k[i] = segk[i]; s.K += segk[i]; }
+    s.seg_col0[nseg] = kColOnes; s.seg_k[nseg] = 16; s.K += 16;
+    s.chunk_k = chunk_k; s.epi = epi; s.fresh_mask = fresh; s.pre_wait_mask = 0; s.w_off = woff;
+    s.net = net; s.layer = layer; s.row0 = row0; s.colmap = colmap; s.src_split = src_split; s.post_scale = post;
+    woff += (long long)align_up((int64_t)N * s.K * 2, 128);
     ++ns;
   };
+  const int main0[1] = {0};
   for (int l = 0; l < L - 1; ++l) {
-    const bool pre_skip = (l + 1 == skip_layer);
-    add(l == 0 ? 2 * Epad : 256, round16(vf.out_dim[l]), vf.out_dim[l], 32,
-        pre_skip ? TC_EPI_RELU_SKIPFILL : TC_EPI_RELU, 0, l, 0, l == 0 ? 1 : 0, Epad, pre_skip ? kInvSqrt2 : 1.f);
+    const float post = (l + 1 == skip_layer) ? kInvSqrt2 : 1.f;
+    const int N = round16(vf.out_dim[l]);
+    if (l == 0) {
+      const int k[1] = {2 * Epad};
+      add(N, vf.out_dim[l], 1, main0, k, 64, TC_EPI_RELU, (1 << ((2 * Epad + 31) / 32)) - 1, 0, l, 0, 1, 0, post);
+    } else if (l == skip_layer) {
+      const int prev = vf.out_dim[l - 1];
+      const int c[2] = {0, kColSkip}, k[2] = {round16(prev), 48};
+      add(N, vf.out_dim[l], 2, c, k, 64, TC_EPI_RELU, 0xFF | (1 << kBarSkip), 0, l, 0, 3, prev, post);
+    } else {
+      const int k[1] = {256};
+      add(N, vf.out_dim[l], 1, main0, k, 64, TC_EPI_RELU, 0xFF, 0, l, 0, 0, 0, post);
+    }
   }
-  add(256, 16, 3, 256, TC_EPI_V, 0, L - 1, 0, 0, 0, 1.f);
+  const int k256[1] = {256};
+  add(16, 3, 1, main0, k256, 256, TC_EPI_V, 0xFF, 0, L - 1, 0, 0, 0, 1.f);
   const int n_v = ns;
-  add(256, 256, 256, 32, TC_EPI_FEAT, 0, L - 1, 3, 0, 0, 1.f);
+  add(256, 256, 1, main0, k256, 64, TC_EPI_FEAT, 0, 0, L - 1, 3, 0, 0, 1.f);
   const int n_full = ns;
   if (rn) {
     const int Lr = rn->n_layers;
@@ -423,15 +582,17 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
                   "tensor-core path supports the shipped 256-wide colour net (layer %d is %d->%d); use precision fp32",
                   l, rn->in_dim[l], rn->out_dim[l]);
     }
-    add(256 + 48, 256, 256, 32, TC_EPI_RELU, 1, 0, 0, 2, pr.small_w, 1.f);
-    for (int l = 1; l < Lr - 1; ++l) add(256, 256, 256, 32, TC_EPI_RELU, 1, l, 0, 0, 0, 1.f);
-    add(256, 16, 3, 256, TC_EPI_RGB, 1, Lr - 1, 0, 0, 0, 1.f);
+    const int c[2] = {0, kColAux}, k[2] = {256, 48};
+    add(256, 256, 2, c, k, 64, TC_EPI_RELU, 0xFF | (1 << kBarAux), 1, 0, 0, 2, pr.small_w, 1.f);
+    for (int l = 1; l < Lr - 1; ++l) add(256, 256, 1, main0, k256, 64, TC_EPI_RELU, 0xFF, 1, l, 0, 0, 0, 1.f);
+    add(16, 3, 1, main0, k256, 256, TC_EPI_RGB, 0xFF, 1, Lr - 1, 0, 0, 0, 1.f);
   }
   plan.wpack_bytes = woff;
-  pr.n_steps = ns; pr.act_cols = 304; pr.n_stages = 2;
+  pr.n_steps = ns; pr.render = 1;
   plan.render = pr;
-  plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.act_cols = 256; plan.vf_full.n_stages = 3;
-  plan.v_only = pr; plan.v_only.n_steps = n_v; plan.v_only.act_cols = 256; plan.v_only.n_stages = 3;
+  plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.render = 0;
+  plan.vf_full.s[n_full - 1].pre_wait_mask = 1 << kBarAux;
+  plan.v_only = pr; plan.v_only.n_steps = n_v; plan.v_only.render = 0;
   return 0;
 }
 
@@ -441,8 +602,6 @@ int tc_carve(char* base, int64_t& off, int multires, int multires_view, int skip
   off = align_up(off, 1024);
   plan.wpack = base ? reinterpret_cast<uint8_t*>(base + off) : nullptr;
   off += align_up(plan.wpack_bytes, 1024);
-  plan.affine = base ? reinterpret_cast<float*>(base + off) : nullptr;
-  off += kTcMaxSteps * 256 * sizeof(float);
   return 0;
 }
 
@@ -450,8 +609,7 @@ int tc_prepare(const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_ml
                const float* rn_arena, float bn_eps, const TcPlan& plan, cudaStream_t s) {
   const TcProgram& pr = rn ? plan.render : plan.vf_full;
   vfnerf_mlp_desc none{};
-  tc_pack_kernel<<<dim3(32, pr.n_steps), 256, 0, s>>>(pr, vf, vf_arena, rn ? *rn : none, rn_arena, bn_eps,
-                                                       plan.wpack, plan.affine);
+  tc_pack_kernel<<<dim3(32, pr.n_steps), 256, 0, s>>>(pr, vf, vf_arena, rn ? *rn : none, rn_arena, bn_eps, plan.wpack);
   VFN_LAUNCH_CHECK();
   return 0;
 }
@@ -464,12 +622,18 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   if (n <= 0) return 0;
   TcParams p{};
   p.prog = mode == TC_MODE_RENDER ? plan.render : (mode == TC_MODE_VF_FULL ? plan.vf_full : plan.v_only);
-  p.wpack = plan.wpack; p.affine = plan.affine;
+  p.wpack = plan.wpack;
   p.points = points; p.use_grid = grid ? 1 : 0;
   if (grid) p.grid = *grid;
   p.grid_res = grid_res; p.grid_i0 = grid_i0; p.n_points = n;
   p.ray_dirs = ray_dirs; p.samples_per_ray = samples_per_ray > 0 ? samples_per_ray : 1;
   p.out_v = out_v; p.v_ld = v_ld; p.out_feat = out_feat; p.feat_ld = feat_ld; p.colors = colors;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("VFNERF_TC_DBG"); dbg = e ? atoi(e) : 0; }
+  static long long* dbg_buf = nullptr;
+  if ((dbg & 64) && !dbg_buf) VFN_CHECK_CUDA(cudaMalloc(&dbg_buf, 256 * sizeof(long long)));
+  p.dbg_buf = (dbg & 64) ? dbg_buf : nullptr;
+  if (p.dbg_buf) VFN_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), s));
   VFN_REQUIRE(out_v, "tc_forward: out_v is null");
   VFN_REQUIRE(mode != TC_MODE_RENDER || (colors && ray_dirs), "tc_forward: RENDER mode needs colors and ray_dirs");
   if (g_num_sms == 0) {
@@ -478,24 +642,32 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
     VFN_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int64_t tiles = (n + kTileM - 1) / kTileM;
-  const int grid_x = (int)std::min<int64_t>(tiles, 2LL * g_num_sms);
-  const size_t smem = (size_t)p.prog.act_cols * kTileM * 2 + (size_t)p.prog.n_stages * kStageBytes + 128;
-  if (p.prog.n_stages == 3) {
-    static bool attr3 = false;
-    if (!attr3) {
-      VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
-      attr3 = true;
-    }
-    mlp_tc_kernel<3><<<grid_x, kTcThreads, smem, s>>>(p);
-  } else {
-    static bool attr2 = false;
-    if (!attr2) {
-      VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
-      attr2 = true;
-    }
-    mlp_tc_kernel<2><<<grid_x, kTcThreads, smem, s>>>(p);
+  const int grid_x = (int)std::min<int64_t>(tiles, (int64_t)g_num_sms);
+  const size_t smem = (size_t)kActCols * kTileM * 2 + (size_t)kTcStages * kStageBytes + 512;
+  static bool attr = false;
+  if (!attr) {
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
   }
+  mlp_tc_kernel<<<grid_x, kTcThreads, smem, s>>>(p);
   VFN_LAUNCH_CHECK();
+  if (p.dbg_buf) {
+    long long h[256];
+    VFN_CHECK_CUDA(cudaStreamSynchronize(s));
+    VFN_CHECK_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long tc = (tiles + grid_x - 1) / grid_x;
+    fprintf(stderr, "[tc dbg] tiles/CTA %lld steps %d | MMA thread cycles/tile: wait_grp %lld wait_full %lld issue %lld | "
+            "epi h0: acc %lld ld %lld math %lld sig %lld other %lld | epi h1: acc %lld ld %lld math %lld sig %lld other %lld\n",
+            tc, p.prog.n_steps, h[0] / tc, h[1] / tc, h[2] / tc, h[8] / tc, h[9] / tc, h[10] / tc, h[11] / tc, h[12] / tc,
+            h[16] / tc, h[17] / tc, h[18] / tc, h[19] / tc, h[20] / tc);
+    const long long base = h[64];
+    for (int si = 0; si < p.prog.n_steps && base; ++si) {
+      const long long* e = h + 64 + si * 8;
+      fprintf(stderr, "[tc timeline] step %2d: first_mma %6lld commit %6lld | h0: acc_seen %6lld first_arrive %6lld last_arrive %6lld | "
+              "h1: acc_seen %6lld first_arrive %6lld last_arrive %6lld\n", si, e[0] - base, e[1] - base, e[2] - base,
+              e[3] ? e[3] - base : 0, e[4] ? e[4] - base : 0, e[5] - base, e[6] ? e[6] - base : 0, e[7] ? e[7] - base : 0);
+    }
+  }
   return 0;
 }
 

@@ -5,45 +5,54 @@
 namespace vfn {
 
 constexpr int kTcMaxSteps = 16;
+constexpr int kTcMaxSegs = 3;
 
-// One GEMM step of the fused chain: acc[128 x N] = A[:, a_col0 : a_col0+K] * Wimg^T, then an epilogue.
+// Activation-tile column map (bf16 columns of the 128-row A operand, K-slab layout, tc_common.cuh):
+//   [0,256)    main: current layer input / output (step 0 reads the hi/lo embedding from [0, 2*emb_pad))
+//   [256,304)  aux:  colour-net small inputs [p(3), embed(view dir), n(3), 0..]     (written by the V step)
+//   [304,352)  skip: positional encoding / sqrt(2) for the skip layer               (written by the prologue)
+//   [352,368)  ones: [1, 1, 0, ...] constant -- multiplies the (hi, lo) bias row of every weight image,
+//                    so the folded BatchNorm shift is added by the tensor core, not by the epilogue
+constexpr int kColAux = 256, kColSkip = 304, kColOnes = 352, kActCols = 368;
+
+// One GEMM step of the fused chain: acc[128 x N] = sum over segments A[:, col0 : col0+k] * Wimg^T, then an epilogue.
 struct TcStep {
-  int K;          // multiple of 16
-  int a_col0;     // first activation-tile column consumed
   int N;          // UMMA N (multiple of 16, <= 256)
   int n_valid;    // real output channels (<= N)
-  int chunk_k;    // K columns per pipeline chunk (multiple of 16, N*chunk_k*2 <= 16 KiB)
-  int n_chunks;
+  int n_seg;
+  int seg_col0[kTcMaxSegs];   // first activation-tile column of the segment
+  int seg_k[kTcMaxSegs];      // columns (multiple of 16)
+  int K;          // sum of seg_k == columns of the weight image
+  int chunk_k;    // K columns per pipeline chunk (multiple of 16, N*chunk_k*2 <= 32 KiB); chunks never straddle segments
   int epi;        // TcEpi
-  int aff_off;    // offset (floats) of this step's shift vector in the affine table
-  long long w_off;  // byte offset of this step's weight image in the pack buffer
+  int fresh_mask; // readiness barriers (see mlp_tc.cu) whose phase this step's MMAs must wait for
+  int pre_wait_mask;  // barriers waited on before the first MMA (accumulator hand-off only)
+  long long w_off;    // byte offset of this step's weight image in the pack buffer
   // pack-time description of the source weights
   int net;        // 0 = VF net, 1 = colour net
   int layer;      // source Linear
   int row0;       // first source row
-  int colmap;     // 0: identity (zero padded), 1: [W | W] duplicated for a hi/lo split input of width `dup_w`,
-                  // 2: colour-net input permutation (features first, then the `small` leading columns)
-  int dup_w;      // padded width of one copy (colmap 1) / number of leading small columns (colmap 2)
+  int colmap;     // 0 identity | 1 hi/lo duplicated embedding | 2 colour-net input permutation | 3 skip layer
+  int src_split;  // colmap 2: number of leading small columns; colmap 3: columns fed by the previous layer
   float post_scale;  // folded 1/sqrt(2) of the skip connection (applies to scale and shift)
 };
 
-enum TcEpi { TC_EPI_RELU = 0, TC_EPI_RELU_SKIPFILL = 1, TC_EPI_V = 2, TC_EPI_FEAT = 3, TC_EPI_RGB = 4 };
+enum TcEpi { TC_EPI_RELU = 0, TC_EPI_V = 2, TC_EPI_FEAT = 3, TC_EPI_RGB = 4 };
 enum TcMode { TC_MODE_V_ONLY = 0, TC_MODE_VF_FULL = 1, TC_MODE_RENDER = 2 };
 
 struct TcProgram {
   int n_steps;
-  int act_cols;     // activation tile width in bf16 columns (256, or 304 with the colour-net aux region)
-  int n_stages;
+  int render;       // colour steps follow (V step writes the aux columns, FEAT step writes the main columns)
   int emb_w;        // 3 + 6*multires
   int emb_pad;      // emb_w rounded up to 16
   int multires, multires_view;
   int small_w;      // 3 + (3 + 6*multires_view) + 3
+  int skip_step;    // index of the step that consumes the skip columns (-1: none)
   TcStep s[kTcMaxSteps];
 };
 
 struct TcPlan {
   uint8_t* wpack = nullptr;   // weight images of every step of the RENDER program (VF steps are shared by all modes)
-  float* affine = nullptr;    // shift vectors, 256 floats per step
   int64_t wpack_bytes = 0;
   TcProgram render{}, vf_full{}, v_only{};
 };

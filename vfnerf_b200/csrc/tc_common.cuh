@@ -111,6 +111,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)1 << 46;
   return d;
 }
+// swizzled K-major operand (rows of 32/64/128 bytes, 8-row atoms): LBO field = 1 (unused), SBO = atom pitch,
+// layout_type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
 // instruction descriptor for kind::f16, bf16 x bf16 -> fp32, A and B K-major
 // (cute::UMMA::InstrDescriptor: c_format [4,6)=1 (F32), a_format [7,10)=1 (BF16), b_format [10,13)=1,
 //  a_major bit15=0, b_major bit16=0, n_dim [17,23)=N>>3, m_dim [24,29)=M>>4)
@@ -126,6 +137,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Same, with the descriptors given as 32-bit halves: the issuing thread only ever adds a constant to the low
+// words (start address field) between MMAs, so the per-instruction scalar work is two IADDs.
+__device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrive on an mbarrier once every previously issued MMA of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
