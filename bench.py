@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--rays", type=int, default=H * W_IMG, help="rays per step (default: the full image)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     return ap.parse_args()
 
 
@@ -261,29 +262,83 @@ def main():
         e2e = {"value": world * R / (ms2.item() * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "chunk": ck}
 
-    # ---- roofline of the dominant kernel: the VF MLP chain on one chunk of merged points
+    # ---- training step (BASELINE config 3): 1024-ray batch, render -> VFLoss terms -> backward -> clip -> Adam,
+    # the sequence of train/vector_field_nerf_train.py:177-260 (fp32 path: the tensor-core backward is not built yet)
+    train = None
+    if not args.no_train:
+        tm = U.make_model(dict(CASE, perturb=True, dir_to_normal_th=-2.0), st, dev, precision="fp32")
+        Rt = 1024
+        uvt, poset, Kt = uv_d[:Rt], pose_d[:Rt], K_d[:Rt]
+        g2 = torch.Generator(device=dev).manual_seed(7 + rank)
+        draws_t = (torch.rand(Rt, N_COARSE, device=dev, generator=g2), torch.rand(Rt, N_FINE, device=dev, generator=g2),
+                   torch.rand(Rt, N_FINE, device=dev, generator=g2))
+        rgb_gt = torch.rand(Rt, 3, device=dev, generator=g2)
+        dep_gt = torch.rand(Rt, 1, device=dev, generator=g2) * CASE["far"]
+
+        def train_step():
+            out = tm.render(poset, uvt, Kt, 0, draws=draws_t)
+            nrm = torch.norm(out.coarse_normals.reshape(-1, 3), dim=1)
+            loss = 2.0 * (out.coarse_rgb_values - rgb_gt).abs().mean() + \
+                0.5 * (out.coarse_depth_map - dep_gt).abs().clamp(max=0.5).mean() + 0.1 * torch.mean((nrm - 1) ** 2)
+            tm.optimizer.zero_grad()
+            loss.backward()
+            if world > 1:
+                from vfnerf_b200 import dist as vd
+                vd.allreduce_gradients(tm)
+            torch.nn.utils.clip_grad_norm_(tm.parameters(), 0.5)
+            tm.optimizer.step()
+        for _ in range(3):
+            train_step()
+        sync_all()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_tr = 5
+        t0e.record()
+        for _ in range(n_tr):
+            train_step()
+        t1e.record()
+        sync_all()
+        mst = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
+        if world > 1:
+            dist.all_reduce(mst, op=dist.ReduceOp.MAX)
+        train = {"value": world * Rt * n_tr / (mst.item() * 1e-3), "unit": "rays/s", "rays_per_step_per_gpu": Rt,
+                 "ms_per_step": mst.item() / n_tr, "precision": "fp32",
+                 "includes": "render fwd + loss + backward + (allreduce) + clip_grad_norm_ + Adam"}
+
+    # ---- roofline of the dominant kernel, timed alone with CUDA events on the launching stream:
+    #   bf16: the fused tcgen05 launch (VF + colour MLPs, RENDER program) on one chunk of merged points;
+    #   fp32: the CUDA-core VF MLP chain (9 GEMM launches) on one chunk.
     from vfnerf_b200 import ops
     pk, pk_src = peaks()
     P = min(R, chunk) * (N_COARSE + N_FINE)
     pts = (torch.rand(P, 3, device=dev) - 0.5) * 6
+    dirs = torch.nn.functional.normalize(torch.randn(P // (N_COARSE + N_FINE), 3, device=dev), dim=1)
+    reps = 5
     with torch.no_grad():
+        if args.precision == "bf16":
+            _, _, ws_k = ops.mlp_points(model.vector_field_network, model.rendering_network, pts, dirs, N_COARSE + N_FINE)
+            run = lambda: ops.mlp_points(model.vector_field_network, model.rendering_network, pts, dirs,
+                                         N_COARSE + N_FINE, workspace=ws_k, repack=False)
+            flop_pt, kname = F_VF + F_RN, "vfn::mlp_tc_kernel, RENDER program (VF + colour MLPs fused, one launch)"
+        else:
+            run = lambda: ops.vf_query(model.vector_field_network, pts)
+            flop_pt, kname = F_VF, "vfn::gemm_kernel x9 (fp32 CUDA-core VF MLP chain)"
         for _ in range(3):
-            ops.vf_query(model.vector_field_network, pts)
+            run()
         torch.cuda.synchronize()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
         r0.record()
         for _ in range(reps):
-            ops.vf_query(model.vector_field_network, pts)
+            run()
         r1.record()
         torch.cuda.synchronize()
-    t_vf = r0.elapsed_time(r1) * 1e-3 / reps
-    ach = F_VF * P / t_vf / 1e12
+    t_k = r0.elapsed_time(r1) * 1e-3 / reps
+    ach = flop_pt * P / t_k / 1e12
     peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "kernel": "VF MLP chain over one chunk (%d points)" % P,
-                "algorithmic_flop_per_launch": F_VF * P, "ms_per_launch": t_vf * 1e3, "peak_source": pk_src,
-                "whole_path_frac": (A_FWD * value / world) / 1e12 / peak_tf}
+                "traffic": None, "kernel": kname, "points_per_launch": P,
+                "algorithmic_flop_per_launch": flop_pt * P, "ms_per_launch": t_k * 1e3,
+                "peak_source": pk_src + ", sustained figure (kernel timed in a loop)",
+                "whole_path_algorithmic_frac": (A_FWD * value / world) / 1e12 / peak_tf}
 
     line = {
         "metric": "render_fwd_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world,
@@ -300,6 +355,8 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if train:
+        line["train_step"] = train
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, med, threads = cpu_reference_rays_per_s(3, 1)
         line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",

@@ -150,6 +150,19 @@ int vfnerf_vf_bwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
                   float* vf_grad_arena, int accumulate,
                   void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- both MLPs on given points: the VF + colour evaluation of VectorFieldNerf.get_colors ---------------- */
+/* (vector_field_nerf.py:341-375 / the merged pass of render(), :292-321).  points [P,3]; ray_dirs [P/samples_per_ray,3]
+ * unit view directions, one per ray; normals [P,3] = tanh VF vectors; colors [P,3] = sigmoid colour-net output.
+ * One fused tcgen05 launch (bf16 precision only); repack != 0 re-tiles the weights first (needed after any
+ * parameter update; 0 reuses the images already in `workspace`). */
+int64_t vfnerf_mlp_points_workspace_bytes(const vfnerf_mlp_desc* vf, const vfnerf_mlp_desc* rn, int multires,
+                                          int multires_view, int skip_layer);
+int vfnerf_mlp_points_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, const vfnerf_mlp_desc* rn,
+                          const float* rn_arena, int multires, int multires_view, int skip_layer, float bn_eps,
+                          int precision, const float* points, const float* ray_dirs, int samples_per_ray,
+                          int64_t n_points, float* normals, float* colors, void* workspace,
+                          int64_t workspace_bytes, int repack, void* stream);
+
 /* Same query with grid coordinates generated in-kernel (evaluation/methods.py:194-208): point i has
  * integer coordinates (ix,iy,iz) = unravel(i0 + i, [res,res,res]) (z fastest) and position
  * ((index * voxel + origin) + translation) + centroid per axis -- the reference's fp32 op order.

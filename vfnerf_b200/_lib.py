@@ -66,6 +66,8 @@ PROTOTYPES = {
     "vfnerf_vf_bwd": (_I, [_DESC, _P, _I, _I, _F, _I, _L, _P, _L, _P, _L, _I, _P, _I, _P, _L, _P]),
     "vfnerf_vf_grid_query": (_I, [_DESC, _P, _I, _I, _F, _I, _I, _L, _L, C.POINTER(C.c_float),
                                   C.POINTER(C.c_float), C.POINTER(C.c_float), _F, _P, _P, _L, _P]),
+    "vfnerf_mlp_points_workspace_bytes": (_L, [_DESC, _DESC, _I, _I, _I]),
+    "vfnerf_mlp_points_fwd": (_I, [_DESC, _P, _DESC, _P, _I, _I, _I, _F, _I, _P, _P, _I, _L, _P, _P, _P, _L, _I, _P]),
     "vfnerf_ray_geometry": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "vfnerf_coarse_sample": (_I, [_I, _I, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P]),
     "vfnerf_fine_sample": (_I, [_I, _I, _I, _D, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -465,6 +465,34 @@ int vfnerf_vf_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
   return vf_forward_fp32(*vf, vf_arena, p.b, skip_layer, p.emb, n_points, out, out_ld, n_out_cols, s);
 }
 
+int64_t vfnerf_mlp_points_workspace_bytes(const vfnerf_mlp_desc* vf, const vfnerf_mlp_desc* rn, int multires,
+                                          int multires_view, int skip_layer) {
+  if (!vf || !rn) { set_error("null argument"); return -1; }
+  TcPlan plan;
+  int64_t off = 0;
+  if (tc_carve(nullptr, off, multires, multires_view, skip_layer, *vf, rn, plan)) return -1;
+  return off + 1024;
+}
+
+int vfnerf_mlp_points_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, const vfnerf_mlp_desc* rn,
+                          const float* rn_arena, int multires, int multires_view, int skip_layer, float bn_eps,
+                          int precision, const float* points, const float* ray_dirs, int samples_per_ray,
+                          int64_t n_points, float* normals, float* colors, void* workspace,
+                          int64_t workspace_bytes, int repack, void* stream) {
+  VFN_REQUIRE(vf && vf_arena && rn && rn_arena && points && ray_dirs && normals && colors, "mlp_points_fwd: null argument");
+  VFN_REQUIRE(precision == VFNERF_PREC_BF16, "mlp_points_fwd: only the bf16 tensor-core path implements this entry");
+  if (int e = validate_vf(*vf, multires, skip_layer)) return e;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  TcPlan plan;
+  int64_t off = 0;
+  if (int e = tc_carve(reinterpret_cast<char*>(workspace), off, multires, multires_view, skip_layer, *vf, rn, plan)) return e;
+  VFN_REQUIRE(workspace && workspace_bytes >= off, "mlp_points_fwd: workspace too small");
+  if (repack)
+    if (int e = tc_prepare(*vf, vf_arena, rn, rn_arena, bn_eps, plan, s)) return e;
+  return tc_forward(plan, TC_MODE_RENDER, points, nullptr, 0, 0, n_points, ray_dirs, samples_per_ray, normals, 3,
+                    nullptr, 0, colors, s);
+}
+
 int vfnerf_vf_bwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires, int skip_layer, float bn_eps,
                   int precision, int64_t n_points, const float* out, int64_t out_ld, const float* d_out,
                   int64_t d_ld, int n_out_cols, float* vf_grad_arena, int accumulate, void* workspace,

@@ -91,6 +91,32 @@ def vf_query(net, points: torch.Tensor, n_cols: Optional[int] = None) -> torch.T
     return _VFQuery.apply(net, points, n_cols, need_bwd, *params)
 
 
+def mlp_points(vf_net, rn_net, points: torch.Tensor, ray_dirs: torch.Tensor, samples_per_ray: int,
+               workspace: Optional[torch.Tensor] = None, repack: bool = True):
+    """VF vectors and colours at ``points[P,3]`` seen along ``ray_dirs[P/samples_per_ray,3]`` -- the two-MLP evaluation
+    of VectorFieldNerf.get_colors (vector_field_nerf.py:341-375) as ONE fused tcgen05 launch (bf16, forward only).
+    Returns (normals[P,3], colors[P,3], workspace)."""
+    L = _lib.lib()
+    points, ray_dirs = _require_cuda("points", points.detach()), _require_cuda("ray_dirs", ray_dirs.detach())
+    va, ra = vf_net.arena(), rn_net.arena()
+    dev = points.device
+    P = points.shape[0]
+    if workspace is None:
+        nb = L.vfnerf_mlp_points_workspace_bytes(C.byref(va.desc), C.byref(ra.desc), vf_net.multires, rn_net.multires_view,
+                                                 vf_net.skip_layer)
+        if nb < 0:
+            _lib.check(1, "vfnerf_mlp_points_workspace_bytes")
+        workspace = _workspace(nb, dev)
+    normals = torch.empty(P, 3, dtype=torch.float32, device=dev)
+    colors = torch.empty(P, 3, dtype=torch.float32, device=dev)
+    _lib.check(L.vfnerf_mlp_points_fwd(C.byref(va.desc), va.flat.data_ptr(), C.byref(ra.desc), ra.flat.data_ptr(),
+                                       vf_net.multires, rn_net.multires_view, vf_net.skip_layer, 1e-5, _lib.PREC_BF16,
+                                       points.data_ptr(), ray_dirs.data_ptr(), int(samples_per_ray), P, normals.data_ptr(),
+                                       colors.data_ptr(), workspace.data_ptr(), workspace.numel(), int(repack),
+                                       _stream_ptr(dev)), "vfnerf_mlp_points_fwd")
+    return normals, colors, workspace
+
+
 # ------------------------------------------------------------------------------------------------
 # render()
 # ------------------------------------------------------------------------------------------------
