@@ -201,6 +201,8 @@ int vfnerf_composite(int n_rays, int n_samples, const float* weights, const floa
 /* One CTA: D[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T through tcgen05.mma + TMEM; pins the UMMA
  * descriptor conventions of csrc/tc_common.cuh (variant 1 = LBO/SBO swapped, expected to be wrong). */
 int vfnerf_debug_umma_gemm(const float* A, const float* B, float* D, int N, int K, int variant, void* stream);
+/* 2-CTA variant (cluster of two, tcgen05.mma.cta_group::2, M = 256): D[256,N] = bf16(A[256,K]) * bf16(B[N,K])^T */
+int vfnerf_debug_umma2_gemm(const float* A, const float* B, float* D, int N, int K, void* stream);
 /* Micro-benchmark: every CTA issues n_mma back-to-back tcgen05.mma (M=128, N, K=16) from one thread; CTA 0 writes
  * the elapsed SM cycles to cycles_dev[0].  mode 1 adds a tcgen05.commit after every second MMA. */
 int vfnerf_debug_umma_bench(int N, int n_mma, int mode, int n_ctas, long long* cycles_dev, void* stream);

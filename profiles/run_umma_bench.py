@@ -6,10 +6,10 @@ from vfnerf_b200 import _lib
 _lib.build()
 L = _lib.lib()
 out = torch.zeros(4, dtype=torch.int64, device="cuda")
-for n_ctas in (1, 148):
-    for N in (256, 128, 64, 16):
-        for mode in (0, 8, 9):
+for n_ctas in (148,):
+    for N in (256,):
+        for mode in (9, 9 + 16, 9 + 32, 9 + 64, 9 + 16 + 32 + 64):
             n = 2048
             _lib.check(L.vfnerf_debug_umma_bench(N, n, mode, n_ctas, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "bench")
             torch.cuda.synchronize()
-            print(f"ctas={n_ctas:3d} N={N:3d} mode={mode} (layout {mode >> 1}, commit {mode & 1}): {out[0].item() / n:7.1f} cycles / MMA (ideal {128 * N / 256:.0f})")
+            print(f"ctas={n_ctas:3d} N={N:3d} mode={mode} (commit per 4; +16 tcgen05 fence, +32 mbarrier wait, +64 runtime kk loop): {out[0].item() / n:7.1f} cycles / MMA (ideal {128 * N / 256:.0f})")

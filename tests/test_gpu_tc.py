@@ -128,3 +128,19 @@ def test_tc_grid_query_matches_fp32_grid_query(built_lib):
     slab = grid_query(model.vector_field_network, res, 1.0, tr, ce, i0=res * res * 7, n_points=res * res * 3)
     assert (out - ref).abs().max().item() <= 5e-3
     assert torch.equal(slab, out[res * res * 7: res * res * 10])      # z-slab partition == slice of the whole grid
+
+
+@pytest.mark.parametrize("N,K", [(256, 256), (32, 256), (256, 64), (224, 96)])
+def test_umma_2cta_conventions(built_lib, N, K):
+    """cta_group::2: A rows split across the CTA pair, B rows (output channels) split in halves, M = 256."""
+    g = torch.Generator().manual_seed(N + K)
+    A = torch.randn(256, K, generator=g).to(DEV)
+    B = torch.randn(N, K, generator=g).to(DEV)
+    D = torch.zeros(256, N, device=DEV)
+    _lib.check(built_lib.vfnerf_debug_umma2_gemm(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K,
+                                                 torch.cuda.current_stream().cuda_stream), "debug_umma2_gemm")
+    torch.cuda.synchronize()
+    ref = A.bfloat16().float() @ B.bfloat16().float().T
+    err = (D - ref).abs().max().item()
+    print(f"2-CTA N={N} K={K}: max abs err {err:.3e}")
+    assert err <= 1e-3 * max(1.0, ref.abs().max().item())

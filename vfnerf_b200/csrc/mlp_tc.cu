@@ -2,11 +2,16 @@
 // layers with skip -> tanh) and, in RENDER mode, the colour MLP (5 layers -> sigmoid) evaluated for a
 // tile of 128 points entirely on chip.  SURVEY.md §8 rows a3 + a8.
 //
-// One CTA per SM, 320 threads:
-//   warp 0      weight producer: one lane streams pre-tiled bf16 weight chunks (<= 32 KiB) from L2 into a
-//               4-slot shared-memory ring with cp.async.bulk, completion on mbarriers      (SASS UBLKCP)
-//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N<=256, K=16, bf16 x bf16 -> fp32 in TMEM);
-//               tcgen05.commit releases ring slots and publishes the accumulator           (SASS UTCHMMA)
+// One CTA per SM, 320 threads, CTAs paired into clusters of two (tcgen05 cta_group::2): each CTA owns one
+// 128-point tile (its A operand and its TMEM accumulators) but only HALF of every weight chunk (N/2 output
+// channels); one MMA instruction of the leader drives both SMs' tensor cores with M = 256.  Per SM this halves
+// the shared-memory bytes moved per MMA (the limiter of the 1-CTA version) and the L2 traffic.
+//   warp 0      weight producer: one lane streams this CTA's half of each pre-tiled bf16 weight chunk (<= 16 KiB)
+//               from L2 into an 8-slot shared-memory ring with cp.async.bulk + mbarriers     (SASS UBLKCP)
+//   warp 1      leader CTA: MMA issuer -- one lane issues tcgen05.mma.cta_group::2 (M=256, N<=256, K=16, bf16 x
+//               bf16 -> fp32 in TMEM); tcgen05.commit (multicast) releases ring slots and publishes the
+//               accumulators in both CTAs (SASS UTCHMMA).  Peer CTA: relay lane that forwards "my half of the
+//               chunk has landed" to the leader with a remote mbarrier arrive
 //   warps 2..9  epilogue: tcgen05.ld the fp32 accumulator (one row per thread, 32 columns at a time),
 //               convert to bf16x2, ReLU / tanh on the packed pair, and write the NEXT layer's A operand
 //               straight into the activation tile in the K-slab UMMA layout -- activations never leave
@@ -24,13 +29,14 @@ namespace vfn {
 using namespace tc;
 
 constexpr int kTileM = 128;
-constexpr int kStageBytes = 32768;
-constexpr int kTcStages = 4;
+constexpr int kStageBytes = 16384;
+constexpr int kTcStages = 8;
 constexpr int kTcThreads = 320;
 constexpr int kAccCols = 256;
 constexpr float kInvSqrt2 = 0.70710678118654752f;
-// readiness barriers: 0..7 = 32-column groups of the main region, 8 = aux region, 9 = skip region
-constexpr int kGroups = 10, kBarAux = 8, kBarSkip = 9;
+// readiness barriers: 0..3 = 64-column groups of the main region (one per K chunk), 4 = aux region, 5 = skip region.
+// Every barrier expects one arrival from each of the 8 epilogue warps of both CTAs of the pair.
+constexpr int kGroups = 6, kBarAux = 4, kBarSkip = 5, kGrpArrivals = 16;
 
 struct TcParams {
   TcProgram prog;
@@ -46,6 +52,7 @@ struct TcParams {
   float* out_v; long long v_ld;
   float* out_feat; long long feat_ld;
   float* colors;
+  int dbg;              // experiments: 1 = MMA issuer ignores A-readiness, 2 = epilogue skips TMEM loads / math / stores
   long long* dbg_buf;   // VFNERF_TC_DBG=64: cycle counters of CTA 0 (MMA thread [0..2], epilogue warp 2 [8..12], warp 3 [16..20])
 };
 
@@ -65,11 +72,13 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int n = e / st.K, k = e - n * st.K;
     // locate (segment, column in segment) and the byte offset of the chunk that holds column k
+    // each CTA of the pair streams one half image: output channels [half*N/2, (half+1)*N/2)
+    const int nh = st.N >> 1, half = n / nh, nn = n - half * nh;
     int sg = 0, kin = k;
-    int64_t base = st.w_off;
-    while (kin >= st.seg_k[sg]) { kin -= st.seg_k[sg]; base += (int64_t)st.N * st.seg_k[sg] * 2; ++sg; }
-    const int64_t off = base + (int64_t)(kin / st.chunk_k) * st.N * st.chunk_k * 2 +
-                        (int64_t)((kin % st.chunk_k) / 8) * st.N * 16 + n * 16 + (kin & 7) * 2;
+    int64_t base = st.w_off + (int64_t)half * nh * st.K * 2;
+    while (kin >= st.seg_k[sg]) { kin -= st.seg_k[sg]; base += (int64_t)nh * st.seg_k[sg] * 2; ++sg; }
+    const int64_t off = base + (int64_t)(kin / st.chunk_k) * nh * st.chunk_k * 2 +
+                        (int64_t)((kin % st.chunk_k) / 8) * nh * 16 + nn * 16 + (kin & 7) * 2;
     float w = 0.f;
     if (n < st.n_valid) {
       const int row = st.row0 + n;
@@ -171,7 +180,54 @@ __device__ __forceinline__ void load_point(const TcParams& p, long long pi, bool
 
 // readiness barrier that guards activation-tile column `col` (-1: constant region, nothing to wait for)
 __device__ __forceinline__ int col_barrier(int col) {
-  return col < kColAux ? (col >> 5) : (col < kColSkip ? kBarAux : (col < kColOnes ? kBarSkip : -1));
+  return col < kColAux ? (col >> 6) : (col < kColSkip ? kBarAux : (col < kColOnes ? kBarSkip : -1));
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                 uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all previously issued MMAs -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
 #define TCK(acc_) do { if (prof) { long long t1_ = clock64(); acc_ += t1_ - t0; t0 = t1_; } } while (0)
@@ -179,7 +235,8 @@ __device__ __forceinline__ int col_barrier(int col) {
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcProgram& prog = p.prog;
   uint8_t* s_act = smem;
@@ -187,18 +244,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kTcStages * kStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kTcStages;
-  uint64_t* acc_full = bars + 2 * kTcStages;
-  uint64_t* grp = acc_full + 1;
+  uint64_t* fullp = bars + 2 * kTcStages;      // leader only: "the peer's half of the chunk has landed"
+  uint64_t* acc_full = bars + 3 * kTcStages;
+  uint64_t* grp = acc_full + 1;                 // leader only: A-operand readiness, 128 local + 128 remote arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(grp + kGroups);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kTcStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    // leader: a ring slot is full when its own bulk copy has landed AND the peer's relay has arrived
+    for (int i = 0; i < kTcStages; ++i) { mbar_init(&full[i], rank == 0 ? 2 : 1); mbar_init(&empty[i], 1); mbar_init(&fullp[i], 1); }
     mbar_init(acc_full, 1);
-    for (int i = 0; i < kGroups; ++i) mbar_init(&grp[i], 128);
+    for (int i = 0; i < kGroups; ++i) mbar_init(&grp[i], kGrpArrivals);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kTileM) {
     // constant ones-columns [1, 1, 0, ...] that pick up the bias row of every weight image
     const int r = threadIdx.x - 64;
@@ -207,23 +270,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
     fence_proxy_async_smem();
   }
   tc_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();                       // barriers of BOTH CTAs are initialised before any remote arrive / multicast
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const long long num_tiles = (p.n_points + kTileM - 1) / kTileM;
+  // tiles are handed out in pairs: cluster c processes tile pairs c, c + n_clusters, ...; CTA `rank` takes tile 2*pair + rank
+  const long long num_pairs = (num_tiles + 1) / 2;
+  const long long pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+  // called by all 32 lanes of an epilogue warp after each lane's fence.proxy.async: one arrival per warp
+  auto arrive_grp = [&](int g) {
+    __syncwarp();
+    if (lane == 0) {
+      if (rank == 0) mbar_arrive(&grp[g]); else mbar_arrive_remote(&grp[g], 0);
+    }
+  };
 
   if (warp == 0) {
     // ===================== weight producer =====================
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
         for (int si = 0; si < prog.n_steps; ++si) {
           const TcStep& st = prog.s[si];
-          const uint8_t* src = p.wpack + st.w_off;
+          const int nh = st.N >> 1;
+          const uint8_t* src = p.wpack + st.w_off + (int64_t)rank * nh * st.K * 2;
           for (int sg = 0; sg < st.n_seg; ++sg) {
             for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
               const int kc = min(st.chunk_k, st.seg_k[sg] - k0);
-              const uint32_t bytes = (uint32_t)(st.N * kc * 2);
+              const uint32_t bytes = (uint32_t)(nh * kc * 2);
               mbar_wait(&empty[stage], phase ^ 1);
               mbar_arrive_expect_tx(&full[stage], bytes);
               bulk_g2s(s_stage + stage * kStageBytes, src, bytes, &full[stage]);
@@ -235,8 +309,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== peer CTA: relay lane =====================
+    if (lane == 0 && rank == 1) {
+      int stage = 0, phase = 0;
+      for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
+        for (int si = 0; si < prog.n_steps; ++si) {
+          const TcStep& st = prog.s[si];
+          for (int sg = 0; sg < st.n_seg; ++sg) {
+            for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
+              mbar_wait(&full[stage], phase);           // my half of the chunk is in my shared memory
+              mbar_arrive_remote(&full[stage], 0);      // second arrival on the leader's "slot full" barrier
+              if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    // ===================== leader CTA: MMA issuer =====================
+    if (lane == 0 && rank == 0) {
       int stage = 0, phase = 0;
       uint32_t grp_par = 0, gstep = 0;
       long long t_grp = 0, t_full = 0, t_issue = 0, t0 = 0;
@@ -244,24 +334,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
       if (prof) t0 = clock64();
       const uint32_t act_base = smem_u32(s_act), stage_base = smem_u32(s_stage);
       int tile_no = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_no) {
+      for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++tile_no) {
         const bool tl = prof && tile_no == 2;
         for (int si = 0; si < prog.n_steps; ++si, ++gstep) {
           const TcStep& st = prog.s[si];
           bool first_mma = true;
-          const uint32_t idesc = make_idesc_bf16(kTileM, st.N);
+          const uint32_t idesc = make_idesc_bf16(2 * kTileM, st.N);
           // descriptor halves: only the start-address field of the low words changes between MMAs
           const uint32_t desc_hi = (128u >> 4) | (1u << 14);                   // SBO = 128 B, version 1
           const uint32_t a_lo0 = ((act_base >> 4) & 0x3FFF) | (((kTileM * 16u) >> 4) << 16);
-          const uint32_t b_lo0 = ((stage_base >> 4) & 0x3FFF) | ((((uint32_t)st.N * 16u) >> 4) << 16);
-          const uint32_t b_kstep = 2u * (uint32_t)st.N;                        // two K-slabs of the weight chunk, in 16-byte units
+          const uint32_t b_lo0 = ((stage_base >> 4) & 0x3FFF) | ((((uint32_t)(st.N >> 1) * 16u) >> 4) << 16);
+          const uint32_t b_kstep = (uint32_t)st.N;                             // two K-slabs of the HALF weight chunk, in 16-byte units
           const uint32_t acc = tmem + (gstep & 1) * kAccCols;
-          uint32_t fresh = (uint32_t)st.fresh_mask;
+          uint32_t fresh = (p.dbg & 1) ? 0u : (uint32_t)st.fresh_mask;
           uint32_t accumulate = 0;
           TCK(t_issue);
           for (int g = 0; g < kGroups; ++g) {
             if (st.pre_wait_mask & (1 << g)) {
-              mbar_wait(&grp[g], (grp_par >> g) & 1u);
+              mbar_wait_cluster(&grp[g], (grp_par >> g) & 1u);
               grp_par ^= (1u << g);
             }
           }
@@ -269,35 +359,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
             for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
               const int kc = min(st.chunk_k, st.seg_k[sg] - k0);
               const int col = st.seg_col0[sg] + k0;
-              // the A columns of this chunk must have been (re)written: wait for their readiness barriers
-              if (fresh) {
-                const int b0 = col_barrier(col), b1 = col_barrier(col + kc - 1);
-                for (int b = b0; b >= 0 && b <= b1; ++b) {
-                  if (fresh & (1u << b)) {
-                    mbar_wait(&grp[b], (grp_par >> b) & 1u);
-                    grp_par ^= (1u << b);
-                    fresh &= ~(1u << b);
-                  }
-                }
+              // the A columns of this chunk must have been (re)written: one readiness barrier per chunk
+              const int b = col_barrier(col);
+              if (b >= 0 && (fresh & (1u << b))) {
+                mbar_wait_cluster(&grp[b], (grp_par >> b) & 1u);
+                grp_par ^= (1u << b);
+                fresh &= ~(1u << b);
               }
               TCK(t_grp);
-              mbar_wait(&full[stage], phase);
+              mbar_wait_cluster(&full[stage], phase);      // both halves of the weight chunk have landed
               TCK(t_full);
               tc_fence_after_sync();
-              uint32_t a_lo = a_lo0 + (uint32_t)(col >> 3) * ((kTileM * 16u) >> 4);
-              uint32_t b_lo = b_lo0 + (uint32_t)stage * (kStageBytes >> 4);
+              const uint32_t a_lo = a_lo0 + (uint32_t)(col >> 3) * ((kTileM * 16u) >> 4);
+              const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kStageBytes >> 4);
+              constexpr uint32_t a_kstep = 2u * ((kTileM * 16u) >> 4);
               if (tl && first_mma) { p.dbg_buf[64 + si * 8 + 0] = clock64(); first_mma = false; }
-              for (int kk = 0; kk < kc; kk += 16) {
-                umma_bf16_split(acc, a_lo, desc_hi, b_lo, desc_hi, idesc, accumulate);
-                accumulate = 1;
-                a_lo += 2u * ((kTileM * 16u) >> 4);
-                b_lo += b_kstep;
+              if (kc == 64) {
+                // steady state: four MMAs with constant descriptor increments (the issue thread must stay well
+                // under 128 cycles of scalar work per MMA, profiles/run_umma_bench.py)
+                umma2_bf16_split(acc, a_lo, desc_hi, b_lo, desc_hi, idesc, accumulate);
+                umma2_bf16_split(acc, a_lo + a_kstep, desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
+                umma2_bf16_split(acc, a_lo + 2 * a_kstep, desc_hi, b_lo + 2 * b_kstep, desc_hi, idesc, 1u);
+                umma2_bf16_split(acc, a_lo + 3 * a_kstep, desc_hi, b_lo + 3 * b_kstep, desc_hi, idesc, 1u);
+              } else {
+                uint32_t al = a_lo, bl = b_lo, ac = accumulate;
+                for (int kk = 0; kk < kc; kk += 16) {
+                  umma2_bf16_split(acc, al, desc_hi, bl, desc_hi, idesc, ac);
+                  ac = 1u; al += a_kstep; bl += b_kstep;
+                }
               }
-              umma_commit(&empty[stage]);          // ring slot reusable once these MMAs have read it
+              accumulate = 1;
+              umma2_commit(&empty[stage]);         // ring slot (in both CTAs) reusable once these MMAs have read it
               if (++stage == kTcStages) { stage = 0; phase ^= 1; }
             }
           }
-          umma_commit(acc_full);                   // accumulator complete -> epilogue
+          umma2_commit(acc_full);                  // accumulators complete -> epilogue warps of both CTAs
           if (tl) p.dbg_buf[64 + si * 8 + 1] = clock64();
         }
       }
@@ -315,13 +411,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
     uint32_t gstep = 0;
     long long t_acc = 0, t_ld = 0, t_math = 0, t_sig = 0, t_other = 0, t0 = 0;
     const bool prof = p.dbg_buf && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 3);
+    auto tile_of = [&](long long pair) { return 2 * pair + (long long)rank; };
     if (prof) t0 = clock64();
 
     // A operand of step 0 (half-0 warps: bf16 hi/lo split of the embedding -> main columns [0, 2*Epad)) and the skip
     // layer's extra input (half-1 warps: embedding / sqrt(2) -> skip columns).  Both are computed for the NEXT tile
     // while this tile's MMAs run: half 1 stores right away (the skip columns are free once the skip step's MMAs
     // are done), half 0 parks the packed values in registers and stores them during the last step.
-    uint32_t pk0[48];
+    uint32_t pk0[24];
     auto embed_tile = [&](long long tile, float* emb) {
       const long long pi = tile * kTileM + row;
       float pt[3];
@@ -333,48 +430,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
       for (int i = 0; i < 48; ++i)
         if (i >= E) emb[i] = 0.f;
     };
-    auto prologue_compute = [&](long long tile) {        // half 0
+    // half-0 warps keep the bf16 "hi" part of the embedding, half-1 warps the "lo" remainder
+    auto prologue_compute = [&](long long tile) {
       float emb[48];
       embed_tile(tile, emb);
 #pragma unroll
       for (int j = 0; j < 24; ++j) {
         const float a = emb[2 * j], b = emb[2 * j + 1];
         const float ah = __bfloat162float(__float2bfloat16(a)), bh = __bfloat162float(__float2bfloat16(b));
-        pk0[j] = pack_bf16x2(ah, bh);
-        pk0[24 + j] = pack_bf16x2(a - ah, b - bh);
+        pk0[j] = h == 0 ? pack_bf16x2(ah, bh) : pack_bf16x2(a - ah, b - bh);
       }
     };
-    auto prologue_store = [&]() {                        // half 0
+    auto prologue_store = [&]() {
       const int nsl = Epad >> 3;
 #pragma unroll
-      for (int sl = 0; sl < 6; ++sl) {
-        if (sl < nsl) {
-          store_slab_u(s_act, sl, row, pk0[4 * sl], pk0[4 * sl + 1], pk0[4 * sl + 2], pk0[4 * sl + 3]);
-          store_slab_u(s_act, nsl + sl, row, pk0[24 + 4 * sl], pk0[25 + 4 * sl], pk0[26 + 4 * sl], pk0[27 + 4 * sl]);
-        }
-      }
+      for (int sl = 0; sl < 6; ++sl)
+        if (sl < nsl) store_slab_u(s_act, h * nsl + sl, row, pk0[4 * sl], pk0[4 * sl + 1], pk0[4 * sl + 2], pk0[4 * sl + 3]);
       fence_proxy_async_smem();
-      const int ng = (2 * Epad + 31) >> 5;
-      for (int g = 0; g < ng; ++g) mbar_arrive(&grp[g]);
+      const int ng = (2 * Epad + 63) >> 6;
+      for (int g = 0; g < ng; ++g) arrive_grp(g);
     };
-    auto prologue_skip = [&](long long tile) {           // half 1
-      float emb[48];
-      embed_tile(tile, emb);
+    auto prologue_skip = [&](long long tile) {
+      if (h == 1) {
+        float emb[48];
+        embed_tile(tile, emb);
 #pragma unroll
-      for (int i = 0; i < 48; ++i) emb[i] *= kInvSqrt2;
+        for (int i = 0; i < 48; ++i) emb[i] *= kInvSqrt2;
 #pragma unroll
-      for (int sl = 0; sl < 6; ++sl) store_slab_f(s_act, kColSkip / 8 + sl, row, emb + 8 * sl);
-      fence_proxy_async_smem();
-      mbar_arrive(&grp[kBarSkip]);
+        for (int sl = 0; sl < 6; ++sl) store_slab_f(s_act, kColSkip / 8 + sl, row, emb + 8 * sl);
+        fence_proxy_async_smem();
+      }
+      arrive_grp(kBarSkip);
     };
 
-    if ((long long)blockIdx.x < num_tiles) {
-      if (h == 0) { prologue_compute(blockIdx.x); prologue_store(); }
-      else if (prog.skip_step >= 0) prologue_skip(blockIdx.x);
+    if (pair0 < num_pairs) {
+      prologue_compute(tile_of(pair0));
+      prologue_store();
+      if (prog.skip_step >= 0) prologue_skip(tile_of(pair0));
     }
 
     int tile_no = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_no) {
+    for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++tile_no) {
+      const long long tile = tile_of(pair);
       const long long pi = tile * kTileM + row;
       const bool valid = pi < p.n_points;
       const bool tl = prof && tile_no == 2;
@@ -394,10 +491,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll 1
           for (int gi = 0; gi < 4; ++gi) {
             const int g = 2 * gi + h, c0 = g * 32;
-            if (c0 >= st.N) break;
+            if (c0 >= st.N) {                       // narrow layer: nothing to write, but the barrier still expects this warp
+              if (to_act) arrive_grp(g >> 1);
+              continue;
+            }
             TCK(t_other);
             tmem_ld_wait();
             TCK(t_ld);
+            if (p.dbg & 2) {
+              if (to_act) { tc_fence_before_sync(); arrive_grp(g >> 1); }
+              continue;
+            }
             if (to_act) {
               uint32_t pk[16];
 #pragma unroll
@@ -412,7 +516,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
               TCK(t_math);
               fence_proxy_async_smem();
               tc_fence_before_sync();
-              mbar_arrive(&grp[g]);
+              arrive_grp(g >> 1);
               TCK(t_sig);
               if (tl && gi == 0) p.dbg_buf[64 + si * 8 + 3 + 3 * h] = clock64();
               if (tl) p.dbg_buf[64 + si * 8 + 4 + 3 * h] = clock64();
@@ -471,14 +575,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
               for (int sl = 0; sl < 6; ++sl) store_slab_f(s_act, kColAux / 8 + sl, row, a + 8 * sl);
               fence_proxy_async_smem();
-              tc_fence_before_sync();
-              mbar_arrive(&grp[kBarAux]);
-            } else if (si + 1 < prog.n_steps) {
-              // VF_FULL: the FEAT step's MMAs do not depend on any A rewrite; this arrival orders them (and through
-              // them the next tile's first MMA into this accumulator buffer) after the read above
-              tc_fence_before_sync();
-              mbar_arrive(&grp[kBarAux]);
             }
+          }
+          // RENDER: the aux columns are ready.  VF_FULL: the FEAT step's MMAs do not depend on any A rewrite; this
+          // arrival orders them (and through them the next tile's first MMA into this accumulator buffer) after the
+          // accumulator read above.  Half-1 warps arrive too (every barrier expects all 8 warps).
+          if (si + 1 < prog.n_steps) {
+            tc_fence_before_sync();
+            arrive_grp(kBarAux);
           }
         } else {  // TC_EPI_RGB
           if (h == 0) {
@@ -492,13 +596,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
           }
         }
         // next tile's prologue, off the critical path (see above)
-        if (tile + gridDim.x < num_tiles) {
-          if (h == 0) {
-            if (si == 0) prologue_compute(tile + gridDim.x);
-            if (si == prog.n_steps - 1) prologue_store();      // this step's MMAs have finished reading the A tile
-          } else if (si == prog.skip_step) {
-            prologue_skip(tile + gridDim.x);                    // the skip step's MMAs (the only readers) are done
-          }
+        if (pair + pair_step < num_pairs) {
+          const long long nxt = tile_of(pair + pair_step);
+          if (si == 0) prologue_compute(nxt);
+          if (si == prog.n_steps - 1) prologue_store();        // this step's MMAs have finished reading the A tile
+          if (si == prog.skip_step) prologue_skip(nxt);         // the skip step's MMAs (the only readers) are done
         }
         tc_fence_before_sync();
       }
@@ -510,8 +612,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
     }
   }
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  cluster_sync_all();                       // neither CTA may exit (or free TMEM) while its peer can still touch it
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -557,18 +659,18 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
     const int N = round16(vf.out_dim[l]);
     if (l == 0) {
       const int k[1] = {2 * Epad};
-      add(N, vf.out_dim[l], 1, main0, k, 64, TC_EPI_RELU, (1 << ((2 * Epad + 31) / 32)) - 1, 0, l, 0, 1, 0, post);
+      add(N, vf.out_dim[l], 1, main0, k, 64, TC_EPI_RELU, (1 << ((2 * Epad + 63) / 64)) - 1, 0, l, 0, 1, 0, post);
     } else if (l == skip_layer) {
       const int prev = vf.out_dim[l - 1];
       const int c[2] = {0, kColSkip}, k[2] = {round16(prev), 48};
-      add(N, vf.out_dim[l], 2, c, k, 64, TC_EPI_RELU, 0xFF | (1 << kBarSkip), 0, l, 0, 3, prev, post);
+      add(N, vf.out_dim[l], 2, c, k, 64, TC_EPI_RELU, 0xF | (1 << kBarSkip), 0, l, 0, 3, prev, post);
     } else {
       const int k[1] = {256};
-      add(N, vf.out_dim[l], 1, main0, k, 64, TC_EPI_RELU, 0xFF, 0, l, 0, 0, 0, post);
+      add(N, vf.out_dim[l], 1, main0, k, 64, TC_EPI_RELU, 0xF, 0, l, 0, 0, 0, post);
     }
   }
   const int k256[1] = {256};
-  add(16, 3, 1, main0, k256, 256, TC_EPI_V, 0xFF, 0, L - 1, 0, 0, 0, 1.f);
+  add(16, 3, 1, main0, k256, 64, TC_EPI_V, 0xF, 0, L - 1, 0, 0, 0, 1.f);
   const int n_v = ns;
   add(256, 256, 1, main0, k256, 64, TC_EPI_FEAT, 0, 0, L - 1, 3, 0, 0, 1.f);
   const int n_full = ns;
@@ -583,9 +685,9 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
                   l, rn->in_dim[l], rn->out_dim[l]);
     }
     const int c[2] = {0, kColAux}, k[2] = {256, 48};
-    add(256, 256, 2, c, k, 64, TC_EPI_RELU, 0xFF | (1 << kBarAux), 1, 0, 0, 2, pr.small_w, 1.f);
-    for (int l = 1; l < Lr - 1; ++l) add(256, 256, 1, main0, k256, 64, TC_EPI_RELU, 0xFF, 1, l, 0, 0, 0, 1.f);
-    add(16, 3, 1, main0, k256, 256, TC_EPI_RGB, 0xFF, 1, Lr - 1, 0, 0, 0, 1.f);
+    add(256, 256, 2, c, k, 64, TC_EPI_RELU, 0xF | (1 << kBarAux), 1, 0, 0, 2, pr.small_w, 1.f);
+    for (int l = 1; l < Lr - 1; ++l) add(256, 256, 1, main0, k256, 64, TC_EPI_RELU, 0xF, 1, l, 0, 0, 0, 1.f);
+    add(16, 3, 1, main0, k256, 64, TC_EPI_RGB, 0xF, 1, Lr - 1, 0, 0, 0, 1.f);
   }
   plan.wpack_bytes = woff;
   pr.n_steps = ns; pr.render = 1;
@@ -633,6 +735,7 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   static long long* dbg_buf = nullptr;
   if ((dbg & 64) && !dbg_buf) VFN_CHECK_CUDA(cudaMalloc(&dbg_buf, 256 * sizeof(long long)));
   p.dbg_buf = (dbg & 64) ? dbg_buf : nullptr;
+  p.dbg = dbg & 63;
   if (p.dbg_buf) VFN_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), s));
   VFN_REQUIRE(out_v, "tc_forward: out_v is null");
   VFN_REQUIRE(mode != TC_MODE_RENDER || (colors && ray_dirs), "tc_forward: RENDER mode needs colors and ray_dirs");
@@ -642,7 +745,8 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
     VFN_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int64_t tiles = (n + kTileM - 1) / kTileM;
-  const int grid_x = (int)std::min<int64_t>(tiles, (int64_t)g_num_sms);
+  const int64_t pairs = (tiles + 1) / 2;
+  const int grid_x = 2 * (int)std::min<int64_t>(pairs, (int64_t)(g_num_sms / 2));
   const size_t smem = (size_t)kActCols * kTileM * 2 + (size_t)kTcStages * kStageBytes + 512;
   static bool attr = false;
   if (!attr) {
@@ -655,7 +759,7 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
     long long h[256];
     VFN_CHECK_CUDA(cudaStreamSynchronize(s));
     VFN_CHECK_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
-    const long long tc = (tiles + grid_x - 1) / grid_x;
+    const long long tc = (pairs + grid_x / 2 - 1) / (grid_x / 2);
     fprintf(stderr, "[tc dbg] tiles/CTA %lld steps %d | MMA thread cycles/tile: wait_grp %lld wait_full %lld issue %lld | "
             "epi h0: acc %lld ld %lld math %lld sig %lld other %lld | epi h1: acc %lld ld %lld math %lld sig %lld other %lld\n",
             tc, p.prog.n_steps, h[0] / tc, h[1] / tc, h[2] / tc, h[8] / tc, h[9] / tc, h[10] / tc, h[11] / tc, h[12] / tc,

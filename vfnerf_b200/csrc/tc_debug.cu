@@ -71,19 +71,31 @@ extern "C" int vfnerf_debug_umma_gemm(const float* A, const float* B, float* D, 
 // ---- micro-benchmark: cycles per tcgen05.mma (M=128, N, K=16) issued back to back by one thread of every CTA.
 // mode 0: MMAs only; mode 1: a tcgen05.commit after every second MMA (the ring-release pattern of mlp_tc.cu).
 namespace vfn {
-__global__ void __launch_bounds__(128) umma_bench_kernel(int N, int n_mma, int mode, int a_slabs, long long* out) {
+__global__ void __launch_bounds__(128) umma_bench_kernel(int N, int n_mma, int mode, int a_slabs, long long* out,
+                                                         const uint8_t* gsrc) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar, bar2;
+  __shared__ uint64_t bar, bar2, bar3;
+  __shared__ volatile int done_flag;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int e = tid; e < (64 + 128) * 1024 / 4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u;
-  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1 << 20); fence_barrier_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1 << 20); mbar_init(&bar3, 1); done_flag = 0; fence_barrier_init(); }
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
+  if (tid == 32 && (mode & 4)) {
+    // background weight-ring traffic: 16 KB bulk copies global -> shared, back to back, until the MMAs are done
+    int ph = 0;
+    while (!done_flag) {
+      mbar_arrive_expect_tx(&bar3, 16384);
+      bulk_g2s(smem + 192 * 1024, gsrc + (size_t)(blockIdx.x % 64) * 16384, 16384, &bar3);
+      mbar_wait(&bar3, ph);
+      ph ^= 1;
+    }
+  }
   if (tid == 0) {
     const uint32_t idesc = make_idesc_bf16(128, N);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 64 * 1024);
@@ -94,10 +106,24 @@ __global__ void __launch_bounds__(128) umma_bench_kernel(int N, int n_mma, int m
       const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32);
       const uint32_t a_lo0 = (uint32_t)da0, b_lo0 = (uint32_t)db0;
       const uint32_t a_step = (2 * slab_bytes(128)) >> 4, b_step = (2 * slab_bytes(N)) >> 4;
+      const bool stream = (mode & 2) != 0;    // walk over all 16 K-steps of the 64 KB A tile / 128 KB B tile instead of re-reading 4
       for (int i = 0; i < n_mma; i += 4) {
+        const uint32_t base = stream ? (uint32_t)((i >> 2) & 3) * 4u : 0u;
+        if (mode & 32) mbar_wait(&bar3, 1);          // already-complete phase: returns immediately
+        if (mode & 16) tc_fence_after_sync();
+        if (mode & 64) {
+          // the runtime-trip-count inner loop of mlp_tc.cu
+          uint32_t a_lo = a_lo0 + base * a_step, b_lo = b_lo0 + base * b_step, accumulate = i > 0;
+          const int kc = (n_mma > 7) ? 64 : 48;
+          for (int kk = 0; kk < kc; kk += 16) {
+            umma_bf16_split(tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+            accumulate = 1; a_lo += a_step; b_lo += b_step;
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          umma_bf16_split(tmem, a_lo0 + j * a_step, a_hi, b_lo0 + j * b_step, b_hi, idesc, (i | j) > 0);
+          umma_bf16_split(tmem, a_lo0 + (base + j) * a_step, a_hi, b_lo0 + (base + j) * b_step, b_hi, idesc, (i | j) > 0);
+        }
         if (mode & 1) umma_commit(&bar2);
       }
     } else
@@ -120,6 +146,7 @@ __global__ void __launch_bounds__(128) umma_bench_kernel(int N, int n_mma, int m
     umma_commit(&bar);
     mbar_wait(&bar, 0);
     long long t1 = clock64();
+    done_flag = 1;
     if (blockIdx.x == 0) out[0] = t1 - t0;
   }
   tc_fence_before_sync();
@@ -130,9 +157,94 @@ __global__ void __launch_bounds__(128) umma_bench_kernel(int N, int n_mma, int m
 
 extern "C" int vfnerf_debug_umma_bench(int N, int n_mma, int mode, int n_ctas, long long* cycles_dev, void* stream) {
   using namespace vfn;
-  size_t smem = (64 + 128) * 1024;
+  size_t smem = (64 + 128 + 16) * 1024;
+  static uint8_t* gsrc = nullptr;
+  if (!gsrc) { VFN_CHECK_CUDA(cudaMalloc(&gsrc, 64 * 16384)); VFN_CHECK_CUDA(cudaMemset(gsrc, 0, 64 * 16384)); }
   VFN_CHECK_CUDA(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  umma_bench_kernel<<<n_ctas, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(N, n_mma, mode, 32, cycles_dev);
+  umma_bench_kernel<<<n_ctas, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(N, n_mma, mode, 32, cycles_dev, gsrc);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- 2-CTA (cta_group::2) convention check: a cluster of two CTAs computes D[256 x N] = A[256 x K] * B[N x K]^T.
+// CTA r holds rows [128r, 128r+128) of A and rows [N/2 * r, N/2 * (r+1)) of B at identical shared-memory offsets;
+// the leader issues tcgen05.mma.cta_group::2 with M = 256; each CTA drains its own 128 accumulator rows.
+namespace vfn {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+umma2_debug_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = cluster_ctarank();
+  const int Nh = N / 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * K * 2;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int e = tid; e < 128 * K; e += 128) {
+    int r = e / K, k = e % K;
+    *reinterpret_cast<__nv_bfloat16*>(sA + slab_offset(128, r, k)) = __float2bfloat16(A[(int64_t)(rank * 128 + r) * K + k]);
+  }
+  for (int e = tid; e < Nh * K; e += 128) {
+    int r = e / K, k = e % K;
+    *reinterpret_cast<__nv_bfloat16*>(sB + slab_offset(Nh, r, k)) = __float2bfloat16(B[(int64_t)(rank * Nh + r) * K + k]);
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, N);
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      const uint64_t da = make_smem_desc(smem_u32(sA) + (k0 / 8) * slab_bytes(128), slab_bytes(128), 128);
+      const uint64_t db = make_smem_desc(smem_u32(sB) + (k0 / 8) * slab_bytes(Nh), slab_bytes(Nh), 128);
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+          "}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(k0 > 0)) : "memory");
+    }
+    // completion to the same barrier offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(int64_t)(rank * 128 + row) * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+}
+}  // namespace vfn
+
+extern "C" int vfnerf_debug_umma2_gemm(const float* A, const float* B, float* D, int N, int K, void* stream) {
+  using namespace vfn;
+  VFN_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256, "debug_umma2_gemm: bad N/K");
+  size_t smem = (size_t)(128 + N / 2) * K * 2;
+  VFN_CHECK_CUDA(cudaFuncSetAttribute(umma2_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma2_debug_kernel<<<2, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(A, B, D, N, K);
   VFN_LAUNCH_CHECK();
   return 0;
 }
