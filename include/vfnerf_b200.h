@@ -206,6 +206,8 @@ int vfnerf_debug_umma2_gemm(const float* A, const float* B, float* D, int N, int
 /* Micro-benchmark: every CTA issues n_mma back-to-back tcgen05.mma (M=128, N, K=16) from one thread; CTA 0 writes
  * the elapsed SM cycles to cycles_dev[0].  mode 1 adds a tcgen05.commit after every second MMA. */
 int vfnerf_debug_umma_bench(int N, int n_mma, int mode, int n_ctas, long long* cycles_dev, void* stream);
+/* Same for tcgen05.mma.cta_group::2 (M=256, N=256): mode 0 no commits, 1 multicast commit per 4 MMAs, 2 leader-only commit */
+int vfnerf_debug_umma2_bench(int n_mma, int mode, int n_ctas, long long* cycles_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,3 +13,10 @@ for n_ctas in (148,):
             _lib.check(L.vfnerf_debug_umma_bench(N, n, mode, n_ctas, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "bench")
             torch.cuda.synchronize()
             print(f"ctas={n_ctas:3d} N={N:3d} mode={mode} (commit per 4; +16 tcgen05 fence, +32 mbarrier wait, +64 runtime kk loop): {out[0].item() / n:7.1f} cycles / MMA (ideal {128 * N / 256:.0f})")
+
+for mode in (0, 1, 2):
+    n = 2048
+    _lib.check(L.vfnerf_debug_umma2_bench(n, mode, 148, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "bench2")
+    torch.cuda.synchronize()
+    print(f"2-CTA pairs=74 N=256 M=256 mode={mode} (0 none, 1 multicast commit / 4 MMAs, 2 leader-only commit): "
+          f"{out[0].item() / n:7.1f} cycles / MMA (ideal 128)")

@@ -75,6 +75,7 @@ PROTOTYPES = {
     "vfnerf_composite": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "vfnerf_debug_umma_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "vfnerf_debug_umma2_gemm": (_I, [_P, _P, _P, _I, _I, _P]),
+    "vfnerf_debug_umma2_bench": (_I, [_I, _I, _I, _P, _P]),
     "vfnerf_debug_umma_bench": (_I, [_I, _I, _I, _I, _P, _P]),
 }
 

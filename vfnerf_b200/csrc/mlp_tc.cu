@@ -29,14 +29,15 @@ namespace vfn {
 using namespace tc;
 
 constexpr int kTileM = 128;
-constexpr int kStageBytes = 16384;
-constexpr int kTcStages = 8;
-constexpr int kTcThreads = 320;
+constexpr int kStageBytes = 32768;
+constexpr int kTcStages = 3;
+constexpr int kTcThreads = 448;      // warp 0 producer, warp 1 MMA/relay, warps 2..9 epilogue, warps 10..13 prologue
 constexpr int kAccCols = 256;
 constexpr float kInvSqrt2 = 0.70710678118654752f;
-// readiness barriers: 0..3 = 64-column groups of the main region (one per K chunk), 4 = aux region, 5 = skip region.
-// Every barrier expects one arrival from each of the 8 epilogue warps of both CTAs of the pair.
-constexpr int kGroups = 6, kBarAux = 4, kBarSkip = 5, kGrpArrivals = 16;
+// readiness barriers (leader CTA): 0..3 = 64-column groups of the main region (one per K chunk; group g is written by
+// the epilogue warps of half g%2), 4 = the normal in the aux region (half-0 epilogue warps); 5 = skip region, 6 = emb0
+// region, 7 = point/view part of the aux region (prologue warps).  Each expects 4 warps x 2 CTAs = 8 arrivals.
+constexpr int kGroups = 8, kBarAux = 4, kBarSkip = 5, kBarEmb0 = 6, kBarAuxStatic = 7;
 
 struct TcParams {
   TcProgram prog;
@@ -98,7 +99,15 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
         int src = -1;
         if (st.colmap == 0) src = kin;
         else if (st.colmap == 1) { src = kin < Epad ? kin : kin - Epad; if (src >= E) src = -1; }
-        else if (st.colmap == 2) src = sg == 0 ? st.src_split + kin : (kin < st.src_split ? kin : -1);
+        else if (st.colmap == 2) {
+          // colour-net layer 0: main segment = features; aux segment = [n(3), 0 x5, p(3), embed(view), 0...]
+          const int ev = st.src_split - 6;                    // width of the view-direction embedding
+          if (sg == 0) src = st.src_split + kin;
+          else if (kin < 3) src = 3 + ev + kin;               // normals (reference columns 3+ev ..)
+          else if (kin >= 8 && kin < 11) src = kin - 8;       // point
+          else if (kin >= 11 && kin < 11 + ev) src = 3 + (kin - 11);
+          else src = -1;
+        }
         else src = sg == 0 ? (kin < st.src_split ? kin : -1) : (kin < E ? st.src_split + kin : -1);
         if (src >= 0 && src < in_dim) w = arena[d.w_off[l] + (int64_t)row * in_dim + src] * sc * st.post_scale;
       }
@@ -179,8 +188,13 @@ __device__ __forceinline__ void load_point(const TcParams& p, long long pi, bool
 }
 
 // readiness barrier that guards activation-tile column `col` (-1: constant region, nothing to wait for)
-__device__ __forceinline__ int col_barrier(int col) {
-  return col < kColAux ? (col >> 6) : (col < kColSkip ? kBarAux : (col < kColOnes ? kBarSkip : -1));
+// readiness barriers (bit mask) that guard the 64-column chunk starting at activation-tile column `col`
+__device__ __forceinline__ uint32_t col_barriers(int col) {
+  if (col < kColAux) return 1u << (col >> 6);
+  if (col < kColSkip) return (1u << kBarAux) | (1u << kBarAuxStatic);
+  if (col < kColOnes) return 1u << kBarSkip;
+  if (col < kColEmb0) return 0u;
+  return 1u << kBarEmb0;
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -230,6 +244,23 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// 32-bit shared-address forms for the single-lane issue loop (no generic->shared conversion per call)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_u32(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 #define TCK(acc_) do { if (prof) { long long t1_ = clock64(); acc_ += t1_ - t0; t0 = t1_; } } while (0)
 
 // ---------------------------------------------------------------------------------------------
@@ -246,8 +277,15 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   uint64_t* empty = bars + kTcStages;
   uint64_t* fullp = bars + 2 * kTcStages;      // leader only: "the peer's half of the chunk has landed"
   uint64_t* acc_full = bars + 3 * kTcStages;
-  uint64_t* grp = acc_full + 1;                 // leader only: A-operand readiness, 128 local + 128 remote arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(grp + kGroups);
+  uint64_t* grp = acc_full + 1;                 // leader only: A-operand readiness
+  uint64_t* reg_free = grp + kGroups;           // [0] emb0, [1] skip, [2] aux-static: their reader MMAs have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reg_free + 3);
+  // chunk table: the single-lane producer / MMA-issuer loops must not chase per-chunk facts through the kernel
+  // parameters (dependent constant loads cost them ~500 cycles per chunk): everything a chunk needs is one LDS.128.
+  //   x = A start-address increment (16-byte units), y = K columns | readiness-barrier mask << 16,
+  //   z = bytes of this CTA's half of the weight chunk, w = 1 on the last chunk of the step
+  uint4* s_chunks = reinterpret_cast<uint4*>(bars + 64);
+  int* s_nchunks = reinterpret_cast<int*>(s_chunks + kTcMaxSteps * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -255,12 +293,34 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     // leader: a ring slot is full when its own bulk copy has landed AND the peer's relay has arrived
     for (int i = 0; i < kTcStages; ++i) { mbar_init(&full[i], rank == 0 ? 2 : 1); mbar_init(&empty[i], 1); mbar_init(&fullp[i], 1); }
     mbar_init(acc_full, 1);
-    for (int i = 0; i < kGroups; ++i) mbar_init(&grp[i], kGrpArrivals);
+    for (int i = 0; i < kGroups; ++i) mbar_init(&grp[i], 8);    // 4 warps (one half, or the prologue warps) x 2 CTAs
+    for (int i = 0; i < 3; ++i) mbar_init(&reg_free[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 256 && threadIdx.x < 256 + prog.n_steps) {
+    const int si = threadIdx.x - 256;
+    const TcStep& st = prog.s[si];
+    uint32_t seen = 0;
+    int nc = 0;
+    for (int sg = 0; sg < st.n_seg; ++sg) {
+      for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
+        const int kc = min(st.chunk_k, st.seg_k[sg] - k0);
+        const int col = st.seg_col0[sg] + k0;
+        uint32_t need = 0;
+        for (int cc = col; cc < col + kc; cc += 64) need |= col_barriers(cc);
+        need &= (uint32_t)st.fresh_mask & ~seen;
+        seen |= need;
+        s_chunks[si * 8 + nc] = make_uint4((uint32_t)(col >> 3) * ((kTileM * 16u) >> 4), (uint32_t)kc | (need << 16),
+                                           (uint32_t)((st.N >> 1) * kc * 2), 0u);
+        ++nc;
+      }
+    }
+    s_chunks[si * 8 + nc - 1].w = 1u;
+    s_nchunks[si] = nc;
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kTileM) {
     // constant ones-columns [1, 1, 0, ...] that pick up the bias row of every weight image
@@ -292,18 +352,16 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
         for (int si = 0; si < prog.n_steps; ++si) {
           const TcStep& st = prog.s[si];
-          const int nh = st.N >> 1;
-          const uint8_t* src = p.wpack + st.w_off + (int64_t)rank * nh * st.K * 2;
-          for (int sg = 0; sg < st.n_seg; ++sg) {
-            for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
-              const int kc = min(st.chunk_k, st.seg_k[sg] - k0);
-              const uint32_t bytes = (uint32_t)(nh * kc * 2);
-              mbar_wait(&empty[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full[stage], bytes);
-              bulk_g2s(s_stage + stage * kStageBytes, src, bytes, &full[stage]);
-              src += bytes;
-              if (++stage == kTcStages) { stage = 0; phase ^= 1; }
-            }
+          const uint8_t* src = p.wpack + st.w_off + (int64_t)rank * (st.N >> 1) * st.K * 2;
+          const uint4* ck = s_chunks + si * 8;
+          for (;; ++ck) {
+            const uint4 c = *ck;
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], c.z);
+            bulk_g2s(s_stage + stage * kStageBytes, src, c.z, &full[stage]);
+            src += c.z;
+            if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            if (c.w) break;
           }
         }
       }
@@ -314,13 +372,11 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       int stage = 0, phase = 0;
       for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
         for (int si = 0; si < prog.n_steps; ++si) {
-          const TcStep& st = prog.s[si];
-          for (int sg = 0; sg < st.n_seg; ++sg) {
-            for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
-              mbar_wait(&full[stage], phase);           // my half of the chunk is in my shared memory
-              mbar_arrive_remote(&full[stage], 0);      // second arrival on the leader's "slot full" barrier
-              if (++stage == kTcStages) { stage = 0; phase ^= 1; }
-            }
+          const int nc = s_nchunks[si];
+          for (int c = 0; c < nc; ++c) {
+            mbar_wait(&full[stage], phase);           // my half of the chunk is in my shared memory
+            mbar_arrive_remote(&full[stage], 0);      // second arrival on the leader's "slot full" barrier
+            if (++stage == kTcStages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -333,6 +389,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       const bool prof = p.dbg_buf && blockIdx.x == 0;
       if (prof) t0 = clock64();
       const uint32_t act_base = smem_u32(s_act), stage_base = smem_u32(s_stage);
+      const uint32_t grp_u32 = smem_u32(grp), full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
       int tile_no = 0;
       for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++tile_no) {
         const bool tl = prof && tile_no == 2;
@@ -346,7 +403,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const uint32_t b_lo0 = ((stage_base >> 4) & 0x3FFF) | ((((uint32_t)(st.N >> 1) * 16u) >> 4) << 16);
           const uint32_t b_kstep = (uint32_t)st.N;                             // two K-slabs of the HALF weight chunk, in 16-byte units
           const uint32_t acc = tmem + (gstep & 1) * kAccCols;
-          uint32_t fresh = (p.dbg & 1) ? 0u : (uint32_t)st.fresh_mask;
+          const uint32_t fresh = (p.dbg & 1) ? 0u : 0xFFFFu;   // per-chunk masks are pre-filtered in the chunk table
           uint32_t accumulate = 0;
           TCK(t_issue);
           for (int g = 0; g < kGroups; ++g) {
@@ -355,50 +412,138 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               grp_par ^= (1u << g);
             }
           }
-          for (int sg = 0; sg < st.n_seg; ++sg) {
-            for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
-              const int kc = min(st.chunk_k, st.seg_k[sg] - k0);
-              const int col = st.seg_col0[sg] + k0;
-              // the A columns of this chunk must have been (re)written: one readiness barrier per chunk
-              const int b = col_barrier(col);
-              if (b >= 0 && (fresh & (1u << b))) {
-                mbar_wait_cluster(&grp[b], (grp_par >> b) & 1u);
+          const uint4* ckp = s_chunks + si * 8;
+          uint4 ck = *ckp;
+          for (;;) {
+            const uint4 nxt = ckp[1];                      // next chunk's facts arrive while this chunk's MMAs issue
+            // the A columns of this chunk must have been (re)written: wait for their readiness barrier(s) (at most two)
+            uint32_t need = (ck.y >> 16) & fresh;
+            if (need) {
+              int b = __ffs(need) - 1;
+              mbar_wait_u32(grp_u32 + 8u * b, (grp_par >> b) & 1u);
+              grp_par ^= (1u << b);
+              need &= need - 1;
+              if (need) {
+                b = __ffs(need) - 1;
+                mbar_wait_u32(grp_u32 + 8u * b, (grp_par >> b) & 1u);
                 grp_par ^= (1u << b);
-                fresh &= ~(1u << b);
               }
-              TCK(t_grp);
-              mbar_wait_cluster(&full[stage], phase);      // both halves of the weight chunk have landed
-              TCK(t_full);
-              tc_fence_after_sync();
-              const uint32_t a_lo = a_lo0 + (uint32_t)(col >> 3) * ((kTileM * 16u) >> 4);
-              const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kStageBytes >> 4);
-              constexpr uint32_t a_kstep = 2u * ((kTileM * 16u) >> 4);
-              if (tl && first_mma) { p.dbg_buf[64 + si * 8 + 0] = clock64(); first_mma = false; }
-              if (kc == 64) {
-                // steady state: four MMAs with constant descriptor increments (the issue thread must stay well
-                // under 128 cycles of scalar work per MMA, profiles/run_umma_bench.py)
-                umma2_bf16_split(acc, a_lo, desc_hi, b_lo, desc_hi, idesc, accumulate);
-                umma2_bf16_split(acc, a_lo + a_kstep, desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
-                umma2_bf16_split(acc, a_lo + 2 * a_kstep, desc_hi, b_lo + 2 * b_kstep, desc_hi, idesc, 1u);
-                umma2_bf16_split(acc, a_lo + 3 * a_kstep, desc_hi, b_lo + 3 * b_kstep, desc_hi, idesc, 1u);
-              } else {
-                uint32_t al = a_lo, bl = b_lo, ac = accumulate;
-                for (int kk = 0; kk < kc; kk += 16) {
-                  umma2_bf16_split(acc, al, desc_hi, bl, desc_hi, idesc, ac);
-                  ac = 1u; al += a_kstep; bl += b_kstep;
-                }
-              }
-              accumulate = 1;
-              umma2_commit(&empty[stage]);         // ring slot (in both CTAs) reusable once these MMAs have read it
-              if (++stage == kTcStages) { stage = 0; phase ^= 1; }
             }
+            TCK(t_grp);
+            mbar_wait_u32(full_u32 + 8u * stage, phase);   // both halves of the weight chunk have landed
+            TCK(t_full);
+            tc_fence_after_sync();
+            const uint32_t a_lo = a_lo0 + ck.x;
+            const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kStageBytes >> 4);
+            constexpr uint32_t a_kstep = 2u * ((kTileM * 16u) >> 4);
+            const int kc = (int)(ck.y & 0xFFFFu);
+            if (tl && first_mma) { p.dbg_buf[64 + si * 8 + 0] = clock64(); first_mma = false; }
+            if (kc == 128) {
+              // steady state: eight MMAs with constant descriptor increments (the issue thread must stay well
+              // under 128 cycles of scalar work per MMA, profiles/run_umma_bench.py)
+              umma2_bf16_split(acc, a_lo, desc_hi, b_lo, desc_hi, idesc, accumulate);
+#pragma unroll
+              for (uint32_t j = 1; j < 8; ++j)
+                umma2_bf16_split(acc, a_lo + j * a_kstep, desc_hi, b_lo + j * b_kstep, desc_hi, idesc, 1u);
+            } else {
+              uint32_t al = a_lo, bl = b_lo, ac = accumulate;
+              for (int kk = 0; kk < kc; kk += 16) {
+                umma2_bf16_split(acc, al, desc_hi, bl, desc_hi, idesc, ac);
+                ac = 1u; al += a_kstep; bl += b_kstep;
+              }
+            }
+            accumulate = 1;
+            umma2_commit_u32(empty_u32 + 8u * stage);      // ring slot (in both CTAs) reusable once these MMAs have read it
+            if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            if (ck.w) break;
+            ck = nxt; ++ckp;
           }
           umma2_commit(acc_full);                  // accumulators complete -> epilogue warps of both CTAs
+          // side regions whose only reader was this step may now be rewritten for the next tile (prologue warps)
+          if (si == 0) umma2_commit(&reg_free[0]);
+          if (si == prog.skip_step) umma2_commit(&reg_free[1]);
+          if (si == prog.aux_step) umma2_commit(&reg_free[2]);
           if (tl) p.dbg_buf[64 + si * 8 + 1] = clock64();
         }
       }
       TCK(t_issue);
       if (prof) { p.dbg_buf[0] = t_grp; p.dbg_buf[1] = t_full; p.dbg_buf[2] = t_issue; }
+    }
+  } else if (warp >= 10) {
+    // ===================== prologue warps (one row per thread) =====================
+    // They build, one tile ahead, every A-operand region that depends only on the inputs: the bf16 hi|lo positional
+    // encoding of layer 0 (emb0 columns), the encoding / sqrt(2) for the skip layer, and the point + view-direction
+    // part of the colour net's small inputs.  A region is rewritten only after the MMAs that read it for the
+    // previous tile have completed (reg_free barriers, committed by the MMA issuer).
+    const int row = threadIdx.x - 320;
+    const int E = prog.emb_w, Epad = prog.emb_pad, nsl = Epad >> 3;
+    auto tile_of = [&](long long pair) { return 2 * pair + (long long)rank; };
+    auto arrive_pro = [&](int b) {
+      __syncwarp();
+      if (lane == 0) { if (rank == 0) mbar_arrive(&grp[b]); else mbar_arrive_remote(&grp[b], 0); }
+    };
+    int n = 0;
+    for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++n) {
+      const long long pi = tile_of(pair) * kTileM + row;
+      const bool valid = pi < p.n_points;
+      float pt[3], emb[48];
+      load_point(p, pi, valid, pt);
+#pragma unroll
+      for (int i = 0; i < 48; ++i) emb[i] = 0.f;
+      embed3(pt, prog.multires, emb);
+#pragma unroll
+      for (int i = 0; i < 48; ++i)
+        if (i >= E) emb[i] = 0.f;
+      // ---- emb0: hi slabs then lo slabs
+      if (n > 0) mbar_wait(&reg_free[0], (n - 1) & 1);
+#pragma unroll
+      for (int sl = 0; sl < 6; ++sl) {
+        if (sl < nsl) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float v = emb[sl * 8 + j];
+            hi[j] = __bfloat162float(__float2bfloat16(v));
+            lo[j] = v - hi[j];
+          }
+          store_slab_f(s_act, kColEmb0 / 8 + sl, row, hi);
+          store_slab_f(s_act, kColEmb0 / 8 + nsl + sl, row, lo);
+        }
+      }
+      fence_proxy_async_smem();
+      arrive_pro(kBarEmb0);
+      // ---- skip region: embedding / sqrt(2)
+      if (prog.skip_step >= 0) {
+        if (n > 0) mbar_wait(&reg_free[1], (n - 1) & 1);
+#pragma unroll
+        for (int i = 0; i < 48; ++i) emb[i] *= kInvSqrt2;
+#pragma unroll
+        for (int sl = 0; sl < 6; ++sl) store_slab_f(s_act, kColSkip / 8 + sl, row, emb + 8 * sl);
+        fence_proxy_async_smem();
+        arrive_pro(kBarSkip);
+      }
+      // ---- aux region, columns 8..47: [p(3), embed(view dir)(3+6*Lv), 0...]  (columns 0..7 belong to the V step)
+      if (prog.aux_step >= 0) {
+        float a[40], d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 40; ++j) a[j] = 0.f;
+        if (valid) {
+          const long long r = pi / p.samples_per_ray;
+          d[0] = __ldg(p.ray_dirs + 3 * r); d[1] = __ldg(p.ray_dirs + 3 * r + 1); d[2] = __ldg(p.ray_dirs + 3 * r + 2);
+        }
+        embed3(d, prog.multires_view, a + 3);
+        const int ev = 3 + 6 * prog.multires_view;
+#pragma unroll
+        for (int j = 0; j < 40; ++j) {
+          if (j < 3) a[j] = pt[j];
+          if (j >= 3 + ev) a[j] = 0.f;
+        }
+        if (n > 0) mbar_wait(&reg_free[2], (n - 1) & 1);
+#pragma unroll
+        for (int sl = 0; sl < 5; ++sl) store_slab_f(s_act, kColAux / 8 + 1 + sl, row, a + 8 * sl);
+        fence_proxy_async_smem();
+        arrive_pro(kBarAuxStatic);
+      }
     }
   } else {
     // ===================== epilogue warps =====================
@@ -406,68 +551,12 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     const int h = (warp - 2) >> 2;          // column-group parity: this warp owns groups g with g % 2 == h
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const int E = prog.emb_w, Epad = prog.emb_pad;
     const bool render = prog.render != 0;
     uint32_t gstep = 0;
     long long t_acc = 0, t_ld = 0, t_math = 0, t_sig = 0, t_other = 0, t0 = 0;
     const bool prof = p.dbg_buf && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 3);
     auto tile_of = [&](long long pair) { return 2 * pair + (long long)rank; };
     if (prof) t0 = clock64();
-
-    // A operand of step 0 (half-0 warps: bf16 hi/lo split of the embedding -> main columns [0, 2*Epad)) and the skip
-    // layer's extra input (half-1 warps: embedding / sqrt(2) -> skip columns).  Both are computed for the NEXT tile
-    // while this tile's MMAs run: half 1 stores right away (the skip columns are free once the skip step's MMAs
-    // are done), half 0 parks the packed values in registers and stores them during the last step.
-    uint32_t pk0[24];
-    auto embed_tile = [&](long long tile, float* emb) {
-      const long long pi = tile * kTileM + row;
-      float pt[3];
-      load_point(p, pi, pi < p.n_points, pt);
-#pragma unroll
-      for (int i = 0; i < 48; ++i) emb[i] = 0.f;
-      embed3(pt, prog.multires, emb);
-#pragma unroll
-      for (int i = 0; i < 48; ++i)
-        if (i >= E) emb[i] = 0.f;
-    };
-    // half-0 warps keep the bf16 "hi" part of the embedding, half-1 warps the "lo" remainder
-    auto prologue_compute = [&](long long tile) {
-      float emb[48];
-      embed_tile(tile, emb);
-#pragma unroll
-      for (int j = 0; j < 24; ++j) {
-        const float a = emb[2 * j], b = emb[2 * j + 1];
-        const float ah = __bfloat162float(__float2bfloat16(a)), bh = __bfloat162float(__float2bfloat16(b));
-        pk0[j] = h == 0 ? pack_bf16x2(ah, bh) : pack_bf16x2(a - ah, b - bh);
-      }
-    };
-    auto prologue_store = [&]() {
-      const int nsl = Epad >> 3;
-#pragma unroll
-      for (int sl = 0; sl < 6; ++sl)
-        if (sl < nsl) store_slab_u(s_act, h * nsl + sl, row, pk0[4 * sl], pk0[4 * sl + 1], pk0[4 * sl + 2], pk0[4 * sl + 3]);
-      fence_proxy_async_smem();
-      const int ng = (2 * Epad + 63) >> 6;
-      for (int g = 0; g < ng; ++g) arrive_grp(g);
-    };
-    auto prologue_skip = [&](long long tile) {
-      if (h == 1) {
-        float emb[48];
-        embed_tile(tile, emb);
-#pragma unroll
-        for (int i = 0; i < 48; ++i) emb[i] *= kInvSqrt2;
-#pragma unroll
-        for (int sl = 0; sl < 6; ++sl) store_slab_f(s_act, kColSkip / 8 + sl, row, emb + 8 * sl);
-        fence_proxy_async_smem();
-      }
-      arrive_grp(kBarSkip);
-    };
-
-    if (pair0 < num_pairs) {
-      prologue_compute(tile_of(pair0));
-      prologue_store();
-      if (prog.skip_step >= 0) prologue_skip(tile_of(pair0));
-    }
 
     int tile_no = 0;
     for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++tile_no) {
@@ -486,45 +575,63 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         if (st.epi == TC_EPI_RELU || st.epi == TC_EPI_FEAT) {
           const bool feat = st.epi == TC_EPI_FEAT;
           const bool to_act = !feat || render;
-          uint32_t v[32];
-          if (h * 32 < st.N) tmem_ld32(acc + h * 32, v);
+          const int stN = st.N;
+          if (to_act) {
+            // Each warp owns two of the four 64-column groups (= K chunks of the next layer): h=0 -> groups 0 and 2,
+            // h=1 -> groups 1 and 3.  One generic->async proxy fence (a MEMBAR.ALL.CTA) and one barrier arrival per
+            // 64 columns: the fence, not the math, is the expensive part of this loop.
 #pragma unroll 1
-          for (int gi = 0; gi < 4; ++gi) {
-            const int g = 2 * gi + h, c0 = g * 32;
-            if (c0 >= st.N) {                       // narrow layer: nothing to write, but the barrier still expects this warp
-              if (to_act) arrive_grp(g >> 1);
-              continue;
-            }
-            TCK(t_other);
-            tmem_ld_wait();
-            TCK(t_ld);
-            if (p.dbg & 2) {
-              if (to_act) { tc_fence_before_sync(); arrive_grp(g >> 1); }
-              continue;
-            }
-            if (to_act) {
-              uint32_t pk[16];
+            for (int it = 0; it < 2; ++it) {
+              const int bg = 2 * it + h, c0 = bg * 64;
+              if (c0 >= stN) { arrive_grp(bg); continue; }     // narrow layer: nothing to write, the barrier still counts us
+              const bool second = c0 + 32 < stN;
+              uint32_t va[32], vb[32];
+              TCK(t_other);
+              tmem_ld32(acc + c0, va);
+              if (second) tmem_ld32(acc + c0 + 32, vb);
+              tmem_ld_wait();
+              TCK(t_ld);
+              if (!(p.dbg & 2)) {
+                uint32_t pk[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const uint32_t b2 = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                pk[j] = feat ? tanh_bf16x2(b2) : relu_bf16x2(b2);
+                for (int j = 0; j < 16; ++j) {
+                  const uint32_t b2 = pack_bf16x2(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
+                  pk[j] = feat ? tanh_bf16x2(b2) : relu_bf16x2(b2);
+                }
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl)
+                  store_slab_u(s_act, (c0 >> 3) + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+                if (second) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const uint32_t b2 = pack_bf16x2(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
+                    pk[j] = feat ? tanh_bf16x2(b2) : relu_bf16x2(b2);
+                  }
+#pragma unroll
+                  for (int sl = 0; sl < 4; ++sl)
+                    store_slab_u(s_act, (c0 >> 3) + 4 + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+                }
               }
-              if (c0 + 64 < st.N) tmem_ld32(acc + c0 + 64, v);        // next group in flight behind the stores
-#pragma unroll
-              for (int sl = 0; sl < 4; ++sl)
-                store_slab_u(s_act, (c0 >> 3) + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
               TCK(t_math);
               fence_proxy_async_smem();
               tc_fence_before_sync();
-              arrive_grp(g >> 1);
+              arrive_grp(bg);
               TCK(t_sig);
-              if (tl && gi == 0) p.dbg_buf[64 + si * 8 + 3 + 3 * h] = clock64();
+              if (tl && it == 0) p.dbg_buf[64 + si * 8 + 3 + 3 * h] = clock64();
               if (tl) p.dbg_buf[64 + si * 8 + 4 + 3 * h] = clock64();
-            } else {
+            }
+          } else {
+            // VF_FULL: features go to global memory as fp32 (module-call output), 32 columns at a time
+#pragma unroll 1
+            for (int gi = 0; gi < 4; ++gi) {
+              const int c0 = (2 * gi + h) * 32;
+              if (c0 >= stN) continue;
+              uint32_t v[32];
+              tmem_ld32(acc + c0, v);
+              tmem_ld_wait();
               float f[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = tanh_fast(__uint_as_float(v[j]));
-              if (c0 + 64 < st.N) tmem_ld32(acc + c0 + 64, v);
               if (p.out_feat && valid) {
                 float* o = p.out_feat + pi * p.feat_ld + c0;
                 if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
@@ -536,7 +643,6 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                   for (int j = 0; j < 32; ++j) o[j] = f[j];
                 }
               }
-              TCK(t_math);
             }
           }
         } else if (st.epi == TC_EPI_V) {
@@ -552,37 +658,18 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               for (int j = 0; j < 3; ++j) p.out_v[pi * p.v_ld + j] = nv[j];
             }
             if (render) {
-              // colour-net small inputs [p(3), embed(view dir)(3+6*Lv), n(3), 0...] -> aux columns
-              float a[48];
-#pragma unroll
-              for (int j = 0; j < 48; ++j) a[j] = 0.f;
-              float pt[3], d[3] = {0.f, 0.f, 0.f};
-              load_point(p, pi, valid, pt);
-              if (valid) {
-                const long long r = pi / p.samples_per_ray;
-                d[0] = __ldg(p.ray_dirs + 3 * r); d[1] = __ldg(p.ray_dirs + 3 * r + 1); d[2] = __ldg(p.ray_dirs + 3 * r + 2);
-              }
-              embed3(d, prog.multires_view, a + 3);
-              const int ev = 3 + 6 * prog.multires_view;
-#pragma unroll
-              for (int j = 0; j < 48; ++j) {
-                if (j < 3) a[j] = pt[j];
-                if (j >= 3 + ev) a[j] = 0.f;
-                if (j == 3 + ev) a[j] = nv[0];
-                if (j == 4 + ev) a[j] = nv[1];
-                if (j == 5 + ev) a[j] = nv[2];
-              }
-#pragma unroll
-              for (int sl = 0; sl < 6; ++sl) store_slab_f(s_act, kColAux / 8 + sl, row, a + 8 * sl);
+              // the normal is the first 16-byte unit of the colour net's small inputs (aux columns 0..7)
+              float a[8] = {nv[0], nv[1], nv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+              store_slab_f(s_act, kColAux / 8, row, a);
               fence_proxy_async_smem();
             }
-          }
-          // RENDER: the aux columns are ready.  VF_FULL: the FEAT step's MMAs do not depend on any A rewrite; this
-          // arrival orders them (and through them the next tile's first MMA into this accumulator buffer) after the
-          // accumulator read above.  Half-1 warps arrive too (every barrier expects all 8 warps).
-          if (si + 1 < prog.n_steps) {
-            tc_fence_before_sync();
-            arrive_grp(kBarAux);
+            // RENDER: the aux columns are ready.  VF_FULL: the FEAT step's MMAs do not depend on any A rewrite; this
+            // arrival orders them (and through them the next tile's first MMA into this accumulator buffer) after the
+            // accumulator read above.
+            if (si + 1 < prog.n_steps) {
+              tc_fence_before_sync();
+              arrive_grp(kBarAux);
+            }
           }
         } else {  // TC_EPI_RGB
           if (h == 0) {
@@ -594,13 +681,6 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               for (int j = 0; j < 3; ++j) p.colors[3 * pi + j] = 1.f / (1.f + expf(-__uint_as_float(v[j])));
             }
           }
-        }
-        // next tile's prologue, off the critical path (see above)
-        if (pair + pair_step < num_pairs) {
-          const long long nxt = tile_of(pair + pair_step);
-          if (si == 0) prologue_compute(nxt);
-          if (si == prog.n_steps - 1) prologue_store();        // this step's MMAs have finished reading the A tile
-          if (si == prog.skip_step) prologue_skip(nxt);         // the skip step's MMAs (the only readers) are done
         }
         tc_fence_before_sync();
       }
@@ -639,6 +719,7 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   pr.emb_w = E; pr.emb_pad = Epad; pr.multires = multires; pr.multires_view = multires_view;
   pr.small_w = 3 + (3 + 6 * multires_view) + 3;
   pr.skip_step = skip_layer;
+  pr.aux_step = -1;
   int ns = 0;
   long long woff = 0;
   // appends a step; the bias (ones) segment is added automatically as the last segment
@@ -659,24 +740,25 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
     const int N = round16(vf.out_dim[l]);
     if (l == 0) {
       const int k[1] = {2 * Epad};
-      add(N, vf.out_dim[l], 1, main0, k, 64, TC_EPI_RELU, (1 << ((2 * Epad + 63) / 64)) - 1, 0, l, 0, 1, 0, post);
+      const int c0[1] = {kColEmb0};
+      add(N, vf.out_dim[l], 1, c0, k, 128, TC_EPI_RELU, 1 << kBarEmb0, 0, l, 0, 1, 0, post);
     } else if (l == skip_layer) {
       const int prev = vf.out_dim[l - 1];
       const int c[2] = {0, kColSkip}, k[2] = {round16(prev), 48};
-      add(N, vf.out_dim[l], 2, c, k, 64, TC_EPI_RELU, 0xF | (1 << kBarSkip), 0, l, 0, 3, prev, post);
+      add(N, vf.out_dim[l], 2, c, k, 128, TC_EPI_RELU, 0xF | (1 << kBarSkip), 0, l, 0, 3, prev, post);
     } else {
       const int k[1] = {256};
-      add(N, vf.out_dim[l], 1, main0, k, 64, TC_EPI_RELU, 0xF, 0, l, 0, 0, 0, post);
+      add(N, vf.out_dim[l], 1, main0, k, 128, TC_EPI_RELU, 0xF, 0, l, 0, 0, 0, post);
     }
   }
   const int k256[1] = {256};
-  add(16, 3, 1, main0, k256, 64, TC_EPI_V, 0xF, 0, L - 1, 0, 0, 0, 1.f);
+  add(16, 3, 1, main0, k256, 128, TC_EPI_V, 0xF, 0, L - 1, 0, 0, 0, 1.f);
   const int n_v = ns;
-  add(256, 256, 1, main0, k256, 64, TC_EPI_FEAT, 0, 0, L - 1, 3, 0, 0, 1.f);
+  add(256, 256, 1, main0, k256, 128, TC_EPI_FEAT, 0, 0, L - 1, 3, 0, 0, 1.f);
   const int n_full = ns;
   if (rn) {
     const int Lr = rn->n_layers;
-    VFN_REQUIRE(pr.small_w <= 48, "tensor-core path: colour-net small inputs %d > 48", pr.small_w);
+    VFN_REQUIRE(pr.small_w + 5 <= 48, "tensor-core path: colour-net small inputs %d too wide", pr.small_w);
     for (int l = 0; l < Lr; ++l) {
       const int want_in = (l == 0) ? pr.small_w + 256 : 256;
       const int want_out = (l == Lr - 1) ? 3 : 256;
@@ -685,16 +767,17 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
                   l, rn->in_dim[l], rn->out_dim[l]);
     }
     const int c[2] = {0, kColAux}, k[2] = {256, 48};
-    add(256, 256, 2, c, k, 64, TC_EPI_RELU, 0xF | (1 << kBarAux), 1, 0, 0, 2, pr.small_w, 1.f);
-    for (int l = 1; l < Lr - 1; ++l) add(256, 256, 1, main0, k256, 64, TC_EPI_RELU, 0xF, 1, l, 0, 0, 0, 1.f);
-    add(16, 3, 1, main0, k256, 64, TC_EPI_RGB, 0xF, 1, Lr - 1, 0, 0, 0, 1.f);
+    pr.aux_step = ns;
+    add(256, 256, 2, c, k, 128, TC_EPI_RELU, 0xF | (1 << kBarAux) | (1 << kBarAuxStatic), 1, 0, 0, 2, pr.small_w, 1.f);
+    for (int l = 1; l < Lr - 1; ++l) add(256, 256, 1, main0, k256, 128, TC_EPI_RELU, 0xF, 1, l, 0, 0, 0, 1.f);
+    add(16, 3, 1, main0, k256, 128, TC_EPI_RGB, 0xF, 1, Lr - 1, 0, 0, 0, 1.f);
   }
   plan.wpack_bytes = woff;
   pr.n_steps = ns; pr.render = 1;
   plan.render = pr;
-  plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.render = 0;
+  plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.render = 0; plan.vf_full.aux_step = -1;
   plan.vf_full.s[n_full - 1].pre_wait_mask = 1 << kBarAux;
-  plan.v_only = pr; plan.v_only.n_steps = n_v; plan.v_only.render = 0;
+  plan.v_only = pr; plan.v_only.n_steps = n_v; plan.v_only.render = 0; plan.v_only.aux_step = -1;
   return 0;
 }
 
@@ -747,7 +830,7 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   const int64_t tiles = (n + kTileM - 1) / kTileM;
   const int64_t pairs = (tiles + 1) / 2;
   const int grid_x = 2 * (int)std::min<int64_t>(pairs, (int64_t)(g_num_sms / 2));
-  const size_t smem = (size_t)kActCols * kTileM * 2 + (size_t)kTcStages * kStageBytes + 512;
+  const size_t smem = (size_t)kActCols * kTileM * 2 + (size_t)kTcStages * kStageBytes + 512 + kTcMaxSteps * 8 * 16 + 128;
   static bool attr = false;
   if (!attr) {
     VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -765,6 +848,8 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
             tc, p.prog.n_steps, h[0] / tc, h[1] / tc, h[2] / tc, h[8] / tc, h[9] / tc, h[10] / tc, h[11] / tc, h[12] / tc,
             h[16] / tc, h[17] / tc, h[18] / tc, h[19] / tc, h[20] / tc);
     const long long base = h[64];
+
+
     for (int si = 0; si < p.prog.n_steps && base; ++si) {
       const long long* e = h + 64 + si * 8;
       fprintf(stderr, "[tc timeline] step %2d: first_mma %6lld commit %6lld | h0: acc_seen %6lld first_arrive %6lld last_arrive %6lld | "

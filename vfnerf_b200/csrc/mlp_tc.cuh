@@ -9,11 +9,14 @@ constexpr int kTcMaxSegs = 3;
 
 // Activation-tile column map (bf16 columns of the 128-row A operand, K-slab layout, tc_common.cuh):
 //   [0,256)    main: current layer input / output (step 0 reads the hi/lo embedding from [0, 2*emb_pad))
-//   [256,304)  aux:  colour-net small inputs [p(3), embed(view dir), n(3), 0..]     (written by the V step)
+//   [256,304)  aux:  colour-net small inputs (normal written by the V step, point + view embedding by the prologue warps)
 //   [304,352)  skip: positional encoding / sqrt(2) for the skip layer               (written by the prologue)
 //   [352,368)  ones: [1, 1, 0, ...] constant -- multiplies the (hi, lo) bias row of every weight image,
 //                    so the folded BatchNorm shift is added by the tensor core, not by the epilogue
-constexpr int kColAux = 256, kColSkip = 304, kColOnes = 352, kActCols = 368;
+//   [368,464)  emb0: bf16 hi | lo split of the positional encoding, the A operand of layer 0 (written by the
+//                    prologue warps, so it never collides with the main columns)
+// aux column order: [n(3), 0 x5 | p(3), embed(view dir), 0...]: the V step only rewrites the first 16-byte unit.
+constexpr int kColAux = 256, kColSkip = 304, kColOnes = 352, kColEmb0 = 368, kActCols = 464;
 
 // One GEMM step of the fused chain: acc[128 x N] = sum over segments A[:, col0 : col0+k] * Wimg^T, then an epilogue.
 struct TcStep {
@@ -48,6 +51,7 @@ struct TcProgram {
   int multires, multires_view;
   int small_w;      // 3 + (3 + 6*multires_view) + 3
   int skip_step;    // index of the step that consumes the skip columns (-1: none)
+  int aux_step;     // index of the step that consumes the aux columns (-1: none)
   TcStep s[kTcMaxSteps];
 };
 

@@ -248,3 +248,69 @@ extern "C" int vfnerf_debug_umma2_gemm(const float* A, const float* B, float* D,
   VFN_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- 2-CTA micro-benchmark: cycles per tcgen05.mma.cta_group::2 (M=256, N=256, K=16), with an optional
+// multicast tcgen05.commit after every 4th MMA (mode 1) or a non-multicast commit to the leader only (mode 2).
+namespace vfn {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+umma2_bench_kernel(int n_mma, int mode, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar, bar2;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int e = tid; e < 128 * 1024 / 4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1 << 20); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, 256);
+    const uint64_t da0 = make_smem_desc(smem_u32(smem), slab_bytes(128), 128);
+    const uint64_t db0 = make_smem_desc(smem_u32(smem + 64 * 1024), slab_bytes(128), 128);
+    const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32), a_lo0 = (uint32_t)da0, b_lo0 = (uint32_t)db0;
+    const uint32_t step = (2 * slab_bytes(128)) >> 4;
+    long long t0 = clock64();
+    for (int i = 0; i < n_mma; i += 4) {
+      const uint32_t base = (uint32_t)((i >> 2) & 3) * 4u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(tmem), "r"(a_lo0 + (base + j) * step), "r"(a_hi), "r"(b_lo0 + (base + j) * step), "r"(b_hi), "r"(idesc),
+              "r"((uint32_t)((i | j) > 0)) : "memory");
+      }
+      if (mode == 1)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar2)), "h"((uint16_t)3) : "memory");
+      if (mode == 2)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  if (rank == 1 && tid == 0) mbar_wait(&bar, 0);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+}  // namespace vfn
+
+extern "C" int vfnerf_debug_umma2_bench(int n_mma, int mode, int n_ctas, long long* cycles_dev, void* stream) {
+  using namespace vfn;
+  size_t smem = 128 * 1024;
+  VFN_CHECK_CUDA(cudaFuncSetAttribute(umma2_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma2_bench_kernel<<<n_ctas & ~1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(n_mma, mode, cycles_dev);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
