@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("VFNERF_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("VFNERF_PRECISION", "bf16"))
     ap.add_argument("--chunk", type=int, default=0, help="rays per render() call of the device-resident leg")
     ap.add_argument("--rays", type=int, default=H * W_IMG, help="rays per step (default: the full image)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
