@@ -114,8 +114,12 @@ def cpu_reference_rays_per_s(n_steps, n_warm, threads=None):
     """The reference's CPU path (oracle port, torch-CPU fp32 eager, all host threads): one 1024-ray chunk
     per step, deterministic sampling -- the `--gpu cpu` configuration of BASELINE config 1."""
     U = oracle_pack()
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use every host core it is allowed to run on
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    torch.set_num_threads(threads or ncores)
     st = U.S.synthetic_state(CASE["seed"], vf_gain=CASE["vf_gain"])
     R = 1024
     uv, pose, K = U.S.synthetic_rays(R, seed=0, start=0, stride=797)
