@@ -267,10 +267,11 @@ def main():
                "d2h_bytes_per_step": d2h, "chunk": ck}
 
     # ---- training step (BASELINE config 3): 1024-ray batch, render -> VFLoss terms -> backward -> clip -> Adam,
-    # the sequence of train/vector_field_nerf_train.py:177-260 (fp32 path: the tensor-core backward is not built yet)
+    # the sequence of train/vector_field_nerf_train.py:177-260.  Timed on the bench precision (bf16: fused tcgen05
+    # forward with activation stash, fused tcgen05 dgrad chain, MN-major tcgen05 weight-gradient GEMMs) and, for
+    # comparison, on the fp32 CUDA-core path.
     train = None
     if not args.no_train:
-        tm = U.make_model(dict(CASE, perturb=True, dir_to_normal_th=-2.0), st, dev, precision="fp32")
         Rt = 1024
         uvt, poset, Kt = uv_d[:Rt], pose_d[:Rt], K_d[:Rt]
         g2 = torch.Generator(device=dev).manual_seed(7 + rank)
@@ -279,34 +280,42 @@ def main():
         rgb_gt = torch.rand(Rt, 3, device=dev, generator=g2)
         dep_gt = torch.rand(Rt, 1, device=dev, generator=g2) * CASE["far"]
 
-        def train_step():
-            out = tm.render(poset, uvt, Kt, 0, draws=draws_t)
-            nrm = torch.norm(out.coarse_normals.reshape(-1, 3), dim=1)
-            loss = 2.0 * (out.coarse_rgb_values - rgb_gt).abs().mean() + \
-                0.5 * (out.coarse_depth_map - dep_gt).abs().clamp(max=0.5).mean() + 0.1 * torch.mean((nrm - 1) ** 2)
-            tm.optimizer.zero_grad()
-            loss.backward()
+        def time_train(prec, n_tr):
+            tm = U.make_model(dict(CASE, perturb=True, dir_to_normal_th=-2.0), st, dev, precision=prec)
+
+            def train_step():
+                out = tm.render(poset, uvt, Kt, 0, draws=draws_t)
+                nrm = torch.norm(out.coarse_normals.reshape(-1, 3), dim=1)
+                loss = 2.0 * (out.coarse_rgb_values - rgb_gt).abs().mean() + \
+                    0.5 * (out.coarse_depth_map - dep_gt).abs().clamp(max=0.5).mean() + 0.1 * torch.mean((nrm - 1) ** 2)
+                tm.optimizer.zero_grad()
+                loss.backward()
+                if world > 1:
+                    from vfnerf_b200 import dist as vd
+                    vd.allreduce_gradients(tm)
+                torch.nn.utils.clip_grad_norm_(tm.parameters(), 0.5)
+                tm.optimizer.step()
+            for _ in range(3):
+                train_step()
+            sync_all()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for _ in range(n_tr):
+                train_step()
+            t1e.record()
+            sync_all()
+            mst = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
             if world > 1:
-                from vfnerf_b200 import dist as vd
-                vd.allreduce_gradients(tm)
-            torch.nn.utils.clip_grad_norm_(tm.parameters(), 0.5)
-            tm.optimizer.step()
-        for _ in range(3):
-            train_step()
-        sync_all()
-        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_tr = 5
-        t0e.record()
-        for _ in range(n_tr):
-            train_step()
-        t1e.record()
-        sync_all()
-        mst = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
-        if world > 1:
-            dist.all_reduce(mst, op=dist.ReduceOp.MAX)
-        train = {"value": world * Rt * n_tr / (mst.item() * 1e-3), "unit": "rays/s", "rays_per_step_per_gpu": Rt,
-                 "ms_per_step": mst.item() / n_tr, "precision": "fp32",
+                dist.all_reduce(mst, op=dist.ReduceOp.MAX)
+            del tm
+            torch.cuda.empty_cache()
+            return mst.item() / n_tr
+        ms_tr = time_train(args.precision, 10 if args.precision == "bf16" else 5)
+        train = {"value": world * Rt / (ms_tr * 1e-3), "unit": "rays/s", "rays_per_step_per_gpu": Rt,
+                 "ms_per_step": ms_tr, "precision": args.precision,
                  "includes": "render fwd + loss + backward + (allreduce) + clip_grad_norm_ + Adam"}
+        if args.precision != "fp32":
+            train["fp32_ms_per_step"] = time_train("fp32", 3)
 
     # ---- roofline of the dominant kernel, timed alone with CUDA events on the launching stream:
     #   bf16: the fused tcgen05 launch (VF + colour MLPs, RENDER program) on one chunk of merged points;

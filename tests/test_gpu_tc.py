@@ -144,3 +144,21 @@ def test_umma_2cta_conventions(built_lib, N, K):
     err = (D - ref).abs().max().item()
     print(f"2-CTA N={N} K={K}: max abs err {err:.3e}")
     assert err <= 1e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("N,K", [(256, 128), (48, 128), (256, 64), (96, 16)])
+def test_umma_mn_major_conventions(built_lib, N, K):
+    """Both operands MN-major (reduction index = row of the stashed [points, channels] tiles): the wgrad GEMM."""
+    g = torch.Generator().manual_seed(3 * N + K)
+    At = torch.randn(K, 128, generator=g).to(DEV)
+    Bt = torch.randn(K, N, generator=g).to(DEV)
+    ref = At.bfloat16().float().T @ Bt.bfloat16().float()
+    errs = []
+    for variant in (0, 1):
+        D = torch.zeros(128, N, device=DEV)
+        _lib.check(built_lib.vfnerf_debug_umma_mn_gemm(At.data_ptr(), Bt.data_ptr(), D.data_ptr(), N, K, variant,
+                                                       torch.cuda.current_stream().cuda_stream), "debug_umma_mn_gemm")
+        torch.cuda.synchronize()
+        errs.append((D - ref).abs().max().item())
+    print(f"MN-major N={N} K={K}: max abs err variant0 {errs[0]:.3e} variant1 {errs[1]:.3e}")
+    assert errs[0] <= 1e-3 * max(1.0, ref.abs().max().item())

@@ -250,8 +250,7 @@ static int make_plan(const vfnerf_render_cfg& cfg, const vfnerf_mlp_desc& vf, co
     }
   } else {
     VFN_REQUIRE(cfg.precision == VFNERF_PREC_BF16, "precision bf16x3 is not built yet; use fp32 or bf16");
-    VFN_REQUIRE(!keep, "the tensor-core path has no backward yet: train with precision fp32");
-    if (int e = tc_carve(c.base, c.off, cfg.multires, cfg.multires_view, cfg.skip_layer, vf, &rn, p.tc)) return e;
+    if (int e = tc_carve(c.base, c.off, cfg.multires, cfg.multires_view, cfg.skip_layer, vf, &rn, p.tc, p.P, keep)) return e;
   }
   p.bytes = c.off;
   return 0;
@@ -343,8 +342,8 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
     if (out->ray_dirs_rep)
       if (int e = launch_color_input_head(out->points, p.ray_dirs, p.R, p.N, cfg->multires_view, nullptr, 0,
                                           out->ray_dirs_rep, s)) return e;
-    if (int e = tc_forward(p.tc, TC_MODE_RENDER, out->points, nullptr, 0, 0, p.P, p.ray_dirs, p.N, out->normals, 3,
-                           nullptr, 0, out->colors, s)) return e;
+    if (int e = tc_forward(p.tc, keep_for_backward ? TC_MODE_RENDER_STASH : TC_MODE_RENDER, out->points, nullptr, 0, 0, p.P,
+                           p.ray_dirs, p.N, out->normals, 3, nullptr, 0, out->colors, s)) return e;
     if (int e = launch_density_weights(*cfg, p.R, p.N, density_params, out->normals, 3, p.ray_dirs, out->z_vals,
                                        nullptr, nullptr, weights, s)) return e;
   }
@@ -370,7 +369,16 @@ int vfnerf_render_bwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
   VFN_CHECK_CUDA(cudaMemsetAsync(vf_grad_arena, 0, sizeof(float) * vf->arena_floats, s));
   VFN_CHECK_CUDA(cudaMemsetAsync(rn_grad_arena, 0, sizeof(float) * rn->arena_floats, s));
   if (p.R == 0) return 0;
-  VFN_REQUIRE(cfg->precision == VFNERF_PREC_FP32, "render_bwd: only the fp32 path has a backward in this build");
+  if (cfg->precision != VFNERF_PREC_FP32) {
+    // tensor-core training path (mlp_tc_bwd.cu): the forward left the activation stash and the packed transposed
+    // weights in the workspace; ray_dirs are recomputed by the caller-visible forward only, so they must still be there
+    float* dcol = p.tc.d3;
+    float* dv = p.tc.d3 + 3 * p.P;
+    if (int e = launch_render_tail_bwd(*cfg, p.R, p.N, density_params, out->normals, 3, p.ray_dirs, out->z_vals,
+                                       out->colors, d_rgb, d_depth, d_normals, d_colors, dcol, dv, 3, d_density, s)) return e;
+    return tc_backward(p.tc, *vf, vf_arena, *rn, rn_arena, cfg->bn_eps, p.P, out->colors, out->normals, dcol, dv,
+                       vf_grad_arena, rn_grad_arena, s);
+  }
   const float* vf_out = p.cin + 3 + p.Ev;
   const int Dv = 3 + p.F;
   // a9..a4 fused: d_colors, dL/dv (into columns 0..2 of d_out), density parameter grads
@@ -387,6 +395,15 @@ int vfnerf_render_bwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
   if (int e = mlp_backward_fp32(*vf, vf_arena, p.vf, cfg->skip_layer, cfg->bn_eps, p.emb, p.E, p.P, p.d_out, Dv,
                                 p.bw, vf_grad_arena, 0, nullptr, 0, 0, 0, s)) return e;
   return 0;
+}
+
+int vfnerf_debug_stash_read(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, const vfnerf_mlp_desc* rn,
+                            void* workspace, int tensor, float* out, int* n_cols, void* stream) {
+  VFN_REQUIRE(cfg && vf && rn && workspace, "stash_read: null argument");
+  VFN_REQUIRE(cfg->precision == VFNERF_PREC_BF16, "stash_read: only the bf16 path keeps a stash");
+  RenderPlan p;
+  if (int e = make_plan(*cfg, *vf, *rn, 1, workspace, p)) return e;
+  return tc_debug_stash_read(p.tc, tensor, p.P, out, n_cols, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- VF-only query -----------------------------------------------------------------------------

@@ -53,6 +53,11 @@ struct TcParams {
   float* out_v; long long v_ld;
   float* out_feat; long long feat_ld;
   float* colors;
+  // training: activation stash (forward writes Y tensors, backward reads them and writes D tensors)
+  uint8_t* stash;
+  TcStash sinfo;
+  const float* dcol_pre;   // backward input [n,3]: dL/d(colour pre-sigmoid)
+  const float* dv_pre;     // backward input [n,3]: dL/d(vector pre-tanh)
   int dbg;              // experiments: 1 = MMA issuer ignores A-readiness, 2 = epilogue skips TMEM loads / math / stores
   long long* dbg_buf;   // VFNERF_TC_DBG=64: cycle counters of CTA 0 (MMA thread [0..2], epilogue warp 2 [8..12], warp 3 [16..20])
 };
@@ -82,10 +87,10 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
                         (int64_t)((kin % st.chunk_k) / 8) * nh * 16 + nn * 16 + (kin & 7) * 2;
     float w = 0.f;
     if (n < st.n_valid) {
-      const int row = st.row0 + n;
+      const int row = st.colmap >= 10 ? 0 : st.row0 + n;
       float sc = 1.f;
-      if (bn) sc = arena[d.gamma_off[l] + row] / sqrtf(arena[d.var_off[l] + row] + eps);
-      if (sg == st.n_seg - 1) {
+      if (bn && st.colmap < 10) sc = arena[d.gamma_off[l] + row] / sqrtf(arena[d.var_off[l] + row] + eps);
+      if (sg == st.n_seg - 1 && !st.no_bias) {
         // bias row: folded shift as a bf16 (hi, lo) pair in columns 0 and 1
         if (kin < 2) {
           const float b = arena[d.b_off[l] + row];
@@ -97,7 +102,21 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
         }
       } else {
         int src = -1;
-        if (st.colmap == 0) src = kin;
+        if (st.colmap >= 10) {
+          // backward image: MMA "output channel" n = forward input column, MMA "K" index = forward output channel
+          int n_out = -1;
+          if (st.colmap == 11 || (st.colmap == 12 && sg == 1)) n_out = kin < 3 ? kin : (kin < 6 ? kin - 3 : -1);   // (hi, lo) unit
+          else n_out = st.row0 + kin;
+          const int k_in = st.src_split + n;
+          w = 0.f;
+          if (n_out >= 0 && n_out < d.out_dim[l] && k_in < in_dim) {
+            float sc2 = 1.f;
+            if (bn) sc2 = arena[d.gamma_off[l] + n_out] / sqrtf(arena[d.var_off[l] + n_out] + eps);
+            w = arena[d.w_off[l] + (int64_t)n_out * in_dim + k_in] * sc2 * st.post_scale;
+          }
+          src = -2;
+        }
+        else if (st.colmap == 0) src = kin;
         else if (st.colmap == 1) { src = kin < Epad ? kin : kin - Epad; if (src >= E) src = -1; }
         else if (st.colmap == 2) {
           // colour-net layer 0: main segment = features; aux segment = [n(3), 0 x5, p(3), embed(view), 0...]
@@ -188,6 +207,12 @@ __device__ __forceinline__ void load_point(const TcParams& p, long long pi, bool
 }
 
 // readiness barrier that guards activation-tile column `col` (-1: constant region, nothing to wait for)
+// 16-byte unit (slab, row) of tile `tile` of stash tensor t
+__device__ __forceinline__ uint4* stash_unit(const TcParams& p, int t, long long tile, int slab, int row) {
+  return reinterpret_cast<uint4*>(p.stash + p.sinfo.off[t] + tile * ((long long)p.sinfo.slabs[t] * (kTileM * 16)) +
+                                  (long long)slab * (kTileM * 16) + row * 16);
+}
+
 // readiness barriers (bit mask) that guard the 64-column chunk starting at activation-tile column `col`
 __device__ __forceinline__ uint32_t col_barriers(int col) {
   if (col < kColAux) return 1u << (col >> 6);
@@ -266,6 +291,7 @@ __device__ __forceinline__ void umma2_commit_u32(uint32_t bar) {
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
+template <bool kBwd>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -483,9 +509,40 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       if (lane == 0) { if (rank == 0) mbar_arrive(&grp[b]); else mbar_arrive_remote(&grp[b], 0); }
     };
     int n = 0;
+    if (kBwd) {
+      // backward: the two 3-wide gradient inputs enter as bf16 (hi, lo) pairs in 16-column units:
+      //   d(colour pre-sigmoid) -> aux columns 0..15 (A operand of the first step), d(vector pre-tanh) -> skip columns 0..15
+      for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++n) {
+        const long long pi = tile_of(pair) * kTileM + row;
+        const bool valid = pi < p.n_points;
+        float u[16], w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { u[j] = 0.f; w[j] = 0.f; }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float a = p.dcol_pre[3 * pi + j], b = p.dv_pre[3 * pi + j];
+            u[j] = __bfloat162float(__float2bfloat16(a)); u[3 + j] = a - u[j];
+            w[j] = __bfloat162float(__float2bfloat16(b)); w[3 + j] = b - w[j];
+          }
+        }
+        if (n > 0) mbar_wait(&reg_free[2], (n - 1) & 1);
+        store_slab_f(s_act, kColAux / 8, row, u);
+        store_slab_f(s_act, kColAux / 8 + 1, row, u + 8);
+        fence_proxy_async_smem();
+        arrive_pro(kBarAuxStatic);
+        if (n > 0) mbar_wait(&reg_free[1], (n - 1) & 1);
+        store_slab_f(s_act, kColSkip / 8, row, w);
+        store_slab_f(s_act, kColSkip / 8 + 1, row, w + 8);
+        fence_proxy_async_smem();
+        arrive_pro(kBarSkip);
+      }
+    } else
     for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++n) {
-      const long long pi = tile_of(pair) * kTileM + row;
+      const long long tile = tile_of(pair);
+      const long long pi = tile * kTileM + row;
       const bool valid = pi < p.n_points;
+      const bool st_on = p.stash != nullptr && tile < num_tiles;
       float pt[3], emb[48];
       load_point(p, pi, valid, pt);
 #pragma unroll
@@ -508,6 +565,12 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           }
           store_slab_f(s_act, kColEmb0 / 8 + sl, row, hi);
           store_slab_f(s_act, kColEmb0 / 8 + nsl + sl, row, lo);
+          if (st_on) {
+            *stash_unit(p, p.sinfo.idx_emb0, tile, sl, row) =
+                make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+            *stash_unit(p, p.sinfo.idx_emb0, tile, nsl + sl, row) =
+                make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+          }
         }
       }
       fence_proxy_async_smem();
@@ -518,7 +581,14 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
         for (int i = 0; i < 48; ++i) emb[i] *= kInvSqrt2;
 #pragma unroll
-        for (int sl = 0; sl < 6; ++sl) store_slab_f(s_act, kColSkip / 8 + sl, row, emb + 8 * sl);
+        for (int sl = 0; sl < 6; ++sl) {
+          store_slab_f(s_act, kColSkip / 8 + sl, row, emb + 8 * sl);
+          if (st_on) {
+            const float* e8 = emb + 8 * sl;
+            *stash_unit(p, p.sinfo.idx_skip, tile, sl, row) =
+                make_uint4(pack_bf16x2(e8[0], e8[1]), pack_bf16x2(e8[2], e8[3]), pack_bf16x2(e8[4], e8[5]), pack_bf16x2(e8[6], e8[7]));
+          }
+        }
         fence_proxy_async_smem();
         arrive_pro(kBarSkip);
       }
@@ -540,7 +610,14 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         }
         if (n > 0) mbar_wait(&reg_free[2], (n - 1) & 1);
 #pragma unroll
-        for (int sl = 0; sl < 5; ++sl) store_slab_f(s_act, kColAux / 8 + 1 + sl, row, a + 8 * sl);
+        for (int sl = 0; sl < 5; ++sl) {
+          store_slab_f(s_act, kColAux / 8 + 1 + sl, row, a + 8 * sl);
+          if (st_on) {
+            const float* e8 = a + 8 * sl;
+            *stash_unit(p, p.sinfo.idx_aux, tile, 1 + sl, row) =
+                make_uint4(pack_bf16x2(e8[0], e8[1]), pack_bf16x2(e8[2], e8[3]), pack_bf16x2(e8[4], e8[5]), pack_bf16x2(e8[6], e8[7]));
+          }
+        }
         fence_proxy_async_smem();
         arrive_pro(kBarAuxStatic);
       }
@@ -572,10 +649,11 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         TCK(t_acc);
         if (tl) p.dbg_buf[64 + si * 8 + 2 + 3 * h] = clock64();
         tc_fence_after_sync();
-        if (st.epi == TC_EPI_RELU || st.epi == TC_EPI_FEAT) {
+        if (!kBwd && (st.epi == TC_EPI_RELU || st.epi == TC_EPI_FEAT)) {
           const bool feat = st.epi == TC_EPI_FEAT;
           const bool to_act = !feat || render;
           const int stN = st.N;
+          const bool st_on = p.stash != nullptr && st.stash_out >= 0 && tile < num_tiles;
           if (to_act) {
             // Each warp owns two of the four 64-column groups (= K chunks of the next layer): h=0 -> groups 0 and 2,
             // h=1 -> groups 1 and 3.  One generic->async proxy fence (a MEMBAR.ALL.CTA) and one barrier arrival per
@@ -601,6 +679,12 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                 for (int sl = 0; sl < 4; ++sl)
                   store_slab_u(s_act, (c0 >> 3) + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+                if (st_on) {
+#pragma unroll
+                  for (int sl = 0; sl < 4; ++sl)
+                    *stash_unit(p, st.stash_out, tile, (c0 >> 3) + sl, row) =
+                        make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+                }
                 if (second) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
@@ -610,6 +694,12 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                   for (int sl = 0; sl < 4; ++sl)
                     store_slab_u(s_act, (c0 >> 3) + 4 + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+                  if (st_on) {
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl)
+                      *stash_unit(p, st.stash_out, tile, (c0 >> 3) + 4 + sl, row) =
+                          make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+                  }
                 }
               }
               TCK(t_math);
@@ -645,7 +735,62 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               }
             }
           }
-        } else if (st.epi == TC_EPI_V) {
+        } else if (kBwd && (st.epi == TC_EPI_BWD_RELU || st.epi == TC_EPI_BWD_TANH)) {
+          // dgrad step: acc = dL/d(this layer's input); gate it with the stashed forward activation Y of that input
+          // (ReLU: Y > 0; tanh: 1 - Y^2), hand it on as the next step's A operand and stash it for the wgrad GEMM.
+          const bool is_tanh = st.epi == TC_EPI_BWD_TANH;
+          const int stN = st.N;
+          const bool t_ok = tile < num_tiles;
+          // the last step's output (dL/d pre-activation of layer 0) has no consumer in this launch: it is only stashed,
+          // and it must not arrive on the column-group barriers (every arrival set is matched by exactly one wait of
+          // the MMA issuer; an unmatched one would shift the barrier phases of the next tile)
+          const bool hand_on = si + 1 < prog.n_steps;
+#pragma unroll 1
+          for (int it = 0; it < 2; ++it) {
+            const int bg = 2 * it + h, c0 = bg * 64;
+            if (c0 >= stN) { if (hand_on) arrive_grp(bg); continue; }
+            const bool second = c0 + 32 < stN;
+            uint4 ym[8];
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl)
+              ym[sl] = (t_ok && (sl < 4 || second)) ? __ldg(stash_unit(p, st.mask_src, tile, (c0 >> 3) + sl, row)) : make_uint4(0, 0, 0, 0);
+            uint32_t va[32], vb[32];
+            tmem_ld32(acc + c0, va);
+            if (second) tmem_ld32(acc + c0 + 32, vb);
+            tmem_ld_wait();
+            auto gate = [&](uint32_t y2, uint32_t a_lo_bits, uint32_t a_hi_bits) -> uint32_t {
+              const float a0 = __uint_as_float(a_lo_bits), a1 = __uint_as_float(a_hi_bits);
+              if (is_tanh) {
+                const float y0 = __uint_as_float(y2 << 16), y1 = __uint_as_float(y2 & 0xFFFF0000u);
+                return pack_bf16x2(a0 * (1.f - y0 * y0), a1 * (1.f - y1 * y1));
+              }
+              return pack_bf16x2((y2 & 0xFFFFu) ? a0 : 0.f, (y2 >> 16) ? a1 : 0.f);
+            };
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+              const uint32_t* y = reinterpret_cast<const uint32_t*>(&ym[sl]);
+              const uint4 o = make_uint4(gate(y[0], va[8 * sl + 0], va[8 * sl + 1]), gate(y[1], va[8 * sl + 2], va[8 * sl + 3]),
+                                         gate(y[2], va[8 * sl + 4], va[8 * sl + 5]), gate(y[3], va[8 * sl + 6], va[8 * sl + 7]));
+              store_slab_u(s_act, (c0 >> 3) + sl, row, o.x, o.y, o.z, o.w);
+              if (t_ok) *stash_unit(p, st.stash_out, tile, (c0 >> 3) + sl, row) = o;
+            }
+            if (second) {
+#pragma unroll
+              for (int sl = 0; sl < 4; ++sl) {
+                const uint32_t* y = reinterpret_cast<const uint32_t*>(&ym[4 + sl]);
+                const uint4 o = make_uint4(gate(y[0], vb[8 * sl + 0], vb[8 * sl + 1]), gate(y[1], vb[8 * sl + 2], vb[8 * sl + 3]),
+                                           gate(y[2], vb[8 * sl + 4], vb[8 * sl + 5]), gate(y[3], vb[8 * sl + 6], vb[8 * sl + 7]));
+                store_slab_u(s_act, (c0 >> 3) + 4 + sl, row, o.x, o.y, o.z, o.w);
+                if (t_ok) *stash_unit(p, st.stash_out, tile, (c0 >> 3) + 4 + sl, row) = o;
+              }
+            }
+            if (hand_on) {
+              fence_proxy_async_smem();
+              tc_fence_before_sync();
+              arrive_grp(bg);
+            }
+          }
+        } else if (!kBwd && st.epi == TC_EPI_V) {
           if (h == 0) {
             uint32_t v[16];
             tmem_ld16(acc, v);
@@ -661,6 +806,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               // the normal is the first 16-byte unit of the colour net's small inputs (aux columns 0..7)
               float a[8] = {nv[0], nv[1], nv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
               store_slab_f(s_act, kColAux / 8, row, a);
+              if (p.stash != nullptr && tile < num_tiles)
+                *stash_unit(p, p.sinfo.idx_aux, tile, 0, row) = make_uint4(pack_bf16x2(nv[0], nv[1]), pack_bf16x2(nv[2], 0.f), 0u, 0u);
               fence_proxy_async_smem();
             }
             // RENDER: the aux columns are ready.  VF_FULL: the FEAT step's MMAs do not depend on any A rewrite; this
@@ -671,7 +818,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               arrive_grp(kBarAux);
             }
           }
-        } else {  // TC_EPI_RGB
+        } else if (!kBwd) {  // TC_EPI_RGB
           if (h == 0) {
             uint32_t v[16];
             tmem_ld16(acc, v);
@@ -724,11 +871,12 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   long long woff = 0;
   // appends a step; the bias (ones) segment is added automatically as the last segment
   auto add = [&](int N, int n_valid, int nseg, const int* col0, const int* segk, int chunk_k, int epi, int fresh,
-                 int net, int layer, int row0, int colmap, int src_split, float post) {
+                 int net, int layer, int row0, int colmap, int src_split, float post, int no_bias = 0) {
     TcStep& s = pr.s[ns];
-    s.N = N; s.n_valid = n_valid; s.n_seg = nseg + 1; s.K = 0;
+    s.N = N; s.n_valid = n_valid; s.n_seg = nseg + (no_bias ? 0 : 1); s.K = 0;
     for (int i = 0; i < nseg; ++i) { s.seg_col0[i] = col0[i]; s.seg_k[i] = segk[i]; s.K += segk[i]; }
-    s.seg_col0[nseg] = kColOnes; s.seg_k[nseg] = 16; s.K += 16;
+    if (!no_bias) { s.seg_col0[nseg] = kColOnes; s.seg_k[nseg] = 16; s.K += 16; }
+    s.no_bias = no_bias; s.stash_out = -1; s.mask_src = -1;
     s.chunk_k = chunk_k; s.epi = epi; s.fresh_mask = fresh; s.pre_wait_mask = 0; s.w_off = woff;
     s.net = net; s.layer = layer; s.row0 = row0; s.colmap = colmap; s.src_split = src_split; s.post_scale = post;
     woff += (long long)align_up((int64_t)N * s.K * 2, 128);
@@ -778,15 +926,86 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.render = 0; plan.vf_full.aux_step = -1;
   plan.vf_full.s[n_full - 1].pre_wait_mask = 1 << kBarAux;
   plan.v_only = pr; plan.v_only.n_steps = n_v; plan.v_only.render = 0; plan.v_only.aux_step = -1;
+  if (!rn) return 0;
+
+  // ---------------- training: stash tensor numbering ----------------
+  const int Lr = rn->n_layers;
+  TcStash& S = plan.stash;
+  S.n_y = L + Lr - 1;                       // Y_s[0..L-2], Y_FEAT, Y_c[0..Lr-2]
+  S.idx_emb0 = S.n_y; S.idx_skip = S.n_y + 1; S.idx_aux = S.n_y + 2; S.idx_d0 = S.n_y + 3;
+  S.n_tensors = 2 * S.n_y + 3;
+  VFN_REQUIRE(S.n_tensors <= kTcMaxStash, "tensor-core path: too many layers for the activation stash");
+  for (int i = 0; i < S.n_tensors; ++i) S.slabs[i] = 32;
+  S.slabs[S.idx_emb0] = 2 * Epad / 8; S.slabs[S.idx_skip] = 6; S.slabs[S.idx_aux] = 6;
+  auto yS = [&](int l) { return l; };                  // VF hidden layer l
+  const int yFeat = L - 1;
+  auto yC = [&](int l) { return L + l; };              // colour hidden layer l
+  for (int l = 0; l < L - 1; ++l) plan.render.s[l].stash_out = yS(l);
+  plan.render.s[n_v].stash_out = yFeat;
+  for (int l = 0; l < Lr - 1; ++l) plan.render.s[n_full + l].stash_out = yC(l);
+
+  // ---------------- training: the dgrad program (weights transposed, no bias, gate with the stash) ----------------
+  TcProgram fwd = pr;                          // keep the forward description for post_scale look-ups
+  pr = TcProgram{};
+  pr.emb_w = E; pr.emb_pad = Epad; pr.multires = multires; pr.multires_view = multires_view;
+  pr.small_w = fwd.small_w; pr.bwd = 1;
+  ns = 0; woff = 0;
+  const int D0 = S.idx_d0;
+  {
+    // colour output layer: A = d(colour pre-sigmoid) as a bf16 (hi, lo) unit in the aux columns
+    const int c[1] = {kColAux}, k[1] = {16};
+    add(256, 256, 1, c, k, 128, TC_EPI_BWD_RELU, 1 << kBarAuxStatic, 1, Lr - 1, 0, 11, 0, 1.f, 1);
+    pr.s[ns - 1].mask_src = yC(Lr - 2); pr.s[ns - 1].stash_out = D0 + yC(Lr - 2);
+  }
+  for (int l = Lr - 2; l >= 1; --l) {
+    add(256, 256, 1, main0, k256, 128, TC_EPI_BWD_RELU, 0xF, 1, l, 0, 10, 0, 1.f, 1);
+    pr.s[ns - 1].mask_src = yC(l - 1); pr.s[ns - 1].stash_out = D0 + yC(l - 1);
+  }
+  // colour layer 0: only the feature columns of its input carry gradient (points / view dirs have none, the normal
+  // is detached, rendering_network.py:76-77); gate with tanh'
+  add(256, 256, 1, main0, k256, 128, TC_EPI_BWD_TANH, 0xF, 1, 0, 0, 10, fwd.small_w, 1.f, 1);
+  pr.s[ns - 1].mask_src = yFeat; pr.s[ns - 1].stash_out = D0 + yFeat;
+  {
+    // VF output layer: A = [d(feature pre-tanh) (main) | d(vector pre-tanh) (hi, lo) unit in the skip columns]
+    const int c[2] = {0, kColSkip}, k[2] = {256, 16};
+    pr.skip_step = ns;
+    add(256, 256, 2, c, k, 128, TC_EPI_BWD_RELU, 0xF | (1 << kBarSkip), 0, L - 1, 3, 12, 0, 1.f, 1);
+    pr.s[ns - 1].mask_src = yS(L - 2); pr.s[ns - 1].stash_out = D0 + yS(L - 2);
+  }
+  for (int l = L - 2; l >= 1; --l) {
+    const int kk[1] = {round16(vf.out_dim[l])};
+    const int Nn = round16(vf.out_dim[l - 1]);
+    add(Nn, vf.out_dim[l - 1], 1, main0, kk, 128, TC_EPI_BWD_RELU, 0xF, 0, l, 0, 10, 0, fwd.s[l].post_scale, 1);
+    pr.s[ns - 1].mask_src = yS(l - 1); pr.s[ns - 1].stash_out = D0 + yS(l - 1);
+  }
+  pr.n_steps = ns; pr.aux_step = 0;
+  plan.bwd = pr;
+  plan.wpack_bwd_bytes = woff;
   return 0;
 }
 
 int tc_carve(char* base, int64_t& off, int multires, int multires_view, int skip_layer,
-             const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc* rn, TcPlan& plan) {
+             const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc* rn, TcPlan& plan, int64_t n_points, int keep) {
   if (int e = build_programs(multires, multires_view, skip_layer, vf, rn, plan)) return e;
   off = align_up(off, 1024);
   plan.wpack = base ? reinterpret_cast<uint8_t*>(base + off) : nullptr;
   off += align_up(plan.wpack_bytes, 1024);
+  if (keep && rn) {
+    plan.wpack_bwd = base ? reinterpret_cast<uint8_t*>(base + off) : nullptr;
+    off += align_up(plan.wpack_bwd_bytes, 1024);
+    const int64_t tiles = (n_points + kTileM - 1) / kTileM, tiles2 = (tiles + 1) / 2 * 2;
+    TcStash& S = plan.stash;
+    int64_t so = 0;
+    for (int i = 0; i < S.n_tensors; ++i) { S.off[i] = so; so += tiles2 * S.slabs[i] * (kTileM * 16); }
+    S.bytes = so;
+    plan.stash_buf = base ? reinterpret_cast<uint8_t*>(base + off) : nullptr;
+    off += align_up(so, 1024);
+    plan.gbuf_floats = (int64_t)(S.n_y + 2) * (256 * 320 + 256);
+    plan.gbuf = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += align_up(plan.gbuf_floats * 4, 1024);
+    plan.d3 = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += align_up(n_points * 6 * 4, 1024);
+  }
   return 0;
 }
 
@@ -796,6 +1015,10 @@ int tc_prepare(const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_ml
   vfnerf_mlp_desc none{};
   tc_pack_kernel<<<dim3(32, pr.n_steps), 256, 0, s>>>(pr, vf, vf_arena, rn ? *rn : none, rn_arena, bn_eps, plan.wpack);
   VFN_LAUNCH_CHECK();
+  if (plan.wpack_bwd) {
+    tc_pack_kernel<<<dim3(32, plan.bwd.n_steps), 256, 0, s>>>(plan.bwd, vf, vf_arena, *rn, rn_arena, bn_eps, plan.wpack_bwd);
+    VFN_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -806,8 +1029,14 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
                int64_t v_ld, float* out_feat, int64_t feat_ld, float* colors, cudaStream_t s) {
   if (n <= 0) return 0;
   TcParams p{};
-  p.prog = mode == TC_MODE_RENDER ? plan.render : (mode == TC_MODE_VF_FULL ? plan.vf_full : plan.v_only);
-  p.wpack = plan.wpack;
+  p.prog = (mode == TC_MODE_RENDER || mode == TC_MODE_RENDER_STASH) ? plan.render
+           : (mode == TC_MODE_VF_FULL ? plan.vf_full : (mode == TC_MODE_BWD ? plan.bwd : plan.v_only));
+  p.wpack = mode == TC_MODE_BWD ? plan.wpack_bwd : plan.wpack;
+  if (mode == TC_MODE_RENDER_STASH || mode == TC_MODE_BWD) {
+    VFN_REQUIRE(plan.stash_buf, "tc_forward: this mode needs the training workspace (keep_for_backward)");
+    p.stash = plan.stash_buf; p.sinfo = plan.stash;
+  }
+  if (mode == TC_MODE_BWD) { p.dcol_pre = points; p.dv_pre = ray_dirs; }
   p.points = points; p.use_grid = grid ? 1 : 0;
   if (grid) p.grid = *grid;
   p.grid_res = grid_res; p.grid_i0 = grid_i0; p.n_points = n;
@@ -820,8 +1049,9 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   p.dbg_buf = (dbg & 64) ? dbg_buf : nullptr;
   p.dbg = dbg & 63;
   if (p.dbg_buf) VFN_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), s));
-  VFN_REQUIRE(out_v, "tc_forward: out_v is null");
-  VFN_REQUIRE(mode != TC_MODE_RENDER || (colors && ray_dirs), "tc_forward: RENDER mode needs colors and ray_dirs");
+  VFN_REQUIRE(out_v || mode == TC_MODE_BWD, "tc_forward: out_v is null");
+  VFN_REQUIRE((mode != TC_MODE_RENDER && mode != TC_MODE_RENDER_STASH) || (colors && ray_dirs),
+              "tc_forward: RENDER mode needs colors and ray_dirs");
   if (g_num_sms == 0) {
     int dev = 0;
     VFN_CHECK_CUDA(cudaGetDevice(&dev));
@@ -833,10 +1063,12 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   const size_t smem = (size_t)kActCols * kTileM * 2 + (size_t)kTcStages * kStageBytes + 512 + kTcMaxSteps * 8 * 16 + 128;
   static bool attr = false;
   if (!attr) {
-    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  mlp_tc_kernel<<<grid_x, kTcThreads, smem, s>>>(p);
+  if (mode == TC_MODE_BWD) mlp_tc_kernel<true><<<grid_x, kTcThreads, smem, s>>>(p);
+  else mlp_tc_kernel<false><<<grid_x, kTcThreads, smem, s>>>(p);
   VFN_LAUNCH_CHECK();
   if (p.dbg_buf) {
     long long h[256];

@@ -38,10 +38,31 @@ struct TcStep {
   int colmap;     // 0 identity | 1 hi/lo duplicated embedding | 2 colour-net input permutation | 3 skip layer
   int src_split;  // colmap 2: number of leading small columns; colmap 3: columns fed by the previous layer
   float post_scale;  // folded 1/sqrt(2) of the skip connection (applies to scale and shift)
+  // training support
+  int no_bias;       // 1: no ones-column bias segment (backward steps)
+  int stash_out;     // activation-stash tensor that receives this step's epilogue output (-1: none)
+  int mask_src;      // backward: stash tensor whose sign pattern (ReLU) or value (tanh) gates this step's output
 };
 
-enum TcEpi { TC_EPI_RELU = 0, TC_EPI_V = 2, TC_EPI_FEAT = 3, TC_EPI_RGB = 4 };
-enum TcMode { TC_MODE_V_ONLY = 0, TC_MODE_VF_FULL = 1, TC_MODE_RENDER = 2 };
+enum TcEpi { TC_EPI_RELU = 0, TC_EPI_V = 2, TC_EPI_FEAT = 3, TC_EPI_RGB = 4,
+             TC_EPI_BWD_RELU = 5,    // dX * (Y > 0)            (Y = stashed forward activation)
+             TC_EPI_BWD_TANH = 6 };  // dX * (1 - Y^2)          (Y = stashed tanh features)
+enum TcMode { TC_MODE_V_ONLY = 0, TC_MODE_VF_FULL = 1, TC_MODE_RENDER = 2, TC_MODE_RENDER_STASH = 3, TC_MODE_BWD = 4 };
+
+// Activation stash (training): every tensor is bf16 in "tile-major K-slab" order, i.e. the exact shared-memory
+// image of a 128-point tile, tile after tile:  [tile][slab = 8 channels][row = point in tile][8 channels].
+// The same bytes serve as a K-major operand (dgrad: points x channels) and, with the MN-major descriptor bits,
+// as the transposed operand of the weight-gradient GEMM (channels x points) -- no transpose pass exists.
+constexpr int kTcMaxStash = 32;
+struct TcStash {
+  int n_y;                          // number of forward activation tensors (VF hidden layers, features, colour hidden layers)
+  int idx_emb0, idx_skip, idx_aux;  // prologue-written side inputs
+  int idx_d0;                       // first gradient tensor: D_i = idx_d0 + i mirrors Y_i
+  int n_tensors;
+  int slabs[kTcMaxStash];           // 8-channel slabs per tile
+  long long off[kTcMaxStash];       // byte offset of the tensor inside the stash buffer
+  long long bytes;
+};
 
 struct TcProgram {
   int n_steps;
@@ -52,6 +73,7 @@ struct TcProgram {
   int small_w;      // 3 + (3 + 6*multires_view) + 3
   int skip_step;    // index of the step that consumes the skip columns (-1: none)
   int aux_step;     // index of the step that consumes the aux columns (-1: none)
+  int bwd;          // 1: backward (dgrad) program -- different prologue, no bias segments
   TcStep s[kTcMaxSteps];
 };
 
@@ -59,11 +81,20 @@ struct TcPlan {
   uint8_t* wpack = nullptr;   // weight images of every step of the RENDER program (VF steps are shared by all modes)
   int64_t wpack_bytes = 0;
   TcProgram render{}, vf_full{}, v_only{};
+  // training (keep_for_backward): stash layout, the dgrad program with its transposed weight images, scratch
+  TcProgram bwd{};
+  TcStash stash{};
+  uint8_t* stash_buf = nullptr;
+  uint8_t* wpack_bwd = nullptr;
+  int64_t wpack_bwd_bytes = 0;
+  float* gbuf = nullptr;       // fp32 weight-gradient scratch: one [256 x 320] block per layer + column sums
+  int64_t gbuf_floats = 0;
+  float* d3 = nullptr;         // [P,3] x 2: d(colour pre-sigmoid), d(vector pre-tanh)
 };
 
 // carve the tensor-core buffers out of the workspace (base may be NULL when only sizing)
 int tc_carve(char* base, int64_t& off, int multires, int multires_view, int skip_layer,
-             const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc* rn, TcPlan& plan);
+             const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc* rn, TcPlan& plan, int64_t n_points = 0, int keep = 0);
 // fold BatchNorm + convert/tile the weights of both nets into their shared-memory images
 int tc_prepare(const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_mlp_desc* rn,
                const float* rn_arena, float bn_eps, const TcPlan& plan, cudaStream_t s);
@@ -73,5 +104,15 @@ int tc_prepare(const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_ml
 int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec* grid, int grid_res,
                int64_t grid_i0, int64_t n, const float* ray_dirs, int samples_per_ray, float* out_v,
                int64_t v_ld, float* out_feat, int64_t feat_ld, float* colors, cudaStream_t s);
+
+// Training backward of the RENDER program on the tensor cores.  d_colors [n,3] = dL/d colours, d_v [n,3] = dL/d VF
+// vectors (both fp32, already including every upstream term); colors / normals are the forward outputs.  Writes
+// (not accumulates) the gradients of every Linear / BatchNorm parameter into the two gradient arenas.
+int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_mlp_desc& rn,
+                const float* rn_arena, float bn_eps, int64_t n, const float* colors, const float* normals,
+                const float* d_colors, const float* d_v, float* vf_grad, float* rn_grad, cudaStream_t s);
+
+// test support: convert one stash tensor (or, tensor == 1000, the two [n,3] output-layer gradients) to row-major fp32
+int tc_debug_stash_read(const TcPlan& plan, int tensor, int64_t n, float* out, int* n_cols, cudaStream_t s);
 
 }  // namespace vfn

@@ -1,0 +1,421 @@
+// Training backward on the tensor cores (VFNERF_PREC_BF16), SURVEY.md §8 row a12.
+//
+//   1. d(colour pre-sigmoid), d(vector pre-tanh)                      elementwise (fp32)
+//   2. fused dgrad chain: mlp_tc_kernel<true> (mlp_tc.cu) walks the layers backwards with transposed weight
+//      images, gates with the stashed forward activations and stashes dL/d(pre-activation) of every layer (bf16)
+//   3. weight gradients: wgrad_tc_kernel below -- G[layer] = dY^T X over all points.  Both operands are read from the
+//      activation stash exactly as stored (tile-major K-slab bf16) through MN-major UMMA descriptors, i.e. the
+//      transposition needed by dY^T X is done by the tensor core's operand fetch, not by a memory pass.  HBM-bound:
+//      one pass over the stash (1 KB per point per layer).
+//   4. thin reductions (3-row gradients of the two output layers, column sums for the bias / BatchNorm terms)
+//   5. finalize: map G back to the reference's parameter layout and apply the BatchNorm-eval chain rule.
+#include "mlp_tc.cuh"
+#include "tc_common.cuh"
+
+namespace vfn {
+using namespace tc;
+
+constexpr int kTileM = 128;
+constexpr int kGLd = 320;                          // columns of one layer's G block: [0,256) main input, [256,304) side input
+constexpr int kGSlot = 256 * kGLd + 256;           // + 256 column sums
+constexpr int kWgSlotBytes = 65536;                // one 128-point tile of a 256-channel tensor
+constexpr int kWgSlots = 3;
+constexpr int kWgThreads = 192;                    // warp 0: loader lane, warp 1: MMA lane, warps 2..5: final epilogue
+
+struct WgTask {
+  long long d_off, x_off;      // byte offsets of the dY / X tensors inside the stash
+  int d_slabs, x_slabs;        // slabs per tile of each tensor
+  int x_slab0, n_xslabs;       // slab range of X used (N = 8 * n_xslabs <= 256)
+  int g_off;                   // float offset of the destination block (row stride kGLd) + column offset
+  int cta0, nctas;             // CTAs [cta0, cta0 + nctas) work on this task, tiles split evenly
+};
+struct WgParams {
+  const uint8_t* stash;
+  float* gbuf;
+  long long n_tiles;
+  int n_tasks;
+  WgTask t[24];
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgSlots * kWgSlotBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWgSlots;
+  uint64_t* done = bars + 2 * kWgSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // which task / tile range
+  int ti = 0;
+  while (ti + 1 < p.n_tasks && (int)blockIdx.x >= p.t[ti + 1].cta0) ++ti;
+  const WgTask& T = p.t[ti];
+  const int local = blockIdx.x - T.cta0;
+  const long long per = (p.n_tiles + T.nctas - 1) / T.nctas;
+  const long long t0 = (long long)local * per, t1 = min(p.n_tiles, t0 + per);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int N = 8 * T.n_xslabs;
+  const int halves = (T.d_slabs + 15) / 16;
+  if (warp == 0 && lane == 0) {
+    // loader: per tile, slot k <- dY tile, slot k+1 <- the used slabs of the X tile
+    int slot = 0, phase = 0;
+    const uint32_t d_bytes = (uint32_t)T.d_slabs * 2048u, x_bytes = (uint32_t)T.n_xslabs * 2048u;
+    for (long long t = t0; t < t1; ++t) {
+      mbar_wait(&empty[slot], phase ^ 1);
+      mbar_arrive_expect_tx(&full[slot], d_bytes);
+      bulk_g2s(smem + slot * kWgSlotBytes, p.stash + T.d_off + t * (long long)T.d_slabs * 2048, d_bytes, &full[slot]);
+      if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
+      mbar_wait(&empty[slot], phase ^ 1);
+      mbar_arrive_expect_tx(&full[slot], x_bytes);
+      bulk_g2s(smem + slot * kWgSlotBytes, p.stash + T.x_off + (t * (long long)T.x_slabs + T.x_slab0) * 2048, x_bytes, &full[slot]);
+      if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // MMA issuer: G[half] (128 channels x N) += dY_tile[half]^T (channels x points) * X_tile (points x N)
+    // both operands MN-major: 16-byte unit = 8 consecutive channels of one point, units of consecutive points are
+    // 16 bytes apart (LBO field = 128 B per group of 8 points), channel groups are one slab (2048 B) apart (SBO field)
+    int slot = 0, phase = 0;
+    const uint32_t idesc = make_idesc_bf16(128, N) | (1u << 15) | (1u << 16);
+    const uint32_t desc_hi = (2048u >> 4) | (1u << 14);
+    const uint32_t lo_hi = (128u >> 4) << 16;
+    const uint32_t base = smem_u32(smem);
+    uint32_t acc_started = 0;
+    for (long long t = t0; t < t1; ++t) {
+      const int sd = slot;
+      mbar_wait(&full[slot], phase);
+      if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
+      const int sx = slot;
+      mbar_wait(&full[slot], phase);
+      if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
+      tc_fence_after_sync();
+      const uint32_t a0 = (((base + sd * kWgSlotBytes) >> 4) & 0x3FFF) | lo_hi;
+      const uint32_t b0 = (((base + sx * kWgSlotBytes) >> 4) & 0x3FFF) | lo_hi;
+      for (int h = 0; h < halves; ++h) {
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k)      // 16 points per MMA: start address advances 16 points x 16 B
+          umma_bf16_split(tmem + h * 256, a0 + (uint32_t)h * (16u * 2048u >> 4) + k * 16u, desc_hi, b0 + k * 16u, desc_hi, idesc,
+                          acc_started | k);
+      }
+      acc_started = 1;
+      umma_commit(&empty[sd]);
+      umma_commit(&empty[sx]);
+    }
+    umma_commit(done);
+  } else if (warp >= 2) {
+    // final epilogue: TMEM -> fp32 atomics into this layer's G block (a handful of CTAs share a block)
+    mbar_wait(done, 0);
+    tc_fence_after_sync();
+    if (t1 > t0) {
+      const int q = warp & 3, row = q * 32 + lane;
+      for (int h = 0; h < halves; ++h) {
+        float* g = p.gbuf + T.g_off + (long long)(h * 128 + row) * kGLd;
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem + h * 256 + (((uint32_t)(q * 32)) << 16) + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(g + c0 + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// thin reductions over a stash tensor Y (tile-major bf16, 32 slabs):
+//   d3 != null: out[j*ld + c] += sum_p d3[p, j] * Y[p, c]  (j < 3)      (3-row weight gradients of the output layers)
+//   d3 == null: out[c]        += sum_p Y[p, c]                          (column sums)
+// ---------------------------------------------------------------------------------------------
+struct ThinTask { long long y_off; int slabs; const float* d3; float* out; int ld; };
+struct ThinParams { const uint8_t* stash; long long n_tiles, n_points; int n_tasks; ThinTask t[20]; };
+
+__global__ void __launch_bounds__(256) thin_reduce_kernel(const __grid_constant__ ThinParams p) {
+  const ThinTask& T = p.t[blockIdx.y];
+  const int c = threadIdx.x;                       // channel
+  if (c >= T.slabs * 8) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(p.stash + T.y_off + tile * (long long)T.slabs * 2048) +
+                             (c >> 3) * (kTileM * 8) + (c & 7);
+    const long long p0 = tile * kTileM;
+    const int rows = (int)min((long long)kTileM, p.n_points - p0);
+    if (T.d3) {
+      for (int r = 0; r < rows; ++r) {
+        const float v = __bfloat162float(y[r * 8]);
+        const float* d = T.d3 + 3 * (p0 + r);
+        a0 += __ldg(d) * v; a1 += __ldg(d + 1) * v; a2 += __ldg(d + 2) * v;
+      }
+    } else {
+      for (int r = 0; r < rows; ++r) a0 += __bfloat162float(y[r * 8]);
+    }
+  }
+  atomicAdd(T.out + c, a0);
+  if (T.d3) { atomicAdd(T.out + T.ld + c, a1); atomicAdd(T.out + 2 * T.ld + c, a2); }
+}
+
+// column sums of a [n,3] fp32 tensor -> out[0..2]
+__global__ void sum3_kernel(const float* __restrict__ d3, long long n, float* __restrict__ out) {
+  float a[3] = {0.f, 0.f, 0.f};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    for (int j = 0; j < 3; ++j) a[j] += d3[3 * i + j];
+  for (int j = 0; j < 3; ++j) {
+    a[j] = warp_sum(a[j]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + j, a[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: G (gradient wrt the folded weights, in the packed column order) + column sums -> gradient arena
+//   y = (x W^T + b - mean) * gamma * istd + beta (then * post):  W_eff = W * gamma*istd*post
+//   dW = gamma*istd*post * G,  db = gamma*istd*post * s,  dbeta = post * s,
+//   dgamma = istd*post * (rowdot(W, G) + (b - mean) * s)
+// ---------------------------------------------------------------------------------------------
+enum { FK_IDENT = 0, FK_EMB = 1, FK_SKIP = 2, FK_C0 = 3 };
+struct FinLayer {
+  int net, layer, kind, split, epad, ev;   // kind-specific: split = columns fed by the previous layer (FK_SKIP) / small_w (FK_C0)
+  int g_slot;          // gbuf slot holding G rows for output channels [row0, ..)
+  int row0;            // first output channel served by the G block (3 for the VF output layer: rows 0..2 come from thin3)
+  int thin_slot;       // slot whose first 3 G rows hold the thin gradient of channels 0..2 (-1: none)
+  float post;
+};
+struct FinParams {
+  vfnerf_mlp_desc vf, rn;
+  const float* vf_arena; const float* rn_arena;
+  float* vf_grad; float* rn_grad;
+  const float* gbuf;
+  float eps;
+  int n_layers;
+  FinLayer L[VFNERF_MAX_LAYERS * 2];
+};
+
+__global__ void __launch_bounds__(128) tc_finalize_kernel(const __grid_constant__ FinParams p) {
+  const FinLayer& F = p.L[blockIdx.y];
+  const vfnerf_mlp_desc& d = F.net == 0 ? p.vf : p.rn;
+  const float* arena = F.net == 0 ? p.vf_arena : p.rn_arena;
+  float* grad = F.net == 0 ? p.vf_grad : p.rn_grad;
+  const int l = F.layer, n = blockIdx.x;
+  if (n >= d.out_dim[l]) return;
+  const int K = d.in_dim[l];
+  const bool bn = d.gamma_off[l] >= 0;
+  // source rows
+  const bool thin = F.thin_slot >= 0 && n < F.row0;
+  const float* G = thin ? p.gbuf + (long long)F.thin_slot * kGSlot + (long long)n * kGLd
+                        : p.gbuf + (long long)F.g_slot * kGSlot + (long long)(n - F.row0) * kGLd;
+  const float s = thin ? p.gbuf[(long long)F.thin_slot * kGSlot + 256 * kGLd + n]
+                       : p.gbuf[(long long)F.g_slot * kGSlot + 256 * kGLd + (n - F.row0)];
+  float istd = 1.f, sc = 1.f;
+  if (bn) {
+    istd = 1.f / sqrtf(arena[d.var_off[l] + n] + p.eps);
+    sc = arena[d.gamma_off[l] + n] * istd;
+  }
+  const float* Wn = arena + d.w_off[l] + (long long)n * K;
+  float* dWn = grad + d.w_off[l] + (long long)n * K;
+  float dot = 0.f;
+  for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    float g;
+    if (thin || F.kind == FK_IDENT) g = G[j];
+    else if (F.kind == FK_EMB) g = G[j] + G[F.epad + j];
+    else if (F.kind == FK_SKIP) g = j < F.split ? G[j] : G[256 + (j - F.split)];
+    else {  // FK_C0: reference input [p(3), embed(view)(ev), n(3), feat]; packed [feat | n(3), 0 x5, p(3), embed(view)]
+      if (j < 3) g = G[256 + 8 + j];
+      else if (j < 3 + F.ev) g = G[256 + 11 + (j - 3)];
+      else if (j < F.split) g = G[256 + (j - 3 - F.ev)];
+      else g = G[j - F.split];
+    }
+    dot += Wn[j] * g;
+    dWn[j] = sc * F.post * g;
+  }
+  __shared__ float red[4];
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float tot = red[0] + red[1] + red[2] + red[3];
+    grad[d.b_off[l] + n] = sc * F.post * s;
+    if (bn) {
+      const float b = arena[d.b_off[l] + n];
+      grad[d.gamma_off[l] + n] = istd * F.post * (tot + (b - arena[d.mean_off[l] + n]) * s);
+      grad[d.beta_off[l] + n] = F.post * s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// orchestration
+// ---------------------------------------------------------------------------------------------
+static int g_sms = 0;
+
+int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_mlp_desc& rn,
+                const float* rn_arena, float bn_eps, int64_t n, const float* colors, const float* normals,
+                const float* d_colors, const float* d_v, float* vf_grad, float* rn_grad, cudaStream_t s) {
+  VFN_REQUIRE(plan.stash_buf && plan.wpack_bwd && plan.gbuf && plan.d3, "tc_backward: training workspace missing");
+  const TcStash& S = plan.stash;
+  const int L = vf.n_layers, Lr = rn.n_layers;
+  const int64_t tiles = (n + kTileM - 1) / kTileM;
+  float* dcol_pre = plan.d3;
+  float* dv_pre = plan.d3 + 3 * n;
+  // 1. gradients wrt the pre-activations of the two output layers
+  if (int e = launch_act_bwd(colors, 3, d_colors, 3, n, 3, ACT_SIGMOID, dcol_pre, 3, s)) return e;
+  if (int e = launch_act_bwd(normals, 3, d_v, 3, n, 3, ACT_TANH, dv_pre, 3, s)) return e;
+  VFN_CHECK_CUDA(cudaMemsetAsync(plan.gbuf, 0, plan.gbuf_floats * sizeof(float), s));
+  // 2. fused dgrad chain (also stashes dL/d(pre-activation) of every layer)
+  if (int e = tc_forward(plan, TC_MODE_BWD, dcol_pre, nullptr, 0, 0, n, dv_pre, 1, nullptr, 0, nullptr, 0, nullptr, s)) return e;
+
+  // stash tensor numbering (mlp_tc.cu build_programs)
+  auto yS = [&](int l) { return l; };
+  const int yFeat = L - 1;
+  auto yC = [&](int l) { return L + l; };
+  const int D0 = S.idx_d0;
+  // gbuf slots: VF layer l -> l, colour layer l -> L + l; thin results: VF v rows -> slot L + Lr (rows 0..2)
+  auto slotVF = [&](int l) { return l; };
+  auto slotRN = [&](int l) { return L + l; };
+  const int slotThinV = L + Lr;
+  VFN_REQUIRE((int64_t)(L + Lr + 1) * kGSlot <= plan.gbuf_floats, "tc_backward: gradient scratch too small");
+
+  // 3. weight-gradient GEMMs
+  WgParams wp{};
+  wp.stash = plan.stash_buf; wp.gbuf = plan.gbuf; wp.n_tiles = tiles;
+  int nt = 0;
+  auto task = [&](int d_t, int x_t, int x_slab0, int n_xslabs, int slot, int col0, int d_slabs_used) {
+    WgTask& T = wp.t[nt++];
+    T.d_off = S.off[d_t]; T.x_off = S.off[x_t]; T.d_slabs = S.slabs[d_t]; T.x_slabs = S.slabs[x_t];
+    T.x_slab0 = x_slab0; T.n_xslabs = n_xslabs; T.g_off = slot * kGSlot + col0;
+    (void)d_slabs_used;
+  };
+  const int skip = plan.render.skip_step;
+  task(D0 + yS(0), S.idx_emb0, 0, S.slabs[S.idx_emb0], slotVF(0), 0, 32);
+  for (int l = 1; l <= L - 2; ++l) {
+    task(D0 + yS(l), yS(l - 1), 0, 32, slotVF(l), 0, 32);
+    if (l == skip) task(D0 + yS(l), S.idx_skip, 0, 6, slotVF(l), 256, 32);
+  }
+  task(D0 + yFeat, yS(L - 2), 0, 32, slotVF(L - 1), 0, 32);
+  task(D0 + yC(0), yFeat, 0, 32, slotRN(0), 0, 32);
+  task(D0 + yC(0), S.idx_aux, 0, 6, slotRN(0), 256, 32);
+  for (int l = 1; l <= Lr - 2; ++l) task(D0 + yC(l), yC(l - 1), 0, 32, slotRN(l), 0, 32);
+  wp.n_tasks = nt;
+  if (g_sms == 0) {
+    int dev = 0;
+    VFN_CHECK_CUDA(cudaGetDevice(&dev));
+    VFN_CHECK_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  {
+    // CTAs per task proportional to the bytes it streams
+    double total = 0;
+    for (int i = 0; i < nt; ++i) total += wp.t[i].d_slabs + wp.t[i].n_xslabs;
+    int used = 0;
+    for (int i = 0; i < nt; ++i) {
+      int c = std::max(1, (int)((wp.t[i].d_slabs + wp.t[i].n_xslabs) / total * g_sms));
+      c = (int)std::min<int64_t>(c, std::max<int64_t>(1, tiles));
+      wp.t[i].cta0 = used; wp.t[i].nctas = c; used += c;
+    }
+    const size_t smem = (size_t)kWgSlots * kWgSlotBytes + 256;
+    static bool attr = false;
+    if (!attr) {
+      VFN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    wgrad_tc_kernel<<<used, kWgThreads, smem, s>>>(wp);
+    VFN_LAUNCH_CHECK();
+  }
+  // 4. thin reductions: column sums of every dY tensor, 3-row gradients of the output layers
+  {
+    ThinParams tp{};
+    tp.stash = plan.stash_buf; tp.n_tiles = tiles; tp.n_points = n;
+    int k = 0;
+    auto colsum = [&](int d_t, int slot) {
+      ThinTask& T = tp.t[k++];
+      T.y_off = S.off[d_t]; T.slabs = S.slabs[d_t]; T.d3 = nullptr; T.out = plan.gbuf + (int64_t)slot * kGSlot + 256 * kGLd; T.ld = 0;
+    };
+    for (int l = 0; l <= L - 2; ++l) colsum(D0 + yS(l), slotVF(l));
+    colsum(D0 + yFeat, slotVF(L - 1));
+    for (int l = 0; l <= Lr - 2; ++l) colsum(D0 + yC(l), slotRN(l));
+    {  // colour output layer: G[3 x 256] = dcol_pre^T Y_c[Lr-2]
+      ThinTask& T = tp.t[k++];
+      T.y_off = S.off[yC(Lr - 2)]; T.slabs = 32; T.d3 = dcol_pre; T.out = plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot; T.ld = kGLd;
+    }
+    {  // VF output layer, vector rows: G[3 x 256] = dv_pre^T Y_s[L-2]
+      ThinTask& T = tp.t[k++];
+      T.y_off = S.off[yS(L - 2)]; T.slabs = 32; T.d3 = dv_pre; T.out = plan.gbuf + (int64_t)slotThinV * kGSlot; T.ld = kGLd;
+    }
+    tp.n_tasks = k;
+    const int gx = (int)std::min<int64_t>(tiles, 4 * g_sms / std::max(1, k) + 1);
+    thin_reduce_kernel<<<dim3(gx, k), 256, 0, s>>>(tp);
+    VFN_LAUNCH_CHECK();
+    sum3_kernel<<<64, 256, 0, s>>>(dcol_pre, n, plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot + 256 * kGLd);
+    VFN_LAUNCH_CHECK();
+    sum3_kernel<<<64, 256, 0, s>>>(dv_pre, n, plan.gbuf + (int64_t)slotThinV * kGSlot + 256 * kGLd);
+    VFN_LAUNCH_CHECK();
+  }
+  // 5. finalize into the gradient arenas
+  {
+    FinParams fp{};
+    fp.vf = vf; fp.rn = rn; fp.vf_arena = vf_arena; fp.rn_arena = rn_arena; fp.vf_grad = vf_grad; fp.rn_grad = rn_grad;
+    fp.gbuf = plan.gbuf; fp.eps = bn_eps;
+    int k = 0, maxrows = 0;
+    const int Epad = plan.render.emb_pad, ev = 3 + 6 * plan.render.multires_view;
+    for (int l = 0; l < L; ++l) {
+      FinLayer& F = fp.L[k++];
+      F.net = 0; F.layer = l; F.kind = l == 0 ? FK_EMB : (l == skip ? FK_SKIP : FK_IDENT);
+      F.split = l == skip ? vf.out_dim[l - 1] : 0; F.epad = Epad; F.ev = ev;
+      F.g_slot = slotVF(l); F.row0 = l == L - 1 ? 3 : 0; F.thin_slot = l == L - 1 ? slotThinV : -1;
+      F.post = l < L - 1 ? plan.render.s[l].post_scale : 1.f;
+      maxrows = std::max(maxrows, vf.out_dim[l]);
+    }
+    for (int l = 0; l < Lr; ++l) {
+      FinLayer& F = fp.L[k++];
+      F.net = 1; F.layer = l; F.kind = l == 0 ? FK_C0 : FK_IDENT; F.split = plan.render.small_w; F.epad = Epad; F.ev = ev;
+      F.g_slot = slotRN(l); F.row0 = 0; F.thin_slot = -1; F.post = 1.f;
+      maxrows = std::max(maxrows, rn.out_dim[l]);
+    }
+    fp.n_layers = k;
+    tc_finalize_kernel<<<dim3(maxrows, k), 128, 0, s>>>(fp);
+    VFN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// test support: one stash tensor -> row-major fp32 [n, 8 * slabs]
+// ---------------------------------------------------------------------------------------------
+__global__ void stash_read_kernel(const uint8_t* __restrict__ t, int slabs, long long n, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // (point, slab)
+  if (i >= n * slabs) return;
+  const long long pnt = i / slabs;
+  const int sl = (int)(i % slabs);
+  const long long tile = pnt / kTileM;
+  const int row = (int)(pnt % kTileM);
+  const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(t + tile * (long long)slabs * 2048 + (long long)sl * 2048 + row * 16);
+  for (int j = 0; j < 8; ++j) out[pnt * (slabs * 8) + sl * 8 + j] = __bfloat162float(u[j]);
+}
+
+int tc_debug_stash_read(const TcPlan& plan, int tensor, int64_t n, float* out, int* n_cols, cudaStream_t s) {
+  VFN_REQUIRE(plan.stash_buf, "stash_read: no training workspace");
+  const TcStash& S = plan.stash;
+  if (tensor == 1000) {       // [n, 6]: d(colour pre-sigmoid), d(vector pre-tanh)
+    if (n_cols) *n_cols = 6;
+    if (!out) return 0;
+    VFN_CHECK_CUDA(cudaMemcpy2DAsync(out, 24, plan.d3, 12, 12, n, cudaMemcpyDeviceToDevice, s));
+    VFN_CHECK_CUDA(cudaMemcpy2DAsync(out + 3, 24, plan.d3 + 3 * n, 12, 12, n, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+  VFN_REQUIRE(tensor >= 0 && tensor < S.n_tensors, "stash_read: tensor %d out of range [0, %d)", tensor, S.n_tensors);
+  if (n_cols) *n_cols = S.slabs[tensor] * 8;
+  if (!out || n == 0) return 0;
+  const long long work = n * S.slabs[tensor];
+  stash_read_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s>>>(plan.stash_buf + S.off[tensor], S.slabs[tensor], n, out);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vfn

@@ -314,3 +314,69 @@ extern "C" int vfnerf_debug_umma2_bench(int n_mma, int mode, int n_ctas, long lo
   VFN_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- MN-major operand convention check (the weight-gradient GEMM): D[M=128, N] = At[K, 128]^T * Bt[K, N] where At / Bt
+// are row-major with the REDUCTION index as the row (points x channels, exactly how activations are stashed).
+// Shared-memory image: slab s holds channels 8s..8s+7 of every row k as one 16-byte unit, rows contiguous
+// (the same K-slab image the forward uses, read here with the major bits set): unit(m/8, k) at (m/8)*K*16 + k*16.
+// For an MN-major operand the canonical no-swizzle layout is ((8 m-elems),(8 k)) core matrices of 128 contiguous
+// bytes; SBO = stride between m-groups (K*16 bytes here), LBO = stride between k-groups of 8 (128 bytes).
+namespace vfn {
+__global__ void __launch_bounds__(128) umma_mn_debug_kernel(const float* __restrict__ At, const float* __restrict__ Bt,
+                                                            float* __restrict__ D, int N, int K, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * K * 2;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int e = tid; e < K * 128; e += 128) {
+    int k = e / 128, m = e % 128;
+    *reinterpret_cast<__nv_bfloat16*>(sA + (m / 8) * K * 16 + k * 16 + (m % 8) * 2) = __float2bfloat16(At[e]);
+  }
+  for (int e = tid; e < K * N; e += 128) {
+    int k = e / N, n = e % N;
+    *reinterpret_cast<__nv_bfloat16*>(sB + (n / 8) * K * 16 + k * 16 + (n % 8) * 2) = __float2bfloat16(Bt[e]);
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
+    const uint32_t sbo = K * 16, lbo = 128;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      const uint32_t a_addr = smem_u32(sA) + k0 * 16, b_addr = smem_u32(sB) + k0 * 16;
+      const uint64_t da = variant ? make_smem_desc(a_addr, sbo, lbo) : make_smem_desc(a_addr, lbo, sbo);
+      const uint64_t db = variant ? make_smem_desc(b_addr, sbo, lbo) : make_smem_desc(b_addr, lbo, sbo);
+      umma_bf16(tmem, da, db, idesc, k0 > 0);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(int64_t)row * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+}  // namespace vfn
+
+extern "C" int vfnerf_debug_umma_mn_gemm(const float* At, const float* Bt, float* D, int N, int K, int variant, void* stream) {
+  using namespace vfn;
+  VFN_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256, "debug_umma_mn_gemm: bad N/K");
+  size_t smem = (size_t)(128 + N) * K * 2;
+  VFN_CHECK_CUDA(cudaFuncSetAttribute(umma_mn_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_mn_debug_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(At, Bt, D, N, K, variant);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}

@@ -120,6 +120,28 @@ def mlp_points(vf_net, rn_net, points: torch.Tensor, ray_dirs: torch.Tensor, sam
 # ------------------------------------------------------------------------------------------------
 # render()
 # ------------------------------------------------------------------------------------------------
+# test support: keep the last training workspace alive so the activation stash can be inspected
+# (vfnerf_debug_stash_read); never set in production, the workspace is several KB per sample point
+DEBUG_KEEP_WORKSPACE = False
+_debug_last: dict = {}
+
+
+def debug_stash_read(tensor: int) -> torch.Tensor:
+    d = _debug_last
+    if not d:
+        raise RuntimeError("no workspace kept: set ops.DEBUG_KEEP_WORKSPACE = True before backward()")
+    L = _lib.lib()
+    cfg = d["cfg"]
+    n_cols = C.c_int(0)
+    args = (C.byref(cfg), C.byref(d["vf"].desc), C.byref(d["rn"].desc), d["ws"].data_ptr(), int(tensor))
+    _lib.check(L.vfnerf_debug_stash_read(*args, None, C.byref(n_cols), None), "vfnerf_debug_stash_read")
+    P = cfg.n_rays * (cfg.n_coarse + cfg.n_fine)
+    out = torch.empty(P, n_cols.value, dtype=torch.float32, device=d["ws"].device)
+    _lib.check(L.vfnerf_debug_stash_read(*args, out.data_ptr(), C.byref(n_cols), _stream_ptr(out.device)),
+               "vfnerf_debug_stash_read")
+    return out
+
+
 class RenderCall:
     """Everything one render() call needs besides the parameters (built by nerf.VectorFieldNerf)."""
 
@@ -143,8 +165,8 @@ class _Render(torch.autograd.Function):
         dev = call.uv.device
         R, N = cfg.n_rays, cfg.n_coarse + cfg.n_fine
         need_bwd = call.need_bwd
-        if need_bwd and cfg.precision != _lib.PREC_FP32:
-            raise RuntimeError("training (backward) currently runs on precision='fp32' only")
+        if need_bwd and cfg.precision not in (_lib.PREC_FP32, _lib.PREC_BF16):
+            raise RuntimeError("training (backward) runs on precision 'fp32' or 'bf16'")
         nbytes = L.vfnerf_render_workspace_bytes(C.byref(cfg), C.byref(vf_ar.desc), C.byref(rn_ar.desc), int(need_bwd))
         if nbytes < 0:
             _lib.check(1, "vfnerf_render_workspace_bytes")
@@ -204,6 +226,8 @@ class _Render(torch.autograd.Function):
             dflat.data_ptr(), C.byref(ctx.out_struct), d_rgb.data_ptr(), d_depth.data_ptr(), _lib.ptr(d_normals),
             _lib.ptr(d_colors), g_vf.data_ptr(), g_rn.data_ptr(), g_d.data_ptr(), ctx.ws.data_ptr(),
             ctx.ws.numel(), _stream_ptr(dev)), "vfnerf_render_bwd")
+        if DEBUG_KEEP_WORKSPACE:
+            _debug_last.update(cfg=cfg, ws=ctx.ws, vf=vf_ar, rn=rn_ar)
         ctx.ws = ctx.keep = None
         grads = vf_ar.grad_views(g_vf) + rn_ar.grad_views(g_rn) + [g_d[0], g_d[1], g_d[2]]
         return (None,) + tuple(grads)
