@@ -291,7 +291,7 @@ __device__ __forceinline__ void umma2_commit_u32(uint32_t bar) {
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
-template <bool kBwd>
+template <bool kBwd, bool kStash>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -542,7 +542,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       const long long tile = tile_of(pair);
       const long long pi = tile * kTileM + row;
       const bool valid = pi < p.n_points;
-      const bool st_on = p.stash != nullptr && tile < num_tiles;
+      const bool st_on = kStash && tile < num_tiles;
       float pt[3], emb[48];
       load_point(p, pi, valid, pt);
 #pragma unroll
@@ -653,7 +653,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const bool feat = st.epi == TC_EPI_FEAT;
           const bool to_act = !feat || render;
           const int stN = st.N;
-          const bool st_on = p.stash != nullptr && st.stash_out >= 0 && tile < num_tiles;
+          const bool st_on = kStash && st.stash_out >= 0 && tile < num_tiles;
           if (to_act) {
             // Each warp owns two of the four 64-column groups (= K chunks of the next layer): h=0 -> groups 0 and 2,
             // h=1 -> groups 1 and 3.  One generic->async proxy fence (a MEMBAR.ALL.CTA) and one barrier arrival per
@@ -806,7 +806,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               // the normal is the first 16-byte unit of the colour net's small inputs (aux columns 0..7)
               float a[8] = {nv[0], nv[1], nv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
               store_slab_f(s_act, kColAux / 8, row, a);
-              if (p.stash != nullptr && tile < num_tiles)
+              if (kStash && tile < num_tiles)
                 *stash_unit(p, p.sinfo.idx_aux, tile, 0, row) = make_uint4(pack_bf16x2(nv[0], nv[1]), pack_bf16x2(nv[2], 0.f), 0u, 0u);
               fence_proxy_async_smem();
             }
@@ -1063,12 +1063,14 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   const size_t smem = (size_t)kActCols * kTileM * 2 + (size_t)kTcStages * kStageBytes + 512 + kTcMaxSteps * 8 * 16 + 128;
   static bool attr = false;
   if (!attr) {
-    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  if (mode == TC_MODE_BWD) mlp_tc_kernel<true><<<grid_x, kTcThreads, smem, s>>>(p);
-  else mlp_tc_kernel<false><<<grid_x, kTcThreads, smem, s>>>(p);
+  if (mode == TC_MODE_BWD) mlp_tc_kernel<true, true><<<grid_x, kTcThreads, smem, s>>>(p);
+  else if (mode == TC_MODE_RENDER_STASH) mlp_tc_kernel<false, true><<<grid_x, kTcThreads, smem, s>>>(p);
+  else mlp_tc_kernel<false, false><<<grid_x, kTcThreads, smem, s>>>(p);
   VFN_LAUNCH_CHECK();
   if (p.dbg_buf) {
     long long h[256];
