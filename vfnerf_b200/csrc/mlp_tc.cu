@@ -303,7 +303,10 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   uint64_t* empty = bars + kTcStages;
   uint64_t* fullp = bars + 2 * kTcStages;      // leader only: "the peer's half of the chunk has landed"
   uint64_t* acc_full = bars + 3 * kTcStages;
-  uint64_t* grp = acc_full + 1;                 // leader only: A-operand readiness
+  // one "accumulator complete" barrier per TMEM accumulator buffer: buffer b is committed once per two steps, and the
+  // MMAs of step g+2 depend (through the column-group barriers) on every epilogue warp having finished step g+1, hence
+  // having passed its wait for step g -- the issuer can never complete a phase twice before a slow warp has seen it
+  uint64_t* grp = acc_full + 2;                 // leader only: A-operand readiness
   uint64_t* reg_free = grp + kGroups;           // [0] emb0, [1] skip, [2] aux-static: their reader MMAs have completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reg_free + 3);
   // chunk table: the single-lane producer / MMA-issuer loops must not chase per-chunk facts through the kernel
@@ -318,7 +321,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   if (threadIdx.x == 0) {
     // leader: a ring slot is full when its own bulk copy has landed AND the peer's relay has arrived
     for (int i = 0; i < kTcStages; ++i) { mbar_init(&full[i], rank == 0 ? 2 : 1); mbar_init(&empty[i], 1); mbar_init(&fullp[i], 1); }
-    mbar_init(acc_full, 1);
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     for (int i = 0; i < kGroups; ++i) mbar_init(&grp[i], 8);    // 4 warps (one half, or the prologue warps) x 2 CTAs
     for (int i = 0; i < 3; ++i) mbar_init(&reg_free[i], 1);
     fence_barrier_init();
@@ -484,7 +487,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             if (ck.w) break;
             ck = nxt; ++ckp;
           }
-          umma2_commit(acc_full);                  // accumulators complete -> epilogue warps of both CTAs
+          umma2_commit(&acc_full[gstep & 1]);      // accumulators complete -> epilogue warps of both CTAs
           // side regions whose only reader was this step may now be rewritten for the next tile (prologue warps)
           if (si == 0) umma2_commit(&reg_free[0]);
           if (si == prog.skip_step) umma2_commit(&reg_free[1]);
@@ -644,8 +647,96 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       for (int si = 0; si < prog.n_steps; ++si, ++gstep) {
         const TcStep& st = prog.s[si];
         const uint32_t acc = tmem + (gstep & 1) * kAccCols + lane_off;
+        if (kBwd) {
+          // dgrad step: acc = dL/d(this layer's input); gate it with the stashed forward activation Y of that input
+          // (ReLU: Y > 0; tanh: 1 - Y^2), hand it on as the next step's A operand and stash it for the wgrad GEMM.
+          // The gates are fetched BEFORE waiting for the accumulator, so their HBM latency hides behind this step's
+          // MMAs; ReLU gates are compressed to one bit per element on arrival (2 registers per 64 columns).
+          const bool is_tanh = st.epi == TC_EPI_BWD_TANH;
+          const int stN = st.N;
+          const bool t_ok = tile < num_tiles;
+          // the last step's output (dL/d pre-activation of layer 0) has no consumer in this launch: it is only stashed,
+          // and it must not arrive on the column-group barriers (every arrival set is matched by exactly one wait of
+          // the MMA issuer; an unmatched one would shift the barrier phases of the next tile)
+          const bool hand_on = si + 1 < prog.n_steps;
+          uint32_t gbits[2][2] = {{0u, 0u}, {0u, 0u}};
+          if (!is_tanh && t_ok) {
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+              const int c0 = (2 * it + h) * 64;
+              if (c0 < stN) {
+                const bool second = c0 + 32 < stN;
+                uint4 ym[8];
+#pragma unroll
+                for (int sl = 0; sl < 8; ++sl)
+                  ym[sl] = (sl < 4 || second) ? __ldg(stash_unit(p, st.mask_src, tile, (c0 >> 3) + sl, row)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int sl = 0; sl < 8; ++sl) {
+                  const uint32_t* y = reinterpret_cast<const uint32_t*>(&ym[sl]);
+                  uint32_t b = 0;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    b |= ((y[j] & 0x7FFFu) && !(y[j] & 0x8000u)) ? (1u << (2 * j)) : 0u;
+                    b |= ((y[j] & 0x7FFF0000u) && !(y[j] & 0x80000000u)) ? (2u << (2 * j)) : 0u;
+                  }
+                  gbits[it][sl >> 2] |= b << (8 * (sl & 3));
+                }
+              }
+            }
+          }
+          TCK(t_other);
+          mbar_wait(&acc_full[gstep & 1], (gstep >> 1) & 1);
+          TCK(t_acc);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int bg = 2 * it + h, c0 = bg * 64;
+            if (c0 >= stN) { if (hand_on) arrive_grp(bg); continue; }
+            const bool second = c0 + 32 < stN;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              if (half == 1 && !second) break;
+              const int cb = c0 + 32 * half;
+              uint32_t va[32];
+              tmem_ld32(acc + cb, va);
+              uint4 yt[4];
+              if (is_tanh) {
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl)
+                  yt[sl] = t_ok ? __ldg(stash_unit(p, st.mask_src, tile, (cb >> 3) + sl, row)) : make_uint4(0, 0, 0, 0);
+              }
+              tmem_ld_wait();
+              const uint32_t bits = gbits[it][half];
+#pragma unroll
+              for (int sl = 0; sl < 4; ++sl) {
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float a0 = __uint_as_float(va[8 * sl + 2 * j]), a1 = __uint_as_float(va[8 * sl + 2 * j + 1]);
+                  if (is_tanh) {
+                    const uint32_t y2 = reinterpret_cast<const uint32_t*>(&yt[sl])[j];
+                    const float y0 = __uint_as_float(y2 << 16), y1 = __uint_as_float(y2 & 0xFFFF0000u);
+                    o[j] = pack_bf16x2(a0 * (1.f - y0 * y0), a1 * (1.f - y1 * y1));
+                  } else {
+                    const int e = 8 * sl + 2 * j;
+                    o[j] = pack_bf16x2(((bits >> e) & 1u) ? a0 : 0.f, ((bits >> (e + 1)) & 1u) ? a1 : 0.f);
+                  }
+                }
+                if (hand_on) store_slab_u(s_act, (cb >> 3) + sl, row, o[0], o[1], o[2], o[3]);
+                if (t_ok) *stash_unit(p, st.stash_out, tile, (cb >> 3) + sl, row) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+            }
+            if (hand_on) {
+              fence_proxy_async_smem();
+              tc_fence_before_sync();
+              arrive_grp(bg);
+            }
+          }
+          tc_fence_before_sync();
+          continue;
+        }
         TCK(t_other);
-        mbar_wait(acc_full, gstep & 1);
+        mbar_wait(&acc_full[gstep & 1], (gstep >> 1) & 1);
         TCK(t_acc);
         if (tl) p.dbg_buf[64 + si * 8 + 2 + 3 * h] = clock64();
         tc_fence_after_sync();
@@ -736,60 +827,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             }
           }
         } else if (kBwd && (st.epi == TC_EPI_BWD_RELU || st.epi == TC_EPI_BWD_TANH)) {
-          // dgrad step: acc = dL/d(this layer's input); gate it with the stashed forward activation Y of that input
-          // (ReLU: Y > 0; tanh: 1 - Y^2), hand it on as the next step's A operand and stash it for the wgrad GEMM.
-          const bool is_tanh = st.epi == TC_EPI_BWD_TANH;
-          const int stN = st.N;
-          const bool t_ok = tile < num_tiles;
-          // the last step's output (dL/d pre-activation of layer 0) has no consumer in this launch: it is only stashed,
-          // and it must not arrive on the column-group barriers (every arrival set is matched by exactly one wait of
-          // the MMA issuer; an unmatched one would shift the barrier phases of the next tile)
-          const bool hand_on = si + 1 < prog.n_steps;
-#pragma unroll 1
-          for (int it = 0; it < 2; ++it) {
-            const int bg = 2 * it + h, c0 = bg * 64;
-            if (c0 >= stN) { if (hand_on) arrive_grp(bg); continue; }
-            const bool second = c0 + 32 < stN;
-            uint4 ym[8];
-#pragma unroll
-            for (int sl = 0; sl < 8; ++sl)
-              ym[sl] = (t_ok && (sl < 4 || second)) ? __ldg(stash_unit(p, st.mask_src, tile, (c0 >> 3) + sl, row)) : make_uint4(0, 0, 0, 0);
-            uint32_t va[32], vb[32];
-            tmem_ld32(acc + c0, va);
-            if (second) tmem_ld32(acc + c0 + 32, vb);
-            tmem_ld_wait();
-            auto gate = [&](uint32_t y2, uint32_t a_lo_bits, uint32_t a_hi_bits) -> uint32_t {
-              const float a0 = __uint_as_float(a_lo_bits), a1 = __uint_as_float(a_hi_bits);
-              if (is_tanh) {
-                const float y0 = __uint_as_float(y2 << 16), y1 = __uint_as_float(y2 & 0xFFFF0000u);
-                return pack_bf16x2(a0 * (1.f - y0 * y0), a1 * (1.f - y1 * y1));
-              }
-              return pack_bf16x2((y2 & 0xFFFFu) ? a0 : 0.f, (y2 >> 16) ? a1 : 0.f);
-            };
-#pragma unroll
-            for (int sl = 0; sl < 4; ++sl) {
-              const uint32_t* y = reinterpret_cast<const uint32_t*>(&ym[sl]);
-              const uint4 o = make_uint4(gate(y[0], va[8 * sl + 0], va[8 * sl + 1]), gate(y[1], va[8 * sl + 2], va[8 * sl + 3]),
-                                         gate(y[2], va[8 * sl + 4], va[8 * sl + 5]), gate(y[3], va[8 * sl + 6], va[8 * sl + 7]));
-              store_slab_u(s_act, (c0 >> 3) + sl, row, o.x, o.y, o.z, o.w);
-              if (t_ok) *stash_unit(p, st.stash_out, tile, (c0 >> 3) + sl, row) = o;
-            }
-            if (second) {
-#pragma unroll
-              for (int sl = 0; sl < 4; ++sl) {
-                const uint32_t* y = reinterpret_cast<const uint32_t*>(&ym[4 + sl]);
-                const uint4 o = make_uint4(gate(y[0], vb[8 * sl + 0], vb[8 * sl + 1]), gate(y[1], vb[8 * sl + 2], vb[8 * sl + 3]),
-                                           gate(y[2], vb[8 * sl + 4], vb[8 * sl + 5]), gate(y[3], vb[8 * sl + 6], vb[8 * sl + 7]));
-                store_slab_u(s_act, (c0 >> 3) + 4 + sl, row, o.x, o.y, o.z, o.w);
-                if (t_ok) *stash_unit(p, st.stash_out, tile, (c0 >> 3) + 4 + sl, row) = o;
-              }
-            }
-            if (hand_on) {
-              fence_proxy_async_smem();
-              tc_fence_before_sync();
-              arrive_grp(bg);
-            }
-          }
+          // unreachable: backward steps are handled before the accumulator wait (mask prefetch)
         } else if (!kBwd && st.epi == TC_EPI_V) {
           if (h == 0) {
             uint32_t v[16];

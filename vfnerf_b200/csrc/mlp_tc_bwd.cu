@@ -140,28 +140,61 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 struct ThinTask { long long y_off; int slabs; const float* d3; float* out; int ld; };
 struct ThinParams { const uint8_t* stash; long long n_tiles, n_points; int n_tasks; ThinTask t[20]; };
 
+// warp w of a block owns slabs w, w+8, w+16, w+24; lane l owns rows l, l+32, l+64, l+96 of every tile: each load
+// instruction of a warp reads 512 contiguous bytes.  Sums stay in registers across the block's tiles and are reduced
+// across lanes once at the end.
+template <bool kD3>
 __global__ void __launch_bounds__(256) thin_reduce_kernel(const __grid_constant__ ThinParams p) {
   const ThinTask& T = p.t[blockIdx.y];
-  const int c = threadIdx.x;                       // channel
-  if (c >= T.slabs * 8) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((T.d3 != nullptr) != kD3) return;
+  constexpr int kOut = kD3 ? 3 : 1;
+  float acc[4][8][kOut];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int o = 0; o < kOut; ++o) acc[a][j][o] = 0.f;
   for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(p.stash + T.y_off + tile * (long long)T.slabs * 2048) +
-                             (c >> 3) * (kTileM * 8) + (c & 7);
+    const uint8_t* base = p.stash + T.y_off + tile * (long long)T.slabs * 2048;
     const long long p0 = tile * kTileM;
-    const int rows = (int)min((long long)kTileM, p.n_points - p0);
-    if (T.d3) {
-      for (int r = 0; r < rows; ++r) {
-        const float v = __bfloat162float(y[r * 8]);
-        const float* d = T.d3 + 3 * (p0 + r);
-        a0 += __ldg(d) * v; a1 += __ldg(d + 1) * v; a2 += __ldg(d + 2) * v;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = lane + 32 * rr;
+      const bool ok = p0 + r < p.n_points;
+      float d[3] = {1.f, 0.f, 0.f};
+      if (kD3) {
+        if (ok) { const float* dp = T.d3 + 3 * (p0 + r); d[0] = __ldg(dp); d[1] = __ldg(dp + 1); d[2] = __ldg(dp + 2); }
+        else d[0] = 0.f;
+      } else if (!ok) d[0] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int sl = warp + 8 * a;
+        if (sl >= T.slabs) continue;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)sl * 2048 + r * 16));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v0 = __uint_as_float(w[j] << 16), v1 = __uint_as_float(w[j] & 0xFFFF0000u);
+#pragma unroll
+          for (int o = 0; o < kOut; ++o) { acc[a][2 * j][o] += d[o] * v0; acc[a][2 * j + 1][o] += d[o] * v1; }
+        }
       }
-    } else {
-      for (int r = 0; r < rows; ++r) a0 += __bfloat162float(y[r * 8]);
     }
   }
-  atomicAdd(T.out + c, a0);
-  if (T.d3) { atomicAdd(T.out + T.ld + c, a1); atomicAdd(T.out + 2 * T.ld + c, a2); }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int sl = warp + 8 * a;
+    if (sl >= T.slabs) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int o = 0; o < kOut; ++o) {
+        const float v = warp_sum(acc[a][j][o]);
+        if (lane == 0) atomicAdd(T.out + o * T.ld + sl * 8 + j, v);
+      }
+  }
 }
 
 // column sums of a [n,3] fp32 tensor -> out[0..2]
@@ -350,7 +383,9 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
     }
     tp.n_tasks = k;
     const int gx = (int)std::min<int64_t>(tiles, 4 * g_sms / std::max(1, k) + 1);
-    thin_reduce_kernel<<<dim3(gx, k), 256, 0, s>>>(tp);
+    thin_reduce_kernel<false><<<dim3(gx, k), 256, 0, s>>>(tp);     // column sums (tasks with d3 == null)
+    VFN_LAUNCH_CHECK();
+    thin_reduce_kernel<true><<<dim3(gx, k), 256, 0, s>>>(tp);      // 3-row gradients
     VFN_LAUNCH_CHECK();
     sum3_kernel<<<64, 256, 0, s>>>(dcol_pre, n, plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot + 256 * kGLd);
     VFN_LAUNCH_CHECK();
