@@ -213,6 +213,10 @@ __device__ __forceinline__ uint4* stash_unit(const TcParams& p, int t, long long
                                   (long long)slab * (kTileM * 16) + row * 16);
 }
 
+__device__ __forceinline__ uint2* gate_unit(const TcParams& p, int t, long long tile, int group, int row) {
+  return reinterpret_cast<uint2*>(p.stash + p.sinfo.gate_off[t] + ((tile * 4 + group) * kTileM + row) * 8);
+}
+
 // readiness barriers (bit mask) that guard the 64-column chunk starting at activation-tile column `col`
 __device__ __forceinline__ uint32_t col_barriers(int col) {
   if (col < kColAux) return 1u << (col >> 6);
@@ -650,8 +654,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         if (kBwd) {
           // dgrad step: acc = dL/d(this layer's input); gate it with the stashed forward activation Y of that input
           // (ReLU: Y > 0; tanh: 1 - Y^2), hand it on as the next step's A operand and stash it for the wgrad GEMM.
-          // The gates are fetched BEFORE waiting for the accumulator, so their HBM latency hides behind this step's
-          // MMAs; ReLU gates are compressed to one bit per element on arrival (2 registers per 64 columns).
+          // ReLU gates were stored by the forward as one bit per element (8 bytes per row and 64 columns); they are
+          // fetched BEFORE waiting for the accumulator, so their latency hides behind this step's MMAs.
           const bool is_tanh = st.epi == TC_EPI_BWD_TANH;
           const int stN = st.N;
           const bool t_ok = tile < num_tiles;
@@ -663,24 +667,10 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           if (!is_tanh && t_ok) {
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
-              const int c0 = (2 * it + h) * 64;
-              if (c0 < stN) {
-                const bool second = c0 + 32 < stN;
-                uint4 ym[8];
-#pragma unroll
-                for (int sl = 0; sl < 8; ++sl)
-                  ym[sl] = (sl < 4 || second) ? __ldg(stash_unit(p, st.mask_src, tile, (c0 >> 3) + sl, row)) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int sl = 0; sl < 8; ++sl) {
-                  const uint32_t* y = reinterpret_cast<const uint32_t*>(&ym[sl]);
-                  uint32_t b = 0;
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    b |= ((y[j] & 0x7FFFu) && !(y[j] & 0x8000u)) ? (1u << (2 * j)) : 0u;
-                    b |= ((y[j] & 0x7FFF0000u) && !(y[j] & 0x80000000u)) ? (2u << (2 * j)) : 0u;
-                  }
-                  gbits[it][sl >> 2] |= b << (8 * (sl & 3));
-                }
+              const int bg = 2 * it + h;
+              if (bg * 64 < stN) {
+                const uint2 g2 = __ldg(gate_unit(p, st.mask_src, tile, bg, row));
+                gbits[it][0] = g2.x; gbits[it][1] = g2.y;
               }
             }
           }
@@ -770,11 +760,18 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                 for (int sl = 0; sl < 4; ++sl)
                   store_slab_u(s_act, (c0 >> 3) + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+                uint32_t gate_lo = 0, gate_hi = 0;
                 if (st_on) {
 #pragma unroll
                   for (int sl = 0; sl < 4; ++sl)
                     *stash_unit(p, st.stash_out, tile, (c0 >> 3) + sl, row) =
                         make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+                  // gate bit e = "pre-activation of column c0 + e is not negative": one funnel shift per element
+                  // collects the fp32 sign bits (an exact zero passes the gate; its gradient contribution is zero or
+                  // belongs to a padded channel)
+#pragma unroll
+                  for (int j = 31; j >= 0; --j) gate_lo = __funnelshift_l(va[j], gate_lo, 1);
+                  gate_lo = ~gate_lo;
                 }
                 if (second) {
 #pragma unroll
@@ -790,8 +787,13 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                     for (int sl = 0; sl < 4; ++sl)
                       *stash_unit(p, st.stash_out, tile, (c0 >> 3) + 4 + sl, row) =
                           make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+#pragma unroll
+                    for (int j = 31; j >= 0; --j) gate_hi = __funnelshift_l(vb[j], gate_hi, 1);
+                    gate_hi = ~gate_hi;
                   }
                 }
+                // the backward gates on the sign only: 8 bytes per row and 64-column group instead of 128
+                if (st_on && !feat) *gate_unit(p, st.stash_out, tile, bg, row) = make_uint2(gate_lo, gate_hi);
               }
               TCK(t_math);
               fence_proxy_async_smem();
@@ -1035,6 +1037,7 @@ int tc_carve(char* base, int64_t& off, int multires, int multires_view, int skip
     TcStash& S = plan.stash;
     int64_t so = 0;
     for (int i = 0; i < S.n_tensors; ++i) { S.off[i] = so; so += tiles2 * S.slabs[i] * (kTileM * 16); }
+    for (int i = 0; i < S.n_tensors; ++i) { S.gate_off[i] = so; if (i < S.n_y) so += tiles2 * 4 * kTileM * 8; }
     S.bytes = so;
     plan.stash_buf = base ? reinterpret_cast<uint8_t*>(base + off) : nullptr;
     off += align_up(so, 1024);

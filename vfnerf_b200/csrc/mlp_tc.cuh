@@ -61,6 +61,7 @@ struct TcStash {
   int n_tensors;
   int slabs[kTcMaxStash];           // 8-channel slabs per tile
   long long off[kTcMaxStash];       // byte offset of the tensor inside the stash buffer
+  long long gate_off[kTcMaxStash];  // ReLU gates of hidden-layer tensor i as bits: [tile][64-column group][row] x 8 bytes
   long long bytes;
 };
 

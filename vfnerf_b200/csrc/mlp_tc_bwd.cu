@@ -382,10 +382,14 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
       T.y_off = S.off[yS(L - 2)]; T.slabs = 32; T.d3 = dv_pre; T.out = plan.gbuf + (int64_t)slotThinV * kGSlot; T.ld = kGLd;
     }
     tp.n_tasks = k;
-    const int gx = (int)std::min<int64_t>(tiles, 4 * g_sms / std::max(1, k) + 1);
-    thin_reduce_kernel<false><<<dim3(gx, k), 256, 0, s>>>(tp);     // column sums (tasks with d3 == null)
+    // the two 3-row tasks are the last two entries: column sums and 3-row gradients get their own launches and grids
+    const int n_sum = k - 2;
+    const int gx = (int)std::min<int64_t>(tiles, 4 * g_sms / std::max(1, n_sum) + 1);
+    thin_reduce_kernel<false><<<dim3(gx, n_sum), 256, 0, s>>>(tp);
     VFN_LAUNCH_CHECK();
-    thin_reduce_kernel<true><<<dim3(gx, k), 256, 0, s>>>(tp);      // 3-row gradients
+    ThinParams t3 = tp;
+    t3.t[0] = tp.t[k - 2]; t3.t[1] = tp.t[k - 1]; t3.n_tasks = 2;
+    thin_reduce_kernel<true><<<dim3((int)std::min<int64_t>(tiles, 2 * g_sms), 2), 256, 0, s>>>(t3);
     VFN_LAUNCH_CHECK();
     sum3_kernel<<<64, 256, 0, s>>>(dcol_pre, n, plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot + 256 * kGLd);
     VFN_LAUNCH_CHECK();
