@@ -183,7 +183,13 @@ class VectorFieldNerf:
             U2, U3 = self.fine_sampler.draw(R)
         else:
             U1, U2, U3 = draws
-        t_vals = self.ray_sampler.t_vals()
+        # host linspace (bit-exact with the reference), uploaded once per (device, count): keeps render() free of
+        # host->device copies when the draws are given on the device (CUDA-graph capture, graphed.py)
+        key = (str(dev), self.ray_sampler.N_samples)
+        if getattr(self, "_t_vals_key", None) != key:
+            self._t_vals_dev = self.ray_sampler.t_vals().to(dev).float().contiguous()
+            self._t_vals_key = key
+        t_vals = self._t_vals_dev
 
         def dev_(t):
             return None if t is None else t.to(dev, non_blocking=True).float().contiguous()
