@@ -313,9 +313,56 @@ def main():
         ms_tr = time_train(args.precision, 10 if args.precision == "bf16" else 5)
         train = {"value": world * Rt / (ms_tr * 1e-3), "unit": "rays/s", "rays_per_step_per_gpu": Rt,
                  "ms_per_step": ms_tr, "precision": args.precision,
-                 "includes": "render fwd + loss + backward + (allreduce) + clip_grad_norm_ + Adam"}
+                 "includes": "eager: render fwd + loss + backward + (allreduce) + clip_grad_norm_ + Adam"}
         if args.precision != "fp32":
             train["fp32_ms_per_step"] = time_train("fp32", 3)
+
+        # the same sequence captured once as a CUDA graph and replayed (vfnerf_b200/graphed.py), and -- SURVEY.md §8(d)
+        # training protocol (i) -- the kernels alone: fwd + loss gradient + bwd into the flat gradient buffers,
+        # graph replay, median of 50.  Single-GPU legs (the allreduce of a multi-GPU step is not captured).
+        if world == 1:
+            from vfnerf_b200 import graphed
+
+            def loss_fn(out, rgb_gt, depth_gt):
+                nrm = torch.norm(out.coarse_normals.reshape(-1, 3), dim=1)
+                return 2.0 * (out.coarse_rgb_values - rgb_gt).abs().mean() + \
+                    0.5 * (out.coarse_depth_map - depth_gt).abs().clamp(max=0.5).mean() + 0.1 * torch.mean((nrm - 1) ** 2)
+
+            def time_graphed(n_rays, full, reps=50):
+                tm = U.make_model(dict(CASE, perturb=True, dir_to_normal_th=-2.0), st, dev, precision=args.precision)
+                graphed.make_capturable(tm)
+                uvg, poseg, Kg = uv_d[:n_rays], pose_d[:n_rays], K_d[:n_rays]
+                tg = dict(rgb_gt=torch.rand(n_rays, 3, device=dev), depth_gt=torch.rand(n_rays, 1, device=dev) * CASE["far"])
+                step = graphed.GraphedTrainStep(tm, loss_fn, n_rays, tg, clip_norm=0.5 if full else None, optimizer_step=full)
+                for _ in range(3):
+                    step(poseg, uvg, Kg, **tg)
+                torch.cuda.synchronize()
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+                for a, b in ev:
+                    a.record()
+                    if full:
+                        step(poseg, uvg, Kg, **tg)
+                    else:
+                        step.graph.replay()
+                    b.record()
+                torch.cuda.synchronize()
+                ts = sorted(a.elapsed_time(b) for a, b in ev)
+                del step, tm
+                torch.cuda.empty_cache()
+                return ts[len(ts) // 2]
+            A_train = 3 * (N_COARSE + N_FINE) * (F_VF + F_RN)
+            pk_t = peaks()[0]
+            ms_g = time_graphed(Rt, True)
+            train["graphed"] = {"ms_per_step": ms_g, "value": Rt / (ms_g * 1e-3), "unit": "rays/s",
+                                "includes": "CUDA-graph replay of render + loss + backward + clip + Adam, inputs copied per step"}
+            ko = {}
+            for n_r in (Rt, 8192):
+                ms_k = time_graphed(n_r, False)
+                tf = A_train * n_r / (ms_k * 1e-3) / 1e12
+                ko[str(n_r)] = {"ms_per_step": ms_k, "rays_per_s": n_r / (ms_k * 1e-3), "algorithmic_tflops": tf,
+                                "frac_of_sustained_bf16_peak": tf / pk_t.get("bf16_tflops_sustained", pk_t["bf16_tflops"])}
+            train["kernels_only"] = dict(ko, note="fwd + loss gradient + bwd into the flat gradient buffers, CUDA-graph replay, "
+                                         "median of 50; algorithmic FLOP = 3 * 203.88 MFLOP/ray (SURVEY.md 8d)")
 
     # ---- roofline of the dominant kernel, timed alone with CUDA events on the launching stream:
     #   bf16: the fused tcgen05 launch (VF + colour MLPs, RENDER program) on one chunk of merged points;
