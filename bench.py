@@ -52,6 +52,23 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(points_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused RENDER launch from the committed `ncu --set full` capture
+    (profiles/run_render_points.py, same points per launch); None if the capture does not match this launch size."""
+    path = os.path.join(ROOT, "profiles", "r01_prof_render_v4_raw.csv")
+    if points_per_launch != 65536 * (N_COARSE + N_FINE) or not os.path.exists(path):
+        return None, None
+    import csv
+    rows = list(csv.reader(open(path)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        i = hdr.index(name)
+        tot += float(vals[i]) * scale[units[i]]
+    return tot, "profiles/r01_prof_render_v4_raw.csv (ncu --set full, one launch of the same size)"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -404,8 +421,10 @@ def main():
     t_k = r0.elapsed_time(r1) * 1e-3 / reps
     ach = flop_pt * P / t_k / 1e12
     peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    traffic, traffic_src = ncu_traffic(P) if args.precision == "bf16" else (None, None)
     roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "kernel": kname, "points_per_launch": P,
+                "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch", "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": P * 36 + (P // (N_COARSE + N_FINE)) * 12, "kernel": kname, "points_per_launch": P,
                 "algorithmic_flop_per_launch": flop_pt * P, "ms_per_launch": t_k * 1e3,
                 "peak_source": pk_src + ", sustained figure (kernel timed in a loop)",
                 "whole_path_algorithmic_frac": (A_FWD * value / world) / 1e12 / peak_tf}
