@@ -27,6 +27,7 @@ struct WgTask {
   int d_slabs, x_slabs;        // slabs per tile of each tensor
   int x_slab0, n_xslabs;       // slab range of X used (N = 8 * n_xslabs <= 256)
   int g_off;                   // float offset of the destination block (row stride kGLd) + column offset
+  int colsum_off;              // float offset of the 256 column sums of dY (bias / BatchNorm terms); -1: not this task
   int cta0, nctas;             // CTAs [cta0, cta0 + nctas) work on this task, tiles split evenly
 };
 struct WgParams {
@@ -53,7 +54,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const long long per = (p.n_tiles + T.nctas - 1) / T.nctas;
   const long long t0 = (long long)local * per, t1 = min(p.n_tiles, t0 + per);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWgSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    // a ring slot is free when the MMAs that read it have completed and, for tasks that also reduce dY over the points,
+    // when the four reduction warps are done with it
+    for (int i = 0; i < kWgSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], T.colsum_off >= 0 ? 5 : 1); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -110,6 +113,54 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     }
     umma_commit(done);
   } else if (warp >= 2) {
+    if (T.colsum_off >= 0) {
+      // column sums of dY straight from the shared-memory tile the tensor core is reading: warp w owns slabs 8w..8w+7,
+      // lane l owns points l, l+32, l+64, l+96 (each LDS.128 of a warp covers 512 contiguous bytes); partial sums stay
+      // in registers across this CTA's tiles.  Rows past the end of the batch are exact zeros in the gradient stash.
+      float acc[8][8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+      int slot = 0, phase = 0;
+      const int w = warp - 2;
+      for (long long t = t0; t < t1; ++t) {
+        const int sd = slot;
+        mbar_wait(&full[slot], phase);
+        if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
+        const int sx = slot;
+        mbar_wait(&full[slot], phase);      // only so that the arrival below lands in the right phase of empty[sx]
+        if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
+        const uint8_t* dt = smem + sd * kWgSlotBytes;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int sl = 8 * w + a;
+          if (sl < T.d_slabs) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const uint4 u = *reinterpret_cast<const uint4*>(dt + sl * 2048 + (lane + 32 * rr) * 16);
+              const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                acc[a][2 * j] += __uint_as_float(x[j] << 16);
+                acc[a][2 * j + 1] += __uint_as_float(x[j] & 0xFFFF0000u);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&empty[sd]); mbar_arrive(&empty[sx]); }
+      }
+      if (t1 > t0) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float v = warp_sum(acc[a][j]);
+            if (lane == 0 && 8 * w + a < T.d_slabs) atomicAdd(p.gbuf + T.colsum_off + (8 * w + a) * 8 + j, v);
+          }
+      }
+    }
     // final epilogue: TMEM -> fp32 atomics into this layer's G block (a handful of CTAs share a block)
     mbar_wait(done, 0);
     tc_fence_after_sync();
@@ -320,10 +371,12 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
   WgParams wp{};
   wp.stash = plan.stash_buf; wp.gbuf = plan.gbuf; wp.n_tiles = tiles;
   int nt = 0;
+  // the main task of a layer (col0 == 0) also produces the column sums of its dY tensor
   auto task = [&](int d_t, int x_t, int x_slab0, int n_xslabs, int slot, int col0, int d_slabs_used) {
     WgTask& T = wp.t[nt++];
     T.d_off = S.off[d_t]; T.x_off = S.off[x_t]; T.d_slabs = S.slabs[d_t]; T.x_slabs = S.slabs[x_t];
     T.x_slab0 = x_slab0; T.n_xslabs = n_xslabs; T.g_off = slot * kGSlot + col0;
+    T.colsum_off = col0 == 0 ? slot * kGSlot + 256 * kGLd : -1;
     (void)d_slabs_used;
   };
   const int skip = plan.render.skip_step;
@@ -361,18 +414,12 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
     wgrad_tc_kernel<<<used, kWgThreads, smem, s>>>(wp);
     VFN_LAUNCH_CHECK();
   }
-  // 4. thin reductions: column sums of every dY tensor, 3-row gradients of the output layers
+  // 4. thin reductions: 3-row gradients of the two output layers (the column sums of every dY tensor come out of the
+  //    wgrad kernel, which has the tiles in shared memory anyway)
   {
     ThinParams tp{};
     tp.stash = plan.stash_buf; tp.n_tiles = tiles; tp.n_points = n;
     int k = 0;
-    auto colsum = [&](int d_t, int slot) {
-      ThinTask& T = tp.t[k++];
-      T.y_off = S.off[d_t]; T.slabs = S.slabs[d_t]; T.d3 = nullptr; T.out = plan.gbuf + (int64_t)slot * kGSlot + 256 * kGLd; T.ld = 0;
-    };
-    for (int l = 0; l <= L - 2; ++l) colsum(D0 + yS(l), slotVF(l));
-    colsum(D0 + yFeat, slotVF(L - 1));
-    for (int l = 0; l <= Lr - 2; ++l) colsum(D0 + yC(l), slotRN(l));
     {  // colour output layer: G[3 x 256] = dcol_pre^T Y_c[Lr-2]
       ThinTask& T = tp.t[k++];
       T.y_off = S.off[yC(Lr - 2)]; T.slabs = 32; T.d3 = dcol_pre; T.out = plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot; T.ld = kGLd;
@@ -382,14 +429,7 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
       T.y_off = S.off[yS(L - 2)]; T.slabs = 32; T.d3 = dv_pre; T.out = plan.gbuf + (int64_t)slotThinV * kGSlot; T.ld = kGLd;
     }
     tp.n_tasks = k;
-    // the two 3-row tasks are the last two entries: column sums and 3-row gradients get their own launches and grids
-    const int n_sum = k - 2;
-    const int gx = (int)std::min<int64_t>(tiles, 4 * g_sms / std::max(1, n_sum) + 1);
-    thin_reduce_kernel<false><<<dim3(gx, n_sum), 256, 0, s>>>(tp);
-    VFN_LAUNCH_CHECK();
-    ThinParams t3 = tp;
-    t3.t[0] = tp.t[k - 2]; t3.t[1] = tp.t[k - 1]; t3.n_tasks = 2;
-    thin_reduce_kernel<true><<<dim3((int)std::min<int64_t>(tiles, 2 * g_sms), 2), 256, 0, s>>>(t3);
+    thin_reduce_kernel<true><<<dim3((int)std::min<int64_t>(tiles, 2 * g_sms), k), 256, 0, s>>>(tp);
     VFN_LAUNCH_CHECK();
     sum3_kernel<<<64, 256, 0, s>>>(dcol_pre, n, plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot + 256 * kGLd);
     VFN_LAUNCH_CHECK();
