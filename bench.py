@@ -409,6 +409,38 @@ def main():
             train["kernels_only"] = dict(ko, note="fwd + loss gradient + bwd into the flat gradient buffers, CUDA-graph replay, "
                                          "median of 50; algorithmic FLOP = 3 * 203.88 MFLOP/ray (SURVEY.md 8d)")
 
+    # ---- VF-only grid query (BASELINE config 5 shape: a marching-cubes grid, coordinates generated in-kernel); each rank
+    # takes a z-slab of the 256^3 grid.  `value` with the result left on the device, `e2e` through the
+    # reference-shaped get_set_predictions (CPU samples in, CPU vectors out, mc_utils.py:88-104).
+    gridq = None
+    if not args.no_train:
+        from vfnerf_b200 import grid_query as gq
+        res = 256
+        n_all = res ** 3
+        lo, hi = n_all * rank // world, n_all * (rank + 1) // world
+        with torch.no_grad():
+            gq.grid_query(model.vector_field_network, res, i0=lo, n_points=hi - lo, chunk=1 << 23)
+            sync_all()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(3):
+                gq.grid_query(model.vector_field_network, res, i0=lo, n_points=hi - lo, chunk=1 << 23)
+            g1.record()
+            sync_all()
+        msg = torch.tensor([g0.elapsed_time(g1) / 3], device=dev)
+        if world > 1:
+            dist.all_reduce(msg, op=dist.ReduceOp.MAX)
+        gridq = {"value": n_all / (msg.item() * 1e-3), "unit": "points/s", "resolution": res, "ms": msg.item(),
+                 "algorithmic_tflops": F_VF * n_all / (msg.item() * 1e-3) / 1e12}
+        if world == 1:
+            samples = torch.rand(4 * 1024 * 1024, 3)
+            gq.get_set_predictions(model.vector_field_network, samples[:1 << 20], 1 << 20, torch.device(dev))
+            t0g = time.perf_counter()
+            gq.get_set_predictions(model.vector_field_network, samples, 1 << 20, torch.device(dev))
+            dtg = time.perf_counter() - t0g
+            gridq["e2e"] = {"value": samples.shape[0] / dtg, "unit": "points/s", "points": samples.shape[0],
+                            "note": "get_set_predictions: pageable CPU samples in, CPU vectors out (24 B/point over PCIe)"}
+
     # ---- roofline of the dominant kernel, timed alone with CUDA events on the launching stream:
     #   bf16: the fused tcgen05 launch (VF + colour MLPs, RENDER program) on one chunk of merged points;
     #   fp32: the CUDA-core VF MLP chain (9 GEMM launches) on one chunk.
@@ -464,6 +496,8 @@ def main():
         line["e2e"] = e2e
     if train:
         line["train_step"] = train
+    if gridq:
+        line["grid_query"] = gridq
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, med, threads = cpu_reference_rays_per_s(3, 1)
         line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
