@@ -338,3 +338,64 @@ def test_bf16_backward_stage_by_stage(built_lib, n_rays):
     chk("rn.4.weight", Pc["layers.4.weight"].grad, dcol.T @ Yc[3])
     chk("rn.4.bias", Pc["layers.4.bias"].grad, dcol.sum(0))
     print(f"worst parameter-gradient deviation: {worst[0]} {worst[1]:.2e}")
+
+
+@pytest.mark.parametrize("n_cols,P", [(None, 4096), (3, 4096), (None, 128 * 300 + 77)])
+def test_bf16_vf_query_backward(built_lib, n_cols, P):
+    """The VF-only module call with gradients (supervision points of the trainer, train/vector_field_nerf_train.py:
+    191-216) on the tensor cores: forward with activation stash, VF-only dgrad chain, the shared wgrad / finalize
+    kernels.  Compared with the fp32 path on the tame model (same bound and reasoning as the render() gradients)."""
+    from vfnerf_b200 import ops
+    case, z = U.load_golden("full_det")
+    st = U.S.synthetic_state(0, vf_gain=1.0, center_output=False)
+    g = torch.Generator().manual_seed(11)
+    pts = ((torch.rand(P, 3, generator=g) - 0.5) * 6).to(DEV)
+    cols = 259 if n_cols is None else n_cols
+    c = (torch.randn(P, cols, generator=g) * 0.01).to(DEV)
+    grads = {}
+    for prec in ("fp32", "bf16"):
+        model = U.make_model(case, st, DEV, precision=prec)
+        out = ops.vf_query(model.vector_field_network, pts, n_cols=n_cols)
+        model.optimizer.zero_grad()
+        (out * c).sum().backward()
+        grads[prec] = {k: p.grad.detach().cpu().clone() for k, p in model.vector_field_network.named_parameters()}
+    worst = ("", 0.0)
+    for k, a in grads["fp32"].items():
+        b = grads["bf16"][k]
+        assert torch.isfinite(b).all(), k
+        rel = ((a - b).norm() / (a.norm() + 1e-20)).item()
+        if rel > worst[1]:
+            worst = (k, rel)
+    print(f"n_cols={n_cols} P={P}: worst tensor {worst[0]} rel L2 {worst[1]:.2e}")
+    assert worst[1] <= REL_L2, worst
+
+
+def test_bf16_render_plus_supervision_accumulates(built_lib):
+    """The trainer's step with supervision points: render() gradients and VF-only gradients of extra points add up in
+    .grad through autograd, exactly like two separate backward() calls."""
+    from vfnerf_b200 import ops
+    case, z = U.load_golden("full_det")
+    st = U.S.synthetic_state(0, vf_gain=1.0, center_output=False)
+    g16, out = _grads(case, z, st, "bf16")
+    model = U.make_model(case, st, DEV, precision="bf16")
+    draws = (U.t(z, "U1"), U.t(z, "U2"), U.t(z, "U3"))
+    zr = U.t(z, "ref_z_vals")
+    o = model.render(U.t(z, "pose").to(DEV), U.t(z, "uv").to(DEV), U.t(z, "K").to(DEV), 0, draws=draws, z_vals_override=zr)
+    R, N = zr.shape
+    c_rgb, c_dep, c_nrm, c_col = (c.to(DEV) for c in _upstream(R, N))
+    gsup = torch.Generator().manual_seed(5)
+    pts = ((torch.rand(3000, 3, generator=gsup) - 0.5) * 6).to(DEV)
+    tgt = torch.nn.functional.normalize(torch.randn(3000, 3, generator=gsup), dim=1).to(DEV)
+    v = model.vector_field_network(pts)[:, :3]
+    loss = (o.coarse_rgb_values * c_rgb).sum() + (o.coarse_depth_map * c_dep).sum() + (o.coarse_normals * c_nrm).sum() + \
+        (o.coarse_colors * c_col).sum() + ((v - tgt) ** 2).mean()
+    model.optimizer.zero_grad()
+    loss.backward()
+    # the supervision term alone
+    m2 = U.make_model(case, st, DEV, precision="bf16")
+    v2 = m2.vector_field_network(pts)[:, :3]
+    m2.optimizer.zero_grad()
+    ((v2 - tgt) ** 2).mean().backward()
+    for (k, p), (_, p2) in zip(model.vector_field_network.named_parameters(), m2.vector_field_network.named_parameters()):
+        want = g16["vf." + k] + p2.grad.cpu()
+        assert ((p.grad.cpu() - want).norm() <= 1e-4 * want.norm() + 1e-9), k

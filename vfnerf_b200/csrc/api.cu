@@ -428,9 +428,10 @@ static void make_vf_plan(const vfnerf_mlp_desc& vf, int64_t n, int multires, int
   p.bytes = c.off;
 }
 
-static int vf_tc_plan(const vfnerf_mlp_desc& vf, int multires, int skip_layer, void* ws, TcPlan& plan, int64_t& bytes) {
+static int vf_tc_plan(const vfnerf_mlp_desc& vf, int multires, int skip_layer, void* ws, TcPlan& plan, int64_t& bytes,
+                      int64_t n_points = 0, int keep = 0) {
   int64_t off = 0;
-  if (int e = tc_carve(reinterpret_cast<char*>(ws), off, multires, 0, skip_layer, vf, nullptr, plan)) return e;
+  if (int e = tc_carve(reinterpret_cast<char*>(ws), off, multires, 0, skip_layer, vf, nullptr, plan, n_points, keep)) return e;
   bytes = off;
   return 0;
 }
@@ -439,12 +440,12 @@ int64_t vfnerf_vf_workspace_bytes(const vfnerf_mlp_desc* vf, int64_t n_points, i
                                   int keep_for_backward, int precision) {
   if (!vf) { set_error("null argument"); return -1; }
   if (precision != VFNERF_PREC_FP32) {
-    if (precision != VFNERF_PREC_BF16 || keep_for_backward) { set_error("vf query: only fp32 (with backward) and bf16 (forward) are built"); return -1; }
+    if (precision != VFNERF_PREC_BF16) { set_error("vf query: only fp32 and bf16 are built"); return -1; }
     TcPlan plan;
     int64_t bytes = 0;
     int skip = -1;
     for (int l = 1; l < vf->n_layers; ++l) if (vf->in_dim[l] != vf->out_dim[l - 1]) skip = l;
-    if (vf_tc_plan(*vf, multires, skip, nullptr, plan, bytes)) return -1;
+    if (vf_tc_plan(*vf, multires, skip, nullptr, plan, bytes, n_points, keep_for_backward)) return -1;
     return bytes + 1024;
   }
   VfPlan p;
@@ -462,16 +463,18 @@ int vfnerf_vf_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
   if (n_points == 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (precision != VFNERF_PREC_FP32) {
-    VFN_REQUIRE(precision == VFNERF_PREC_BF16 && !keep_for_backward, "vf_fwd: only fp32 (with backward) and bf16 (forward) are built");
+    VFN_REQUIRE(precision == VFNERF_PREC_BF16, "vf_fwd: only fp32 and bf16 are built");
     VFN_REQUIRE(n_out_cols == 3 || n_out_cols == vf->out_dim[vf->n_layers - 1], "vf_fwd(bf16): n_out_cols must be 3 or all");
     TcPlan plan;
     int64_t bytes = 0;
-    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes)) return e;
+    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes, n_points, keep_for_backward)) return e;
     VFN_REQUIRE(workspace && workspace_bytes >= bytes, "vf_fwd: workspace too small");
     if (int e = tc_prepare(*vf, vf_arena, nullptr, nullptr, bn_eps, plan, s)) return e;
     const bool full = n_out_cols > 3;
-    return tc_forward(plan, full ? TC_MODE_VF_FULL : TC_MODE_V_ONLY, points, nullptr, 0, 0, n_points, nullptr, 0, out,
-                      out_ld, full ? out + 3 : nullptr, out_ld, nullptr, s);
+    const int mode = keep_for_backward ? (full ? TC_MODE_VF_FULL_STASH : TC_MODE_V_ONLY_STASH)
+                                       : (full ? TC_MODE_VF_FULL : TC_MODE_V_ONLY);
+    return tc_forward(plan, mode, points, nullptr, 0, 0, n_points, nullptr, 0, out, out_ld, full ? out + 3 : nullptr, out_ld,
+                      nullptr, s);
   }
   VfPlan p;
   make_vf_plan(*vf, n_points, multires, keep_for_backward, 1, workspace, p);
@@ -515,8 +518,20 @@ int vfnerf_vf_bwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
                   int64_t d_ld, int n_out_cols, float* vf_grad_arena, int accumulate, void* workspace,
                   int64_t workspace_bytes, void* stream) {
   VFN_REQUIRE(vf && vf_arena && out && d_out && vf_grad_arena, "vf_bwd: null argument");
-  VFN_REQUIRE(precision == VFNERF_PREC_FP32, "vf_bwd: only the fp32 path has a backward in this build");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (precision != VFNERF_PREC_FP32) {
+    // tensor-core path: the forward (keep_for_backward) left the activation stash and the transposed weight images
+    VFN_REQUIRE(precision == VFNERF_PREC_BF16, "vf_bwd: only fp32 and bf16 are built");
+    VFN_REQUIRE(n_out_cols == 3 || n_out_cols == vf->out_dim[vf->n_layers - 1], "vf_bwd(bf16): n_out_cols must be 3 or all");
+    if (!accumulate) VFN_CHECK_CUDA(cudaMemsetAsync(vf_grad_arena, 0, sizeof(float) * vf->arena_floats, s));
+    if (n_points == 0) return 0;
+    TcPlan plan;
+    int64_t bytes = 0;
+    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes, n_points, 1)) return e;
+    VFN_REQUIRE(workspace && workspace_bytes >= bytes, "vf_bwd: workspace too small");
+    return tc_backward_vf(plan, *vf, vf_arena, bn_eps, n_points, out, out_ld, d_out, d_ld, n_out_cols, vf_grad_arena,
+                          accumulate, s);
+  }
   const int Do = vf->out_dim[vf->n_layers - 1];
   VFN_REQUIRE(n_out_cols >= 1 && n_out_cols <= Do, "vf_bwd: n_out_cols invalid");
   VfPlan p;

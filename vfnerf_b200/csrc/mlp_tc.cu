@@ -493,7 +493,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           }
           umma2_commit(&acc_full[gstep & 1]);      // accumulators complete -> epilogue warps of both CTAs
           // side regions whose only reader was this step may now be rewritten for the next tile (prologue warps)
-          if (si == 0) umma2_commit(&reg_free[0]);
+          // [0]: layer-0 operand region (forward) / the whole main region once the VF-only dgrad tile is finished
+          if (si == (prog.bwd == 2 ? prog.n_steps - 1 : 0)) umma2_commit(&reg_free[0]);
           if (si == prog.skip_step) umma2_commit(&reg_free[1]);
           if (si == prog.aux_step) umma2_commit(&reg_free[2]);
           if (tl) p.dbg_buf[64 + si * 8 + 1] = clock64();
@@ -519,8 +520,12 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     if (kBwd) {
       // backward: the two 3-wide gradient inputs enter as bf16 (hi, lo) pairs in 16-column units:
       //   d(colour pre-sigmoid) -> aux columns 0..15 (A operand of the first step), d(vector pre-tanh) -> skip columns 0..15
+      //   VF-only dgrad (prog.bwd == 2): no colour unit; the main region starts as d(feature pre-tanh), which
+      //   tc_backward_vf left in the gradient stash as a bf16 tile image -- copied here, one row per thread
+      const bool with_rn = prog.aux_step >= 0;
       for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++n) {
-        const long long pi = tile_of(pair) * kTileM + row;
+        const long long tile = tile_of(pair);
+        const long long pi = tile * kTileM + row;
         const bool valid = pi < p.n_points;
         float u[16], w[16];
 #pragma unroll
@@ -528,16 +533,29 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            const float a = p.dcol_pre[3 * pi + j], b = p.dv_pre[3 * pi + j];
+            const float a = with_rn ? p.dcol_pre[3 * pi + j] : 0.f, b = p.dv_pre[3 * pi + j];
             u[j] = __bfloat162float(__float2bfloat16(a)); u[3 + j] = a - u[j];
             w[j] = __bfloat162float(__float2bfloat16(b)); w[3 + j] = b - w[j];
           }
         }
-        if (n > 0) mbar_wait(&reg_free[2], (n - 1) & 1);
-        store_slab_f(s_act, kColAux / 8, row, u);
-        store_slab_f(s_act, kColAux / 8 + 1, row, u + 8);
-        fence_proxy_async_smem();
-        arrive_pro(kBarAuxStatic);
+        if (with_rn) {
+          if (n > 0) mbar_wait(&reg_free[2], (n - 1) & 1);
+          store_slab_f(s_act, kColAux / 8, row, u);
+          store_slab_f(s_act, kColAux / 8 + 1, row, u + 8);
+          fence_proxy_async_smem();
+          arrive_pro(kBarAuxStatic);
+        } else {
+          if (n > 0) mbar_wait(&reg_free[0], (n - 1) & 1);
+          const int t_feat = p.sinfo.idx_d0 + p.prog.s[0].mask_src + 1;      // gradient twin of the feature tensor
+          const bool t_ok = tile < num_tiles;
+#pragma unroll 4
+          for (int sl = 0; sl < 32; ++sl) {
+            const uint4 v = t_ok ? __ldg(stash_unit(p, t_feat, tile, sl, row)) : make_uint4(0u, 0u, 0u, 0u);
+            store_slab_u(s_act, sl, row, v.x, v.y, v.z, v.w);
+          }
+          fence_proxy_async_smem();
+          arrive_pro(0); arrive_pro(1); arrive_pro(2); arrive_pro(3);
+        }
         if (n > 0) mbar_wait(&reg_free[1], (n - 1) & 1);
         store_slab_f(s_act, kColSkip / 8, row, w);
         store_slab_f(s_act, kColSkip / 8 + 1, row, w + 8);
@@ -815,6 +833,13 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               float f[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = tanh_fast(__uint_as_float(v[j]));
+              if (st_on) {       // module call kept for a backward: the features are the tanh gate of the dgrad chain
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl)
+                  *stash_unit(p, st.stash_out, tile, (c0 >> 3) + sl, row) =
+                      make_uint4(pack_bf16x2(f[8 * sl], f[8 * sl + 1]), pack_bf16x2(f[8 * sl + 2], f[8 * sl + 3]),
+                                 pack_bf16x2(f[8 * sl + 4], f[8 * sl + 5]), pack_bf16x2(f[8 * sl + 6], f[8 * sl + 7]));
+              }
               if (p.out_feat && valid) {
                 float* o = p.out_feat + pi * p.feat_ld + c0;
                 if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
@@ -966,10 +991,9 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.render = 0; plan.vf_full.aux_step = -1;
   plan.vf_full.s[n_full - 1].pre_wait_mask = 1 << kBarAux;
   plan.v_only = pr; plan.v_only.n_steps = n_v; plan.v_only.render = 0; plan.v_only.aux_step = -1;
-  if (!rn) return 0;
 
   // ---------------- training: stash tensor numbering ----------------
-  const int Lr = rn->n_layers;
+  const int Lr = rn ? rn->n_layers : 1;     // VF-only plans have no colour tensors
   TcStash& S = plan.stash;
   S.n_y = L + Lr - 1;                       // Y_s[0..L-2], Y_FEAT, Y_c[0..Lr-2]
   S.idx_emb0 = S.n_y; S.idx_skip = S.n_y + 1; S.idx_aux = S.n_y + 2; S.idx_d0 = S.n_y + 3;
@@ -980,17 +1004,40 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   auto yS = [&](int l) { return l; };                  // VF hidden layer l
   const int yFeat = L - 1;
   auto yC = [&](int l) { return L + l; };              // colour hidden layer l
-  for (int l = 0; l < L - 1; ++l) plan.render.s[l].stash_out = yS(l);
-  plan.render.s[n_v].stash_out = yFeat;
+  for (int l = 0; l < L - 1; ++l) plan.render.s[l].stash_out = plan.vf_full.s[l].stash_out = plan.v_only.s[l].stash_out = yS(l);
+  plan.render.s[n_v].stash_out = plan.vf_full.s[n_v].stash_out = yFeat;
   for (int l = 0; l < Lr - 1; ++l) plan.render.s[n_full + l].stash_out = yC(l);
+  const int D0 = S.idx_d0;
+  TcProgram fwd = pr;                          // keep the forward description for post_scale look-ups
+
+  // ---------------- training: the dgrad program of the VF net alone (module call with gradients) ----------------
+  {
+    pr = TcProgram{};
+    pr.emb_w = E; pr.emb_pad = Epad; pr.multires = multires; pr.multires_view = multires_view;
+    pr.small_w = fwd.small_w; pr.bwd = 2; pr.aux_step = -1;
+    ns = 0; woff = 0;
+    // VF output layer: A = [d(feature pre-tanh) (main, copied from the stash by the prologue) | d(vector pre-tanh) unit]
+    const int c[2] = {0, kColSkip}, k[2] = {256, 16};
+    pr.skip_step = ns;
+    add(256, 256, 2, c, k, 128, TC_EPI_BWD_RELU, 0xF | (1 << kBarSkip), 0, L - 1, 3, 12, 0, 1.f, 1);
+    pr.s[ns - 1].mask_src = yS(L - 2); pr.s[ns - 1].stash_out = D0 + yS(L - 2);
+    for (int l = L - 2; l >= 1; --l) {
+      const int kk[1] = {round16(vf.out_dim[l])};
+      const int Nn = round16(vf.out_dim[l - 1]);
+      add(Nn, vf.out_dim[l - 1], 1, main0, kk, 128, TC_EPI_BWD_RELU, 0xF, 0, l, 0, 10, 0, fwd.s[l].post_scale, 1);
+      pr.s[ns - 1].mask_src = yS(l - 1); pr.s[ns - 1].stash_out = D0 + yS(l - 1);
+    }
+    pr.n_steps = ns;
+    plan.bwd_vf = pr;
+    plan.wpack_bwd_vf_bytes = woff;
+  }
+  if (!rn) return 0;
 
   // ---------------- training: the dgrad program (weights transposed, no bias, gate with the stash) ----------------
-  TcProgram fwd = pr;                          // keep the forward description for post_scale look-ups
   pr = TcProgram{};
   pr.emb_w = E; pr.emb_pad = Epad; pr.multires = multires; pr.multires_view = multires_view;
   pr.small_w = fwd.small_w; pr.bwd = 1;
   ns = 0; woff = 0;
-  const int D0 = S.idx_d0;
   {
     // colour output layer: A = d(colour pre-sigmoid) as a bf16 (hi, lo) unit in the aux columns
     const int c[1] = {kColAux}, k[1] = {16};
@@ -1030,7 +1077,8 @@ int tc_carve(char* base, int64_t& off, int multires, int multires_view, int skip
   off = align_up(off, 1024);
   plan.wpack = base ? reinterpret_cast<uint8_t*>(base + off) : nullptr;
   off += align_up(plan.wpack_bytes, 1024);
-  if (keep && rn) {
+  if (keep) {
+    if (!rn) plan.wpack_bwd_bytes = plan.wpack_bwd_vf_bytes;
     plan.wpack_bwd = base ? reinterpret_cast<uint8_t*>(base + off) : nullptr;
     off += align_up(plan.wpack_bwd_bytes, 1024);
     const int64_t tiles = (n_points + kTileM - 1) / kTileM, tiles2 = (tiles + 1) / 2 * 2;
@@ -1057,7 +1105,8 @@ int tc_prepare(const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_ml
   tc_pack_kernel<<<dim3(32, pr.n_steps), 256, 0, s>>>(pr, vf, vf_arena, rn ? *rn : none, rn_arena, bn_eps, plan.wpack);
   VFN_LAUNCH_CHECK();
   if (plan.wpack_bwd) {
-    tc_pack_kernel<<<dim3(32, plan.bwd.n_steps), 256, 0, s>>>(plan.bwd, vf, vf_arena, *rn, rn_arena, bn_eps, plan.wpack_bwd);
+    const TcProgram& pb = rn ? plan.bwd : plan.bwd_vf;
+    tc_pack_kernel<<<dim3(32, pb.n_steps), 256, 0, s>>>(pb, vf, vf_arena, rn ? *rn : none, rn_arena, bn_eps, plan.wpack_bwd);
     VFN_LAUNCH_CHECK();
   }
   return 0;
@@ -1070,14 +1119,17 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
                int64_t v_ld, float* out_feat, int64_t feat_ld, float* colors, cudaStream_t s) {
   if (n <= 0) return 0;
   TcParams p{};
+  const bool is_bwd = mode == TC_MODE_BWD || mode == TC_MODE_VF_BWD;
+  const bool stashing = mode == TC_MODE_RENDER_STASH || mode == TC_MODE_V_ONLY_STASH || mode == TC_MODE_VF_FULL_STASH;
   p.prog = (mode == TC_MODE_RENDER || mode == TC_MODE_RENDER_STASH) ? plan.render
-           : (mode == TC_MODE_VF_FULL ? plan.vf_full : (mode == TC_MODE_BWD ? plan.bwd : plan.v_only));
-  p.wpack = mode == TC_MODE_BWD ? plan.wpack_bwd : plan.wpack;
-  if (mode == TC_MODE_RENDER_STASH || mode == TC_MODE_BWD) {
+           : (mode == TC_MODE_VF_FULL || mode == TC_MODE_VF_FULL_STASH) ? plan.vf_full
+           : mode == TC_MODE_BWD ? plan.bwd : mode == TC_MODE_VF_BWD ? plan.bwd_vf : plan.v_only;
+  p.wpack = is_bwd ? plan.wpack_bwd : plan.wpack;
+  if (stashing || is_bwd) {
     VFN_REQUIRE(plan.stash_buf, "tc_forward: this mode needs the training workspace (keep_for_backward)");
     p.stash = plan.stash_buf; p.sinfo = plan.stash;
   }
-  if (mode == TC_MODE_BWD) { p.dcol_pre = points; p.dv_pre = ray_dirs; }
+  if (is_bwd) { p.dcol_pre = points; p.dv_pre = ray_dirs; }
   p.points = points; p.use_grid = grid ? 1 : 0;
   if (grid) p.grid = *grid;
   p.grid_res = grid_res; p.grid_i0 = grid_i0; p.n_points = n;
@@ -1090,7 +1142,7 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   p.dbg_buf = (dbg & 64) ? dbg_buf : nullptr;
   p.dbg = dbg & 63;
   if (p.dbg_buf) VFN_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), s));
-  VFN_REQUIRE(out_v || mode == TC_MODE_BWD, "tc_forward: out_v is null");
+  VFN_REQUIRE(out_v || is_bwd, "tc_forward: out_v is null");
   VFN_REQUIRE((mode != TC_MODE_RENDER && mode != TC_MODE_RENDER_STASH) || (colors && ray_dirs),
               "tc_forward: RENDER mode needs colors and ray_dirs");
   if (g_num_sms == 0) {
@@ -1109,8 +1161,8 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
     VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  if (mode == TC_MODE_BWD) mlp_tc_kernel<true, true><<<grid_x, kTcThreads, smem, s>>>(p);
-  else if (mode == TC_MODE_RENDER_STASH) mlp_tc_kernel<false, true><<<grid_x, kTcThreads, smem, s>>>(p);
+  if (is_bwd) mlp_tc_kernel<true, true><<<grid_x, kTcThreads, smem, s>>>(p);
+  else if (stashing) mlp_tc_kernel<false, true><<<grid_x, kTcThreads, smem, s>>>(p);
   else mlp_tc_kernel<false, false><<<grid_x, kTcThreads, smem, s>>>(p);
   VFN_LAUNCH_CHECK();
   if (p.dbg_buf) {

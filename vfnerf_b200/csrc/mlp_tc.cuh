@@ -47,7 +47,9 @@ struct TcStep {
 enum TcEpi { TC_EPI_RELU = 0, TC_EPI_V = 2, TC_EPI_FEAT = 3, TC_EPI_RGB = 4,
              TC_EPI_BWD_RELU = 5,    // dX * (Y > 0)            (Y = stashed forward activation)
              TC_EPI_BWD_TANH = 6 };  // dX * (1 - Y^2)          (Y = stashed tanh features)
-enum TcMode { TC_MODE_V_ONLY = 0, TC_MODE_VF_FULL = 1, TC_MODE_RENDER = 2, TC_MODE_RENDER_STASH = 3, TC_MODE_BWD = 4 };
+enum TcMode { TC_MODE_V_ONLY = 0, TC_MODE_VF_FULL = 1, TC_MODE_RENDER = 2, TC_MODE_RENDER_STASH = 3, TC_MODE_BWD = 4,
+              TC_MODE_V_ONLY_STASH = 5, TC_MODE_VF_FULL_STASH = 6,   // VF-only module call kept for a backward
+              TC_MODE_VF_BWD = 7 };                                   // dgrad chain of the VF net alone
 
 // Activation stash (training): every tensor is bf16 in "tile-major K-slab" order, i.e. the exact shared-memory
 // image of a 128-point tile, tile after tile:  [tile][slab = 8 channels][row = point in tile][8 channels].
@@ -74,7 +76,7 @@ struct TcProgram {
   int small_w;      // 3 + (3 + 6*multires_view) + 3
   int skip_step;    // index of the step that consumes the skip columns (-1: none)
   int aux_step;     // index of the step that consumes the aux columns (-1: none)
-  int bwd;          // 1: backward (dgrad) program -- different prologue, no bias segments
+  int bwd;          // 1: backward (dgrad) program of render() -- different prologue, no bias segments; 2: of the VF net alone
   TcStep s[kTcMaxSteps];
 };
 
@@ -83,11 +85,11 @@ struct TcPlan {
   int64_t wpack_bytes = 0;
   TcProgram render{}, vf_full{}, v_only{};
   // training (keep_for_backward): stash layout, the dgrad program with its transposed weight images, scratch
-  TcProgram bwd{};
+  TcProgram bwd{}, bwd_vf{};
   TcStash stash{};
   uint8_t* stash_buf = nullptr;
   uint8_t* wpack_bwd = nullptr;
-  int64_t wpack_bwd_bytes = 0;
+  int64_t wpack_bwd_bytes = 0, wpack_bwd_vf_bytes = 0;
   float* gbuf = nullptr;       // fp32 weight-gradient scratch: one [256 x 320] block per layer + column sums
   int64_t gbuf_floats = 0;
   float* d3 = nullptr;         // [P,3] x 2: d(colour pre-sigmoid), d(vector pre-tanh)
@@ -112,6 +114,12 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
 int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_mlp_desc& rn,
                 const float* rn_arena, float bn_eps, int64_t n, const float* colors, const float* normals,
                 const float* d_colors, const float* d_v, float* vf_grad, float* rn_grad, cudaStream_t s);
+
+// Training backward of the VF-only module call (VF_FULL / V_ONLY program kept with *_STASH): out [n, out_ld] are the
+// forward outputs (vector | features), d_out [n, d_ld] their gradients (first n_out_cols columns, 3 or all).
+int tc_backward_vf(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_arena, float bn_eps, int64_t n,
+                   const float* out, int64_t out_ld, const float* d_out, int64_t d_ld, int n_out_cols, float* vf_grad,
+                   int accumulate, cudaStream_t s);
 
 // test support: convert one stash tensor (or, tensor == 1000, the two [n,3] output-layer gradients) to row-major fp32
 int tc_debug_stash_read(const TcPlan& plan, int tensor, int64_t n, float* out, int* n_cols, cudaStream_t s);

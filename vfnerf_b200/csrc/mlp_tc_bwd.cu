@@ -279,6 +279,7 @@ struct FinParams {
   float* vf_grad; float* rn_grad;
   const float* gbuf;
   float eps;
+  int accumulate;      // 1: add to the gradient arenas (supervision points after render()), 0: overwrite
   int n_layers;
   FinLayer L[VFNERF_MAX_LAYERS * 2];
 };
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(128) tc_finalize_kernel(const __grid_constant_
       else g = G[j - F.split];
     }
     dot += Wn[j] * g;
-    dWn[j] = sc * F.post * g;
+    dWn[j] = (p.accumulate ? dWn[j] : 0.f) + sc * F.post * g;
   }
   __shared__ float red[4];
   dot = warp_sum(dot);
@@ -326,11 +327,12 @@ __global__ void __launch_bounds__(128) tc_finalize_kernel(const __grid_constant_
   __syncthreads();
   if (threadIdx.x == 0) {
     const float tot = red[0] + red[1] + red[2] + red[3];
-    grad[d.b_off[l] + n] = sc * F.post * s;
+    auto put = [&](float* dst, float v) { *dst = (p.accumulate ? *dst : 0.f) + v; };
+    put(grad + d.b_off[l] + n, sc * F.post * s);
     if (bn) {
       const float b = arena[d.b_off[l] + n];
-      grad[d.gamma_off[l] + n] = istd * F.post * (tot + (b - arena[d.mean_off[l] + n]) * s);
-      grad[d.beta_off[l] + n] = F.post * s;
+      put(grad + d.gamma_off[l] + n, istd * F.post * (tot + (b - arena[d.mean_off[l] + n]) * s));
+      put(grad + d.beta_off[l] + n, F.post * s);
     }
   }
 }
@@ -340,21 +342,21 @@ __global__ void __launch_bounds__(128) tc_finalize_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 static int g_sms = 0;
 
-int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_mlp_desc& rn,
-                const float* rn_arena, float bn_eps, int64_t n, const float* colors, const float* normals,
-                const float* d_colors, const float* d_v, float* vf_grad, float* rn_grad, cudaStream_t s) {
-  VFN_REQUIRE(plan.stash_buf && plan.wpack_bwd && plan.gbuf && plan.d3, "tc_backward: training workspace missing");
+// steps 2-5 of the backward.  rn == nullptr: the VF net alone (dcol_pre unused; d(feature pre-tanh) is already in the
+// gradient stash).  dcol_pre / dv_pre: [n,3] gradients wrt the pre-activations of the two 3-wide outputs.
+static int backward_common(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_mlp_desc* rnp,
+                           const float* rn_arena, float bn_eps, int64_t n, const float* dcol_pre, const float* dv_pre,
+                           float* vf_grad, float* rn_grad, int accumulate, cudaStream_t s) {
   const TcStash& S = plan.stash;
-  const int L = vf.n_layers, Lr = rn.n_layers;
+  const bool with_rn = rnp != nullptr;
+  vfnerf_mlp_desc none{};
+  const vfnerf_mlp_desc& rn = with_rn ? *rnp : none;
+  const int L = vf.n_layers, Lr = with_rn ? rn.n_layers : 1;
   const int64_t tiles = (n + kTileM - 1) / kTileM;
-  float* dcol_pre = plan.d3;
-  float* dv_pre = plan.d3 + 3 * n;
-  // 1. gradients wrt the pre-activations of the two output layers
-  if (int e = launch_act_bwd(colors, 3, d_colors, 3, n, 3, ACT_SIGMOID, dcol_pre, 3, s)) return e;
-  if (int e = launch_act_bwd(normals, 3, d_v, 3, n, 3, ACT_TANH, dv_pre, 3, s)) return e;
   VFN_CHECK_CUDA(cudaMemsetAsync(plan.gbuf, 0, plan.gbuf_floats * sizeof(float), s));
   // 2. fused dgrad chain (also stashes dL/d(pre-activation) of every layer)
-  if (int e = tc_forward(plan, TC_MODE_BWD, dcol_pre, nullptr, 0, 0, n, dv_pre, 1, nullptr, 0, nullptr, 0, nullptr, s)) return e;
+  if (int e = tc_forward(plan, with_rn ? TC_MODE_BWD : TC_MODE_VF_BWD, dcol_pre, nullptr, 0, 0, n, dv_pre, 1, nullptr, 0,
+                         nullptr, 0, nullptr, s)) return e;
 
   // stash tensor numbering (mlp_tc.cu build_programs)
   auto yS = [&](int l) { return l; };
@@ -386,9 +388,11 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
     if (l == skip) task(D0 + yS(l), S.idx_skip, 0, 6, slotVF(l), 256, 32);
   }
   task(D0 + yFeat, yS(L - 2), 0, 32, slotVF(L - 1), 0, 32);
-  task(D0 + yC(0), yFeat, 0, 32, slotRN(0), 0, 32);
-  task(D0 + yC(0), S.idx_aux, 0, 6, slotRN(0), 256, 32);
-  for (int l = 1; l <= Lr - 2; ++l) task(D0 + yC(l), yC(l - 1), 0, 32, slotRN(l), 0, 32);
+  if (with_rn) {
+    task(D0 + yC(0), yFeat, 0, 32, slotRN(0), 0, 32);
+    task(D0 + yC(0), S.idx_aux, 0, 6, slotRN(0), 256, 32);
+    for (int l = 1; l <= Lr - 2; ++l) task(D0 + yC(l), yC(l - 1), 0, 32, slotRN(l), 0, 32);
+  }
   wp.n_tasks = nt;
   if (g_sms == 0) {
     int dev = 0;
@@ -420,7 +424,7 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
     ThinParams tp{};
     tp.stash = plan.stash_buf; tp.n_tiles = tiles; tp.n_points = n;
     int k = 0;
-    {  // colour output layer: G[3 x 256] = dcol_pre^T Y_c[Lr-2]
+    if (with_rn) {  // colour output layer: G[3 x 256] = dcol_pre^T Y_c[Lr-2]
       ThinTask& T = tp.t[k++];
       T.y_off = S.off[yC(Lr - 2)]; T.slabs = 32; T.d3 = dcol_pre; T.out = plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot; T.ld = kGLd;
     }
@@ -431,8 +435,10 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
     tp.n_tasks = k;
     thin_reduce_kernel<true><<<dim3((int)std::min<int64_t>(tiles, 2 * g_sms), k), 256, 0, s>>>(tp);
     VFN_LAUNCH_CHECK();
-    sum3_kernel<<<64, 256, 0, s>>>(dcol_pre, n, plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot + 256 * kGLd);
-    VFN_LAUNCH_CHECK();
+    if (with_rn) {
+      sum3_kernel<<<64, 256, 0, s>>>(dcol_pre, n, plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot + 256 * kGLd);
+      VFN_LAUNCH_CHECK();
+    }
     sum3_kernel<<<64, 256, 0, s>>>(dv_pre, n, plan.gbuf + (int64_t)slotThinV * kGSlot + 256 * kGLd);
     VFN_LAUNCH_CHECK();
   }
@@ -440,7 +446,7 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
   {
     FinParams fp{};
     fp.vf = vf; fp.rn = rn; fp.vf_arena = vf_arena; fp.rn_arena = rn_arena; fp.vf_grad = vf_grad; fp.rn_grad = rn_grad;
-    fp.gbuf = plan.gbuf; fp.eps = bn_eps;
+    fp.gbuf = plan.gbuf; fp.eps = bn_eps; fp.accumulate = accumulate;
     int k = 0, maxrows = 0;
     const int Epad = plan.render.emb_pad, ev = 3 + 6 * plan.render.multires_view;
     for (int l = 0; l < L; ++l) {
@@ -451,7 +457,7 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
       F.post = l < L - 1 ? plan.render.s[l].post_scale : 1.f;
       maxrows = std::max(maxrows, vf.out_dim[l]);
     }
-    for (int l = 0; l < Lr; ++l) {
+    for (int l = 0; with_rn && l < Lr; ++l) {
       FinLayer& F = fp.L[k++];
       F.net = 1; F.layer = l; F.kind = l == 0 ? FK_C0 : FK_IDENT; F.split = plan.render.small_w; F.epad = Epad; F.ev = ev;
       F.g_slot = slotRN(l); F.row0 = 0; F.thin_slot = -1; F.post = 1.f;
@@ -462,6 +468,69 @@ int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_a
     VFN_LAUNCH_CHECK();
   }
   return 0;
+}
+
+int tc_backward(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_mlp_desc& rn,
+                const float* rn_arena, float bn_eps, int64_t n, const float* colors, const float* normals,
+                const float* d_colors, const float* d_v, float* vf_grad, float* rn_grad, cudaStream_t s) {
+  VFN_REQUIRE(plan.stash_buf && plan.wpack_bwd && plan.gbuf && plan.d3, "tc_backward: training workspace missing");
+  float* dcol_pre = plan.d3;
+  float* dv_pre = plan.d3 + 3 * n;
+  // 1. gradients wrt the pre-activations of the two output layers
+  if (int e = launch_act_bwd(colors, 3, d_colors, 3, n, 3, ACT_SIGMOID, dcol_pre, 3, s)) return e;
+  if (int e = launch_act_bwd(normals, 3, d_v, 3, n, 3, ACT_TANH, dv_pre, 3, s)) return e;
+  return backward_common(plan, vf, vf_arena, &rn, rn_arena, bn_eps, n, dcol_pre, dv_pre, vf_grad, rn_grad, 0, s);
+}
+
+// d(vector pre-tanh) -> dv_pre [n,3] fp32; d(feature pre-tanh) -> the gradient twin of the feature tensor in the stash
+// (bf16 tile image, the first A operand of the VF-only dgrad chain).  One thread per (point, 8-channel slab).
+__global__ void vf_dout_prepare_kernel(const float* __restrict__ out, long long out_ld, const float* __restrict__ d_out,
+                                       long long d_ld, int n_cols, long long n, long long n_padded, float* __restrict__ dv_pre,
+                                       uint8_t* __restrict__ dfeat_tiles) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_padded * 32) return;
+  const long long pnt = i >> 5;
+  const int sl = (int)(i & 31);
+  float g[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  if (pnt < n) {
+    if (n_cols > 3) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = 3 + sl * 8 + j;
+        if (c < n_cols) {
+          const float y = out[pnt * out_ld + c];
+          g[j] = d_out[pnt * d_ld + c] * (1.f - y * y);
+        }
+      }
+    }
+    if (sl == 0) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float y = out[pnt * out_ld + j];
+        dv_pre[3 * pnt + j] = d_out[pnt * d_ld + j] * (1.f - y * y);
+      }
+    }
+  }
+  const long long tile = pnt / kTileM;
+  const int row = (int)(pnt % kTileM);
+  *reinterpret_cast<uint4*>(dfeat_tiles + tile * (32LL * 2048) + (long long)sl * 2048 + row * 16) =
+      make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+}
+
+int tc_backward_vf(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* vf_arena, float bn_eps, int64_t n,
+                   const float* out, int64_t out_ld, const float* d_out, int64_t d_ld, int n_out_cols, float* vf_grad,
+                   int accumulate, cudaStream_t s) {
+  VFN_REQUIRE(plan.stash_buf && plan.wpack_bwd && plan.gbuf && plan.d3, "tc_backward_vf: training workspace missing");
+  const TcStash& S = plan.stash;
+  const int t_dfeat = S.idx_d0 + vf.n_layers - 1;
+  const int64_t n_padded = (n + kTileM - 1) / kTileM * kTileM;
+  float* dv_pre = plan.d3;
+  vf_dout_prepare_kernel<<<(unsigned)((n_padded * 32 + 255) / 256), 256, 0, s>>>(out, out_ld, d_out, d_ld, n_out_cols, n, n_padded,
+                                                                                dv_pre, plan.stash_buf + S.off[t_dfeat]);
+  VFN_LAUNCH_CHECK();
+  return backward_common(plan, vf, vf_arena, nullptr, nullptr, bn_eps, n, nullptr, dv_pre, vf_grad, nullptr, accumulate, s);
 }
 
 // ---------------------------------------------------------------------------------------------

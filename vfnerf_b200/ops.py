@@ -46,8 +46,6 @@ class _VFQuery(torch.autograd.Function):
         Do = ar.desc.out_dim[ar.desc.n_layers - 1]
         n_cols = Do if n_cols is None else int(n_cols)
         prec = _lib.PRECISIONS[net.precision]
-        if need_bwd and prec != _lib.PREC_FP32:
-            prec = _lib.PREC_FP32
         nbytes = L.vfnerf_vf_workspace_bytes(C.byref(ar.desc), P, net.multires, int(need_bwd), prec)
         if nbytes < 0:
             _lib.check(1, "vfnerf_vf_workspace_bytes")
@@ -56,7 +54,7 @@ class _VFQuery(torch.autograd.Function):
         _lib.check(L.vfnerf_vf_fwd(C.byref(ar.desc), ar.flat.data_ptr(), net.multires, net.skip_layer, 1e-5,
                                    prec, points.data_ptr(), P, out.data_ptr(), n_cols, n_cols,
                                    ws.data_ptr(), ws.numel(), int(need_bwd), _stream_ptr(dev)), "vfnerf_vf_fwd")
-        ctx.net, ctx.ws, ctx.P, ctx.n_cols = net, ws, P, n_cols
+        ctx.net, ctx.ws, ctx.P, ctx.n_cols, ctx.prec = net, ws, P, n_cols, prec
         ctx.save_for_backward(out)
         return out
 
@@ -70,7 +68,7 @@ class _VFQuery(torch.autograd.Function):
         d_out = d_out.contiguous().float()
         grad = torch.empty(ar.desc.arena_floats, dtype=torch.float32, device=dev)
         _lib.check(L.vfnerf_vf_bwd(C.byref(ar.desc), ar.flat.data_ptr(), net.multires, net.skip_layer, 1e-5,
-                                   _lib.PREC_FP32, ctx.P, out.data_ptr(), ctx.n_cols, d_out.data_ptr(), ctx.n_cols,
+                                   ctx.prec, ctx.P, out.data_ptr(), ctx.n_cols, d_out.data_ptr(), ctx.n_cols,
                                    ctx.n_cols, grad.data_ptr(), 0, ctx.ws.data_ptr(), ctx.ws.numel(),
                                    _stream_ptr(dev)), "vfnerf_vf_bwd")
         ctx.ws = None
