@@ -325,14 +325,26 @@ def main():
         rgb_gt = torch.rand(Rt, 3, device=dev, generator=g2)
         dep_gt = torch.rand(Rt, 1, device=dev, generator=g2) * CASE["far"]
 
+        # the reference's VFLoss with the shipped weights (confs/vf_nerf.conf:77-91), epoch 0, as ONE fused launch
+        # (vfnerf_b200/losses.py); sync=False: the per-term values stay on the device instead of six .item() calls
+        import types
+        from vfnerf_b200.losses import VFLoss
+        loss_mod = VFLoss(types.SimpleNamespace(norm_smaller_than_one_start=11000, depth_loss_clamp=0.5,
+                                                directional_derivatives_start=100),
+                          types.SimpleNamespace(rgb=2.0, depth=0.5, unit_norm=0.1, supervision=1.0,
+                                                norm_smaller_than_one=0.1, directional_derivatives=0.0), sync=False)
+
+        def vf_loss(out, rgb_t, dep_t):
+            return loss_mod({"rgb": out.coarse_rgb_values, "depth": out.coarse_depth_map,
+                             "normals": out.coarse_normals.reshape(-1, 3), "supervised_normals": None,
+                             "directional_derivatives": None}, {"rgb": rgb_t, "depth": dep_t}, 0)[0]
+
         def time_train(prec, n_tr):
             tm = U.make_model(dict(CASE, perturb=True, dir_to_normal_th=-2.0), st, dev, precision=prec)
 
             def train_step():
                 out = tm.render(poset, uvt, Kt, 0, draws=draws_t)
-                nrm = torch.norm(out.coarse_normals.reshape(-1, 3), dim=1)
-                loss = 2.0 * (out.coarse_rgb_values - rgb_gt).abs().mean() + \
-                    0.5 * (out.coarse_depth_map - dep_gt).abs().clamp(max=0.5).mean() + 0.1 * torch.mean((nrm - 1) ** 2)
+                loss = vf_loss(out, rgb_gt, dep_gt)
                 tm.optimizer.zero_grad()
                 loss.backward()
                 if world > 1:
@@ -358,7 +370,7 @@ def main():
         ms_tr = time_train(args.precision, 10 if args.precision == "bf16" else 5)
         train = {"value": world * Rt / (ms_tr * 1e-3), "unit": "rays/s", "rays_per_step_per_gpu": Rt,
                  "ms_per_step": ms_tr, "precision": args.precision,
-                 "includes": "eager: render fwd + loss + backward + (allreduce) + clip_grad_norm_ + Adam"}
+                 "includes": "eager: render fwd + fused VFLoss + backward + (allreduce) + clip_grad_norm_ + Adam"}
         if args.precision != "fp32":
             train["fp32_ms_per_step"] = time_train("fp32", 3)
 
@@ -369,9 +381,7 @@ def main():
             from vfnerf_b200 import graphed
 
             def loss_fn(out, rgb_gt, depth_gt):
-                nrm = torch.norm(out.coarse_normals.reshape(-1, 3), dim=1)
-                return 2.0 * (out.coarse_rgb_values - rgb_gt).abs().mean() + \
-                    0.5 * (out.coarse_depth_map - depth_gt).abs().clamp(max=0.5).mean() + 0.1 * torch.mean((nrm - 1) ** 2)
+                return vf_loss(out, rgb_gt, depth_gt)
 
             def time_graphed(n_rays, full, reps=50):
                 tm = U.make_model(dict(CASE, perturb=True, dir_to_normal_th=-2.0), st, dev, precision=args.precision)

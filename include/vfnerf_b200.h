@@ -150,6 +150,23 @@ int vfnerf_vf_bwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
                   float* vf_grad_arena, int accumulate,
                   void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- fused VFLoss (models/losses/vf_loss.py:34-87) ------------------------------------------
+ * Forward: all six terms in one reduction launch, no host synchronisation.  rgb/rgb_gt [n_rays,3]; depth/depth_gt
+ * [n_rays,1] (depth_gt NULL: the batch has no depth, term = 0); normals [n_points,3] (raw VF vectors); sup/sup_gt
+ * [n_sup,3] (n_sup may be 0); dd [n_dd] directional derivatives or NULL.  weights[6] in the order rgb, depth, unit_norm,
+ * supervision, norm_smaller_than_one, directional_derivatives; norm_lt1_active = (epoch >= norm_smaller_than_one_start).
+ * terms: 16 device floats -- [0..5] the unweighted terms in that order, [6] the weighted total, the rest scratch.
+ * Backward: gradients of the total times the device scalar *grad_loss; any output pointer may be NULL. */
+int vfnerf_vf_loss_fwd(int64_t n_rays, int64_t n_points, int64_t n_sup, int64_t n_dd, const float* rgb,
+                       const float* rgb_gt, const float* depth, const float* depth_gt, const float* normals,
+                       const float* sup, const float* sup_gt, const float* dd, const float* weights,
+                       float depth_clamp, int norm_lt1_active, float* terms, void* stream);
+int vfnerf_vf_loss_bwd(int64_t n_rays, int64_t n_points, int64_t n_sup, const float* rgb, const float* rgb_gt,
+                       const float* depth, const float* depth_gt, const float* normals, const float* sup,
+                       const float* sup_gt, const float* weights, float depth_clamp, int norm_lt1_active,
+                       const float* grad_loss, float* d_rgb, float* d_depth, float* d_normals, float* d_sup,
+                       void* stream);
+
 /* ---- both MLPs on given points: the VF + colour evaluation of VectorFieldNerf.get_colors ---------------- */
 /* (vector_field_nerf.py:341-375 / the merged pass of render(), :292-321).  points [P,3]; ray_dirs [P/samples_per_ray,3]
  * unit view directions, one per ray; normals [P,3] = tanh VF vectors; colors [P,3] = sigmoid colour-net output.

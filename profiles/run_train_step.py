@@ -11,6 +11,7 @@ import vfn_testutil as U
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 Rt = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+SUP = int(sys.argv[4]) if len(sys.argv) > 4 else 0        # supervision points through the VF-only entry (trainer: 2 x 13107)
 dev = "cuda"
 case, z = U.load_golden("full_det")
 case = dict(case, perturb=True, dir_to_normal_th=-2.0)
@@ -21,6 +22,8 @@ g2 = torch.Generator(device=dev).manual_seed(7)
 Nc, Nf = case["n_coarse"], case["n_fine"]
 draws = (torch.rand(Rt, Nc, device=dev, generator=g2), torch.rand(Rt, Nf, device=dev, generator=g2),
          torch.rand(Rt, Nf, device=dev, generator=g2))
+sup_pts = (torch.rand(max(SUP, 1), 3, device=dev, generator=g2) - 0.5) * 6
+sup_tgt = torch.nn.functional.normalize(torch.randn(max(SUP, 1), 3, device=dev, generator=g2), dim=1)
 rgb_gt = torch.rand(Rt, 3, device=dev, generator=g2)
 dep_gt = torch.rand(Rt, 1, device=dev, generator=g2) * case["far"]
 
@@ -32,6 +35,8 @@ def train_step(parts=None):
     nrm = torch.norm(out.coarse_normals.reshape(-1, 3), dim=1)
     loss = 2.0 * (out.coarse_rgb_values - rgb_gt).abs().mean() + \
         0.5 * (out.coarse_depth_map - dep_gt).abs().clamp(max=0.5).mean() + 0.1 * torch.mean((nrm - 1) ** 2)
+    if SUP:
+        loss = loss + ((tm.vector_field_network(sup_pts)[:, :3] - sup_tgt) ** 2).mean()
     tm.optimizer.zero_grad()
     if parts is not None: torch.cuda.synchronize(); parts["loss"] += time.perf_counter() - t; t = time.perf_counter()
     loss.backward()
@@ -53,7 +58,7 @@ for _ in range(n_steps):
 e1.record()
 t_host = time.perf_counter() - t0
 torch.cuda.synchronize()
-print(f"{prec} R={Rt}: {e0.elapsed_time(e1) / n_steps:.3f} ms/step (events); host issue time {t_host / n_steps * 1e3:.3f} ms/step")
+print(f"{prec} R={Rt} sup={SUP}: {e0.elapsed_time(e1) / n_steps:.3f} ms/step (events); host issue time {t_host / n_steps * 1e3:.3f} ms/step")
 parts = dict(render=0.0, loss=0.0, backward=0.0, clip=0.0, adam=0.0)
 for _ in range(n_steps):
     train_step(parts)

@@ -1,0 +1,153 @@
+// Fused VFLoss (models/losses/vf_loss.py:34-87): the reference evaluates six loss terms with
+// ~35 small aten kernels and reads each term back with .item() (six host syncs per step).  Here: one reduction launch
+// for all terms, one elementwise launch for all gradients, no host synchronisation.
+//   terms[0] rgb        = mean |rgb - rgb_gt|                                  (nn.L1Loss, :28)
+//   terms[1] depth      = mean min(|depth - depth_gt|, clamp)                  (:29-30; 0 when there is no depth)
+//   terms[2] unit_norm  = mean (||n|| - 1)^2                                   (:31)
+//   terms[3] supervision= mean (sup - sup_gt)^2                                (nn.MSELoss, :32; 0 when empty)
+//   terms[4] norm<1     = mean relu(||n|| - 1)^2                               (:33; only from norm_smaller_than_one_start)
+//   terms[5] dir.deriv. = mean dd                                              (:66-68; carries no gradient on this path)
+//   terms[6] total      = sum_i w_i * terms[i]
+#include "common.cuh"
+
+namespace vfn {
+
+struct LossArgs {
+  long long n_rays, n_points, n_sup, n_dd;
+  const float *rgb, *rgb_gt, *depth, *depth_gt, *normals, *sup, *sup_gt, *dd;
+  float w[6];
+  float depth_clamp;
+  int norm_lt1;
+};
+
+__global__ void __launch_bounds__(256) vf_loss_sums_kernel(const LossArgs a, float* __restrict__ sums) {
+  float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (long long i = t0; i < 3 * a.n_rays; i += stride) s[0] += fabsf(a.rgb[i] - a.rgb_gt[i]);
+  if (a.depth_gt)
+    for (long long i = t0; i < a.n_rays; i += stride) s[1] += fminf(fabsf(a.depth[i] - a.depth_gt[i]), a.depth_clamp);
+  for (long long i = t0; i < a.n_points; i += stride) {
+    const float x = a.normals[3 * i], y = a.normals[3 * i + 1], z = a.normals[3 * i + 2];
+    const float d = sqrtf(x * x + y * y + z * z) - 1.f;
+    s[2] += d * d;
+    if (a.norm_lt1 && d > 0.f) s[4] += d * d;
+  }
+  for (long long i = t0; i < 3 * a.n_sup; i += stride) { const float d = a.sup[i] - a.sup_gt[i]; s[3] += d * d; }
+  for (long long i = t0; i < a.n_dd; i += stride) s[5] += a.dd[i];
+  __shared__ float red[6][8];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float v = warp_sum(s[k]);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, v);
+  }
+}
+
+__global__ void vf_loss_finish_kernel(const LossArgs a, const float* __restrict__ sums, float* __restrict__ terms) {
+  if (threadIdx.x) return;
+  const float cnt[6] = {3.f * a.n_rays, (float)a.n_rays, (float)a.n_points, 3.f * a.n_sup, (float)a.n_points, (float)a.n_dd};
+  float total = 0.f;
+  for (int k = 0; k < 6; ++k) {
+    const bool on = cnt[k] > 0.f && !(k == 1 && !a.depth_gt) && !(k == 4 && !a.norm_lt1);
+    const float t = on ? sums[k] / cnt[k] : 0.f;
+    terms[k] = t;
+    total += a.w[k] * t;
+  }
+  terms[6] = total;
+}
+
+// gradients of the TOTAL loss times the upstream scalar *g_up
+__global__ void __launch_bounds__(256) vf_loss_grad_kernel(const LossArgs a, const float* __restrict__ g_up, float* __restrict__ d_rgb,
+                                                           float* __restrict__ d_depth, float* __restrict__ d_normals,
+                                                           float* __restrict__ d_sup) {
+  const float g = *g_up;
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (d_rgb) {
+    const float c = g * a.w[0] / (3.f * a.n_rays);
+    for (long long i = t0; i < 3 * a.n_rays; i += stride) {
+      const float d = a.rgb[i] - a.rgb_gt[i];
+      d_rgb[i] = d > 0.f ? c : (d < 0.f ? -c : 0.f);                    // torch: sign(0) = 0
+    }
+  }
+  if (d_depth) {
+    const float c = a.depth_gt ? g * a.w[1] / (float)a.n_rays : 0.f;
+    for (long long i = t0; i < a.n_rays; i += stride) {
+      float v = 0.f;
+      if (a.depth_gt) {
+        const float d = a.depth[i] - a.depth_gt[i];
+        if (fabsf(d) <= a.depth_clamp) v = d > 0.f ? c : (d < 0.f ? -c : 0.f);   // clamp(max) passes gradient at x <= max
+      }
+      d_depth[i] = v;
+    }
+  }
+  if (d_normals) {
+    const float c = 2.f * g / (float)a.n_points;
+    for (long long i = t0; i < a.n_points; i += stride) {
+      const float x = a.normals[3 * i], y = a.normals[3 * i + 1], z = a.normals[3 * i + 2];
+      const float nrm = sqrtf(x * x + y * y + z * z), d = nrm - 1.f;
+      float k = a.w[2] * d + ((a.norm_lt1 && d > 0.f) ? a.w[4] * d : 0.f);
+      k = nrm > 0.f ? c * k / nrm : 0.f;                               // torch.norm's subgradient at 0 is 0
+      d_normals[3 * i] = k * x; d_normals[3 * i + 1] = k * y; d_normals[3 * i + 2] = k * z;
+    }
+  }
+  if (d_sup) {
+    const float c = a.n_sup ? 2.f * g * a.w[3] / (3.f * a.n_sup) : 0.f;
+    for (long long i = t0; i < 3 * a.n_sup; i += stride) d_sup[i] = c * (a.sup[i] - a.sup_gt[i]);
+  }
+}
+
+static int grid_for(long long n) { return (int)std::min<long long>(std::max<long long>((n + 255) / 256, 1), 148 * 8); }
+
+}  // namespace vfn
+
+using namespace vfn;
+
+static LossArgs make_args(long long n_rays, long long n_points, long long n_sup, long long n_dd, const float* rgb,
+                          const float* rgb_gt, const float* depth, const float* depth_gt, const float* normals,
+                          const float* sup, const float* sup_gt, const float* dd, const float* w, float clamp, int lt1) {
+  LossArgs a{};
+  a.n_rays = n_rays; a.n_points = n_points; a.n_sup = n_sup; a.n_dd = dd ? n_dd : 0;
+  a.rgb = rgb; a.rgb_gt = rgb_gt; a.depth = depth; a.depth_gt = depth_gt; a.normals = normals; a.sup = sup; a.sup_gt = sup_gt; a.dd = dd;
+  for (int i = 0; i < 6; ++i) a.w[i] = w[i];
+  a.depth_clamp = clamp; a.norm_lt1 = lt1;
+  return a;
+}
+
+extern "C" int vfnerf_vf_loss_fwd(int64_t n_rays, int64_t n_points, int64_t n_sup, int64_t n_dd, const float* rgb,
+                                  const float* rgb_gt, const float* depth, const float* depth_gt, const float* normals,
+                                  const float* sup, const float* sup_gt, const float* dd, const float* weights,
+                                  float depth_clamp, int norm_lt1_active, float* terms, void* stream) {
+  VFN_REQUIRE(rgb && rgb_gt && normals && weights && terms, "vf_loss_fwd: null argument");
+  VFN_REQUIRE(n_rays > 0 && n_points > 0, "vf_loss_fwd: empty batch");
+  VFN_REQUIRE(!depth_gt || depth, "vf_loss_fwd: depth_gt without depth");
+  VFN_REQUIRE(n_sup == 0 || (sup && sup_gt), "vf_loss_fwd: supervision pointers missing");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const LossArgs a = make_args(n_rays, n_points, n_sup, n_dd, rgb, rgb_gt, depth, depth_gt, normals, sup, sup_gt, dd, weights,
+                               depth_clamp, norm_lt1_active);
+  float* sums = terms + 8;                      // terms is [16]: [0..6] results, [8..13] raw sums
+  VFN_CHECK_CUDA(cudaMemsetAsync(sums, 0, 8 * sizeof(float), s));
+  vf_loss_sums_kernel<<<grid_for(std::max<long long>(n_points, 3 * n_sup)), 256, 0, s>>>(a, sums);
+  VFN_LAUNCH_CHECK();
+  vf_loss_finish_kernel<<<1, 32, 0, s>>>(a, sums, terms);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vfnerf_vf_loss_bwd(int64_t n_rays, int64_t n_points, int64_t n_sup, const float* rgb, const float* rgb_gt,
+                                  const float* depth, const float* depth_gt, const float* normals, const float* sup,
+                                  const float* sup_gt, const float* weights, float depth_clamp, int norm_lt1_active,
+                                  const float* grad_loss, float* d_rgb, float* d_depth, float* d_normals, float* d_sup,
+                                  void* stream) {
+  VFN_REQUIRE(rgb && rgb_gt && normals && weights && grad_loss, "vf_loss_bwd: null argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const LossArgs a = make_args(n_rays, n_points, n_sup, 0, rgb, rgb_gt, depth, depth_gt, normals, sup, sup_gt, nullptr, weights,
+                               depth_clamp, norm_lt1_active);
+  vf_loss_grad_kernel<<<grid_for(std::max<long long>(n_points, 3 * n_sup)), 256, 0, s>>>(a, grad_loss, d_rgb, d_depth, d_normals, d_sup);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
