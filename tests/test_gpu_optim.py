@@ -1,0 +1,100 @@
+"""GPU: ArenaAdam (csrc/optim.cu, vfnerf_b200/optim.py) == torch's clip_grad_norm_ + Adam.step on every parameter once
+(train/vector_field_nerf_train.py:252-258), and its use inside the eager and the CUDA-graph training step."""
+import pytest
+import torch
+
+import vfn_testutil as U
+from vfnerf_b200 import graphed, optim
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _unique_params(model):
+    return list({id(p): p for p in model.parameters()}.values())
+
+
+@pytest.mark.parametrize("max_norm,weight_decay", [(0.5, 0.0), (None, 0.0), (0.05, 0.01)])
+def test_arena_adam_matches_torch_adam(built_lib, max_norm, weight_decay):
+    case, z = U.load_golden("small_det")
+    st = U.case_state(case, z)
+    ref = U.make_model(case, st, DEV)
+    new = U.make_model(case, st, DEV)
+    params = _unique_params(ref)
+    topt = torch.optim.Adam(params, lr=5e-4, weight_decay=weight_decay)
+    aopt = optim.ArenaAdam(new, lr=5e-4, weight_decay=weight_decay, max_norm=max_norm)
+    bn_before = new.vector_field_network.layers[0][1].running_var.clone()
+    g = torch.Generator().manual_seed(0)
+    new_params = _unique_params(new)
+    for it in range(6):
+        scale = 10.0 ** (it - 3)                       # gradient norms from far below to far above the clip threshold
+        aopt.zero_grad()
+        for p, q in zip(params, new_params):
+            gr = (torch.randn(p.shape, generator=g) * scale).to(DEV)
+            p.grad = gr.clone()
+            q.grad.add_(gr)                            # the persistent flat-gradient views
+        if max_norm is not None:
+            tn = torch.nn.utils.clip_grad_norm_(params, max_norm)
+        topt.step()
+        aopt.step()
+        if max_norm is not None:
+            assert abs(aopt.grad_norm().item() - tn.item()) <= 1e-4 * tn.item()
+    for p, q in zip(params, new_params):
+        assert torch.allclose(p, q, rtol=2e-5, atol=2e-7), (p - q).abs().max()
+    # BatchNorm running statistics share the arena but are not parameters: untouched even with weight decay
+    assert torch.equal(new.vector_field_network.layers[0][1].running_var, bn_before)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_training_with_arena_optimizer_eager_and_graphed(built_lib, precision):
+    case, z = U.load_golden("full_det")
+    st = U.case_state(case, z)
+    R = 64
+    uv, pose, K = (t.to(DEV) for t in U.S.synthetic_rays(R, seed=0, start=case["start"], stride=case["stride"]))
+    draws = U.S.synthetic_draws(R, case["n_coarse"], case["n_fine"])
+    rgb_gt, dep_gt = torch.rand(R, 3, device=DEV), torch.rand(R, 1, device=DEV) * case["far"]
+
+    def loss_fn(out, rgb_gt, depth_gt):
+        nrm = torch.norm(out.coarse_normals.reshape(-1, 3), dim=1)
+        return 2.0 * (out.coarse_rgb_values - rgb_gt).abs().mean() + \
+            0.5 * (out.coarse_depth_map - depth_gt).abs().clamp(max=0.5).mean() + 0.1 * torch.mean((nrm - 1) ** 2)
+
+    # reference sequence with torch's optimizer on unique parameters
+    ref = U.make_model(case, st, DEV, precision=precision)
+    params = _unique_params(ref)
+    topt = torch.optim.Adam(params, lr=5e-4)
+    out = ref.render(pose, uv, K, 0, draws=draws)
+    l_ref = loss_fn(out, rgb_gt, dep_gt)
+    topt.zero_grad()
+    l_ref.backward()
+    torch.nn.utils.clip_grad_norm_(params, 0.5)
+    g_ref = [p.grad.clone() for p in params]
+    w0 = ref.rendering_network.layers[1][0].weight.detach().clone()
+    topt.step()
+
+    # eager with ArenaAdam
+    m = U.make_model(case, st, DEV, precision=precision)
+    optim.use_arena_optimizer(m, max_norm=0.5)
+    out = m.render(pose, uv, K, 0, draws=draws)
+    loss = loss_fn(out, rgb_gt, dep_gt)
+    m.optimizer.zero_grad()
+    loss.backward()
+    m.optimizer.step()
+    m.scheduler.step()
+    assert loss.item() == l_ref.item()
+    for gr, p in zip(g_ref, _unique_params(m)):          # ArenaAdam leaves the clipped gradient in .grad, like clip_grad_norm_
+        assert (gr - p.grad).norm() <= 1e-4 * gr.norm() + 1e-12
+    lr = 5e-4
+    we, wa = ref.rendering_network.layers[1][0].weight, m.rendering_network.layers[1][0].weight
+    assert (we - w0).abs().max().item() > 0.5 * lr and ((we - wa).abs() > 0.5 * lr).float().mean().item() < 0.02
+
+    # graphed with ArenaAdam
+    gm = U.make_model(case, st, DEV, precision=precision)
+    optim.use_arena_optimizer(gm)
+    step = graphed.GraphedTrainStep(gm, loss_fn, R, dict(rgb_gt=rgb_gt, depth_gt=dep_gt), clip_norm=0.5, given_draws=True)
+    l0 = step(pose, uv, K, draws=draws, rgb_gt=rgb_gt, depth_gt=dep_gt).item()
+    wg = gm.rendering_network.layers[1][0].weight
+    assert l0 == l_ref.item()
+    assert ((we - wg).abs() > 0.5 * lr).float().mean().item() < 0.02
+    l1 = step(pose, uv, K, draws=draws, rgb_gt=rgb_gt, depth_gt=dep_gt).item()
+    assert l1 == l1 and l1 != l0

@@ -15,7 +15,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libvfnerf_b200.so")
-SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "tc_debug.cu"]
+SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "optim.cu", "tc_debug.cu"]
 HEADERS = ["common.cuh", "mlp_tc.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "vfnerf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -68,6 +68,8 @@ PROTOTYPES = {
                                   C.POINTER(C.c_float), C.POINTER(C.c_float), _F, _P, _P, _L, _P]),
     "vfnerf_vf_loss_fwd": (_I, [_L, _L, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float), _F, _I, _P, _P]),
     "vfnerf_vf_loss_bwd": (_I, [_L, _L, _L, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float), _F, _I, _P, _P, _P, _P, _P, _P]),
+    "vfnerf_sqnorm_accumulate": (_I, [_P, _L, _P, _P]),
+    "vfnerf_adam_step": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _F, _F, _F, _F, _F, _P, _P]),
     "vfnerf_mlp_points_workspace_bytes": (_L, [_DESC, _DESC, _I, _I, _I]),
     "vfnerf_mlp_points_fwd": (_I, [_DESC, _P, _DESC, _P, _I, _I, _I, _F, _I, _P, _P, _I, _L, _P, _P, _P, _L, _I, _P]),
     "vfnerf_ray_geometry": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P]),

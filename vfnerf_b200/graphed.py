@@ -56,8 +56,11 @@ class GraphedTrainStep:
         dev = next(iter(model.parameters())).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
-        if optimizer_step and not model.optimizer.param_groups[0].get("capturable", False):
-            raise RuntimeError("optimizer is not capturable: call vfnerf_b200.graphed.make_capturable(model) first")
+        from .optim import ArenaAdam
+        self._arena_opt = isinstance(model.optimizer, ArenaAdam)
+        if optimizer_step and not self._arena_opt and not model.optimizer.param_groups[0].get("capturable", False):
+            raise RuntimeError("optimizer is not capturable: call vfnerf_b200.graphed.make_capturable(model) or "
+                               "vfnerf_b200.optim.use_arena_optimizer(model) first")
         f32 = dict(dtype=torch.float32, device=dev)
         self.pose = torch.zeros((n_rays, 7) if quat_pose else (n_rays, 4, 4), **f32)
         self.pixels = torch.zeros(n_rays, 2, **f32)
@@ -99,6 +102,11 @@ class GraphedTrainStep:
         out = m.render(self.pose, self.pixels, self.intrinsics, 0, draws=self._draws())
         loss = self.loss_fn(out, **self.targets)
         loss.backward()
+        if self._arena_opt:
+            # flat arenas: clipping is part of the fused update (csrc/optim.cu)
+            if self.optimizer_step:
+                m.optimizer.step(max_norm=self.clip_norm)
+            return out, loss
         if self.clip_norm is not None:
             torch.nn.utils.clip_grad_norm_(self._params, self.clip_norm)
         if self.optimizer_step:
@@ -114,7 +122,7 @@ class GraphedTrainStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(max(1, warmup)):
-                m.optimizer.zero_grad(set_to_none=True)
+                m.optimizer.zero_grad(set_to_none=not self._arena_opt)
                 self._step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
@@ -125,9 +133,14 @@ class GraphedTrainStep:
                 for v in st.values():
                     if isinstance(v, torch.Tensor):
                         v.zero_()
+            if self._arena_opt:
+                for t in m.optimizer._m + m.optimizer._v + [m.optimizer._step]:
+                    t.zero_()
         self.graph.register_generator_state(self.gen)
-        m.optimizer.zero_grad(set_to_none=True)
+        m.optimizer.zero_grad(set_to_none=not self._arena_opt)
         with torch.cuda.graph(self.graph):
+            if self._arena_opt:
+                m.optimizer.zero_grad()            # persistent flat gradients: zeroed inside the graph, every replay
             self.outputs, self.loss = self._step()
 
     def __call__(self, pose: torch.Tensor, pixels: torch.Tensor, intrinsics: torch.Tensor, draws=None,

@@ -28,6 +28,7 @@ class ParamArena:
         self.flat: Optional[torch.Tensor] = None
         self.desc = _lib.MlpDesc()
         self.slots: List[Tuple[str, torch.Tensor, int]] = []   # (kind, tensor, offset)
+        self.grad_flat: Optional[torch.Tensor] = None           # flat gradient arena (optim.ArenaAdam), else None
         self.rebuild()
 
     def _tensors(self):
@@ -70,6 +71,28 @@ class ParamArena:
                 off += n
         d.arena_floats = total
         self.flat = flat
+        if self.grad_flat is not None:          # storage was replaced (.to(), load_state_dict(assign=True)): follow it
+            self.grad_flat = None
+            self.enable_flat_grad()
+
+    def enable_flat_grad(self) -> torch.Tensor:
+        """Give the gradients the arena's layout too: one zero-initialised flat tensor, every Parameter's ``.grad`` a
+        view of it.  The backward of ops.render_call / ops.vf_query then accumulates straight into it (one add per
+        network instead of one per parameter) and optim.ArenaAdam updates the whole network with two launches."""
+        if self.grad_flat is None:
+            self.grad_flat = torch.zeros_like(self.flat)
+        for _, t, off in self.slots:
+            if isinstance(t, nn.Parameter):
+                t.grad = self.grad_flat[off:off + t.numel()].view(t.shape)
+        return self.grad_flat
+
+    def trainable_mask(self) -> torch.Tensor:
+        """uint8 [arena_floats]: 1 on Parameter elements, 0 on BatchNorm running statistics."""
+        m = torch.zeros(self.flat.numel(), dtype=torch.uint8, device=self.flat.device)
+        for _, t, off in self.slots:
+            if isinstance(t, nn.Parameter):
+                m[off:off + t.numel()] = 1
+        return m
 
     def sync(self) -> torch.Tensor:
         """Arena tensor, re-flattened first if someone replaced parameter / buffer storage (``.to()``,
@@ -235,7 +258,19 @@ class LaplaceDensity(nn.Module):
                     f[i] = p.detach()
                     p.data = f[i]
             self._flat = f
+            if getattr(self, "grad_flat", None) is not None:
+                self.grad_flat = None
+                self.enable_flat_grad()
         return f
+
+    def enable_flat_grad(self) -> torch.Tensor:
+        """[d beta, d scale, d mean] as one tensor; the three Parameters' ``.grad`` are views of it (optim.ArenaAdam)."""
+        self.flat()
+        if getattr(self, "grad_flat", None) is None:
+            self.grad_flat = torch.zeros(3, dtype=torch.float32, device=self.beta.device)
+        for i, p in enumerate((self.beta, self.scale, self.mean)):
+            p.grad = self.grad_flat[i]
+        return self.grad_flat
 
     def get_beta(self) -> torch.Tensor:
         return torch.clamp(self.beta, float(self.beta_bounds[0]), float(self.beta_bounds[1]))

@@ -72,6 +72,9 @@ class _VFQuery(torch.autograd.Function):
                                    ctx.n_cols, grad.data_ptr(), 0, ctx.ws.data_ptr(), ctx.ws.numel(),
                                    _stream_ptr(dev)), "vfnerf_vf_bwd")
         ctx.ws = None
+        if ar.grad_flat is not None:               # flat-gradient mode (optim.ArenaAdam): one accumulate per network
+            ar.grad_flat.add_(grad)
+            return (None, None, None, None) + (None,) * len(ar.params())
         return (None, None, None, None) + tuple(ar.grad_views(grad))
 
 
@@ -227,6 +230,12 @@ class _Render(torch.autograd.Function):
         if DEBUG_KEEP_WORKSPACE:
             _debug_last.update(cfg=cfg, ws=ctx.ws, vf=vf_ar, rn=rn_ar)
         ctx.ws = ctx.keep = None
+        if vf_ar.grad_flat is not None and rn_ar.grad_flat is not None and getattr(call.density, "grad_flat", None) is not None:
+            # flat-gradient mode (optim.ArenaAdam): three accumulates instead of 55 per-parameter ones
+            vf_ar.grad_flat.add_(g_vf)
+            rn_ar.grad_flat.add_(g_rn)
+            call.density.grad_flat.add_(g_d)
+            return (None,) * (1 + len(vf_ar.params()) + len(rn_ar.params()) + 3)
         grads = vf_ar.grad_views(g_vf) + rn_ar.grad_views(g_rn) + [g_d[0], g_d[1], g_d[2]]
         return (None,) + tuple(grads)
 

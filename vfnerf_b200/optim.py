@@ -1,0 +1,87 @@
+"""ArenaAdam: clip_grad_norm_ + Adam over the flat parameter arenas (csrc/optim.cu).
+
+The reference trainer ends every step with ``clip_grad_norm_(model.parameters(), clip_norm)`` and ``Adam.step()``
+(train/vector_field_nerf_train.py:252-258): on a B200 those ~25 foreach launches over 55 tensors take 0.55 ms of a
+2 ms step.  Here every network is one flat tensor, its gradient is one flat tensor (``ParamArena.enable_flat_grad``),
+and a step is one squared-norm reduction + one elementwise launch per network.  Everything stays on the device
+(learning rate and step counter are device scalars), so the step can be captured in a CUDA graph (graphed.py).
+
+Semantics: exactly torch.optim.Adam (amsgrad off) after exactly torch's clip_grad_norm_ -- with every parameter counted
+ONCE.  The reference lists the VF parameters twice in its optimizer (vector_field_nerf.py:132-137), which makes torch
+clip and update them twice with racy foreach kernels; that quirk is deliberately not reproduced here (the default
+``model.optimizer`` still does)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+class ArenaAdam(torch.optim.Optimizer):
+    def __init__(self, model, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 max_norm: Optional[float] = None) -> None:
+        self.model = model
+        vf, rn = model.vector_field_network.arena(), model.rendering_network.arena()
+        vf.sync(); rn.sync()
+        dev = vf.flat.device
+        if dev.type != "cuda":
+            raise RuntimeError("ArenaAdam needs the model on a CUDA device")
+        self._arenas = (vf, rn)
+        self._density = model.density
+        flats = [vf.flat, rn.flat, model.density.flat()]
+        super().__init__([{"params": flats}], dict(lr=torch.tensor(float(lr), device=dev), betas=betas, eps=eps,
+                                                   weight_decay=weight_decay))
+        self.max_norm = max_norm
+        self._grads = [vf.enable_flat_grad(), rn.enable_flat_grad(), model.density.enable_flat_grad()]
+        self._masks = [vf.trainable_mask(), rn.trainable_mask(), None]
+        self._m = [torch.zeros_like(f) for f in flats]
+        self._v = [torch.zeros_like(f) for f in flats]
+        self._step = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._flats = flats
+
+    def zero_grad(self, set_to_none: bool = False) -> None:      # the gradients are persistent views: always zero in place
+        for g in self._grads:
+            g.zero_()
+
+    def grad_norm(self) -> torch.Tensor:
+        """Global 2-norm of the gradient as clip_grad_norm_ returns it (after step(): of the unclipped gradient)."""
+        return self._sq.sqrt()
+
+    @torch.no_grad()
+    def step(self, closure=None, max_norm: Optional[float] = None):
+        L = _lib.lib()
+        g0 = self.param_groups[0]
+        lr = g0["lr"]
+        if not isinstance(lr, torch.Tensor):                 # a scheduler replaced the tensor by a float
+            lr = g0["lr"] = torch.tensor(float(lr), device=self._step.device)
+        lr = lr.reshape(1).float()
+        b1, b2 = g0["betas"]
+        mn = self.max_norm if max_norm is None else max_norm
+        mn = 0.0 if mn is None else float(mn)
+        stream = torch.cuda.current_stream(self._step.device).cuda_stream
+        self._step.add_(1.0)
+        if mn > 0:
+            self._sq.zero_()
+            for g in self._grads:
+                _lib.check(L.vfnerf_sqnorm_accumulate(g.data_ptr(), g.numel(), self._sq.data_ptr(), stream), "vfnerf_sqnorm_accumulate")
+        for p, g, m, v, mask in zip(self._flats, self._grads, self._m, self._v, self._masks):
+            _lib.check(L.vfnerf_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _lib.ptr(mask), p.numel(),
+                                          lr.data_ptr(), self._step.data_ptr(), float(b1), float(b2), float(g0["eps"]),
+                                          float(g0["weight_decay"]), mn, self._sq.data_ptr(), stream), "vfnerf_adam_step")
+        return None
+
+
+def use_arena_optimizer(model, max_norm: Optional[float] = None) -> ArenaAdam:
+    """Replace model.optimizer / model.scheduler by ArenaAdam + the same ExponentialLR decay."""
+    sc = model.config.scheduler_config
+    old = model.optimizer.param_groups[0]
+    lr = old["lr"]
+    lr = float(lr.item()) if isinstance(lr, torch.Tensor) else float(lr)
+    opt = ArenaAdam(model, lr=lr, weight_decay=old.get("weight_decay", 0.0), max_norm=max_norm)
+    gamma = getattr(model.scheduler, "gamma", sc.lr_decay_factor ** (1. / sc.lr_decay_steps))
+    model.optimizer = opt
+    model.scheduler = torch.optim.lr_scheduler.ExponentialLR(opt, gamma)
+    return opt
