@@ -383,9 +383,13 @@ def main():
             def loss_fn(out, rgb_gt, depth_gt):
                 return vf_loss(out, rgb_gt, depth_gt)
 
-            def time_graphed(n_rays, full, reps=50):
+            def time_graphed(n_rays, full, reps=50, arena=False):
                 tm = U.make_model(dict(CASE, perturb=True, dir_to_normal_th=-2.0), st, dev, precision=args.precision)
-                graphed.make_capturable(tm)
+                if arena:
+                    from vfnerf_b200 import optim as voptim
+                    voptim.use_arena_optimizer(tm)
+                else:
+                    graphed.make_capturable(tm)
                 uvg, poseg, Kg = uv_d[:n_rays], pose_d[:n_rays], K_d[:n_rays]
                 tg = dict(rgb_gt=torch.rand(n_rays, 3, device=dev), depth_gt=torch.rand(n_rays, 1, device=dev) * CASE["far"])
                 step = graphed.GraphedTrainStep(tm, loss_fn, n_rays, tg, clip_norm=0.5 if full else None, optimizer_step=full)
@@ -410,6 +414,10 @@ def main():
             ms_g = time_graphed(Rt, True)
             train["graphed"] = {"ms_per_step": ms_g, "value": Rt / (ms_g * 1e-3), "unit": "rays/s",
                                 "includes": "CUDA-graph replay of render + loss + backward + clip + Adam, inputs copied per step"}
+            ms_a = time_graphed(Rt, True, arena=True)
+            train["graphed_arena_adam"] = {"ms_per_step": ms_a, "value": Rt / (ms_a * 1e-3), "unit": "rays/s",
+                                           "includes": "CUDA-graph replay of render + fused VFLoss + backward + ArenaAdam "
+                                                       "(clip + Adam on the flat arenas, 2 launches per network)"}
             ko = {}
             for n_r in (Rt, 8192):
                 ms_k = time_graphed(n_r, False)
