@@ -339,8 +339,11 @@ def main():
                              "normals": out.coarse_normals.reshape(-1, 3), "supervised_normals": None,
                              "directional_derivatives": None}, {"rgb": rgb_t, "depth": dep_t}, 0)[0]
 
-        def time_train(prec, n_tr):
+        def time_train(prec, n_tr, arena=False):
             tm = U.make_model(dict(CASE, perturb=True, dir_to_normal_th=-2.0), st, dev, precision=prec)
+            if arena:
+                from vfnerf_b200 import optim as voptim
+                voptim.use_arena_optimizer(tm, max_norm=0.5)
 
             def train_step():
                 out = tm.render(poset, uvt, Kt, 0, draws=draws_t)
@@ -350,7 +353,8 @@ def main():
                 if world > 1:
                     from vfnerf_b200 import dist as vd
                     vd.allreduce_gradients(tm)
-                torch.nn.utils.clip_grad_norm_(tm.parameters(), 0.5)
+                if not arena:
+                    torch.nn.utils.clip_grad_norm_(tm.parameters(), 0.5)
                 tm.optimizer.step()
             for _ in range(3):
                 train_step()
@@ -373,6 +377,10 @@ def main():
                  "includes": "eager: render fwd + fused VFLoss + backward + (allreduce) + clip_grad_norm_ + Adam"}
         if args.precision != "fp32":
             train["fp32_ms_per_step"] = time_train("fp32", 3)
+        ms_ar = time_train(args.precision, 10, arena=True)
+        train["arena_adam_eager"] = {"ms_per_step": ms_ar, "value": world * Rt / (ms_ar * 1e-3), "unit": "rays/s",
+                                     "includes": "eager: render + fused VFLoss + backward + (allreduce of the flat gradient "
+                                                 "arenas) + ArenaAdam (clip + Adam)"}
 
         # the same sequence captured once as a CUDA graph and replayed (vfnerf_b200/graphed.py), and -- SURVEY.md §8(d)
         # training protocol (i) -- the kernels alone: fwd + loss gradient + bwd into the flat gradient buffers,

@@ -58,6 +58,16 @@ def _worker(rank, world, port, ret):
         # grads still alias nothing weird: a second reduce of the same values is idempotent under averaging
         vd.allreduce_gradients(model, average=True)
         assert torch.allclose(model.density.beta.grad, torch.tensor(1.5))
+        # --- flat-gradient mode: the gradient arenas themselves are reduced, the .grad views see the result
+        vf_g = model.vector_field_network.arena().enable_flat_grad()
+        rn_g = model.rendering_network.arena().enable_flat_grad()
+        dn_g = model.density.enable_flat_grad()
+        for gflat in (vf_g, rn_g, dn_g):
+            gflat.fill_(float(2 * rank + 1))
+        vd.allreduce_gradients(model, average=True)
+        assert torch.allclose(model.rendering_network.layers[0][0].weight.grad,
+                              torch.full_like(model.rendering_network.layers[0][0].weight, 2.0))
+        assert torch.allclose(model.density.mean.grad, torch.tensor(2.0)) and torch.allclose(vf_g, torch.full_like(vf_g, 2.0))
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()

@@ -70,6 +70,16 @@ def allreduce_gradients(model, average: bool = True) -> None:
     rank, w = world()
     if w == 1:
         return
+    flats = [model.vector_field_network.arena().grad_flat, model.rendering_network.arena().grad_flat,
+             getattr(model.density, "grad_flat", None)]
+    if all(f is not None for f in flats):
+        # flat-gradient mode (optim.ArenaAdam): the gradient arenas ARE the communication buffers -- no packing, no
+        # scatter; three collectives (3.2 MB in total) queued back to back on the NCCL stream
+        for f in flats:
+            dist.all_reduce(f, op=dist.ReduceOp.SUM)
+            if average:
+                f /= w
+        return
     seen, params = set(), []
     for p in model.parameters():            # the reference's list holds the VF parameters twice
         if id(p) not in seen and p.grad is not None:
