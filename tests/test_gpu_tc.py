@@ -162,3 +162,38 @@ def test_umma_mn_major_conventions(built_lib, N, K):
         errs.append((D - ref).abs().max().item())
     print(f"MN-major N={N} K={K}: max abs err variant0 {errs[0]:.3e} variant1 {errs[1]:.3e}")
     assert errs[0] <= 1e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("R,n_coarse,n_fine", [(3, 40, 24), (77, 64, 36), (1, 64, 64)])
+def test_tc_render_ragged_sample_counts(built_lib, R, n_coarse, n_fine):
+    """Sample counts for which R*N is not a multiple of the 128-point tile (partial last tile, odd tile counts, the
+    caller-mutable sampler attributes of SURVEY.md §8b): forward vs the fp32 path, and a bf16 backward that stays
+    within the gate-flip bound of the fp32 gradients."""
+    case, z = U.load_golden("full_perturb")
+    case = dict(case, n_coarse=n_coarse, n_fine=n_fine, max_samples=100)
+    st = _tame_state()
+    uv, pose, K = U.S.synthetic_rays(R, seed=0, start=11, stride=797)
+    draws = U.S.synthetic_draws(R, n_coarse, n_fine, seed=7)
+    a = (pose.to(DEV), uv.to(DEV), K.to(DEV), 0)
+    grads = {}
+    outs = {}
+    zref = None
+    for prec in ("fp32", "bf16"):
+        model = U.make_model(case, st, DEV, precision=prec)
+        out = model.render(*a, draws=draws, z_vals_override=zref)
+        if zref is None:
+            zref = out.z_vals.detach()
+        model.optimizer.zero_grad()
+        (out.coarse_rgb_values.sum() + out.coarse_depth_map.sum() + (out.coarse_normals ** 2).sum() * 0.01).backward()
+        outs[prec] = out
+        grads[prec] = [p.grad.detach().clone() for p in model.rendering_network.parameters()] + \
+                      [p.grad.detach().clone() for p in model.vector_field_network.parameters()]
+    N = n_coarse + n_fine
+    assert outs["bf16"].coarse_normals.shape == (R, N, 3)
+    assert torch.equal(outs["bf16"].points_coarse, outs["fp32"].points_coarse)
+    assert (outs["bf16"].coarse_normals - outs["fp32"].coarse_normals).abs().max().item() <= 5e-3
+    assert (outs["bf16"].coarse_colors - outs["fp32"].coarse_colors).abs().max().item() <= 5e-3
+    assert (outs["bf16"].coarse_rgb_values - outs["fp32"].coarse_rgb_values).abs().max().item() <= 5e-3
+    for ga, gb in zip(grads["fp32"], grads["bf16"]):
+        assert torch.isfinite(gb).all()
+        assert (ga - gb).norm() <= 0.2 * ga.norm() + 1e-7
