@@ -538,6 +538,19 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             w[j] = __bfloat162float(__float2bfloat16(b)); w[3 + j] = b - w[j];
           }
         }
+        if (tile < num_tiles) {
+          // the same units are the A operands of the 3-row weight-gradient GEMMs of the two output layers
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            const float* a8 = u + 8 * sl;
+            const float* b8 = w + 8 * sl;
+            if (with_rn)
+              *stash_unit(p, p.sinfo.idx_dcolu, tile, sl, row) =
+                  make_uint4(pack_bf16x2(a8[0], a8[1]), pack_bf16x2(a8[2], a8[3]), pack_bf16x2(a8[4], a8[5]), pack_bf16x2(a8[6], a8[7]));
+            *stash_unit(p, p.sinfo.idx_dvu, tile, sl, row) =
+                make_uint4(pack_bf16x2(b8[0], b8[1]), pack_bf16x2(b8[2], b8[3]), pack_bf16x2(b8[4], b8[5]), pack_bf16x2(b8[6], b8[7]));
+          }
+        }
         if (with_rn) {
           if (n > 0) mbar_wait(&reg_free[2], (n - 1) & 1);
           store_slab_f(s_act, kColAux / 8, row, u);
@@ -669,7 +682,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       for (int si = 0; si < prog.n_steps; ++si, ++gstep) {
         const TcStep& st = prog.s[si];
         const uint32_t acc = tmem + (gstep & 1) * kAccCols + lane_off;
-        if (kBwd) {
+        if constexpr (kBwd) {
           // dgrad step: acc = dL/d(this layer's input); gate it with the stashed forward activation Y of that input
           // (ReLU: Y > 0; tanh: 1 - Y^2), hand it on as the next step's A operand and stash it for the wgrad GEMM.
           // ReLU gates were stored by the forward as one bit per element (8 bytes per row and 64 columns); they are
@@ -741,14 +754,13 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             }
           }
           tc_fence_before_sync();
-          continue;
-        }
+        } else {
         TCK(t_other);
         mbar_wait(&acc_full[gstep & 1], (gstep >> 1) & 1);
         TCK(t_acc);
         if (tl) p.dbg_buf[64 + si * 8 + 2 + 3 * h] = clock64();
         tc_fence_after_sync();
-        if (!kBwd && (st.epi == TC_EPI_RELU || st.epi == TC_EPI_FEAT)) {
+        if (st.epi == TC_EPI_RELU || st.epi == TC_EPI_FEAT) {
           const bool feat = st.epi == TC_EPI_FEAT;
           const bool to_act = !feat || render;
           const int stN = st.N;
@@ -853,9 +865,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               }
             }
           }
-        } else if (kBwd && (st.epi == TC_EPI_BWD_RELU || st.epi == TC_EPI_BWD_TANH)) {
-          // unreachable: backward steps are handled before the accumulator wait (mask prefetch)
-        } else if (!kBwd && st.epi == TC_EPI_V) {
+        } else if (st.epi == TC_EPI_V) {
           if (h == 0) {
             uint32_t v[16];
             tmem_ld16(acc, v);
@@ -883,7 +893,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               arrive_grp(kBarAux);
             }
           }
-        } else if (!kBwd) {  // TC_EPI_RGB
+        } else {  // TC_EPI_RGB
           if (h == 0) {
             uint32_t v[16];
             tmem_ld16(acc, v);
@@ -895,6 +905,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           }
         }
         tc_fence_before_sync();
+        }   // forward steps
       }
     }
     TCK(t_other);
@@ -997,10 +1008,12 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   TcStash& S = plan.stash;
   S.n_y = L + Lr - 1;                       // Y_s[0..L-2], Y_FEAT, Y_c[0..Lr-2]
   S.idx_emb0 = S.n_y; S.idx_skip = S.n_y + 1; S.idx_aux = S.n_y + 2; S.idx_d0 = S.n_y + 3;
-  S.n_tensors = 2 * S.n_y + 3;
+  S.idx_dcolu = 2 * S.n_y + 3; S.idx_dvu = 2 * S.n_y + 4;
+  S.n_tensors = 2 * S.n_y + 5;
   VFN_REQUIRE(S.n_tensors <= kTcMaxStash, "tensor-core path: too many layers for the activation stash");
   for (int i = 0; i < S.n_tensors; ++i) S.slabs[i] = 32;
   S.slabs[S.idx_emb0] = 2 * Epad / 8; S.slabs[S.idx_skip] = 6; S.slabs[S.idx_aux] = 6;
+  S.slabs[S.idx_dcolu] = 2; S.slabs[S.idx_dvu] = 2;
   auto yS = [&](int l) { return l; };                  // VF hidden layer l
   const int yFeat = L - 1;
   auto yC = [&](int l) { return L + l; };              // colour hidden layer l

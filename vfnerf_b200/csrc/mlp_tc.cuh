@@ -60,6 +60,8 @@ struct TcStash {
   int n_y;                          // number of forward activation tensors (VF hidden layers, features, colour hidden layers)
   int idx_emb0, idx_skip, idx_aux;  // prologue-written side inputs
   int idx_d0;                       // first gradient tensor: D_i = idx_d0 + i mirrors Y_i
+  int idx_dcolu, idx_dvu;           // 16-channel (hi, lo) units of d(colour pre-sigmoid) / d(vector pre-tanh), written by the
+                                    // dgrad kernel's prologue: the A operands of the two 3-row weight-gradient GEMMs
   int n_tensors;
   int slabs[kTcMaxStash];           // 8-channel slabs per tile
   long long off[kTcMaxStash];       // byte offset of the tensor inside the stash buffer

@@ -7,7 +7,8 @@
 //      activation stash exactly as stored (tile-major K-slab bf16) through MN-major UMMA descriptors, i.e. the
 //      transposition needed by dY^T X is done by the tensor core's operand fetch, not by a memory pass.  HBM-bound:
 //      one pass over the stash (1 KB per point per layer).
-//   4. thin reductions (3-row gradients of the two output layers, column sums for the bias / BatchNorm terms)
+//   4. the 3-row gradients of the two output layers ride along as 16-channel (hi, lo) unit tasks of the same kernel;
+//      every column sum of dY (bias / BatchNorm terms) is reduced from the shared-memory tiles it streams anyway
 //   5. finalize: map G back to the reference's parameter layout and apply the BatchNorm-eval chain rule.
 #include "mlp_tc.cuh"
 #include "tc_common.cuh"
@@ -28,6 +29,7 @@ struct WgTask {
   int x_slab0, n_xslabs;       // slab range of X used (N = 8 * n_xslabs <= 256)
   int g_off;                   // float offset of the destination block (row stride kGLd) + column offset
   int colsum_off;              // float offset of the 256 column sums of dY (bias / BatchNorm terms); -1: not this task
+  int m_rows;                  // rows of G that are meaningful (128 per half; 16 for the (hi, lo) unit tasks)
   int cta0, nctas;             // CTAs [cta0, cta0 + nctas) work on this task, tiles split evenly
 };
 struct WgParams {
@@ -167,13 +169,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     if (t1 > t0) {
       const int q = warp & 3, row = q * 32 + lane;
       for (int h = 0; h < halves; ++h) {
+        if (q * 32 >= T.m_rows) continue;          // unit tasks: only the first 16 accumulator rows mean anything
         float* g = p.gbuf + T.g_off + (long long)(h * 128 + row) * kGLd;
         for (int c0 = 0; c0 < N; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(tmem + h * 256 + (((uint32_t)(q * 32)) << 16) + c0, v);
           tmem_ld_wait();
+          if (row < T.m_rows) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(g + c0 + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 16; ++j) atomicAdd(g + c0 + j, __uint_as_float(v[j]));
+          }
         }
       }
     }
@@ -184,70 +189,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------
-// thin reductions over a stash tensor Y (tile-major bf16, 32 slabs):
-//   d3 != null: out[j*ld + c] += sum_p d3[p, j] * Y[p, c]  (j < 3)      (3-row weight gradients of the output layers)
-//   d3 == null: out[c]        += sum_p Y[p, c]                          (column sums)
-// ---------------------------------------------------------------------------------------------
-struct ThinTask { long long y_off; int slabs; const float* d3; float* out; int ld; };
-struct ThinParams { const uint8_t* stash; long long n_tiles, n_points; int n_tasks; ThinTask t[20]; };
-
-// warp w of a block owns slabs w, w+8, w+16, w+24; lane l owns rows l, l+32, l+64, l+96 of every tile: each load
-// instruction of a warp reads 512 contiguous bytes.  Sums stay in registers across the block's tiles and are reduced
-// across lanes once at the end.
-template <bool kD3>
-__global__ void __launch_bounds__(256) thin_reduce_kernel(const __grid_constant__ ThinParams p) {
-  const ThinTask& T = p.t[blockIdx.y];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if ((T.d3 != nullptr) != kD3) return;
-  constexpr int kOut = kD3 ? 3 : 1;
-  float acc[4][8][kOut];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int o = 0; o < kOut; ++o) acc[a][j][o] = 0.f;
-  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const uint8_t* base = p.stash + T.y_off + tile * (long long)T.slabs * 2048;
-    const long long p0 = tile * kTileM;
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int r = lane + 32 * rr;
-      const bool ok = p0 + r < p.n_points;
-      float d[3] = {1.f, 0.f, 0.f};
-      if (kD3) {
-        if (ok) { const float* dp = T.d3 + 3 * (p0 + r); d[0] = __ldg(dp); d[1] = __ldg(dp + 1); d[2] = __ldg(dp + 2); }
-        else d[0] = 0.f;
-      } else if (!ok) d[0] = 0.f;
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int sl = warp + 8 * a;
-        if (sl >= T.slabs) continue;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)sl * 2048 + r * 16));
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v0 = __uint_as_float(w[j] << 16), v1 = __uint_as_float(w[j] & 0xFFFF0000u);
-#pragma unroll
-          for (int o = 0; o < kOut; ++o) { acc[a][2 * j][o] += d[o] * v0; acc[a][2 * j + 1][o] += d[o] * v1; }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int sl = warp + 8 * a;
-    if (sl >= T.slabs) continue;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int o = 0; o < kOut; ++o) {
-        const float v = warp_sum(acc[a][j][o]);
-        if (lane == 0) atomicAdd(T.out + o * T.ld + sl * 8 + j, v);
-      }
-  }
-}
-
 // column sums of a [n,3] fp32 tensor -> out[0..2]
 __global__ void sum3_kernel(const float* __restrict__ d3, long long n, float* __restrict__ out) {
   float a[3] = {0.f, 0.f, 0.f};
@@ -265,7 +206,7 @@ __global__ void sum3_kernel(const float* __restrict__ d3, long long n, float* __
 //   dW = gamma*istd*post * G,  db = gamma*istd*post * s,  dbeta = post * s,
 //   dgamma = istd*post * (rowdot(W, G) + (b - mean) * s)
 // ---------------------------------------------------------------------------------------------
-enum { FK_IDENT = 0, FK_EMB = 1, FK_SKIP = 2, FK_C0 = 3 };
+enum { FK_IDENT = 0, FK_EMB = 1, FK_SKIP = 2, FK_C0 = 3, FK_HILO = 4 };
 struct FinLayer {
   int net, layer, kind, split, epad, ev;   // kind-specific: split = columns fed by the previous layer (FK_SKIP) / small_w (FK_C0)
   int g_slot;          // gbuf slot holding G rows for output channels [row0, ..)
@@ -295,6 +236,7 @@ __global__ void __launch_bounds__(128) tc_finalize_kernel(const __grid_constant_
   const bool bn = d.gamma_off[l] >= 0;
   // source rows
   const bool thin = F.thin_slot >= 0 && n < F.row0;
+  const bool hilo = thin || F.kind == FK_HILO;      // rows n (hi part) and n + 3 (lo part) of a unit task
   const float* G = thin ? p.gbuf + (long long)F.thin_slot * kGSlot + (long long)n * kGLd
                         : p.gbuf + (long long)F.g_slot * kGSlot + (long long)(n - F.row0) * kGLd;
   const float s = thin ? p.gbuf[(long long)F.thin_slot * kGSlot + 256 * kGLd + n]
@@ -309,7 +251,8 @@ __global__ void __launch_bounds__(128) tc_finalize_kernel(const __grid_constant_
   float dot = 0.f;
   for (int j = threadIdx.x; j < K; j += blockDim.x) {
     float g;
-    if (thin || F.kind == FK_IDENT) g = G[j];
+    if (hilo) g = G[j] + G[3 * kGLd + j];
+    else if (F.kind == FK_IDENT) g = G[j];
     else if (F.kind == FK_EMB) g = G[j] + G[F.epad + j];
     else if (F.kind == FK_SKIP) g = j < F.split ? G[j] : G[256 + (j - F.split)];
     else {  // FK_C0: reference input [p(3), embed(view)(ev), n(3), feat]; packed [feat | n(3), 0 x5, p(3), embed(view)]
@@ -379,7 +322,15 @@ static int backward_common(const TcPlan& plan, const vfnerf_mlp_desc& vf, const 
     T.d_off = S.off[d_t]; T.x_off = S.off[x_t]; T.d_slabs = S.slabs[d_t]; T.x_slabs = S.slabs[x_t];
     T.x_slab0 = x_slab0; T.n_xslabs = n_xslabs; T.g_off = slot * kGSlot + col0;
     T.colsum_off = col0 == 0 ? slot * kGSlot + 256 * kGLd : -1;
+    T.m_rows = 128;
     (void)d_slabs_used;
+  };
+  // 3-row gradients of the two output layers: G[16 x 256] = unit^T Y with unit = [hi(3), lo(3), 0...]; rows j and j+3
+  // are summed by the finalize kernel.  The accumulator rows past 16 read stale shared memory and are never stored.
+  auto unit_task = [&](int u_t, int x_t, int slot) {
+    WgTask& T = wp.t[nt++];
+    T.d_off = S.off[u_t]; T.x_off = S.off[x_t]; T.d_slabs = S.slabs[u_t]; T.x_slabs = S.slabs[x_t];
+    T.x_slab0 = 0; T.n_xslabs = 32; T.g_off = slot * kGSlot; T.colsum_off = -1; T.m_rows = 16;
   };
   const int skip = plan.render.skip_step;
   task(D0 + yS(0), S.idx_emb0, 0, S.slabs[S.idx_emb0], slotVF(0), 0, 32);
@@ -392,7 +343,9 @@ static int backward_common(const TcPlan& plan, const vfnerf_mlp_desc& vf, const 
     task(D0 + yC(0), yFeat, 0, 32, slotRN(0), 0, 32);
     task(D0 + yC(0), S.idx_aux, 0, 6, slotRN(0), 256, 32);
     for (int l = 1; l <= Lr - 2; ++l) task(D0 + yC(l), yC(l - 1), 0, 32, slotRN(l), 0, 32);
+    unit_task(S.idx_dcolu, yC(Lr - 2), slotRN(Lr - 1));
   }
+  unit_task(S.idx_dvu, yS(L - 2), slotThinV);
   wp.n_tasks = nt;
   if (g_sms == 0) {
     int dev = 0;
@@ -418,23 +371,9 @@ static int backward_common(const TcPlan& plan, const vfnerf_mlp_desc& vf, const 
     wgrad_tc_kernel<<<used, kWgThreads, smem, s>>>(wp);
     VFN_LAUNCH_CHECK();
   }
-  // 4. thin reductions: 3-row gradients of the two output layers (the column sums of every dY tensor come out of the
-  //    wgrad kernel, which has the tiles in shared memory anyway)
+  // 4. bias gradients of the two output layers (the 3-row weight gradients and every column sum of dY come out of the
+  //    wgrad kernel)
   {
-    ThinParams tp{};
-    tp.stash = plan.stash_buf; tp.n_tiles = tiles; tp.n_points = n;
-    int k = 0;
-    if (with_rn) {  // colour output layer: G[3 x 256] = dcol_pre^T Y_c[Lr-2]
-      ThinTask& T = tp.t[k++];
-      T.y_off = S.off[yC(Lr - 2)]; T.slabs = 32; T.d3 = dcol_pre; T.out = plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot; T.ld = kGLd;
-    }
-    {  // VF output layer, vector rows: G[3 x 256] = dv_pre^T Y_s[L-2]
-      ThinTask& T = tp.t[k++];
-      T.y_off = S.off[yS(L - 2)]; T.slabs = 32; T.d3 = dv_pre; T.out = plan.gbuf + (int64_t)slotThinV * kGSlot; T.ld = kGLd;
-    }
-    tp.n_tasks = k;
-    thin_reduce_kernel<true><<<dim3((int)std::min<int64_t>(tiles, 2 * g_sms), k), 256, 0, s>>>(tp);
-    VFN_LAUNCH_CHECK();
     if (with_rn) {
       sum3_kernel<<<64, 256, 0, s>>>(dcol_pre, n, plan.gbuf + (int64_t)slotRN(Lr - 1) * kGSlot + 256 * kGLd);
       VFN_LAUNCH_CHECK();
@@ -459,7 +398,7 @@ static int backward_common(const TcPlan& plan, const vfnerf_mlp_desc& vf, const 
     }
     for (int l = 0; with_rn && l < Lr; ++l) {
       FinLayer& F = fp.L[k++];
-      F.net = 1; F.layer = l; F.kind = l == 0 ? FK_C0 : FK_IDENT; F.split = plan.render.small_w; F.epad = Epad; F.ev = ev;
+      F.net = 1; F.layer = l; F.kind = l == 0 ? FK_C0 : (l == Lr - 1 ? FK_HILO : FK_IDENT); F.split = plan.render.small_w; F.epad = Epad; F.ev = ev;
       F.g_slot = slotRN(l); F.row0 = 0; F.thin_slot = -1; F.post = 1.f;
       maxrows = std::max(maxrows, rn.out_dim[l]);
     }
