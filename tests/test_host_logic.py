@@ -109,3 +109,38 @@ def test_sampler_attributes_are_read_at_call_time(model):
     assert cfg.window == 11 and cfg.skip_layer == 4 and cfg.multires == 6 and cfg.multires_view == 4
     model.ray_sampler.near, model.ray_sampler.far = 0.0, 6.0
     model.fine_sampler.N_samples = 64
+
+
+def test_device_side_trainer_pieces_refuse_cpu(model):
+    """losses.VFLoss, optim.ArenaAdam and graphed.GraphedTrainStep are CUDA-only like the rest of the package."""
+    import types
+    from vfnerf_b200 import graphed, optim
+    from vfnerf_b200.losses import VFLoss
+    loss = VFLoss(types.SimpleNamespace(norm_smaller_than_one_start=11000, depth_loss_clamp=0.5, directional_derivatives_start=100),
+                  types.SimpleNamespace(rgb=2.0, depth=0.5, unit_norm=0.1, supervision=1.0, norm_smaller_than_one=0.1,
+                                        directional_derivatives=0.0))
+    pred = {"rgb": torch.rand(4, 3), "depth": torch.rand(4, 1), "normals": torch.rand(8, 3), "supervised_normals": None,
+            "directional_derivatives": None}
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        loss(pred, {"rgb": torch.rand(4, 3), "depth": torch.rand(4, 1)}, 0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        optim.ArenaAdam(model)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        graphed.GraphedTrainStep(model, lambda out: out, 4, {})
+
+
+def test_flat_gradient_mode_aliases_parameter_grads(model):
+    """ParamArena.enable_flat_grad: every Parameter's .grad is a view of one flat tensor in arena layout."""
+    ar = model.rendering_network.arena()
+    g = ar.enable_flat_grad()
+    assert g.shape == ar.flat.shape and float(g.abs().sum()) == 0.0
+    w = model.rendering_network.layers[1][0].weight
+    w.grad.fill_(3.0)
+    off = ar.desc.w_off[1]
+    assert torch.equal(g[off:off + w.numel()], torch.full((w.numel(),), 3.0))
+    mask = ar.trainable_mask()
+    n_params = sum(p.numel() for p in model.rendering_network.parameters())
+    assert int(mask.sum()) == n_params and mask.numel() == ar.flat.numel() and n_params < mask.numel()
+    ar.grad_flat = None
+    for p in model.rendering_network.parameters():
+        p.grad = None

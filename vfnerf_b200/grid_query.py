@@ -15,20 +15,54 @@ import torch
 from . import _lib, ops
 
 
+_STAGING: dict = {}
+
+
+def _staging(device: torch.device, rows: int):
+    """Two pinned (input, output) staging pairs per (device, chunk size), allocated once: pinning memory costs
+    milliseconds, far more than moving a chunk."""
+    key = (str(device), rows)
+    if key not in _STAGING:
+        _STAGING.clear()                 # keep one size alive
+        _STAGING[key] = [(torch.empty(rows, 3).pin_memory(), torch.empty(rows, 3).pin_memory(), torch.cuda.Event())
+                         for _ in range(2)]
+    return _STAGING[key]
+
+
 def get_set_predictions(decoder, samples: torch.Tensor, max_batch: int, device: torch.device) -> torch.Tensor:
+    """evaluation/utils/mc_utils.py:88-104: CPU samples [P, >=3] in, CPU vectors [P,3] out, chunked over the GPU.
+    Chunks are double-buffered through pinned staging memory so the host copies, both PCIe directions and the tensor-core
+    query of consecutive chunks overlap."""
     samples.requires_grad = False
     n = samples.shape[0]
-    out = torch.zeros_like(samples[:, :3])
-    pinned = out.pin_memory() if out.device.type == "cpu" else out
-    head = 0
+    out = torch.zeros(n, 3, dtype=samples.dtype)
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("get_set_predictions needs a CUDA device: vfnerf_b200 has no CPU fallback")
+    rows = min(max_batch, max(n, 1))
+    slots = _staging(device, rows)
+    pending = [None, None]                 # (lo, hi) of the chunk whose result sits in the slot's output buffer
+    stream = torch.cuda.current_stream(device)
+
+    def drain(k):
+        if pending[k] is not None:
+            lo, hi = pending[k]
+            slots[k][2].synchronize()
+            out[lo:hi].copy_(slots[k][1][:hi - lo])
+            pending[k] = None
     with torch.no_grad():
-        while head < n:
-            sub = samples[head:min(head + max_batch, n)].to(device, non_blocking=True)
-            pinned[head:min(head + max_batch, n)].copy_(ops.vf_query(decoder, sub[:, :3], n_cols=3), non_blocking=True)
-            head += max_batch
-    if device.type == "cuda":
-        torch.cuda.current_stream(device).synchronize()
-    out.copy_(pinned)
+        for i, head in enumerate(range(0, n, max_batch)):
+            k = i & 1
+            lo, hi = head, min(head + max_batch, n)
+            drain(k)
+            s_in, s_out, ev = slots[k]
+            s_in[:hi - lo].copy_(samples[lo:hi, :3])
+            sub = s_in[:hi - lo].to(device, non_blocking=True)
+            s_out[:hi - lo].copy_(ops.vf_query(decoder, sub, n_cols=3), non_blocking=True)
+            ev.record(stream)
+            pending[k] = (lo, hi)
+    drain(0)
+    drain(1)
     return out
 
 
