@@ -234,6 +234,10 @@ int vfnerf_debug_umma_gemm(const float* A, const float* B, float* D, int N, int 
 int vfnerf_debug_umma_mn_gemm(const float* At, const float* Bt, float* D, int N, int K, int variant, void* stream);
 /* 2-CTA variant (cluster of two, tcgen05.mma.cta_group::2, M = 256): D[256,N] = bf16(A[256,K]) * bf16(B[N,K])^T */
 int vfnerf_debug_umma2_gemm(const float* A, const float* B, float* D, int N, int K, void* stream);
+/* Layout probe for cta_group::2 with M = 128 (64 rows per CTA): A [128,K], B [N,K]; the accumulator is placed at TMEM
+ * (lane_off, col_off); dump receives all 128 lanes x 512 columns of both CTAs ([2,128,512] floats, sentinel -777). */
+int vfnerf_debug_umma2_m128_probe(const float* A, const float* B, float* dump, int N, int K, int lane_off, int col_off,
+                                  void* stream);
 /* Micro-benchmark: every CTA issues n_mma back-to-back tcgen05.mma (M=128, N, K=16) from one thread; CTA 0 writes
  * the elapsed SM cycles to cycles_dev[0].  mode 1 adds a tcgen05.commit after every second MMA. */
 int vfnerf_debug_umma_bench(int N, int n_mma, int mode, int n_ctas, long long* cycles_dev, void* stream);

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "vfnerf_debug_umma_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "vfnerf_debug_umma_mn_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "vfnerf_debug_umma2_gemm": (_I, [_P, _P, _P, _I, _I, _P]),
+    "vfnerf_debug_umma2_m128_probe": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "vfnerf_debug_umma2_bench": (_I, [_I, _I, _I, _P, _P]),
     "vfnerf_debug_stash_read": (_I, [_P, _P, _P, _P, _I, _P, _P, _P]),
     "vfnerf_debug_umma_bench": (_I, [_I, _I, _I, _I, _P, _P]),

@@ -249,6 +249,90 @@ extern "C" int vfnerf_debug_umma2_gemm(const float* A, const float* B, float* D,
   return 0;
 }
 
+// ---- layout probe: tcgen05.mma.cta_group::2 with M = 128 (64 rows per CTA).  Dumps all 128 TMEM lanes x 512 columns of
+// both CTAs so the test can see where the 64 x N accumulator of each CTA lands, and whether it can be placed at a lane
+// offset (two 64-row sub-tiles side by side in the lanes of the same columns).
+namespace vfn {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+umma2_m128_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ dump, int N, int K,
+                        int lane_off, int col_off) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = cluster_ctarank();
+  const int Nh = N / 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 64 * K * 2;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int e = tid; e < 64 * K; e += 128) {
+    int r = e / K, k = e % K;
+    *reinterpret_cast<__nv_bfloat16*>(sA + slab_offset(64, r, k)) = __float2bfloat16(A[(int64_t)(rank * 64 + r) * K + k]);
+  }
+  for (int e = tid; e < Nh * K; e += 128) {
+    int r = e / K, k = e % K;
+    *reinterpret_cast<__nv_bfloat16*>(sB + slab_offset(Nh, r, k)) = __float2bfloat16(B[(int64_t)(rank * Nh + r) * K + k]);
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  // fill TMEM with a sentinel
+  for (int c0 = 0; c0 < 512; c0 += 16) {
+    const uint32_t z = __float_as_uint(-777.f);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                 ::"r"(tmem + ((uint32_t)(warp * 32) << 16) + c0), "r"(z) : "memory");
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      const uint64_t da = make_smem_desc(smem_u32(sA) + (k0 / 8) * slab_bytes(64), slab_bytes(64), 128);
+      const uint64_t db = make_smem_desc(smem_u32(sB) + (k0 / 8) * slab_bytes(Nh), slab_bytes(Nh), 128);
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+          "}" ::"r"(tmem + ((uint32_t)lane_off << 16) + col_off), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(k0 > 0)) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  const int lane_row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < 512; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) dump[((int64_t)rank * 128 + lane_row) * 512 + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+}  // namespace vfn
+
+extern "C" int vfnerf_debug_umma2_m128_probe(const float* A, const float* B, float* dump, int N, int K, int lane_off,
+                                             int col_off, void* stream) {
+  using namespace vfn;
+  VFN_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256, "debug_umma2_m128_probe: bad N/K");
+  size_t smem = (size_t)(64 + N / 2) * K * 2;
+  VFN_CHECK_CUDA(cudaFuncSetAttribute(umma2_m128_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma2_m128_probe_kernel<<<2, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(A, B, dump, N, K, lane_off, col_off);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- 2-CTA micro-benchmark: cycles per tcgen05.mma.cta_group::2 (M=256, N=256, K=16), with an optional
 // multicast tcgen05.commit after every 4th MMA (mode 1) or a non-multicast commit to the leader only (mode 2).
 namespace vfn {
