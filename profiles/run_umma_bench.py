@@ -20,3 +20,9 @@ for mode in (0, 1, 2):
     torch.cuda.synchronize()
     print(f"2-CTA pairs=74 N=256 M=256 mode={mode} (0 none, 1 multicast commit / 4 MMAs, 2 leader-only commit): "
           f"{out[0].item() / n:7.1f} cycles / MMA (ideal 128)")
+
+for mode, what in ((0, "M=256 N=256"), (4, "M=128 (64 rows per CTA) N=256"), (8, "M=256 N=128"), (12, "M=128 N=128")):
+    n = 2048
+    _lib.check(L.vfnerf_debug_umma2_bench(n, mode, 148, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "bench2")
+    torch.cuda.synchronize()
+    print(f"2-CTA {what}: {out[0].item() / n:7.1f} cycles / MMA")

@@ -355,7 +355,7 @@ umma2_bench_kernel(int n_mma, int mode, long long* out) {
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   if (rank == 0 && tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(256, 256);
+    const uint32_t idesc = make_idesc_bf16((mode & 4) ? 128 : 256, (mode & 8) ? 128 : 256);   // mode bit 2: M = 128 (64 rows per CTA); bit 3: N = 128
     const uint64_t da0 = make_smem_desc(smem_u32(smem), slab_bytes(128), 128);
     const uint64_t db0 = make_smem_desc(smem_u32(smem + 64 * 1024), slab_bytes(128), 128);
     const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32), a_lo0 = (uint32_t)da0, b_lo0 = (uint32_t)db0;
@@ -371,10 +371,10 @@ umma2_bench_kernel(int n_mma, int mode, long long* out) {
             ::"r"(tmem), "r"(a_lo0 + (base + j) * step), "r"(a_hi), "r"(b_lo0 + (base + j) * step), "r"(b_hi), "r"(idesc),
               "r"((uint32_t)((i | j) > 0)) : "memory");
       }
-      if (mode == 1)
+      if ((mode & 3) == 1)
         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                      ::"r"(smem_u32(&bar2)), "h"((uint16_t)3) : "memory");
-      if (mode == 2)
+      if ((mode & 3) == 2)
         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
     }
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
