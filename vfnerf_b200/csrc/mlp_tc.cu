@@ -390,8 +390,13 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           for (;; ++ck) {
             const uint4 c = *ck;
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], c.z);
-            bulk_g2s(s_stage + stage * kStageBytes, src, c.z, &full[stage]);
+            if (p.dbg & 4) {
+              // experiment: no weight traffic at all (results are garbage) -- isolates the L2 -> shared-memory streaming
+              mbar_arrive(&full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], c.z);
+              bulk_g2s(s_stage + stage * kStageBytes, src, c.z, &full[stage]);
+            }
             src += c.z;
             if (++stage == kTcStages) { stage = 0; phase ^= 1; }
             if (c.w) break;
