@@ -467,6 +467,62 @@ def main():
             gridq["e2e"] = {"value": samples.shape[0] / dtg, "unit": "points/s", "points": samples.shape[0],
                             "note": "get_set_predictions: pageable CPU samples in, CPU vectors out (24 B/point over PCIe)"}
 
+    # ---- HBM-bound kernels of the path (sampler, density/transmittance scan, compositor), each timed alone with CUDA
+    # events through its stage entry point of the C ABI on 262 144 rays (working sets of 0.2-0.9 GB, far beyond L2):
+    # achieved = algorithmic bytes / time, against the measured HBM copy bandwidth.
+    hbm = None
+    if not args.no_train and world == 1:
+        import ctypes as C
+        Rh, Nc, Nf = 262144, N_COARSE, N_FINE
+        N = Nc + Nf
+        sp = torch.cuda.current_stream().cuda_stream
+        f = lambda *sh: torch.empty(*sh, device=dev)
+        dirs_h = torch.nn.functional.normalize(torch.randn(Rh, 3, device=dev), dim=1)
+        cam_h = torch.randn(Rh, 3, device=dev)
+        tv = torch.linspace(0., 1., Nc).to(dev)
+        U3h = torch.rand(Rh, Nf, device=dev)
+        z_c, pts_c, w_c = f(Rh, Nc), f(Rh, Nc, 3), torch.rand(Rh, Nc, device=dev)
+        z_m, pts_m = f(Rh, N), f(Rh, N, 3)
+        nrm = torch.tanh(torch.randn(Rh, N, 3, device=dev))
+        col = torch.rand(Rh, N, 3, device=dev)
+        wts, rgb_o, dep_o = f(Rh, N), f(Rh, 3), f(Rh, 1)
+        cfg_h = model._render_cfg(Rh, False)
+        dpar = model.density.flat()
+        near, far, fr = float(model.ray_sampler.near), float(model.ray_sampler.far), float(model.fine_sampler.range)
+        kernels = {
+            "coarse_sample_kernel": (lambda: L.vfnerf_coarse_sample(Rh, Nc, near, far, 0, tv.data_ptr(), None, dirs_h.data_ptr(),
+                                                                    cam_h.data_ptr(), z_c.data_ptr(), pts_c.data_ptr(), sp),
+                                     Rh * (16 * Nc + 24)),
+            "fine_sample_kernel": (lambda: L.vfnerf_fine_sample(Rh, Nc, Nf, near, far, fr, 0, z_c.data_ptr(), w_c.data_ptr(), None,
+                                                                U3h.data_ptr(), dirs_h.data_ptr(), cam_h.data_ptr(), z_m.data_ptr(),
+                                                                pts_m.data_ptr(), sp),
+                                   Rh * (8 * Nc + 4 * Nf + 16 * N + 24)),
+            "density_weights_kernel": (lambda: L.vfnerf_density_weights(C.byref(cfg_h), N, dpar.data_ptr(), nrm.data_ptr(), 3,
+                                                                        dirs_h.data_ptr(), z_m.data_ptr(), None, None,
+                                                                        wts.data_ptr(), sp),
+                                       Rh * (20 * N + 12)),
+            "composite_kernel": (lambda: L.vfnerf_composite(Rh, N, wts.data_ptr(), col.data_ptr(), z_m.data_ptr(), rgb_o.data_ptr(),
+                                                            dep_o.data_ptr(), sp),
+                                 Rh * (20 * N + 16)),
+        }
+        hbm_peak = peaks()[0]["hbm_gbs"]
+        hbm = {"rays": Rh, "n_coarse": Nc, "n_fine": Nf, "peak_gbs": hbm_peak, "kernels": {}}
+        for name, (fn, nbytes) in kernels.items():
+            for _ in range(3):
+                assert fn() == 0, name
+            torch.cuda.synchronize()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(20):
+                fn()
+            h1.record()
+            torch.cuda.synchronize()
+            t_h = h0.elapsed_time(h1) * 1e-3 / 20
+            hbm["kernels"][name] = {"ms": t_h * 1e3, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / t_h / 1e9,
+                                    "frac_of_measured_hbm_peak": nbytes / t_h / 1e9 / hbm_peak}
+        del z_c, pts_c, w_c, z_m, pts_m, nrm, col, wts
+        torch.cuda.empty_cache()
+
     # ---- roofline of the dominant kernel, timed alone with CUDA events on the launching stream:
     #   bf16: the fused tcgen05 launch (VF + colour MLPs, RENDER program) on one chunk of merged points;
     #   fp32: the CUDA-core VF MLP chain (9 GEMM launches) on one chunk.
@@ -524,6 +580,8 @@ def main():
         line["train_step"] = train
     if gridq:
         line["grid_query"] = gridq
+    if hbm:
+        line["hbm_kernels"] = hbm
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, med, threads = cpu_reference_rays_per_s(3, 1)
         line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",

@@ -22,6 +22,12 @@ extern "C" {
 #endif
 
 #define VFNERF_MAX_LAYERS 16
+/* render_cfg.flags.  The reference evaluates the VF MLP on the coarse points twice (once in the coarse sweep,
+ * vector_field_nerf.py:252-272, once among the merged points, :289-312).  On the bf16 forward-only path both MLPs run on
+ * the coarse points once and the merged pass evaluates only the new fine candidates; results are bit-identical to
+ * recomputing because the merged coarse points carry the same bits and the fused chain is a pure per-point function.
+ * This flag restores the literal two-evaluation schedule (parity tests compare the two). */
+#define VFNERF_FLAG_RECOMPUTE_COARSE 1
 #define VFNERF_MAX_SAMPLES 256 /* samples per ray (coarse + fine) handled by one warp */
 
 /* precision of the two MLPs */
@@ -61,7 +67,7 @@ typedef struct vfnerf_render_cfg {
   int32_t multires_view;    /* rendering-net embedder_multires (4)                           */
   int32_t skip_layer;       /* VF skip_connection_in[0], -1 = none                           */
   int32_t precision;        /* VFNERF_PREC_*                                                 */
-  int32_t reserved;
+  int32_t flags;            /* VFNERF_FLAG_*                                                 */
   double near_, far_, fine_range;   /* python floats of the samplers (kept in double: the reference
                                        forms far-near and 2*range/(Nf-1) in double before rounding) */
   float dir_to_normal_th;
@@ -215,6 +221,17 @@ int vfnerf_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, doubl
                        double fine_range, int perturb, const float* z_coarse, const float* w_coarse,
                        const float* U2, const float* U3, const float* directions, const float* cam_loc,
                        float* z, float* points, void* stream);
+/* SURVEY.md 8f rank 4 -- the inverse-CDF importance sampler, FineSampler (ray_sampler.py:145-237); not called by the
+ * reference's render().  sample_pdf (:163-215): bins [R,n_bins], weights [R,n_bins-1] -> samples [R,n_samples];
+ * u is the reference's uniform tensor made explicit: [n_samples] (its linspace, deterministic, u_per_ray = 0) or
+ * [R,n_samples] (its torch.rand draw, u_per_ray = 1).  pdf_fine_sample = get_z_vals (:217-237): midpoint bins of
+ * z_coarse [R,Nc], weights w_coarse[:, 1:-1], result merged and sorted with z_coarse -> z [R,Nc+Nf] (+ points,
+ * nullable).  Warp prefix scan + binary search; parity is to 1e-5 (aten's CPU summation order is not reproduced). */
+int vfnerf_sample_pdf(int n_rays, int n_bins, int n_samples, const float* bins, const float* weights,
+                      const float* u, int u_per_ray, float* samples, void* stream);
+int vfnerf_pdf_fine_sample(int n_rays, int n_coarse, int n_fine, const float* z_coarse, const float* w_coarse,
+                           const float* u, int u_per_ray, const float* directions, const float* cam_loc,
+                           float* z, float* points, void* stream);
 /* a4+a5+a6: window_cosine_similarity + get_density + volsdf_volume_rendering
  * (functions.py:41-72, vector_field_nerf.py:442-474, rendering.py:122-148).
  * normals [R,N,*] with row stride normals_ld floats per sample. */

@@ -16,6 +16,8 @@ computes on the path ``VectorFieldNerf.render()``:
     models/samplers/ray_sampler.py:49-80       RaySampler.sample
     models/samplers/ray_sampler.py:113-142     UniformSampler.get_z_vals
     models/samplers/ray_sampler.py:264-302     RangeFineSampler.get_z_vals
+    models/samplers/ray_sampler.py:163-237     FineSampler.sample_pdf / get_z_vals (inverse-CDF sampler; not called
+                                               by render() upstream)
     models/helpers/embedder.py:6-52            positional encoding
     models/vector_field/vector_field_network.py:177-208   VF MLP (eval mode)
     models/vector_field/rendering_network.py:62-108       colour MLP
@@ -142,6 +144,35 @@ def fine_z_vals(z_coarse: torch.Tensor, w_coarse: torch.Tensor, near: float, far
     out = torch.sort(torch.cat([z_coarse, z_add], dim=-1), dim=-1)[0]
     alt = torch.sort(torch.cat([z_coarse, z_f], dim=-1), dim=-1)[0]
     return torch.where((m > 0)[:, None], alt, out)
+
+
+def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """FineSampler.sample_pdf, ray_sampler.py:163-215: inverse-CDF sampling of the piecewise-constant pdf that
+    ``weights[R,B-1]`` define over ``bins[R,B]``.  ``u`` is the reference's uniform tensor made explicit: its
+    ``linspace(0, 1, N_samples)`` when deterministic (:180-181), its ``torch.rand`` draw otherwise (:183);
+    [n] or [R,n]."""
+    weights = weights + 1e-5                                                # :174
+    pdf = weights / torch.sum(weights, -1, keepdim=True)                    # :175
+    cdf = torch.cumsum(pdf, -1)                                             # :176
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)              # :177
+    u = u.expand(list(cdf.shape[:-1]) + [u.shape[-1]]).contiguous()         # :181, :197
+    inds = torch.searchsorted(cdf, u, right=True)                           # :198
+    below = torch.clamp(inds - 1, min=0)                                    # :199
+    above = torch.clamp(inds, max=cdf.shape[-1] - 1)                        # :200
+    cdf_lo, cdf_hi = torch.gather(cdf, 1, below), torch.gather(cdf, 1, above)     # :205-207 (gather per ray)
+    bin_lo, bin_hi = torch.gather(bins, 1, below), torch.gather(bins, 1, above)
+    denom = cdf_hi - cdf_lo                                                 # :209
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)        # :210
+    t = (u - cdf_lo) / denom                                                # :211
+    return bin_lo + t * (bin_hi - bin_lo)                                   # :212
+
+
+def pdf_fine_z_vals(z_coarse: torch.Tensor, w_coarse: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """FineSampler.get_z_vals, ray_sampler.py:217-237: bins are the midpoints of the coarse samples, the weights drop
+    their first and last entry, and the new samples are merged (sorted) with the coarse ones."""
+    mid = .5 * (z_coarse[..., 1:] + z_coarse[..., :-1])                     # :231
+    z_new = sample_pdf(mid, w_coarse[..., 1:-1], u)                         # :233
+    return torch.sort(torch.cat([z_coarse, z_new], dim=-1), dim=-1)[0]      # :236
 
 
 # --------------------------------------------------------------------------------------

@@ -197,3 +197,30 @@ def test_tc_render_ragged_sample_counts(built_lib, R, n_coarse, n_fine):
     for ga, gb in zip(grads["fp32"], grads["bf16"]):
         assert torch.isfinite(gb).all()
         assert (ga - gb).norm() <= 0.2 * ga.norm() + 1e-7
+
+
+@pytest.mark.parametrize("R,n_coarse,n_fine,perturb", [(512, 64, 64, True), (333, 64, 64, False), (77, 100, 30, True),
+                                                        (5, 40, 24, False), (1, 20, 16, True)])
+def test_tc_render_reusing_coarse_results_is_bit_identical(built_lib, R, n_coarse, n_fine, perturb):
+    """bf16 forward-only render(): by default the coarse sweep runs both MLPs and the merged pass evaluates only the
+    fine candidates (include/vfnerf_b200.h, VFNERF_FLAG_RECOMPUTE_COARSE).  Every output field must equal, bit for
+    bit, the literal schedule of vector_field_nerf.py:252-312 (VF on the coarse points, then both MLPs on all merged
+    points): same points, and the fused chain is a pure function of (point, ray direction)."""
+    case, z = U.load_golden("full_perturb" if perturb else "full_det")
+    case = dict(case, n_coarse=n_coarse, n_fine=n_fine, max_samples=100, perturb=perturb)
+    model = U.make_model(case, U.case_state(case, z), DEV, precision="bf16")
+    uv, pose, K = U.S.synthetic_rays(R, seed=0, start=5, stride=797)
+    draws = U.S.synthetic_draws(R, n_coarse, n_fine, seed=21)
+    a = (pose.to(DEV), uv.to(DEV), K.to(DEV), 0)
+    with torch.no_grad():
+        fast = model.render(*a, draws=draws)
+        w_fast = model.last_extras["weights"].clone()
+        model.recompute_coarse = True
+        lit = model.render(*a, draws=draws)
+        w_lit = model.last_extras["weights"]
+    for f in ("points_coarse", "z_vals", "coarse_normals", "coarse_colors", "coarse_rgb_values", "coarse_depth_map",
+              "ray_dirs"):
+        assert torch.equal(getattr(fast, f), getattr(lit, f)), f
+    assert torch.equal(w_fast, w_lit)
+    assert (fast.z_vals[:, 1:] >= fast.z_vals[:, :-1]).all()
+    assert fast.coarse_rgb_values.abs().sum().item() > 0 or R < 8

@@ -23,6 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 MAX_LAYERS = 16
 MAX_SAMPLES = 256
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+FLAG_RECOMPUTE_COARSE = 1
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 
 
@@ -39,7 +40,7 @@ class RenderCfg(C.Structure):
     _fields_ = [("n_rays", C.c_int32), ("n_coarse", C.c_int32), ("n_fine", C.c_int32),
                 ("perturb", C.c_int32), ("pose_is_quat", C.c_int32), ("window", C.c_int32),
                 ("normalize", C.c_int32), ("multires", C.c_int32), ("multires_view", C.c_int32),
-                ("skip_layer", C.c_int32), ("precision", C.c_int32), ("reserved", C.c_int32),
+                ("skip_layer", C.c_int32), ("precision", C.c_int32), ("flags", C.c_int32),
                 ("near_", C.c_double), ("far_", C.c_double), ("fine_range", C.c_double),
                 ("dir_to_normal_th", C.c_float),
                 ("beta_lo", C.c_float), ("beta_hi", C.c_float), ("mean_lo", C.c_float),
@@ -75,6 +76,8 @@ PROTOTYPES = {
     "vfnerf_ray_geometry": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "vfnerf_coarse_sample": (_I, [_I, _I, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P]),
     "vfnerf_fine_sample": (_I, [_I, _I, _I, _D, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vfnerf_sample_pdf": (_I, [_I, _I, _I, _P, _P, _P, _I, _P, _P]),
+    "vfnerf_pdf_fine_sample": (_I, [_I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "vfnerf_density_weights": (_I, [_CFG, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "vfnerf_composite": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "vfnerf_debug_umma_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
@@ -103,11 +106,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
+    tmp = LIB_PATH + ".building.so"      # swapped in atomically: a concurrent snapshot/load never sees a partial file
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(res.stderr)
     return LIB_PATH

@@ -211,6 +211,10 @@ struct RenderPlan {
   int R, Nc, Nf, N, E, Ev, F, cin_ld;
   int64_t P, Pc;
   float *directions, *ray_dirs, *cam_loc, *z_c, *pts_c, *normals_c, *w_c, *emb, *cin, *weights;
+  // bf16 inference: coarse results are reused in the merged pass, only the fine candidates are evaluated again
+  int reuse_coarse;
+  float *colors_c, *pts_f, *normals_f, *colors_f;
+  uint8_t* src;      // [R,N] candidate index (coarse 0..Nc-1, fine Nc..N-1) at every merged position
   MlpBufs vf, rn;
   BwdBufs bw;
   float* d_out;      // [P, 3+F]   gradient wrt the VF net's tanh outputs / pre-activations
@@ -220,7 +224,7 @@ struct RenderPlan {
 };
 
 static int make_plan(const vfnerf_render_cfg& cfg, const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc& rn,
-                     int keep, void* ws, RenderPlan& p) {
+                     int keep, void* ws, RenderPlan& p, int have_z_override = 0) {
   p.R = cfg.n_rays; p.Nc = cfg.n_coarse; p.Nf = cfg.n_fine; p.N = p.Nc + p.Nf;
   p.P = (int64_t)p.R * p.N; p.Pc = (int64_t)p.R * p.Nc;
   p.E = 3 + 6 * cfg.multires; p.Ev = 3 + 6 * cfg.multires_view;
@@ -251,6 +255,15 @@ static int make_plan(const vfnerf_render_cfg& cfg, const vfnerf_mlp_desc& vf, co
   } else {
     VFN_REQUIRE(cfg.precision == VFNERF_PREC_BF16, "precision bf16x3 is not built yet; use fp32 or bf16");
     if (int e = tc_carve(c.base, c.off, cfg.multires, cfg.multires_view, cfg.skip_layer, vf, &rn, p.tc, p.P, keep)) return e;
+  }
+  // Sized for every call (the workspace query does not know about z_override); used when it applies.
+  p.reuse_coarse = cfg.precision == VFNERF_PREC_BF16 && !keep && !(cfg.flags & VFNERF_FLAG_RECOMPUTE_COARSE);
+  p.colors_c = p.pts_f = p.normals_f = p.colors_f = nullptr; p.src = nullptr;
+  if (p.reuse_coarse) {
+    const int64_t Pf = (int64_t)p.R * p.Nf;
+    p.colors_c = c.f(3 * p.Pc); p.pts_f = c.f(3 * Pf); p.normals_f = c.f(3 * Pf); p.colors_f = c.f(3 * Pf);
+    p.src = reinterpret_cast<uint8_t*>(c.f((p.P + 3) / 4));
+    if (have_z_override) p.reuse_coarse = 0;
   }
   p.bytes = c.off;
   return 0;
@@ -291,7 +304,7 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
   if (int e = check_precision(*cfg)) return e;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   RenderPlan p;
-  if (int e = make_plan(*cfg, *vf, *rn, keep_for_backward, workspace, p)) return e;
+  if (int e = make_plan(*cfg, *vf, *rn, keep_for_backward, workspace, p, z_override != nullptr)) return e;
   VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "render_fwd: workspace %lld B < required %lld B",
               (long long)workspace_bytes, (long long)p.bytes);
   VFN_REQUIRE(out->points && out->normals && out->rgb && out->depth && out->z_vals && out->colors,
@@ -315,9 +328,14 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
     }
   } else {
     if (int e = tc_prepare(*vf, vf_arena, rn, rn_arena, cfg->bn_eps, p.tc, s)) return e;
-    if (!z_override)
+    if (p.reuse_coarse) {
+      // both MLPs on the coarse points now: the merged pass moves these results instead of recomputing them
+      if (int e = tc_forward(p.tc, TC_MODE_RENDER, p.pts_c, nullptr, 0, 0, p.Pc, p.ray_dirs, p.Nc, p.normals_c, 3,
+                             nullptr, 0, p.colors_c, s)) return e;
+    } else if (!z_override) {
       if (int e = tc_forward(p.tc, TC_MODE_V_ONLY, p.pts_c, nullptr, 0, 0, p.Pc, nullptr, 0, p.normals_c, 3,
                              nullptr, 0, nullptr, s)) return e;
+    }
   }
   if (!z_override) {
     if (int e = launch_density_weights(*cfg, p.R, p.Nc, density_params, p.normals_c, 3, p.ray_dirs, z_c,
@@ -325,7 +343,8 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
   }
   // ---- fine sampling: merged, sorted z values and points (vector_field_nerf.py:284-287)
   if (int e = launch_fine_sample(p.R, p.Nc, p.Nf, cfg->near_, cfg->far_, cfg->fine_range, cfg->perturb, z_c, w_c,
-                                 U2, U3, z_override, p.directions, p.cam_loc, out->z_vals, out->points, s)) return e;
+                                 U2, U3, z_override, p.directions, p.cam_loc, out->z_vals, out->points,
+                                 p.reuse_coarse ? p.src : nullptr, p.reuse_coarse ? p.pts_f : nullptr, s)) return e;
   // ---- merged pass
   if (cfg->precision == VFNERF_PREC_FP32) {
     if (int e = launch_color_input_head(out->points, p.ray_dirs, p.R, p.N, cfg->multires_view, p.cin, p.cin_ld,
@@ -342,8 +361,17 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
     if (out->ray_dirs_rep)
       if (int e = launch_color_input_head(out->points, p.ray_dirs, p.R, p.N, cfg->multires_view, nullptr, 0,
                                           out->ray_dirs_rep, s)) return e;
-    if (int e = tc_forward(p.tc, keep_for_backward ? TC_MODE_RENDER_STASH : TC_MODE_RENDER, out->points, nullptr, 0, 0, p.P,
-                           p.ray_dirs, p.N, out->normals, 3, nullptr, 0, out->colors, s)) return e;
+    if (p.reuse_coarse) {
+      // the fine candidates are the only points not evaluated yet (the merged coarse points carry the same bits as
+      // the coarse sweep's, and the fused chain is a pure per-point function): evaluate them, then merge by `src`
+      if (int e = tc_forward(p.tc, TC_MODE_RENDER, p.pts_f, nullptr, 0, 0, (int64_t)p.R * p.Nf, p.ray_dirs, p.Nf,
+                             p.normals_f, 3, nullptr, 0, p.colors_f, s)) return e;
+      if (int e = launch_merge_samples(p.R, p.Nc, p.Nf, p.src, p.normals_c, p.normals_f, out->normals, p.colors_c,
+                                       p.colors_f, out->colors, s)) return e;
+    } else {
+      if (int e = tc_forward(p.tc, keep_for_backward ? TC_MODE_RENDER_STASH : TC_MODE_RENDER, out->points, nullptr, 0, 0, p.P,
+                             p.ray_dirs, p.N, out->normals, 3, nullptr, 0, out->colors, s)) return e;
+    }
     if (int e = launch_density_weights(*cfg, p.R, p.N, density_params, out->normals, 3, p.ray_dirs, out->z_vals,
                                        nullptr, nullptr, weights, s)) return e;
   }
@@ -597,7 +625,21 @@ int vfnerf_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, doubl
                        const float* U3, const float* directions, const float* cam_loc, float* z,
                        float* points, void* stream) {
   return launch_fine_sample(n_rays, n_coarse, n_fine, near_, far_, fine_range, perturb, z_coarse, w_coarse, U2, U3,
-                            nullptr, directions, cam_loc, z, points, reinterpret_cast<cudaStream_t>(stream));
+                            nullptr, directions, cam_loc, z, points, nullptr, nullptr,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vfnerf_sample_pdf(int n_rays, int n_bins, int n_samples, const float* bins, const float* weights, const float* u,
+                      int u_per_ray, float* samples, void* stream) {
+  return launch_sample_pdf(n_rays, n_bins, n_samples, bins, weights, u, u_per_ray, samples,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vfnerf_pdf_fine_sample(int n_rays, int n_coarse, int n_fine, const float* z_coarse, const float* w_coarse,
+                           const float* u, int u_per_ray, const float* directions, const float* cam_loc, float* z,
+                           float* points, void* stream) {
+  return launch_pdf_fine_sample(n_rays, n_coarse, n_fine, z_coarse, w_coarse, u, u_per_ray, directions, cam_loc, z,
+                                points, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vfnerf_density_weights(const vfnerf_render_cfg* cfg, int n_samples, const float* density_params,

@@ -71,7 +71,16 @@ int launch_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, doubl
                        double fine_range, int perturb, const float* z_coarse, const float* w_coarse,
                        const float* U2, const float* U3, const float* z_override,
                        const float* directions, const float* cam_loc, float* z, float* points,
-                       cudaStream_t s);
+                       uint8_t* src, float* points_fine, cudaStream_t s);
+int launch_sample_pdf(int n_rays, int n_bins, int n_samples, const float* bins, const float* weights, const float* u,
+                      int u_per_ray, float* samples, cudaStream_t s);
+int launch_pdf_fine_sample(int n_rays, int n_coarse, int n_fine, const float* z_coarse, const float* w_coarse,
+                           const float* u, int u_per_ray, const float* directions, const float* cam_loc, float* z,
+                           float* points, cudaStream_t s);
+// out[r, j, :] = src[r,j] < n_coarse ? coarse[r, src, :] : fine[r, src - n_coarse, :] for two [.,3] tensor pairs
+int launch_merge_samples(int n_rays, int n_coarse, int n_fine, const uint8_t* src, const float* a_coarse,
+                         const float* a_fine, float* a_out, const float* b_coarse, const float* b_fine,
+                         float* b_out, cudaStream_t s);
 
 // density_composite.cu
 int launch_density_weights(const vfnerf_render_cfg& cfg, int n_rays, int n_samples,

@@ -47,6 +47,10 @@ class VectorFieldNerf:
             pass
         self.to(config.cuda_config.device)
         self.return_ray_dirs = True
+        # True: evaluate the VF MLP on the coarse points a second time among the merged points, literally like
+        # vector_field_nerf.py:289-312; False (default): reuse the coarse sweep's results on the bf16 forward-only
+        # path (bit-identical output, 25 % fewer FLOPs; include/vfnerf_b200.h VFNERF_FLAG_RECOMPUTE_COARSE)
+        self.recompute_coarse = False
         self.last_extras: dict = {}
 
     # ---- module plumbing (vector_field_nerf.py:84-214) ------------------------------------------
@@ -143,6 +147,7 @@ class VectorFieldNerf:
         cfg.multires_view = self.rendering_network.multires_view
         cfg.skip_layer = self.vector_field_network.skip_layer
         cfg.precision = _lib.PRECISIONS[self.precision]
+        cfg.flags = _lib.FLAG_RECOMPUTE_COARSE if self.recompute_coarse else 0
         cfg.near_, cfg.far_, cfg.fine_range = float(near), float(far), float(self.fine_sampler.range)
         cfg.dir_to_normal_th = float(c.dir_to_normal_th)
         cfg.beta_lo, cfg.beta_hi = float(d.beta_bounds[0]), float(d.beta_bounds[1])

@@ -60,3 +60,72 @@ class RangeFineSampler(RaySampler):
         U2 = None if self.deterministic else torch.rand([n_rays, nf])
         U3 = torch.rand((n_rays, nf))
         return U2, U3
+
+
+class FineSampler(RaySampler):
+    """The inverse-CDF importance sampler, ray_sampler.py:145-237 (same constructor and methods).  The reference's
+    render() never calls it; it is the alternative fine sampler.  The uniform numbers are
+    made where the reference makes them -- ``linspace`` on the host when deterministic (:180), the global CPU
+    generator otherwise (:183) -- and everything else (pdf, warp prefix-scan cdf, binary search, lerp, merge sort)
+    is one kernel launch, ``pdf_sample_kernel`` in csrc/geometry_sampler.cu."""
+
+    def __init__(self, N_samples: int, deterministic: bool = False, pytest: bool = False) -> None:
+        super().__init__(near=-1.0, far=-1.0, N_samples=N_samples)
+        self.deterministic, self.pytest = deterministic, pytest
+
+    def _u(self, n_rays: int) -> torch.Tensor:
+        if self.pytest:
+            # :186-194 -- numpy's generator, seeded per call (float64 there; the kernel computes in fp32)
+            import numpy as np
+            np.random.seed(0)
+            if self.deterministic:
+                return torch.tensor(np.linspace(0., 1., self.N_samples)).float()
+            return torch.tensor(np.random.rand(n_rays, self.N_samples)).float()
+        if self.deterministic:
+            return torch.linspace(0., 1., steps=self.N_samples)
+        return torch.rand([n_rays, self.N_samples])
+
+    def sample_pdf(self, bins: torch.Tensor, weights: torch.Tensor, u: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """bins [R,B], weights [R,B-1] on the GPU -> samples [R,N_samples] (detached, like :214)."""
+        from . import _lib, ops
+        bins, weights = ops._require_cuda("bins", bins.detach()), ops._require_cuda("weights", weights.detach())
+        R, B = bins.shape
+        if weights.shape != (R, B - 1):
+            raise ValueError(f"weights must be [R, B-1] = {(R, B - 1)}, got {tuple(weights.shape)}")
+        u = (self._u(R) if u is None else u).to(bins.device).float().contiguous()
+        out = torch.empty(R, u.shape[-1], dtype=torch.float32, device=bins.device)
+        _lib.check(_lib.lib().vfnerf_sample_pdf(R, B, u.shape[-1], bins.data_ptr(), weights.data_ptr(), u.data_ptr(),
+                                                int(u.dim() == 2), out.data_ptr(), ops._stream_ptr(bins.device)),
+                   "vfnerf_sample_pdf")
+        return out
+
+    def get_z_vals(self, ray_dirs=None, cam_loc=None, device=None, coarse_z_vals: torch.Tensor = None,
+                   coarse_weights: torch.Tensor = None, u: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Merged, sorted z values [R, Nc + N_samples] (:217-237).  ``ray_dirs``/``cam_loc``/``device`` are accepted
+        and unused, like in the reference."""
+        return self._merged(coarse_z_vals, coarse_weights, u, None, None)[0]
+
+    def sample(self, directions: torch.Tensor, cam_loc: torch.Tensor, coarse_z_vals: torch.Tensor,
+               coarse_weights: torch.Tensor, u: Optional[torch.Tensor] = None):
+        """get_z_vals + RaySampler.sample (:49-80) in the same launch -> (z [R,N], points [R,N,3])."""
+        return self._merged(coarse_z_vals, coarse_weights, u, directions, cam_loc)
+
+    def _merged(self, z_c, w_c, u, directions, cam_loc):
+        from . import _lib, ops
+        z_c, w_c = ops._require_cuda("coarse_z_vals", z_c.detach()), ops._require_cuda("coarse_weights", w_c.detach())
+        R, Nc = z_c.shape
+        if w_c.shape != (R, Nc):
+            raise ValueError(f"coarse_weights must be {(R, Nc)}, got {tuple(w_c.shape)}")
+        dev = z_c.device
+        u = (self._u(R) if u is None else u).to(dev).float().contiguous()
+        Nf = u.shape[-1]
+        z = torch.empty(R, Nc + Nf, dtype=torch.float32, device=dev)
+        pts = None
+        if directions is not None:
+            directions, cam_loc = ops._require_cuda("directions", directions), ops._require_cuda("cam_loc", cam_loc)
+            pts = torch.empty(R, Nc + Nf, 3, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().vfnerf_pdf_fine_sample(R, Nc, Nf, z_c.data_ptr(), w_c.data_ptr(), u.data_ptr(),
+                                                     int(u.dim() == 2), _lib.ptr(directions), _lib.ptr(cam_loc),
+                                                     z.data_ptr(), _lib.ptr(pts), ops._stream_ptr(dev)),
+                   "vfnerf_pdf_fine_sample")
+        return z, pts
