@@ -89,3 +89,16 @@ def test_window_cosine_closed_form():
     assert torch.allclose(c[:, j], want, atol=2e-6)
     assert torch.allclose(c[:, 2], (u[:, 2] * u[:, 3]).sum(-1), atol=1e-6)
     assert c.shape == (3, 39)
+
+
+@pytest.mark.parametrize("tag", ["det", "rand", "ragged", "tiny"])
+def test_pdf_sampler_oracle_matches_reference_golden(tag):
+    """FineSampler.sample_pdf / get_z_vals (ray_sampler.py:163-237): the oracle restatement reproduces the live
+    reference's outputs bit for bit on CPU (fixture from tests/golden/make_golden_pdf.py)."""
+    import os
+    z = np.load(os.path.join(U.GOLDEN_DIR, "pdf_sampler.npz"))
+    g = {k: torch.from_numpy(z[f"{tag}.{k}"]) for k in ("z_c", "w_c", "u", "ref_z", "ref_samples")}
+    assert torch.equal(U.O.pdf_fine_z_vals(g["z_c"], g["w_c"], g["u"]), g["ref_z"])
+    mid = .5 * (g["z_c"][..., 1:] + g["z_c"][..., :-1])
+    assert torch.equal(U.O.sample_pdf(mid, g["w_c"][..., 1:-1], g["u"]), g["ref_samples"])
+    assert g["ref_z"].shape[1] == g["z_c"].shape[1] + g["u"].shape[-1]

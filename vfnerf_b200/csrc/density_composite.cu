@@ -10,6 +10,7 @@ namespace vfn {
 
 constexpr int kRayWarps = 4;
 constexpr int kMaxPerLane = VFNERF_MAX_SAMPLES / 32;  // 8
+constexpr int kUS = 4;   // floats per staged unit vector (x, y, z, pad): one LDS.128 per stencil partner
 
 struct Laplace {
   float beta, scale, mean;   // effective (clamped) parameters
@@ -68,7 +69,7 @@ __device__ __forceinline__ void stage_unit_vectors(const float* __restrict__ nrm
     const float* p = nrm_row + (int64_t)j * ld;
     float x = p[0], y = p[1], z = p[2];
     float n = fmaxf(sqrtf(x * x + y * y + z * z), 1e-8f);
-    su[3 * j] = x / n; su[3 * j + 1] = y / n; su[3 * j + 2] = z / n;
+    *reinterpret_cast<float4*>(su + kUS * j) = make_float4(x / n, y / n, z / n, 0.f);
     if (sinv) sinv[j] = 1.f / n;
   }
 }
@@ -76,15 +77,28 @@ __device__ __forceinline__ void stage_unit_vectors(const float* __restrict__ nrm
 __device__ __forceinline__ float dot3(const float* a, const float* b) {
   return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
 }
+__device__ __forceinline__ float dot3(const float4& a, const float4& b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z;
+}
 
 // windowed cosine c_j (functions.py:41-72 with the uniform weights of vector_field_nerf.py:453)
 __device__ __forceinline__ float window_cos(const float* su, int j, const Window& w) {
-  float base = dot3(su + 3 * j, su + 3 * (j + 1));
+  const float4* u4 = reinterpret_cast<const float4*>(su);
+  const float4 uj = u4[j];
+  float base = dot3(uj, u4[j + 1]);
   if (j < w.lo || j >= w.hi) return base;
   float c = base * w.coef;
+  if (w.nb == 5) {            // the shipped 11-tap window, unrolled (same order of operations as the loop below)
+#pragma unroll
+    for (int i = 1; i <= 5; ++i) {
+      c = c + dot3(uj, u4[j + 1 + i]) * w.coef;
+      c = c + dot3(uj, u4[j - i]) * w.coef;
+    }
+    return c;
+  }
   for (int i = 1; i <= w.nb; ++i) {
-    c = c + dot3(su + 3 * j, su + 3 * (j + 1 + i)) * w.coef;
-    c = c + dot3(su + 3 * j, su + 3 * (j - i)) * w.coef;
+    c = c + dot3(uj, u4[j + 1 + i]) * w.coef;
+    c = c + dot3(uj, u4[j - i]) * w.coef;
   }
   return c;
 }
@@ -92,12 +106,14 @@ __device__ __forceinline__ float window_cos(const float* su, int j, const Window
 // ---------------------------------------------------------------------------------------------
 // forward: c, sigma, weights
 // ---------------------------------------------------------------------------------------------
+// KP = samples per lane (N <= 32 * KP): instantiated for 2, 4 and 8 so a 128-sample ray does not pay for 256.
+template <int KP>
 __global__ void __launch_bounds__(kRayWarps * 32)
 density_weights_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __restrict__ dparams,
                        const float* __restrict__ normals, int64_t ld, const float* __restrict__ ray_dirs,
                        const float* __restrict__ z, float* __restrict__ cosw, float* __restrict__ sigma_out,
                        float* __restrict__ weights) {
-  __shared__ float s_u[kRayWarps][3 * VFNERF_MAX_SAMPLES];
+  __shared__ __align__(16) float s_u[kRayWarps][kUS * VFNERF_MAX_SAMPLES];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int r = blockIdx.x * kRayWarps + wid;
   if (r >= n_rays) return;
@@ -113,14 +129,14 @@ density_weights_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
   __syncwarp();
   const float* zr = z + (int64_t)r * N;
   float carry = 0.f, wsum = 0.f;
-  float what[kMaxPerLane];
+  float what[KP];
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
+  for (int i = 0; i < KP; ++i) {
     const int j = lane + 32 * i;
     float E = 0.f, sg = 0.f;
     if (j < N - 1) {
       float c = window_cos(su, j, win);
-      float cdir = dot3(su + 3 * j, d);
+      float cdir = dot3(su + kUS * j, d);
       sg = fmaxf(lap.cdf(-c) - lap.L0, 0.f);
       if (cdir < cfg.dir_to_normal_th && c < 0.f) sg = 0.f;
       E = (zr[j + 1] - zr[j]) * sg;
@@ -138,7 +154,7 @@ density_weights_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
   wsum = warp_sum(wsum);
   const float inv = cfg.normalize ? 1.f / (wsum + 1e-5f) : 1.f;
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
+  for (int i = 0; i < KP; ++i) {
     const int j = lane + 32 * i;
     if (j < N) weights[(int64_t)r * N + j] = what[i] * inv;
   }
@@ -152,8 +168,11 @@ int launch_density_weights(const vfnerf_render_cfg& cfg, int n_rays, int n_sampl
   VFN_REQUIRE(n_samples >= 2 && n_samples <= VFNERF_MAX_SAMPLES, "density_weights: n_samples=%d out of [2,%d]",
               n_samples, VFNERF_MAX_SAMPLES);
   VFN_REQUIRE(cfg.window >= 1 && cfg.window <= 63, "density_weights: window=%d unsupported", cfg.window);
-  density_weights_kernel<<<(n_rays + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, s>>>(
-      cfg, n_rays, n_samples, density_params, normals, normals_ld, ray_dirs, z, cosw, sigma, weights);
+  const dim3 grid((n_rays + kRayWarps - 1) / kRayWarps), block(kRayWarps * 32);
+#define VFN_DW(KP) density_weights_kernel<KP><<<grid, block, 0, s>>>( \
+      cfg, n_rays, n_samples, density_params, normals, normals_ld, ray_dirs, z, cosw, sigma, weights)
+  if (n_samples <= 64) VFN_DW(2); else if (n_samples <= 128) VFN_DW(4); else VFN_DW(kMaxPerLane);
+#undef VFN_DW
   VFN_LAUNCH_CHECK();
   return 0;
 }
@@ -196,6 +215,7 @@ int launch_composite(int n_rays, int n_samples, const float* weights, const floa
 //   d_colors [R*N,3] = w_j * d_rgb (+ upstream),   d_normals [R,N,ld] = dL/dv_j (+ upstream),
 //   d_density[3] += d(beta, scale, mean)   (atomicAdd of one value per ray; caller zeroes it).
 // ---------------------------------------------------------------------------------------------
+template <int KP>
 __global__ void __launch_bounds__(kRayWarps * 32)
 render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __restrict__ dparams,
                        const float* __restrict__ normals, int64_t ld, const float* __restrict__ ray_dirs,
@@ -204,7 +224,7 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
                        const float* __restrict__ d_normals_up, const float* __restrict__ d_colors_up,
                        float* __restrict__ d_colors, float* __restrict__ d_normals, int64_t dn_ld,
                        float* __restrict__ d_density) {
-  __shared__ float s_u[kRayWarps][3 * VFNERF_MAX_SAMPLES];
+  __shared__ __align__(16) float s_u[kRayWarps][kUS * VFNERF_MAX_SAMPLES];
   __shared__ float s_inv[kRayWarps][VFNERF_MAX_SAMPLES];
   __shared__ float s_dc[kRayWarps][VFNERF_MAX_SAMPLES];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -227,17 +247,17 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
   const float gd = d_depth[r];
 
   // ---- forward recompute
-  float cj[kMaxPerLane], E[kMaxPerLane], T[kMaxPerLane], what[kMaxPerLane], dw[kMaxPerLane], delta[kMaxPerLane];
-  bool active[kMaxPerLane];
+  float cj[KP], E[KP], T[KP], what[KP], dw[KP], delta[KP];
+  bool active[KP];
   float carry = 0.f, wsum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
+  for (int i = 0; i < KP; ++i) {
     const int j = lane + 32 * i;
     float e = 0.f, c = 1.f, dl = 0.f;
     bool act = false;
     if (j < N - 1) {
       c = window_cos(su, j, win);
-      float cdir = dot3(su + 3 * j, d);
+      float cdir = dot3(su + kUS * j, d);
       float sg = lap.cdf(-c) - lap.L0;
       act = sg > 0.f && !(cdir < cfg.dir_to_normal_th && c < 0.f);
       sg = act ? sg : 0.f;
@@ -257,7 +277,7 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
   // ---- composite backward: d_colors and dL/dw
   float dot_dw_w = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
+  for (int i = 0; i < KP; ++i) {
     const int j = lane + 32 * i;
     dw[i] = 0.f;
     if (j < N) {
@@ -273,9 +293,9 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
   }
   dot_dw_w = warp_sum(dot_dw_w);
   // w = what / (S + eps)  =>  d what_j = (dw_j - sum_i dw_i w_i) / (S + eps)
-  float q[kMaxPerLane], qtot = 0.f;
+  float q[KP], qtot = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
+  for (int i = 0; i < KP; ++i) {
     const int j = lane + 32 * i;
     float dwh = 0.f;
     if (j < N) dwh = cfg.normalize ? (dw[i] - dot_dw_w) * inv : dw[i];
@@ -287,7 +307,7 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
   // dE_j = d what_j * T_j * exp(-E_j) - sum_{i>j} d what_i * what_i
   float ds_acc = 0.f, dm_acc = 0.f, db_acc = 0.f, qcarry = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
+  for (int i = 0; i < KP; ++i) {
     const int j = lane + 32 * i;
     float inc = warp_inclusive_scan(q[i], lane);
     float suffix = qtot - (qcarry + inc);            // sum over i > j
@@ -312,7 +332,7 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
   const int reach = win.nb + 1;
   for (int k = lane; k < N; k += 32) {
     float gx = 0.f, gy = 0.f, gz = 0.f;
-    const float* uk = su + 3 * k;
+    const float* uk = su + kUS * k;
     const bool k_band = (k >= win.lo && k < win.hi);
     for (int m = max(0, k - reach); m <= min(N - 1, k + reach); ++m) {
       if (m == k) continue;
@@ -327,7 +347,7 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
         else if (k == m + 1) om += sdc[m];
       }
       if (om != 0.f) {
-        const float* um = su + 3 * m;
+        const float* um = su + kUS * m;
         float cs = dot3(uk, um);
         gx += om * (um[0] - cs * uk[0]); gy += om * (um[1] - cs * uk[1]); gz += om * (um[2] - cs * uk[2]);
       }
@@ -361,9 +381,12 @@ int launch_render_tail_bwd(const vfnerf_render_cfg& cfg, int n_rays, int n_sampl
                            int64_t d_normals_ld, float* d_density, cudaStream_t s) {
   if (n_rays <= 0) return 0;
   VFN_REQUIRE(n_samples >= 2 && n_samples <= VFNERF_MAX_SAMPLES, "render_tail_bwd: n_samples=%d out of range", n_samples);
-  render_tail_bwd_kernel<<<(n_rays + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, s>>>(
-      cfg, n_rays, n_samples, density_params, normals, normals_ld, ray_dirs, z, colors, d_rgb, d_depth,
-      d_normals_up, d_colors_up, d_colors, d_normals, d_normals_ld, d_density);
+  const dim3 grid((n_rays + kRayWarps - 1) / kRayWarps), block(kRayWarps * 32);
+#define VFN_TB(KP) render_tail_bwd_kernel<KP><<<grid, block, 0, s>>>( \
+      cfg, n_rays, n_samples, density_params, normals, normals_ld, ray_dirs, z, colors, d_rgb, d_depth, \
+      d_normals_up, d_colors_up, d_colors, d_normals, d_normals_ld, d_density)
+  if (n_samples <= 64) VFN_TB(2); else if (n_samples <= 128) VFN_TB(4); else VFN_TB(kMaxPerLane);
+#undef VFN_TB
   VFN_LAUNCH_CHECK();
   return 0;
 }

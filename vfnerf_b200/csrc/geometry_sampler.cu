@@ -119,9 +119,66 @@ int launch_coarse_sample(int n_rays, int n_coarse, double near_, double far_, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-level sort of cat(run A = s[0, na), run B = s[na, na + nb)) into t[0, na + nb), with the source index of every
+// output in ti.  Values are only moved, so the result equals torch.sort's values bit for bit.
+//  * fast path (both runs already ascending -- coarse z values are, and so is the fine ramp): merge by rank.  An element
+//    of A lands at (its index + number of B elements smaller than it), an element of B at (its index + number of A
+//    elements not larger than it): two binary searches per lane and sample instead of a full sort;
+//  * otherwise (the uniform "z_add" candidates, random inverse-CDF draws, NaNs): bitonic sort in place, then copy.
+// s / si need room for the next power of two >= na + nb (<= VFNERF_MAX_SAMPLES).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_sort_two_runs(float* s, uint8_t* si, float* t, uint8_t* ti, int na, int nb, int lane) {
+  const int N = na + nb;
+  bool ok = true;
+  for (int j = lane; j < N; j += 32)
+    if (j != 0 && j != na) ok = ok && (s[j - 1] <= s[j]);
+  if (__all_sync(kFull, ok)) {
+    for (int e = lane; e < N; e += 32) {
+      const float v = s[e];
+      int rank;
+      if (e < na) {                       // lower bound of v in B
+        int lo = 0, hi = nb;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (s[na + mid] < v) lo = mid + 1; else hi = mid; }
+        rank = e + lo;
+      } else {                            // upper bound of v in A
+        int lo = 0, hi = na;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (s[mid] <= v) lo = mid + 1; else hi = mid; }
+        rank = (e - na) + lo;
+      }
+      t[rank] = v;
+      ti[rank] = (uint8_t)e;
+    }
+    __syncwarp();
+    return;
+  }
+  int P2 = 32;
+  while (P2 < N) P2 <<= 1;
+  for (int j = N + lane; j < P2; j += 32) s[j] = INFINITY;
+  for (int j = lane; j < P2; j += 32) si[j] = (uint8_t)j;
+  __syncwarp();
+  for (int k = 2; k <= P2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int q = lane; q < (P2 >> 1); q += 32) {
+        int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));   // index with bit j cleared
+        int hi = lo | j;
+        bool asc = (lo & k) == 0;
+        float a = s[lo], b = s[hi];
+        if ((a > b) == asc) {
+          s[lo] = b; s[hi] = a;
+          uint8_t ia = si[lo]; si[lo] = si[hi]; si[hi] = ia;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int j = lane; j < N; j += 32) { t[j] = s[j]; ti[j] = si[j]; }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // a7: RangeFineSampler.get_z_vals (ray_sampler.py:264-302) + sample.  One warp per ray:
-// warp argmax (first index on ties), candidate generation, bitonic sort of <= 256 values in the
-// warp's shared-memory slice (value-exact, so identical to torch.sort's values), point generation.
+// warp argmax (first index on ties), candidate generation, warp sort of <= 256 values in the warp's
+// shared-memory slice (value-exact, so identical to torch.sort's values), point generation.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFineWarps = 4;
 
@@ -134,17 +191,19 @@ fine_sample_kernel(int n_rays, int n_coarse, int n_fine, float nearf, float far_
                    float* __restrict__ z_out, float* __restrict__ points,
                    uint8_t* __restrict__ src, float* __restrict__ points_fine) {
   __shared__ float sbuf[kFineWarps][VFNERF_MAX_SAMPLES];
-  __shared__ uint8_t sidx[kFineWarps][VFNERF_MAX_SAMPLES];   // candidate index travelling with its value (src != null)
+  __shared__ float tbuf[kFineWarps][VFNERF_MAX_SAMPLES];
+  __shared__ uint8_t sidx[kFineWarps][VFNERF_MAX_SAMPLES];
+  __shared__ uint8_t tidx[kFineWarps][VFNERF_MAX_SAMPLES];   // candidate index (coarse 0.., fine n_coarse..) per output
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int r = blockIdx.x * kFineWarps + wid;
   if (r >= n_rays) return;
   float* s = sbuf[wid];
-  uint8_t* si = sidx[wid];
+  float* t = tbuf[wid];
   const int N = n_coarse + n_fine;
   const float dx = directions[3 * (int64_t)r], dy = directions[3 * (int64_t)r + 1], dz = directions[3 * (int64_t)r + 2];
   const float ox = cam_loc[3 * (int64_t)r], oy = cam_loc[3 * (int64_t)r + 1], oz = cam_loc[3 * (int64_t)r + 2];
   if (z_override) {
-    for (int j = lane; j < N; j += 32) s[j] = z_override[(int64_t)r * N + j];
+    for (int j = lane; j < N; j += 32) t[j] = z_override[(int64_t)r * N + j];
   } else {
     // argmax of the coarse weights, first index on ties (torch.argmax)
     float best = -INFINITY;
@@ -178,10 +237,6 @@ fine_sample_kernel(int n_rays, int n_coarse, int n_fine, float nearf, float far_
       }
       s[n_coarse + i] = v;
     }
-    int P2 = 32;
-    while (P2 < N) P2 <<= 1;
-    for (int j = N + lane; j < P2; j += 32) s[j] = INFINITY;
-    for (int j = lane; j < P2; j += 32) si[j] = (uint8_t)j;
     __syncwarp();
     if (points_fine) {
       // the fine candidates alone, in candidate order: the only points of this ray the MLPs have not seen yet
@@ -194,32 +249,18 @@ fine_sample_kernel(int n_rays, int n_coarse, int n_fine, float nearf, float far_
       }
       __syncwarp();
     }
-    for (int k = 2; k <= P2; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int t = lane; t < (P2 >> 1); t += 32) {
-          int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j cleared
-          int hi = lo | j;
-          bool asc = (lo & k) == 0;
-          float a = s[lo], b = s[hi];
-          if ((a > b) == asc) {
-            s[lo] = b; s[hi] = a;
-            uint8_t ia = si[lo]; si[lo] = si[hi]; si[hi] = ia;
-          }
-        }
-        __syncwarp();
-      }
-    }
+    warp_sort_two_runs(s, sidx[wid], t, tidx[wid], n_coarse, n_fine, lane);
+    if (src) for (int j = lane; j < N; j += 32) src[(int64_t)r * N + j] = tidx[wid][j];
   }
   __syncwarp();
-  for (int j = lane; j < N; j += 32) z_out[(int64_t)r * N + j] = s[j];
-  if (src) for (int j = lane; j < N; j += 32) src[(int64_t)r * N + j] = si[j];
+  for (int j = lane; j < N; j += 32) z_out[(int64_t)r * N + j] = t[j];
   if (points) {
     float* pr = points + (int64_t)r * N * 3;
     for (int e = lane; e < 3 * N; e += 32) {
       int j = e / 3, c = e - 3 * j;
       float d = (c == 0) ? dx : (c == 1 ? dy : dz);
       float o = (c == 0) ? ox : (c == 1 ? oy : oz);
-      pr[e] = __fadd_rn(o, __fmul_rn(s[j], d));
+      pr[e] = __fadd_rn(o, __fmul_rn(t[j], d));
     }
   }
 }
@@ -264,6 +305,7 @@ pdf_sample_kernel(int n_rays, int n_bins, int n_new, const float* __restrict__ b
   __shared__ float s_cdf[kPdfWarps][VFNERF_MAX_SAMPLES];
   __shared__ float s_bin[kPdfWarps][VFNERF_MAX_SAMPLES];
   __shared__ float s_z[kPdfWarps][VFNERF_MAX_SAMPLES];
+  __shared__ uint8_t s_i[kPdfWarps][VFNERF_MAX_SAMPLES], s_ti[kPdfWarps][VFNERF_MAX_SAMPLES];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int r = blockIdx.x * kPdfWarps + wid;
   if (r >= n_rays) return;
@@ -320,23 +362,10 @@ pdf_sample_kernel(int n_rays, int n_bins, int n_new, const float* __restrict__ b
   }
   if (!kMerged) return;
   const int N = Nc + n_new;
-  int P2 = 32;
-  while (P2 < N) P2 <<= 1;
-  for (int j = N + lane; j < P2; j += 32) z[j] = INFINITY;
   __syncwarp();
-  for (int k = 2; k <= P2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = lane; t < (P2 >> 1); t += 32) {
-        int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        int hi = lo | j;
-        bool asc = (lo & k) == 0;
-        float a = z[lo], b = z[hi];
-        if ((a > b) == asc) { z[lo] = b; z[hi] = a; }
-      }
-      __syncwarp();
-    }
-  }
-  for (int j = lane; j < N; j += 32) out[(int64_t)r * N + j] = z[j];
+  float* t = s_cdf[wid];                 // the cdf is dead: its slice receives the merged, sorted values
+  warp_sort_two_runs(z, s_i[wid], t, s_ti[wid], Nc, n_new, lane);
+  for (int j = lane; j < N; j += 32) out[(int64_t)r * N + j] = t[j];
   if (points) {
     const float dx = directions[3 * (int64_t)r], dy = directions[3 * (int64_t)r + 1], dz = directions[3 * (int64_t)r + 2];
     const float ox = cam_loc[3 * (int64_t)r], oy = cam_loc[3 * (int64_t)r + 1], oz = cam_loc[3 * (int64_t)r + 2];
@@ -345,7 +374,7 @@ pdf_sample_kernel(int n_rays, int n_bins, int n_new, const float* __restrict__ b
       int j = e / 3, c = e - 3 * j;
       float d = (c == 0) ? dx : (c == 1 ? dy : dz);
       float o = (c == 0) ? ox : (c == 1 ? oy : oz);
-      pr[e] = __fadd_rn(o, __fmul_rn(z[j], d));
+      pr[e] = __fadd_rn(o, __fmul_rn(t[j], d));
     }
   }
 }
