@@ -220,7 +220,7 @@ def test_bf16_training_step_runs(built_lib):
     assert torch.isfinite(loss) and not torch.equal(before, model.vector_field_network.layers[3][0].weight.detach())
 
 
-@pytest.mark.parametrize("n_rays", [32, 601])
+@pytest.mark.parametrize("n_rays", [32, 601, 602])
 def test_bf16_backward_stage_by_stage(built_lib, n_rays):
     """Tight check of every stage of the tensor-core backward on its OWN inputs: the activation stash is read back
     (vfnerf_debug_stash_read) and each step is recomputed in float64 from the tensors the kernels actually consumed --
@@ -228,7 +228,9 @@ def test_bf16_backward_stage_by_stage(built_lib, n_rays):
     GEMM and the BatchNorm chain rule of the finalize kernel.  No ReLU-gate ambiguity enters, so the bounds are bf16
     rounding of single values (dgrad outputs) and fp32 accumulation order (parameter gradients: 2e-4).
     32 rays: the golden rays with the reference's sample positions (one tile per CTA).  601 rays: synthetic rays,
-    own sampler, an odd number of 128-point tiles and several tiles per CTA (persistent loops, barrier phases)."""
+    own sampler, an odd number of 128-point tiles and several tiles per CTA (persistent loops, barrier phases).
+    602 rays: the coarse block ends on a tile boundary, so the forward reuses the coarse sweep (two stash-writing launches,
+    301 + 301 tiles, points stashed in evaluation order; vfnerf_debug_stash_read hands the rows back in merged order)."""
     from vfnerf_b200 import ops
     case, z = U.load_golden("full_det")
     st = U.case_state(case, z)                       # the bending model: density terms are alive
@@ -399,3 +401,41 @@ def test_bf16_render_plus_supervision_accumulates(built_lib):
     for (k, p), (_, p2) in zip(model.vector_field_network.named_parameters(), m2.vector_field_network.named_parameters()):
         want = g16["vf." + k] + p2.grad.cpu()
         assert ((p.grad.cpu() - want).norm() <= 1e-4 * want.norm() + 1e-9), k
+
+
+@pytest.mark.parametrize("R", [64, 602])
+def test_bf16_backward_with_reused_coarse_sweep_matches_literal_schedule(built_lib, R):
+    """Training forward that evaluates every unique point once (coarse sweep with stash + fine candidates with stash,
+    gradients scattered into evaluation order) vs the literal schedule of vector_field_nerf.py:252-312 (VF-only coarse
+    sweep, both MLPs on all merged points).  Forward outputs are bit-identical; the per-point gradient contributions are
+    identical too, only the order in which the weight-gradient GEMMs and column sums add them differs (fp32)."""
+    case, z = U.load_golden("full_perturb")
+    st = U.case_state(case, z)
+    uv, pose, K = U.S.synthetic_rays(R, seed=0, start=3, stride=797)
+    draws = U.S.synthetic_draws(R, case["n_coarse"], case["n_fine"], seed=17)
+    N = case["n_coarse"] + case["n_fine"]
+    c_rgb, c_dep, c_nrm, c_col = (c.to(DEV) for c in _upstream(R, N))
+    res = {}
+    for literal in (False, True):
+        model = U.make_model(case, st, DEV, precision="bf16")
+        model.recompute_coarse = literal
+        out = model.render(pose.to(DEV), uv.to(DEV), K.to(DEV), 0, draws=draws)
+        model.optimizer.zero_grad()
+        ((out.coarse_rgb_values * c_rgb).sum() + (out.coarse_depth_map * c_dep).sum() +
+         (out.coarse_normals * c_nrm).sum() + (out.coarse_colors * c_col).sum()).backward()
+        g = {}
+        for prefix, net in (("vf.", model.vector_field_network), ("rn.", model.rendering_network), ("density.", model.density)):
+            for k, p in net.named_parameters():
+                g[prefix + k] = p.grad.detach().clone()
+        res[literal] = (out, g)
+    for f in ("z_vals", "points_coarse", "coarse_normals", "coarse_colors", "coarse_rgb_values", "coarse_depth_map"):
+        assert torch.equal(getattr(res[False][0], f), getattr(res[True][0], f)), f
+    worst = ("", 0.0)
+    for k, a in res[True][1].items():
+        b = res[False][1][k]
+        assert torch.isfinite(b).all(), k
+        rel = ((a - b).norm() / (a.norm() + 1e-20)).item()
+        if rel > worst[1]:
+            worst = (k, rel)
+    print(f"R={R}: worst relative L2 difference of a parameter gradient, reuse vs literal: {worst[1]:.2e} ({worst[0]})")
+    assert worst[1] <= 2e-4

@@ -213,6 +213,7 @@ struct RenderPlan {
   float *directions, *ray_dirs, *cam_loc, *z_c, *pts_c, *normals_c, *w_c, *emb, *cin, *weights;
   // bf16 inference: coarse results are reused in the merged pass, only the fine candidates are evaluated again
   int reuse_coarse;
+  float *normals_cf, *colors_cf;   // [P,3] in evaluation order: all coarse candidates of all rays, then all fine candidates
   float *colors_c, *pts_f, *normals_f, *colors_f;
   uint8_t* src;      // [R,N] candidate index (coarse 0..Nc-1, fine Nc..N-1) at every merged position
   MlpBufs vf, rn;
@@ -256,13 +257,18 @@ static int make_plan(const vfnerf_render_cfg& cfg, const vfnerf_mlp_desc& vf, co
     VFN_REQUIRE(cfg.precision == VFNERF_PREC_BF16, "precision bf16x3 is not built yet; use fp32 or bf16");
     if (int e = tc_carve(c.base, c.off, cfg.multires, cfg.multires_view, cfg.skip_layer, vf, &rn, p.tc, p.P, keep)) return e;
   }
-  // Sized for every call (the workspace query does not know about z_override); used when it applies.
-  p.reuse_coarse = cfg.precision == VFNERF_PREC_BF16 && !keep && !(cfg.flags & VFNERF_FLAG_RECOMPUTE_COARSE);
-  p.colors_c = p.pts_f = p.normals_f = p.colors_f = nullptr; p.src = nullptr;
+  // Sized for every call (the workspace query does not know about z_override); used when it applies.  With a stash
+  // (training) the two launches fill consecutive tile ranges of the same stash, so the coarse block must end on a tile
+  // boundary; the backward then runs over the points in evaluation order (render_tail_bwd scatters through `src`).
+  p.reuse_coarse = cfg.precision == VFNERF_PREC_BF16 && !(cfg.flags & VFNERF_FLAG_RECOMPUTE_COARSE) &&
+                   (!keep || p.Pc % 128 == 0);
+  p.normals_cf = p.colors_cf = p.colors_c = p.pts_f = p.normals_f = p.colors_f = nullptr; p.src = nullptr;
   if (p.reuse_coarse) {
     const int64_t Pf = (int64_t)p.R * p.Nf;
-    p.colors_c = c.f(3 * p.Pc); p.pts_f = c.f(3 * Pf); p.normals_f = c.f(3 * Pf); p.colors_f = c.f(3 * Pf);
+    p.normals_cf = c.f(3 * p.P); p.colors_cf = c.f(3 * p.P); p.pts_f = c.f(3 * Pf);
     p.src = reinterpret_cast<uint8_t*>(c.f((p.P + 3) / 4));
+    p.normals_c = p.normals_cf; p.normals_f = p.normals_cf + 3 * p.Pc;
+    p.colors_c = p.colors_cf; p.colors_f = p.colors_cf + 3 * p.Pc;
     if (have_z_override) p.reuse_coarse = 0;
   }
   p.bytes = c.off;
@@ -309,6 +315,10 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
               (long long)workspace_bytes, (long long)p.bytes);
   VFN_REQUIRE(out->points && out->normals && out->rgb && out->depth && out->z_vals && out->colors,
               "render_fwd: required output pointer is null");
+  VFN_REQUIRE(!(z_override && keep_for_backward && cfg->precision == VFNERF_PREC_BF16 &&
+                !(cfg->flags & VFNERF_FLAG_RECOMPUTE_COARSE)),
+              "render_fwd: z_override with keep_for_backward needs VFNERF_FLAG_RECOMPUTE_COARSE in cfg.flags (render_bwd "
+              "derives the order of the stash from cfg alone)");
   if (p.R == 0) return 0;
   float* weights = out->weights ? out->weights : p.weights;
   float* z_c = out->z_coarse ? out->z_coarse : p.z_c;
@@ -330,8 +340,8 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
     if (int e = tc_prepare(*vf, vf_arena, rn, rn_arena, cfg->bn_eps, p.tc, s)) return e;
     if (p.reuse_coarse) {
       // both MLPs on the coarse points now: the merged pass moves these results instead of recomputing them
-      if (int e = tc_forward(p.tc, TC_MODE_RENDER, p.pts_c, nullptr, 0, 0, p.Pc, p.ray_dirs, p.Nc, p.normals_c, 3,
-                             nullptr, 0, p.colors_c, s)) return e;
+      if (int e = tc_forward(p.tc, keep_for_backward ? TC_MODE_RENDER_STASH : TC_MODE_RENDER, p.pts_c, nullptr, 0, 0, p.Pc,
+                             p.ray_dirs, p.Nc, p.normals_c, 3, nullptr, 0, p.colors_c, s, 0)) return e;
     } else if (!z_override) {
       if (int e = tc_forward(p.tc, TC_MODE_V_ONLY, p.pts_c, nullptr, 0, 0, p.Pc, nullptr, 0, p.normals_c, 3,
                              nullptr, 0, nullptr, s)) return e;
@@ -364,8 +374,9 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
     if (p.reuse_coarse) {
       // the fine candidates are the only points not evaluated yet (the merged coarse points carry the same bits as
       // the coarse sweep's, and the fused chain is a pure per-point function): evaluate them, then merge by `src`
-      if (int e = tc_forward(p.tc, TC_MODE_RENDER, p.pts_f, nullptr, 0, 0, (int64_t)p.R * p.Nf, p.ray_dirs, p.Nf,
-                             p.normals_f, 3, nullptr, 0, p.colors_f, s)) return e;
+      if (int e = tc_forward(p.tc, keep_for_backward ? TC_MODE_RENDER_STASH : TC_MODE_RENDER, p.pts_f, nullptr, 0, 0,
+                             (int64_t)p.R * p.Nf, p.ray_dirs, p.Nf, p.normals_f, 3, nullptr, 0, p.colors_f, s,
+                             keep_for_backward ? p.Pc / 128 : 0)) return e;
       if (int e = launch_merge_samples(p.R, p.Nc, p.Nf, p.src, p.normals_c, p.normals_f, out->normals, p.colors_c,
                                        p.colors_f, out->colors, s)) return e;
     } else {
@@ -402,6 +413,15 @@ int vfnerf_render_bwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
     // weights in the workspace; ray_dirs are recomputed by the caller-visible forward only, so they must still be there
     float* dcol = p.tc.d3;
     float* dv = p.tc.d3 + 3 * p.P;
+    if (p.reuse_coarse) {
+      // the forward evaluated (and stashed) the coarse candidates, then the fine ones: the per-sample gradients are
+      // written in that order, and the per-point forward outputs are the evaluation-order buffers
+      if (int e = launch_render_tail_bwd(*cfg, p.R, p.N, density_params, out->normals, 3, p.ray_dirs, out->z_vals,
+                                         out->colors, d_rgb, d_depth, d_normals, d_colors, dcol, dv, 3, d_density, s,
+                                         p.src, p.Nc)) return e;
+      return tc_backward(p.tc, *vf, vf_arena, *rn, rn_arena, cfg->bn_eps, p.P, p.colors_cf, p.normals_cf, dcol, dv,
+                         vf_grad_arena, rn_grad_arena, s);
+    }
     if (int e = launch_render_tail_bwd(*cfg, p.R, p.N, density_params, out->normals, 3, p.ray_dirs, out->z_vals,
                                        out->colors, d_rgb, d_depth, d_normals, d_colors, dcol, dv, 3, d_density, s)) return e;
     return tc_backward(p.tc, *vf, vf_arena, *rn, rn_arena, cfg->bn_eps, p.P, out->colors, out->normals, dcol, dv,
@@ -431,7 +451,18 @@ int vfnerf_debug_stash_read(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc*
   VFN_REQUIRE(cfg->precision == VFNERF_PREC_BF16, "stash_read: only the bf16 path keeps a stash");
   RenderPlan p;
   if (int e = make_plan(*cfg, *vf, *rn, 1, workspace, p)) return e;
-  return tc_debug_stash_read(p.tc, tensor, p.P, out, n_cols, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!p.reuse_coarse || !out) return tc_debug_stash_read(p.tc, tensor, p.P, out, n_cols, s);
+  // the stash is in evaluation order (coarse candidates, then fine ones): hand the rows back in merged sample order
+  int cols = 0;
+  if (int e = tc_debug_stash_read(p.tc, tensor, p.P, nullptr, &cols, s)) return e;
+  float* tmp = nullptr;
+  VFN_CHECK_CUDA(cudaMalloc(&tmp, sizeof(float) * (size_t)p.P * cols));
+  int e = tc_debug_stash_read(p.tc, tensor, p.P, tmp, n_cols, s);
+  if (!e) e = launch_rows_to_merged_order(p.R, p.Nc, p.Nf, p.src, tmp, out, cols, s);
+  cudaStreamSynchronize(s);
+  cudaFree(tmp);
+  return e;
 }
 
 // ---- VF-only query -----------------------------------------------------------------------------

@@ -77,6 +77,8 @@ int launch_sample_pdf(int n_rays, int n_bins, int n_samples, const float* bins, 
 int launch_pdf_fine_sample(int n_rays, int n_coarse, int n_fine, const float* z_coarse, const float* w_coarse,
                            const float* u, int u_per_ray, const float* directions, const float* cam_loc, float* z,
                            float* points, cudaStream_t s);
+int launch_rows_to_merged_order(int n_rays, int n_coarse, int n_fine, const uint8_t* src, const float* in, float* out,
+                                int cols, cudaStream_t s);
 // out[r, j, :] = src[r,j] < n_coarse ? coarse[r, src, :] : fine[r, src - n_coarse, :] for two [.,3] tensor pairs
 int launch_merge_samples(int n_rays, int n_coarse, int n_fine, const uint8_t* src, const float* a_coarse,
                          const float* a_fine, float* a_out, const float* b_coarse, const float* b_fine,
@@ -95,7 +97,8 @@ int launch_render_tail_bwd(const vfnerf_render_cfg& cfg, int n_rays, int n_sampl
                            const float* ray_dirs, const float* z, const float* colors,
                            const float* d_rgb, const float* d_depth, const float* d_normals_up,
                            const float* d_colors_up, float* d_colors, float* d_normals,
-                           int64_t d_normals_ld, float* d_density, cudaStream_t s);
+                           int64_t d_normals_ld, float* d_density, cudaStream_t s,
+                           const uint8_t* src = nullptr, int n_coarse = 0);
 
 // mlp_simt.cu
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_SIGMOID = 3 };

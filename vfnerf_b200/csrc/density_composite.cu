@@ -215,6 +215,16 @@ int launch_composite(int n_rays, int n_samples, const float* weights, const floa
 //   d_colors [R*N,3] = w_j * d_rgb (+ upstream),   d_normals [R,N,ld] = dL/dv_j (+ upstream),
 //   d_density[3] += d(beta, scale, mean)   (atomicAdd of one value per ray; caller zeroes it).
 // ---------------------------------------------------------------------------------------------
+// Row that receives the gradient of merged sample idx = r*N + j.  Without a map: idx itself.  With the candidate map of
+// the fine sampler (src[idx] = k: coarse candidate k < n_coarse, fine candidate k - n_coarse otherwise) the rows follow the
+// order in which the forward evaluated the points: all coarse candidates of all rays, then all fine candidates.
+__device__ __forceinline__ int64_t out_row(const uint8_t* __restrict__ src, int64_t idx, int r, int n_rays, int N, int n_coarse) {
+  if (!src) return idx;
+  const int k = src[idx];
+  return k < n_coarse ? (int64_t)r * n_coarse + k
+                      : (int64_t)n_rays * n_coarse + (int64_t)r * (N - n_coarse) + (k - n_coarse);
+}
+
 template <int KP>
 __global__ void __launch_bounds__(kRayWarps * 32)
 render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __restrict__ dparams,
@@ -223,7 +233,7 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
                        const float* __restrict__ d_rgb, const float* __restrict__ d_depth,
                        const float* __restrict__ d_normals_up, const float* __restrict__ d_colors_up,
                        float* __restrict__ d_colors, float* __restrict__ d_normals, int64_t dn_ld,
-                       float* __restrict__ d_density) {
+                       float* __restrict__ d_density, const uint8_t* __restrict__ src, int n_coarse) {
   __shared__ __align__(16) float s_u[kRayWarps][kUS * VFNERF_MAX_SAMPLES];
   __shared__ float s_inv[kRayWarps][VFNERF_MAX_SAMPLES];
   __shared__ float s_dc[kRayWarps][VFNERF_MAX_SAMPLES];
@@ -287,7 +297,8 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
       dw[i] = g0 * c0 + g1 * c1 + g2 * c2 + gd * zr[j];
       float o0 = w * g0, o1 = w * g1, o2 = w * g2;
       if (d_colors_up) { o0 += d_colors_up[3 * idx]; o1 += d_colors_up[3 * idx + 1]; o2 += d_colors_up[3 * idx + 2]; }
-      d_colors[3 * idx] = o0; d_colors[3 * idx + 1] = o1; d_colors[3 * idx + 2] = o2;
+      const int64_t od = out_row(src, idx, r, n_rays, N, n_coarse);
+      d_colors[3 * od] = o0; d_colors[3 * od + 1] = o1; d_colors[3 * od + 2] = o2;
       dot_dw_w += dw[i] * w;
     }
   }
@@ -356,7 +367,7 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
     gx *= iv; gy *= iv; gz *= iv;
     const int64_t idx = (int64_t)r * N + k;
     if (d_normals_up) { gx += d_normals_up[3 * idx]; gy += d_normals_up[3 * idx + 1]; gz += d_normals_up[3 * idx + 2]; }
-    float* o = d_normals + idx * dn_ld;
+    float* o = d_normals + out_row(src, idx, r, n_rays, N, n_coarse) * dn_ld;
     o[0] = gx; o[1] = gy; o[2] = gz;
   }
 
@@ -378,13 +389,13 @@ int launch_render_tail_bwd(const vfnerf_render_cfg& cfg, int n_rays, int n_sampl
                            const float* ray_dirs, const float* z, const float* colors,
                            const float* d_rgb, const float* d_depth, const float* d_normals_up,
                            const float* d_colors_up, float* d_colors, float* d_normals,
-                           int64_t d_normals_ld, float* d_density, cudaStream_t s) {
+                           int64_t d_normals_ld, float* d_density, cudaStream_t s, const uint8_t* src, int n_coarse) {
   if (n_rays <= 0) return 0;
   VFN_REQUIRE(n_samples >= 2 && n_samples <= VFNERF_MAX_SAMPLES, "render_tail_bwd: n_samples=%d out of range", n_samples);
   const dim3 grid((n_rays + kRayWarps - 1) / kRayWarps), block(kRayWarps * 32);
 #define VFN_TB(KP) render_tail_bwd_kernel<KP><<<grid, block, 0, s>>>( \
       cfg, n_rays, n_samples, density_params, normals, normals_ld, ray_dirs, z, colors, d_rgb, d_depth, \
-      d_normals_up, d_colors_up, d_colors, d_normals, d_normals_ld, d_density)
+      d_normals_up, d_colors_up, d_colors, d_normals, d_normals_ld, d_density, src, n_coarse)
   if (n_samples <= 64) VFN_TB(2); else if (n_samples <= 128) VFN_TB(4); else VFN_TB(kMaxPerLane);
 #undef VFN_TB
   VFN_LAUNCH_CHECK();

@@ -438,4 +438,28 @@ int launch_merge_samples(int n_rays, int n_coarse, int n_fine, const uint8_t* sr
   return 0;
 }
 
+// test support (vfnerf_debug_stash_read): rows in evaluation order -> rows in merged sample order
+__global__ void rows_to_merged_order_kernel(int64_t total, int n_rays, int n_coarse, int n_fine, int cols,
+                                            const uint8_t* __restrict__ src, const float* __restrict__ in,
+                                            float* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t pt = e / cols;
+  const int c = (int)(e - pt * cols);
+  const int N = n_coarse + n_fine;
+  const int64_t r = pt / N;
+  const int k = src[pt];
+  const int64_t from = k < n_coarse ? r * n_coarse + k : (int64_t)n_rays * n_coarse + r * n_fine + (k - n_coarse);
+  out[e] = in[from * cols + c];
+}
+
+int launch_rows_to_merged_order(int n_rays, int n_coarse, int n_fine, const uint8_t* src, const float* in, float* out,
+                                int cols, cudaStream_t s) {
+  const int64_t total = (int64_t)n_rays * (n_coarse + n_fine) * cols;
+  if (total <= 0) return 0;
+  rows_to_merged_order_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(total, n_rays, n_coarse, n_fine, cols, src, in, out);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace vfn

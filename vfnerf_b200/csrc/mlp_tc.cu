@@ -1134,7 +1134,7 @@ static int g_num_sms = 0;
 
 int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec* grid, int grid_res,
                int64_t grid_i0, int64_t n, const float* ray_dirs, int samples_per_ray, float* out_v,
-               int64_t v_ld, float* out_feat, int64_t feat_ld, float* colors, cudaStream_t s) {
+               int64_t v_ld, float* out_feat, int64_t feat_ld, float* colors, cudaStream_t s, int64_t stash_tile0) {
   if (n <= 0) return 0;
   TcParams p{};
   const bool is_bwd = mode == TC_MODE_BWD || mode == TC_MODE_VF_BWD;
@@ -1146,6 +1146,14 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   if (stashing || is_bwd) {
     VFN_REQUIRE(plan.stash_buf, "tc_forward: this mode needs the training workspace (keep_for_backward)");
     p.stash = plan.stash_buf; p.sinfo = plan.stash;
+    if (stash_tile0) {
+      // this launch fills tiles [stash_tile0, ...) of every tensor: the kernel numbers its tiles from 0, so shift the bases
+      VFN_REQUIRE(stashing, "tc_forward: stash_tile0 only applies to the forward *_STASH modes");
+      for (int t = 0; t < p.sinfo.n_tensors; ++t) {
+        p.sinfo.off[t] += stash_tile0 * (long long)p.sinfo.slabs[t] * (kTileM * 16);
+        p.sinfo.gate_off[t] += stash_tile0 * 4ll * kTileM * 8;
+      }
+    }
   }
   if (is_bwd) { p.dcol_pre = points; p.dv_pre = ray_dirs; }
   p.points = points; p.use_grid = grid ? 1 : 0;

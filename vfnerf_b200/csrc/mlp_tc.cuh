@@ -108,7 +108,8 @@ int tc_prepare(const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_ml
 // (VF_FULL); colors [n,3] (RENDER).
 int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec* grid, int grid_res,
                int64_t grid_i0, int64_t n, const float* ray_dirs, int samples_per_ray, float* out_v,
-               int64_t v_ld, float* out_feat, int64_t feat_ld, float* colors, cudaStream_t s);
+               int64_t v_ld, float* out_feat, int64_t feat_ld, float* colors, cudaStream_t s,
+               int64_t stash_tile0 = 0);   // *_STASH modes: first 128-point tile of the stash this launch writes
 
 // Training backward of the RENDER program on the tensor cores.  d_colors [n,3] = dL/d colours, d_v [n,3] = dL/d VF
 // vectors (both fp32, already including every upstream term); colors / normals are the forward outputs.  Writes

@@ -166,6 +166,9 @@ class _Render(torch.autograd.Function):
         dev = call.uv.device
         R, N = cfg.n_rays, cfg.n_coarse + cfg.n_fine
         need_bwd = call.need_bwd
+        if call.z_override is not None:
+            # a prescribed z has no coarse sweep to reuse; render_bwd derives the stash order from cfg alone
+            cfg.flags |= _lib.FLAG_RECOMPUTE_COARSE
         if need_bwd and cfg.precision not in (_lib.PREC_FP32, _lib.PREC_BF16):
             raise RuntimeError("training (backward) runs on precision 'fp32' or 'bf16'")
         nbytes = L.vfnerf_render_workspace_bytes(C.byref(cfg), C.byref(vf_ar.desc), C.byref(rn_ar.desc), int(need_bwd))
