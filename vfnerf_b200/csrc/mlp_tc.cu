@@ -749,7 +749,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                   }
                 }
                 if (hand_on) store_slab_u(s_act, (cb >> 3) + sl, row, o[0], o[1], o[2], o[3]);
-                if (t_ok) *stash_unit(p, st.stash_out, tile, (cb >> 3) + sl, row) = make_uint4(o[0], o[1], o[2], o[3]);
+                if (t_ok && !(p.dbg & 8)) *stash_unit(p, st.stash_out, tile, (cb >> 3) + sl, row) = make_uint4(o[0], o[1], o[2], o[3]);
               }
             }
             if (hand_on) {
@@ -796,11 +796,14 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                 for (int sl = 0; sl < 4; ++sl)
                   store_slab_u(s_act, (c0 >> 3) + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
                 uint32_t gate_lo = 0, gate_hi = 0;
-                if (st_on) {
+                const bool st_act = st_on && !(p.dbg & 8), st_gate = st_on && !(p.dbg & 16);   // experiment switches
+                if (st_act) {
 #pragma unroll
                   for (int sl = 0; sl < 4; ++sl)
                     *stash_unit(p, st.stash_out, tile, (c0 >> 3) + sl, row) =
                         make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+                }
+                if (st_gate) {
                   // gate bit e = "pre-activation of column c0 + e is not negative": one funnel shift per element
                   // collects the fp32 sign bits (an exact zero passes the gate; its gradient contribution is zero or
                   // belongs to a padded channel)
@@ -817,18 +820,20 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                   for (int sl = 0; sl < 4; ++sl)
                     store_slab_u(s_act, (c0 >> 3) + 4 + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
-                  if (st_on) {
+                  if (st_act) {
 #pragma unroll
                     for (int sl = 0; sl < 4; ++sl)
                       *stash_unit(p, st.stash_out, tile, (c0 >> 3) + 4 + sl, row) =
                           make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+                  }
+                  if (st_gate) {
 #pragma unroll
                     for (int j = 31; j >= 0; --j) gate_hi = __funnelshift_l(vb[j], gate_hi, 1);
                     gate_hi = ~gate_hi;
                   }
                 }
                 // the backward gates on the sign only: 8 bytes per row and 64-column group instead of 128
-                if (st_on && !feat) *gate_unit(p, st.stash_out, tile, bg, row) = make_uint2(gate_lo, gate_hi);
+                if (st_gate && !feat) *gate_unit(p, st.stash_out, tile, bg, row) = make_uint2(gate_lo, gate_hi);
               }
               TCK(t_math);
               fence_proxy_async_smem();
