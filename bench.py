@@ -505,6 +505,14 @@ def main():
                                                             dep_o.data_ptr(), sp),
                                  Rh * (20 * N + 16)),
         }
+        # marching-cubes preprocessing of a 256^3 grid (count pass: 12 B/point in, 1 B/cell out)
+        Ng = 256
+        from vfnerf_b200 import mc_utils as vmc
+        pred_g = U.S.synthetic_vector_grid(Ng, seed=1).to(dev)
+        keep_g = torch.empty(Ng ** 3, dtype=torch.uint8, device=dev)
+        cnt_g = torch.zeros((Ng ** 3 + 255) // 256, dtype=torch.int32, device=dev)
+        kernels["mc_count_kernel"] = (lambda: L.vfnerf_mc_count(pred_g.data_ptr(), Ng, keep_g.data_ptr(), cnt_g.data_ptr(), None,
+                                                                None, sp), Ng ** 3 * 13)
         hbm_peak = peaks()[0]["hbm_gbs"]
         hbm = {"rays": Rh, "n_coarse": Nc, "n_fine": Nf, "peak_gbs": hbm_peak, "kernels": {}}
         for name, (fn, nbytes) in kernels.items():

@@ -207,6 +207,21 @@ int vfnerf_vf_grid_query(const vfnerf_mlp_desc* vf, const float* vf_arena, int m
                          const float* centroid3_host, float voxel, float* out,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- marching-cubes preprocessing of the dense grid --------------------- */
+/* evaluation/methods.py:209-278 (default flags) = mc_utils.extract_divergence (:34-85) + unify_direction (:107-166) +
+ * make_comb_format (:169-223) + the block-ordered compaction, fused per cell.  pred [res^3,3] is the grid query's
+ * output (x index slowest).  Cells are visited in the reference's order: 2x2x2 blocks in C order, `inc` order inside.
+ *   vfnerf_mc_count: keep [8*(res/2)^3] = 1 for cells whose corner pairs differ; cta_counts [ceil(n/256)] kept cells per
+ *     256-cell CTA.  Optional dense outputs in grid order for tests: div_raw [res^3] (raw divergence of interior cells,
+ *     caller zero-fills), choice [res^3] (bit s = side of corner s).
+ *   vfnerf_mc_emit: cta_offsets = inclusive scan of cta_counts (int64); writes cells [M,3], comb [M,28], udf [M,28,2]
+ *     -- exactly the arrays contrastive_marching_cubes receives (methods.py:272-283) before their flattening reshape. */
+#define VFNERF_MC_CTA 256
+int vfnerf_mc_count(const float* pred, int resolution, uint8_t* keep, int32_t* cta_counts, float* div_raw,
+                    uint8_t* choice, void* stream);
+int vfnerf_mc_emit(const float* pred, int resolution, const uint8_t* keep, const int64_t* cta_offsets,
+                   int32_t* cells, float* comb, float* udf, void* stream);
+
 /* ---- stage entry points (one per SURVEY.md §8(a) row; used by the parity tests) ------------- */
 /* a1: get_ray_directions_and_cam_location, utils/rendering.py:12-60 */
 int vfnerf_ray_geometry(int n_rays, int pose_is_quat, const float* uv, const float* pose,

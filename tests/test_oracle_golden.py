@@ -102,3 +102,20 @@ def test_pdf_sampler_oracle_matches_reference_golden(tag):
     mid = .5 * (g["z_c"][..., 1:] + g["z_c"][..., :-1])
     assert torch.equal(U.O.sample_pdf(mid, g["w_c"][..., 1:-1], g["u"]), g["ref_samples"])
     assert g["ref_z"].shape[1] == g["z_c"].shape[1] + g["u"].shape[-1]
+
+
+@pytest.mark.parametrize("tag,N", [("n24", 24), ("n33", 33)])
+def test_mc_oracle_matches_reference_golden(tag, N):
+    """extract_divergence / unify_direction / make_comb_format / block-ordered compaction (evaluation/utils/mc_utils.py,
+    evaluation/methods.py:209-278): the per-cell oracle restatement equals the live reference's outputs exactly
+    (fixture from tests/golden/make_golden_mc.py)."""
+    import os
+    from oracle import mc_oracle as MO
+    z = np.load(os.path.join(U.GOLDEN_DIR, "mc_preprocess.npz"))
+    g = {k: torch.from_numpy(z[f"{tag}.{k}"]) for k in ("pred", "div", "choice", "cells", "comb", "udf")}
+    div = MO.extract_divergence(g["pred"], N)
+    assert torch.equal(div, g["div"])
+    assert torch.equal(MO.unify_direction(div, g["pred"], N).to(torch.uint8), g["choice"])
+    cells, comb, udf = MO.mc_preprocess(g["pred"], N)
+    assert torch.equal(cells.int(), g["cells"]) and torch.equal(comb, g["comb"]) and torch.equal(udf, g["udf"])
+    assert g["cells"].shape[0] > 1000

@@ -660,6 +660,16 @@ int vfnerf_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, doubl
                             reinterpret_cast<cudaStream_t>(stream));
 }
 
+int vfnerf_mc_count(const float* pred, int resolution, uint8_t* keep, int32_t* cta_counts, float* div_raw,
+                    uint8_t* choice, void* stream) {
+  return launch_mc_count(pred, resolution, keep, cta_counts, div_raw, choice, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vfnerf_mc_emit(const float* pred, int resolution, const uint8_t* keep, const int64_t* cta_offsets, int32_t* cells,
+                   float* comb, float* udf, void* stream) {
+  return launch_mc_emit(pred, resolution, keep, cta_offsets, cells, comb, udf, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int vfnerf_sample_pdf(int n_rays, int n_bins, int n_samples, const float* bins, const float* weights, const float* u,
                       int u_per_ray, float* samples, void* stream) {
   return launch_sample_pdf(n_rays, n_bins, n_samples, bins, weights, u, u_per_ray, samples,

@@ -181,3 +181,18 @@ def synthetic_draws(n_rays: int, n_coarse: int, n_fine: int, seed: int = 1234
     U2 = torch.from_numpy(rng.random((n_rays, n_fine), dtype=np.float32))
     U3 = torch.from_numpy(rng.random((n_rays, n_fine), dtype=np.float32))
     return U1, U2, U3
+
+
+def synthetic_vector_grid(N: int, seed: int = 0, scale: float = 1.0) -> torch.Tensor:
+    """[N^3, 3] vector field on the marching-cubes grid of evaluation/methods.py:194-208 (x index slowest): vectors
+    pointing at the nearer of a sphere (radius 0.6) and a plane (z = -0.8), tanh-squashed like the VF net's output,
+    plus seeded noise -- it flips direction across both surfaces, so the divergence test fires on two sheets of cells."""
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.arange(N ** 3)
+    p = torch.stack([((idx // N) // N) % N, (idx // N) % N, idx % N], dim=1).float() * (2.0 * scale / (N - 1)) - scale
+    d = p.norm(dim=1, keepdim=True)
+    to_sphere = (0.6 - d) * p / d.clamp(min=1e-6)
+    to_plane = torch.zeros_like(p)
+    to_plane[:, 2] = -0.8 - p[:, 2]
+    v = torch.where(to_sphere.norm(dim=1, keepdim=True) < to_plane.norm(dim=1, keepdim=True), to_sphere, to_plane)
+    return torch.tanh(3.0 * v) + 0.02 * torch.randn(N ** 3, 3, generator=g)
