@@ -55,7 +55,7 @@ def parse():
 def ncu_traffic(points_per_launch):
     """dram__bytes_read.sum + dram__bytes_write.sum of the fused RENDER launch from the committed `ncu --set full` capture
     (profiles/run_render_points.py, same points per launch); None if the capture does not match this launch size."""
-    path = os.path.join(ROOT, "profiles", "r01_prof_render_v4_raw.csv")
+    path = os.path.join(ROOT, "profiles", "r01_prof_render_final_raw.csv")
     if points_per_launch != 65536 * (N_COARSE + N_FINE) or not os.path.exists(path):
         return None, None
     import csv
@@ -66,7 +66,7 @@ def ncu_traffic(points_per_launch):
     for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         i = hdr.index(name)
         tot += float(vals[i]) * scale[units[i]]
-    return tot, "profiles/r01_prof_render_v4_raw.csv (ncu --set full, one launch of the same size)"
+    return tot, "profiles/r01_prof_render_final_raw.csv (ncu --set full, one launch of the same size)"
 
 
 def peaks():
