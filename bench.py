@@ -307,9 +307,14 @@ def main():
             return world * R / (ms2.item() * 1e-3), h2d, d2h
         v_big, h2d, d2h = time_e2e(chunk)
         v_1k, _, _ = time_e2e(1024)
+        model.draws_on_device = True
+        v_1k_dev, _, _ = time_e2e(1024)
+        model.draws_on_device = False
         e2e = {"value": v_big, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "chunk": chunk,
                "chunk_1024": {"value": v_1k, "unit": "rays/s", "note": "the reference's evaluation chunk size; bounded by "
-                              "Python launch overhead per render() call, not by the GPU"}}
+                              "Python launch overhead per render() call, not by the GPU",
+                              "draws_on_device": {"value": v_1k_dev, "unit": "rays/s", "note": "opt-in: uniform draws made on "
+                                                  "the device instead of the reference's CPU generator + H2D copy"}}}
 
     # ---- training step (BASELINE config 3): 1024-ray batch, render -> VFLoss terms -> backward -> clip -> Adam,
     # the sequence of train/vector_field_nerf_train.py:177-260.  Timed on the bench precision (bf16: fused tcgen05

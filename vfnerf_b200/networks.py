@@ -29,6 +29,7 @@ class ParamArena:
         self.desc = _lib.MlpDesc()
         self.slots: List[Tuple[str, torch.Tensor, int]] = []   # (kind, tensor, offset)
         self.grad_flat: Optional[torch.Tensor] = None           # flat gradient arena (optim.ArenaAdam), else None
+        self.dirty = False                                      # set by the owner's _apply / load_state_dict overrides
         self.rebuild()
 
     def _tensors(self):
@@ -99,6 +100,14 @@ class ParamArena:
         ``load_state_dict(assign=True)``, ...).  Looks the tensors up afresh: ``Module._apply`` swaps
         buffer objects."""
         base = self.flat.data_ptr()
+        # fast path (this runs several times per render() call): storage can only move through Module._apply
+        # (.to(), .cuda(), .float() ...) or load_state_dict(assign=True), both of which the owning module reports by
+        # setting `dirty`; a spot check of the first and last slot catches manual `.data` swaps
+        if not self.dirty:
+            t0, tl, ol = self.slots[0][1], self.slots[-1][1], self.slots[-1][2]
+            if t0.data_ptr() == base and tl.data_ptr() == base + 4 * ol:
+                return self.flat
+        self.dirty = False
         off = 0
         for _, _, t in self._tensors():
             if t.data_ptr() != base + 4 * off or t.dtype != torch.float32:
@@ -114,6 +123,22 @@ class ParamArena:
         """Views of a gradient arena matching ``params()`` one to one."""
         return [grad_flat[off:off + t.numel()].view(t.shape)
                 for _, t, off in self.slots if isinstance(t, nn.Parameter)]
+
+
+class _ArenaOwner:
+    """Mixin of the two network modules: tells the arena when parameter / buffer storage may have been replaced."""
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if getattr(self, "_arena", None) is not None:
+            self._arena.dirty = True
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        if getattr(self, "_arena", None) is not None:
+            self._arena.dirty = True
+        return out
 
 
 def _make_layers(dims: Sequence[Tuple[int, int]], batch_norm: bool, weight_norm: bool, xavier: bool,
@@ -135,7 +160,7 @@ def _make_layers(dims: Sequence[Tuple[int, int]], batch_norm: bool, weight_norm:
     return layers
 
 
-class VectorFieldNetwork(nn.Module):
+class VectorFieldNetwork(_ArenaOwner, nn.Module):
     """Drop-in for models/vector_field/vector_field_network.py:14-208 (eval-mode forward).
 
     ``forward(points[P,3]) -> [P, 3 + feature_vector_dims]`` = tanh([v, feat]).  Training mode (BatchNorm
@@ -200,7 +225,7 @@ class VectorFieldNetwork(nn.Module):
         return vf_query(self, points)
 
 
-class RenderingNetwork(nn.Module):
+class RenderingNetwork(_ArenaOwner, nn.Module):
     """Parameter owner for models/vector_field/rendering_network.py:13-108 (mode 'idr')."""
 
     def __init__(self, config) -> None:
