@@ -128,3 +128,37 @@ def test_cpu_generator_draws_are_reproducible(built_lib):
     with torch.no_grad():
         b = model.render(pose, uv, K, 0)
     assert torch.equal(a.z_vals, b.z_vals) and torch.equal(a.coarse_rgb_values, b.coarse_rgb_values)
+
+
+@pytest.mark.parametrize("precision,R,chunk", [("bf16", 65536, 1024), ("fp32", 4096, 1024)])
+def test_full_size_chunk_invariance_and_properties(built_lib, precision, R, chunk):
+    """BASELINE.json's full sizes (config 2: Replica camera, 64+64 samples, shipped nets) through size-independent
+    properties: one 65 536-ray call (8.4 M sample points, the chunk bench.py times) must equal, bit for bit, the same
+    rays rendered in the reference's 1024-ray chunks (evaluation/methods.py:516-530) -- rays are independent and the
+    fused chain is a pure per-point function, whatever tile / CTA / launch a point lands in.  Plus: merged z sorted,
+    weights a sub-probability vector, rgb in [0,1], depth inside [near, far + range]."""
+    case, z = U.load_golden("full_det")
+    model = U.make_model(case, U.case_state(case, z), DEV, precision=precision)
+    model.return_ray_dirs = False
+    pose1, K1 = U.S.synthetic_camera(seed=0, height=680, width=1200, focal=600.0)
+    uv = U.S.pixel_grid(680, 1200)[100 * 1200:100 * 1200 + R].contiguous().to(DEV)
+    pose, K = pose1.repeat(R, 1, 1).to(DEV), K1.repeat(R, 1, 1).to(DEV)
+    U3 = torch.rand(R, case["n_fine"], generator=torch.Generator().manual_seed(3)).to(DEV)
+    fields = ("z_vals", "points_coarse", "coarse_normals", "coarse_colors", "coarse_rgb_values", "coarse_depth_map")
+    with torch.no_grad():
+        whole = model.render(pose, uv, K, 0, draws=(None, None, U3))
+        w_whole = model.last_extras["weights"]
+        parts, w_parts = [], []
+        for a in range(0, R, chunk):
+            parts.append(model.render(pose[a:a + chunk], uv[a:a + chunk], K[a:a + chunk], 0, draws=(None, None, U3[a:a + chunk])))
+            w_parts.append(model.last_extras["weights"])
+    N = case["n_coarse"] + case["n_fine"]
+    for f in fields:
+        assert torch.equal(torch.cat([getattr(p, f) for p in parts]), getattr(whole, f)), f
+    assert torch.equal(torch.cat(w_parts), w_whole)
+    assert (whole.z_vals[:, 1:] >= whole.z_vals[:, :-1]).all() and whole.z_vals.shape == (R, N)
+    assert (w_whole >= 0).all() and (w_whole.sum(1) <= 1 + 1e-5).all()
+    assert (whole.coarse_rgb_values >= 0).all() and (whole.coarse_rgb_values <= 1).all()
+    assert (whole.coarse_depth_map >= 0).all() and (whole.coarse_depth_map <= case["far"] + case["fine_range"] + 1e-4).all()
+    assert torch.isfinite(whole.coarse_normals).all() and (whole.coarse_normals.abs() <= 1).all()
+    assert w_whole.sum().item() > 0          # the synthetic scene is not empty
