@@ -19,8 +19,10 @@ using namespace tc;
 constexpr int kTileM = 128;
 constexpr int kGLd = 320;                          // columns of one layer's G block: [0,256) main input, [256,304) side input
 constexpr int kGSlot = 256 * kGLd + 256;           // + 256 column sums
-constexpr int kWgSlotBytes = 65536;                // one 128-point tile of a 256-channel tensor
-constexpr int kWgSlots = 3;
+constexpr int kWgDGran = 32768;                    // dY granule: 16 slabs = 128 channels of a 128-point tile = one M = 128 half
+constexpr int kWgDSlots = 3;
+constexpr int kWgXBytes = 65536;                   // X slot: one 128-point tile of a 256-channel tensor
+constexpr int kWgXSlots = 2;
 constexpr int kWgThreads = 192;                    // warp 0: loader lane, warp 1: MMA lane, warps 2..5: final epilogue
 
 struct WgTask {
@@ -40,12 +42,21 @@ struct WgParams {
   WgTask t[24];
 };
 
+// Shared memory: a ring of three 32 KB dY granules and a ring of two 64 KB X tiles.  The kernel streams the stash once and
+// is bound by HBM latency x bytes in flight: with the former ring of three 64 KB slots only ONE slot could be loading while
+// a tile (two slots) was being consumed -- 64 KB in flight per SM, 4.6 TB/s.  Now everything tile t+1 needs first (X and
+// the first dY half, 96 KB) is in flight while tile t is in the tensor core, and the second dY half follows as soon as
+// the first half of tile t has been consumed.
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgSlots * kWgSlotBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kWgSlots;
-  uint64_t* done = bars + 2 * kWgSlots;
+  uint8_t* dring = smem;
+  uint8_t* xring = smem + kWgDSlots * kWgDGran;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xring + kWgXSlots * kWgXBytes);
+  uint64_t* dfull = bars;
+  uint64_t* dempty = dfull + kWgDSlots;
+  uint64_t* xfull = dempty + kWgDSlots;
+  uint64_t* xempty = xfull + kWgXSlots;
+  uint64_t* done = xempty + kWgXSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // which task / tile range
@@ -56,9 +67,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const long long per = (p.n_tiles + T.nctas - 1) / T.nctas;
   const long long t0 = (long long)local * per, t1 = min(p.n_tiles, t0 + per);
   if (threadIdx.x == 0) {
-    // a ring slot is free when the MMAs that read it have completed and, for tasks that also reduce dY over the points,
-    // when the four reduction warps are done with it
-    for (int i = 0; i < kWgSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], T.colsum_off >= 0 ? 5 : 1); }
+    // a dY granule is free when the MMAs that read it have completed and, for tasks that also reduce dY over the
+    // points, when the four reduction warps are done with it
+    for (int i = 0; i < kWgDSlots; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dempty[i], T.colsum_off >= 0 ? 5 : 1); }
+    for (int i = 0; i < kWgXSlots; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -70,97 +82,110 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const int N = 8 * T.n_xslabs;
   const int halves = (T.d_slabs + 15) / 16;
   if (warp == 0 && lane == 0) {
-    // loader: per tile, slot k <- dY tile, slot k+1 <- the used slabs of the X tile
-    int slot = 0, phase = 0;
-    const uint32_t d_bytes = (uint32_t)T.d_slabs * 2048u, x_bytes = (uint32_t)T.n_xslabs * 2048u;
+    // loader: per tile dY half 0, the used slabs of X, dY half 1
+    int ds = 0, dph = 0, xs = 0, xph = 0;
+    const uint32_t x_bytes = (uint32_t)T.n_xslabs * 2048u;
     for (long long t = t0; t < t1; ++t) {
-      mbar_wait(&empty[slot], phase ^ 1);
-      mbar_arrive_expect_tx(&full[slot], d_bytes);
-      bulk_g2s(smem + slot * kWgSlotBytes, p.stash + T.d_off + t * (long long)T.d_slabs * 2048, d_bytes, &full[slot]);
-      if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
-      mbar_wait(&empty[slot], phase ^ 1);
-      mbar_arrive_expect_tx(&full[slot], x_bytes);
-      bulk_g2s(smem + slot * kWgSlotBytes, p.stash + T.x_off + (t * (long long)T.x_slabs + T.x_slab0) * 2048, x_bytes, &full[slot]);
-      if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
+      const uint8_t* dsrc = p.stash + T.d_off + t * (long long)T.d_slabs * 2048;
+      for (int h = 0; h < halves; ++h) {
+        const uint32_t bytes = (uint32_t)min(16, T.d_slabs - 16 * h) * 2048u;
+        mbar_wait(&dempty[ds], dph ^ 1);
+        mbar_arrive_expect_tx(&dfull[ds], bytes);
+        bulk_g2s(dring + ds * kWgDGran, dsrc + (long long)h * kWgDGran, bytes, &dfull[ds]);
+        if (++ds == kWgDSlots) { ds = 0; dph ^= 1; }
+        if (h == 0) {
+          mbar_wait(&xempty[xs], xph ^ 1);
+          mbar_arrive_expect_tx(&xfull[xs], x_bytes);
+          bulk_g2s(xring + xs * kWgXBytes, p.stash + T.x_off + (t * (long long)T.x_slabs + T.x_slab0) * 2048, x_bytes, &xfull[xs]);
+          if (++xs == kWgXSlots) { xs = 0; xph ^= 1; }
+        }
+      }
     }
   } else if (warp == 1 && lane == 0) {
     // MMA issuer: G[half] (128 channels x N) += dY_tile[half]^T (channels x points) * X_tile (points x N)
     // both operands MN-major: 16-byte unit = 8 consecutive channels of one point, units of consecutive points are
     // 16 bytes apart (LBO field = 128 B per group of 8 points), channel groups are one slab (2048 B) apart (SBO field)
-    int slot = 0, phase = 0;
+    int ds = 0, dph = 0, xs = 0, xph = 0;
     const uint32_t idesc = make_idesc_bf16(128, N) | (1u << 15) | (1u << 16);
     const uint32_t desc_hi = (2048u >> 4) | (1u << 14);
     const uint32_t lo_hi = (128u >> 4) << 16;
-    const uint32_t base = smem_u32(smem);
+    const uint32_t dbase = smem_u32(dring), xbase = smem_u32(xring);
     uint32_t acc_started = 0;
     for (long long t = t0; t < t1; ++t) {
-      const int sd = slot;
-      mbar_wait(&full[slot], phase);
-      if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
-      const int sx = slot;
-      mbar_wait(&full[slot], phase);
-      if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
-      tc_fence_after_sync();
-      const uint32_t a0 = (((base + sd * kWgSlotBytes) >> 4) & 0x3FFF) | lo_hi;
-      const uint32_t b0 = (((base + sx * kWgSlotBytes) >> 4) & 0x3FFF) | lo_hi;
+      const int sx = xs;
+      mbar_wait(&xfull[xs], xph);
+      if (++xs == kWgXSlots) { xs = 0; xph ^= 1; }
+      const uint32_t b0 = (((xbase + sx * kWgXBytes) >> 4) & 0x3FFF) | lo_hi;
       for (int h = 0; h < halves; ++h) {
+        const int sd = ds;
+        mbar_wait(&dfull[ds], dph);
+        if (++ds == kWgDSlots) { ds = 0; dph ^= 1; }
+        tc_fence_after_sync();
+        const uint32_t a0 = (((dbase + sd * kWgDGran) >> 4) & 0x3FFF) | lo_hi;
 #pragma unroll
         for (uint32_t k = 0; k < 8; ++k)      // 16 points per MMA: start address advances 16 points x 16 B
-          umma_bf16_split(tmem + h * 256, a0 + (uint32_t)h * (16u * 2048u >> 4) + k * 16u, desc_hi, b0 + k * 16u, desc_hi, idesc,
-                          acc_started | k);
+          umma_bf16_split(tmem + h * 256, a0 + k * 16u, desc_hi, b0 + k * 16u, desc_hi, idesc, acc_started | k);
+        umma_commit(&dempty[sd]);
       }
       acc_started = 1;
-      umma_commit(&empty[sd]);
-      umma_commit(&empty[sx]);
+      umma_commit(&xempty[sx]);
     }
     umma_commit(done);
   } else if (warp >= 2) {
+    const int w = warp - 2;
     if (T.colsum_off >= 0) {
-      // column sums of dY straight from the shared-memory tile the tensor core is reading: warp w owns slabs 8w..8w+7,
-      // lane l owns points l, l+32, l+64, l+96 (each LDS.128 of a warp covers 512 contiguous bytes); partial sums stay
-      // in registers across this CTA's tiles.  Rows past the end of the batch are exact zeros in the gradient stash.
-      float acc[8][8];
+      // column sums of dY straight from the shared-memory granules the tensor core is reading.  Every warp visits EVERY
+      // granule in ring order (a warp that skipped uses of a slot could mistake an older completed phase of its barrier
+      // for the one it waits for) and reduces 4 of its 16 slabs: warp w owns slabs 4w..4w+3 of each half; lane l owns
+      // points l, l+32, l+64, l+96 (each LDS.128 of a warp covers 512 contiguous bytes).  Partial sums stay in registers
+      // across this CTA's tiles.  Rows past the end of the batch are exact zeros in the gradient stash.
+      float acc[2][4][8];
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
-      int slot = 0, phase = 0;
-      const int w = warp - 2;
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[h][a][j] = 0.f;
+      int ds = 0, dph = 0;
       for (long long t = t0; t < t1; ++t) {
-        const int sd = slot;
-        mbar_wait(&full[slot], phase);
-        if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
-        const int sx = slot;
-        mbar_wait(&full[slot], phase);      // only so that the arrival below lands in the right phase of empty[sx]
-        if (++slot == kWgSlots) { slot = 0; phase ^= 1; }
-        const uint8_t* dt = smem + sd * kWgSlotBytes;
 #pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          const int sl = 8 * w + a;
-          if (sl < T.d_slabs) {
+        for (int h = 0; h < 2; ++h) {
+          if (h < halves) {
+            mbar_wait(&dfull[ds], dph);
+            const uint8_t* dt = dring + ds * kWgDGran;
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-              const uint4 u = *reinterpret_cast<const uint4*>(dt + sl * 2048 + (lane + 32 * rr) * 16);
-              const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+            for (int a = 0; a < 4; ++a) {
+              const int sl = 4 * w + a;                     // slab inside the granule
+              if (16 * h + sl < T.d_slabs) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                acc[a][2 * j] += __uint_as_float(x[j] << 16);
-                acc[a][2 * j + 1] += __uint_as_float(x[j] & 0xFFFF0000u);
+                for (int rr = 0; rr < 4; ++rr) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(dt + sl * 2048 + (lane + 32 * rr) * 16);
+                  const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    acc[h][a][2 * j] += __uint_as_float(x[j] << 16);
+                    acc[h][a][2 * j + 1] += __uint_as_float(x[j] & 0xFFFF0000u);
+                  }
+                }
               }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dempty[ds]);
+            if (++ds == kWgDSlots) { ds = 0; dph ^= 1; }
           }
         }
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&empty[sd]); mbar_arrive(&empty[sx]); }
       }
       if (t1 > t0) {
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float v = warp_sum(acc[a][j]);
-            if (lane == 0 && 8 * w + a < T.d_slabs) atomicAdd(p.gbuf + T.colsum_off + (8 * w + a) * 8 + j, v);
-          }
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float v = warp_sum(acc[h][a][j]);
+              const int slab = 16 * h + 4 * w + a;
+              if (lane == 0 && slab < T.d_slabs) atomicAdd(p.gbuf + T.colsum_off + slab * 8 + j, v);
+            }
       }
     }
     // final epilogue: TMEM -> fp32 atomics into this layer's G block (a handful of CTAs share a block)
@@ -353,16 +378,31 @@ static int backward_common(const TcPlan& plan, const vfnerf_mlp_desc& vf, const 
     VFN_CHECK_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   {
-    // CTAs per task proportional to the bytes it streams
+    // CTAs per task proportional to the bytes it streams: floor of the proportional share first, then the CTAs that
+    // rounding left over go, one at a time, to the task whose CTAs carry the most bytes (the kernel ends with its
+    // slowest CTA, so the maximum per-CTA load is what counts)
     double total = 0;
+    int cnt[24];
     for (int i = 0; i < nt; ++i) total += wp.t[i].d_slabs + wp.t[i].n_xslabs;
     int used = 0;
     for (int i = 0; i < nt; ++i) {
       int c = std::max(1, (int)((wp.t[i].d_slabs + wp.t[i].n_xslabs) / total * g_sms));
-      c = (int)std::min<int64_t>(c, std::max<int64_t>(1, tiles));
-      wp.t[i].cta0 = used; wp.t[i].nctas = c; used += c;
+      cnt[i] = (int)std::min<int64_t>(c, std::max<int64_t>(1, tiles));
+      used += cnt[i];
     }
-    const size_t smem = (size_t)kWgSlots * kWgSlotBytes + 256;
+    auto load = [&](int i) {   // bytes (in slabs) the busiest CTA of task i streams
+      return (double)((tiles + cnt[i] - 1) / cnt[i]) * (wp.t[i].d_slabs + wp.t[i].n_xslabs);
+    };
+    while (used < g_sms) {
+      int best = -1;
+      for (int i = 0; i < nt; ++i)
+        if (cnt[i] < tiles && (best < 0 || load(i) > load(best))) best = i;
+      if (best < 0) break;
+      ++cnt[best]; ++used;
+    }
+    used = 0;
+    for (int i = 0; i < nt; ++i) { wp.t[i].cta0 = used; wp.t[i].nctas = cnt[i]; used += cnt[i]; }
+    const size_t smem = (size_t)kWgDSlots * kWgDGran + (size_t)kWgXSlots * kWgXBytes + 256;
     static bool attr = false;
     if (!attr) {
       VFN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
