@@ -31,7 +31,8 @@ using namespace tc;
 constexpr int kTileM = 128;
 constexpr int kStageBytes = 32768;
 constexpr int kTcStages = 3;
-constexpr int kTcThreads = 448;      // warp 0 producer, warp 1 MMA/relay, warps 2..9 epilogue, warps 10..13 prologue
+constexpr int kTcThreads = 480;      // warp 0 producer, warp 1 MMA/relay, warps 2..9 epilogue, warps 10..13 prologue,
+                                     // warp 14: activation-stash store lane (training forward)
 constexpr int kAccCols = 256;
 constexpr float kInvSqrt2 = 0.70710678118654752f;
 // readiness barriers (leader CTA): 0..3 = 64-column groups of the main region (one per K chunk; group g is written by
@@ -312,7 +313,14 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   // having passed its wait for step g -- the issuer can never complete a phase twice before a slow warp has seen it
   uint64_t* grp = acc_full + 2;                 // leader only: A-operand readiness
   uint64_t* reg_free = grp + kGroups;           // [0] emb0, [1] skip, [2] aux-static: their reader MMAs have completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reg_free + 3);
+  // training forward: the bf16 activations an epilogue warp writes into the activation tile ARE the stash image of
+  // that tile (same K-slab bytes), so they are not stored to global memory by the epilogue warps: one lane of warp 14
+  // copies each finished 64-column group with cp.async.bulk (shared -> global) and tells the epilogue when the group's
+  // columns may be overwritten.  st_ready[g]: the 4 warps owning group g have written + fenced it; st_done[g]: the bulk
+  // copy has finished reading it.
+  uint64_t* st_ready = reg_free + 3;
+  uint64_t* st_done = st_ready + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_done + 4);
   // chunk table: the single-lane producer / MMA-issuer loops must not chase per-chunk facts through the kernel
   // parameters (dependent constant loads cost them ~500 cycles per chunk): everything a chunk needs is one LDS.128.
   //   x = A start-address increment (16-byte units), y = K columns | readiness-barrier mask << 16,
@@ -328,6 +336,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     for (int i = 0; i < kGroups; ++i) mbar_init(&grp[i], 8);    // 4 warps (one half, or the prologue warps) x 2 CTAs
     for (int i = 0; i < 3; ++i) mbar_init(&reg_free[i], 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&st_ready[i], 4); mbar_init(&st_done[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -508,6 +517,33 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       TCK(t_issue);
       if (prof) { p.dbg_buf[0] = t_grp; p.dbg_buf[1] = t_full; p.dbg_buf[2] = t_issue; }
     }
+  } else if (warp == 14) {
+    // ===================== activation-stash store lane (training forward) =====================
+    if constexpr (kStash && !kBwd) {
+      if (lane == 0) {
+        uint32_t su = 0;
+        for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
+          const long long tile = 2 * pair + (long long)rank;
+          for (int si = 0; si < prog.n_steps; ++si) {
+            const TcStep& st = prog.s[si];
+            const bool via_tile = (st.epi == TC_EPI_RELU || (st.epi == TC_EPI_FEAT && prog.render != 0)) && st.stash_out >= 0;
+            if (!via_tile) continue;
+            for (int bg = 0; bg < 4; ++bg) {
+              const int c0 = bg * 64;
+              mbar_wait(&st_ready[bg], su & 1);
+              if (c0 < st.N && tile < num_tiles && !(p.dbg & 8)) {
+                const uint32_t bytes = (uint32_t)(min(64, st.N - c0) >> 3) * (kTileM * 16);
+                bulk_s2g(stash_unit(p, st.stash_out, tile, c0 >> 3, 0), s_act + (size_t)(c0 >> 3) * (kTileM * 16), bytes);
+                bulk_wait_read_all();
+              }
+              mbar_arrive(&st_done[bg]);
+            }
+            ++su;
+          }
+        }
+        bulk_wait_all();
+      }
+    }
   } else if (warp >= 10) {
     // ===================== prologue warps (one row per thread) =====================
     // They build, one tile ahead, every A-operand region that depends only on the inputs: the bf16 hi|lo positional
@@ -673,6 +709,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const bool render = prog.render != 0;
     uint32_t gstep = 0;
+    uint32_t su = 0;          // stashed steps whose output left through warp 14 so far (st_ready / st_done phases)
     long long t_acc = 0, t_ld = 0, t_math = 0, t_sig = 0, t_other = 0, t0 = 0;
     const bool prof = p.dbg_buf && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 3);
     auto tile_of = [&](long long pair) { return 2 * pair + (long long)rank; };
@@ -770,6 +807,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const bool to_act = !feat || render;
           const int stN = st.N;
           const bool st_on = kStash && st.stash_out >= 0 && tile < num_tiles;
+          const bool st_tile = kStash && st.stash_out >= 0 && to_act;     // this step's output leaves through warp 14
           if (to_act) {
             // Each warp owns two of the four 64-column groups (= K chunks of the next layer): h=0 -> groups 0 and 2,
             // h=1 -> groups 1 and 3.  One generic->async proxy fence (a MEMBAR.ALL.CTA) and one barrier arrival per
@@ -777,7 +815,13 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll 1
             for (int it = 0; it < 2; ++it) {
               const int bg = 2 * it + h, c0 = bg * 64;
-              if (c0 >= stN) { arrive_grp(bg); continue; }     // narrow layer: nothing to write, the barrier still counts us
+              // the bulk copy of this group's previous contents (last stashed step) must have read them
+              if (st_tile) mbar_wait(&st_done[bg], (su & 1) ^ 1);
+              if (c0 >= stN) {                                 // narrow layer: nothing to write, the barriers still count us
+                if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
+                arrive_grp(bg);
+                continue;
+              }
               const bool second = c0 + 32 < stN;
               uint32_t va[32], vb[32];
               TCK(t_other);
@@ -796,13 +840,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                 for (int sl = 0; sl < 4; ++sl)
                   store_slab_u(s_act, (c0 >> 3) + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
                 uint32_t gate_lo = 0, gate_hi = 0;
-                const bool st_act = st_on && !(p.dbg & 8), st_gate = st_on && !(p.dbg & 16);   // experiment switches
-                if (st_act) {
-#pragma unroll
-                  for (int sl = 0; sl < 4; ++sl)
-                    *stash_unit(p, st.stash_out, tile, (c0 >> 3) + sl, row) =
-                        make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
-                }
+                const bool st_gate = st_on && !(p.dbg & 16);   // experiment switch (the activations themselves leave via warp 14)
                 if (st_gate) {
                   // gate bit e = "pre-activation of column c0 + e is not negative": one funnel shift per element
                   // collects the fp32 sign bits (an exact zero passes the gate; its gradient contribution is zero or
@@ -820,12 +858,6 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                   for (int sl = 0; sl < 4; ++sl)
                     store_slab_u(s_act, (c0 >> 3) + 4 + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
-                  if (st_act) {
-#pragma unroll
-                    for (int sl = 0; sl < 4; ++sl)
-                      *stash_unit(p, st.stash_out, tile, (c0 >> 3) + 4 + sl, row) =
-                          make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
-                  }
                   if (st_gate) {
 #pragma unroll
                     for (int j = 31; j >= 0; --j) gate_hi = __funnelshift_l(vb[j], gate_hi, 1);
@@ -838,11 +870,13 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               TCK(t_math);
               fence_proxy_async_smem();
               tc_fence_before_sync();
+              if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
               arrive_grp(bg);
               TCK(t_sig);
               if (tl && it == 0) p.dbg_buf[64 + si * 8 + 3 + 3 * h] = clock64();
               if (tl) p.dbg_buf[64 + si * 8 + 4 + 3 * h] = clock64();
             }
+            if (st_tile) ++su;
           } else {
             // VF_FULL: features go to global memory as fp32 (module-call output), 32 columns at a time
 #pragma unroll 1
