@@ -519,14 +519,17 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     }
   } else if (warp == 14) {
     // ===================== activation-stash store lane (training forward) =====================
-    if constexpr (kStash && !kBwd) {
+    if constexpr (kStash) {
       if (lane == 0) {
         uint32_t su = 0;
         for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
           const long long tile = 2 * pair + (long long)rank;
           for (int si = 0; si < prog.n_steps; ++si) {
             const TcStep& st = prog.s[si];
-            const bool via_tile = (st.epi == TC_EPI_RELU || (st.epi == TC_EPI_FEAT && prog.render != 0)) && st.stash_out >= 0;
+            // forward: hidden-layer / feature outputs that become the next A operand; backward (render() dgrad chain):
+            // every step but the last hands its gated gradient on through the activation tile
+            const bool via_tile = kBwd ? (prog.bwd == 1 && si + 1 < prog.n_steps && st.stash_out >= 0)
+                                       : ((st.epi == TC_EPI_RELU || (st.epi == TC_EPI_FEAT && prog.render != 0)) && st.stash_out >= 0);
             if (!via_tile) continue;
             for (int bg = 0; bg < 4; ++bg) {
               const int c0 = bg * 64;
@@ -736,6 +739,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           // and it must not arrive on the column-group barriers (every arrival set is matched by exactly one wait of
           // the MMA issuer; an unmatched one would shift the barrier phases of the next tile)
           const bool hand_on = si + 1 < prog.n_steps;
+          // render() dgrad chain: handed-on gradients are stashed by warp 14 from the activation tile (see st_ready)
+          const bool st_tile = prog.bwd == 1 && hand_on && st.stash_out >= 0;
           uint32_t gbits[2][2] = {{0u, 0u}, {0u, 0u}};
           if (!is_tanh && t_ok) {
 #pragma unroll
@@ -754,7 +759,12 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int it = 0; it < 2; ++it) {
             const int bg = 2 * it + h, c0 = bg * 64;
-            if (c0 >= stN) { if (hand_on) arrive_grp(bg); continue; }
+            if (st_tile) mbar_wait(&st_done[bg], (su & 1) ^ 1);
+            if (c0 >= stN) {
+              if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
+              if (hand_on) arrive_grp(bg);
+              continue;
+            }
             const bool second = c0 + 32 < stN;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -786,15 +796,18 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                   }
                 }
                 if (hand_on) store_slab_u(s_act, (cb >> 3) + sl, row, o[0], o[1], o[2], o[3]);
-                if (t_ok && !(p.dbg & 8)) *stash_unit(p, st.stash_out, tile, (cb >> 3) + sl, row) = make_uint4(o[0], o[1], o[2], o[3]);
+                if (!st_tile && t_ok && !(p.dbg & 8))
+                  *stash_unit(p, st.stash_out, tile, (cb >> 3) + sl, row) = make_uint4(o[0], o[1], o[2], o[3]);
               }
             }
             if (hand_on) {
               fence_proxy_async_smem();
               tc_fence_before_sync();
+              if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
               arrive_grp(bg);
             }
           }
+          if (st_tile) ++su;
           tc_fence_before_sync();
         } else {
         TCK(t_other);
