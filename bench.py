@@ -278,14 +278,31 @@ def main():
         rgb_h = torch.empty(R, 3).pin_memory()
         dep_h = torch.empty(R, 1).pin_memory()
 
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def stage(a, b):
+            # the caller's H2D of one chunk (train/vector_field_nerf_train.py:172-174 does it inline); here the next
+            # chunk's copy runs on a side stream while the current chunk renders
+            with torch.cuda.stream(copy_stream):
+                t = (uv_h[a:b].to(dev, non_blocking=True), pose_h[a:b].to(dev, non_blocking=True),
+                     K_h[a:b].to(dev, non_blocking=True))
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return t, ev
+
         def step_e2e(ck):
             h2d = d2h = 0
+            main = torch.cuda.current_stream(dev)
             with torch.no_grad():
+                nxt = stage(0, min(R, ck))
                 for a in range(0, R, ck):
                     b = min(R, a + ck)
-                    px = uv_h[a:b].to(dev, non_blocking=True)
-                    po = pose_h[a:b].to(dev, non_blocking=True)
-                    ki = K_h[a:b].to(dev, non_blocking=True)
+                    (px, po, ki), ev = nxt
+                    if b < R:
+                        nxt = stage(b, min(R, b + ck))
+                    main.wait_event(ev)
+                    for t in (px, po, ki):
+                        t.record_stream(main)
                     out = model.render(po, px, ki, 0)          # draws U3 on the CPU generator + H2D, like the reference
                     rgb_h[a:b].copy_(out.coarse_rgb_values, non_blocking=True)
                     dep_h[a:b].copy_(out.coarse_depth_map, non_blocking=True)

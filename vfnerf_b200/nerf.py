@@ -55,6 +55,7 @@ class VectorFieldNerf:
         # the device, so torch.manual_seed reproduces the reference's sample positions bit for bit.  True: draw them on
         # the device (same distribution, a different random stream) -- saves ~100 us of host time per 1024-ray call.
         self.draws_on_device = False
+        self._stage: dict = {}          # pinned staging rings of the CPU-generator draws, per device
         self.last_extras: dict = {}
 
     # ---- module plumbing (vector_field_nerf.py:84-214) ------------------------------------------
@@ -129,6 +130,43 @@ class VectorFieldNerf:
         torch.save(state, os.path.join(path, f"{epoch}.pth"))
         torch.save(state, os.path.join(path, "latest.pth"))
 
+    # ---- host draws -> device ---------------------------------------------------------------------
+    def _upload_draw(self, rows: int, cols: int, dev: torch.device) -> torch.Tensor:
+        """``torch.rand([rows, cols])`` on the global CPU generator (the reference's stream, ray_sampler.py:138,292,297)
+        made directly in pinned memory and copied with one DMA.  A pageable tensor would be staged by the driver at a
+        few GB/s on the compute stream (16.8 MB per 65 536-ray chunk).  The DMA runs on a dedicated upload stream, so it
+        overlaps the previous call's kernels; ring of four buffers per device, a buffer is reused only after the copy that
+        read it has completed (event)."""
+        if rows * cols < (1 << 18):
+            # small draws (the reference's 1024-ray chunks: 256 KB): the plain pageable copy is cheaper than stream / event
+            # bookkeeping on the host, which is what bounds calls of that size
+            return torch.rand([rows, cols]).to(dev, non_blocking=True)
+        ring = self._stage.get(str(dev))
+        if ring is None:
+            ring = self._stage[str(dev)] = {"bufs": [], "next": 0, "stream": torch.cuda.Stream(device=dev)}
+        n = rows * cols
+        if len(ring["bufs"]) < 4:
+            ring["bufs"].append([torch.empty(max(n, 1 << 16), dtype=torch.float32).pin_memory(), None])
+            slot = ring["bufs"][-1]
+        else:
+            slot = ring["bufs"][ring["next"]]
+            ring["next"] = (ring["next"] + 1) % 4
+        if slot[1] is not None:
+            slot[1].synchronize()          # the copy runs on its own stream: done long before the buffer comes round again
+        if slot[0].numel() < n:
+            slot[0] = torch.empty(n, dtype=torch.float32).pin_memory()
+        host = slot[0][:n].view(rows, cols)
+        torch.rand([rows, cols], out=host)
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(ring["stream"]):
+            out = host.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(ring["stream"])
+        main.wait_event(ev)                # render()'s kernels are stream-ordered after the upload
+        out.record_stream(main)
+        slot[1] = ev
+        return out
+
     # ---- the hot path ---------------------------------------------------------------------------
     def _render_cfg(self, n_rays: int, pose_is_quat: bool) -> _lib.RenderCfg:
         c, d = self.config, self.density
@@ -193,8 +231,11 @@ class VectorFieldNerf:
             U2 = None if self.fine_sampler.deterministic else torch.rand(R, nf, device=dev)
             U3 = torch.rand(R, nf, device=dev)
         elif draws is None:
-            U1 = self.ray_sampler.draw(R)
-            U2, U3 = self.fine_sampler.draw(R)
+            # same generator, same order and sizes as ray_sampler.draw / fine_sampler.draw (U1 -> U2 -> U3)
+            nf = self.fine_sampler.n_fine()
+            U1 = None if self.ray_sampler.deterministic else self._upload_draw(R, self.ray_sampler.N_samples, dev)
+            U2 = None if self.fine_sampler.deterministic else self._upload_draw(R, nf, dev)
+            U3 = self._upload_draw(R, nf, dev)
         else:
             U1, U2, U3 = draws
         # host linspace (bit-exact with the reference), uploaded once per (device, count): keeps render() free of
