@@ -253,6 +253,12 @@ int vfnerf_pdf_fine_sample(int n_rays, int n_coarse, int n_fine, const float* z_
 int vfnerf_density_weights(const vfnerf_render_cfg* cfg, int n_samples, const float* density_params,
                            const float* normals, int64_t normals_ld, const float* ray_dirs,
                            const float* z, float* cosw, float* sigma, float* weights, void* stream);
+/* utils/rendering.py as stand-alone ops on a given density sigma [R,N] and z [R,N] -> weights [R,N]:
+ * mode 0 = volsdf_volume_rendering (:122-148), mode 1 = nerf_volume_rendering (:98-119, inclusive cumprod, +1e-10).
+ * The reference's render() calls the latter with swapped arguments, so rendering="nerf" stays rejected in
+ * render(); this is the corrected-order op of SURVEY.md 8f rank 4. */
+int vfnerf_volume_weights(int n_rays, int n_samples, int mode, int normalize, const float* sigma,
+                          const float* z, float* weights, void* stream);
 /* a9: rgb = sum_j w_j c_j, depth = sum_j w_j z_j, vector_field_nerf.py:322-323 */
 int vfnerf_composite(int n_rays, int n_samples, const float* weights, const float* colors,
                      const float* z, float* rgb, float* depth, void* stream);

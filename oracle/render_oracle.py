@@ -315,6 +315,17 @@ def volsdf_weights(z: torch.Tensor, sigma: torch.Tensor, normalize: bool = True)
 # --------------------------------------------------------------------------------------
 # render()
 # --------------------------------------------------------------------------------------
+def nerf_weights(sigma: torch.Tensor, z: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+    """nerf_volume_rendering, utils/rendering.py:98-119 (note the INCLUSIVE cumprod and the +1e-10)."""
+    dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((z.shape[0], 1), 1e10)], dim=-1)
+    free_energy = dists * sigma
+    alpha = 1.0 - torch.exp(-free_energy)
+    w = alpha * torch.cumprod(1. - alpha + 1e-10, dim=-1, dtype=torch.float32)
+    if normalize:
+        w = w / (w.sum(dim=-1, keepdim=True) + 1e-5)
+    return w
+
+
 def render(vf_sd, rn_sd, density_params, cfg: dict, uv, pose, intrinsics, t_vals,
            U1=None, U2=None, U3=None, z_vals_override: Optional[torch.Tensor] = None) -> dict:
     """VectorFieldNerf.render() in eval mode with rendering='volsdf', vector_field_nerf.py:216-338.

@@ -119,3 +119,15 @@ def test_mc_oracle_matches_reference_golden(tag, N):
     cells, comb, udf = MO.mc_preprocess(g["pred"], N)
     assert torch.equal(cells.int(), g["cells"]) and torch.equal(comb, g["comb"]) and torch.equal(udf, g["udf"])
     assert g["cells"].shape[0] > 1000
+
+
+@pytest.mark.parametrize("tag", ["n128", "n200", "n2"])
+def test_weight_function_oracles_match_reference_golden(tag):
+    """nerf_volume_rendering / volsdf_volume_rendering (utils/rendering.py:98-148): oracle == live reference, bit for bit
+    (fixture from tests/golden/make_golden_weights.py)."""
+    import os
+    z = np.load(os.path.join(U.GOLDEN_DIR, "volume_weights.npz"))
+    zz, sg = torch.from_numpy(z[f"{tag}.z"]), torch.from_numpy(z[f"{tag}.sigma"])
+    for norm in (0, 1):
+        assert torch.equal(U.O.nerf_weights(sg, zz, bool(norm)), torch.from_numpy(z[f"{tag}.nerf.{norm}"]))
+        assert torch.equal(U.O.volsdf_weights(zz, sg, bool(norm)), torch.from_numpy(z[f"{tag}.volsdf.{norm}"]))

@@ -81,6 +81,7 @@ PROTOTYPES = {
     "vfnerf_sample_pdf": (_I, [_I, _I, _I, _P, _P, _P, _I, _P, _P]),
     "vfnerf_pdf_fine_sample": (_I, [_I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "vfnerf_density_weights": (_I, [_CFG, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
+    "vfnerf_volume_weights": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "vfnerf_composite": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "vfnerf_debug_umma_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "vfnerf_debug_umma_mn_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),

@@ -691,6 +691,11 @@ int vfnerf_density_weights(const vfnerf_render_cfg* cfg, int n_samples, const fl
                                 cosw, sigma, weights, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int vfnerf_volume_weights(int n_rays, int n_samples, int mode, int normalize, const float* sigma, const float* z,
+                          float* weights, void* stream) {
+  return launch_volume_weights(n_rays, n_samples, mode, normalize, sigma, z, weights, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int vfnerf_composite(int n_rays, int n_samples, const float* weights, const float* colors, const float* z,
                      float* rgb, float* depth, void* stream) {
   return launch_composite(n_rays, n_samples, weights, colors, z, rgb, depth, reinterpret_cast<cudaStream_t>(stream));

@@ -84,6 +84,8 @@ int launch_merge_samples(int n_rays, int n_coarse, int n_fine, const uint8_t* sr
                          const float* a_fine, float* a_out, const float* b_coarse, const float* b_fine,
                          float* b_out, cudaStream_t s);
 
+int launch_volume_weights(int n_rays, int n_samples, int mode, int normalize, const float* sigma, const float* z,
+                          float* weights, cudaStream_t s);
 // mc_preprocess.cu
 int launch_mc_count(const float* pred, int N, uint8_t* keep, int* cta_counts, float* div_raw, uint8_t* choice, cudaStream_t s);
 int launch_mc_emit(const float* pred, int N, const uint8_t* keep, const int64_t* cta_offsets, int* cells, float* comb,

@@ -178,6 +178,74 @@ int launch_density_weights(const vfnerf_render_cfg& cfg, int n_rays, int n_sampl
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stand-alone compositing weights from a given density (utils/rendering.py): one warp per ray, chunked warp scans.
+//   mode 0  volsdf_volume_rendering (:122-148): w_j = (1 - exp(-E_j)) * exp(-sum_{i<j} E_i),  E_j = (z_{j+1} - z_j) * sigma_j,
+//           last interval 1e10 -- what density_weights_kernel fuses behind the density
+//   mode 1  nerf_volume_rendering (:98-119): w_j = a_j * prod_{i<=j} (1 - a_i + 1e-10), a_j = 1 - exp(-E_j) (the reference's
+//           cumprod is INCLUSIVE of sample j).  render() upstream passes this function its arguments swapped
+//           (SURVEY.md §8a), so it is offered as the corrected stand-alone op only.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_inclusive_prod(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(kFull, v, o);
+    if (lane >= o) v *= t;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(kRayWarps * 32)
+volume_weights_kernel(int n_rays, int N, int mode, int normalize, const float* __restrict__ sigma,
+                      const float* __restrict__ z, float* __restrict__ weights) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * kRayWarps + wid;
+  if (r >= n_rays) return;
+  const float* zr = z + (int64_t)r * N;
+  const float* sr = sigma + (int64_t)r * N;
+  float* wr = weights + (int64_t)r * N;
+  float carry = mode ? 1.f : 0.f, wsum = 0.f;
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    const int j = j0 + lane;
+    float E = 0.f;
+    if (j < N) E = ((j < N - 1) ? (zr[j + 1] - zr[j]) : 1e10f) * sr[j];
+    const float a = 1.f - expf(-E);
+    float w;
+    if (mode == 0) {
+      // exclusive prefix by shifting the inclusive scan (inc - E would cancel catastrophically on the 1e10 interval)
+      const float inc = warp_inclusive_scan(E, lane);
+      float exc = __shfl_up_sync(kFull, inc, 1);
+      if (lane == 0) exc = 0.f;
+      w = a * expf(-(carry + exc));
+      carry += __shfl_sync(kFull, inc, 31);
+    } else {
+      const float f = (j < N) ? (1.f - a + 1e-10f) : 1.f;
+      const float inc = warp_inclusive_prod(f, lane);
+      w = a * (carry * inc);
+      carry *= __shfl_sync(kFull, inc, 31);
+    }
+    if (j < N) { if (normalize) wsum += w; else wr[j] = w; }
+    if (normalize && j < N) wr[j] = w;
+  }
+  if (normalize) {
+    wsum = warp_sum(wsum);
+    const float inv = 1.f / (wsum + 1e-5f);
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) wr[j] *= inv;
+  }
+}
+
+int launch_volume_weights(int n_rays, int n_samples, int mode, int normalize, const float* sigma, const float* z,
+                          float* weights, cudaStream_t s) {
+  if (n_rays <= 0 || n_samples <= 0) return 0;
+  VFN_REQUIRE(sigma && z && weights, "volume_weights: null argument");
+  VFN_REQUIRE(mode == 0 || mode == 1, "volume_weights: mode %d (0 volsdf, 1 nerf)", mode);
+  volume_weights_kernel<<<(n_rays + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, s>>>(n_rays, n_samples, mode, normalize,
+                                                                                     sigma, z, weights);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // a9: rgb = sum_j w_j c_j, depth = sum_j w_j z_j
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRayWarps * 32)
