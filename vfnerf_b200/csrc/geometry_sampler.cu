@@ -133,20 +133,28 @@ __device__ __forceinline__ void warp_sort_two_runs(float* s, uint8_t* si, float*
   for (int j = lane; j < N; j += 32)
     if (j != 0 && j != na) ok = ok && (s[j - 1] <= s[j]);
   if (__all_sync(kFull, ok)) {
+    // branch-free binary searches with a fixed trip count (log2 of the next power of two >= run length)
+    int pa = 1, pb = 1;
+    while (pa < na) pa <<= 1;
+    while (pb < nb) pb <<= 1;
     for (int e = lane; e < N; e += 32) {
       const float v = s[e];
-      int rank;
-      if (e < na) {                       // lower bound of v in B
-        int lo = 0, hi = nb;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (s[na + mid] < v) lo = mid + 1; else hi = mid; }
-        rank = e + lo;
-      } else {                            // upper bound of v in A
-        int lo = 0, hi = na;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (s[mid] <= v) lo = mid + 1; else hi = mid; }
-        rank = (e - na) + lo;
+      int pos = 0;
+      if (e < na) {                       // number of B elements smaller than v (lower bound)
+        for (int st = pb; st > 0; st >>= 1) {
+          const int q = pos + st;
+          if (q <= nb && s[na + q - 1] < v) pos = q;
+        }
+        pos += e;
+      } else {                            // number of A elements not larger than v (upper bound)
+        for (int st = pa; st > 0; st >>= 1) {
+          const int q = pos + st;
+          if (q <= na && s[q - 1] <= v) pos = q;
+        }
+        pos += e - na;
       }
-      t[rank] = v;
-      ti[rank] = (uint8_t)e;
+      t[pos] = v;
+      ti[pos] = (uint8_t)e;
     }
     __syncwarp();
     return;
@@ -241,11 +249,11 @@ fine_sample_kernel(int n_rays, int n_coarse, int n_fine, float nearf, float far_
     if (points_fine) {
       // the fine candidates alone, in candidate order: the only points of this ray the MLPs have not seen yet
       float* pf = points_fine + (int64_t)r * n_fine * 3;
-      for (int e = lane; e < 3 * n_fine; e += 32) {
-        int j = e / 3, c = e - 3 * j;
-        float d = (c == 0) ? dx : (c == 1 ? dy : dz);
-        float o = (c == 0) ? ox : (c == 1 ? oy : oz);
-        pf[e] = __fadd_rn(o, __fmul_rn(s[n_coarse + j], d));
+      for (int j = lane; j < n_fine; j += 32) {
+        const float zj = s[n_coarse + j];
+        pf[3 * j] = __fadd_rn(ox, __fmul_rn(zj, dx));
+        pf[3 * j + 1] = __fadd_rn(oy, __fmul_rn(zj, dy));
+        pf[3 * j + 2] = __fadd_rn(oz, __fmul_rn(zj, dz));
       }
       __syncwarp();
     }
@@ -255,12 +263,13 @@ fine_sample_kernel(int n_rays, int n_coarse, int n_fine, float nearf, float far_
   __syncwarp();
   for (int j = lane; j < N; j += 32) z_out[(int64_t)r * N + j] = t[j];
   if (points) {
+    // one sample per lane and iteration, three 12-byte-strided stores (a warp still writes one contiguous 384-byte span)
     float* pr = points + (int64_t)r * N * 3;
-    for (int e = lane; e < 3 * N; e += 32) {
-      int j = e / 3, c = e - 3 * j;
-      float d = (c == 0) ? dx : (c == 1 ? dy : dz);
-      float o = (c == 0) ? ox : (c == 1 ? oy : oz);
-      pr[e] = __fadd_rn(o, __fmul_rn(t[j], d));
+    for (int j = lane; j < N; j += 32) {
+      const float zj = t[j];
+      pr[3 * j] = __fadd_rn(ox, __fmul_rn(zj, dx));
+      pr[3 * j + 1] = __fadd_rn(oy, __fmul_rn(zj, dy));
+      pr[3 * j + 2] = __fadd_rn(oz, __fmul_rn(zj, dz));
     }
   }
 }
