@@ -257,7 +257,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
       "@P1 bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
@@ -287,7 +287,7 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
       "@P1 bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
