@@ -110,7 +110,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     tmp = LIB_PATH + ".building.so"      # swapped in atomically: a concurrent snapshot/load never sees a partial file
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+    extra = os.environ.get("NVCC_EXTRA", "").split()     # e.g. -DVFNERF_TC_PROFILE for the in-kernel cycle counters
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -298,7 +298,16 @@ __device__ __forceinline__ void umma2_commit_u32(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// In-kernel cycle counters / per-step timeline (VFNERF_TC_DBG=64) exist only in builds with -DVFNERF_TC_PROFILE: the
+// single MMA-issuing lane has no slack -- even predicated-off clock reads and one more run-time switch in its loop cost
+// several per cent (profiles/r01_forward_kernel_experiments.md) -- so the product build compiles the hooks out.
+#ifdef VFNERF_TC_PROFILE
+constexpr bool kTcProfile = true;
 #define TCK(acc_) do { if (prof) { long long t1_ = clock64(); acc_ += t1_ - t0; t0 = t1_; } } while (0)
+#else
+constexpr bool kTcProfile = false;
+#define TCK(acc_) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
@@ -306,6 +315,7 @@ __device__ __forceinline__ void umma2_commit_u32(uint32_t bar) {
 template <bool kBwd, bool kStash>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcParams p) {
+  const int kdbg = kTcProfile ? p.dbg : 0;   // experiment switches (VFNERF_TC_DBG) exist in profile builds only
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcProgram& prog = p.prog;
   uint8_t* s_act = smem;
@@ -406,7 +416,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           for (;; ++ck) {
             const uint4 c = *ck;
             mbar_wait(&empty[stage], phase ^ 1);
-            if (p.dbg & 4) {
+            if (kdbg & 4) {
               // experiment: no weight traffic at all (results are garbage) -- isolates the L2 -> shared-memory streaming
               mbar_arrive(&full[stage]);
             } else {
@@ -440,7 +450,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       int stage = 0, phase = 0;
       uint32_t grp_par = 0, gstep = 0;
       long long t_grp = 0, t_full = 0, t_issue = 0, t0 = 0;
-      const bool prof = p.dbg_buf && blockIdx.x == 0;
+      const bool prof = kTcProfile && p.dbg_buf && blockIdx.x == 0;
       if (prof) t0 = clock64();
       const uint32_t act_base = smem_u32(s_act), stage_base = smem_u32(s_stage);
       const uint32_t grp_u32 = smem_u32(grp), full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
@@ -457,7 +467,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const uint32_t b_lo0 = ((stage_base >> 4) & 0x3FFF) | ((((uint32_t)(st.N >> 1) * 16u) >> 4) << 16);
           const uint32_t b_kstep = (uint32_t)st.N;                             // two K-slabs of the HALF weight chunk, in 16-byte units
           const uint32_t acc = tmem + (gstep & 1) * kAccCols;
-          const uint32_t fresh = (p.dbg & 1) ? 0u : 0xFFFFu;   // per-chunk masks are pre-filtered in the chunk table
+          const uint32_t fresh = (kdbg & 1) ? 0u : 0xFFFFu;   // per-chunk masks are pre-filtered in the chunk table
           uint32_t accumulate = 0;
           TCK(t_issue);
           for (int g = 0; g < kGroups; ++g) {
@@ -541,7 +551,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             for (int bg = 0; bg < 4; ++bg) {
               const int c0 = bg * 64;
               mbar_wait(&st_ready[bg], su & 1);
-              if (c0 < st.N && tile < num_tiles && !(p.dbg & 8)) {
+              if (c0 < st.N && tile < num_tiles && !(kdbg & 8)) {
                 const uint32_t bytes = (uint32_t)(min(64, st.N - c0) >> 3) * (kTileM * 16);
                 bulk_s2g(stash_unit(p, st.stash_out, tile, c0 >> 3, 0), s_act + (size_t)(c0 >> 3) * (kTileM * 16), bytes);
                 bulk_wait_read_all();
@@ -721,7 +731,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     uint32_t gstep = 0;
     uint32_t su = 0;          // stashed steps whose output left through warp 14 so far (st_ready / st_done phases)
     long long t_acc = 0, t_ld = 0, t_math = 0, t_sig = 0, t_other = 0, t0 = 0;
-    const bool prof = p.dbg_buf && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 3);
+    const bool prof = kTcProfile && p.dbg_buf && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 3);
     auto tile_of = [&](long long pair) { return 2 * pair + (long long)rank; };
     if (prof) t0 = clock64();
 
@@ -803,7 +813,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                   }
                 }
                 if (hand_on) store_slab_u(s_act, (cb >> 3) + sl, row, o[0], o[1], o[2], o[3]);
-                if (!st_tile && t_ok && !(p.dbg & 8))
+                if (!st_tile && t_ok && !(kdbg & 8))
                   *stash_unit(p, st.stash_out, tile, (cb >> 3) + sl, row) = make_uint4(o[0], o[1], o[2], o[3]);
               }
             }
@@ -849,7 +859,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               if (second) tmem_ld32(acc + c0 + 32, vb);
               tmem_ld_wait();
               TCK(t_ld);
-              if (!(p.dbg & 2)) {
+              if (!(kdbg & 2)) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -860,7 +870,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                 for (int sl = 0; sl < 4; ++sl)
                   store_slab_u(s_act, (c0 >> 3) + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
                 uint32_t gate_lo = 0, gate_hi = 0;
-                const bool st_gate = st_on && !(p.dbg & 16);   // experiment switch (the activations themselves leave via warp 14)
+                const bool st_gate = st_on && !(kdbg & 16);   // experiment switch (the activations themselves leave via warp 14)
                 if (st_gate) {
                   // gate bit e = "pre-activation of column c0 + e is not negative": one funnel shift per element
                   // collects the fp32 sign bits (an exact zero passes the gate; its gradient contribution is zero or
@@ -1223,6 +1233,12 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("VFNERF_TC_DBG"); dbg = e ? atoi(e) : 0; }
   static long long* dbg_buf = nullptr;
+  if ((dbg & 64) && !kTcProfile) {
+    static bool told = false;
+    if (!told) fprintf(stderr, "[tc dbg] VFNERF_TC_DBG=64 needs a build with -DVFNERF_TC_PROFILE (NVCC_EXTRA=-DVFNERF_TC_PROFILE)\n");
+    told = true;
+    dbg &= ~64;
+  }
   if ((dbg & 64) && !dbg_buf) VFN_CHECK_CUDA(cudaMalloc(&dbg_buf, 256 * sizeof(long long)));
   p.dbg_buf = (dbg & 64) ? dbg_buf : nullptr;
   p.dbg = dbg & 63;
