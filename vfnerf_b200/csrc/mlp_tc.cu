@@ -275,6 +275,28 @@ __device__ __forceinline__ void umma2_bf16_split(uint32_t tmem_d, uint32_t a_lo,
       "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
       "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Warp-collective variants: executed by all 32 lanes in uniform control flow, one elected lane issues.
+__device__ __forceinline__ void umma2_bf16_split_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                   uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_u32_w(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 // completion of all previously issued MMAs -> the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -446,7 +468,12 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       }
     }
     // ===================== leader CTA: MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    // The WHOLE warp runs this loop (waits, chunk-table reads, descriptor arithmetic) in uniform control flow and only the
+    // tcgen05 instructions themselves are issued by lane 0: the compiler then keeps the descriptor words in uniform
+    // registers.  Run by lane 0 alone, every tcgen05.mma was wrapped in an ELECT / 7 x R2UR.BROADCAST waterfall (17
+    // instructions of scalar work per 128-cycle MMA).  Values that come from shared memory are made uniform with a shuffle.
+    if (rank == 0) {
+      const uint32_t tmem_w = __shfl_sync(0xffffffffu, tmem, 0);
       int stage = 0, phase = 0;
       uint32_t grp_par = 0, gstep = 0;
       long long t_grp = 0, t_full = 0, t_issue = 0, t0 = 0;
@@ -466,7 +493,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const uint32_t a_lo0 = ((act_base >> 4) & 0x3FFF) | (((kTileM * 16u) >> 4) << 16);
           const uint32_t b_lo0 = ((stage_base >> 4) & 0x3FFF) | ((((uint32_t)(st.N >> 1) * 16u) >> 4) << 16);
           const uint32_t b_kstep = (uint32_t)st.N;                             // two K-slabs of the HALF weight chunk, in 16-byte units
-          const uint32_t acc = tmem + (gstep & 1) * kAccCols;
+          const uint32_t acc = tmem_w + (gstep & 1) * kAccCols;
           const uint32_t fresh = (kdbg & 1) ? 0u : 0xFFFFu;   // per-chunk masks are pre-filtered in the chunk table
           uint32_t accumulate = 0;
           TCK(t_issue);
@@ -478,8 +505,10 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           }
           const uint4* ckp = s_chunks + si * 8;
           uint4 ck = *ckp;
+          ck.x = __shfl_sync(0xffffffffu, ck.x, 0); ck.y = __shfl_sync(0xffffffffu, ck.y, 0); ck.w = __shfl_sync(0xffffffffu, ck.w, 0);
           for (;;) {
-            const uint4 nxt = ckp[1];                      // next chunk's facts arrive while this chunk's MMAs issue
+            uint4 nxt = ckp[1];                            // next chunk's facts arrive while this chunk's MMAs issue
+            nxt.x = __shfl_sync(0xffffffffu, nxt.x, 0); nxt.y = __shfl_sync(0xffffffffu, nxt.y, 0); nxt.w = __shfl_sync(0xffffffffu, nxt.w, 0);
             // the A columns of this chunk must have been (re)written: wait for their readiness barrier(s) (at most two)
             uint32_t need = (ck.y >> 16) & fresh;
             if (need) {
@@ -502,32 +531,36 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             constexpr uint32_t a_kstep = 2u * ((kTileM * 16u) >> 4);
             const int kc = (int)(ck.y & 0xFFFFu);
             if (tl && first_mma) { p.dbg_buf[64 + si * 8 + 0] = clock64(); first_mma = false; }
-            if (kc == 128) {
-              // steady state: eight MMAs with constant descriptor increments (the issue thread must stay well
-              // under 128 cycles of scalar work per MMA, profiles/run_umma_bench.py)
-              umma2_bf16_split(acc, a_lo, desc_hi, b_lo, desc_hi, idesc, accumulate);
+            {
+              if (kc == 128) {
+                // steady state: eight MMAs with constant descriptor increments (the issue thread must stay well
+                // under 128 cycles of scalar work per MMA, profiles/run_umma_bench.py)
+                umma2_bf16_split_w(acc, a_lo, desc_hi, b_lo, desc_hi, idesc, accumulate);
 #pragma unroll
-              for (uint32_t j = 1; j < 8; ++j)
-                umma2_bf16_split(acc, a_lo + j * a_kstep, desc_hi, b_lo + j * b_kstep, desc_hi, idesc, 1u);
-            } else {
-              uint32_t al = a_lo, bl = b_lo, ac = accumulate;
-              for (int kk = 0; kk < kc; kk += 16) {
-                umma2_bf16_split(acc, al, desc_hi, bl, desc_hi, idesc, ac);
-                ac = 1u; al += a_kstep; bl += b_kstep;
+                for (uint32_t j = 1; j < 8; ++j)
+                  umma2_bf16_split_w(acc, a_lo + j * a_kstep, desc_hi, b_lo + j * b_kstep, desc_hi, idesc, 1u);
+              } else {
+                uint32_t al = a_lo, bl = b_lo, ac = accumulate;
+                for (int kk = 0; kk < kc; kk += 16) {
+                  umma2_bf16_split_w(acc, al, desc_hi, bl, desc_hi, idesc, ac);
+                  ac = 1u; al += a_kstep; bl += b_kstep;
+                }
               }
+              umma2_commit_u32_w(empty_u32 + 8u * stage);    // ring slot (in both CTAs) reusable once these MMAs have read it
             }
             accumulate = 1;
-            umma2_commit_u32(empty_u32 + 8u * stage);      // ring slot (in both CTAs) reusable once these MMAs have read it
             if (++stage == kTcStages) { stage = 0; phase ^= 1; }
             if (ck.w) break;
             ck = nxt; ++ckp;
           }
-          umma2_commit(&acc_full[gstep & 1]);      // accumulators complete -> epilogue warps of both CTAs
-          // side regions whose only reader was this step may now be rewritten for the next tile (prologue warps)
-          // [0]: layer-0 operand region (forward) / the whole main region once the VF-only dgrad tile is finished
-          if (si == (prog.bwd == 2 ? prog.n_steps - 1 : 0)) umma2_commit(&reg_free[0]);
-          if (si == prog.skip_step) umma2_commit(&reg_free[1]);
-          if (si == prog.aux_step) umma2_commit(&reg_free[2]);
+          {
+            umma2_commit_u32_w(smem_u32(&acc_full[gstep & 1]));      // accumulators complete -> epilogue warps of both CTAs
+            // side regions whose only reader was this step may now be rewritten for the next tile (prologue warps)
+            // [0]: layer-0 operand region (forward) / the whole main region once the VF-only dgrad tile is finished
+            if (si == (prog.bwd == 2 ? prog.n_steps - 1 : 0)) umma2_commit_u32_w(smem_u32(&reg_free[0]));
+            if (si == prog.skip_step) umma2_commit_u32_w(smem_u32(&reg_free[1]));
+            if (si == prog.aux_step) umma2_commit_u32_w(smem_u32(&reg_free[2]));
+          }
           if (tl) p.dbg_buf[64 + si * 8 + 1] = clock64();
         }
       }
