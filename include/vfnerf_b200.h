@@ -207,6 +207,12 @@ int vfnerf_vf_grid_query(const vfnerf_mlp_desc* vf, const float* vf_arena, int m
                          const float* centroid3_host, float voxel, float* out,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- host helper ------------------------------------------------------------------------------ */
+/* n uniform floats in [0,1) from torch's CPU generator engine (MT19937, 24-bit float conversion), identical to what
+ * torch.rand would draw from the same state; state624 / left / next are the engine fields of torch.get_rng_state()
+ * and are advanced in place.  HOST pointers; no device work.  Replaces the draws of ray_sampler.py:138,292,297. */
+int vfnerf_mt19937_uniform(uint32_t* state624, int32_t* left, uint32_t* next, int64_t n, float* out);
+
 /* ---- marching-cubes preprocessing of the dense grid --------------------- */
 /* evaluation/methods.py:209-278 (default flags) = mc_utils.extract_divergence (:34-85) + unify_direction (:107-166) +
  * make_comb_format (:169-223) + the block-ordered compaction, fused per cell.  pred [res^3,3] is the grid query's

@@ -144,3 +144,30 @@ def test_flat_gradient_mode_aliases_parameter_grads(model):
     ar.grad_flat = None
     for p in model.rendering_network.parameters():
         p.grad = None
+
+
+def test_fast_cpu_generator_stream_is_torch_rand():
+    """csrc/host_rng.cu: the vectorised MT19937 behind the large sampler draws reproduces torch.rand on the global CPU
+    generator bit for bit -- values AND the generator state afterwards -- from arbitrary stream positions, so seeding
+    torch.manual_seed reproduces the reference's sample positions exactly as before."""
+    import vfn_testutil  # noqa: F401  (path setup)
+    from vfnerf_b200 import _lib, samplers as S
+    _lib.build()
+    assert S._fast_rng_self_check()
+    for seed, skip, n in ((0, 0, 1 << 16), (5, 3, 70001), (9, 623, 4 * 65536 + 5), (11, 624, 1 << 18)):
+        torch.manual_seed(seed)
+        if skip:
+            torch.rand(skip)
+        st = torch.get_rng_state()
+        want = torch.rand(n)
+        st_after = torch.get_rng_state()
+        torch.set_rng_state(st)
+        got = S.cpu_generator_rand_(torch.empty(n))
+        assert torch.equal(got, want)
+        assert torch.equal(torch.get_rng_state(), st_after)
+        assert torch.equal(torch.rand(9), (torch.set_rng_state(st_after), torch.rand(9))[1])
+    # small or non-contiguous tensors take torch.rand itself
+    torch.manual_seed(1)
+    a = torch.rand(10)
+    torch.manual_seed(1)
+    assert torch.equal(S.cpu_generator_rand_(torch.empty(10)), a)

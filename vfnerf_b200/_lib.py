@@ -15,7 +15,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libvfnerf_b200.so")
-SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "optim.cu", "mc_preprocess.cu", "tc_debug.cu"]
+SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "optim.cu", "mc_preprocess.cu", "host_rng.cu", "tc_debug.cu"]
 HEADERS = ["common.cuh", "mlp_tc.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "vfnerf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -76,6 +76,7 @@ PROTOTYPES = {
     "vfnerf_ray_geometry": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "vfnerf_coarse_sample": (_I, [_I, _I, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P]),
     "vfnerf_fine_sample": (_I, [_I, _I, _I, _D, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vfnerf_mt19937_uniform": (_I, [_P, _P, _P, _L, _P]),
     "vfnerf_mc_count": (_I, [_P, _I, _P, _P, _P, _P, _P]),
     "vfnerf_mc_emit": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
     "vfnerf_sample_pdf": (_I, [_I, _I, _I, _P, _P, _P, _I, _P, _P]),

@@ -17,7 +17,7 @@ import torch
 from . import _lib, ops
 from .networks import LaplaceDensity, RenderingNetwork, VectorFieldNetwork
 from .output import NerfOutput
-from .samplers import RangeFineSampler, UniformSampler
+from .samplers import RangeFineSampler, UniformSampler, cpu_generator_rand_
 
 
 class VectorFieldNerf:
@@ -156,7 +156,7 @@ class VectorFieldNerf:
         if slot[0].numel() < n:
             slot[0] = torch.empty(n, dtype=torch.float32).pin_memory()
         host = slot[0][:n].view(rows, cols)
-        torch.rand([rows, cols], out=host)
+        cpu_generator_rand_(host)      # == torch.rand([rows, cols], out=host), same stream and state (samplers.py)
         main = torch.cuda.current_stream(dev)
         with torch.cuda.stream(ring["stream"]):
             out = host.to(dev, non_blocking=True)

@@ -13,6 +13,66 @@ from typing import Optional
 import torch
 
 
+# ---- the reference's CPU-generator stream, faster -------------------------------------------------------------
+_FAST_RNG = {"ok": None}
+
+
+def _mt_fields(raw_np):
+    """Views of the engine fields inside torch.get_rng_state() (CPUGeneratorImplStateLegacy: seed u64, left i32,
+    seeded i32, next u64, state u64[624], ...)."""
+    import numpy as np
+    return raw_np[8:12].view(np.int32), raw_np[16:24].view(np.uint64), raw_np[24:24 + 624 * 8].view(np.uint64)
+
+
+def _fast_rand_raw(host: torch.Tensor) -> None:
+    import numpy as np
+    from . import _lib
+    raw = torch.get_rng_state()
+    a = raw.numpy()
+    left_v, next_v, state_v = _mt_fields(a)
+    state = state_v.astype(np.uint32)
+    left = np.array([left_v[0]], dtype=np.int32)
+    nxt = np.array([next_v[0]], dtype=np.uint32)
+    _lib.check(_lib.lib().vfnerf_mt19937_uniform(state.ctypes.data, left.ctypes.data, nxt.ctypes.data, host.numel(),
+                                                 host.data_ptr()), "vfnerf_mt19937_uniform")
+    state_v[:] = state
+    left_v[0] = left[0]
+    next_v[0] = nxt[0]
+    torch.set_rng_state(raw)
+
+
+def _fast_rng_self_check() -> bool:
+    """The fast path is used only if, from a copy of the current generator state, it reproduces torch.rand bit for bit
+    (values and final state) across a block boundary; the caller's generator state is left untouched."""
+    saved = torch.get_rng_state()
+    try:
+        if saved.numel() != 5056 or saved.dtype != torch.uint8:
+            return False
+        n = 3 * 624 + 17
+        want = torch.rand(n)
+        after_want = torch.get_rng_state()
+        torch.set_rng_state(saved)
+        got = torch.empty(n)
+        _fast_rand_raw(got)
+        return bool(torch.equal(got, want) and torch.equal(torch.get_rng_state(), after_want))
+    except Exception:
+        return False
+    finally:
+        torch.set_rng_state(saved)
+
+
+def cpu_generator_rand_(host: torch.Tensor) -> torch.Tensor:
+    """``torch.rand(host.shape, out=host)`` on the global CPU generator -- same numbers, same generator state afterwards --
+    through the vectorised MT19937 of csrc/host_rng.cu when ``host`` is a large contiguous float32 CPU tensor."""
+    if host.numel() >= (1 << 16) and host.dtype == torch.float32 and host.is_contiguous() and not host.is_cuda:
+        if _FAST_RNG["ok"] is None:
+            _FAST_RNG["ok"] = _fast_rng_self_check()
+        if _FAST_RNG["ok"]:
+            _fast_rand_raw(host)
+            return host
+    return torch.rand(host.shape, out=host)
+
+
 class RaySampler:
     def __init__(self, near: float, far: float, N_samples: int) -> None:
         self.near, self.far, self._N_samples = near, far, N_samples
