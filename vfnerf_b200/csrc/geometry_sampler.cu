@@ -418,28 +418,33 @@ int launch_pdf_fine_sample(int n_rays, int n_coarse, int n_fine, const float* z_
 // Merge of per-sample results computed separately for the coarse and the fine candidates into the
 // merged (sorted) sample order of vector_field_nerf.py:284-312.  The reference re-evaluates both MLPs
 // on all merged points; the coarse half of those points is bit-identical to the coarse sweep's points,
-// so their results are moved instead of recomputed.  One thread per output float, two tensors per pass.
+// so their results are moved instead of recomputed.  One thread per merged sample, two [.,3] tensors per pass.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-merge_samples_kernel(int64_t total, int n_coarse, int n_fine, const uint8_t* __restrict__ src,
+merge_samples_kernel(int64_t n_points, int n_coarse, int n_fine, const uint8_t* __restrict__ src,
                      const float* __restrict__ a_coarse, const float* __restrict__ a_fine, float* __restrict__ a_out,
                      const float* __restrict__ b_coarse, const float* __restrict__ b_fine, float* __restrict__ b_out) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into [R, N, 3]
-  if (e >= total) return;
+  const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // merged sample index r * N + j
+  if (pt >= n_points) return;
   const int N = n_coarse + n_fine;
-  const int64_t pt = e / 3;
-  const int c = (int)(e - 3 * pt);
   const int64_t r = pt / N;
   const int k = src[pt];
-  const int64_t from = (k < n_coarse) ? (r * n_coarse + k) * 3 + c : (r * n_fine + (k - n_coarse)) * 3 + c;
-  a_out[e] = __ldg((k < n_coarse ? a_coarse : a_fine) + from);
-  if (b_out) b_out[e] = __ldg((k < n_coarse ? b_coarse : b_fine) + from);
+  const bool c = k < n_coarse;
+  const int64_t from = 3 * (c ? r * n_coarse + k : r * n_fine + (k - n_coarse));
+  const float* pa = (c ? a_coarse : a_fine) + from;
+  const float a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+  a_out[3 * pt] = a0; a_out[3 * pt + 1] = a1; a_out[3 * pt + 2] = a2;
+  if (b_out) {
+    const float* pb = (c ? b_coarse : b_fine) + from;
+    const float b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+    b_out[3 * pt] = b0; b_out[3 * pt + 1] = b1; b_out[3 * pt + 2] = b2;
+  }
 }
 
 int launch_merge_samples(int n_rays, int n_coarse, int n_fine, const uint8_t* src, const float* a_coarse,
                          const float* a_fine, float* a_out, const float* b_coarse, const float* b_fine,
                          float* b_out, cudaStream_t s) {
-  int64_t total = (int64_t)n_rays * (n_coarse + n_fine) * 3;
+  int64_t total = (int64_t)n_rays * (n_coarse + n_fine);
   if (total <= 0) return 0;
   merge_samples_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(total, n_coarse, n_fine, src, a_coarse, a_fine,
                                                                         a_out, b_coarse, b_fine, b_out);
