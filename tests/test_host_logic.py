@@ -171,3 +171,23 @@ def test_fast_cpu_generator_stream_is_torch_rand():
     a = torch.rand(10)
     torch.manual_seed(1)
     assert torch.equal(S.cpu_generator_rand_(torch.empty(10)), a)
+
+
+def test_schedule_flag_and_arena_spot_check(model):
+    """recompute_coarse selects the literal two-evaluation schedule through cfg.flags; the O(1) arena validation still
+    notices storage that was swapped behind the module's back (first / last tensor), not only Module._apply."""
+    from vfnerf_b200 import _lib
+    assert model._render_cfg(8, False).flags == 0
+    model.recompute_coarse = True
+    assert model._render_cfg(8, False).flags == _lib.FLAG_RECOMPUTE_COARSE
+    model.recompute_coarse = False
+    net = model.rendering_network
+    ar = net.arena()
+    flat0 = ar.flat
+    w = net.layers[0][0].weight
+    w.data = w.data.clone()                    # manual swap of the first tensor: no _apply, no load_state_dict
+    ar2 = net.arena()
+    assert ar2.flat is not flat0
+    assert w.data_ptr() == ar2.flat.data_ptr() + 4 * ar2.desc.w_off[0]
+    net.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})     # marks dirty, aliasing kept
+    assert net.arena().flat is ar2.flat
