@@ -538,7 +538,7 @@ def main():
         keep_g = torch.empty(Ng ** 3, dtype=torch.uint8, device=dev)
         cnt_g = torch.zeros((Ng ** 3 + 255) // 256, dtype=torch.int32, device=dev)
         kernels["mc_count_kernel"] = (lambda: L.vfnerf_mc_count(pred_g.data_ptr(), Ng, keep_g.data_ptr(), cnt_g.data_ptr(), None,
-                                                                None, sp), Ng ** 3 * 13)
+                                                                None, None, sp), Ng ** 3 * 13)
         hbm_peak = peaks()[0]["hbm_gbs"]
         hbm = {"rays": Rh, "n_coarse": Nc, "n_fine": Nf, "peak_gbs": hbm_peak, "kernels": {}}
         for name, (fn, nbytes) in kernels.items():

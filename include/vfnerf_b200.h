@@ -219,14 +219,22 @@ int vfnerf_mt19937_uniform(uint32_t* state624, int32_t* left, uint32_t* next, in
  * output (x index slowest).  Cells are visited in the reference's order: 2x2x2 blocks in C order, `inc` order inside.
  *   vfnerf_mc_count: keep [8*(res/2)^3] = 1 for cells whose corner pairs differ; cta_counts [ceil(n/256)] kept cells per
  *     256-cell CTA.  Optional dense outputs in grid order for tests: div_raw [res^3] (raw divergence of interior cells,
- *     caller zero-fills), choice [res^3] (bit s = side of corner s).
+ *     caller zero-fills), choice [res^3] (bit s = side of corner s).  surface (nullable) [res^3] u8 in grid order: surface
+ *     cells decided elsewhere (the reference's smooth_after: divergence of the raw field, sides of the smoothed one).
  *   vfnerf_mc_emit: cta_offsets = inclusive scan of cta_counts (int64); writes cells [M,3], comb [M,28], udf [M,28,2]
  *     -- exactly the arrays contrastive_marching_cubes receives (methods.py:272-283) before their flattening reshape. */
 #define VFNERF_MC_CTA 256
 int vfnerf_mc_count(const float* pred, int resolution, uint8_t* keep, int32_t* cta_counts, float* div_raw,
-                    uint8_t* choice, void* stream);
+                    uint8_t* choice, const uint8_t* surface, void* stream);
 int vfnerf_mc_emit(const float* pred, int resolution, const uint8_t* keep, const int64_t* cta_offsets,
                    int32_t* cells, float* comb, float* udf, void* stream);
+
+/* smooth_vf (evaluation/utils/guassian_smoothing.py:81-97; the optional smooth_after / smooth_all steps of
+ * methods.py:211-218): replicate-padded depthwise 3-D gaussian of the [res^3,3] grid as three 1-D passes.  taps_host: the
+ * kernel_size (odd, <= 31) normalised 1-D taps, HOST floats; tmp: a second [res^3,3] device buffer; out may be `in`'s size
+ * only (no aliasing with tmp). */
+int vfnerf_smooth_vf(const float* in, float* tmp, float* out, int resolution, int kernel_size,
+                     const float* taps_host, void* stream);
 
 /* ---- stage entry points (one per SURVEY.md §8(a) row; used by the parity tests) ------------- */
 /* a1: get_ray_directions_and_cam_location, utils/rendering.py:12-60 */

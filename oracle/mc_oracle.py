@@ -108,3 +108,37 @@ def mc_preprocess(pred: torch.Tensor, N: int):
     n = nrm[cells[:, 0], cells[:, 1], cells[:, 2]]
     mask = c.sum(-1) > 0
     return cells[mask], c[mask], n[mask]
+
+
+def smooth_vf(vf: torch.Tensor, k: int = 3, sigma: float = 1.0) -> torch.Tensor:
+    """evaluation/utils/guassian_smoothing.py:81-97 (GaussianSmoothing :24-72): replicate-padded depthwise k^3 gaussian of a
+    [N,N,N,3] grid, restated as the explicit weighted sum of shifted copies.  The kernel is the reference's: the product
+    over axes of 1/(sigma sqrt(2 pi)) exp(-((i - mean) / (2 sigma))^2), divided by its sum, all in fp32."""
+    ax = torch.arange(k, dtype=torch.float32)
+    mean = (k - 1) / 2
+    g1 = 1 / (sigma * math.sqrt(2 * math.pi)) * torch.exp(-(((ax - mean) / (2 * sigma)) ** 2))
+    kern = g1[:, None, None] * g1[None, :, None] * g1[None, None, :]
+    kern = kern / torch.sum(kern)
+    h = k // 2
+    N = vf.shape[0]
+    pad = F.pad(vf.permute(3, 0, 1, 2).unsqueeze(0), (h, h, h, h, h, h), mode="replicate")[0]    # [3, N+2h, ...]
+    out = torch.zeros(3, N, N, N)
+    for a in range(k):
+        for b in range(k):
+            for c in range(k):
+                out = out + kern[a, b, c] * pad[:, a:a + N, b:b + N, c:c + N]
+    return out.permute(1, 2, 3, 0)
+
+
+def mc_preprocess_smooth_after(pred: torch.Tensor, N: int):
+    """methods.py:209-278 with smooth_after=True: divergence of the raw field, sides / norms of the k = 9, sigma = 2
+    smoothed one."""
+    div = extract_divergence(pred, N)
+    sm = smooth_vf(pred.reshape(N, N, N, 3), 9, 2.0).reshape(N ** 3, 3)
+    choice = unify_direction(div, sm, N)
+    diff, nrm = comb_format(choice, sm, N)
+    cells = block_order_cells(N)
+    c = diff[cells[:, 0], cells[:, 1], cells[:, 2]]
+    n = nrm[cells[:, 0], cells[:, 1], cells[:, 2]]
+    mask = c.sum(-1) > 0
+    return cells[mask], c[mask], n[mask]

@@ -89,3 +89,28 @@ def test_mc_preprocess_edge_cases(built_lib):
         M.mc_preprocess(pred, N)                       # host tensor: no CPU path
     with pytest.raises(ValueError):
         M.mc_preprocess(pred[:-1].to(DEV), N)
+
+
+def test_smooth_vf_and_smooth_after_chain_match_reference_golden(built_lib):
+    """smooth_vf as three 1-D passes (csrc/mc_preprocess.cu) vs the reference's k^3-tap conv3d, and the smooth_after
+    variant of the chain (divergence of the raw field, sides and norms of the k = 9 smoothed one) through
+    mc_preprocess(..., surface=...)."""
+    from vfnerf_b200 import mc_utils as M
+    z = np.load(os.path.join(U.GOLDEN_DIR, "mc_smooth.npz"))
+    pred = torch.from_numpy(z["pred"])
+    N = round(pred.shape[0] ** (1 / 3))
+    for k, sigma in ((3, 1.0), (9, 2.0)):
+        got = M.smooth_vf(pred.reshape(N, N, N, 3).to(DEV), k=k, sigma=sigma).cpu()
+        err = (got - torch.from_numpy(z[f"smooth_k{k}"])).abs().max().item()
+        print(f"smooth_vf k={k}: max abs err {err:.1e}")
+        assert err <= 2e-6
+    div = M.extract_divergence(pred.to(DEV), N)
+    sm = M.smooth_vf(pred.reshape(N, N, N, 3).to(DEV), k=9, sigma=2.0).reshape(N ** 3, 3)
+    cells, comb, udf = (t.cpu() for t in M.mc_preprocess(sm, N, surface=div))
+    ref_cells, ref_comb, ref_udf = (torch.from_numpy(z[f"after.{k}"]) for k in ("cells", "comb", "udf"))
+    assert torch.equal(cells, ref_cells)
+    agree = (comb == ref_comb).all(dim=1).float().mean().item()
+    assert agree >= 0.995, agree
+    assert (udf - ref_udf).abs().max().item() <= 2e-6
+    with pytest.raises(ValueError):
+        M.smooth_vf(pred.to(DEV), 3, 1.0)              # wants [N,N,N,3]

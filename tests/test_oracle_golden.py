@@ -131,3 +131,20 @@ def test_weight_function_oracles_match_reference_golden(tag):
     for norm in (0, 1):
         assert torch.equal(U.O.nerf_weights(sg, zz, bool(norm)), torch.from_numpy(z[f"{tag}.nerf.{norm}"]))
         assert torch.equal(U.O.volsdf_weights(zz, sg, bool(norm)), torch.from_numpy(z[f"{tag}.volsdf.{norm}"]))
+
+
+def test_smooth_oracle_matches_reference_golden():
+    """smooth_vf (guassian_smoothing.py:81-97) and the smooth_after variant of the mesh preprocessing: the oracle
+    restatements vs outputs of the live reference (tests/golden/make_golden_smooth.py)."""
+    import os
+    from oracle import mc_oracle as MO
+    z = np.load(os.path.join(U.GOLDEN_DIR, "mc_smooth.npz"))
+    pred = torch.from_numpy(z["pred"])
+    N = round(pred.shape[0] ** (1 / 3))
+    for k, sigma in ((3, 1.0), (9, 2.0)):
+        got = MO.smooth_vf(pred.reshape(N, N, N, 3), k, sigma)
+        assert (got - torch.from_numpy(z[f"smooth_k{k}"])).abs().max().item() <= 2e-6
+    cells, comb, udf = MO.mc_preprocess_smooth_after(pred, N)
+    assert torch.equal(cells.int(), torch.from_numpy(z["after.cells"]))
+    assert torch.equal(comb, torch.from_numpy(z["after.comb"]))
+    assert (udf - torch.from_numpy(z["after.udf"])).abs().max().item() <= 2e-6

@@ -77,7 +77,8 @@ PROTOTYPES = {
     "vfnerf_coarse_sample": (_I, [_I, _I, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P]),
     "vfnerf_fine_sample": (_I, [_I, _I, _I, _D, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vfnerf_mt19937_uniform": (_I, [_P, _P, _P, _L, _P]),
-    "vfnerf_mc_count": (_I, [_P, _I, _P, _P, _P, _P, _P]),
+    "vfnerf_smooth_vf": (_I, [_P, _P, _P, _I, _I, C.POINTER(C.c_float), _P]),
+    "vfnerf_mc_count": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
     "vfnerf_mc_emit": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
     "vfnerf_sample_pdf": (_I, [_I, _I, _I, _P, _P, _P, _I, _P, _P]),
     "vfnerf_pdf_fine_sample": (_I, [_I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P]),

@@ -661,13 +661,18 @@ int vfnerf_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, doubl
 }
 
 int vfnerf_mc_count(const float* pred, int resolution, uint8_t* keep, int32_t* cta_counts, float* div_raw,
-                    uint8_t* choice, void* stream) {
-  return launch_mc_count(pred, resolution, keep, cta_counts, div_raw, choice, reinterpret_cast<cudaStream_t>(stream));
+                    uint8_t* choice, const uint8_t* surface, void* stream) {
+  return launch_mc_count(pred, resolution, keep, cta_counts, div_raw, choice, surface, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vfnerf_mc_emit(const float* pred, int resolution, const uint8_t* keep, const int64_t* cta_offsets, int32_t* cells,
                    float* comb, float* udf, void* stream) {
   return launch_mc_emit(pred, resolution, keep, cta_offsets, cells, comb, udf, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vfnerf_smooth_vf(const float* in, float* tmp, float* out, int resolution, int kernel_size, const float* taps_host,
+                     void* stream) {
+  return launch_smooth_vf(in, tmp, out, resolution, kernel_size, taps_host, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vfnerf_sample_pdf(int n_rays, int n_bins, int n_samples, const float* bins, const float* weights, const float* u,

@@ -87,9 +87,12 @@ int launch_merge_samples(int n_rays, int n_coarse, int n_fine, const uint8_t* sr
 int launch_volume_weights(int n_rays, int n_samples, int mode, int normalize, const float* sigma, const float* z,
                           float* weights, cudaStream_t s);
 // mc_preprocess.cu
-int launch_mc_count(const float* pred, int N, uint8_t* keep, int* cta_counts, float* div_raw, uint8_t* choice, cudaStream_t s);
+int launch_mc_count(const float* pred, int N, uint8_t* keep, int* cta_counts, float* div_raw, uint8_t* choice,
+                    const uint8_t* surface, cudaStream_t s);
 int launch_mc_emit(const float* pred, int N, const uint8_t* keep, const int64_t* cta_offsets, int* cells, float* comb,
                    float* udf, cudaStream_t s);
+
+int launch_smooth_vf(const float* in, float* tmp, float* out, int N, int k, const float* w_host, cudaStream_t s);
 
 // density_composite.cu
 int launch_density_weights(const vfnerf_render_cfg& cfg, int n_rays, int n_samples,

@@ -94,7 +94,8 @@ __device__ __forceinline__ void mc_cell_of(int64_t q, int N, int& i, int& j, int
 
 __global__ void __launch_bounds__(kMcThreads)
 mc_count_kernel(const float* __restrict__ pred, int N, int64_t n_q, uint8_t* __restrict__ keep,
-                int* __restrict__ cta_counts, float* __restrict__ div_raw, uint8_t* __restrict__ choice_out) {
+                int* __restrict__ cta_counts, float* __restrict__ div_raw, uint8_t* __restrict__ choice_out,
+                const uint8_t* __restrict__ surface) {
   const int64_t q = (int64_t)blockIdx.x * kMcThreads + threadIdx.x;
   int kept = 0;
   if (q < n_q) {
@@ -104,9 +105,15 @@ mc_count_kernel(const float* __restrict__ pred, int N, int64_t n_q, uint8_t* __r
     if (i < N - 1 && j < N - 1 && k < N - 1) {               // boundary cells never carry a surface (mc_utils.py:79-80)
       McCell c;
       mc_load(pred, N, i, j, k, c);
-      const float dv = mc_divergence(c);
-      if (div_raw) div_raw[((int64_t)i * N + j) * N + k] = dv;
-      if (dv <= -0.5f) {
+      const int64_t cell = ((int64_t)i * N + j) * N + k;
+      bool surf;
+      if (surface && !div_raw) surf = surface[cell] != 0;          // surface cells decided on another field (smooth_after)
+      else {
+        const float dv = mc_divergence(c);
+        if (div_raw) div_raw[cell] = dv;
+        surf = surface ? surface[cell] != 0 : dv <= -0.5f;
+      }
+      if (surf) {
         bits = mc_choice(c);
         kept = (bits != 0u && bits != 0xFFu) ? 1 : 0;        // some pair of corners on different sides
       }
@@ -155,12 +162,12 @@ mc_emit_kernel(const float* __restrict__ pred, int N, int64_t n_q, const uint8_t
 }
 
 int launch_mc_count(const float* pred, int N, uint8_t* keep, int* cta_counts, float* div_raw, uint8_t* choice,
-                    cudaStream_t s) {
+                    const uint8_t* surface, cudaStream_t s) {
   VFN_REQUIRE(pred && keep && cta_counts, "mc_count: null argument");
   VFN_REQUIRE(N >= 2 && N <= 2048, "mc_count: resolution %d out of range", N);
   const int64_t n_q = 8 * (int64_t)(N / 2) * (N / 2) * (N / 2);
   if (n_q == 0) return 0;
-  mc_count_kernel<<<(unsigned)ceil_div64(n_q, kMcThreads), kMcThreads, 0, s>>>(pred, N, n_q, keep, cta_counts, div_raw, choice);
+  mc_count_kernel<<<(unsigned)ceil_div64(n_q, kMcThreads), kMcThreads, 0, s>>>(pred, N, n_q, keep, cta_counts, div_raw, choice, surface);
   VFN_LAUNCH_CHECK();
   return 0;
 }
@@ -171,6 +178,55 @@ int launch_mc_emit(const float* pred, int N, const uint8_t* keep, const int64_t*
   const int64_t n_q = 8 * (int64_t)(N / 2) * (N / 2) * (N / 2);
   if (n_q == 0) return 0;
   mc_emit_kernel<<<(unsigned)ceil_div64(n_q, kMcThreads), kMcThreads, 0, s>>>(pred, N, n_q, keep, cta_offsets, cells, comb, udf);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vfn
+
+// ---------------------------------------------------------------------------------------------
+// smooth_vf (evaluation/utils/guassian_smoothing.py:81-97): depthwise 3-D gaussian of the [N,N,N,3] vector grid with
+// replicate padding.  The reference's k^3-tap kernel is the outer product of one 1-D factor per axis (normalised as a
+// whole, which equals normalising each factor), so it runs as three 1-D passes of k taps: 24 B/point of traffic per
+// pass instead of 27 (k = 3) or 729 (k = 9) gathered taps per point.  One thread per grid point, taps clamped to the grid.
+// ---------------------------------------------------------------------------------------------
+namespace vfn {
+
+constexpr int kMaxTaps = 31;
+struct SmoothW { float w[kMaxTaps]; };
+
+__global__ void __launch_bounds__(256)
+smooth_axis_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int64_t stride, int k, SmoothW W) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)N * N * N;
+  if (p >= total) return;
+  const int c = (int)((p / stride) % N);           // coordinate along the smoothed axis
+  const int h = k >> 1;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int t = 0; t < k; ++t) {
+    const int cc = min(max(c + t - h, 0), N - 1);
+    const float* q = in + 3 * (p + (int64_t)(cc - c) * stride);
+    const float w = W.w[t];
+    a0 = fmaf(w, __ldg(q), a0); a1 = fmaf(w, __ldg(q + 1), a1); a2 = fmaf(w, __ldg(q + 2), a2);
+  }
+  out[3 * p] = a0; out[3 * p + 1] = a1; out[3 * p + 2] = a2;
+}
+
+int launch_smooth_vf(const float* in, float* tmp, float* out, int N, int k, const float* w_host, cudaStream_t s) {
+  VFN_REQUIRE(in && tmp && out && w_host, "smooth_vf: null argument");
+  VFN_REQUIRE(k >= 1 && (k & 1) && k <= kMaxTaps, "smooth_vf: kernel size %d must be odd and <= %d", k, kMaxTaps);
+  VFN_REQUIRE(N >= 1 && N <= 2048, "smooth_vf: resolution %d out of range", N);
+  VFN_REQUIRE(in != tmp && tmp != out, "smooth_vf: tmp must not alias in / out");
+  SmoothW W{};
+  for (int t = 0; t < k; ++t) W.w[t] = w_host[t];
+  const int64_t total = (int64_t)N * N * N;
+  const unsigned grid = (unsigned)ceil_div64(total, 256);
+  // x index is slowest (stride N^2), z fastest (stride 1): in -> out (z), out -> tmp (y), tmp -> out (x)
+  smooth_axis_kernel<<<grid, 256, 0, s>>>(in, out, N, 1, k, W);
+  VFN_LAUNCH_CHECK();
+  smooth_axis_kernel<<<grid, 256, 0, s>>>(out, tmp, N, N, k, W);
+  VFN_LAUNCH_CHECK();
+  smooth_axis_kernel<<<grid, 256, 0, s>>>(tmp, out, N, (int64_t)N * N, k, W);
   VFN_LAUNCH_CHECK();
   return 0;
 }
