@@ -210,7 +210,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    U = oracle_pack()     # test helpers build the model; the oracle itself is only used by cpu_baseline
+    import types
+    from vfnerf_b200 import synthetic as _S
+    U = types.SimpleNamespace(S=_S, make_model=_S.make_model)    # this arm imports nothing from oracle/ or tests/
     from vfnerf_b200 import _lib
     _lib.build()
     L = _lib.lib()

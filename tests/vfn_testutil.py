@@ -44,26 +44,7 @@ def oracle_cfg(case):
                 multires=6, multires_view=4, skip_in=(4,))
 
 
-def make_config(case, device):
-    return VFNerfConfig(
-        vf_net_config=VFNetConfig(dimensions=list(case["vf_hidden"]), feature_vector_dims=case["feat"]),
-        rendering_net_config=RenderingNetConfig(dimensions=list(case["rn_hidden"]), feature_vector_dims=case["feat"]),
-        ray_sampler_config=RaySamplerConfig(n_samples=case["n_coarse"], n_importance=case["n_fine"],
-                                            perturb=case["perturb"], near=case["near"], far=case["far"],
-                                            fine_range=case["fine_range"], max_samples=case["max_samples"]),
-        cuda_config=CudaConfig(device=torch.device(device), num_gpus=1),
-        scheduler_config=SchedulerConfig(), density_config=DensityConfig(),
-        cos_sim_weights=[0.09] * case["window"], dir_to_normal_th=case["dir_to_normal_th"])
-
-
-def make_model(case, state, device, precision="fp32"):
-    from vfnerf_b200 import VectorFieldNerf
-    model = VectorFieldNerf(make_config(case, device), precision=precision)
-    model.vector_field_network.load_state_dict(state["vf_net"])
-    model.rendering_network.load_state_dict(state["rendering_net"])
-    model.density.load_state_dict(state["density"])
-    model.eval()
-    return model
+make_config, make_model = S.make_config, S.make_model      # (live in the package: bench.py builds its models with them too)
 
 
 def t(z, key):

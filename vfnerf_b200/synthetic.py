@@ -196,3 +196,31 @@ def synthetic_vector_grid(N: int, seed: int = 0, scale: float = 1.0) -> torch.Te
     to_plane[:, 2] = -0.8 - p[:, 2]
     v = torch.where(to_sphere.norm(dim=1, keepdim=True) < to_plane.norm(dim=1, keepdim=True), to_sphere, to_plane)
     return torch.tanh(3.0 * v) + 0.02 * torch.randn(N ** 3, 3, generator=g)
+
+
+def make_config(case: dict, device):
+    """VFNerfConfig of a synthetic / golden case (dict with vf_hidden, feat, rn_hidden, n_coarse, n_fine, perturb, near,
+    far, fine_range, max_samples, window, dir_to_normal_th) -- the shipped confs/vf_nerf.conf shapes by default."""
+    from .config import (CudaConfig, DensityConfig, RaySamplerConfig, RenderingNetConfig, SchedulerConfig, VFNerfConfig,
+                         VFNetConfig)
+    return VFNerfConfig(
+        vf_net_config=VFNetConfig(dimensions=list(case["vf_hidden"]), feature_vector_dims=case["feat"]),
+        rendering_net_config=RenderingNetConfig(dimensions=list(case["rn_hidden"]), feature_vector_dims=case["feat"]),
+        ray_sampler_config=RaySamplerConfig(n_samples=case["n_coarse"], n_importance=case["n_fine"],
+                                            perturb=case["perturb"], near=case["near"], far=case["far"],
+                                            fine_range=case["fine_range"], max_samples=case["max_samples"]),
+        cuda_config=CudaConfig(device=torch.device(device), num_gpus=1),
+        scheduler_config=SchedulerConfig(), density_config=DensityConfig(),
+        cos_sim_weights=[0.09] * case["window"], dir_to_normal_th=case["dir_to_normal_th"])
+
+
+def make_model(case: dict, state: dict, device, precision: str = "fp32"):
+    """A vfnerf_b200.VectorFieldNerf for `case` with the weights of `state` ({"vf_net", "rendering_net", "density"}), in
+    eval mode."""
+    from .nerf import VectorFieldNerf
+    model = VectorFieldNerf(make_config(case, device), precision=precision)
+    model.vector_field_network.load_state_dict(state["vf_net"])
+    model.rendering_network.load_state_dict(state["rendering_net"])
+    model.density.load_state_dict(state["density"])
+    model.eval()
+    return model
