@@ -8,9 +8,10 @@ import vfn_testutil as U
 from vfnerf_b200 import ops
 
 rays = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"          # bf16 | bf16x3
 N = 128
 case, z = U.load_golden("full_det")
-model = U.make_model(case, U.case_state(case, z), "cuda", precision="bf16")
+model = U.make_model(case, U.case_state(case, z), "cuda", precision=prec)
 pts = (torch.rand(rays * N, 3, device="cuda") - 0.5) * 6
 dirs = torch.nn.functional.normalize(torch.randn(rays, 3, device="cuda"), dim=1)
 ws = None
@@ -25,4 +26,4 @@ with torch.no_grad():
     e1.record()
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print(f"{rays * N} points: {ms:.3f} ms/launch, {1592832 * rays * N / ms / 1e9:.1f} TFLOP/s algorithmic")
+print(f"{prec}: {rays * N} points: {ms:.3f} ms/launch, {1592832 * rays * N / ms / 1e9:.1f} TFLOP/s algorithmic")

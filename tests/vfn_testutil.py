@@ -61,3 +61,16 @@ def discontinuity_guard(oracle_out, case, eps=2e-4):
     if case["dir_to_normal_th"] > -1.0:
         risky |= c.abs() < eps
     return ~risky.any(dim=1)
+
+
+def reference_grid_points(res, scale, translation, centroid):
+    """Restatement of the grid construction of evaluation/methods.py:194-208 (z fastest, fp32 op order)."""
+    idx = torch.arange(0, res ** 3, 1, dtype=torch.long)
+    samples = torch.zeros(res ** 3, 3)
+    samples[:, 2] = idx % res
+    samples[:, 1] = (idx // res) % res
+    samples[:, 0] = ((idx // res) // res) % res
+    vs = scale * 2.0 / (res - 1)
+    for c in range(3):
+        samples[:, c] = (samples[:, c] * vs) + (-scale) + translation[c] + centroid[c]
+    return samples

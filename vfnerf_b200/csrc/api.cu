@@ -254,13 +254,13 @@ static int make_plan(const vfnerf_render_cfg& cfg, const vfnerf_mlp_desc& vf, co
       p.d_colors = c.f(3 * p.P);
     }
   } else {
-    VFN_REQUIRE(cfg.precision == VFNERF_PREC_BF16, "precision bf16x3 is not built yet; use fp32 or bf16");
-    if (int e = tc_carve(c.base, c.off, cfg.multires, cfg.multires_view, cfg.skip_layer, vf, &rn, p.tc, p.P, keep)) return e;
+    if (int e = tc_carve(c.base, c.off, cfg.multires, cfg.multires_view, cfg.skip_layer, vf, &rn, p.tc, p.P, keep,
+                         cfg.precision == VFNERF_PREC_BF16X3)) return e;
   }
   // Sized for every call (the workspace query does not know about z_override); used when it applies.  With a stash
   // (training) the two launches fill consecutive tile ranges of the same stash, so the coarse block must end on a tile
   // boundary; the backward then runs over the points in evaluation order (render_tail_bwd scatters through `src`).
-  p.reuse_coarse = cfg.precision == VFNERF_PREC_BF16 && !(cfg.flags & VFNERF_FLAG_RECOMPUTE_COARSE) &&
+  p.reuse_coarse = cfg.precision != VFNERF_PREC_FP32 && !(cfg.flags & VFNERF_FLAG_RECOMPUTE_COARSE) &&
                    (!keep || p.Pc % 128 == 0);
   p.normals_cf = p.colors_cf = p.colors_c = p.pts_f = p.normals_f = p.colors_f = nullptr; p.src = nullptr;
   if (p.reuse_coarse) {
@@ -315,7 +315,7 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
               (long long)workspace_bytes, (long long)p.bytes);
   VFN_REQUIRE(out->points && out->normals && out->rgb && out->depth && out->z_vals && out->colors,
               "render_fwd: required output pointer is null");
-  VFN_REQUIRE(!(z_override && keep_for_backward && cfg->precision == VFNERF_PREC_BF16 &&
+  VFN_REQUIRE(!(z_override && keep_for_backward && cfg->precision != VFNERF_PREC_FP32 &&
                 !(cfg->flags & VFNERF_FLAG_RECOMPUTE_COARSE)),
               "render_fwd: z_override with keep_for_backward needs VFNERF_FLAG_RECOMPUTE_COARSE in cfg.flags (render_bwd "
               "derives the order of the stash from cfg alone)");
@@ -487,10 +487,15 @@ static void make_vf_plan(const vfnerf_mlp_desc& vf, int64_t n, int multires, int
   p.bytes = c.off;
 }
 
+static int tc_precision(int precision, const char* who) {
+  VFN_REQUIRE(precision == VFNERF_PREC_BF16 || precision == VFNERF_PREC_BF16X3, "%s: unknown precision %d", who, precision);
+  return 0;
+}
+
 static int vf_tc_plan(const vfnerf_mlp_desc& vf, int multires, int skip_layer, void* ws, TcPlan& plan, int64_t& bytes,
-                      int64_t n_points = 0, int keep = 0) {
+                      int64_t n_points = 0, int keep = 0, int x3 = 0) {
   int64_t off = 0;
-  if (int e = tc_carve(reinterpret_cast<char*>(ws), off, multires, 0, skip_layer, vf, nullptr, plan, n_points, keep)) return e;
+  if (int e = tc_carve(reinterpret_cast<char*>(ws), off, multires, 0, skip_layer, vf, nullptr, plan, n_points, keep, x3)) return e;
   bytes = off;
   return 0;
 }
@@ -499,12 +504,12 @@ int64_t vfnerf_vf_workspace_bytes(const vfnerf_mlp_desc* vf, int64_t n_points, i
                                   int keep_for_backward, int precision) {
   if (!vf) { set_error("null argument"); return -1; }
   if (precision != VFNERF_PREC_FP32) {
-    if (precision != VFNERF_PREC_BF16) { set_error("vf query: only fp32 and bf16 are built"); return -1; }
+    if (tc_precision(precision, "vf_workspace_bytes")) return -1;
     TcPlan plan;
     int64_t bytes = 0;
     int skip = -1;
     for (int l = 1; l < vf->n_layers; ++l) if (vf->in_dim[l] != vf->out_dim[l - 1]) skip = l;
-    if (vf_tc_plan(*vf, multires, skip, nullptr, plan, bytes, n_points, keep_for_backward)) return -1;
+    if (vf_tc_plan(*vf, multires, skip, nullptr, plan, bytes, n_points, keep_for_backward, precision == VFNERF_PREC_BF16X3)) return -1;
     return bytes + 1024;
   }
   VfPlan p;
@@ -522,11 +527,12 @@ int vfnerf_vf_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
   if (n_points == 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (precision != VFNERF_PREC_FP32) {
-    VFN_REQUIRE(precision == VFNERF_PREC_BF16, "vf_fwd: only fp32 and bf16 are built");
+    if (int e = tc_precision(precision, "vf_fwd")) return e;
     VFN_REQUIRE(n_out_cols == 3 || n_out_cols == vf->out_dim[vf->n_layers - 1], "vf_fwd(bf16): n_out_cols must be 3 or all");
     TcPlan plan;
     int64_t bytes = 0;
-    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes, n_points, keep_for_backward)) return e;
+    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes, n_points, keep_for_backward,
+                           precision == VFNERF_PREC_BF16X3)) return e;
     VFN_REQUIRE(workspace && workspace_bytes >= bytes, "vf_fwd: workspace too small");
     if (int e = tc_prepare(*vf, vf_arena, nullptr, nullptr, bn_eps, plan, s)) return e;
     const bool full = n_out_cols > 3;
@@ -549,7 +555,7 @@ int64_t vfnerf_mlp_points_workspace_bytes(const vfnerf_mlp_desc* vf, const vfner
   if (!vf || !rn) { set_error("null argument"); return -1; }
   TcPlan plan;
   int64_t off = 0;
-  if (tc_carve(nullptr, off, multires, multires_view, skip_layer, *vf, rn, plan)) return -1;
+  if (tc_carve(nullptr, off, multires, multires_view, skip_layer, *vf, rn, plan, 0, 0, 1)) return -1;   // the larger (bf16x3) images
   return off + 1024;
 }
 
@@ -559,12 +565,14 @@ int vfnerf_mlp_points_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, cons
                           int64_t n_points, float* normals, float* colors, void* workspace,
                           int64_t workspace_bytes, int repack, void* stream) {
   VFN_REQUIRE(vf && vf_arena && rn && rn_arena && points && ray_dirs && normals && colors, "mlp_points_fwd: null argument");
-  VFN_REQUIRE(precision == VFNERF_PREC_BF16, "mlp_points_fwd: only the bf16 tensor-core path implements this entry");
+  VFN_REQUIRE(precision == VFNERF_PREC_BF16 || precision == VFNERF_PREC_BF16X3,
+              "mlp_points_fwd: only the tensor-core paths (bf16, bf16x3) implement this entry");
   if (int e = validate_vf(*vf, multires, skip_layer)) return e;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   TcPlan plan;
   int64_t off = 0;
-  if (int e = tc_carve(reinterpret_cast<char*>(workspace), off, multires, multires_view, skip_layer, *vf, rn, plan)) return e;
+  if (int e = tc_carve(reinterpret_cast<char*>(workspace), off, multires, multires_view, skip_layer, *vf, rn, plan, 0, 0,
+                       precision == VFNERF_PREC_BF16X3)) return e;
   VFN_REQUIRE(workspace && workspace_bytes >= off, "mlp_points_fwd: workspace too small");
   if (repack)
     if (int e = tc_prepare(*vf, vf_arena, rn, rn_arena, bn_eps, plan, s)) return e;
@@ -580,7 +588,7 @@ int vfnerf_vf_bwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (precision != VFNERF_PREC_FP32) {
     // tensor-core path: the forward (keep_for_backward) left the activation stash and the transposed weight images
-    VFN_REQUIRE(precision == VFNERF_PREC_BF16, "vf_bwd: only fp32 and bf16 are built");
+    VFN_REQUIRE(precision == VFNERF_PREC_BF16, "vf_bwd: precision bf16x3 is forward-only; train with bf16 or fp32");
     VFN_REQUIRE(n_out_cols == 3 || n_out_cols == vf->out_dim[vf->n_layers - 1], "vf_bwd(bf16): n_out_cols must be 3 or all");
     if (!accumulate) VFN_CHECK_CUDA(cudaMemsetAsync(vf_grad_arena, 0, sizeof(float) * vf->arena_floats, s));
     if (n_points == 0) return 0;
@@ -618,10 +626,10 @@ int vfnerf_vf_grid_query(const vfnerf_mlp_desc* vf, const float* vf_arena, int m
   for (int c = 0; c < 3; ++c) { gs.origin[c] = origin3_host[c]; gs.translation[c] = translation3_host[c]; gs.centroid[c] = centroid3_host[c]; }
   gs.voxel = voxel;
   if (precision != VFNERF_PREC_FP32) {
-    VFN_REQUIRE(precision == VFNERF_PREC_BF16, "grid_query: only fp32 and bf16 are built");
+    if (int e = tc_precision(precision, "grid_query")) return e;
     TcPlan plan;
     int64_t bytes = 0;
-    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes)) return e;
+    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes, 0, 0, precision == VFNERF_PREC_BF16X3)) return e;
     VFN_REQUIRE(workspace && workspace_bytes >= bytes, "grid_query: workspace too small");
     if (int e = tc_prepare(*vf, vf_arena, nullptr, nullptr, bn_eps, plan, s)) return e;
     return tc_forward(plan, TC_MODE_V_ONLY, nullptr, &gs, res, i0, n_points, nullptr, 0, out, 3, nullptr, 0, nullptr, s);

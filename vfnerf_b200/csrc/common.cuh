@@ -38,6 +38,7 @@ extern long long g_launches;
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxDevices = 64;     // per-device caches (SM count, shared-memory opt-in) are indexed by device ordinal
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

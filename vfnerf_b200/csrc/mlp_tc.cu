@@ -29,8 +29,22 @@ namespace vfn {
 using namespace tc;
 
 constexpr int kTileM = 128;
-constexpr int kStageBytes = 32768;
 constexpr int kTcStages = 3;
+// activation-tile layout and ring-slot size of the two tile formats (mlp_tc.cuh)
+template <bool kX3> struct Lay;
+template <> struct Lay<false> {
+  static constexpr int aux = kColAux, skip = kColSkip, ones = kColOnes, emb0 = kColEmb0, lo = 0, cols = kActCols;
+  static constexpr int stage_bytes = 32768;
+};
+template <> struct Lay<true> {
+  static constexpr int aux = kX3ColAux, skip = -1, ones = kX3ColOnes, emb0 = kX3ColEmb0, lo = kX3ColLo, cols = kX3ActCols;
+  static constexpr int stage_bytes = 16384;
+};
+template <bool kX3> constexpr size_t tc_smem_bytes() {
+  return (size_t)Lay<kX3>::cols * kTileM * 2 + (size_t)kTcStages * Lay<kX3>::stage_bytes + 512 +
+         (size_t)kTcMaxSteps * kTcMaxChunks * 16 + 128;
+}
+static_assert(tc_smem_bytes<true>() <= 227 * 1024 && tc_smem_bytes<false>() <= 227 * 1024, "activation tile + ring exceed shared memory");
 constexpr int kTcThreads = 480;      // warp 0 producer, warp 1 MMA/relay, warps 2..9 epilogue, warps 10..13 prologue,
                                      // warp 14: activation-stash store lane (training forward)
 constexpr int kAccCols = 256;
@@ -78,14 +92,27 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
   const int total = st.N * st.K;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int n = e / st.K, k = e - n * st.K;
-    // locate (segment, column in segment) and the byte offset of the chunk that holds column k
-    // each CTA of the pair streams one half image: output channels [half*N/2, (half+1)*N/2)
+    // locate (segment, chunk, hi or lo part, column in segment) and the byte offset inside the image.
+    // each CTA of the pair streams one half image: output channels [half*N/2, (half+1)*N/2).  Inside a half the
+    // segments follow each other; a segment is a sequence of K chunks; a split-precision segment stores, per chunk,
+    // the bf16 weights W_hi [N/2 x kc] and right after them the remainders W_lo [N/2 x kc]
     const int nh = st.N >> 1, half = n / nh, nn = n - half * nh;
-    int sg = 0, kin = k;
+    int sg = 0, q = k;
     int64_t base = st.w_off + (int64_t)half * nh * st.K * 2;
-    while (kin >= st.seg_k[sg]) { kin -= st.seg_k[sg]; base += (int64_t)nh * st.seg_k[sg] * 2; ++sg; }
-    const int64_t off = base + (int64_t)(kin / st.chunk_k) * nh * st.chunk_k * 2 +
-                        (int64_t)((kin % st.chunk_k) / 8) * nh * 16 + nn * 16 + (kin & 7) * 2;
+    for (;;) {
+      const int wimg = st.seg_k[sg] * (st.seg_lo[sg] ? 2 : 1);
+      if (q < wimg) break;
+      q -= wimg; base += (int64_t)nh * wimg * 2; ++sg;
+    }
+    const bool split = st.seg_lo[sg] != 0;
+    const int span = st.chunk_k * (split ? 2 : 1);
+    const int ci = q / span, r = q - ci * span;
+    const int kc = min(st.chunk_k, st.seg_k[sg] - ci * st.chunk_k);
+    const bool is_lo = r >= kc;
+    const int kk = r - (is_lo ? kc : 0);
+    const int kin = ci * st.chunk_k + kk;
+    const int64_t off = base + (int64_t)ci * span * nh * 2 + (is_lo ? (int64_t)kc * nh * 2 : 0) +
+                        (int64_t)(kk / 8) * nh * 16 + nn * 16 + (kk & 7) * 2;
     float w = 0.f;
     if (n < st.n_valid) {
       const int row = st.colmap >= 10 ? 0 : st.row0 + n;
@@ -131,6 +158,11 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
         else src = sg == 0 ? (kin < st.src_split ? kin : -1) : (kin < E ? st.src_split + kin : -1);
         if (src >= 0 && src < in_dim) w = arena[d.w_off[l] + (int64_t)row * in_dim + src] * sc * st.post_scale;
       }
+      w *= st.seg_wscale[sg];
+    }
+    if (split) {
+      const float hi = __bfloat162float(__float2bfloat16(w));
+      if (is_lo) w -= hi;
     }
     *reinterpret_cast<__nv_bfloat16*>(wpack + off) = __float2bfloat16(w);
   }
@@ -177,7 +209,10 @@ __device__ __forceinline__ void store_slab_u(uint8_t* s_act, int slab, int row, 
 // positional encoding of embedder.py:11-37 into e[0 .. 3+6*L).  sin/cos of the base frequency come from
 // sincosf; the octaves above it use the double-angle recurrence (error doubles per octave: <= 4e-6 at 2^5,
 // far below the bf16 quantisation this path feeds).  Fully unrolled so e[] stays in registers.
+// kExact (split-precision path): every octave is its own sincosf of the exactly scaled argument, like the reference's
+// torch.sin(x * 2^k) -- the recurrence's 4e-6 would be a visible share of that path's 1e-3 budget.
 constexpr int kMaxRes = 7;
+template <bool kExact = false>
 __device__ __forceinline__ void embed3(const float* p, int L, float* e) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -189,8 +224,12 @@ __device__ __forceinline__ void embed3(const float* p, int L, float* e) {
       if (k < L) {
         e[3 + 6 * k + c] = sv;
         e[6 + 6 * k + c] = cv;
-        const float s2 = 2.f * sv * cv, c2 = cv * cv - sv * sv;
-        sv = s2; cv = c2;
+        if (kExact) {
+          sincosf(p[c] * (float)(2 << k), &sv, &cv);
+        } else {
+          const float s2 = 2.f * sv * cv, c2 = cv * cv - sv * sv;
+          sv = s2; cv = c2;
+        }
       }
     }
   }
@@ -226,8 +265,15 @@ __device__ __forceinline__ uint2* gate_unit(const TcParams& p, int t, long long 
 }
 
 // readiness barriers (bit mask) that guard the 64-column chunk starting at activation-tile column `col`
+template <bool kX3>
 __device__ __forceinline__ uint32_t col_barriers(int col) {
   if (col < kColAux) return 1u << (col >> 6);
+  if (kX3) {
+    if (col < kX3ColOnes) return (1u << kBarAux) | (1u << kBarAuxStatic);
+    if (col < kX3ColEmb0) return 0u;
+    if (col < kX3ColLo) return 1u << kBarEmb0;
+    return 1u << ((col - kX3ColLo) >> 6);     // the lo copy of a group is published by the same arrival as its hi copy
+  }
   if (col < kColSkip) return (1u << kBarAux) | (1u << kBarAuxStatic);
   if (col < kColOnes) return 1u << kBarSkip;
   if (col < kColEmb0) return 0u;
@@ -334,14 +380,17 @@ constexpr bool kTcProfile = false;
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
-template <bool kBwd, bool kStash>
+template <bool kBwd, bool kStash, bool kX3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcParams p) {
+  static_assert(!kX3 || (!kBwd && !kStash), "the split-precision tile is built for the forward-only programs");
+  using L = Lay<kX3>;
+  constexpr int kStageBytes = L::stage_bytes;
   const int kdbg = kTcProfile ? p.dbg : 0;   // experiment switches (VFNERF_TC_DBG) exist in profile builds only
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcProgram& prog = p.prog;
   uint8_t* s_act = smem;
-  uint8_t* s_stage = smem + kActCols * (kTileM * 2);
+  uint8_t* s_stage = smem + L::cols * (kTileM * 2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kTcStages * kStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kTcStages;
@@ -363,9 +412,11 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   // chunk table: the single-lane producer / MMA-issuer loops must not chase per-chunk facts through the kernel
   // parameters (dependent constant loads cost them ~500 cycles per chunk): everything a chunk needs is one LDS.128.
   //   x = A start-address increment (16-byte units), y = K columns | readiness-barrier mask << 16,
-  //   z = bytes of this CTA's half of the weight chunk, w = 1 on the last chunk of the step
+  //   z = bytes of this CTA's half of the weight chunk | (its offset inside the step's half image / 16) << 16,
+  //   w = bit 0: last chunk of the step; bits 8..: split-precision "hi" chunk -- distance (16-byte units) from the hi
+  //       to the lo copy of the A columns: the chunk's MMAs are issued a second time on the lo copy
   uint4* s_chunks = reinterpret_cast<uint4*>(bars + 64);
-  int* s_nchunks = reinterpret_cast<int*>(s_chunks + kTcMaxSteps * 8);
+  int* s_nchunks = reinterpret_cast<int*>(s_chunks + kTcMaxSteps * kTcMaxChunks);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -385,29 +436,35 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   if (threadIdx.x >= 256 && threadIdx.x < 256 + prog.n_steps) {
     const int si = threadIdx.x - 256;
     const TcStep& st = prog.s[si];
-    uint32_t seen = 0;
+    uint32_t seen = 0, src16 = 0;
     int nc = 0;
     for (int sg = 0; sg < st.n_seg; ++sg) {
+      const int lo = st.seg_lo[sg];
       for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
         const int kc = min(st.chunk_k, st.seg_k[sg] - k0);
         const int col = st.seg_col0[sg] + k0;
         uint32_t need = 0;
-        for (int cc = col; cc < col + kc; cc += 64) need |= col_barriers(cc);
+        for (int cc = col; cc < col + kc; cc += 64) need |= col_barriers<kX3>(cc);
         need &= (uint32_t)st.fresh_mask & ~seen;
         seen |= need;
-        s_chunks[si * 8 + nc] = make_uint4((uint32_t)(col >> 3) * ((kTileM * 16u) >> 4), (uint32_t)kc | (need << 16),
-                                           (uint32_t)((st.N >> 1) * kc * 2), 0u);
-        ++nc;
+        const uint32_t a_off = (uint32_t)(col >> 3) * ((kTileM * 16u) >> 4), bytes = (uint32_t)((st.N >> 1) * kc * 2);
+        const uint32_t dual = (lo && st.use_lo) ? ((uint32_t)(lo >> 3) * ((kTileM * 16u) >> 4)) << 8 : 0u;
+        s_chunks[si * kTcMaxChunks + nc++] = make_uint4(a_off, (uint32_t)kc | (need << 16), bytes | (src16 << 16), dual);
+        src16 += bytes >> 4;
+        if (lo) {              // the image holds W_lo right after W_hi whether or not this program uses it
+          if (st.use_lo) s_chunks[si * kTcMaxChunks + nc++] = make_uint4(a_off, (uint32_t)kc, bytes | (src16 << 16), 0u);
+          src16 += bytes >> 4;
+        }
       }
     }
-    s_chunks[si * 8 + nc - 1].w = 1u;
+    s_chunks[si * kTcMaxChunks + nc - 1].w |= 1u;
     s_nchunks[si] = nc;
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kTileM) {
     // constant ones-columns [1, 1, 0, ...] that pick up the bias row of every weight image
     const int r = threadIdx.x - 64;
-    store_slab_u(s_act, kColOnes / 8, r, 0x3F803F80u, 0u, 0u, 0u);
-    store_slab_u(s_act, kColOnes / 8 + 1, r, 0u, 0u, 0u, 0u);
+    store_slab_u(s_act, L::ones / 8, r, 0x3F803F80u, 0u, 0u, 0u);
+    store_slab_u(s_act, L::ones / 8 + 1, r, 0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
   }
   tc_fence_before_sync();
@@ -434,20 +491,20 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         for (int si = 0; si < prog.n_steps; ++si) {
           const TcStep& st = prog.s[si];
           const uint8_t* src = p.wpack + st.w_off + (int64_t)rank * (st.N >> 1) * st.K * 2;
-          const uint4* ck = s_chunks + si * 8;
+          const uint4* ck = s_chunks + si * kTcMaxChunks;
           for (;; ++ck) {
             const uint4 c = *ck;
+            const uint32_t bytes = c.z & 0xFFFFu;
             mbar_wait(&empty[stage], phase ^ 1);
             if (kdbg & 4) {
               // experiment: no weight traffic at all (results are garbage) -- isolates the L2 -> shared-memory streaming
               mbar_arrive(&full[stage]);
             } else {
-              mbar_arrive_expect_tx(&full[stage], c.z);
-              bulk_g2s(s_stage + stage * kStageBytes, src, c.z, &full[stage]);
+              mbar_arrive_expect_tx(&full[stage], bytes);
+              bulk_g2s(s_stage + stage * kStageBytes, src + (size_t)(c.z >> 16) * 16, bytes, &full[stage]);
             }
-            src += c.z;
             if (++stage == kTcStages) { stage = 0; phase ^= 1; }
-            if (c.w) break;
+            if (c.w & 1u) break;
           }
         }
       }
@@ -503,7 +560,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               grp_par ^= (1u << g);
             }
           }
-          const uint4* ckp = s_chunks + si * 8;
+          const uint4* ckp = s_chunks + si * kTcMaxChunks;
           uint4 ck = *ckp;
           ck.x = __shfl_sync(0xffffffffu, ck.x, 0); ck.y = __shfl_sync(0xffffffffu, ck.y, 0); ck.w = __shfl_sync(0xffffffffu, ck.w, 0);
           for (;;) {
@@ -531,7 +588,37 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             constexpr uint32_t a_kstep = 2u * ((kTileM * 16u) >> 4);
             const int kc = (int)(ck.y & 0xFFFFu);
             if (tl && first_mma) { p.dbg_buf[64 + si * 8 + 0] = clock64(); first_mma = false; }
-            {
+            if constexpr (kX3) {
+              // 16 KiB ring slots: at most 64 K columns per chunk.  A split-precision "hi" chunk multiplies W_hi with
+              // the hi AND the lo copy of the A columns (the weights are fetched once for both products); the "lo"
+              // chunk that follows multiplies W_lo with the hi copy.
+              const uint32_t lo_off = ck.w >> 8;
+              if (kc == 64) {
+                umma2_bf16_split_w(acc, a_lo, desc_hi, b_lo, desc_hi, idesc, accumulate);
+#pragma unroll
+                for (uint32_t j = 1; j < 4; ++j)
+                  umma2_bf16_split_w(acc, a_lo + j * a_kstep, desc_hi, b_lo + j * b_kstep, desc_hi, idesc, 1u);
+                if (lo_off) {
+#pragma unroll
+                  for (uint32_t j = 0; j < 4; ++j)
+                    umma2_bf16_split_w(acc, a_lo + lo_off + j * a_kstep, desc_hi, b_lo + j * b_kstep, desc_hi, idesc, 1u);
+                }
+              } else {
+                uint32_t al = a_lo, bl = b_lo, ac = accumulate;
+                for (int kk = 0; kk < kc; kk += 16) {
+                  umma2_bf16_split_w(acc, al, desc_hi, bl, desc_hi, idesc, ac);
+                  ac = 1u; al += a_kstep; bl += b_kstep;
+                }
+                if (lo_off) {
+                  al = a_lo + lo_off; bl = b_lo;
+                  for (int kk = 0; kk < kc; kk += 16) {
+                    umma2_bf16_split_w(acc, al, desc_hi, bl, desc_hi, idesc, 1u);
+                    al += a_kstep; bl += b_kstep;
+                  }
+                }
+              }
+              umma2_commit_u32_w(empty_u32 + 8u * stage);
+            } else {
               if (kc == 128) {
                 // steady state: eight MMAs with constant descriptor increments (the issue thread must stay well
                 // under 128 cycles of scalar work per MMA, profiles/run_umma_bench.py)
@@ -550,14 +637,14 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             }
             accumulate = 1;
             if (++stage == kTcStages) { stage = 0; phase ^= 1; }
-            if (ck.w) break;
+            if (ck.w & 1u) break;
             ck = nxt; ++ckp;
           }
           {
             umma2_commit_u32_w(smem_u32(&acc_full[gstep & 1]));      // accumulators complete -> epilogue warps of both CTAs
             // side regions whose only reader was this step may now be rewritten for the next tile (prologue warps)
             // [0]: layer-0 operand region (forward) / the whole main region once the VF-only dgrad tile is finished
-            if (si == (prog.bwd == 2 ? prog.n_steps - 1 : 0)) umma2_commit_u32_w(smem_u32(&reg_free[0]));
+            if (si == prog.emb0_last_step) umma2_commit_u32_w(smem_u32(&reg_free[0]));
             if (si == prog.skip_step) umma2_commit_u32_w(smem_u32(&reg_free[1]));
             if (si == prog.aux_step) umma2_commit_u32_w(smem_u32(&reg_free[2]));
           }
@@ -647,8 +734,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         }
         if (with_rn) {
           if (n > 0) mbar_wait(&reg_free[2], (n - 1) & 1);
-          store_slab_f(s_act, kColAux / 8, row, u);
-          store_slab_f(s_act, kColAux / 8 + 1, row, u + 8);
+          store_slab_f(s_act, L::aux / 8, row, u);
+          store_slab_f(s_act, L::aux / 8 + 1, row, u + 8);
           fence_proxy_async_smem();
           arrive_pro(kBarAuxStatic);
         } else {
@@ -664,8 +751,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           arrive_pro(0); arrive_pro(1); arrive_pro(2); arrive_pro(3);
         }
         if (n > 0) mbar_wait(&reg_free[1], (n - 1) & 1);
-        store_slab_f(s_act, kColSkip / 8, row, w);
-        store_slab_f(s_act, kColSkip / 8 + 1, row, w + 8);
+        store_slab_f(s_act, L::skip / 8, row, w);
+        store_slab_f(s_act, L::skip / 8 + 1, row, w + 8);
         fence_proxy_async_smem();
         arrive_pro(kBarSkip);
       }
@@ -679,7 +766,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       load_point(p, pi, valid, pt);
 #pragma unroll
       for (int i = 0; i < 48; ++i) emb[i] = 0.f;
-      embed3(pt, prog.multires, emb);
+      embed3<kX3>(pt, prog.multires, emb);
 #pragma unroll
       for (int i = 0; i < 48; ++i)
         if (i >= E) emb[i] = 0.f;
@@ -695,8 +782,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             hi[j] = __bfloat162float(__float2bfloat16(v));
             lo[j] = v - hi[j];
           }
-          store_slab_f(s_act, kColEmb0 / 8 + sl, row, hi);
-          store_slab_f(s_act, kColEmb0 / 8 + nsl + sl, row, lo);
+          store_slab_f(s_act, L::emb0 / 8 + sl, row, hi);
+          store_slab_f(s_act, L::emb0 / 8 + nsl + sl, row, lo);
           if (st_on) {
             *stash_unit(p, p.sinfo.idx_emb0, tile, sl, row) =
                 make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
@@ -707,14 +794,14 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       }
       fence_proxy_async_smem();
       arrive_pro(kBarEmb0);
-      // ---- skip region: embedding / sqrt(2)
-      if (prog.skip_step >= 0) {
+      // ---- skip region: embedding / sqrt(2)   (split-precision tile: the skip layer reads the emb0 columns instead)
+      if (!kX3 && prog.skip_step >= 0) {
         if (n > 0) mbar_wait(&reg_free[1], (n - 1) & 1);
 #pragma unroll
         for (int i = 0; i < 48; ++i) emb[i] *= kInvSqrt2;
 #pragma unroll
         for (int sl = 0; sl < 6; ++sl) {
-          store_slab_f(s_act, kColSkip / 8 + sl, row, emb + 8 * sl);
+          store_slab_f(s_act, L::skip / 8 + sl, row, emb + 8 * sl);
           if (st_on) {
             const float* e8 = emb + 8 * sl;
             *stash_unit(p, p.sinfo.idx_skip, tile, sl, row) =
@@ -733,7 +820,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const long long r = pi / p.samples_per_ray;
           d[0] = __ldg(p.ray_dirs + 3 * r); d[1] = __ldg(p.ray_dirs + 3 * r + 1); d[2] = __ldg(p.ray_dirs + 3 * r + 2);
         }
-        embed3(d, prog.multires_view, a + 3);
+        embed3<kX3>(d, prog.multires_view, a + 3);
         const int ev = 3 + 6 * prog.multires_view;
 #pragma unroll
         for (int j = 0; j < 40; ++j) {
@@ -743,7 +830,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         if (n > 0) mbar_wait(&reg_free[2], (n - 1) & 1);
 #pragma unroll
         for (int sl = 0; sl < 5; ++sl) {
-          store_slab_f(s_act, kColAux / 8 + 1 + sl, row, a + 8 * sl);
+          store_slab_f(s_act, L::aux / 8 + 1 + sl, row, a + 8 * sl);
           if (st_on) {
             const float* e8 = a + 8 * sl;
             *stash_unit(p, p.sinfo.idx_aux, tile, 1 + sl, row) =
@@ -892,7 +979,35 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               if (second) tmem_ld32(acc + c0 + 32, vb);
               tmem_ld_wait();
               TCK(t_ld);
-              if (!(kdbg & 2)) {
+              if constexpr (kX3) {
+                // split-precision hand-off: y = relu(acc) leaves as hi = bf16(y) in the main columns and, for the VF
+                // layers, lo = bf16(y - hi) in the lo columns (same slab, kX3ColLo further on)
+                const bool out_lo = st.out_lo != 0;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  if (hf == 1 && !second) break;
+                  const uint32_t* v = hf == 0 ? va : vb;
+#pragma unroll
+                  for (int sl = 0; sl < 4; ++sl) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float a0 = __uint_as_float(v[8 * sl + 2 * j]), a1 = __uint_as_float(v[8 * sl + 2 * j + 1]);
+                      if (feat) {
+                        hi[j] = tanh_bf16x2(pack_bf16x2(a0, a1));
+                        lo[j] = 0u;
+                      } else {
+                        const float y0 = fmaxf(a0, 0.f), y1 = fmaxf(a1, 0.f);
+                        hi[j] = pack_bf16x2(y0, y1);
+                        lo[j] = pack_bf16x2(y0 - __uint_as_float(hi[j] << 16), y1 - __uint_as_float(hi[j] & 0xFFFF0000u));
+                      }
+                    }
+                    const int slab = (c0 >> 3) + 4 * hf + sl;
+                    store_slab_u(s_act, slab, row, hi[0], hi[1], hi[2], hi[3]);
+                    if (out_lo) store_slab_u(s_act, slab + L::lo / 8, row, lo[0], lo[1], lo[2], lo[3]);
+                  }
+                }
+              } else if (!(kdbg & 2)) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -951,7 +1066,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               tmem_ld_wait();
               float f[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = tanh_fast(__uint_as_float(v[j]));
+              for (int j = 0; j < 32; ++j) f[j] = kX3 ? tanhf(__uint_as_float(v[j])) : tanh_fast(__uint_as_float(v[j]));
               if (st_on) {       // module call kept for a backward: the features are the tanh gate of the dgrad chain
 #pragma unroll
                 for (int sl = 0; sl < 4; ++sl)
@@ -987,7 +1102,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             if (render) {
               // the normal is the first 16-byte unit of the colour net's small inputs (aux columns 0..7)
               float a[8] = {nv[0], nv[1], nv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-              store_slab_f(s_act, kColAux / 8, row, a);
+              store_slab_f(s_act, L::aux / 8, row, a);
               if (kStash && tile < num_tiles)
                 *stash_unit(p, p.sinfo.idx_aux, tile, 0, row) = make_uint4(pack_bf16x2(nv[0], nv[1]), pack_bf16x2(nv[2], 0.f), 0u, 0u);
               fence_proxy_async_smem();
@@ -1032,7 +1147,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 static int round16(int x) { return (x + 15) / 16 * 16; }
 
 static int build_programs(int multires, int multires_view, int skip_layer, const vfnerf_mlp_desc& vf,
-                          const vfnerf_mlp_desc* rn, TcPlan& plan) {
+                          const vfnerf_mlp_desc* rn, TcPlan& plan, int x3) {
   const int E = 3 + 6 * multires, Epad = round16(E);
   const int L = vf.n_layers;
   VFN_REQUIRE(Epad <= 48 && multires <= kMaxRes && multires_view <= kMaxRes, "tensor-core path: embedding too wide");
@@ -1046,19 +1161,37 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
                 l, vf.in_dim[l], vf.out_dim[l]);
   }
   TcProgram pr{};
+  auto layout = [&](TcProgram& q, int is_x3) {
+    q.x3 = is_x3;
+    q.col_aux = is_x3 ? kX3ColAux : kColAux; q.col_skip = is_x3 ? -1 : kColSkip; q.col_ones = is_x3 ? kX3ColOnes : kColOnes;
+    q.col_emb0 = is_x3 ? kX3ColEmb0 : kColEmb0; q.col_lo = is_x3 ? kX3ColLo : 0;
+  };
+  layout(pr, x3);
   pr.emb_w = E; pr.emb_pad = Epad; pr.multires = multires; pr.multires_view = multires_view;
   pr.small_w = 3 + (3 + 6 * multires_view) + 3;
   pr.skip_step = skip_layer;
   pr.aux_step = -1;
+  pr.emb0_last_step = (x3 && skip_layer > 0) ? skip_layer : 0;
   int ns = 0;
   long long woff = 0;
-  // appends a step; the bias (ones) segment is added automatically as the last segment
+  // the 16 KiB ring slots of the split-precision tile hold 64 K columns of a 256-channel layer
+  const int CK = x3 ? 64 : 128;
+  // appends a step; the bias (ones) segment is added automatically as the last segment.  seglo (may be null): per segment,
+  // column distance to the lo copy of the A operand (split-precision segment); segw (may be null): extra weight factor
   auto add = [&](int N, int n_valid, int nseg, const int* col0, const int* segk, int chunk_k, int epi, int fresh,
-                 int net, int layer, int row0, int colmap, int src_split, float post, int no_bias = 0) {
+                 int net, int layer, int row0, int colmap, int src_split, float post, int no_bias = 0,
+                 const int* seglo = nullptr, const float* segw = nullptr) {
     TcStep& s = pr.s[ns];
+    s = TcStep{};
     s.N = N; s.n_valid = n_valid; s.n_seg = nseg + (no_bias ? 0 : 1); s.K = 0;
-    for (int i = 0; i < nseg; ++i) { s.seg_col0[i] = col0[i]; s.seg_k[i] = segk[i]; s.K += segk[i]; }
-    if (!no_bias) { s.seg_col0[nseg] = kColOnes; s.seg_k[nseg] = 16; s.K += 16; }
+    for (int i = 0; i < kTcMaxSegs; ++i) { s.seg_lo[i] = 0; s.seg_wscale[i] = 1.f; }
+    for (int i = 0; i < nseg; ++i) {
+      s.seg_col0[i] = col0[i]; s.seg_k[i] = segk[i];
+      s.seg_lo[i] = seglo ? seglo[i] : 0; s.seg_wscale[i] = segw ? segw[i] : 1.f;
+      s.K += segk[i] * (s.seg_lo[i] ? 2 : 1);
+    }
+    if (!no_bias) { s.seg_col0[nseg] = pr.col_ones; s.seg_k[nseg] = 16; s.K += 16; }
+    s.use_lo = seglo ? 1 : 0; s.out_lo = 0;
     s.no_bias = no_bias; s.stash_out = -1; s.mask_src = -1;
     s.chunk_k = chunk_k; s.epi = epi; s.fresh_mask = fresh; s.pre_wait_mask = 0; s.w_off = woff;
     s.net = net; s.layer = layer; s.row0 = row0; s.colmap = colmap; s.src_split = src_split; s.post_scale = post;
@@ -1066,26 +1199,46 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
     ++ns;
   };
   const int main0[1] = {0};
+  const int lo_main[1] = {kX3ColLo};
   for (int l = 0; l < L - 1; ++l) {
     const float post = (l + 1 == skip_layer) ? kInvSqrt2 : 1.f;
     const int N = round16(vf.out_dim[l]);
-    if (l == 0) {
+    if (x3) {
+      // every VF hidden layer: three products per K chunk (mlp_tc.cuh), output written as (hi, lo)
+      if (l == 0) {
+        const int c0[1] = {kX3ColEmb0}, k[1] = {Epad}, lo[1] = {Epad};
+        add(N, vf.out_dim[l], 1, c0, k, CK, TC_EPI_RELU, 1 << kBarEmb0, 0, l, 0, 0, 0, post, 0, lo);
+      } else if (l == skip_layer) {
+        // [previous layer (already / sqrt(2)) | embedding]: the embedding comes from the layer-0 operand columns
+        // (their barrier was consumed by step 0: not "fresh"), its weights carry the 1 / sqrt(2)
+        const int prev = vf.out_dim[l - 1];
+        const int c[2] = {0, kX3ColEmb0}, k[2] = {round16(prev), Epad}, lo[2] = {kX3ColLo, Epad};
+        const float w[2] = {1.f, kInvSqrt2};
+        add(N, vf.out_dim[l], 2, c, k, CK, TC_EPI_RELU, 0xF, 0, l, 0, 3, prev, post, 0, lo, w);
+      } else {
+        const int k[1] = {256};
+        add(N, vf.out_dim[l], 1, main0, k, CK, TC_EPI_RELU, 0xF, 0, l, 0, 0, 0, post, 0, lo_main);
+      }
+      pr.s[ns - 1].out_lo = 1;
+    } else if (l == 0) {
       const int k[1] = {2 * Epad};
       const int c0[1] = {kColEmb0};
-      add(N, vf.out_dim[l], 1, c0, k, 128, TC_EPI_RELU, 1 << kBarEmb0, 0, l, 0, 1, 0, post);
+      add(N, vf.out_dim[l], 1, c0, k, CK, TC_EPI_RELU, 1 << kBarEmb0, 0, l, 0, 1, 0, post);
     } else if (l == skip_layer) {
       const int prev = vf.out_dim[l - 1];
       const int c[2] = {0, kColSkip}, k[2] = {round16(prev), 48};
-      add(N, vf.out_dim[l], 2, c, k, 128, TC_EPI_RELU, 0xF | (1 << kBarSkip), 0, l, 0, 3, prev, post);
+      add(N, vf.out_dim[l], 2, c, k, CK, TC_EPI_RELU, 0xF | (1 << kBarSkip), 0, l, 0, 3, prev, post);
     } else {
       const int k[1] = {256};
-      add(N, vf.out_dim[l], 1, main0, k, 128, TC_EPI_RELU, 0xF, 0, l, 0, 0, 0, post);
+      add(N, vf.out_dim[l], 1, main0, k, CK, TC_EPI_RELU, 0xF, 0, l, 0, 0, 0, post);
     }
   }
   const int k256[1] = {256};
-  add(16, 3, 1, main0, k256, 128, TC_EPI_V, 0xF, 0, L - 1, 0, 0, 0, 1.f);
+  add(16, 3, 1, main0, k256, CK, TC_EPI_V, 0xF, 0, L - 1, 0, 0, 0, 1.f, 0, x3 ? lo_main : nullptr);
   const int n_v = ns;
-  add(256, 256, 1, main0, k256, 128, TC_EPI_FEAT, 0, 0, L - 1, 3, 0, 0, 1.f);
+  // feature rows of the VF output layer: the image is split-precision as well; render() uses only its hi products (the
+  // features are rounded to bf16 for the colour net anyway), the module call (VF_FULL) all three
+  add(256, 256, 1, main0, k256, CK, TC_EPI_FEAT, 0, 0, L - 1, 3, 0, 0, 1.f, 0, x3 ? lo_main : nullptr);
   const int n_full = ns;
   if (rn) {
     const int Lr = rn->n_layers;
@@ -1097,15 +1250,16 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
                   "tensor-core path supports the shipped 256-wide colour net (layer %d is %d->%d); use precision fp32",
                   l, rn->in_dim[l], rn->out_dim[l]);
     }
-    const int c[2] = {0, kColAux}, k[2] = {256, 48};
+    const int c[2] = {0, pr.col_aux}, k[2] = {256, 48};
     pr.aux_step = ns;
-    add(256, 256, 2, c, k, 128, TC_EPI_RELU, 0xF | (1 << kBarAux) | (1 << kBarAuxStatic), 1, 0, 0, 2, pr.small_w, 1.f);
-    for (int l = 1; l < Lr - 1; ++l) add(256, 256, 1, main0, k256, 128, TC_EPI_RELU, 0xF, 1, l, 0, 0, 0, 1.f);
-    add(16, 3, 1, main0, k256, 128, TC_EPI_RGB, 0xF, 1, Lr - 1, 0, 0, 0, 1.f);
+    add(256, 256, 2, c, k, CK, TC_EPI_RELU, 0xF | (1 << kBarAux) | (1 << kBarAuxStatic), 1, 0, 0, 2, pr.small_w, 1.f);
+    for (int l = 1; l < Lr - 1; ++l) add(256, 256, 1, main0, k256, CK, TC_EPI_RELU, 0xF, 1, l, 0, 0, 0, 1.f);
+    add(16, 3, 1, main0, k256, CK, TC_EPI_RGB, 0xF, 1, Lr - 1, 0, 0, 0, 1.f);
   }
   plan.wpack_bytes = woff;
   pr.n_steps = ns; pr.render = 1;
   plan.render = pr;
+  if (x3 && rn) plan.render.s[n_v].use_lo = 0;
   plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.render = 0; plan.vf_full.aux_step = -1;
   plan.vf_full.s[n_full - 1].pre_wait_mask = 1 << kBarAux;
   plan.v_only = pr; plan.v_only.n_steps = n_v; plan.v_only.render = 0; plan.v_only.aux_step = -1;
@@ -1133,6 +1287,7 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   // ---------------- training: the dgrad program of the VF net alone (module call with gradients) ----------------
   {
     pr = TcProgram{};
+    layout(pr, 0);
     pr.emb_w = E; pr.emb_pad = Epad; pr.multires = multires; pr.multires_view = multires_view;
     pr.small_w = fwd.small_w; pr.bwd = 2; pr.aux_step = -1;
     ns = 0; woff = 0;
@@ -1148,6 +1303,7 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
       pr.s[ns - 1].mask_src = yS(l - 1); pr.s[ns - 1].stash_out = D0 + yS(l - 1);
     }
     pr.n_steps = ns;
+    pr.emb0_last_step = ns - 1;      // VF-only dgrad: reg_free[0] guards the whole main region, free after the last step
     plan.bwd_vf = pr;
     plan.wpack_bwd_vf_bytes = woff;
   }
@@ -1155,6 +1311,7 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
 
   // ---------------- training: the dgrad program (weights transposed, no bias, gate with the stash) ----------------
   pr = TcProgram{};
+  layout(pr, 0);
   pr.emb_w = E; pr.emb_pad = Epad; pr.multires = multires; pr.multires_view = multires_view;
   pr.small_w = fwd.small_w; pr.bwd = 1;
   ns = 0; woff = 0;
@@ -1192,8 +1349,9 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
 }
 
 int tc_carve(char* base, int64_t& off, int multires, int multires_view, int skip_layer,
-             const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc* rn, TcPlan& plan, int64_t n_points, int keep) {
-  if (int e = build_programs(multires, multires_view, skip_layer, vf, rn, plan)) return e;
+             const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc* rn, TcPlan& plan, int64_t n_points, int keep, int x3) {
+  VFN_REQUIRE(!(x3 && keep), "precision bf16x3 is forward-only: train with precision bf16 or fp32");
+  if (int e = build_programs(multires, multires_view, skip_layer, vf, rn, plan, x3)) return e;
   off = align_up(off, 1024);
   plan.wpack = base ? reinterpret_cast<uint8_t*>(base + off) : nullptr;
   off += align_up(plan.wpack_bytes, 1024);
@@ -1232,7 +1390,6 @@ int tc_prepare(const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_ml
   return 0;
 }
 
-static int g_num_sms = 0;
 
 int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec* grid, int grid_res,
                int64_t grid_i0, int64_t n, const float* ray_dirs, int samples_per_ray, float* out_v,
@@ -1263,42 +1420,45 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   p.grid_res = grid_res; p.grid_i0 = grid_i0; p.n_points = n;
   p.ray_dirs = ray_dirs; p.samples_per_ray = samples_per_ray > 0 ? samples_per_ray : 1;
   p.out_v = out_v; p.v_ld = v_ld; p.out_feat = out_feat; p.feat_ld = feat_ld; p.colors = colors;
+#ifdef VFNERF_TC_PROFILE
+  // experiment switches and in-kernel cycle counters: profile builds only (the product library reads no environment)
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("VFNERF_TC_DBG"); dbg = e ? atoi(e) : 0; }
   static long long* dbg_buf = nullptr;
-  if ((dbg & 64) && !kTcProfile) {
-    static bool told = false;
-    if (!told) fprintf(stderr, "[tc dbg] VFNERF_TC_DBG=64 needs a build with -DVFNERF_TC_PROFILE (NVCC_EXTRA=-DVFNERF_TC_PROFILE)\n");
-    told = true;
-    dbg &= ~64;
-  }
   if ((dbg & 64) && !dbg_buf) VFN_CHECK_CUDA(cudaMalloc(&dbg_buf, 256 * sizeof(long long)));
   p.dbg_buf = (dbg & 64) ? dbg_buf : nullptr;
   p.dbg = dbg & 63;
   if (p.dbg_buf) VFN_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), s));
+#endif
   VFN_REQUIRE(out_v || is_bwd, "tc_forward: out_v is null");
   VFN_REQUIRE((mode != TC_MODE_RENDER && mode != TC_MODE_RENDER_STASH) || (colors && ray_dirs),
               "tc_forward: RENDER mode needs colors and ray_dirs");
-  if (g_num_sms == 0) {
-    int dev = 0;
-    VFN_CHECK_CUDA(cudaGetDevice(&dev));
-    VFN_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  // per-device facts (a process may drive several GPUs): SM count and the opt-in to > 48 KiB of dynamic shared memory
+  int dev = 0;
+  VFN_CHECK_CUDA(cudaGetDevice(&dev));
+  VFN_REQUIRE(dev >= 0 && dev < kMaxDevices, "tc_forward: device ordinal %d unsupported", dev);
+  static int num_sms[kMaxDevices] = {0};
+  if (num_sms[dev] == 0) {
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VFN_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
   }
   const int64_t tiles = (n + kTileM - 1) / kTileM;
   const int64_t pairs = (tiles + 1) / 2;
-  const int grid_x = 2 * (int)std::min<int64_t>(pairs, (int64_t)(g_num_sms / 2));
-  const size_t smem = (size_t)kActCols * kTileM * 2 + (size_t)kTcStages * kStageBytes + 512 + kTcMaxSteps * 8 * 16 + 128;
-  static bool attr = false;
-  if (!attr) {
-    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+  const int grid_x = 2 * (int)std::min<int64_t>(pairs, (int64_t)(num_sms[dev] / 2));
+  if (p.prog.x3) {
+    VFN_REQUIRE(!is_bwd && !stashing, "tc_forward: precision bf16x3 is forward-only");
+    mlp_tc_kernel<false, false, true><<<grid_x, kTcThreads, tc_smem_bytes<true>(), s>>>(p);
+  } else {
+    const size_t smem = tc_smem_bytes<false>();
+    if (is_bwd) mlp_tc_kernel<true, true, false><<<grid_x, kTcThreads, smem, s>>>(p);
+    else if (stashing) mlp_tc_kernel<false, true, false><<<grid_x, kTcThreads, smem, s>>>(p);
+    else mlp_tc_kernel<false, false, false><<<grid_x, kTcThreads, smem, s>>>(p);
   }
-  if (is_bwd) mlp_tc_kernel<true, true><<<grid_x, kTcThreads, smem, s>>>(p);
-  else if (stashing) mlp_tc_kernel<false, true><<<grid_x, kTcThreads, smem, s>>>(p);
-  else mlp_tc_kernel<false, false><<<grid_x, kTcThreads, smem, s>>>(p);
   VFN_LAUNCH_CHECK();
+#ifdef VFNERF_TC_PROFILE
   if (p.dbg_buf) {
     long long h[256];
     VFN_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -1318,6 +1478,7 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
               e[3] ? e[3] - base : 0, e[4] ? e[4] - base : 0, e[5] - base, e[6] ? e[6] - base : 0, e[7] ? e[7] - base : 0);
     }
   }
+#endif
   return 0;
 }
 

@@ -6,6 +6,7 @@ namespace vfn {
 
 constexpr int kTcMaxSteps = 16;
 constexpr int kTcMaxSegs = 3;
+constexpr int kTcMaxChunks = 16;   // pipeline chunks per step (split-precision steps: hi + lo chunk per K range + bias)
 
 // Activation-tile column map (bf16 columns of the 128-row A operand, K-slab layout, tc_common.cuh):
 //   [0,256)    main: current layer input / output (step 0 reads the hi/lo embedding from [0, 2*emb_pad))
@@ -17,6 +18,13 @@ constexpr int kTcMaxSegs = 3;
 //                    prologue warps, so it never collides with the main columns)
 // aux column order: [n(3), 0 x5 | p(3), embed(view dir), 0...]: the V step only rewrites the first 16-byte unit.
 constexpr int kColAux = 256, kColSkip = 304, kColOnes = 352, kColEmb0 = 368, kActCols = 464;
+// Split-precision (VFNERF_PREC_BF16X3) tile: every VF activation exists twice, as its bf16 rounding ("hi", main columns)
+// and as the bf16 rounding of the remainder ("lo", columns kX3ColLo + c); a VF product is three MMAs
+//   acc += A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T          (the A_lo W_lo term is below fp32 accumulation noise)
+// so the chain carries ~16 significant bits instead of 8.  No skip region: the skip layer reads the (hi | lo) layer-0
+// embedding with its weights scaled by 1/sqrt(2).  The colour net stays plain bf16 (its error is 2e-4).
+//   [0,256) main hi | [256,304) aux | [304,320) ones | [320,416) emb0 hi|lo | [416,672) main lo
+constexpr int kX3ColAux = 256, kX3ColOnes = 304, kX3ColEmb0 = 320, kX3ColLo = 416, kX3ActCols = 672;
 
 // One GEMM step of the fused chain: acc[128 x N] = sum over segments A[:, col0 : col0+k] * Wimg^T, then an epilogue.
 struct TcStep {
@@ -25,6 +33,13 @@ struct TcStep {
   int n_seg;
   int seg_col0[kTcMaxSegs];   // first activation-tile column of the segment
   int seg_k[kTcMaxSegs];      // columns (multiple of 16)
+  int seg_lo[kTcMaxSegs];     // split-precision image: activation-tile column distance from the hi to the lo copy of
+                              // this segment's A operand (0: plain segment).  The weight image then holds, per K chunk,
+                              // the bf16 weights W_hi followed by the remainders W_lo
+  float seg_wscale[kTcMaxSegs];   // extra factor on this segment's weights (skip-layer embedding columns: 1/sqrt(2))
+  int use_lo;     // this program issues the lo products of the split segments (0: only A_hi W_hi^T, e.g. the feature step
+                  // inside render(), whose output is rounded to bf16 for the colour net anyway)
+  int out_lo;     // epilogue also writes the lo copy of its output (the next step is a split-precision step)
   int K;          // sum of seg_k == columns of the weight image
   int chunk_k;    // K columns per pipeline chunk (multiple of 16, N*chunk_k*2 <= 32 KiB); chunks never straddle segments
   int epi;        // TcEpi
@@ -79,6 +94,9 @@ struct TcProgram {
   int skip_step;    // index of the step that consumes the skip columns (-1: none)
   int aux_step;     // index of the step that consumes the aux columns (-1: none)
   int bwd;          // 1: backward (dgrad) program of render() -- different prologue, no bias segments; 2: of the VF net alone
+  int x3;           // split-precision tile layout (kX3Col*), 16 KiB ring slots
+  int emb0_last_step;   // the emb0 columns may be rewritten for the next tile once this step's MMAs have completed
+  int col_aux, col_skip, col_ones, col_emb0, col_lo;   // activation-tile layout of this program
   TcStep s[kTcMaxSteps];
 };
 
@@ -99,7 +117,8 @@ struct TcPlan {
 
 // carve the tensor-core buffers out of the workspace (base may be NULL when only sizing)
 int tc_carve(char* base, int64_t& off, int multires, int multires_view, int skip_layer,
-             const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc* rn, TcPlan& plan, int64_t n_points = 0, int keep = 0);
+             const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc* rn, TcPlan& plan, int64_t n_points = 0, int keep = 0,
+             int x3 = 0);
 // fold BatchNorm + convert/tile the weights of both nets into their shared-memory images
 int tc_prepare(const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_mlp_desc* rn,
                const float* rn_arena, float bn_eps, const TcPlan& plan, cudaStream_t s);

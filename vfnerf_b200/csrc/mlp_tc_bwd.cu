@@ -308,7 +308,6 @@ __global__ void __launch_bounds__(128) tc_finalize_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // orchestration
 // ---------------------------------------------------------------------------------------------
-static int g_sms = 0;
 
 // steps 2-5 of the backward.  rn == nullptr: the VF net alone (dcol_pre unused; d(feature pre-tanh) is already in the
 // gradient stash).  dcol_pre / dv_pre: [n,3] gradients wrt the pre-activations of the two 3-wide outputs.
@@ -372,11 +371,14 @@ static int backward_common(const TcPlan& plan, const vfnerf_mlp_desc& vf, const 
   }
   unit_task(S.idx_dvu, yS(L - 2), slotThinV);
   wp.n_tasks = nt;
-  if (g_sms == 0) {
-    int dev = 0;
-    VFN_CHECK_CUDA(cudaGetDevice(&dev));
-    VFN_CHECK_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  // per-device facts: a process may drive several GPUs
+  int dev = 0;
+  VFN_CHECK_CUDA(cudaGetDevice(&dev));
+  VFN_REQUIRE(dev >= 0 && dev < kMaxDevices, "tc_backward: device ordinal %d unsupported", dev);
+  static int sms_of[kMaxDevices] = {0};
+  const bool first_on_device = sms_of[dev] == 0;
+  if (first_on_device) VFN_CHECK_CUDA(cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int g_sms = sms_of[dev];
   {
     // CTAs per task proportional to the bytes it streams: floor of the proportional share first, then the CTAs that
     // rounding left over go, one at a time, to the task whose CTAs carry the most bytes (the kernel ends with its
@@ -403,11 +405,8 @@ static int backward_common(const TcPlan& plan, const vfnerf_mlp_desc& vf, const 
     used = 0;
     for (int i = 0; i < nt; ++i) { wp.t[i].cta0 = used; wp.t[i].nctas = cnt[i]; used += cnt[i]; }
     const size_t smem = (size_t)kWgDSlots * kWgDGran + (size_t)kWgXSlots * kWgXBytes + 256;
-    static bool attr = false;
-    if (!attr) {
+    if (first_on_device)
       VFN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
-    }
     wgrad_tc_kernel<<<used, kWgThreads, smem, s>>>(wp);
     VFN_LAUNCH_CHECK();
   }

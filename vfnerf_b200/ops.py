@@ -95,7 +95,8 @@ def vf_query(net, points: torch.Tensor, n_cols: Optional[int] = None) -> torch.T
 def mlp_points(vf_net, rn_net, points: torch.Tensor, ray_dirs: torch.Tensor, samples_per_ray: int,
                workspace: Optional[torch.Tensor] = None, repack: bool = True):
     """VF vectors and colours at ``points[P,3]`` seen along ``ray_dirs[P/samples_per_ray,3]`` -- the two-MLP evaluation
-    of VectorFieldNerf.get_colors (vector_field_nerf.py:341-375) as ONE fused tcgen05 launch (bf16, forward only).
+    of VectorFieldNerf.get_colors (vector_field_nerf.py:341-375) as ONE fused tcgen05 launch (forward only; bf16, or
+    bf16x3 when ``vf_net.precision == "bf16x3"``).
     Returns (normals[P,3], colors[P,3], workspace)."""
     L = _lib.lib()
     points, ray_dirs = _require_cuda("points", points.detach()), _require_cuda("ray_dirs", ray_dirs.detach())
@@ -111,7 +112,8 @@ def mlp_points(vf_net, rn_net, points: torch.Tensor, ray_dirs: torch.Tensor, sam
     normals = torch.empty(P, 3, dtype=torch.float32, device=dev)
     colors = torch.empty(P, 3, dtype=torch.float32, device=dev)
     _lib.check(L.vfnerf_mlp_points_fwd(C.byref(va.desc), va.flat.data_ptr(), C.byref(ra.desc), ra.flat.data_ptr(),
-                                       vf_net.multires, rn_net.multires_view, vf_net.skip_layer, 1e-5, _lib.PREC_BF16,
+                                       vf_net.multires, rn_net.multires_view, vf_net.skip_layer, 1e-5,
+                                       _lib.PREC_BF16X3 if vf_net.precision == "bf16x3" else _lib.PREC_BF16,
                                        points.data_ptr(), ray_dirs.data_ptr(), int(samples_per_ray), P, normals.data_ptr(),
                                        colors.data_ptr(), workspace.data_ptr(), workspace.numel(), int(repack),
                                        _stream_ptr(dev)), "vfnerf_mlp_points_fwd")
