@@ -42,7 +42,7 @@ template <> struct Lay<true> {
 };
 template <bool kX3> constexpr size_t tc_smem_bytes() {
   return (size_t)Lay<kX3>::cols * kTileM * 2 + (size_t)kTcStages * Lay<kX3>::stage_bytes + 512 +
-         (size_t)kTcMaxSteps * kTcMaxChunks * 16 + 128;
+         (size_t)kTcMaxSteps * kTcMaxChunks * 16 + 128 + (size_t)2 * 3 * 256 * 4;
 }
 static_assert(tc_smem_bytes<true>() <= 227 * 1024 && tc_smem_bytes<false>() <= 227 * 1024, "activation tile + ring exceed shared memory");
 constexpr int kTcThreads = 480;      // warp 0 producer, warp 1 MMA/relay, warps 2..9 epilogue, warps 10..13 prologue,
@@ -71,6 +71,7 @@ struct TcParams {
   // training: activation stash (forward writes Y tensors, backward reads them and writes D tensors)
   uint8_t* stash;
   TcStash sinfo;
+  long long dot_off;       // fp32 rows of the 3-wide output layers inside wpack (forward programs)
   const float* dcol_pre;   // backward input [n,3]: dL/d(colour pre-sigmoid)
   const float* dv_pre;     // backward input [n,3]: dL/d(vector pre-tanh)
   int dbg;              // experiments: 1 = MMA issuer ignores A-readiness, 2 = epilogue skips TMEM loads / math / stores
@@ -165,6 +166,31 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
       if (is_lo) w -= hi;
     }
     *reinterpret_cast<__nv_bfloat16*>(wpack + off) = __float2bfloat16(w);
+  }
+}
+
+// fp32 rows + biases of the 3-wide output layers (vector rows of the VF net's last layer, the colour net's last layer),
+// with a BatchNorm folded in should the layer have one: [v rows 3 x 256 | colour rows 3 x 256 | bias v 3, bias c 3, 0 0]
+__global__ void tc_pack_dot_kernel(vfnerf_mlp_desc vf, const float* __restrict__ vf_arena, vfnerf_mlp_desc rn,
+                                   const float* __restrict__ rn_arena, int have_rn, float eps, float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTcDotFloats; i += gridDim.x * blockDim.x) {
+    const bool is_bias = i >= 2 * 3 * 256;
+    const int net = is_bias ? (i - 2 * 3 * 256) / 3 : i / 768;
+    const int row = is_bias ? (i - 2 * 3 * 256) % 3 : (i % 768) / 256;
+    const int col = i % 256;
+    float v = 0.f;
+    if (net < 2 && (net == 0 || have_rn)) {
+      const vfnerf_mlp_desc& d = net == 0 ? vf : rn;
+      const float* arena = net == 0 ? vf_arena : rn_arena;
+      const int l = d.n_layers - 1, in_dim = d.in_dim[l];
+      float sc = 1.f, sh = arena[d.b_off[l] + row];
+      if (d.gamma_off[l] >= 0) {
+        sc = arena[d.gamma_off[l] + row] / sqrtf(arena[d.var_off[l] + row] + eps);
+        sh = arena[d.beta_off[l] + row] + (sh - arena[d.mean_off[l] + row]) * sc;
+      }
+      v = is_bias ? sh : (col < in_dim ? arena[d.w_off[l] + (int64_t)row * in_dim + col] * sc : 0.f);
+    }
+    out[i] = v;
   }
 }
 
@@ -417,6 +443,9 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   //       to the lo copy of the A columns: the chunk's MMAs are issued a second time on the lo copy
   uint4* s_chunks = reinterpret_cast<uint4*>(bars + 64);
   int* s_nchunks = reinterpret_cast<int*>(s_chunks + kTcMaxSteps * kTcMaxChunks);
+  // fp32 rows (and biases) of the two 3-wide output layers the epilogue warps evaluate on the CUDA cores (TcStep::dot)
+  float* s_dotb = reinterpret_cast<float*>(s_nchunks + kTcMaxSteps);          // [8]: vector bias 3, colour bias 3
+  float* s_dotw = reinterpret_cast<float*>(s_nchunks) + 32;                   // [2][3][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -459,6 +488,11 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     }
     s_chunks[si * kTcMaxChunks + nc - 1].w |= 1u;
     s_nchunks[si] = nc;
+  }
+  if (!kBwd) {
+    const float* dw = reinterpret_cast<const float*>(p.wpack + p.dot_off);
+    for (int i = threadIdx.x; i < 2 * 3 * 256; i += kTcThreads) s_dotw[i] = __ldg(dw + i);
+    if (threadIdx.x < 8) s_dotb[threadIdx.x] = __ldg(dw + 2 * 3 * 256 + threadIdx.x);
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kTileM) {
     // constant ones-columns [1, 1, 0, ...] that pick up the bias row of every weight image
@@ -958,6 +992,13 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const int stN = st.N;
           const bool st_on = kStash && st.stash_out >= 0 && tile < num_tiles;
           const bool st_tile = kStash && st.stash_out >= 0 && to_act;     // this step's output leaves through warp 14
+          // the last step of a program has no consumer in the activation tile: its output is only stashed (training)
+          // and/or reduced to the 3-wide output below, and it must not arrive on the column-group barriers (every
+          // arrival set is matched by exactly one wait of the MMA issuer)
+          const bool consumer = si + 1 < prog.n_steps;
+          const bool store = consumer || st_tile;
+          const int dot = st.dot;
+          float dsum[3] = {0.f, 0.f, 0.f};
           if (to_act) {
             // Each warp owns two of the four 64-column groups (= K chunks of the next layer): h=0 -> groups 0 and 2,
             // h=1 -> groups 1 and 3.  One generic->async proxy fence (a MEMBAR.ALL.CTA) and one barrier arrival per
@@ -969,7 +1010,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               if (st_tile) mbar_wait(&st_done[bg], (su & 1) ^ 1);
               if (c0 >= stN) {                                 // narrow layer: nothing to write, the barriers still count us
                 if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
-                arrive_grp(bg);
+                if (consumer) arrive_grp(bg);
                 continue;
               }
               const bool second = c0 + 32 < stN;
@@ -979,7 +1020,9 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               if (second) tmem_ld32(acc + c0 + 32, vb);
               tmem_ld_wait();
               TCK(t_ld);
-              if constexpr (kX3) {
+              if (!store) {
+                // nothing leaves through the activation tile (V_ONLY / RENDER inference: the last step only feeds `dot`)
+              } else if constexpr (kX3) {
                 // split-precision hand-off: y = relu(acc) leaves as hi = bf16(y) in the main columns and, for the VF
                 // layers, lo = bf16(y - hi) in the lo columns (same slab, kX3ColLo further on)
                 const bool out_lo = st.out_lo != 0;
@@ -1046,15 +1089,71 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                 if (st_gate && !feat) *gate_unit(p, st.stash_out, tile, bg, row) = make_uint2(gate_lo, gate_hi);
               }
               TCK(t_math);
-              fence_proxy_async_smem();
+              if (store) fence_proxy_async_smem();
               tc_fence_before_sync();
               if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
-              arrive_grp(bg);
+              if (consumer) arrive_grp(bg);
               TCK(t_sig);
               if (tl && it == 0) p.dbg_buf[64 + si * 8 + 3 + 3 * h] = clock64();
               if (tl) p.dbg_buf[64 + si * 8 + 4 + 3 * h] = clock64();
+              if (dot) {
+                // 3-wide output layer on the CUDA cores, AFTER the hand-off: the fp32 accumulator row is still in
+                // registers, the weight rows are broadcast reads from shared memory (all lanes read the same address)
+                const float* wd = s_dotw + (dot - 1) * 768 + c0;
+                float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  if (hf == 1 && !second) break;
+                  const uint32_t* v = hf == 0 ? va : vb;
+#pragma unroll
+                  for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(wd + 32 * hf + 4 * c4);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wd + 256 + 32 * hf + 4 * c4);
+                    const float4 w2 = *reinterpret_cast<const float4*>(wd + 512 + 32 * hf + 4 * c4);
+                    const float y0 = fmaxf(__uint_as_float(v[4 * c4]), 0.f), y1 = fmaxf(__uint_as_float(v[4 * c4 + 1]), 0.f);
+                    const float y2 = fmaxf(__uint_as_float(v[4 * c4 + 2]), 0.f), y3 = fmaxf(__uint_as_float(v[4 * c4 + 3]), 0.f);
+                    dsum[0] = fmaf(y0, w0.x, dsum[0]); e0 = fmaf(y1, w0.y, e0); dsum[0] = fmaf(y2, w0.z, dsum[0]); e0 = fmaf(y3, w0.w, e0);
+                    dsum[1] = fmaf(y0, w1.x, dsum[1]); e1 = fmaf(y1, w1.y, e1); dsum[1] = fmaf(y2, w1.z, dsum[1]); e1 = fmaf(y3, w1.w, e1);
+                    dsum[2] = fmaf(y0, w2.x, dsum[2]); e2 = fmaf(y1, w2.y, e2); dsum[2] = fmaf(y2, w2.z, dsum[2]); e2 = fmaf(y3, w2.w, e2);
+                  }
+                }
+                dsum[0] += e0; dsum[1] += e1; dsum[2] += e2;
+              }
             }
             if (st_tile) ++su;
+            if (dot) {
+              // the two warps that share a TMEM lane quarter hold the two halves of each row's sum: the h = 1 warp parks
+              // its half (fp32) in the row's first aux unit -- free at this point: its last reader was the colour net's
+              // first layer of the PREVIOUS use -- and the h = 0 warp finishes the row
+              float4* xch = reinterpret_cast<float4*>(s_act + (L::aux / 8) * (kTileM * 16) + row * 16);
+              if (h == 1) *xch = make_float4(dsum[0], dsum[1], dsum[2], 0.f);
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+              if (h == 0) {
+                const float4 o = *xch;
+                const float* bias = s_dotb + 3 * (dot - 1);
+                const float r0 = dsum[0] + o.x + bias[0], r1 = dsum[1] + o.y + bias[1], r2 = dsum[2] + o.z + bias[2];
+                if (dot == 1) {
+                  const float nv[3] = {tanhf(r0), tanhf(r1), tanhf(r2)};
+                  if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) p.out_v[pi * p.v_ld + j] = nv[j];
+                  }
+                  if (render) {
+                    // the normal is the first 16-byte unit of the colour net's small inputs (aux columns 0..7)
+                    const float a[8] = {nv[0], nv[1], nv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+                    store_slab_f(s_act, L::aux / 8, row, a);
+                    if (kStash && tile < num_tiles)
+                      *stash_unit(p, p.sinfo.idx_aux, tile, 0, row) = make_uint4(pack_bf16x2(nv[0], nv[1]), pack_bf16x2(nv[2], 0.f), 0u, 0u);
+                    fence_proxy_async_smem();
+                    arrive_grp(kBarAux);           // matched by the colour net's first step
+                  }
+                } else if (valid) {
+                  p.colors[3 * pi] = 1.f / (1.f + expf(-r0));
+                  p.colors[3 * pi + 1] = 1.f / (1.f + expf(-r1));
+                  p.colors[3 * pi + 2] = 1.f / (1.f + expf(-r2));
+                }
+              }
+            }
           } else {
             // VF_FULL: features go to global memory as fp32 (module-call output), 32 columns at a time
 #pragma unroll 1
@@ -1087,44 +1186,6 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               }
             }
           }
-        } else if (st.epi == TC_EPI_V) {
-          if (h == 0) {
-            uint32_t v[16];
-            tmem_ld16(acc, v);
-            tmem_ld_wait();
-            float nv[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) nv[j] = tanhf(__uint_as_float(v[j]));
-            if (valid) {
-#pragma unroll
-              for (int j = 0; j < 3; ++j) p.out_v[pi * p.v_ld + j] = nv[j];
-            }
-            if (render) {
-              // the normal is the first 16-byte unit of the colour net's small inputs (aux columns 0..7)
-              float a[8] = {nv[0], nv[1], nv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-              store_slab_f(s_act, L::aux / 8, row, a);
-              if (kStash && tile < num_tiles)
-                *stash_unit(p, p.sinfo.idx_aux, tile, 0, row) = make_uint4(pack_bf16x2(nv[0], nv[1]), pack_bf16x2(nv[2], 0.f), 0u, 0u);
-              fence_proxy_async_smem();
-            }
-            // RENDER: the aux columns are ready.  VF_FULL: the FEAT step's MMAs do not depend on any A rewrite; this
-            // arrival orders them (and through them the next tile's first MMA into this accumulator buffer) after the
-            // accumulator read above.
-            if (si + 1 < prog.n_steps) {
-              tc_fence_before_sync();
-              arrive_grp(kBarAux);
-            }
-          }
-        } else {  // TC_EPI_RGB
-          if (h == 0) {
-            uint32_t v[16];
-            tmem_ld16(acc, v);
-            tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-              for (int j = 0; j < 3; ++j) p.colors[3 * pi + j] = 1.f / (1.f + expf(-__uint_as_float(v[j])));
-            }
-          }
         }
         tc_fence_before_sync();
         }   // forward steps
@@ -1151,7 +1212,7 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   const int E = 3 + 6 * multires, Epad = round16(E);
   const int L = vf.n_layers;
   VFN_REQUIRE(Epad <= 48 && multires <= kMaxRes && multires_view <= kMaxRes, "tensor-core path: embedding too wide");
-  VFN_REQUIRE(L >= 3 && L + 1 + (rn ? rn->n_layers : 0) <= kTcMaxSteps, "tensor-core path: too many layers");
+  VFN_REQUIRE(L >= 3 && L + (rn ? rn->n_layers - 1 : 0) <= kTcMaxSteps, "tensor-core path: too many layers");
   VFN_REQUIRE(skip_layer < 0 || (skip_layer >= 2 && skip_layer < L - 1), "tensor-core path: skip_layer=%d unsupported", skip_layer);
   for (int l = 0; l < L; ++l) {
     const int want_in = (l == 0) ? E : 256;
@@ -1234,11 +1295,13 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
     }
   }
   const int k256[1] = {256};
-  add(16, 3, 1, main0, k256, CK, TC_EPI_V, 0xF, 0, L - 1, 0, 0, 0, 1.f, 0, x3 ? lo_main : nullptr);
+  // the 3 vector rows of the VF output layer are evaluated by the epilogue of the last hidden layer (TcStep::dot)
+  VFN_REQUIRE(vf.out_dim[L - 2] == 256, "tensor-core path: the last hidden VF layer must be 256 wide");
+  pr.s[ns - 1].dot = 1;
   const int n_v = ns;
   // feature rows of the VF output layer: the image is split-precision as well; render() uses only its hi products (the
   // features are rounded to bf16 for the colour net anyway), the module call (VF_FULL) all three
-  add(256, 256, 1, main0, k256, CK, TC_EPI_FEAT, 0, 0, L - 1, 3, 0, 0, 1.f, 0, x3 ? lo_main : nullptr);
+  add(256, 256, 1, main0, k256, CK, TC_EPI_FEAT, 0xF, 0, L - 1, 3, 0, 0, 1.f, 0, x3 ? lo_main : nullptr);
   const int n_full = ns;
   if (rn) {
     const int Lr = rn->n_layers;
@@ -1254,14 +1317,16 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
     pr.aux_step = ns;
     add(256, 256, 2, c, k, CK, TC_EPI_RELU, 0xF | (1 << kBarAux) | (1 << kBarAuxStatic), 1, 0, 0, 2, pr.small_w, 1.f);
     for (int l = 1; l < Lr - 1; ++l) add(256, 256, 1, main0, k256, CK, TC_EPI_RELU, 0xF, 1, l, 0, 0, 0, 1.f);
-    add(16, 3, 1, main0, k256, CK, TC_EPI_RGB, 0xF, 1, Lr - 1, 0, 0, 0, 1.f);
+    VFN_REQUIRE(Lr >= 2, "tensor-core path: the colour net needs a hidden layer");
+    pr.s[ns - 1].dot = 2;         // the 3 colour rows: epilogue of the last hidden colour layer
   }
+  plan.dot_off = align_up(woff, 128);
+  woff = plan.dot_off + kTcDotFloats * 4;
   plan.wpack_bytes = woff;
   pr.n_steps = ns; pr.render = 1;
   plan.render = pr;
   if (x3 && rn) plan.render.s[n_v].use_lo = 0;
   plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.render = 0; plan.vf_full.aux_step = -1;
-  plan.vf_full.s[n_full - 1].pre_wait_mask = 1 << kBarAux;
   plan.v_only = pr; plan.v_only.n_steps = n_v; plan.v_only.render = 0; plan.v_only.aux_step = -1;
 
   // ---------------- training: stash tensor numbering ----------------
@@ -1382,6 +1447,9 @@ int tc_prepare(const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_ml
   vfnerf_mlp_desc none{};
   tc_pack_kernel<<<dim3(32, pr.n_steps), 256, 0, s>>>(pr, vf, vf_arena, rn ? *rn : none, rn_arena, bn_eps, plan.wpack);
   VFN_LAUNCH_CHECK();
+  tc_pack_dot_kernel<<<2, 256, 0, s>>>(vf, vf_arena, rn ? *rn : none, rn_arena, rn ? 1 : 0, bn_eps,
+                                       reinterpret_cast<float*>(plan.wpack + plan.dot_off));
+  VFN_LAUNCH_CHECK();
   if (plan.wpack_bwd) {
     const TcProgram& pb = rn ? plan.bwd : plan.bwd_vf;
     tc_pack_kernel<<<dim3(32, pb.n_steps), 256, 0, s>>>(pb, vf, vf_arena, rn ? *rn : none, rn_arena, bn_eps, plan.wpack_bwd);
@@ -1402,6 +1470,7 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
            : (mode == TC_MODE_VF_FULL || mode == TC_MODE_VF_FULL_STASH) ? plan.vf_full
            : mode == TC_MODE_BWD ? plan.bwd : mode == TC_MODE_VF_BWD ? plan.bwd_vf : plan.v_only;
   p.wpack = is_bwd ? plan.wpack_bwd : plan.wpack;
+  p.dot_off = plan.dot_off;
   if (stashing || is_bwd) {
     VFN_REQUIRE(plan.stash_buf, "tc_forward: this mode needs the training workspace (keep_for_backward)");
     p.stash = plan.stash_buf; p.sinfo = plan.stash;

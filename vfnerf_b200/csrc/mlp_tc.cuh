@@ -40,6 +40,11 @@ struct TcStep {
   int use_lo;     // this program issues the lo products of the split segments (0: only A_hi W_hi^T, e.g. the feature step
                   // inside render(), whose output is rounded to bf16 for the colour net anyway)
   int out_lo;     // epilogue also writes the lo copy of its output (the next step is a split-precision step)
+  int dot;        // 1 / 2: the epilogue also computes the 3-wide output layer that reads this step's activation -- the VF
+                  // vector (1: tanh, to out_v and, in render(), to the aux columns) or the colour (2: sigmoid, to colors)
+                  // -- as fp32 CUDA-core dot products of the fp32 accumulator row with the fp32 weight rows: an
+                  // M = 256 pair MMA costs 128 cycles whatever its N, so a 3-channel tensor-core step is as expensive
+                  // as a 256-channel one (round 1: 13 % of the tensor time for 6 of 3 334 channels)
   int K;          // sum of seg_k == columns of the weight image
   int chunk_k;    // K columns per pipeline chunk (multiple of 16, N*chunk_k*2 <= 32 KiB); chunks never straddle segments
   int epi;        // TcEpi
@@ -59,7 +64,7 @@ struct TcStep {
   int mask_src;      // backward: stash tensor whose sign pattern (ReLU) or value (tanh) gates this step's output
 };
 
-enum TcEpi { TC_EPI_RELU = 0, TC_EPI_V = 2, TC_EPI_FEAT = 3, TC_EPI_RGB = 4,
+enum TcEpi { TC_EPI_RELU = 0, TC_EPI_FEAT = 3,
              TC_EPI_BWD_RELU = 5,    // dX * (Y > 0)            (Y = stashed forward activation)
              TC_EPI_BWD_TANH = 6 };  // dX * (1 - Y^2)          (Y = stashed tanh features)
 enum TcMode { TC_MODE_V_ONLY = 0, TC_MODE_VF_FULL = 1, TC_MODE_RENDER = 2, TC_MODE_RENDER_STASH = 3, TC_MODE_BWD = 4,
@@ -100,9 +105,13 @@ struct TcProgram {
   TcStep s[kTcMaxSteps];
 };
 
+// fp32 rows of the two 3-wide output layers (TcStep::dot), appended to the weight images:
+// [vector rows 3 x 256 | colour rows 3 x 256 | vector bias 3, colour bias 3, 0, 0]
+constexpr int kTcDotFloats = 2 * 3 * 256 + 8;
 struct TcPlan {
   uint8_t* wpack = nullptr;   // weight images of every step of the RENDER program (VF steps are shared by all modes)
   int64_t wpack_bytes = 0;
+  int64_t dot_off = 0;        // byte offset of the kTcDotFloats block inside wpack
   TcProgram render{}, vf_full{}, v_only{};
   // training (keep_for_backward): stash layout, the dgrad program with its transposed weight images, scratch
   TcProgram bwd{}, bwd_vf{};
