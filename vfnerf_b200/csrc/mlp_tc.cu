@@ -52,7 +52,8 @@ constexpr float kInvSqrt2 = 0.70710678118654752f;
 // readiness barriers (leader CTA): 0..3 = 64-column groups of the main region (one per K chunk; group g is written by
 // the epilogue warps of half g%2), 4 = the normal in the aux region (half-0 epilogue warps); 5 = skip region, 6 = emb0
 // region, 7 = point/view part of the aux region (prologue warps).  Each expects 4 warps x 2 CTAs = 8 arrivals.
-constexpr int kGroups = 8, kBarAux = 4, kBarSkip = 5, kBarEmb0 = 6, kBarAuxStatic = 7;
+constexpr int kGroups = 9, kBarAux = 4, kBarSkip = 5, kBarEmb0 = 6, kBarAuxStatic = 7,
+              kBarDot = 8;   // 8: the prologue warps have read the accumulator row of a TcStep::dot step (both CTAs)
 
 struct TcParams {
   TcProgram prog;
@@ -588,8 +589,9 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const uint32_t fresh = (kdbg & 1) ? 0u : 0xFFFFu;   // per-chunk masks are pre-filtered in the chunk table
           uint32_t accumulate = 0;
           TCK(t_issue);
+          const int pre_wait = st.pre_wait_mask | ((st.dot_guard_next && tile_no > 0) ? (1 << kBarDot) : 0);
           for (int g = 0; g < kGroups; ++g) {
-            if (st.pre_wait_mask & (1 << g)) {
+            if (pre_wait & (1 << g)) {
               mbar_wait_cluster(&grp[g], (grp_par >> g) & 1u);
               grp_par ^= (1u << g);
             }
@@ -790,64 +792,71 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         fence_proxy_async_smem();
         arrive_pro(kBarSkip);
       }
-    } else
-    for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++n) {
-      const long long tile = tile_of(pair);
-      const long long pi = tile * kTileM + row;
-      const bool valid = pi < p.n_points;
-      const bool st_on = kStash && tile < num_tiles;
-      float pt[3], emb[48];
-      load_point(p, pi, valid, pt);
+    } else {
+      // ---- inputs of tile `pair` (the n-th tile of this CTA), part A: emb0 (+ skip) columns
+      auto prep_a = [&](long long pair, int n) {
+        const long long tile = tile_of(pair);
+        const long long pi = tile * kTileM + row;
+        const bool valid = pi < p.n_points;
+        const bool st_on = kStash && tile < num_tiles;
+        float pt[3], emb[48];
+        load_point(p, pi, valid, pt);
 #pragma unroll
-      for (int i = 0; i < 48; ++i) emb[i] = 0.f;
-      embed3<kX3>(pt, prog.multires, emb);
+        for (int i = 0; i < 48; ++i) emb[i] = 0.f;
+        embed3<kX3>(pt, prog.multires, emb);
 #pragma unroll
-      for (int i = 0; i < 48; ++i)
-        if (i >= E) emb[i] = 0.f;
-      // ---- emb0: hi slabs then lo slabs
-      if (n > 0) mbar_wait(&reg_free[0], (n - 1) & 1);
-#pragma unroll
-      for (int sl = 0; sl < 6; ++sl) {
-        if (sl < nsl) {
-          float hi[8], lo[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float v = emb[sl * 8 + j];
-            hi[j] = __bfloat162float(__float2bfloat16(v));
-            lo[j] = v - hi[j];
-          }
-          store_slab_f(s_act, L::emb0 / 8 + sl, row, hi);
-          store_slab_f(s_act, L::emb0 / 8 + nsl + sl, row, lo);
-          if (st_on) {
-            *stash_unit(p, p.sinfo.idx_emb0, tile, sl, row) =
-                make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-            *stash_unit(p, p.sinfo.idx_emb0, tile, nsl + sl, row) =
-                make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      arrive_pro(kBarEmb0);
-      // ---- skip region: embedding / sqrt(2)   (split-precision tile: the skip layer reads the emb0 columns instead)
-      if (!kX3 && prog.skip_step >= 0) {
-        if (n > 0) mbar_wait(&reg_free[1], (n - 1) & 1);
-#pragma unroll
-        for (int i = 0; i < 48; ++i) emb[i] *= kInvSqrt2;
+        for (int i = 0; i < 48; ++i)
+          if (i >= E) emb[i] = 0.f;
+        // ---- emb0: hi slabs then lo slabs
+        if (n > 0) mbar_wait(&reg_free[0], (n - 1) & 1);
 #pragma unroll
         for (int sl = 0; sl < 6; ++sl) {
-          store_slab_f(s_act, L::skip / 8 + sl, row, emb + 8 * sl);
-          if (st_on) {
-            const float* e8 = emb + 8 * sl;
-            *stash_unit(p, p.sinfo.idx_skip, tile, sl, row) =
-                make_uint4(pack_bf16x2(e8[0], e8[1]), pack_bf16x2(e8[2], e8[3]), pack_bf16x2(e8[4], e8[5]), pack_bf16x2(e8[6], e8[7]));
+          if (sl < nsl) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float v = emb[sl * 8 + j];
+              hi[j] = __bfloat162float(__float2bfloat16(v));
+              lo[j] = v - hi[j];
+            }
+            store_slab_f(s_act, L::emb0 / 8 + sl, row, hi);
+            store_slab_f(s_act, L::emb0 / 8 + nsl + sl, row, lo);
+            if (st_on) {
+              *stash_unit(p, p.sinfo.idx_emb0, tile, sl, row) =
+                  make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+              *stash_unit(p, p.sinfo.idx_emb0, tile, nsl + sl, row) =
+                  make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+            }
           }
         }
         fence_proxy_async_smem();
-        arrive_pro(kBarSkip);
-      }
-      // ---- aux region, columns 8..47: [p(3), embed(view dir)(3+6*Lv), 0...]  (columns 0..7 belong to the V step)
-      if (prog.aux_step >= 0) {
-        float a[40], d[3] = {0.f, 0.f, 0.f};
+        arrive_pro(kBarEmb0);
+        // ---- skip region: embedding / sqrt(2)   (split-precision tile: the skip layer reads the emb0 columns instead)
+        if (!kX3 && prog.skip_step >= 0) {
+          if (n > 0) mbar_wait(&reg_free[1], (n - 1) & 1);
+#pragma unroll
+          for (int i = 0; i < 48; ++i) emb[i] *= kInvSqrt2;
+#pragma unroll
+          for (int sl = 0; sl < 6; ++sl) {
+            store_slab_f(s_act, L::skip / 8 + sl, row, emb + 8 * sl);
+            if (st_on) {
+              const float* e8 = emb + 8 * sl;
+              *stash_unit(p, p.sinfo.idx_skip, tile, sl, row) =
+                  make_uint4(pack_bf16x2(e8[0], e8[1]), pack_bf16x2(e8[2], e8[3]), pack_bf16x2(e8[4], e8[5]), pack_bf16x2(e8[6], e8[7]));
+            }
+          }
+          fence_proxy_async_smem();
+          arrive_pro(kBarSkip);
+        }
+      };
+      // ---- part B: aux region, columns 8..47: [p(3), embed(view dir)(3+6*Lv), 0...]  (columns 0..7: the normal, below)
+      auto prep_b = [&](long long pair, int n) {
+        const long long tile = tile_of(pair);
+        const long long pi = tile * kTileM + row;
+        const bool valid = pi < p.n_points;
+        const bool st_on = kStash && tile < num_tiles;
+        float pt[3], a[40], d[3] = {0.f, 0.f, 0.f};
+        load_point(p, pi, valid, pt);
 #pragma unroll
         for (int j = 0; j < 40; ++j) a[j] = 0.f;
         if (valid) {
@@ -873,6 +882,78 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         }
         fence_proxy_async_smem();
         arrive_pro(kBarAuxStatic);
+      };
+      // ---- the 3-wide output layer that reads step si's activation (TcStep::dot), on the CUDA cores: this thread owns
+      // TMEM lane (warp % 4) * 32 + lane = one point; it reads the step's fp32 accumulator row (256 columns), applies the
+      // ReLU and takes the three dot products with the fp32 weight rows (broadcast reads from shared memory).  The
+      // epilogue warps do the hand-off of the same accumulator concurrently; the MMA issuer does not reuse the
+      // accumulator buffer before this warp has arrived on kBarDot.
+      const int qd = warp & 3, rowd = qd * 32 + lane;
+      auto dot_step = [&](int si, uint32_t gstep, long long pair) {
+        const int dot = prog.s[si].dot;
+        const long long tile = tile_of(pair);
+        const long long pi = tile * kTileM + rowd;
+        const bool valid = pi < p.n_points;
+        mbar_wait(&acc_full[gstep & 1], (gstep >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t acc = tmem + (gstep & 1) * kAccCols + ((uint32_t)(qd * 32) << 16);
+        const float* wd = s_dotw + (dot - 1) * 768;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(acc + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wd + c0 + 4 * c4);
+            const float4 w1 = *reinterpret_cast<const float4*>(wd + 256 + c0 + 4 * c4);
+            const float4 w2 = *reinterpret_cast<const float4*>(wd + 512 + c0 + 4 * c4);
+            const float y0 = fmaxf(__uint_as_float(v[4 * c4]), 0.f), y1 = fmaxf(__uint_as_float(v[4 * c4 + 1]), 0.f);
+            const float y2 = fmaxf(__uint_as_float(v[4 * c4 + 2]), 0.f), y3 = fmaxf(__uint_as_float(v[4 * c4 + 3]), 0.f);
+            d0 = fmaf(y0, w0.x, d0); e0 = fmaf(y1, w0.y, e0); d0 = fmaf(y2, w0.z, d0); e0 = fmaf(y3, w0.w, e0);
+            d1 = fmaf(y0, w1.x, d1); e1 = fmaf(y1, w1.y, e1); d1 = fmaf(y2, w1.z, d1); e1 = fmaf(y3, w1.w, e1);
+            d2 = fmaf(y0, w2.x, d2); e2 = fmaf(y1, w2.y, e2); d2 = fmaf(y2, w2.z, d2); e2 = fmaf(y3, w2.w, e2);
+          }
+        }
+        tc_fence_before_sync();
+        // accumulator row consumed: the buffer may be overwritten (matched by the issuer's wait at TcProgram::dot_guard)
+        { __syncwarp(); if (lane == 0) { if (rank == 0) mbar_arrive(&grp[kBarDot]); else mbar_arrive_remote(&grp[kBarDot], 0); } }
+        const float* bias = s_dotb + 3 * (dot - 1);
+        const float r0 = d0 + e0 + bias[0], r1 = d1 + e1 + bias[1], r2 = d2 + e2 + bias[2];
+        if (dot == 1) {
+          const float nv[3] = {tanhf(r0), tanhf(r1), tanhf(r2)};
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) p.out_v[pi * p.v_ld + j] = nv[j];
+          }
+          if (prog.render) {
+            // the normal is the first 16-byte unit of the colour net's small inputs (aux columns 0..7); its previous
+            // reader (the colour net's first layer of the previous tile) completed long ago
+            const float a[8] = {nv[0], nv[1], nv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+            store_slab_f(s_act, L::aux / 8, rowd, a);
+            if (kStash && tile < num_tiles)
+              *stash_unit(p, p.sinfo.idx_aux, tile, 0, rowd) = make_uint4(pack_bf16x2(nv[0], nv[1]), pack_bf16x2(nv[2], 0.f), 0u, 0u);
+            fence_proxy_async_smem();
+            arrive_pro(kBarAux);           // matched by the colour net's first step
+          }
+        } else if (valid) {
+          p.colors[3 * pi] = 1.f / (1.f + expf(-r0));
+          p.colors[3 * pi + 1] = 1.f / (1.f + expf(-r1));
+          p.colors[3 * pi + 2] = 1.f / (1.f + expf(-r2));
+        }
+      };
+      // per tile: [inputs A of the NEXT tile] -> vector dot -> [inputs B of the next tile] -> colour dot, so the next
+      // tile's operands are in place long before its first MMA and no region is rewritten while it is still being read
+      const int d_first = prog.dot_step[0], d_second = prog.dot_step[1];
+      if (pair0 < num_pairs) { prep_a(pair0, 0); if (prog.aux_step >= 0) prep_b(pair0, 0); }
+      for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++n) {
+        const long long next = pair + pair_step;
+        const uint32_t g0 = (uint32_t)n * (uint32_t)prog.n_steps;
+        if (next < num_pairs) prep_a(next, n + 1);
+        if (d_first >= 0) dot_step(d_first, g0 + d_first, pair);
+        if (next < num_pairs && prog.aux_step >= 0) prep_b(next, n + 1);
+        if (d_second >= 0) dot_step(d_second, g0 + d_second, pair);
       }
     }
   } else {
@@ -993,12 +1074,10 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const bool st_on = kStash && st.stash_out >= 0 && tile < num_tiles;
           const bool st_tile = kStash && st.stash_out >= 0 && to_act;     // this step's output leaves through warp 14
           // the last step of a program has no consumer in the activation tile: its output is only stashed (training)
-          // and/or reduced to the 3-wide output below, and it must not arrive on the column-group barriers (every
-          // arrival set is matched by exactly one wait of the MMA issuer)
+          // and/or reduced to a 3-wide output by the prologue warps (TcStep::dot), and it must not arrive on the
+          // column-group barriers (every arrival set is matched by exactly one wait of the MMA issuer)
           const bool consumer = si + 1 < prog.n_steps;
           const bool store = consumer || st_tile;
-          const int dot = st.dot;
-          float dsum[3] = {0.f, 0.f, 0.f};
           if (to_act) {
             // Each warp owns two of the four 64-column groups (= K chunks of the next layer): h=0 -> groups 0 and 2,
             // h=1 -> groups 1 and 3.  One generic->async proxy fence (a MEMBAR.ALL.CTA) and one barrier arrival per
@@ -1013,6 +1092,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                 if (consumer) arrive_grp(bg);
                 continue;
               }
+              // nothing leaves through the activation tile (inference: the last step only feeds the prologue warps' dot)
+              if (!store) continue;
               const bool second = c0 + 32 < stN;
               uint32_t va[32], vb[32];
               TCK(t_other);
@@ -1020,9 +1101,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               if (second) tmem_ld32(acc + c0 + 32, vb);
               tmem_ld_wait();
               TCK(t_ld);
-              if (!store) {
-                // nothing leaves through the activation tile (V_ONLY / RENDER inference: the last step only feeds `dot`)
-              } else if constexpr (kX3) {
+              if constexpr (kX3) {
                 // split-precision hand-off: y = relu(acc) leaves as hi = bf16(y) in the main columns and, for the VF
                 // layers, lo = bf16(y - hi) in the lo columns (same slab, kX3ColLo further on)
                 const bool out_lo = st.out_lo != 0;
@@ -1089,71 +1168,15 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                 if (st_gate && !feat) *gate_unit(p, st.stash_out, tile, bg, row) = make_uint2(gate_lo, gate_hi);
               }
               TCK(t_math);
-              if (store) fence_proxy_async_smem();
+              fence_proxy_async_smem();
               tc_fence_before_sync();
               if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
               if (consumer) arrive_grp(bg);
               TCK(t_sig);
               if (tl && it == 0) p.dbg_buf[64 + si * 8 + 3 + 3 * h] = clock64();
               if (tl) p.dbg_buf[64 + si * 8 + 4 + 3 * h] = clock64();
-              if (dot) {
-                // 3-wide output layer on the CUDA cores, AFTER the hand-off: the fp32 accumulator row is still in
-                // registers, the weight rows are broadcast reads from shared memory (all lanes read the same address)
-                const float* wd = s_dotw + (dot - 1) * 768 + c0;
-                float e0 = 0.f, e1 = 0.f, e2 = 0.f;
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                  if (hf == 1 && !second) break;
-                  const uint32_t* v = hf == 0 ? va : vb;
-#pragma unroll
-                  for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(wd + 32 * hf + 4 * c4);
-                    const float4 w1 = *reinterpret_cast<const float4*>(wd + 256 + 32 * hf + 4 * c4);
-                    const float4 w2 = *reinterpret_cast<const float4*>(wd + 512 + 32 * hf + 4 * c4);
-                    const float y0 = fmaxf(__uint_as_float(v[4 * c4]), 0.f), y1 = fmaxf(__uint_as_float(v[4 * c4 + 1]), 0.f);
-                    const float y2 = fmaxf(__uint_as_float(v[4 * c4 + 2]), 0.f), y3 = fmaxf(__uint_as_float(v[4 * c4 + 3]), 0.f);
-                    dsum[0] = fmaf(y0, w0.x, dsum[0]); e0 = fmaf(y1, w0.y, e0); dsum[0] = fmaf(y2, w0.z, dsum[0]); e0 = fmaf(y3, w0.w, e0);
-                    dsum[1] = fmaf(y0, w1.x, dsum[1]); e1 = fmaf(y1, w1.y, e1); dsum[1] = fmaf(y2, w1.z, dsum[1]); e1 = fmaf(y3, w1.w, e1);
-                    dsum[2] = fmaf(y0, w2.x, dsum[2]); e2 = fmaf(y1, w2.y, e2); dsum[2] = fmaf(y2, w2.z, dsum[2]); e2 = fmaf(y3, w2.w, e2);
-                  }
-                }
-                dsum[0] += e0; dsum[1] += e1; dsum[2] += e2;
-              }
             }
             if (st_tile) ++su;
-            if (dot) {
-              // the two warps that share a TMEM lane quarter hold the two halves of each row's sum: the h = 1 warp parks
-              // its half (fp32) in the row's first aux unit -- free at this point: its last reader was the colour net's
-              // first layer of the PREVIOUS use -- and the h = 0 warp finishes the row
-              float4* xch = reinterpret_cast<float4*>(s_act + (L::aux / 8) * (kTileM * 16) + row * 16);
-              if (h == 1) *xch = make_float4(dsum[0], dsum[1], dsum[2], 0.f);
-              asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-              if (h == 0) {
-                const float4 o = *xch;
-                const float* bias = s_dotb + 3 * (dot - 1);
-                const float r0 = dsum[0] + o.x + bias[0], r1 = dsum[1] + o.y + bias[1], r2 = dsum[2] + o.z + bias[2];
-                if (dot == 1) {
-                  const float nv[3] = {tanhf(r0), tanhf(r1), tanhf(r2)};
-                  if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) p.out_v[pi * p.v_ld + j] = nv[j];
-                  }
-                  if (render) {
-                    // the normal is the first 16-byte unit of the colour net's small inputs (aux columns 0..7)
-                    const float a[8] = {nv[0], nv[1], nv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-                    store_slab_f(s_act, L::aux / 8, row, a);
-                    if (kStash && tile < num_tiles)
-                      *stash_unit(p, p.sinfo.idx_aux, tile, 0, row) = make_uint4(pack_bf16x2(nv[0], nv[1]), pack_bf16x2(nv[2], 0.f), 0u, 0u);
-                    fence_proxy_async_smem();
-                    arrive_grp(kBarAux);           // matched by the colour net's first step
-                  }
-                } else if (valid) {
-                  p.colors[3 * pi] = 1.f / (1.f + expf(-r0));
-                  p.colors[3 * pi + 1] = 1.f / (1.f + expf(-r1));
-                  p.colors[3 * pi + 2] = 1.f / (1.f + expf(-r2));
-                }
-              }
-            }
           } else {
             // VF_FULL: features go to global memory as fp32 (module-call output), 32 columns at a time
 #pragma unroll 1
@@ -1324,10 +1347,24 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   woff = plan.dot_off + kTcDotFloats * 4;
   plan.wpack_bytes = woff;
   pr.n_steps = ns; pr.render = 1;
+  // a dot step's accumulator row is read by the prologue warps: the step that next writes the same TMEM buffer (two
+  // steps later, possibly in the next tile) waits for their kBarDot arrival
+  auto set_guards = [&](TcProgram& q) {
+    q.dot_step[0] = q.dot_step[1] = -1;
+    int nd = 0;
+    for (int i = 0; i < q.n_steps; ++i) { q.s[i].dot_guard_next = 0; q.s[i].pre_wait_mask &= ~(1 << kBarDot); }
+    for (int i = 0; i < q.n_steps; ++i) {
+      if (!q.s[i].dot) continue;
+      q.dot_step[nd++] = i;
+      const int g = i + 2;
+      if (g < q.n_steps) q.s[g].pre_wait_mask |= 1 << kBarDot; else q.s[g - q.n_steps].dot_guard_next = 1;
+    }
+  };
   plan.render = pr;
   if (x3 && rn) plan.render.s[n_v].use_lo = 0;
   plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.render = 0; plan.vf_full.aux_step = -1;
   plan.v_only = pr; plan.v_only.n_steps = n_v; plan.v_only.render = 0; plan.v_only.aux_step = -1;
+  set_guards(plan.render); set_guards(plan.vf_full); set_guards(plan.v_only);
 
   // ---------------- training: stash tensor numbering ----------------
   const int Lr = rn ? rn->n_layers : 1;     // VF-only plans have no colour tensors

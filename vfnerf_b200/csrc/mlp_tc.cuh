@@ -40,11 +40,14 @@ struct TcStep {
   int use_lo;     // this program issues the lo products of the split segments (0: only A_hi W_hi^T, e.g. the feature step
                   // inside render(), whose output is rounded to bf16 for the colour net anyway)
   int out_lo;     // epilogue also writes the lo copy of its output (the next step is a split-precision step)
-  int dot;        // 1 / 2: the epilogue also computes the 3-wide output layer that reads this step's activation -- the VF
-                  // vector (1: tanh, to out_v and, in render(), to the aux columns) or the colour (2: sigmoid, to colors)
-                  // -- as fp32 CUDA-core dot products of the fp32 accumulator row with the fp32 weight rows: an
-                  // M = 256 pair MMA costs 128 cycles whatever its N, so a 3-channel tensor-core step is as expensive
-                  // as a 256-channel one (round 1: 13 % of the tensor time for 6 of 3 334 channels)
+  int dot;        // 1 / 2: the 3-wide output layer that reads this step's activation -- the VF vector (1: tanh, to out_v
+                  // and, in render(), to the aux columns) or the colour (2: sigmoid, to colors) -- is evaluated by the
+                  // prologue warps as fp32 CUDA-core dot products of this step's fp32 accumulator row with the fp32
+                  // weight rows: an M = 256 pair MMA costs 128 cycles whatever its N, so a 3-channel tensor-core step is
+                  // as expensive as a 256-channel one (round 1: 13 % of the tensor time for 6 of 3 334 channels)
+  int dot_guard_next;   // this step reuses the accumulator buffer of the PREVIOUS tile's last dot step: from the second
+                        // tile on, the issuer waits for the prologue warps' "row consumed" barrier first (same-tile
+                        // reuse is a pre_wait_mask bit)
   int K;          // sum of seg_k == columns of the weight image
   int chunk_k;    // K columns per pipeline chunk (multiple of 16, N*chunk_k*2 <= 32 KiB); chunks never straddle segments
   int epi;        // TcEpi
@@ -101,6 +104,7 @@ struct TcProgram {
   int bwd;          // 1: backward (dgrad) program of render() -- different prologue, no bias segments; 2: of the VF net alone
   int x3;           // split-precision tile layout (kX3Col*), 16 KiB ring slots
   int emb0_last_step;   // the emb0 columns may be rewritten for the next tile once this step's MMAs have completed
+  int dot_step[2];      // steps with TcStep::dot, in order (-1: none)
   int col_aux, col_skip, col_ones, col_emb0, col_lo;   // activation-tile layout of this program
   TcStep s[kTcMaxSteps];
 };
