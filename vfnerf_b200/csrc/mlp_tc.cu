@@ -435,7 +435,10 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   // copy has finished reading it.
   uint64_t* st_ready = reg_free + 3;
   uint64_t* st_done = st_ready + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_done + 4);
+  // "the accumulator of a TcStep::dot step is complete", for the prologue warps.  They cannot share acc_full: a waiter
+  // that does not observe EVERY phase of an mbarrier cannot tell the phase it wants from an older one of equal parity.
+  uint64_t* dot_full = st_done + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dot_full + 1);
   // chunk table: the single-lane producer / MMA-issuer loops must not chase per-chunk facts through the kernel
   // parameters (dependent constant loads cost them ~500 cycles per chunk): everything a chunk needs is one LDS.128.
   //   x = A start-address increment (16-byte units), y = K columns | readiness-barrier mask << 16,
@@ -457,6 +460,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     for (int i = 0; i < kGroups; ++i) mbar_init(&grp[i], 8);    // 4 warps (one half, or the prologue warps) x 2 CTAs
     for (int i = 0; i < 3; ++i) mbar_init(&reg_free[i], 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&st_ready[i], 4); mbar_init(&st_done[i], 1); }
+    mbar_init(dot_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -678,6 +682,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           }
           {
             umma2_commit_u32_w(smem_u32(&acc_full[gstep & 1]));      // accumulators complete -> epilogue warps of both CTAs
+            if (st.dot) umma2_commit_u32_w(smem_u32(dot_full));       // ... and -> the prologue warps (3-wide output layer)
             // side regions whose only reader was this step may now be rewritten for the next tile (prologue warps)
             // [0]: layer-0 operand region (forward) / the whole main region once the VF-only dgrad tile is finished
             if (si == prog.emb0_last_step) umma2_commit_u32_w(smem_u32(&reg_free[0]));
@@ -889,12 +894,14 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       // epilogue warps do the hand-off of the same accumulator concurrently; the MMA issuer does not reuse the
       // accumulator buffer before this warp has arrived on kBarDot.
       const int qd = warp & 3, rowd = qd * 32 + lane;
+      uint32_t n_dots = 0;
       auto dot_step = [&](int si, uint32_t gstep, long long pair) {
         const int dot = prog.s[si].dot;
         const long long tile = tile_of(pair);
         const long long pi = tile * kTileM + rowd;
         const bool valid = pi < p.n_points;
-        mbar_wait(&acc_full[gstep & 1], (gstep >> 1) & 1);
+        mbar_wait(dot_full, n_dots & 1);
+        ++n_dots;
         tc_fence_after_sync();
         const uint32_t acc = tmem + (gstep & 1) * kAccCols + ((uint32_t)(qd * 32) << 16);
         const float* wd = s_dotw + (dot - 1) * 768;
