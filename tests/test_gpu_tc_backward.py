@@ -80,17 +80,21 @@ def _q(x):
 def _emulated_grads(state, points, view_dirs, c_nrm, c_col, eps=1e-5, skip=4):
     """fp32 autograd through a torch model that rounds exactly where the tensor-core path rounds: BatchNorm folded
     into bf16 weights (1/sqrt(2) of the skip connection folded into the producing layer), bf16 activations, fp32
-    accumulation, fp32 bias.  What is left between this and the kernels is the bf16 rounding of dL/dY and
-    accumulation order."""
+    accumulation, fp32 bias; the two 3-wide output layers (VF vector rows, colour) are fp32 dot products of the
+    UNROUNDED previous activation with fp32 weights (TcStep::dot, csrc/mlp_tc.cuh).  What is left between this and the
+    kernels is the bf16 rounding of dL/dY and accumulation order."""
     def leaves(sd):
         return {k: (v.to(DEV).clone().requires_grad_(True) if "running" not in k and v.is_floating_point() else v.to(DEV))
                 for k, v in sd.items()}
     vf, rn = leaves(state["vf_net"]), leaves(state["rendering_net"])
 
-    def layer(sd, i, x, last, post=1.0):
+    def layer(sd, i, x, last, post=1.0, x32=None, n32=0):
         if last:
             W, b = sd[f"layers.{i}.weight"], sd[f"layers.{i}.bias"]
-            return x @ _q(W).T + b
+            y = x @ _q(W).T + b
+            if n32:
+                y = torch.cat([x32 @ W[:n32].T + b[:n32], y[:, n32:]], 1)
+            return y
         W, b = sd[f"layers.{i}.0.weight"], sd[f"layers.{i}.0.bias"]
         sc = sd[f"layers.{i}.1.weight"] / torch.sqrt(sd[f"layers.{i}.1.running_var"] + eps)
         sh = (b - sd[f"layers.{i}.1.running_mean"]) * sc + sd[f"layers.{i}.1.bias"]
@@ -104,17 +108,22 @@ def _emulated_grads(state, points, view_dirs, c_nrm, c_col, eps=1e-5, skip=4):
         last = i == L - 1
         if i == skip:
             x = torch.cat([x, _q(emb * inv)], 1)
-        y = layer(vf, i, x, last, post=inv if i == skip - 1 else 1.0)
+        y = layer(vf, i, x, last, post=inv if i == skip - 1 else 1.0, x32=x32 if last else None, n32=3 if last else 0)
         if last:
             v, feat = torch.tanh(y[:, :3]), _q(torch.tanh(_q(y[:, 3:])))
         else:
-            x = _q(torch.relu(y))
+            x32 = torch.relu(y)
+            x = _q(x32)
     Lr = 1 + sum(1 for k in rn if k.endswith(".0.weight"))
     x = torch.cat([_q(points), _q(U.O.embed(view_dirs, 4)), _q(v.detach()), feat], 1)
     for i in range(Lr):
         last = i == Lr - 1
-        y = layer(rn, i, x, last)
-        x = y if last else _q(torch.relu(y))
+        y = layer(rn, i, x, last, x32=x32 if last else None, n32=3 if last else 0)
+        if last:
+            x = y
+        else:
+            x32 = torch.relu(y)
+            x = _q(x32)
     colors = torch.sigmoid(x)
     ((v * c_nrm).sum() + (colors * c_col).sum()).backward()
     g = {}

@@ -57,6 +57,13 @@ class VectorFieldNerf:
         self.draws_on_device = False
         self._stage: dict = {}          # pinned staging rings of the CPU-generator draws, per device
         self.last_extras: dict = {}
+        # Opt-in for chunked evaluation loops (evaluation/methods.py:510-530 calls render() once per 1024 rays): under
+        # torch.no_grad() the whole forward is captured once per (ray count, sampler settings, precision) as a CUDA
+        # graph and replayed -- per call the host then only copies the inputs into static buffers.  The NerfOutput of a
+        # replayed call aliases static buffers that the NEXT render() call overwrites (the evaluation loop copies
+        # rgb / depth to the host right away); off by default for that reason.
+        self.graph_replay = False
+        self._graphs: dict = {}
 
     # ---- module plumbing (vector_field_nerf.py:84-214) ------------------------------------------
     def set_precision(self, precision: str) -> None:
@@ -223,6 +230,8 @@ class VectorFieldNerf:
         if pose.shape[0] != R or intrinsics.shape[0] != R:
             raise ValueError("pose, pixels and intrinsics must have one row per ray")
         quat = pose.dim() == 2 and pose.shape[1] == 7
+        if self.graph_replay and z_vals_override is None and R > 0 and not torch.is_grad_enabled():
+            return self._render_replay(pose, pixels, intrinsics, quat, draws)
         cfg = self._render_cfg(R, quat)
         # host-side draws in the reference's order (ray_sampler.py:138, 292, 297), then H2D
         if draws is None and self.draws_on_device:
@@ -261,3 +270,94 @@ class VectorFieldNerf:
                           fine_rgb_values=None, fine_depth_map=None, z_vals=z_vals,
                           directional_derivtives=None, ray_dirs=ray_dirs, coarse_colors=colors,
                           weights=call.extras.get("weights"))
+
+
+    # ---- CUDA-graph replay of the forward-only call (opt-in: self.graph_replay) ---------------------------------------
+    def _replay_key(self, R: int, quat: bool, dev: torch.device):
+        rs, fs, c = self.ray_sampler, self.fine_sampler, self.config
+        return (R, quat, str(dev), rs.N_samples, fs.n_fine(), float(rs.near), float(rs.far), float(fs.range),
+                bool(rs.deterministic), bool(fs.deterministic), self.precision, self.recompute_coarse,
+                self.return_ray_dirs, float(c.dir_to_normal_th), len(c.cos_sim_weights), bool(c.normalize_rendering))
+
+    def _render_replay(self, pose, pixels, intrinsics, quat: bool, draws) -> NerfOutput:
+        dev = pixels.device
+        R = pixels.shape[0]
+        key = self._replay_key(R, quat, dev)
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 8:                 # a caller that keeps changing shapes should not hoard graph memory
+                self._graphs.clear()
+            g = self._graphs[key] = _RenderGraph(self, R, quat, dev)
+        return g.replay(pose, pixels, intrinsics, draws)
+
+
+class _RenderGraph:
+    """One captured forward-only render() for a fixed ray count and sampler configuration.  The weight images are
+    re-packed from the parameter arenas inside the graph, so parameter updates between replays are picked up."""
+
+    def __init__(self, model: VectorFieldNerf, R: int, quat: bool, dev: torch.device) -> None:
+        self.model, self.R, self.dev = model, R, dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        nc, nf = model.ray_sampler.N_samples, model.fine_sampler.n_fine()
+        self.pose = torch.zeros((R, 7) if quat else (R, 4, 4), **f32)
+        if not quat:
+            self.pose[:] = torch.eye(4, **f32)
+        else:
+            self.pose[:, 0] = 1.0
+        self.pixels = torch.zeros(R, 2, **f32)
+        self.intrinsics = torch.eye(4, **f32).repeat(R, 1, 1)
+        self.U = [None if model.ray_sampler.deterministic else torch.rand(R, nc, **f32),
+                  None if model.fine_sampler.deterministic else torch.rand(R, nf, **f32),
+                  torch.rand(R, nf, **f32)]
+        # pinned staging of the CPU-generator draws: ring of 4 per tensor, reused after the copy that read it completed
+        self._host = [[None if u is None else [torch.empty(u.shape, dtype=torch.float32).pin_memory(), None] for _ in range(4)]
+                      for u in self.U]
+        self._slot = 0
+        self.graph = torch.cuda.CUDAGraph()
+        was = model.graph_replay
+        model.graph_replay = False
+        try:
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s), torch.no_grad():
+                for _ in range(2):      # lazy one-time work (kernel attributes, arenas, t_vals upload) outside the capture
+                    model.render(self.pose, self.pixels, self.intrinsics, 0, draws=tuple(self.U))
+            torch.cuda.current_stream(dev).wait_stream(s)
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self.out = model.render(self.pose, self.pixels, self.intrinsics, 0, draws=tuple(self.U))
+            self.extras = model.last_extras
+        finally:
+            model.graph_replay = was
+
+    def replay(self, pose, pixels, intrinsics, draws) -> NerfOutput:
+        m = self.model
+        self.pose.copy_(pose, non_blocking=True)
+        self.pixels.copy_(pixels, non_blocking=True)
+        self.intrinsics.copy_(intrinsics, non_blocking=True)
+        if draws is not None:
+            for dst, src in zip(self.U, draws):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+        elif m.draws_on_device:
+            for dst in self.U:
+                if dst is not None:
+                    dst.uniform_()
+        else:
+            # the reference's stream: global CPU generator, order U1 -> U2 -> U3 (ray_sampler.py:138,292,297)
+            k = self._slot
+            self._slot = (k + 1) % 4
+            for dst, ring in zip(self.U, self._host):
+                if dst is None:
+                    continue
+                host, ev = ring[k]
+                if ev is not None:
+                    ev.synchronize()
+                cpu_generator_rand_(host)
+                dst.copy_(host, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.dev))
+                ring[k][1] = ev
+        self.graph.replay()
+        m.last_extras = self.extras
+        return self.out
