@@ -73,6 +73,8 @@ typedef struct vfnerf_render_cfg {
   float dir_to_normal_th;
   float beta_lo, beta_hi, mean_lo, mean_hi, scale_min;   /* LaplaceDensity bounds                */
   float bn_eps;
+  double fine_near_, fine_far_;     /* fine_sampler.near / .far: the range of the fallback samples z_add
+                                       (ray_sampler.py:296-299); the reference's callers set them equal to near/far */
 } vfnerf_render_cfg;
 
 /* Outputs of render() == fields of NerfOutput (models/nerf/output.py:7-22) as filled at
@@ -89,6 +91,17 @@ typedef struct vfnerf_render_out {
   float* z_coarse;      /* [R,Nc]   nullable                                                      */
   float* weights_coarse;/* [R,Nc]   nullable                                                      */
 } vfnerf_render_out;
+
+/* The binding side (vfnerf_b200/_lib.py) mirrors these layouts field by field; sizes are part of the ABI. */
+#ifdef __cplusplus
+#define VFNERF_STATIC_ASSERT(c, m) static_assert(c, m)
+#else
+#define VFNERF_STATIC_ASSERT(c, m) _Static_assert(c, m)
+#endif
+VFNERF_STATIC_ASSERT(sizeof(vfnerf_mlp_desc) == 912, "vfnerf_mlp_desc: 4 + pad 4 ... = 8 + 2*16*4 + 6*16*8 + 8 bytes");
+VFNERF_STATIC_ASSERT(sizeof(vfnerf_render_cfg) == 120, "vfnerf_render_cfg: 12*4 + 3*8 + 7*4 + 4 (pad) + 2*8 bytes");
+VFNERF_STATIC_ASSERT(sizeof(vfnerf_render_out) == 80, "vfnerf_render_out: 10 pointers");
+
 
 int vfnerf_abi_version(void);
 const char* vfnerf_last_error(void);
@@ -277,32 +290,8 @@ int vfnerf_volume_weights(int n_rays, int n_samples, int mode, int normalize, co
 int vfnerf_composite(int n_rays, int n_samples, const float* weights, const float* colors,
                      const float* z, float* rgb, float* depth, void* stream);
 
-/* ---- debug / regression -------------------------------------------------------------------- */
-/* One CTA: D[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T through tcgen05.mma + TMEM; pins the UMMA
- * descriptor conventions of csrc/tc_common.cuh (variant 1 = LBO/SBO swapped, expected to be wrong). */
-int vfnerf_debug_umma_gemm(const float* A, const float* B, float* D, int N, int K, int variant, void* stream);
-/* MN-major operands (both with the reduction index as the row, as activations are stashed):
- * D[128,N] = bf16(At[K,128])^T * bf16(Bt[K,N]).  variant 1 swaps LBO/SBO (expected wrong). */
-int vfnerf_debug_umma_mn_gemm(const float* At, const float* Bt, float* D, int N, int K, int variant, void* stream);
-/* 2-CTA variant (cluster of two, tcgen05.mma.cta_group::2, M = 256): D[256,N] = bf16(A[256,K]) * bf16(B[N,K])^T */
-int vfnerf_debug_umma2_gemm(const float* A, const float* B, float* D, int N, int K, void* stream);
-/* Layout probe for cta_group::2 with M = 128 (64 rows per CTA): A [128,K], B [N,K]; the accumulator is placed at TMEM
- * (lane_off, col_off); dump receives all 128 lanes x 512 columns of both CTAs ([2,128,512] floats, sentinel -777). */
-int vfnerf_debug_umma2_m128_probe(const float* A, const float* B, float* dump, int N, int K, int lane_off, int col_off,
-                                  void* stream);
-/* Micro-benchmark: every CTA issues n_mma back-to-back tcgen05.mma (M=128, N, K=16) from one thread; CTA 0 writes
- * the elapsed SM cycles to cycles_dev[0].  mode 1 adds a tcgen05.commit after every second MMA. */
-int vfnerf_debug_umma_bench(int N, int n_mma, int mode, int n_ctas, long long* cycles_dev, void* stream);
-/* Same for tcgen05.mma.cta_group::2 (M=256, N=256): mode 0 no commits, 1 multicast commit per 4 MMAs, 2 leader-only commit */
-int vfnerf_debug_umma2_bench(int n_mma, int mode, int n_ctas, long long* cycles_dev, void* stream);
-/* Test support for the bf16 training path: after vfnerf_render_fwd(keep_for_backward = 1) [and vfnerf_render_bwd] on
- * `workspace`, convert activation-stash tensor `tensor` to row-major fp32 out[n_rays * n_samples, *n_cols].
- * Numbering (L = VF layers, Lr = colour layers, n_y = L + Lr - 1): 0..L-2 VF hidden activations, L-1 features,
- * L..n_y-1 colour hidden activations, n_y layer-0 input (embedding hi | lo), n_y+1 skip input, n_y+2 small colour
- * inputs, n_y+3+i = dL/d(pre-activation) of tensor i (valid after the backward); 1000 = [n,6] gradients wrt the
- * pre-activations of the colour (cols 0..2) and vector (cols 3..5) outputs.  out may be NULL to query *n_cols. */
-int vfnerf_debug_stash_read(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, const vfnerf_mlp_desc* rn,
-                            void* workspace, int tensor, float* out, int* n_cols, void* stream);
+/* Test-only entry points (UMMA descriptor probes, micro-benchmarks, activation-stash read-back) are NOT part of this
+ * library: they are declared in vfnerf_b200_debug.h and built into a separate libvfnerf_b200_debug.so by the tests. */
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ B = torch.randn(N, K, generator=g).cuda()
 ref = (A.bfloat16().float() @ B.bfloat16().float().T)          # [128, N]
 for lane_off, col_off in ((0, 0), (0, 128)):
     dump = torch.zeros(2, 128, 512, device="cuda")
-    _lib.check(L.vfnerf_debug_umma2_m128_probe(A.data_ptr(), B.data_ptr(), dump.data_ptr(), N, K, lane_off, col_off,
+    _lib.check_debug(L.vfnerf_debug_umma2_m128_probe(A.data_ptr(), B.data_ptr(), dump.data_ptr(), N, K, lane_off, col_off,
                                                torch.cuda.current_stream().cuda_stream), "probe")
     torch.cuda.synchronize()
     d = dump.cpu()

@@ -18,3 +18,11 @@ def built_lib():
     from vfnerf_b200 import _lib
     _lib.build()
     return _lib.lib()
+
+
+@pytest.fixture(scope="session")
+def debug_lib():
+    """Builds (if stale) and loads the TEST-ONLY libvfnerf_b200_debug.so (UMMA probes, stash read-back)."""
+    from vfnerf_b200 import _lib
+    _lib.build_debug()
+    return _lib.debug_lib()

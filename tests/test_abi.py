@@ -10,8 +10,8 @@ from vfnerf_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "vfnerf_b200.h")).read()
+def declared_symbols(header="vfnerf_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(vfnerf_[a-z0-9_]+)\s*\(", text)))
 
@@ -26,11 +26,36 @@ def test_library_builds_and_exports_every_declared_symbol(built_lib):
     assert built_lib.vfnerf_abi_version() == 1
 
 
+def test_product_library_has_no_debug_surface(built_lib):
+    """Probe kernels, micro-benchmarks and the stash read-back live in the test-only library."""
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    assert not any(s.startswith("vfnerf_debug") for s in declared_symbols())
+    for s in declared_symbols("vfnerf_b200_debug.h"):
+        assert not hasattr(raw, s), f"{s} leaked into the product library"
+    import subprocess
+    strings = subprocess.run(["strings", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "VFNERF_TC_DBG" not in strings            # the product build reads no environment variable
+
+
+def test_debug_library_exports_its_header(debug_lib):
+    syms = declared_symbols("vfnerf_b200_debug.h")
+    assert set(syms) == set(_lib.DEBUG_PROTOTYPES)
+    raw = ctypes.CDLL(_lib.DEBUG_LIB_PATH)
+    for s in syms:
+        assert hasattr(raw, s), s
+
+
 def test_struct_layouts_match_header():
-    # sizes the C side static-asserts implicitly through the ABI: 4 + 2*16*4 + 6*16*8 + 8 (+pad)
-    assert ctypes.sizeof(_lib.MlpDesc) == 8 + 2 * 16 * 4 + 6 * 16 * 8 + 8 - 4 + 4 or ctypes.sizeof(_lib.MlpDesc) == 912
-    assert ctypes.sizeof(_lib.RenderOut) == 10 * 8
-    assert ctypes.sizeof(_lib.RenderCfg) == 12 * 4 + 3 * 8 + 7 * 4 + 4
+    """Exact sizes: the header static_asserts the same numbers (include/vfnerf_b200.h), so the C side and the ctypes
+    mirror cannot drift apart silently."""
+    header = open(os.path.join(ROOT, "include", "vfnerf_b200.h")).read()
+    want = {name: int(n) for name, n in re.findall(r"VFNERF_STATIC_ASSERT\(sizeof\((\w+)\) == (\d+)", header)}
+    assert want == {"vfnerf_mlp_desc": 912, "vfnerf_render_cfg": 120, "vfnerf_render_out": 80}
+    assert ctypes.sizeof(_lib.MlpDesc) == want["vfnerf_mlp_desc"]
+    assert ctypes.sizeof(_lib.RenderCfg) == want["vfnerf_render_cfg"]
+    assert ctypes.sizeof(_lib.RenderOut) == want["vfnerf_render_out"]
+    # field offsets that matter for alignment: the first double of render_cfg and the first int64 of mlp_desc
+    assert _lib.RenderCfg.near_.offset == 48 and _lib.MlpDesc.w_off.offset == 136
 
 
 def test_sass_has_no_legacy_tensor_path(built_lib):

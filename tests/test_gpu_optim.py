@@ -98,3 +98,84 @@ def test_training_with_arena_optimizer_eager_and_graphed(built_lib, precision):
     assert ((we - wg).abs() > 0.5 * lr).float().mean().item() < 0.02
     l1 = step(pose, uv, K, draws=draws, rgb_gt=rgb_gt, depth_gt=dep_gt).item()
     assert l1 == l1 and l1 != l0
+
+
+def _rand_grads(params, gen, scale=1e-2):
+    for p in params:
+        g = (torch.randn(p.shape, generator=gen) * scale).to(DEV)
+        if p.grad is None:
+            p.grad = g
+        else:
+            p.grad.copy_(g)
+
+
+def test_arena_adam_checkpoint_round_trip_and_reference_format(built_lib, tmp_path):
+    """model.save()/load() with ArenaAdam installed (vector_field_nerf.py:178-214): the optimizer state is emitted in the
+    reference's torch.optim.Adam format (one group over model.parameters(), VF entries duplicated), so (a) a resumed run
+    continues bit for bit, and (b) a checkpoint written with the reference's own optimizer loads."""
+    case, z = U.load_golden("small_det")
+    st = U.case_state(case, z)
+    gen = torch.Generator().manual_seed(3)
+    a = U.make_model(case, st, DEV)
+    optim.use_arena_optimizer(a, max_norm=0.5)
+    for _ in range(3):
+        a.optimizer.zero_grad()
+        _rand_grads(_unique_params(a), gen)
+        a.optimizer.step()
+    a.save(7, str(tmp_path))
+    sd = a.optimizer.state_dict()
+    n_par = len(a.parameters())
+    assert len(sd["param_groups"]) == 1 and len(sd["param_groups"][0]["params"]) == n_par
+    assert len(sd["state"]) == len(_unique_params(a))             # duplicates share one state entry, like torch
+    assert float(sd["state"][0]["step"]) == 3.0
+    # (a) resume into a fresh model + fresh ArenaAdam, then take the same step in both
+    b = U.make_model(case, st, DEV)
+    optim.use_arena_optimizer(b, max_norm=0.5)
+    assert b.load(str(tmp_path / "latest.pth")) == 8
+    g2 = torch.Generator().manual_seed(11)
+    grads = [(torch.randn(p.shape, generator=g2) * 1e-2).to(DEV) for p in _unique_params(a)]
+    for m in (a, b):
+        m.optimizer.zero_grad()
+        for p, g in zip(_unique_params(m), grads):
+            p.grad.copy_(g)
+        m.optimizer.step()
+    for p, q in zip(_unique_params(a), _unique_params(b)):
+        assert torch.equal(p, q)
+    # (b) the reference trainer's optimizer state (torch Adam over the duplicated list) -> ArenaAdam
+    c = U.make_model(case, st, DEV)                                # its default optimizer IS the reference's
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(2):
+            c.optimizer.zero_grad()
+            _rand_grads(_unique_params(c), gen)
+            c.optimizer.step()
+    ref_sd = c.optimizer.state_dict()
+    d = U.make_model(case, st, DEV)
+    optim.use_arena_optimizer(d)
+    d.optimizer.load_state_dict(ref_sd)
+    k = len(list(d.vector_field_network.parameters()))            # first colour-net entry of the reference's list
+    assert torch.equal(d.optimizer.state_dict()["state"][k]["exp_avg"], ref_sd["state"][k]["exp_avg"])
+    assert torch.equal(d.optimizer.state_dict()["state"][0]["exp_avg_sq"], ref_sd["state"][0]["exp_avg_sq"])
+    assert float(d.optimizer._step.item()) == 2.0                  # iteration count, not the doubled VF counter
+
+
+def test_leaving_flat_gradient_mode_when_a_torch_optimizer_takes_over(built_lib):
+    """new_scheduler()/reset_scheduler() install a plain torch Adam (vector_field_nerf.py:103-130): gradients must go back
+    to p.grad, or clip + step would silently do nothing."""
+    case, z = U.load_golden("small_perturb")
+    model = U.make_model(case, U.case_state(case, z), DEV)
+    opt = optim.use_arena_optimizer(model)
+    model.reset_scheduler(100)
+    assert isinstance(model.optimizer, torch.optim.Adam) and model.vector_field_network.arena().grad_flat is None
+    uv, pose, K = (U.t(z, k).to(DEV) for k in ("uv", "pose", "K"))
+    model.optimizer.zero_grad()
+    out = model.render(pose, uv, K, 0)
+    (out.coarse_rgb_values.sum() + (out.coarse_normals ** 2).sum()).backward()
+    w = model.vector_field_network.layers[0][0].weight
+    assert w.grad is not None and w.grad.abs().sum().item() > 0
+    before = w.detach().clone()
+    model.optimizer.step()
+    assert not torch.equal(before, w.detach())
+    with pytest.raises(RuntimeError):
+        opt.step()                                  # the orphaned ArenaAdam refuses instead of updating nothing

@@ -10,12 +10,12 @@ DEV = "cuda"
 
 
 @pytest.mark.parametrize("N,K", [(256, 256), (16, 256), (256, 48), (224, 256), (128, 64), (64, 16)])
-def test_umma_descriptor_conventions(built_lib, N, K):
+def test_umma_descriptor_conventions(debug_lib, N, K):
     g = torch.Generator().manual_seed(N * 1000 + K)
     A = torch.randn(128, K, generator=g).to(DEV)
     B = torch.randn(N, K, generator=g).to(DEV)
     D = torch.zeros(128, N, device=DEV)
-    _lib.check(built_lib.vfnerf_debug_umma_gemm(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, 0,
+    _lib.check_debug(debug_lib.vfnerf_debug_umma_gemm(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, 0,
                                                 torch.cuda.current_stream().cuda_stream), "debug_umma_gemm")
     torch.cuda.synchronize()
     ref = A.bfloat16().float() @ B.bfloat16().float().T
@@ -25,119 +25,103 @@ def test_umma_descriptor_conventions(built_lib, N, K):
 
 
 def _tame_state():
-    """A bf16-friendly model: default-like init (gain 1, no output centring).  Its density is degenerate
-     but the per-point MLP outputs are a meaningful bf16 parity target."""
+    """A bf16-friendly model: default-like init (gain 1, no output centring): a plain-bf16 chain can meet north_star's
+    5e-3 on its per-point outputs.  Its DENSITY is degenerate, so render()-level rgb / depth claims
+    are never made on it: those live in tests/test_gpu_x3.py, on the golden model, for the mode that meets them."""
     return U.S.synthetic_state(0, vf_gain=1.0, center_output=False)
 
 
+# Every expected value below comes from the CPU oracle (oracle/render_oracle.py, pinned to the live reference by
+# tests/golden/make_golden.py) or from the reference goldens -- never from this repo's own fp32 kernels.
+
 @pytest.mark.parametrize("P", [1, 127, 128, 129, 5000, 300 * 128 + 17])
-def test_tc_vf_query_matches_fp32_path(built_lib, P):
-    """bf16 tcgen05 chain vs the fp32 CUDA-core chain on the same points (tail tiles, multi-tile CTAs)."""
+def test_tc_vf_query_matches_oracle(built_lib, P):
+    """bf16 tcgen05 chain vs the oracle's VF MLP on the same points (tail tiles, multi-tile CTAs)."""
+    from vfnerf_b200.ops import vf_query
     case, z = U.load_golden("full_det")
-    model = U.make_model(case, _tame_state(), DEV)
+    st = _tame_state()
+    model = U.make_model(case, st, DEV, precision="bf16")
     g = torch.Generator().manual_seed(P)
-    pts = ((torch.rand(P, 3, generator=g) - 0.5) * 8).to(DEV)
+    pts = (torch.rand(P, 3, generator=g) - 0.5) * 8
     with torch.no_grad():
-        ref = model.vector_field_network(pts)
-        model.set_precision("bf16")
-        out = model.vector_field_network(pts)
-        v3 = __import__("vfnerf_b200.ops", fromlist=["vf_query"]).vf_query(model.vector_field_network, pts, n_cols=3)
+        ref = U.O.vf_network(st["vf_net"], pts)
+        out = model.vector_field_network(pts.to(DEV)).cpu()
+        v3 = vf_query(model.vector_field_network, pts.to(DEV), n_cols=3).cpu()
     err = (out - ref).abs()
-    print(f"P={P}: bf16 vs fp32  v max {err[:, :3].max().item():.2e} mean {err[:, :3].mean().item():.2e} | "
+    print(f"P={P}: bf16 vs oracle  v max {err[:, :3].max().item():.2e} mean {err[:, :3].mean().item():.2e} | "
           f"feat max {err[:, 3:].max().item():.2e} mean {err[:, 3:].mean().item():.2e}")
     assert out.shape == ref.shape and torch.isfinite(out).all()
     assert torch.equal(v3, out[:, :3])                    # V_ONLY and VF_FULL programs agree on the vector
     assert err.max().item() <= 5e-3                       # BASELINE.json north_star: 5e-3 abs on the bf16 path
 
 
-def test_tc_vf_query_on_the_bending_model(built_lib):
-    """On the centred (non-degenerate) synthetic model bf16 rounding is amplified by the output rescale;
-    this test documents the error instead of hiding it: mean stays small, the max is reported."""
+def test_tc_bf16_on_the_golden_model_is_outside_the_tolerance_and_says_so(built_lib):
+    """The golden (non-degenerate, centred, gain 2) model amplifies operand rounding ~60x: plain bf16 operands give
+    normals that differ from the REFERENCE by up to ~0.13 -- outside north_star's 5e-3.  Plain bf16 therefore does not
+    claim parity on this model (precision="bf16x3" does: tests/test_gpu_x3.py).  This test pins the size of the gap
+    against the reference goldens so that it cannot grow silently.  (The colour net stays plain bf16 in both modes and
+    is not the problem: with a split-precision VF chain in front of it the colours are within 2e-4, test_gpu_x3.py.)"""
     case, z = U.load_golden("full_det")
-    model = U.make_model(case, U.case_state(case, z), DEV)
-    g = torch.Generator().manual_seed(5)
-    pts = ((torch.rand(20000, 3, generator=g) - 0.5) * 8).to(DEV)
-    with torch.no_grad():
-        ref = model.vector_field_network(pts)
-        model.set_precision("bf16")
-        out = model.vector_field_network(pts)
-    err = (out - ref).abs()
-    print(f"bending model: v max {err[:, :3].max().item():.2e} mean {err[:, :3].mean().item():.2e} | "
-          f"feat max {err[:, 3:].max().item():.2e} mean {err[:, 3:].mean().item():.2e}")
-    assert err[:, :3].mean().item() <= 3e-2 and err[:, 3:].mean().item() <= 1e-2
-
-
-def test_tc_render_matches_fp32_path(built_lib):
-    """Fused VF+colour tcgen05 launch inside render() vs the fp32 path, second pass conditioned on the same z."""
-    case, z = U.load_golden("full_perturb")
-    model = U.make_model(case, _tame_state(), DEV)
-    R = 512
-    uv, pose, K = U.S.synthetic_rays(R, seed=0, start=0, stride=797)
-    draws = U.S.synthetic_draws(R, 64, 64, seed=99)
-    a = (pose.to(DEV), uv.to(DEV), K.to(DEV), 0)
-    with torch.no_grad():
-        ref = model.render(*a, draws=draws)
-        model.set_precision("bf16")
-        out = model.render(*a, draws=draws, z_vals_override=ref.z_vals)
-        free = model.render(*a, draws=draws)
-    N = 128
-    dn = (out.coarse_normals - ref.coarse_normals).abs()
-    dc = (out.coarse_colors - ref.coarse_colors).abs()
-    print(f"render bf16 vs fp32: normals max {dn.max().item():.2e} mean {dn.mean().item():.2e} | colors max "
-          f"{dc.max().item():.2e} mean {dc.mean().item():.2e} | rgb max "
-          f"{(out.coarse_rgb_values - ref.coarse_rgb_values).abs().max().item():.2e} | depth max "
-          f"{(out.coarse_depth_map - ref.coarse_depth_map).abs().max().item():.2e}")
-    same = (free.z_vals == ref.z_vals).all(dim=1).float().mean().item()
-    print(f"fine-sample placement identical to the fp32 path on {100 * same:.1f}% of rays")
-    assert torch.equal(out.points_coarse, ref.points_coarse)
-    assert dn.max().item() <= 5e-3 and dc.max().item() <= 5e-3
-    assert (out.coarse_rgb_values - ref.coarse_rgb_values).abs().max().item() <= 5e-3
-    assert (out.coarse_depth_map - ref.coarse_depth_map).abs().max().item() <= 5e-3
-    assert out.ray_dirs.shape == (R * N, 3) and torch.equal(out.ray_dirs, ref.ray_dirs)
-
-
-def test_tc_render_on_the_bending_model_reports_errors(built_lib):
-    case, z = U.load_golden("full_perturb")
     st = U.case_state(case, z)
-    model = U.make_model(case, st, DEV)
-    R = 512
+    model = U.make_model(case, st, DEV, precision="bf16")
+    uv, pose, K = (U.t(z, k).to(DEV) for k in ("uv", "pose", "K"))
+    draws = (U.t(z, "U1"), U.t(z, "U2"), U.t(z, "U3"))
+    with torch.no_grad():
+        out = model.render(pose, uv, K, 0, draws=draws, z_vals_override=U.t(z, "ref_z_vals"))
+    dn = (out.coarse_normals.cpu() - U.t(z, "ref_normals")).abs()
+    dc = (out.coarse_colors.cpu() - U.t(z, "ref_colors")).abs()
+    print(f"bf16 vs reference golden (bending model): normals max {dn.max().item():.2e} mean {dn.mean().item():.2e} | "
+          f"colours max {dc.max().item():.2e} mean {dc.mean().item():.2e}")
+    assert torch.equal(out.points_coarse.cpu(), U.t(z, "ref_points"))
+    assert dn.mean().item() <= 3e-2 and dn.max().item() <= 0.3          # the documented envelope of the fast mode
+    assert dc.mean().item() <= 1e-2
+
+
+def test_tc_render_per_point_outputs_match_oracle(built_lib):
+    """Fused VF + colour launch inside render() (plain bf16) vs the ORACLE's render on the bf16-friendly model, second
+    pass conditioned on the oracle's z: per-point normals and colours within 5e-3; sample positions bit-exact."""
+    case, z = U.load_golden("full_perturb")
+    st = _tame_state()
+    model = U.make_model(case, st, DEV, precision="bf16")
+    R = 256
     uv, pose, K = U.S.synthetic_rays(R, seed=0, start=0, stride=797)
     draws = U.S.synthetic_draws(R, 64, 64, seed=99)
-    a = (pose.to(DEV), uv.to(DEV), K.to(DEV), 0)
     with torch.no_grad():
-        ref = model.render(*a, draws=draws)
-        model.set_precision("bf16")
-        out = model.render(*a, draws=draws, z_vals_override=ref.z_vals)
-    dr = (out.coarse_rgb_values - ref.coarse_rgb_values).abs()
-    dd = (out.coarse_depth_map - ref.coarse_depth_map).abs()
-    dn = (out.coarse_normals - ref.coarse_normals).abs()
-    print(f"bending model render bf16 vs fp32: normals mean {dn.mean().item():.2e} max {dn.max().item():.2e} | rgb median "
-          f"{dr.median().item():.2e} max {dr.max().item():.2e} | depth median {dd.median().item():.2e} max {dd.max().item():.2e}")
-    assert torch.isfinite(out.coarse_rgb_values).all() and dr.median().item() <= 5e-2
+        ora = U.O.render(st["vf_net"], st["rendering_net"], st["density"], U.oracle_cfg(case), uv, pose, K,
+                         torch.linspace(0., 1., 64), *draws)
+        out = model.render(pose.to(DEV), uv.to(DEV), K.to(DEV), 0, draws=draws, z_vals_override=ora["z_vals"])
+    N = 128
+    dn = (out.coarse_normals.cpu() - ora["normals"]).abs()
+    dc = (out.coarse_colors.cpu() - ora["colors"]).abs()
+    print(f"render bf16 vs oracle: normals max {dn.max().item():.2e} | colours max {dc.max().item():.2e}")
+    assert torch.equal(out.points_coarse.cpu(), ora["points"])
+    assert dn.max().item() <= 5e-3 and dc.max().item() <= 5e-3
+    assert out.ray_dirs.shape == (R * N, 3) and (out.ray_dirs.cpu() - ora["rep_ray_dirs"]).abs().max().item() <= 1e-6
 
 
-def test_tc_grid_query_matches_fp32_grid_query(built_lib):
+def test_tc_grid_query_matches_oracle(built_lib):
     from vfnerf_b200.grid_query import grid_query
     case, z = U.load_golden("full_det")
-    model = U.make_model(case, _tame_state(), DEV)
+    st = _tame_state()
+    model = U.make_model(case, st, DEV, precision="bf16")
     res = 40
     tr, ce = torch.tensor([0.5, -0.5, 0.5]), torch.tensor([0.1, 0.0, -0.2])
-    ref = grid_query(model.vector_field_network, res, 1.0, tr, ce)
-    model.set_precision("bf16")
+    with torch.no_grad():
+        ref = U.O.vf_network(st["vf_net"], U.reference_grid_points(res, 1.0, tr, ce))[:, :3]
     out = grid_query(model.vector_field_network, res, 1.0, tr, ce, chunk=10000)
     slab = grid_query(model.vector_field_network, res, 1.0, tr, ce, i0=res * res * 7, n_points=res * res * 3)
-    assert (out - ref).abs().max().item() <= 5e-3
+    assert (out.cpu() - ref).abs().max().item() <= 5e-3
     assert torch.equal(slab, out[res * res * 7: res * res * 10])      # z-slab partition == slice of the whole grid
 
 
 @pytest.mark.parametrize("N,K", [(256, 256), (32, 256), (256, 64), (224, 96)])
-def test_umma_2cta_conventions(built_lib, N, K):
+def test_umma_2cta_conventions(debug_lib, N, K):
     """cta_group::2: A rows split across the CTA pair, B rows (output channels) split in halves, M = 256."""
     g = torch.Generator().manual_seed(N + K)
     A = torch.randn(256, K, generator=g).to(DEV)
     B = torch.randn(N, K, generator=g).to(DEV)
     D = torch.zeros(256, N, device=DEV)
-    _lib.check(built_lib.vfnerf_debug_umma2_gemm(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K,
+    _lib.check_debug(debug_lib.vfnerf_debug_umma2_gemm(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K,
                                                  torch.cuda.current_stream().cuda_stream), "debug_umma2_gemm")
     torch.cuda.synchronize()
     ref = A.bfloat16().float() @ B.bfloat16().float().T
@@ -147,7 +131,7 @@ def test_umma_2cta_conventions(built_lib, N, K):
 
 
 @pytest.mark.parametrize("N,K", [(256, 128), (48, 128), (256, 64), (96, 16)])
-def test_umma_mn_major_conventions(built_lib, N, K):
+def test_umma_mn_major_conventions(debug_lib, N, K):
     """Both operands MN-major (reduction index = row of the stashed [points, channels] tiles): the wgrad GEMM."""
     g = torch.Generator().manual_seed(3 * N + K)
     At = torch.randn(K, 128, generator=g).to(DEV)
@@ -156,7 +140,7 @@ def test_umma_mn_major_conventions(built_lib, N, K):
     errs = []
     for variant in (0, 1):
         D = torch.zeros(128, N, device=DEV)
-        _lib.check(built_lib.vfnerf_debug_umma_mn_gemm(At.data_ptr(), Bt.data_ptr(), D.data_ptr(), N, K, variant,
+        _lib.check_debug(debug_lib.vfnerf_debug_umma_mn_gemm(At.data_ptr(), Bt.data_ptr(), D.data_ptr(), N, K, variant,
                                                        torch.cuda.current_stream().cuda_stream), "debug_umma_mn_gemm")
         torch.cuda.synchronize()
         errs.append((D - ref).abs().max().item())
@@ -167,33 +151,33 @@ def test_umma_mn_major_conventions(built_lib, N, K):
 @pytest.mark.parametrize("R,n_coarse,n_fine", [(3, 40, 24), (77, 64, 36), (1, 64, 64)])
 def test_tc_render_ragged_sample_counts(built_lib, R, n_coarse, n_fine):
     """Sample counts for which R*N is not a multiple of the 128-point tile (partial last tile, odd tile counts, the
-    caller-mutable sampler attributes of SURVEY.md §8b): forward vs the fp32 path, and a bf16 backward that stays
-    within the gate-flip bound of the fp32 gradients."""
+    caller-mutable sampler attributes of SURVEY.md §8b): bf16 forward vs the ORACLE, and a bf16 backward that stays
+    within the gate-flip bound of the fp32 gradients (which test_gpu_backward.py pins to the reference's gradients)."""
     case, z = U.load_golden("full_perturb")
     case = dict(case, n_coarse=n_coarse, n_fine=n_fine, max_samples=100)
     st = _tame_state()
     uv, pose, K = U.S.synthetic_rays(R, seed=0, start=11, stride=797)
     draws = U.S.synthetic_draws(R, n_coarse, n_fine, seed=7)
     a = (pose.to(DEV), uv.to(DEV), K.to(DEV), 0)
+    with torch.no_grad():
+        ora = U.O.render(st["vf_net"], st["rendering_net"], st["density"], U.oracle_cfg(case), uv, pose, K,
+                         torch.linspace(0., 1., n_coarse), *draws)
     grads = {}
     outs = {}
-    zref = None
     for prec in ("fp32", "bf16"):
         model = U.make_model(case, st, DEV, precision=prec)
-        out = model.render(*a, draws=draws, z_vals_override=zref)
-        if zref is None:
-            zref = out.z_vals.detach()
+        out = model.render(*a, draws=draws, z_vals_override=ora["z_vals"])
         model.optimizer.zero_grad()
         (out.coarse_rgb_values.sum() + out.coarse_depth_map.sum() + (out.coarse_normals ** 2).sum() * 0.01).backward()
         outs[prec] = out
         grads[prec] = [p.grad.detach().clone() for p in model.rendering_network.parameters()] + \
                       [p.grad.detach().clone() for p in model.vector_field_network.parameters()]
     N = n_coarse + n_fine
-    assert outs["bf16"].coarse_normals.shape == (R, N, 3)
-    assert torch.equal(outs["bf16"].points_coarse, outs["fp32"].points_coarse)
-    assert (outs["bf16"].coarse_normals - outs["fp32"].coarse_normals).abs().max().item() <= 5e-3
-    assert (outs["bf16"].coarse_colors - outs["fp32"].coarse_colors).abs().max().item() <= 5e-3
-    assert (outs["bf16"].coarse_rgb_values - outs["fp32"].coarse_rgb_values).abs().max().item() <= 5e-3
+    o = outs["bf16"]
+    assert o.coarse_normals.shape == (R, N, 3)
+    assert torch.equal(o.points_coarse.cpu(), ora["points"])
+    assert (o.coarse_normals.detach().cpu() - ora["normals"]).abs().max().item() <= 5e-3
+    assert (o.coarse_colors.detach().cpu() - ora["colors"]).abs().max().item() <= 5e-3
     for ga, gb in zip(grads["fp32"], grads["bf16"]):
         assert torch.isfinite(gb).all()
         assert (ga - gb).norm() <= 0.2 * ga.norm() + 1e-7

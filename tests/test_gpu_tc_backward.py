@@ -230,7 +230,7 @@ def test_bf16_training_step_runs(built_lib):
 
 
 @pytest.mark.parametrize("n_rays", [32, 601, 602])
-def test_bf16_backward_stage_by_stage(built_lib, n_rays):
+def test_bf16_backward_stage_by_stage(built_lib, debug_lib, n_rays):
     """Tight check of every stage of the tensor-core backward on its OWN inputs: the activation stash is read back
     (vfnerf_debug_stash_read) and each step is recomputed in float64 from the tensors the kernels actually consumed --
     forward stash consistency, every dgrad step (transposed bf16 weights, ReLU / tanh gates), every weight-gradient

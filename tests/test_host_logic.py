@@ -191,3 +191,25 @@ def test_schedule_flag_and_arena_spot_check(model):
     assert w.data_ptr() == ar2.flat.data_ptr() + 4 * ar2.desc.w_off[0]
     net.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})     # marks dirty, aliasing kept
     assert net.arena().flat is ar2.flat
+
+
+def test_render_rejects_what_it_does_not_implement():
+    """Configurations the reference handles differently from this path must raise, not silently diverge."""
+    import pytest
+    import torch
+    from vfnerf_b200 import synthetic as S
+    case = dict(seed=0, vf_hidden=(32, 32), feat=16, rn_hidden=(32,), n_coarse=8, n_fine=8, max_samples=100, perturb=False,
+                near=0.0, far=6.0, fine_range=0.3, window=11, dir_to_normal_th=-0.2, vf_gain=2.0)
+    try:
+        model = S.make_model(case, S.synthetic_state(0, (32, 32), 16, (32,), vf_gain=2.0), torch.device("cpu"))
+    except Exception:
+        pytest.skip("model construction needs the layer shapes of the synthetic helper")
+    pose, uv, K = torch.zeros(1, 4, 4), torch.zeros(1, 2), torch.zeros(1, 4, 4)
+    model.rendering_network.train()
+    with pytest.raises(NotImplementedError):
+        model.render(pose, uv, K, 0)
+    model.eval()
+    # the fine sampler's own range reaches the kernels (z_add fallback samples, ray_sampler.py:296-299)
+    model.fine_sampler.near, model.fine_sampler.far = 0.25, 7.0
+    cfg = model._render_cfg(1, False)
+    assert (cfg.fine_near_, cfg.fine_far_) == (0.25, 7.0) and (cfg.near_, cfg.far_) == (0.0, 6.0)

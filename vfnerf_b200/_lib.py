@@ -15,8 +15,13 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libvfnerf_b200.so")
-SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "optim.cu", "mc_preprocess.cu", "host_rng.cu", "tc_debug.cu"]
+SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "optim.cu", "mc_preprocess.cu", "host_rng.cu"]
 HEADERS = ["common.cuh", "mlp_tc.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "vfnerf_b200.h")]
+# test-only library (UMMA probes, micro-benchmarks, stash read-back): the product sources + tc_debug.cu, compiled with
+# -DVFNERF_DEBUG_EXPORTS; built on demand by the tests (tests/conftest.py: debug_lib), never loaded by the product
+DEBUG_LIB_PATH = os.path.join(HERE, "libvfnerf_b200_debug.so")
+DEBUG_SOURCES = SOURCES + ["tc_debug.cu"]
+DEBUG_HEADERS = HEADERS + [os.path.join("..", "..", "include", "vfnerf_b200_debug.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -44,7 +49,8 @@ class RenderCfg(C.Structure):
                 ("near_", C.c_double), ("far_", C.c_double), ("fine_range", C.c_double),
                 ("dir_to_normal_th", C.c_float),
                 ("beta_lo", C.c_float), ("beta_hi", C.c_float), ("mean_lo", C.c_float),
-                ("mean_hi", C.c_float), ("scale_min", C.c_float), ("bn_eps", C.c_float)]
+                ("mean_hi", C.c_float), ("scale_min", C.c_float), ("bn_eps", C.c_float),
+                ("fine_near_", C.c_double), ("fine_far_", C.c_double)]
 
 
 class RenderOut(C.Structure):
@@ -85,6 +91,10 @@ PROTOTYPES = {
     "vfnerf_density_weights": (_I, [_CFG, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "vfnerf_volume_weights": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "vfnerf_composite": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
+}
+
+DEBUG_PROTOTYPES = {
+    "vfnerf_debug_last_error": (C.c_char_p, []),
     "vfnerf_debug_umma_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "vfnerf_debug_umma_mn_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "vfnerf_debug_umma2_gemm": (_I, [_P, _P, _P, _I, _I, _P]),
@@ -95,33 +105,69 @@ PROTOTYPES = {
 }
 
 _lib: Optional[C.CDLL] = None
+_dbg: Optional[C.CDLL] = None
 _lock = threading.Lock()
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+def _stale(path=None, sources=None, headers=None) -> bool:
+    path, sources, headers = path or LIB_PATH, sources or SOURCES, headers or HEADERS
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    t = os.path.getmtime(path)
+    deps = [os.path.join(CSRC, s) for s in sources] + [os.path.normpath(os.path.join(CSRC, h)) for h in headers]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(path: str, sources, defines, verbose: bool) -> str:
+    nvcc = os.environ.get("NVCC", "nvcc")
+    tmp = path + ".building.so"      # swapped in atomically: a concurrent snapshot/load never sees a partial file
+    extra = os.environ.get("NVCC_EXTRA", "").split()     # e.g. -DVFNERF_TC_PROFILE for the in-kernel cycle counters
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+          [os.path.join(CSRC, s) for s in sources]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(tmp, path)
+    if verbose:
+        print(res.stderr)
+    return path
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into vfnerf_b200/libvfnerf_b200.so (cross-compiles without a GPU)."""
     if not force and not _stale():
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "nvcc")
-    tmp = LIB_PATH + ".building.so"      # swapped in atomically: a concurrent snapshot/load never sees a partial file
-    extra = os.environ.get("NVCC_EXTRA", "").split()     # e.g. -DVFNERF_TC_PROFILE for the in-kernel cycle counters
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    os.replace(tmp, LIB_PATH)
-    if verbose:
-        print(res.stderr)
-    return LIB_PATH
+    return _compile(LIB_PATH, SOURCES, [], verbose)
+
+
+def build_debug(force: bool = False, verbose: bool = False) -> str:
+    """The test-only library (include/vfnerf_b200_debug.h) -> vfnerf_b200/libvfnerf_b200_debug.so."""
+    if not force and not _stale(DEBUG_LIB_PATH, DEBUG_SOURCES, DEBUG_HEADERS):
+        return DEBUG_LIB_PATH
+    return _compile(DEBUG_LIB_PATH, DEBUG_SOURCES, ["-DVFNERF_DEBUG_EXPORTS"], verbose)
+
+
+def debug_lib() -> C.CDLL:
+    """The loaded test-only library (tests and profiling scripts only)."""
+    global _dbg
+    if _dbg is None:
+        with _lock:
+            if _dbg is None:
+                if not os.path.exists(DEBUG_LIB_PATH):
+                    raise RuntimeError(f"{DEBUG_LIB_PATH} is missing: call vfnerf_b200._lib.build_debug() first (test-only library)")
+                L = C.CDLL(DEBUG_LIB_PATH)
+                for name, (res, args) in DEBUG_PROTOTYPES.items():
+                    fn = getattr(L, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _dbg = L
+    return _dbg
+
+
+def check_debug(status: int, what: str) -> None:
+    if status != 0:
+        msg = debug_lib().vfnerf_debug_last_error()
+        raise RuntimeError(f"{what} failed (status {status}): {msg.decode() if msg else '?'}")
 
 
 def lib() -> C.CDLL:

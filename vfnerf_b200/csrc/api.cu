@@ -10,6 +10,9 @@
 
 #include "common.cuh"
 #include "mlp_tc.cuh"
+#ifdef VFNERF_DEBUG_EXPORTS
+#include "../../include/vfnerf_b200_debug.h"
+#endif
 
 namespace vfn {
 
@@ -309,6 +312,7 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
   VFN_REQUIRE(cfg && vf && rn && out, "render_fwd: null argument");
   if (int e = check_precision(*cfg)) return e;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(s);
   RenderPlan p;
   if (int e = make_plan(*cfg, *vf, *rn, keep_for_backward, workspace, p, z_override != nullptr)) return e;
   VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "render_fwd: workspace %lld B < required %lld B",
@@ -352,7 +356,7 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
                                        nullptr, nullptr, w_c, s)) return e;
   }
   // ---- fine sampling: merged, sorted z values and points (vector_field_nerf.py:284-287)
-  if (int e = launch_fine_sample(p.R, p.Nc, p.Nf, cfg->near_, cfg->far_, cfg->fine_range, cfg->perturb, z_c, w_c,
+  if (int e = launch_fine_sample(p.R, p.Nc, p.Nf, cfg->fine_near_, cfg->fine_far_, cfg->fine_range, cfg->perturb, z_c, w_c,
                                  U2, U3, z_override, p.directions, p.cam_loc, out->z_vals, out->points,
                                  p.reuse_coarse ? p.src : nullptr, p.reuse_coarse ? p.pts_f : nullptr, s)) return e;
   // ---- merged pass
@@ -400,6 +404,7 @@ int vfnerf_render_bwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
               "render_bwd: null argument");
   if (int e = check_precision(*cfg)) return e;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(s);
   RenderPlan p;
   if (int e = make_plan(*cfg, *vf, *rn, 1, workspace, p)) return e;
   VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "render_bwd: workspace %lld B < required %lld B",
@@ -445,6 +450,10 @@ int vfnerf_render_bwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
   return 0;
 }
 
+#ifdef VFNERF_DEBUG_EXPORTS
+// test-only (include/vfnerf_b200_debug.h): compiled into libvfnerf_b200_debug.so, not into the product library
+const char* vfnerf_debug_last_error(void) { return g_err; }
+
 int vfnerf_debug_stash_read(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, const vfnerf_mlp_desc* rn,
                             void* workspace, int tensor, float* out, int* n_cols, void* stream) {
   VFN_REQUIRE(cfg && vf && rn && workspace, "stash_read: null argument");
@@ -452,6 +461,7 @@ int vfnerf_debug_stash_read(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc*
   RenderPlan p;
   if (int e = make_plan(*cfg, *vf, *rn, 1, workspace, p)) return e;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(s);
   if (!p.reuse_coarse || !out) return tc_debug_stash_read(p.tc, tensor, p.P, out, n_cols, s);
   // the stash is in evaluation order (coarse candidates, then fine ones): hand the rows back in merged sample order
   int cols = 0;
@@ -464,6 +474,7 @@ int vfnerf_debug_stash_read(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc*
   cudaFree(tmp);
   return e;
 }
+#endif  // VFNERF_DEBUG_EXPORTS
 
 // ---- VF-only query -----------------------------------------------------------------------------
 struct VfPlan {
@@ -526,6 +537,7 @@ int vfnerf_vf_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
   VFN_REQUIRE(n_out_cols >= 1 && n_out_cols <= vf->out_dim[vf->n_layers - 1], "vf_fwd: n_out_cols=%d invalid", n_out_cols);
   if (n_points == 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(s);
   if (precision != VFNERF_PREC_FP32) {
     if (int e = tc_precision(precision, "vf_fwd")) return e;
     VFN_REQUIRE(n_out_cols == 3 || n_out_cols == vf->out_dim[vf->n_layers - 1], "vf_fwd(bf16): n_out_cols must be 3 or all");
@@ -569,6 +581,7 @@ int vfnerf_mlp_points_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, cons
               "mlp_points_fwd: only the tensor-core paths (bf16, bf16x3) implement this entry");
   if (int e = validate_vf(*vf, multires, skip_layer)) return e;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(s);
   TcPlan plan;
   int64_t off = 0;
   if (int e = tc_carve(reinterpret_cast<char*>(workspace), off, multires, multires_view, skip_layer, *vf, rn, plan, 0, 0,
@@ -586,6 +599,7 @@ int vfnerf_vf_bwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
                   int64_t workspace_bytes, void* stream) {
   VFN_REQUIRE(vf && vf_arena && out && d_out && vf_grad_arena, "vf_bwd: null argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(s);
   if (precision != VFNERF_PREC_FP32) {
     // tensor-core path: the forward (keep_for_backward) left the activation stash and the transposed weight images
     VFN_REQUIRE(precision == VFNERF_PREC_BF16, "vf_bwd: precision bf16x3 is forward-only; train with bf16 or fp32");
@@ -622,6 +636,7 @@ int vfnerf_vf_grid_query(const vfnerf_mlp_desc* vf, const float* vf_arena, int m
   if (int e = validate_vf(*vf, multires, skip_layer)) return e;
   if (n_points == 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(s);
   GridSpec gs;
   for (int c = 0; c < 3; ++c) { gs.origin[c] = origin3_host[c]; gs.translation[c] = translation3_host[c]; gs.centroid[c] = centroid3_host[c]; }
   gs.voxel = voxel;
@@ -648,6 +663,7 @@ int vfnerf_vf_grid_query(const vfnerf_mlp_desc* vf, const float* vf_arena, int m
 int vfnerf_ray_geometry(int n_rays, int pose_is_quat, const float* uv, const float* pose,
                         const float* intrinsics, float* directions, float* ray_dirs, float* cam_loc,
                         void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_ray_geometry(n_rays, pose_is_quat, uv, pose, intrinsics, directions, ray_dirs, cam_loc,
                              reinterpret_cast<cudaStream_t>(stream));
 }
@@ -655,6 +671,7 @@ int vfnerf_ray_geometry(int n_rays, int pose_is_quat, const float* uv, const flo
 int vfnerf_coarse_sample(int n_rays, int n_coarse, double near_, double far_, int perturb,
                          const float* t_vals, const float* U1, const float* directions,
                          const float* cam_loc, float* z, float* points, void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_coarse_sample(n_rays, n_coarse, near_, far_, perturb, t_vals, U1, directions, cam_loc, z, points,
                               reinterpret_cast<cudaStream_t>(stream));
 }
@@ -663,6 +680,7 @@ int vfnerf_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, doubl
                        int perturb, const float* z_coarse, const float* w_coarse, const float* U2,
                        const float* U3, const float* directions, const float* cam_loc, float* z,
                        float* points, void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_fine_sample(n_rays, n_coarse, n_fine, near_, far_, fine_range, perturb, z_coarse, w_coarse, U2, U3,
                             nullptr, directions, cam_loc, z, points, nullptr, nullptr,
                             reinterpret_cast<cudaStream_t>(stream));
@@ -670,21 +688,25 @@ int vfnerf_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, doubl
 
 int vfnerf_mc_count(const float* pred, int resolution, uint8_t* keep, int32_t* cta_counts, float* div_raw,
                     uint8_t* choice, const uint8_t* surface, void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_mc_count(pred, resolution, keep, cta_counts, div_raw, choice, surface, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vfnerf_mc_emit(const float* pred, int resolution, const uint8_t* keep, const int64_t* cta_offsets, int32_t* cells,
                    float* comb, float* udf, void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_mc_emit(pred, resolution, keep, cta_offsets, cells, comb, udf, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vfnerf_smooth_vf(const float* in, float* tmp, float* out, int resolution, int kernel_size, const float* taps_host,
                      void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_smooth_vf(in, tmp, out, resolution, kernel_size, taps_host, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vfnerf_sample_pdf(int n_rays, int n_bins, int n_samples, const float* bins, const float* weights, const float* u,
                       int u_per_ray, float* samples, void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_sample_pdf(n_rays, n_bins, n_samples, bins, weights, u, u_per_ray, samples,
                            reinterpret_cast<cudaStream_t>(stream));
 }
@@ -692,6 +714,7 @@ int vfnerf_sample_pdf(int n_rays, int n_bins, int n_samples, const float* bins, 
 int vfnerf_pdf_fine_sample(int n_rays, int n_coarse, int n_fine, const float* z_coarse, const float* w_coarse,
                            const float* u, int u_per_ray, const float* directions, const float* cam_loc, float* z,
                            float* points, void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_pdf_fine_sample(n_rays, n_coarse, n_fine, z_coarse, w_coarse, u, u_per_ray, directions, cam_loc, z,
                                 points, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -699,6 +722,7 @@ int vfnerf_pdf_fine_sample(int n_rays, int n_coarse, int n_fine, const float* z_
 int vfnerf_density_weights(const vfnerf_render_cfg* cfg, int n_samples, const float* density_params,
                            const float* normals, int64_t normals_ld, const float* ray_dirs, const float* z,
                            float* cosw, float* sigma, float* weights, void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   VFN_REQUIRE(cfg, "density_weights: null cfg");
   return launch_density_weights(*cfg, cfg->n_rays, n_samples, density_params, normals, normals_ld, ray_dirs, z,
                                 cosw, sigma, weights, reinterpret_cast<cudaStream_t>(stream));
@@ -706,11 +730,13 @@ int vfnerf_density_weights(const vfnerf_render_cfg* cfg, int n_samples, const fl
 
 int vfnerf_volume_weights(int n_rays, int n_samples, int mode, int normalize, const float* sigma, const float* z,
                           float* weights, void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_volume_weights(n_rays, n_samples, mode, normalize, sigma, z, weights, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vfnerf_composite(int n_rays, int n_samples, const float* weights, const float* colors, const float* z,
                      float* rgb, float* depth, void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_composite(n_rays, n_samples, weights, colors, z, rgb, depth, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -36,6 +36,23 @@ extern long long g_launches;
     VFN_CHECK_CUDA(cudaGetLastError());  \
   } while (0)
 
+// Every C-ABI entry point runs on the device that owns its stream: kernels launch on the calling thread's CURRENT device,
+// which in a multi-GPU process need not be the device of the caller's pointers and stream (the reference accepts any
+// config.cuda_config.device).  NULL / legacy / per-thread streams belong to the current device by definition.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(cudaStream_t s) {
+    if (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) return;
+    int cur = 0, dev = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) return;
+    if (cudaStreamGetDevice(s, &dev) != cudaSuccess) { cudaGetLastError(); return; }
+    if (dev != cur && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxDevices = 64;     // per-device caches (SM count, shared-memory opt-in) are indexed by device ordinal

@@ -127,6 +127,7 @@ extern "C" int vfnerf_vf_loss_fwd(int64_t n_rays, int64_t n_points, int64_t n_su
   VFN_REQUIRE(!depth_gt || depth, "vf_loss_fwd: depth_gt without depth");
   VFN_REQUIRE(n_sup == 0 || (sup && sup_gt), "vf_loss_fwd: supervision pointers missing");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(s);
   const LossArgs a = make_args(n_rays, n_points, n_sup, n_dd, rgb, rgb_gt, depth, depth_gt, normals, sup, sup_gt, dd, weights,
                                depth_clamp, norm_lt1_active);
   float* sums = terms + 8;                      // terms is [16]: [0..6] results, [8..13] raw sums
@@ -145,6 +146,7 @@ extern "C" int vfnerf_vf_loss_bwd(int64_t n_rays, int64_t n_points, int64_t n_su
                                   void* stream) {
   VFN_REQUIRE(rgb && rgb_gt && normals && weights && grad_loss, "vf_loss_bwd: null argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(s);
   const LossArgs a = make_args(n_rays, n_points, n_sup, 0, rgb, rgb_gt, depth, depth_gt, normals, sup, sup_gt, nullptr, weights,
                                depth_clamp, norm_lt1_active);
   vf_loss_grad_kernel<<<grid_for(std::max<long long>(n_points, 3 * n_sup)), 256, 0, s>>>(a, grad_loss, d_rgb, d_depth, d_normals, d_sup);

@@ -52,6 +52,7 @@ using namespace vfn;
 extern "C" int vfnerf_sqnorm_accumulate(const float* g, int64_t n, float* out_sq, void* stream) {
   VFN_REQUIRE(g && out_sq, "sqnorm: null argument");
   if (n <= 0) return 0;
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 4);
   sqnorm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, n, out_sq);
   VFN_LAUNCH_CHECK();
@@ -64,6 +65,7 @@ extern "C" int vfnerf_adam_step(float* p, float* g, float* m, float* v, const ui
   VFN_REQUIRE(p && g && m && v && lr && step, "adam_step: null argument");
   VFN_REQUIRE(max_norm <= 0.f || total_sqnorm, "adam_step: clipping needs the squared gradient norm");
   if (n <= 0) return 0;
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
   adam_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, mask, n, lr, step, beta1, beta2, eps,
                                                                        weight_decay, max_norm, total_sqnorm);

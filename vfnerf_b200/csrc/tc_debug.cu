@@ -2,8 +2,11 @@
 // D[128 x N] = bf16(A[128 x K]) * bf16(B[N x K])^T with tcgen05.mma (fp32 accumulate in TMEM).
 // tests/test_gpu_tc.py compares it with a bf16-rounded fp32 matmul; `variant` 1 swaps LBO/SBO so a
 // descriptor-convention mistake shows up as "variant 1 right, variant 0 wrong" instead of plain garbage.
+// TEST-ONLY translation unit: part of libvfnerf_b200_debug.so (vfnerf_b200/_lib.py: build_debug), never of the product
+// library.  Declarations: include/vfnerf_b200_debug.h.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "../../include/vfnerf_b200_debug.h"
 
 namespace vfn {
 using namespace tc;

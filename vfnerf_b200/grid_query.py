@@ -92,6 +92,9 @@ def grid_query(decoder, resolution: int, scale: float = 1.0, translation: Option
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     pts = torch.empty(n_points, 3, dtype=torch.float32, device=dev) if return_points else None
     stream = torch.cuda.current_stream(dev).cuda_stream
+    from .ops import _on_device
+    guard = _on_device(dev)
+    guard.__enter__()
     head = 0
     while head < n_points:
         n = min(chunk, n_points - head)
@@ -104,4 +107,5 @@ def grid_query(decoder, resolution: int, scale: float = 1.0, translation: Option
             off = ((n * E * 4 + 255) // 256) * 256
             pts[head:head + n] = ws[off:off + n * 12].view(torch.float32).view(n, 3)
         head += n
+    guard.__exit__()
     return (out, pts) if return_points else out

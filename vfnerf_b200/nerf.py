@@ -86,6 +86,11 @@ class VectorFieldNerf:
     def _new_schedule(self, num_steps: int) -> None:
         sc = self.config.scheduler_config
         self.scheduler = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, sc.lr_decay_factor ** (1. / num_steps))
+        # a plain torch optimizer takes over: leave flat-gradient mode (optim.ArenaAdam), or backward() would keep
+        # accumulating into arenas nobody reads while p.grad stays None
+        self.vector_field_network.arena().disable_flat_grad()
+        self.rendering_network.arena().disable_flat_grad()
+        self.density.disable_flat_grad()
         self.optimizer = torch.optim.Adam(self.parameters(), lr=sc.lr)
 
     def new_scheduler(self, num_steps: int) -> None:
@@ -186,6 +191,7 @@ class VectorFieldNerf:
         near, far = self.ray_sampler.near, self.ray_sampler.far
         if not isinstance(far, (int, float)) or not isinstance(near, (int, float)):
             near, far = float(near), float(far)
+
         cfg = _lib.RenderCfg()
         cfg.n_rays, cfg.n_coarse, cfg.n_fine = n_rays, self.ray_sampler.N_samples, self.fine_sampler.n_fine()
         cfg.perturb = 0 if self.ray_sampler.deterministic else 1
@@ -198,6 +204,8 @@ class VectorFieldNerf:
         cfg.precision = _lib.PRECISIONS[self.precision]
         cfg.flags = _lib.FLAG_RECOMPUTE_COARSE if self.recompute_coarse else 0
         cfg.near_, cfg.far_, cfg.fine_range = float(near), float(far), float(self.fine_sampler.range)
+        # the fine sampler draws its fallback samples in ITS OWN [near, far] (ray_sampler.py:296-299)
+        cfg.fine_near_, cfg.fine_far_ = float(self.fine_sampler.near), float(self.fine_sampler.far)
         cfg.dir_to_normal_th = float(c.dir_to_normal_th)
         cfg.beta_lo, cfg.beta_hi = float(d.beta_bounds[0]), float(d.beta_bounds[1])
         cfg.mean_lo, cfg.mean_hi = float(d.mean_bounds[0]), float(d.mean_bounds[1])
@@ -219,9 +227,16 @@ class VectorFieldNerf:
         if white:
             # vector_field_nerf.py:274-277 reads rgb_values_coarse before assignment
             raise UnboundLocalError("white=True is broken in the reference (SURVEY.md fact 2) and unsupported")
-        if self.vector_field_network.training:
-            raise NotImplementedError("render() with the VF net in train() mode (batch-stat BatchNorm + Jacobian) is "
-                                      "SURVEY.md §8(f) rank 1; call model.eval() as the reference trainer does")
+        if self.vector_field_network.training or self.rendering_network.training:
+            # also reached with config.numerical_jacobian: train() then leaves the VF net in eval but still switches the
+            # colour net to batch statistics and asks for numerical directional derivatives (vector_field_nerf.py:84-101)
+            raise NotImplementedError("render() with a network in train() mode (batch-statistic BatchNorm, Jacobian / "
+                                      "directional derivatives) is SURVEY.md §8(f) rank 1; call model.eval() as the "
+                                      "reference trainer does (train/vector_field_nerf_train.py:140-141)")
+        if not getattr(self.config.rendering_net_config, "detach_normals", True):
+            raise NotImplementedError("rendering_net_config.detach_normals=False: the backward kernels implement the shipped "
+                                      "detach (rendering_network.py:76-77); gradients through the colour net's normal "
+                                      "input are not built")
         pixels = ops._require_cuda("pixels", pixels)
         pose = ops._require_cuda("pose", pose)
         intrinsics = ops._require_cuda("intrinsics", intrinsics)

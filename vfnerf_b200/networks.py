@@ -87,6 +87,14 @@ class ParamArena:
                 t.grad = self.grad_flat[off:off + t.numel()].view(t.shape)
         return self.grad_flat
 
+    def disable_flat_grad(self) -> None:
+        """Back to per-parameter gradients (a torch optimizer took over: its zero_grad(set_to_none=True) would drop the
+        views and the flat accumulation of ops.render_call would then feed nobody)."""
+        self.grad_flat = None
+        for _, t, _ in self.slots:
+            if isinstance(t, nn.Parameter):
+                t.grad = None
+
     def trainable_mask(self) -> torch.Tensor:
         """uint8 [arena_floats]: 1 on Parameter elements, 0 on BatchNorm running statistics."""
         m = torch.zeros(self.flat.numel(), dtype=torch.uint8, device=self.flat.device)
@@ -296,6 +304,11 @@ class LaplaceDensity(nn.Module):
         for i, p in enumerate((self.beta, self.scale, self.mean)):
             p.grad = self.grad_flat[i]
         return self.grad_flat
+
+    def disable_flat_grad(self) -> None:
+        self.grad_flat = None
+        for p in (self.beta, self.scale, self.mean):
+            p.grad = None
 
     def get_beta(self) -> torch.Tensor:
         return torch.clamp(self.beta, float(self.beta_bounds[0]), float(self.beta_bounds[1]))

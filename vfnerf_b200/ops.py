@@ -29,6 +29,30 @@ def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _on_device:
+    """Makes `device` the current CUDA device around a library call.  The C ABI launches on the calling thread's current
+    device (kernel attributes and the SM count are cached per device ordinal on the C side), while the stream and every
+    pointer belong to the tensors' device: a model on cuda:1 in a process whose current device is 0 must switch.  Free
+    when the device is already current (the one-process-per-GPU layout)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device: torch.device) -> None:
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -51,9 +75,10 @@ class _VFQuery(torch.autograd.Function):
             _lib.check(1, "vfnerf_vf_workspace_bytes")
         ws = _workspace(nbytes, dev)
         out = torch.empty(P, n_cols, dtype=torch.float32, device=dev)
-        _lib.check(L.vfnerf_vf_fwd(C.byref(ar.desc), ar.flat.data_ptr(), net.multires, net.skip_layer, 1e-5,
-                                   prec, points.data_ptr(), P, out.data_ptr(), n_cols, n_cols,
-                                   ws.data_ptr(), ws.numel(), int(need_bwd), _stream_ptr(dev)), "vfnerf_vf_fwd")
+        with _on_device(dev):
+            _lib.check(L.vfnerf_vf_fwd(C.byref(ar.desc), ar.flat.data_ptr(), net.multires, net.skip_layer, 1e-5,
+                                       prec, points.data_ptr(), P, out.data_ptr(), n_cols, n_cols,
+                                       ws.data_ptr(), ws.numel(), int(need_bwd), _stream_ptr(dev)), "vfnerf_vf_fwd")
         ctx.net, ctx.ws, ctx.P, ctx.n_cols, ctx.prec = net, ws, P, n_cols, prec
         ctx.save_for_backward(out)
         return out
@@ -67,10 +92,11 @@ class _VFQuery(torch.autograd.Function):
         dev = out.device
         d_out = d_out.contiguous().float()
         grad = torch.empty(ar.desc.arena_floats, dtype=torch.float32, device=dev)
-        _lib.check(L.vfnerf_vf_bwd(C.byref(ar.desc), ar.flat.data_ptr(), net.multires, net.skip_layer, 1e-5,
-                                   ctx.prec, ctx.P, out.data_ptr(), ctx.n_cols, d_out.data_ptr(), ctx.n_cols,
-                                   ctx.n_cols, grad.data_ptr(), 0, ctx.ws.data_ptr(), ctx.ws.numel(),
-                                   _stream_ptr(dev)), "vfnerf_vf_bwd")
+        with _on_device(dev):
+            _lib.check(L.vfnerf_vf_bwd(C.byref(ar.desc), ar.flat.data_ptr(), net.multires, net.skip_layer, 1e-5,
+                                       ctx.prec, ctx.P, out.data_ptr(), ctx.n_cols, d_out.data_ptr(), ctx.n_cols,
+                                       ctx.n_cols, grad.data_ptr(), 0, ctx.ws.data_ptr(), ctx.ws.numel(),
+                                       _stream_ptr(dev)), "vfnerf_vf_bwd")
         ctx.ws = None
         if ar.grad_flat is not None:               # flat-gradient mode (optim.ArenaAdam): one accumulate per network
             ar.grad_flat.add_(grad)
@@ -111,12 +137,13 @@ def mlp_points(vf_net, rn_net, points: torch.Tensor, ray_dirs: torch.Tensor, sam
         workspace = _workspace(nb, dev)
     normals = torch.empty(P, 3, dtype=torch.float32, device=dev)
     colors = torch.empty(P, 3, dtype=torch.float32, device=dev)
-    _lib.check(L.vfnerf_mlp_points_fwd(C.byref(va.desc), va.flat.data_ptr(), C.byref(ra.desc), ra.flat.data_ptr(),
-                                       vf_net.multires, rn_net.multires_view, vf_net.skip_layer, 1e-5,
-                                       _lib.PREC_BF16X3 if vf_net.precision == "bf16x3" else _lib.PREC_BF16,
-                                       points.data_ptr(), ray_dirs.data_ptr(), int(samples_per_ray), P, normals.data_ptr(),
-                                       colors.data_ptr(), workspace.data_ptr(), workspace.numel(), int(repack),
-                                       _stream_ptr(dev)), "vfnerf_mlp_points_fwd")
+    with _on_device(dev):
+        _lib.check(L.vfnerf_mlp_points_fwd(C.byref(va.desc), va.flat.data_ptr(), C.byref(ra.desc), ra.flat.data_ptr(),
+                                           vf_net.multires, rn_net.multires_view, vf_net.skip_layer, 1e-5,
+                                           _lib.PREC_BF16X3 if vf_net.precision == "bf16x3" else _lib.PREC_BF16,
+                                           points.data_ptr(), ray_dirs.data_ptr(), int(samples_per_ray), P, normals.data_ptr(),
+                                           colors.data_ptr(), workspace.data_ptr(), workspace.numel(), int(repack),
+                                           _stream_ptr(dev)), "vfnerf_mlp_points_fwd")
     return normals, colors, workspace
 
 
@@ -130,18 +157,19 @@ _debug_last: dict = {}
 
 
 def debug_stash_read(tensor: int) -> torch.Tensor:
+    """Test support: reads one activation-stash tensor back through the TEST-ONLY library (_lib.build_debug())."""
     d = _debug_last
     if not d:
         raise RuntimeError("no workspace kept: set ops.DEBUG_KEEP_WORKSPACE = True before backward()")
-    L = _lib.lib()
+    L = _lib.debug_lib()
     cfg = d["cfg"]
     n_cols = C.c_int(0)
     args = (C.byref(cfg), C.byref(d["vf"].desc), C.byref(d["rn"].desc), d["ws"].data_ptr(), int(tensor))
-    _lib.check(L.vfnerf_debug_stash_read(*args, None, C.byref(n_cols), None), "vfnerf_debug_stash_read")
+    _lib.check_debug(L.vfnerf_debug_stash_read(*args, None, C.byref(n_cols), None), "vfnerf_debug_stash_read")
     P = cfg.n_rays * (cfg.n_coarse + cfg.n_fine)
     out = torch.empty(P, n_cols.value, dtype=torch.float32, device=d["ws"].device)
-    _lib.check(L.vfnerf_debug_stash_read(*args, out.data_ptr(), C.byref(n_cols), _stream_ptr(out.device)),
-               "vfnerf_debug_stash_read")
+    _lib.check_debug(L.vfnerf_debug_stash_read(*args, out.data_ptr(), C.byref(n_cols), _stream_ptr(out.device)),
+                     "vfnerf_debug_stash_read")
     return out
 
 
@@ -191,12 +219,13 @@ class _Render(torch.autograd.Function):
         out = _lib.RenderOut(points.data_ptr(), normals.data_ptr(), rgb.data_ptr(), depth.data_ptr(),
                              z_vals.data_ptr(), _lib.ptr(ray_dirs), colors.data_ptr(), weights.data_ptr(),
                              _lib.ptr(z_c), _lib.ptr(w_c))
-        _lib.check(L.vfnerf_render_fwd(
-            C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),
-            dflat.data_ptr(), call.uv.data_ptr(), call.pose.data_ptr(), call.intrinsics.data_ptr(),
-            call.t_vals.data_ptr(), _lib.ptr(call.U1), _lib.ptr(call.U2), _lib.ptr(call.U3),
-            _lib.ptr(call.z_override), C.byref(out), ws.data_ptr(), ws.numel(), int(need_bwd), _stream_ptr(dev)),
-            "vfnerf_render_fwd")
+        with _on_device(dev):
+            _lib.check(L.vfnerf_render_fwd(
+                C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),
+                dflat.data_ptr(), call.uv.data_ptr(), call.pose.data_ptr(), call.intrinsics.data_ptr(),
+                call.t_vals.data_ptr(), _lib.ptr(call.U1), _lib.ptr(call.U2), _lib.ptr(call.U3),
+                _lib.ptr(call.z_override), C.byref(out), ws.data_ptr(), ws.numel(), int(need_bwd), _stream_ptr(dev)),
+                "vfnerf_render_fwd")
         call.extras = dict(weights=weights, z_coarse=z_c, weights_coarse=w_c)
         if need_bwd:
             ctx.call, ctx.ws, ctx.out_struct = call, ws, out
@@ -227,11 +256,12 @@ class _Render(torch.autograd.Function):
         g_vf = torch.empty(vf_ar.desc.arena_floats, **f32)
         g_rn = torch.empty(rn_ar.desc.arena_floats, **f32)
         g_d = torch.empty(3, **f32)
-        _lib.check(L.vfnerf_render_bwd(
-            C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),
-            dflat.data_ptr(), C.byref(ctx.out_struct), d_rgb.data_ptr(), d_depth.data_ptr(), _lib.ptr(d_normals),
-            _lib.ptr(d_colors), g_vf.data_ptr(), g_rn.data_ptr(), g_d.data_ptr(), ctx.ws.data_ptr(),
-            ctx.ws.numel(), _stream_ptr(dev)), "vfnerf_render_bwd")
+        with _on_device(dev):
+            _lib.check(L.vfnerf_render_bwd(
+                C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),
+                dflat.data_ptr(), C.byref(ctx.out_struct), d_rgb.data_ptr(), d_depth.data_ptr(), _lib.ptr(d_normals),
+                _lib.ptr(d_colors), g_vf.data_ptr(), g_rn.data_ptr(), g_d.data_ptr(), ctx.ws.data_ptr(),
+                ctx.ws.numel(), _stream_ptr(dev)), "vfnerf_render_bwd")
         if DEBUG_KEEP_WORKSPACE:
             _debug_last.update(cfg=cfg, ws=ctx.ws, vf=vf_ar, rn=rn_ar)
         ctx.ws = ctx.keep = None

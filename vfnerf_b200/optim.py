@@ -46,6 +46,100 @@ class ArenaAdam(torch.optim.Optimizer):
         for g in self._grads:
             g.zero_()
 
+    def _check_storage(self) -> None:
+        """The arenas are re-flattened when someone moves the modules (.to(), load_state_dict(assign=True)); moments held
+        for the old storage would silently update orphaned memory."""
+        cur = [self._arenas[0].sync(), self._arenas[1].sync(), self._density.flat()]
+        gcur = [self._arenas[0].grad_flat, self._arenas[1].grad_flat, getattr(self._density, "grad_flat", None)]
+        for a, b in zip(cur, self._flats):
+            if a.data_ptr() != b.data_ptr():
+                raise RuntimeError("ArenaAdam: parameter storage moved after the optimizer was built (.to() / "
+                                   "load_state_dict(assign=True)); call vfnerf_b200.optim.use_arena_optimizer(model) again")
+        for a, b in zip(gcur, self._grads):
+            if a is None or a.data_ptr() != b.data_ptr():
+                raise RuntimeError("ArenaAdam: flat-gradient mode was switched off (another optimizer was installed with "
+                                   "model.new_scheduler()/reset_scheduler()?); call use_arena_optimizer(model) again")
+
+    # ---- checkpoint format: the reference's ---------------------------------------------------------------------------
+    # VectorFieldNerf.save() stores optimizer.state_dict() and load() restores it (vector_field_nerf.py:178-214).  The
+    # reference's optimizer is torch.optim.Adam over model.parameters() -- one group, the VF tensors listed twice
+    # (:132-137) -- so that is the format emitted and accepted here: per-parameter exp_avg / exp_avg_sq / step, packed
+    # out of / into the flat moment arenas.  A checkpoint written by the reference trainer resumes here and vice versa.
+    def _param_slots(self):
+        """id(Parameter) -> (arena index, offset, numel) for every trainable tensor."""
+        where = {}
+        for k, ar in enumerate(self._arenas):
+            for _, t, off in ar.slots:
+                if isinstance(t, torch.nn.Parameter):
+                    where[id(t)] = (k, off, t.numel())
+        for i, p in enumerate((self._density.beta, self._density.scale, self._density.mean)):
+            where[id(p)] = (2, i, 1)
+        return where
+
+    def state_dict(self):
+        where = self._param_slots()
+        params = self.model.parameters()          # the reference's list, duplicates included
+        index = {}
+        for i, p in enumerate(params):
+            index.setdefault(id(p), i)
+        g0 = self.param_groups[0]
+        lr = g0["lr"]
+        state = {}
+        stepped = bool(self._step.item() > 0)
+        if stepped:
+            for p in params:
+                i = index[id(p)]
+                if i in state:
+                    continue
+                k, off, n = where[id(p)]
+                state[i] = {"step": self._step.detach().clone().reshape(()),
+                            "exp_avg": self._m[k][off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": self._v[k][off:off + n].view(p.shape).clone()}
+        group = {"lr": float(lr.item()) if isinstance(lr, torch.Tensor) else float(lr), "betas": tuple(g0["betas"]),
+                 "eps": g0["eps"], "weight_decay": g0["weight_decay"], "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": [index[id(p)] for p in params]}
+        if "initial_lr" in g0:
+            group["initial_lr"] = g0["initial_lr"]
+        return {"state": state, "param_groups": [group]}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd) -> None:
+        groups = sd["param_groups"]
+        if len(groups) != 1:
+            raise ValueError("ArenaAdam.load_state_dict: expected the reference's single parameter group")
+        params = self.model.parameters()
+        ids = groups[0]["params"]
+        if len(ids) != len(params):
+            raise ValueError(f"ArenaAdam.load_state_dict: checkpoint lists {len(ids)} parameters, the model has {len(params)}")
+        where = self._param_slots()
+        for m, v in zip(self._m, self._v):
+            m.zero_(); v.zero_()
+        steps = []
+        done = set()
+        for i, p in zip(ids, params):
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is None or id(p) in done:
+                continue
+            done.add(id(p))
+            k, off, n = where[id(p)]
+            self._m[k][off:off + n].copy_(st["exp_avg"].reshape(-1).to(self._m[k].device, torch.float32))
+            self._v[k][off:off + n].copy_(st["exp_avg_sq"].reshape(-1).to(self._v[k].device, torch.float32))
+            steps.append(float(st["step"]))
+        # the reference's Adam steps its duplicated VF entries twice per iteration: the iteration count is the smallest
+        # per-parameter counter (colour net / density), which is what the single counter here means
+        self._step.fill_(min([x for x in steps if x > 0], default=0.0))
+        g0 = self.param_groups[0]
+        lr = groups[0]["lr"]
+        lr = float(lr.item()) if isinstance(lr, torch.Tensor) else float(lr)
+        if isinstance(g0["lr"], torch.Tensor):
+            g0["lr"].fill_(lr)
+        else:
+            g0["lr"] = torch.tensor(lr, device=self._step.device)
+        for key in ("betas", "eps", "weight_decay", "initial_lr"):
+            if key in groups[0]:
+                g0[key] = tuple(groups[0][key]) if key == "betas" else groups[0][key]
+
     def grad_norm(self) -> torch.Tensor:
         """Global 2-norm of the gradient as clip_grad_norm_ returns it (after step(): of the unclipped gradient)."""
         return self._sq.sqrt()
@@ -53,6 +147,7 @@ class ArenaAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None, max_norm: Optional[float] = None):
         L = _lib.lib()
+        self._check_storage()
         g0 = self.param_groups[0]
         lr = g0["lr"]
         if not isinstance(lr, torch.Tensor):                 # a scheduler replaced the tensor by a float
