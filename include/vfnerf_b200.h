@@ -28,6 +28,14 @@ extern "C" {
  * recomputing because the merged coarse points carry the same bits and the fused chain is a pure per-point function.
  * This flag restores the literal two-evaluation schedule (parity tests compare the two). */
 #define VFNERF_FLAG_RECOMPUTE_COARSE 1
+/* Two paths the reference's render() has but cannot execute, offered behind explicit
+ * opt-in flags with their evident intent:
+ *   WHITE_BG: white background, rgb += 1 - sum_j w_j after the final composite (vector_field_nerf.py:325-329; upstream
+ *             the same statement in the coarse block, :273-277, reads rgb before it is assigned and raises);
+ *   NERF_WEIGHTS: rendering="nerf", w_j = a_j * prod_{i<=j}(1 - a_i + 1e-10) (utils/rendering.py:98-119, inclusive
+ *             cumprod) with the arguments in the function's own order (upstream passes (z_vals, density) swapped). */
+#define VFNERF_FLAG_WHITE_BG 2
+#define VFNERF_FLAG_NERF_WEIGHTS 4
 #define VFNERF_MAX_SAMPLES 256 /* samples per ray (coarse + fine) handled by one warp */
 
 /* precision of the two MLPs */
@@ -289,6 +297,9 @@ int vfnerf_volume_weights(int n_rays, int n_samples, int mode, int normalize, co
 /* a9: rgb = sum_j w_j c_j, depth = sum_j w_j z_j, vector_field_nerf.py:322-323 */
 int vfnerf_composite(int n_rays, int n_samples, const float* weights, const float* colors,
                      const float* z, float* rgb, float* depth, void* stream);
+/* same with the white-background term: rgb += 1 - sum_j w_j (vector_field_nerf.py:325-329) */
+int vfnerf_composite_white(int n_rays, int n_samples, const float* weights, const float* colors,
+                           const float* z, float* rgb, float* depth, void* stream);
 
 /* Test-only entry points (UMMA descriptor probes, micro-benchmarks, activation-stash read-back) are NOT part of this
  * library: they are declared in vfnerf_b200_debug.h and built into a separate libvfnerf_b200_debug.so by the tests. */

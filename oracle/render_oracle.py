@@ -332,7 +332,10 @@ def render(vf_sd, rn_sd, density_params, cfg: dict, uv, pose, intrinsics, t_vals
 
     cfg keys: n_coarse, n_fine (= min(N_samples, max_samples)), near, far, fine_range, perturb,
     window, dir_to_normal_th, normalize, beta_bounds, scale_min, mean_bounds, multires,
-    multires_view, skip_in.
+    multires_view, skip_in.  Optional: rendering ("volsdf" | "nerf": nerf_volume_rendering with its
+    arguments in the function's own order -- upstream's call swaps them), white (True:
+    rgb += 1 - sum of weights after the final composite, vector_field_nerf.py:325-329 -- upstream the same
+    statement in the coarse block raises first), fine_near / fine_far (the fine sampler's own range).
     density_params: dict(beta, scale, mean) of 0-d tensors.
     z_vals_override: if given, the second pass uses these merged z values instead of the ones
     derived from the coarse pass (the parity protocol of SURVEY.md §8c: the argmax that places
@@ -352,10 +355,13 @@ def render(vf_sd, rn_sd, density_params, cfg: dict, uv, pose, intrinsics, t_vals
         vf_c = vf_network(vf_sd, pts_c.reshape(-1, 3), cfg["multires"], cfg["skip_in"])
         n_c = vf_c[:, :3].reshape(R, -1, 3)
         sigma_c, _ = get_density(n_c, ray_dirs, beta, scale, mean, cfg["window"], cfg["dir_to_normal_th"])
-        w_c = volsdf_weights(z_c, sigma_c, cfg["normalize"])
+        nerf_mode = cfg.get("rendering", "volsdf") == "nerf"
+        weights_fn = (lambda zz, ss: nerf_weights(ss, zz, cfg["normalize"])) if nerf_mode else \
+                     (lambda zz, ss: volsdf_weights(zz, ss, cfg["normalize"]))
+        w_c = weights_fn(z_c, sigma_c)
         if z_vals_override is None:
-            z = fine_z_vals(z_c, w_c, cfg["near"], cfg["far"], cfg["fine_range"], cfg["n_fine"],
-                            cfg["perturb"], U2, U3)
+            z = fine_z_vals(z_c, w_c, cfg.get("fine_near", cfg["near"]), cfg.get("fine_far", cfg["far"]),
+                            cfg["fine_range"], cfg["n_fine"], cfg["perturb"], U2, U3)
         else:
             z = z_vals_override
         pts = sample_points(cam_loc, z, directions)
@@ -368,11 +374,13 @@ def render(vf_sd, rn_sd, density_params, cfg: dict, uv, pose, intrinsics, t_vals
     normals = vf[:, :3].reshape(R, N, 3)
     feat = vf[:, 3:]
     sigma, cosw = get_density(normals, ray_dirs, beta, scale, mean, cfg["window"], cfg["dir_to_normal_th"])
-    w = volsdf_weights(z, sigma, cfg["normalize"])
+    w = weights_fn(z, sigma)
     rep_dirs = ray_dirs.unsqueeze(1).repeat(1, N, 1).reshape(-1, 3)
     colors = color_network(rn_sd, pts.reshape(-1, 3), vf[:, :3], rep_dirs, feat, cfg["multires_view"])
     rgb = torch.sum(w.unsqueeze(-1) * colors.reshape(R, N, 3), dim=1)
     depth = torch.sum(w.unsqueeze(-1) * z.unsqueeze(-1), dim=1)
+    if cfg.get("white", False):
+        rgb = rgb + (1. - torch.sum(w, -1)[..., None])                      # :325-329
     out.update(normals=normals, feat=feat, cosw=cosw, sigma=sigma, weights=w, colors=colors,
                rgb=rgb, depth=depth, rep_ray_dirs=rep_dirs)
     return out

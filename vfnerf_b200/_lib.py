@@ -28,7 +28,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 MAX_LAYERS = 16
 MAX_SAMPLES = 256
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
-FLAG_RECOMPUTE_COARSE = 1
+FLAG_RECOMPUTE_COARSE, FLAG_WHITE_BG, FLAG_NERF_WEIGHTS = 1, 2, 4
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 
 
@@ -91,6 +91,7 @@ PROTOTYPES = {
     "vfnerf_density_weights": (_I, [_CFG, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "vfnerf_volume_weights": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "vfnerf_composite": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
+    "vfnerf_composite_white": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
 }
 
 DEBUG_PROTOTYPES = {

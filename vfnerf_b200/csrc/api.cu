@@ -390,7 +390,8 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
     if (int e = launch_density_weights(*cfg, p.R, p.N, density_params, out->normals, 3, p.ray_dirs, out->z_vals,
                                        nullptr, nullptr, weights, s)) return e;
   }
-  if (int e = launch_composite(p.R, p.N, weights, out->colors, out->z_vals, out->rgb, out->depth, s)) return e;
+  if (int e = launch_composite(p.R, p.N, weights, out->colors, out->z_vals, out->rgb, out->depth, s,
+                               (cfg->flags & VFNERF_FLAG_WHITE_BG) ? 1 : 0)) return e;
   return 0;
 }
 
@@ -738,6 +739,12 @@ int vfnerf_composite(int n_rays, int n_samples, const float* weights, const floa
                      float* rgb, float* depth, void* stream) {
   DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
   return launch_composite(n_rays, n_samples, weights, colors, z, rgb, depth, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vfnerf_composite_white(int n_rays, int n_samples, const float* weights, const float* colors, const float* z,
+                           float* rgb, float* depth, void* stream) {
+  DeviceGuard dev_guard(reinterpret_cast<cudaStream_t>(stream));
+  return launch_composite(n_rays, n_samples, weights, colors, z, rgb, depth, reinterpret_cast<cudaStream_t>(stream), 1);
 }
 
 }  // extern "C"

@@ -118,7 +118,7 @@ int launch_density_weights(const vfnerf_render_cfg& cfg, int n_rays, int n_sampl
                            const float* ray_dirs, const float* z, float* cosw, float* sigma,
                            float* weights, cudaStream_t s);
 int launch_composite(int n_rays, int n_samples, const float* weights, const float* colors,
-                     const float* z, float* rgb, float* depth, cudaStream_t s);
+                     const float* z, float* rgb, float* depth, cudaStream_t s, int white = 0);
 // fused backward of composite + volsdf weights + Laplace density + windowed cosine
 int launch_render_tail_bwd(const vfnerf_render_cfg& cfg, int n_rays, int n_samples,
                            const float* density_params, const float* normals, int64_t normals_ld,

@@ -103,6 +103,15 @@ __device__ __forceinline__ float window_cos(const float* su, int j, const Window
   return c;
 }
 
+__device__ __forceinline__ float warp_inclusive_prod(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(kFull, v, o);
+    if (lane >= o) v *= t;
+  }
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward: c, sigma, weights
 // ---------------------------------------------------------------------------------------------
@@ -128,7 +137,8 @@ density_weights_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
   }
   __syncwarp();
   const float* zr = z + (int64_t)r * N;
-  float carry = 0.f, wsum = 0.f;
+  const bool nerf_w = (cfg.flags & VFNERF_FLAG_NERF_WEIGHTS) != 0;
+  float carry = 0.f, wsum = 0.f, pcarry = 1.f;
   float what[KP];
 #pragma unroll
   for (int i = 0; i < KP; ++i) {
@@ -144,12 +154,19 @@ density_weights_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
     }
     if (j < N && sigma_out) sigma_out[(int64_t)r * N + j] = sg;
     // exclusive prefix of the free energy over this 32-sample chunk, plus the carry of earlier chunks
-    float inc = warp_inclusive_scan(E, lane);
-    float T = expf(-(carry + inc - E));
     float a = 1.f - expf(-E);
-    what[i] = (j < N) ? a * T : 0.f;
+    if (nerf_w) {
+      // nerf_volume_rendering (utils/rendering.py:98-119): inclusive cumprod of (1 - a + 1e-10)
+      const float pinc = warp_inclusive_prod((j < N) ? (1.f - a + 1e-10f) : 1.f, lane);
+      what[i] = (j < N) ? a * (pcarry * pinc) : 0.f;
+      pcarry *= __shfl_sync(kFull, pinc, 31);
+    } else {
+      float inc = warp_inclusive_scan(E, lane);
+      float T = expf(-(carry + inc - E));
+      what[i] = (j < N) ? a * T : 0.f;
+      carry += __shfl_sync(kFull, inc, 31);
+    }
     wsum += what[i];
-    carry += __shfl_sync(kFull, inc, 31);
   }
   wsum = warp_sum(wsum);
   const float inv = cfg.normalize ? 1.f / (wsum + 1e-5f) : 1.f;
@@ -185,14 +202,6 @@ int launch_density_weights(const vfnerf_render_cfg& cfg, int n_rays, int n_sampl
 //           cumprod is INCLUSIVE of sample j).  render() upstream passes this function its arguments swapped
 //           (SURVEY.md §8a), so it is offered as the corrected stand-alone op only.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_inclusive_prod(float v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    float t = __shfl_up_sync(kFull, v, o);
-    if (lane >= o) v *= t;
-  }
-  return v;
-}
 
 __global__ void __launch_bounds__(kRayWarps * 32)
 volume_weights_kernel(int n_rays, int N, int mode, int normalize, const float* __restrict__ sigma,
@@ -250,18 +259,24 @@ int launch_volume_weights(int n_rays, int n_samples, int mode, int normalize, co
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRayWarps * 32)
 composite_kernel(int n_rays, int N, const float* __restrict__ w, const float* __restrict__ colors,
-                 const float* __restrict__ z, float* __restrict__ rgb, float* __restrict__ depth) {
+                 const float* __restrict__ z, float* __restrict__ rgb, float* __restrict__ depth, int white) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int r = blockIdx.x * kRayWarps + wid;
   if (r >= n_rays) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, ad = 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, ad = 0.f, aw = 0.f;
   for (int j = lane; j < N; j += 32) {
     int64_t idx = (int64_t)r * N + j;
     float wj = w[idx];
     a0 += wj * colors[3 * idx]; a1 += wj * colors[3 * idx + 1]; a2 += wj * colors[3 * idx + 2];
     ad += wj * z[idx];
+    aw += wj;
   }
   a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); ad = warp_sum(ad);
+  if (white) {             // rgb + (1 - acc_map), vector_field_nerf.py:325-329
+    aw = warp_sum(aw);
+    const float bg = 1.f - aw;
+    a0 = a0 + bg; a1 = a1 + bg; a2 = a2 + bg;
+  }
   if (lane == 0) {
     rgb[3 * (int64_t)r] = a0; rgb[3 * (int64_t)r + 1] = a1; rgb[3 * (int64_t)r + 2] = a2;
     depth[r] = ad;
@@ -269,10 +284,10 @@ composite_kernel(int n_rays, int N, const float* __restrict__ w, const float* __
 }
 
 int launch_composite(int n_rays, int n_samples, const float* weights, const float* colors,
-                     const float* z, float* rgb, float* depth, cudaStream_t s) {
+                     const float* z, float* rgb, float* depth, cudaStream_t s, int white) {
   if (n_rays <= 0) return 0;
   composite_kernel<<<(n_rays + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, s>>>(
-      n_rays, n_samples, weights, colors, z, rgb, depth);
+      n_rays, n_samples, weights, colors, z, rgb, depth, white);
   VFN_LAUNCH_CHECK();
   return 0;
 }
@@ -325,9 +340,11 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
   const float gd = d_depth[r];
 
   // ---- forward recompute
+  const bool nerf_w = (cfg.flags & VFNERF_FLAG_NERF_WEIGHTS) != 0;
+  const bool white = (cfg.flags & VFNERF_FLAG_WHITE_BG) != 0;
   float cj[KP], E[KP], T[KP], what[KP], dw[KP], delta[KP];
   bool active[KP];
-  float carry = 0.f, wsum = 0.f;
+  float carry = 0.f, wsum = 0.f, pcarry = 1.f;
 #pragma unroll
   for (int i = 0; i < KP; ++i) {
     const int j = lane + 32 * i;
@@ -343,11 +360,19 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
       e = dl * sg;
     }
     cj[i] = c; E[i] = e; active[i] = act; delta[i] = dl;
-    float inc = warp_inclusive_scan(e, lane);
-    T[i] = expf(-(carry + inc - e));
+    if (nerf_w) {
+      // T holds the INCLUSIVE product P_j = prod_{i<=j} (1 - a_i + 1e-10), formed like the forward forms it
+      const float a_ = 1.f - expf(-e);
+      const float pinc = warp_inclusive_prod((j < N) ? (1.f - a_ + 1e-10f) : 1.f, lane);
+      T[i] = pcarry * pinc;
+      pcarry *= __shfl_sync(kFull, pinc, 31);
+    } else {
+      float inc = warp_inclusive_scan(e, lane);
+      T[i] = expf(-(carry + inc - e));
+      carry += __shfl_sync(kFull, inc, 31);
+    }
     what[i] = (j < N) ? (1.f - expf(-e)) * T[i] : 0.f;
     wsum += what[i];
-    carry += __shfl_sync(kFull, inc, 31);
   }
   wsum = warp_sum(wsum);
   const float inv = cfg.normalize ? 1.f / (wsum + 1e-5f) : 1.f;
@@ -363,6 +388,7 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
       const float w = what[i] * inv;
       const float c0 = colors[3 * idx], c1 = colors[3 * idx + 1], c2 = colors[3 * idx + 2];
       dw[i] = g0 * c0 + g1 * c1 + g2 * c2 + gd * zr[j];
+      if (white) dw[i] -= g0 + g1 + g2;              // rgb_c += 1 - sum_j w_j
       float o0 = w * g0, o1 = w * g1, o2 = w * g2;
       if (d_colors_up) { o0 += d_colors_up[3 * idx]; o1 += d_colors_up[3 * idx + 1]; o2 += d_colors_up[3 * idx + 2]; }
       const int64_t od = out_row(src, idx, r, n_rays, N, n_coarse);
@@ -393,7 +419,11 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
     qcarry += __shfl_sync(kFull, inc, 31);
     float dc = 0.f;
     if (j < N - 1 && active[i]) {
-      float dE = dw[i] * T[i] * expf(-E[i]) - suffix;
+      const float ex = expf(-E[i]);
+      // volsdf: w_i = a_i exp(-sum_{k<i} E_k): E_j enters a_j and every later transmittance.
+      // nerf:   w_i = a_i prod_{k<=i} (exp(-E_k) + 1e-10): E_j enters a_j and every product from i = j on.
+      float dE = nerf_w ? dw[i] * T[i] * ex - (suffix + q[i]) * ex / (ex + 1e-10f)
+                        : dw[i] * T[i] * ex - suffix;
       float dsig = delta[i] * dE;
       float x = -cj[i];
       float lp = lap.dcdf_dx(x);

@@ -64,6 +64,11 @@ class VectorFieldNerf:
         # rgb / depth to the host right away); off by default for that reason.
         self.graph_replay = False
         self._graphs: dict = {}
+        # Two paths of the reference's render() cannot execute upstream: white=True reads rgb before it is
+        # assigned (vector_field_nerf.py:273-277) and rendering="nerf" passes nerf_volume_rendering its arguments swapped
+        # (:271,312 vs utils/rendering.py:98).  By default both are rejected like upstream behaves; enable_reference_fix()
+        # opts into their evident intent (include/vfnerf_b200.h: VFNERF_FLAG_WHITE_BG / VFNERF_FLAG_NERF_WEIGHTS).
+        self.reference_fixes: set = set()
 
     # ---- module plumbing (vector_field_nerf.py:84-214) ------------------------------------------
     def set_precision(self, precision: str) -> None:
@@ -180,14 +185,26 @@ class VectorFieldNerf:
         return out
 
     # ---- the hot path ---------------------------------------------------------------------------
-    def _render_cfg(self, n_rays: int, pose_is_quat: bool) -> _lib.RenderCfg:
+    def enable_reference_fix(self, *names: str) -> None:
+        """Opt into paths that are broken upstream, with their evident intent: "white_background" (render(white=True):
+        rgb += 1 - sum of weights after the final composite) and/or "nerf_rendering" (config.rendering == "nerf":
+        nerf_volume_rendering with its arguments in the function's own order)."""
+        for n in names:
+            if n not in ("white_background", "nerf_rendering"):
+                raise ValueError(f"unknown fix {n!r}: expected 'white_background' or 'nerf_rendering'")
+            self.reference_fixes.add(n)
+
+    def _render_cfg(self, n_rays: int, pose_is_quat: bool, white: bool = False) -> _lib.RenderCfg:
         c, d = self.config, self.density
         if not c.ray_sampler_config.fine_sampling():
             # the reference dies with UnboundLocalError at vector_field_nerf.py:331 in this configuration
             raise UnboundLocalError("render() needs fine sampling (n_importance > 0), like the reference")
-        if c.rendering != "volsdf":
-            raise NotImplementedError('rendering="nerf" passes its arguments swapped in the reference '
-                                      "(SURVEY.md §8a); only \"volsdf\" is supported")
+        if c.rendering not in ("volsdf", "nerf"):
+            raise ValueError(f"rendering must be 'volsdf' or 'nerf', got {c.rendering!r}")
+        if c.rendering == "nerf" and "nerf_rendering" not in self.reference_fixes:
+            raise NotImplementedError('rendering="nerf" passes its arguments swapped in the reference (SURVEY.md §8a) and '
+                                      "renders garbage there; call model.enable_reference_fix('nerf_rendering') for the "
+                                      "corrected argument order")
         near, far = self.ray_sampler.near, self.ray_sampler.far
         if not isinstance(far, (int, float)) or not isinstance(near, (int, float)):
             near, far = float(near), float(far)
@@ -202,7 +219,8 @@ class VectorFieldNerf:
         cfg.multires_view = self.rendering_network.multires_view
         cfg.skip_layer = self.vector_field_network.skip_layer
         cfg.precision = _lib.PRECISIONS[self.precision]
-        cfg.flags = _lib.FLAG_RECOMPUTE_COARSE if self.recompute_coarse else 0
+        cfg.flags = (_lib.FLAG_RECOMPUTE_COARSE if self.recompute_coarse else 0) | \
+                    (_lib.FLAG_WHITE_BG if white else 0) | (_lib.FLAG_NERF_WEIGHTS if c.rendering == "nerf" else 0)
         cfg.near_, cfg.far_, cfg.fine_range = float(near), float(far), float(self.fine_sampler.range)
         # the fine sampler draws its fallback samples in ITS OWN [near, far] (ray_sampler.py:296-299)
         cfg.fine_near_, cfg.fine_far_ = float(self.fine_sampler.near), float(self.fine_sampler.far)
@@ -224,9 +242,10 @@ class VectorFieldNerf:
             multi-GPU ray sharding where each rank takes its slice of the global draws).
         :param z_vals_override: optional [R,N] merged z values for the second pass (parity protocol).
         """
-        if white:
+        if white and "white_background" not in self.reference_fixes:
             # vector_field_nerf.py:274-277 reads rgb_values_coarse before assignment
-            raise UnboundLocalError("white=True is broken in the reference (SURVEY.md fact 2) and unsupported")
+            raise UnboundLocalError("white=True is broken in the reference (SURVEY.md fact 2); call "
+                                    "model.enable_reference_fix('white_background') for rgb += 1 - sum(weights)")
         if self.vector_field_network.training or self.rendering_network.training:
             # also reached with config.numerical_jacobian: train() then leaves the VF net in eval but still switches the
             # colour net to batch statistics and asks for numerical directional derivatives (vector_field_nerf.py:84-101)
@@ -245,9 +264,9 @@ class VectorFieldNerf:
         if pose.shape[0] != R or intrinsics.shape[0] != R:
             raise ValueError("pose, pixels and intrinsics must have one row per ray")
         quat = pose.dim() == 2 and pose.shape[1] == 7
-        if self.graph_replay and z_vals_override is None and R > 0 and not torch.is_grad_enabled():
+        if self.graph_replay and z_vals_override is None and R > 0 and not white and not torch.is_grad_enabled():
             return self._render_replay(pose, pixels, intrinsics, quat, draws)
-        cfg = self._render_cfg(R, quat)
+        cfg = self._render_cfg(R, quat, white)
         # host-side draws in the reference's order (ray_sampler.py:138, 292, 297), then H2D
         if draws is None and self.draws_on_device:
             nf = self.fine_sampler.n_fine()
@@ -292,7 +311,8 @@ class VectorFieldNerf:
         rs, fs, c = self.ray_sampler, self.fine_sampler, self.config
         return (R, quat, str(dev), rs.N_samples, fs.n_fine(), float(rs.near), float(rs.far), float(fs.range),
                 bool(rs.deterministic), bool(fs.deterministic), self.precision, self.recompute_coarse,
-                self.return_ray_dirs, float(c.dir_to_normal_th), len(c.cos_sim_weights), bool(c.normalize_rendering))
+                self.return_ray_dirs, float(c.dir_to_normal_th), len(c.cos_sim_weights), bool(c.normalize_rendering),
+                c.rendering, float(fs.near), float(fs.far))
 
     def _render_replay(self, pose, pixels, intrinsics, quat: bool, draws) -> NerfOutput:
         dev = pixels.device
