@@ -43,6 +43,11 @@ struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(cudaStream_t s) {
     if (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) return;
+    // a capturing stream must not be queried for its device (that invalidates the capture); a capture is driven from
+    // the thread whose current device owns the stream anyway
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cap != cudaStreamCaptureStatusNone) return;
     int cur = 0, dev = 0;
     if (cudaGetDevice(&cur) != cudaSuccess) return;
     if (cudaStreamGetDevice(s, &dev) != cudaSuccess) { cudaGetLastError(); return; }
