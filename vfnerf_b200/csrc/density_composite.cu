@@ -422,7 +422,9 @@ render_tail_bwd_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
       const float ex = expf(-E[i]);
       // volsdf: w_i = a_i exp(-sum_{k<i} E_k): E_j enters a_j and every later transmittance.
       // nerf:   w_i = a_i prod_{k<=i} (exp(-E_k) + 1e-10): E_j enters a_j and every product from i = j on.
-      float dE = nerf_w ? dw[i] * T[i] * ex - (suffix + q[i]) * ex / (ex + 1e-10f)
+      // (the factor of the product is the ROUNDED 1 - a + 1e-10 the forward multiplied with, not exp(-E) + 1e-10:
+      //  they differ once exp(-E) drops below the fp32 spacing at 1, which a density scale of 100 reaches easily)
+      float dE = nerf_w ? dw[i] * T[i] * ex - (suffix + q[i]) * ex / (1.f - (1.f - ex) + 1e-10f)
                         : dw[i] * T[i] * ex - suffix;
       float dsig = delta[i] * dE;
       float x = -cj[i];

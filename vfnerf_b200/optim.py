@@ -81,7 +81,7 @@ class ArenaAdam(torch.optim.Optimizer):
         params = self.model.parameters()          # the reference's list, duplicates included
         index = {}
         for i, p in enumerate(params):
-            index.setdefault(id(p), i)
+            index[id(p)] = i          # torch's own packing: a duplicated tensor is known by its LAST position
         g0 = self.param_groups[0]
         lr = g0["lr"]
         state = {}
