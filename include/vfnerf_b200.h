@@ -301,6 +301,20 @@ int vfnerf_composite(int n_rays, int n_samples, const float* weights, const floa
 int vfnerf_composite_white(int n_rays, int n_samples, const float* weights, const float* colors,
                            const float* z, float* rgb, float* depth, void* stream);
 
+/* ---- supervision points of the trainer (train/vector_field_nerf_train.py:180-216) --------------------------------- */
+/* SphereSampler.sample (models/samplers/sampler.py:160-193) + sample_border_points / sample_center_points
+ * (models/helpers/functions.py:99-130) from GIVEN float64 draws phi in [0,2pi), cos_theta in [-1,1), u in [0,1) (device
+ * pointers; the reference draws them with np.random.uniform in this order): points[n,3] = fp32(sphere point) + centroid,
+ * gt[n,3] = normalize(centroid - p) (inward = 1: border points) or normalize(p - centroid) (inward = 0: centre points). */
+int vfnerf_sphere_points(int64_t n, const double* phi, const double* cos_theta, const double* u, double r_max, double r_min,
+                         const float* centroid3_host, int inward, float* points, float* gt, void* stream);
+/* get_border_indices_and_gt (mode 0: |p - centroid| > threshold, gt = normalize(centroid - p), functions.py:75-97) and
+ * get_center_indices_and_gt (mode 1: |p - centroid| < threshold, gt = normalize(p - centroid), :132-154) over all n ray
+ * samples in one pass: flag[n] (uint8) marks the selected samples, gt[n,3] holds every sample's target.  The caller
+ * compacts (the reference indexes with the boolean mask, which synchronises the same way). */
+int vfnerf_select_supervised(int64_t n, const float* points, const float* centroid3_host, float threshold, int mode,
+                             uint8_t* flag, float* gt, void* stream);
+
 /* Test-only entry points (UMMA descriptor probes, micro-benchmarks, activation-stash read-back) are NOT part of this
  * library: they are declared in vfnerf_b200_debug.h and built into a separate libvfnerf_b200_debug.so by the tests. */
 

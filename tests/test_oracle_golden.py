@@ -148,3 +148,26 @@ def test_smooth_oracle_matches_reference_golden():
     assert torch.equal(cells.int(), torch.from_numpy(z["after.cells"]))
     assert torch.equal(comb, torch.from_numpy(z["after.comb"]))
     assert (udf - torch.from_numpy(z["after.udf"])).abs().max().item() <= 2e-6
+
+
+def test_supervision_oracle_reproduces_reference_golden():
+    """oracle/supervision_oracle.py vs vectors written by the live reference functions (make_golden_supervision.py)."""
+    import os
+    import numpy as np
+    from oracle import supervision_oracle as SO
+    z = np.load(os.path.join(U.GOLDEN_DIR, "supervision.npz"))
+    c = torch.from_numpy(z["centroid"])
+    far, radius = float(z["far"]), float(z["radius"])
+    p, g = SO.sample_border_points(far / 2 - radius, far / 2, c, z["border_phi"], z["border_cos"], z["border_u"])
+    assert torch.equal(p, torch.from_numpy(z["border_points"])) and torch.equal(g, torch.from_numpy(z["border_gt"]))
+    p, g = SO.sample_center_points(c, radius, z["center_phi"], z["center_cos"], z["center_u"])
+    assert torch.equal(p, torch.from_numpy(z["center_points"])) and torch.equal(g, torch.from_numpy(z["center_gt"]))
+    pts, nrm = torch.from_numpy(z["ray_points"]), torch.from_numpy(z["ray_normals"])
+    n, g = SO.get_border_indices_and_gt(pts, nrm, far, radius, c)
+    assert torch.equal(n, torch.from_numpy(z["sel_border_normals"])) and torch.equal(g, torch.from_numpy(z["sel_border_gt"]))
+    n, g = SO.get_center_indices_and_gt(pts, nrm, c, radius)
+    assert torch.equal(n, torch.from_numpy(z["sel_center_normals"])) and torch.equal(g, torch.from_numpy(z["sel_center_gt"]))
+    # shell / ball membership of the sampled points (size-independent property)
+    d = (torch.from_numpy(z["border_points"]) - c).norm(dim=1)
+    assert (d >= far / 2 - radius - 1e-5).all() and (d <= far / 2 + 1e-5).all()
+    assert ((torch.from_numpy(z["center_points"]) - c).norm(dim=1) <= radius + 1e-6).all()
