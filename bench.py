@@ -469,14 +469,16 @@ def main():
             train["fp32_ms_per_step"] = time_train("fp32", 3)
         ms_ar = time_train(train_prec, 10, arena=True)
         train["arena_adam_eager"] = {"ms_per_step": ms_ar, "value": world * Rt / (ms_ar * 1e-3), "unit": "rays/s",
-                                     "collective": "all_reduce(sum) of the flat gradient arenas over NCCL" if world > 1 else None,
+                                     "collective": "ONE ncclAllReduce(avg) over the single 3.2 MB gradient tensor (VF | colour | "
+                                                   "density), issued when backward() returns" if world > 1 else None,
                                      "includes": "eager: render + fused VFLoss + backward + (allreduce of the flat gradient "
                                                  "arenas) + ArenaAdam (clip + Adam)"}
 
         # the same sequence captured once as a CUDA graph and replayed (vfnerf_b200/graphed.py), and -- SURVEY.md §8(d)
         # training protocol (i) -- the kernels alone: fwd + loss gradient + bwd into the flat gradient buffers,
-        # graph replay, median of 50.  Single-GPU legs (the allreduce of a multi-GPU step is not captured).
-        if world == 1 and train_prec == "bf16":
+        # graph replay, median of 50.  Under torchrun only the ArenaAdam step is measured: its one all-reduce is captured in
+        # the graph (graphed.GraphedTrainStep(allreduce=True)), the step time is the max over ranks.
+        if train_prec == "bf16":
             from vfnerf_b200 import graphed
 
             def loss_fn(out, rgb_gt, depth_gt):
@@ -507,24 +509,31 @@ def main():
                 ts = sorted(a.elapsed_time(b) for a, b in ev)
                 del step, tm
                 torch.cuda.empty_cache()
-                return ts[len(ts) // 2]
+                med = torch.tensor([ts[len(ts) // 2]], device=dev)
+                if world > 1:
+                    dist.all_reduce(med, op=dist.ReduceOp.MAX)
+                return med.item()
             A_train = 3 * (N_COARSE + N_FINE) * (F_VF + F_RN)
-            ms_g = time_graphed(Rt, True)
-            train["graphed"] = {"ms_per_step": ms_g, "value": Rt / (ms_g * 1e-3), "unit": "rays/s",
-                                "includes": "CUDA-graph replay of render + loss + backward + clip + Adam, inputs copied per step"}
+            if world == 1:
+                ms_g = time_graphed(Rt, True)
+                train["graphed"] = {"ms_per_step": ms_g, "value": Rt / (ms_g * 1e-3), "unit": "rays/s",
+                                    "includes": "CUDA-graph replay of render + loss + backward + clip + Adam, inputs copied per step"}
             ms_a = time_graphed(Rt, True, arena=True)
-            train["graphed_arena_adam"] = {"ms_per_step": ms_a, "value": Rt / (ms_a * 1e-3), "unit": "rays/s",
-                                           "includes": "CUDA-graph replay of render + fused VFLoss + backward + ArenaAdam "
-                                                       "(clip + Adam on the flat arenas, 2 launches per network)"}
+            train["graphed_arena_adam"] = {"ms_per_step": ms_a, "value": world * Rt / (ms_a * 1e-3), "unit": "rays/s",
+                                           "collective": "ONE ncclAllReduce(avg) over the 3.2 MB gradient tensor, captured in "
+                                                         "the graph" if world > 1 else None,
+                                           "includes": "CUDA-graph replay of render + fused VFLoss + backward + (all-reduce) + "
+                                                       "ArenaAdam (one norm launch + one update launch per network)"}
             ko = {}
-            for n_r in (Rt, 8192):
+            for n_r in ((Rt, 8192) if world == 1 else ()):
                 ms_k = time_graphed(n_r, False)
                 tf = A_train * n_r / (ms_k * 1e-3) / 1e12
                 ko[str(n_r)] = {"ms_per_step": ms_k, "rays_per_s": n_r / (ms_k * 1e-3), "algorithmic_tflops": tf,
                                 "frac_of_burst_bf16_peak": tf / peak_burst, "frac_of_sustained_bf16_peak": tf / peak_sust}
-            train["kernels_only"] = dict(ko, note="fwd + loss gradient + bwd into the flat gradient buffers, CUDA-graph replay, "
-                                         "median of 50 (a graph replay timed alone: the burst peak is the honest denominator); "
-                                         "algorithmic FLOP = 3 * 203.88 MFLOP/ray (SURVEY.md 8d)")
+            if ko:
+                train["kernels_only"] = dict(ko, note="fwd + loss gradient + bwd into the flat gradient buffers, CUDA-graph "
+                                             "replay, median of 50 (a graph replay timed alone: the burst peak is the honest "
+                                             "denominator); algorithmic FLOP = 3 * 203.88 MFLOP/ray (SURVEY.md 8d)")
 
     # ---- BASELINE config 4: ONE ScanNet-shaped 640x480 image (307 200 rays, normals included in the render), rays sharded
     # over the ranks in contiguous slices, rgb + depth gathered to rank 0 inside the timed region: STRONG scaling.

@@ -195,15 +195,19 @@ int vfnerf_vf_loss_bwd(int64_t n_rays, int64_t n_points, int64_t n_sup, const fl
                        void* stream);
 
 /* ---- clip_grad_norm_ + Adam on the flat arenas (train/vector_field_nerf_train.py:252-258) --------------------------
- * vfnerf_sqnorm_accumulate: *out_sq += sum g[i]^2 (call once per arena, after zeroing *out_sq).
- * vfnerf_adam_step: torch.optim.Adam's update (amsgrad off) of p[0..n) from g, first scaling g IN PLACE by
+ * vfnerf_sqnorm_accumulate: *out_sq += sum (pre_scale * g[i])^2 (call once per arena, after zeroing *out_sq).  The result
+ * is reproducible run to run (per-block partials summed in a fixed order, no float atomics): `scratch` holds
+ * VFNERF_SQNORM_SCRATCH_FLOATS floats, zeroed once by the caller before the first call and left zero by every call.
+ * vfnerf_adam_step: torch.optim.Adam's update (amsgrad off) of p[0..n) from g, first scaling g IN PLACE by pre_scale
+ * (1/world_size after a summing all-reduce of the gradient arena, else 1) and by
  * min(1, max_norm / (sqrt(*total_sqnorm) + 1e-6)) when max_norm > 0.  mask (optional, one byte per element) marks the
  * trainable elements; lr and step are device scalars (step = number of updates including this one), so the call is
  * CUDA-graph capturable and a scheduler can change the rate without touching the graph. */
-int vfnerf_sqnorm_accumulate(const float* g, int64_t n, float* out_sq, void* stream);
+#define VFNERF_SQNORM_SCRATCH_FLOATS 1024
+int vfnerf_sqnorm_accumulate(const float* g, int64_t n, float pre_scale, float* out_sq, float* scratch, void* stream);
 int vfnerf_adam_step(float* p, float* g, float* m, float* v, const uint8_t* mask, int64_t n, const float* lr,
                      const float* step, float beta1, float beta2, float eps, float weight_decay, float max_norm,
-                     const float* total_sqnorm, void* stream);
+                     const float* total_sqnorm, float pre_scale, void* stream);
 
 /* ---- both MLPs on given points: the VF + colour evaluation of VectorFieldNerf.get_colors ---------------- */
 /* (vector_field_nerf.py:341-375 / the merged pass of render(), :292-321).  points [P,3]; ray_dirs [P/samples_per_ray,3]

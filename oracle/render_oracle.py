@@ -399,3 +399,132 @@ def vf_loss(rgb, depth, normals_flat, rgb_gt, depth_gt, weights: dict, depth_cla
     if epoch >= norm_lt1_start:
         loss = loss + weights["norm_smaller_than_one"] * torch.mean(torch.relu(nrm - 1) ** 2)
     return loss
+
+
+# --------------------------------------------------------------------------------------
+# train mode: BatchNorm batch statistics, autograd Jacobian, directional derivatives
+# --------------------------------------------------------------------------------------
+BN_MOMENTUM = 0.1  # torch.nn.BatchNorm1d default
+
+
+def _linear_bn_train(sd: Dict[str, torch.Tensor], i: int, x: torch.Tensor, stats: Optional[dict]) -> torch.Tensor:
+    """Linear + BatchNorm1d in TRAINING mode: normalise with the batch's mean and biased variance; ``stats`` (if given)
+    receives the values the module would fold into its running statistics (mean, UNBIASED variance)."""
+    W, b = sd[f"layers.{i}.0.weight"], sd[f"layers.{i}.0.bias"]
+    g, be = sd[f"layers.{i}.1.weight"], sd[f"layers.{i}.1.bias"]
+    y = F.linear(x, W, b)
+    mean = y.mean(dim=0)
+    var = ((y - mean) ** 2).mean(dim=0)
+    if stats is not None:
+        n = y.shape[0]
+        stats[i] = (mean.detach(), (var * n / max(n - 1, 1)).detach())
+    return (y - mean) / torch.sqrt(var + BN_EPS) * g + be
+
+
+def vf_network_train(sd: Dict[str, torch.Tensor], points: torch.Tensor, multires: int = 6, skip_in=(4,),
+                     stats: Optional[dict] = None) -> torch.Tensor:
+    """VectorFieldNetwork._forward with the module in train() mode, vector_field_network.py:177-208."""
+    n_layers = _num_layers(sd)
+    emb = embed(points, multires)
+    x = emb
+    for i in range(n_layers):
+        if i in skip_in:
+            x = torch.cat([x, emb], 1) / torch.sqrt(torch.tensor([2.0]))
+        last = i == n_layers - 1
+        x = _linear_bn(sd, i, x, has_bn=False) if last else _linear_bn_train(sd, i, x, stats)
+        x = torch.tanh(x) if last else torch.relu(x)
+    return x
+
+
+def vf_network_train_with_jacobian(sd, points, multires: int = 6, skip_in=(4,), stats: Optional[dict] = None):
+    """VectorFieldNetwork.forward in train() mode, vector_field_network.py:140-175: [y, d(sum_j y_j0)/dx, d(sum_j y_j1)/dx,
+    d(sum_j y_j2)/dx].  The three gradients are taken of COLUMN SUMS over the batch, through the batch statistics, so
+    they are not per-sample Jacobians: every sample's row also carries the other samples' dependence on it via the
+    batch mean and variance."""
+    with torch.enable_grad():
+        pts = points.detach().clone().requires_grad_(True)
+        y = vf_network_train(sd, pts, multires, skip_in, stats)
+        rows = [torch.autograd.grad(y[:, k].sum(), pts, create_graph=False, retain_graph=True)[0] for k in range(3)]
+    return y, torch.cat(rows, dim=-1)
+
+
+def directional_derivatives(normals: torch.Tensor, jac9: torch.Tensor) -> torch.Tensor:
+    """compute_directional_derivatives, vector_field_nerf.py:476-498: [P,3], [P,9] -> [P,2,3]."""
+    J = jac9.reshape(-1, 3, 3)
+    n1 = torch.stack([normals[:, 1], -normals[:, 0], torch.zeros_like(normals[:, 0])], dim=1)
+    n2 = torch.cross(normals, n1, dim=-1)
+    d1 = torch.bmm(J, F.normalize(n1, dim=-1).unsqueeze(-1)).squeeze(-1)
+    d2 = torch.bmm(J, F.normalize(n2, dim=-1).unsqueeze(-1)).squeeze(-1)
+    return torch.stack([d1, d2], dim=1)
+
+
+def color_network_train(sd, points, normals, view_dirs, feat, multires_view: int = 4, stats: Optional[dict] = None):
+    """RenderingNetwork.forward (mode 'idr') with the module in train() mode."""
+    n_layers = _num_layers(sd)
+    x = torch.cat([points, embed(view_dirs, multires_view), normals.detach(), feat], dim=-1)
+    for i in range(n_layers):
+        last = i == n_layers - 1
+        x = _linear_bn(sd, i, x, has_bn=False) if last else torch.relu(_linear_bn_train(sd, i, x, stats))
+    return torch.sigmoid(x)
+
+
+def fold_running(sd: Dict[str, torch.Tensor], stats: dict) -> Dict[str, torch.Tensor]:
+    """What one training-mode forward does to the BatchNorm buffers: running = (1 - m) running + m batch."""
+    out = dict(sd)
+    for i, (mean, var_unbiased) in stats.items():
+        out[f"layers.{i}.1.running_mean"] = (1 - BN_MOMENTUM) * sd[f"layers.{i}.1.running_mean"] + BN_MOMENTUM * mean
+        out[f"layers.{i}.1.running_var"] = (1 - BN_MOMENTUM) * sd[f"layers.{i}.1.running_var"] + BN_MOMENTUM * var_unbiased
+        key = f"layers.{i}.1.num_batches_tracked"
+        if key in sd:
+            out[key] = sd[key] + 1
+    return out
+
+
+def render_train(vf_sd, rn_sd, density_params, cfg: dict, uv, pose, intrinsics, t_vals, U1=None, U2=None, U3=None,
+                 z_vals_override: Optional[torch.Tensor] = None) -> dict:
+    """VectorFieldNerf.render() after model.train() (numerical_jacobian False), vector_field_nerf.py:216-338: both passes
+    of the VF net and the colour net normalise with batch statistics; the coarse pass also yields the directional
+    derivatives, which the reference then duplicates (:305: cat([dir, dir]) -- the merged pass's own derivatives are
+    computed and dropped) and returns as per-row norms [4 R Nc] without gradient.  Returns the eval-mode keys plus
+    ``directional_derivatives``, ``vf_sd_after`` / ``rn_sd_after`` (state dicts with the updated running statistics)."""
+    R = uv.shape[0]
+    beta, scale, mean = effective_density_params(
+        density_params["beta"], density_params["scale"], density_params["mean"],
+        cfg["beta_bounds"], cfg["scale_min"], cfg["mean_bounds"])
+    directions, ray_dirs, cam_loc = ray_geometry(uv, pose, intrinsics)
+    out = {"directions": directions, "ray_dirs": ray_dirs, "cam_loc": cam_loc}
+    weights_fn = lambda zz, ss: volsdf_weights(zz, ss, cfg["normalize"])       # noqa: E731
+    with torch.no_grad():
+        z_c = coarse_z_vals(R, cfg["near"], cfg["far"], t_vals, cfg["perturb"], U1)
+        pts_c = sample_points(cam_loc, z_c, directions)
+        st1: dict = {}
+        y_c, jac_c = vf_network_train_with_jacobian(vf_sd, pts_c.reshape(-1, 3), cfg["multires"], cfg["skip_in"], st1)
+        y_c, jac_c = y_c.detach(), jac_c.detach()
+        vf_mid = fold_running(vf_sd, st1)
+        n_c = y_c[:, :3].reshape(R, -1, 3)
+        dd = directional_derivatives(y_c[:, :3], jac_c).reshape(-1, 3)
+        sigma_c, _ = get_density(n_c, ray_dirs, beta, scale, mean, cfg["window"], cfg["dir_to_normal_th"])
+        w_c = weights_fn(z_c, sigma_c)
+        if z_vals_override is None:
+            z = fine_z_vals(z_c, w_c, cfg.get("fine_near", cfg["near"]), cfg.get("fine_far", cfg["far"]),
+                            cfg["fine_range"], cfg["n_fine"], cfg["perturb"], U2, U3)
+        else:
+            z = z_vals_override
+        pts = sample_points(cam_loc, z, directions)
+    out.update(z_coarse=z_c, normals_coarse_pass=n_c, jacobian_coarse=jac_c, weights_coarse=w_c, z_vals=z, points=pts)
+    N = z.shape[1]
+    st2: dict = {}
+    vf = vf_network_train(vf_sd, pts.reshape(-1, 3), cfg["multires"], cfg["skip_in"], st2)
+    normals = vf[:, :3].reshape(R, N, 3)
+    feat = vf[:, 3:]
+    sigma, cosw = get_density(normals, ray_dirs, beta, scale, mean, cfg["window"], cfg["dir_to_normal_th"])
+    w = weights_fn(z, sigma)
+    rep_dirs = ray_dirs.unsqueeze(1).repeat(1, N, 1).reshape(-1, 3)
+    st3: dict = {}
+    colors = color_network_train(rn_sd, pts.reshape(-1, 3), vf[:, :3], rep_dirs, feat, cfg["multires_view"], st3)
+    rgb = torch.sum(w.unsqueeze(-1) * colors.reshape(R, N, 3), dim=1)
+    depth = torch.sum(w.unsqueeze(-1) * z.unsqueeze(-1), dim=1)
+    out.update(normals=normals, feat=feat, cosw=cosw, sigma=sigma, weights=w, colors=colors, rgb=rgb, depth=depth,
+               rep_ray_dirs=rep_dirs, directional_derivatives=torch.cat([dd, dd], dim=0).norm(dim=-1),
+               vf_sd_after=fold_running(vf_mid, st2), rn_sd_after=fold_running(rn_sd, st3))
+    return out

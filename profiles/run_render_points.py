@@ -5,7 +5,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import vfn_testutil as U
-from vfnerf_b200 import ops
+from vfnerf_b200 import ops, _lib
+if len(sys.argv) > 3:                 # A/B timing of a differently built library (e.g. NVCC_EXTRA=-DVFN_X3_SERIAL_GROUPS=0)
+    _lib.LIB_PATH = os.path.abspath(sys.argv[3])
 
 rays = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"          # bf16 | bf16x3

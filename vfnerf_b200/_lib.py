@@ -16,14 +16,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libvfnerf_b200.so")
 SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "optim.cu", "mc_preprocess.cu", "host_rng.cu", "supervision.cu"]
-HEADERS = ["common.cuh", "mlp_tc.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "vfnerf_b200.h")]
+HEADERS = ["common.cuh", "host_plan.cuh", "mlp_tc.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "vfnerf_b200.h")]
 # test-only library (UMMA probes, micro-benchmarks, stash read-back): the product sources + tc_debug.cu, compiled with
 # -DVFNERF_DEBUG_EXPORTS; built on demand by the tests (tests/conftest.py: debug_lib), never loaded by the product
 DEBUG_LIB_PATH = os.path.join(HERE, "libvfnerf_b200_debug.so")
 DEBUG_SOURCES = SOURCES + ["tc_debug.cu"]
 DEBUG_HEADERS = HEADERS + [os.path.join("..", "..", "include", "vfnerf_b200_debug.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "--threads", "0"]
+SQNORM_SCRATCH_FLOATS = 1024
 
 MAX_LAYERS = 16
 MAX_SAMPLES = 256
@@ -75,8 +76,8 @@ PROTOTYPES = {
                                   C.POINTER(C.c_float), C.POINTER(C.c_float), _F, _P, _P, _L, _P]),
     "vfnerf_vf_loss_fwd": (_I, [_L, _L, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float), _F, _I, _P, _P]),
     "vfnerf_vf_loss_bwd": (_I, [_L, _L, _L, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float), _F, _I, _P, _P, _P, _P, _P, _P]),
-    "vfnerf_sqnorm_accumulate": (_I, [_P, _L, _P, _P]),
-    "vfnerf_adam_step": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _F, _F, _F, _F, _F, _P, _P]),
+    "vfnerf_sqnorm_accumulate": (_I, [_P, _L, _F, _P, _P, _P]),
+    "vfnerf_adam_step": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _F, _F, _F, _F, _F, _P, _F, _P]),
     "vfnerf_mlp_points_workspace_bytes": (_L, [_DESC, _DESC, _I, _I, _I]),
     "vfnerf_mlp_points_fwd": (_I, [_DESC, _P, _DESC, _P, _I, _I, _I, _F, _I, _P, _P, _I, _L, _P, _P, _P, _L, _I, _P]),
     "vfnerf_ray_geometry": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -146,6 +146,7 @@ struct GemmArgs {
   const float* scale; const float* shift; int act; float post_div;
   const float* mask; int64_t mask_rs;
   int split_k;                        // >1: partial sums are atomically added into C (C pre-zeroed)
+  int accumulate;                     // !=0: C += result (atomic adds, plain epilogue only) also when split_k == 1
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t s);
 int launch_fold_bn(const vfnerf_mlp_desc& d, const float* arena, float bn_eps, float* scale,

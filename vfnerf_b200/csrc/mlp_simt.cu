@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs g) {
       if (n >= g.N) continue;
       float v = acc[i][j];
       float* c = g.C + m * g.c_rs + n;
-      if (g.split_k > 1) { atomicAdd(c, v); continue; }
+      if (g.split_k > 1 || g.accumulate) { atomicAdd(c, v); continue; }
       if (g.scale) v *= __ldg(g.scale + n);
       if (g.shift) v += __ldg(g.shift + n);
       v = apply_act(v, g.act);

@@ -412,6 +412,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcParams p) {
   static_assert(!kX3 || (!kBwd && !kStash), "the split-precision tile is built for the forward-only programs");
   using L = Lay<kX3>;
+  // epilogue order of the split-precision tile (see the activation-store loop): all eight warps on one 64-column group
+  // at a time.  -DVFN_X3_SERIAL_GROUPS=0 builds the plain tile's order (two groups per warp half) for A/B timing.
+#ifndef VFN_X3_SERIAL_GROUPS
+#define VFN_X3_SERIAL_GROUPS 1
+#endif
+  constexpr bool kSerialGroups = kX3 && VFN_X3_SERIAL_GROUPS;
   constexpr int kStageBytes = L::stage_bytes;
   const int kdbg = kTcProfile ? p.dbg : 0;   // experiment switches (VFNERF_TC_DBG) exist in profile builds only
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -457,7 +463,9 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     // leader: a ring slot is full when its own bulk copy has landed AND the peer's relay has arrived
     for (int i = 0; i < kTcStages; ++i) { mbar_init(&full[i], rank == 0 ? 2 : 1); mbar_init(&empty[i], 1); mbar_init(&fullp[i], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    for (int i = 0; i < kGroups; ++i) mbar_init(&grp[i], 8);    // 4 warps (one half, or the prologue warps) x 2 CTAs
+    // 4 warps (one half of the epilogue warps, or the prologue warps) x 2 CTAs; the split-precision tile's column groups
+    // are written by all 8 epilogue warps
+    for (int i = 0; i < kGroups; ++i) mbar_init(&grp[i], (kSerialGroups && i < 4) ? 16 : 8);
     for (int i = 0; i < 3; ++i) mbar_init(&reg_free[i], 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&st_ready[i], 4); mbar_init(&st_done[i], 1); }
     mbar_init(dot_full, 1);
@@ -1089,9 +1097,15 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             // Each warp owns two of the four 64-column groups (= K chunks of the next layer): h=0 -> groups 0 and 2,
             // h=1 -> groups 1 and 3.  One generic->async proxy fence (a MEMBAR.ALL.CTA) and one barrier arrival per
             // 64 columns: the fence, not the math, is the expensive part of this loop.
+            // Split-precision tile: a step spends three times as long in the tensor core, so the extra fences are free
+            // and what counts is how soon the FIRST K chunk of the next layer exists: all eight warps work on the same
+            // group (32 columns each: h selects the half), groups in K order, four fences + arrivals per warp
+            // (measured the other way round on the plain bf16 tile, profiles/r01_forward_kernel_experiments.md "v4b").
+            constexpr int kIts = kSerialGroups ? 4 : 2;
 #pragma unroll 1
-            for (int it = 0; it < 2; ++it) {
-              const int bg = 2 * it + h, c0 = bg * 64;
+            for (int it = 0; it < kIts; ++it) {
+              const int bg = kSerialGroups ? it : 2 * it + h;
+              const int c0 = kSerialGroups ? bg * 64 + 32 * h : bg * 64;
               // the bulk copy of this group's previous contents (last stashed step) must have read them
               if (st_tile) mbar_wait(&st_done[bg], (su & 1) ^ 1);
               if (c0 >= stN) {                                 // narrow layer: nothing to write, the barriers still count us
@@ -1101,7 +1115,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               }
               // nothing leaves through the activation tile (inference: the last step only feeds the prologue warps' dot)
               if (!store) continue;
-              const bool second = c0 + 32 < stN;
+              const bool second = !kSerialGroups && c0 + 32 < stN;
               uint32_t va[32], vb[32];
               TCK(t_other);
               tmem_ld32(acc + c0, va);

@@ -73,11 +73,16 @@ def allreduce_gradients(model, average: bool = True) -> None:
     flats = [model.vector_field_network.arena().grad_flat, model.rendering_network.arena().grad_flat,
              getattr(model.density, "grad_flat", None)]
     if all(f is not None for f in flats):
-        # flat-gradient mode (optim.ArenaAdam): the gradient arenas ARE the communication buffers -- no packing, no
-        # scatter; three collectives (3.2 MB in total) queued back to back on the NCCL stream
-        for f in flats:
-            dist.all_reduce(f, op=dist.ReduceOp.SUM)
-            if average:
+        # flat-gradient mode (optim.ArenaAdam): the gradient tensor IS the communication buffer -- no packing, no scatter.
+        # ArenaAdam keeps all three segments in one tensor: ONE 3.2 MB collective, averaged by NCCL itself
+        # (ncclAvg) so no divide kernel follows; backends without AVG (gloo) sum and divide.
+        whole = getattr(model.optimizer, "grad_all", None)
+        lo, hi = (whole.data_ptr(), whole.data_ptr() + 4 * whole.numel()) if whole is not None else (0, 0)
+        bufs = [whole] if whole is not None and all(lo <= f.data_ptr() < hi for f in flats) else flats
+        avg_op = average and dist.get_backend() == "nccl"
+        for f in bufs:
+            dist.all_reduce(f, op=dist.ReduceOp.AVG if avg_op else dist.ReduceOp.SUM)
+            if average and not avg_op:
                 f /= w
         return
     seen, params = set(), []

@@ -44,20 +44,25 @@ class GraphedTrainStep:
     :param targets: example target tensors (name -> tensor); their shapes/dtypes fix the static buffers.
     :param clip_norm: max gradient norm (None: no clipping).  :param optimizer_step: include optimizer.step().
     :param quat_pose: poses are [R,7] instead of [R,4,4].
+    :param allreduce: all-reduce the gradients across ranks inside the captured step (default: when torch.distributed is
+        initialised with more than one rank).
     :param given_draws: False: U1/U2/U3 are drawn by the device generator inside the graph; True: the caller passes
         ``draws=(U1, U2, U3)`` to every call (e.g. host draws in the reference's order, or a rank's slice of global draws).
     """
 
     def __init__(self, model, loss_fn: Callable[..., torch.Tensor], n_rays: int, targets: Dict[str, torch.Tensor],
                  clip_norm: Optional[float] = 0.5, optimizer_step: bool = True, quat_pose: bool = False,
-                 warmup: int = 3, seed: int = 0, given_draws: bool = False) -> None:
+                 warmup: int = 3, seed: int = 0, given_draws: bool = False, allreduce: Optional[bool] = None) -> None:
         self.model, self.loss_fn, self.n_rays = model, loss_fn, n_rays
         self.clip_norm, self.optimizer_step = clip_norm, optimizer_step
         dev = next(iter(model.parameters())).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
         from .optim import ArenaAdam
+        from . import dist as vdist
         self._arena_opt = isinstance(model.optimizer, ArenaAdam)
+        # multi-GPU (one process per GPU, SURVEY.md 8e): the gradient all-reduce is part of the captured step
+        self.allreduce = (vdist.world()[1] > 1) if allreduce is None else bool(allreduce)
         if optimizer_step and not self._arena_opt and not model.optimizer.param_groups[0].get("capturable", False):
             raise RuntimeError("optimizer is not capturable: call vfnerf_b200.graphed.make_capturable(model) or "
                                "vfnerf_b200.optim.use_arena_optimizer(model) first")
@@ -102,6 +107,9 @@ class GraphedTrainStep:
         out = m.render(self.pose, self.pixels, self.intrinsics, 0, draws=self._draws())
         loss = self.loss_fn(out, **self.targets)
         loss.backward()
+        if self.allreduce:
+            from . import dist as vdist
+            vdist.allreduce_gradients(m)
         if self._arena_opt:
             # flat arenas: clipping is part of the fused update (csrc/optim.cu)
             if self.optimizer_step:
@@ -138,7 +146,9 @@ class GraphedTrainStep:
                     t.zero_()
         self.graph.register_generator_state(self.gen)
         m.optimizer.zero_grad(set_to_none=not self._arena_opt)
-        with torch.cuda.graph(self.graph):
+        # a captured collective: NCCL's watchdog thread polls events while we capture, which the default (global) capture
+        # mode treats as an error
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if self.allreduce else "global"):
             if self._arena_opt:
                 m.optimizer.zero_grad()            # persistent flat gradients: zeroed inside the graph, every replay
             self.outputs, self.loss = self._step()

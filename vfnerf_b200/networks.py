@@ -76,11 +76,17 @@ class ParamArena:
             self.grad_flat = None
             self.enable_flat_grad()
 
-    def enable_flat_grad(self) -> torch.Tensor:
+    def enable_flat_grad(self, storage: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Give the gradients the arena's layout too: one zero-initialised flat tensor, every Parameter's ``.grad`` a
         view of it.  The backward of ops.render_call / ops.vf_query then accumulates straight into it (one add per
-        network instead of one per parameter) and optim.ArenaAdam updates the whole network with two launches."""
-        if self.grad_flat is None:
+        network instead of one per parameter) and optim.ArenaAdam updates the whole network with two launches.
+        ``storage``: a [arena_floats] slice of a larger buffer to use (optim.ArenaAdam keeps the gradients of both
+        networks and the density in ONE tensor, so clipping reads it once and multi-GPU training all-reduces it once)."""
+        if storage is not None:
+            if storage.numel() != self.flat.numel() or storage.device != self.flat.device or storage.dtype != torch.float32:
+                raise ValueError("enable_flat_grad: storage must be a float32 [arena_floats] tensor on the arena's device")
+            self.grad_flat = storage
+        elif self.grad_flat is None:
             self.grad_flat = torch.zeros_like(self.flat)
         for _, t, off in self.slots:
             if isinstance(t, nn.Parameter):
@@ -296,10 +302,12 @@ class LaplaceDensity(nn.Module):
                 self.enable_flat_grad()
         return f
 
-    def enable_flat_grad(self) -> torch.Tensor:
+    def enable_flat_grad(self, storage: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[d beta, d scale, d mean] as one tensor; the three Parameters' ``.grad`` are views of it (optim.ArenaAdam)."""
         self.flat()
-        if getattr(self, "grad_flat", None) is None:
+        if storage is not None:
+            self.grad_flat = storage
+        elif getattr(self, "grad_flat", None) is None:
             self.grad_flat = torch.zeros(3, dtype=torch.float32, device=self.beta.device)
         for i, p in enumerate((self.beta, self.scale, self.mean)):
             p.grad = self.grad_flat[i]

@@ -34,7 +34,16 @@ class ArenaAdam(torch.optim.Optimizer):
         super().__init__([{"params": flats}], dict(lr=torch.tensor(float(lr), device=dev), betas=betas, eps=eps,
                                                    weight_decay=weight_decay))
         self.max_norm = max_norm
-        self._grads = [vf.enable_flat_grad(), rn.enable_flat_grad(), model.density.enable_flat_grad()]
+        # ONE gradient tensor for everything that trains: [VF arena | colour arena | beta, scale, mean], segments starting
+        # on 256-byte boundaries.  clip reads it with one launch, and multi-GPU training all-reduces it with one collective
+        # (dist.allreduce_gradients); grad_scale is folded into the update (1/world after a SUMMING all-reduce).
+        seg = [(n + 63) // 64 * 64 for n in (vf.flat.numel(), rn.flat.numel())]
+        self.grad_all = torch.zeros(seg[0] + seg[1] + 64, dtype=torch.float32, device=dev)
+        self.grad_scale = 1.0
+        self._grads = [vf.enable_flat_grad(self.grad_all[:vf.flat.numel()]),
+                       rn.enable_flat_grad(self.grad_all[seg[0]:seg[0] + rn.flat.numel()]),
+                       model.density.enable_flat_grad(self.grad_all[seg[0] + seg[1]:seg[0] + seg[1] + 3])]
+        self._scratch = torch.zeros(_lib.SQNORM_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
         self._masks = [vf.trainable_mask(), rn.trainable_mask(), None]
         self._m = [torch.zeros_like(f) for f in flats]
         self._v = [torch.zeros_like(f) for f in flats]
@@ -43,8 +52,7 @@ class ArenaAdam(torch.optim.Optimizer):
         self._flats = flats
 
     def zero_grad(self, set_to_none: bool = False) -> None:      # the gradients are persistent views: always zero in place
-        for g in self._grads:
-            g.zero_()
+        self.grad_all.zero_()
 
     def _check_storage(self) -> None:
         """The arenas are re-flattened when someone moves the modules (.to(), load_state_dict(assign=True)); moments held
@@ -141,7 +149,8 @@ class ArenaAdam(torch.optim.Optimizer):
                 g0[key] = tuple(groups[0][key]) if key == "betas" else groups[0][key]
 
     def grad_norm(self) -> torch.Tensor:
-        """Global 2-norm of the gradient as clip_grad_norm_ returns it (after step(): of the unclipped gradient)."""
+        """Global 2-norm of the gradient as clip_grad_norm_ returns it (after step(): of the unclipped gradient).
+        Reproducible run to run: csrc/optim.cu sums per-block partials in a fixed order."""
         return self._sq.sqrt()
 
     @torch.no_grad()
@@ -158,14 +167,16 @@ class ArenaAdam(torch.optim.Optimizer):
         mn = 0.0 if mn is None else float(mn)
         stream = torch.cuda.current_stream(self._step.device).cuda_stream
         self._step.add_(1.0)
+        gs = float(self.grad_scale)
         if mn > 0:
+            # running statistics and padding hold zeros in the gradient tensor: the norm over all of it is the parameters'
             self._sq.zero_()
-            for g in self._grads:
-                _lib.check(L.vfnerf_sqnorm_accumulate(g.data_ptr(), g.numel(), self._sq.data_ptr(), stream), "vfnerf_sqnorm_accumulate")
+            _lib.check(L.vfnerf_sqnorm_accumulate(self.grad_all.data_ptr(), self.grad_all.numel(), gs, self._sq.data_ptr(),
+                                                  self._scratch.data_ptr(), stream), "vfnerf_sqnorm_accumulate")
         for p, g, m, v, mask in zip(self._flats, self._grads, self._m, self._v, self._masks):
             _lib.check(L.vfnerf_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _lib.ptr(mask), p.numel(),
                                           lr.data_ptr(), self._step.data_ptr(), float(b1), float(b2), float(g0["eps"]),
-                                          float(g0["weight_decay"]), mn, self._sq.data_ptr(), stream), "vfnerf_adam_step")
+                                          float(g0["weight_decay"]), mn, self._sq.data_ptr(), gs, stream), "vfnerf_adam_step")
         return None
 
 
