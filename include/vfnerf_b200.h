@@ -319,6 +319,46 @@ int vfnerf_sphere_points(int64_t n, const double* phi, const double* cos_theta, 
 int vfnerf_select_supervised(int64_t n, const float* points, const float* centroid3_host, float threshold, int mode,
                              uint8_t* flag, float* gt, void* stream);
 
+/* ---- train mode: BatchNorm batch statistics, the autograd "Jacobian", directional derivatives ---- */
+/* What render() and the VF-only call compute after model.train() (models/nerf/vector_field_nerf.py:84-101 puts both
+ * networks into training mode): every hidden layer normalises with the mean and biased variance of ITS BATCH
+ * (vector_field_network.py:177-208, rendering_network.py:62-108 with nn.BatchNorm1d in training mode) and folds them into
+ * the running statistics IN THE ARENA (momentum bn_momentum = 0.1, unbiased variance) -- hence the non-const arenas; the
+ * module's num_batches_tracked counters are the caller's to advance (VF net: +2 per render, colour net: +1).
+ * fp32 layer-wise path only (cfg.precision must be VFNERF_PREC_FP32).
+ *
+ * vfnerf_render_train_fwd: render() as in vfnerf_render_fwd plus dir_derivs [4 * n_rays * n_coarse] (optional) =
+ * NerfOutput.directional_derivtives: per-row norms of compute_directional_derivatives (vector_field_nerf.py:476-498) on the
+ * COARSE pass, the block concatenated with itself as upstream does (:305).  The Jacobian behind it is the reference's
+ * (vector_field_network.py:146-171): three reverse sweeps of output-column SUMS over the batch through the batch
+ * statistics.  The workspace always keeps what vfnerf_render_train_bwd needs.
+ * vfnerf_render_train_bwd: same contract as vfnerf_render_bwd; gradients flow through the batch statistics (exact
+ * BatchNorm-training backward).  Linear biases in front of a BatchNorm get exactly 0 (autograd: rounding noise ~1e-8). */
+int64_t vfnerf_render_train_workspace_bytes(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf,
+                                            const vfnerf_mlp_desc* rn);
+int vfnerf_render_train_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, float* vf_arena,
+                            const vfnerf_mlp_desc* rn, float* rn_arena, const float* density_params, const float* uv,
+                            const float* pose, const float* intrinsics, const float* t_vals, const float* U1,
+                            const float* U2, const float* U3, const float* z_override, const vfnerf_render_out* out,
+                            float* dir_derivs, float bn_momentum, void* workspace, int64_t workspace_bytes, void* stream);
+int vfnerf_render_train_bwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, const float* vf_arena,
+                            const vfnerf_mlp_desc* rn, const float* rn_arena, const float* density_params,
+                            const vfnerf_render_out* out, const float* d_rgb, const float* d_depth, const float* d_normals,
+                            const float* d_colors, float* vf_grad_arena, float* rn_grad_arena, float* d_density,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+/* VectorFieldNetwork.forward in training mode (vector_field_network.py:140-175), the call the trainer makes on its
+ * supervision points (train/vector_field_nerf_train.py:191,204,217): out[:, :n_out_cols] = tanh outputs,
+ * jacobian [n,9] (optional, row stride jacobian_ld) = cat(d sum(y0)/dx, d sum(y1)/dx, d sum(y2)/dx).  The workspace keeps
+ * what vfnerf_vf_train_bwd needs (same arguments as vfnerf_vf_bwd, fp32). */
+int64_t vfnerf_vf_train_workspace_bytes(const vfnerf_mlp_desc* vf, int64_t n_points, int multires);
+int vfnerf_vf_train_fwd(const vfnerf_mlp_desc* vf, float* vf_arena, int multires, int skip_layer, float bn_eps,
+                        float bn_momentum, const float* points, int64_t n_points, float* out, int64_t out_ld,
+                        int n_out_cols, float* jacobian, int64_t jacobian_ld, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+int vfnerf_vf_train_bwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires, int skip_layer, int64_t n_points,
+                        const float* out, int64_t out_ld, const float* d_out, int64_t d_ld, int n_out_cols,
+                        float* vf_grad_arena, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Test-only entry points (UMMA descriptor probes, micro-benchmarks, activation-stash read-back) are NOT part of this
  * library: they are declared in vfnerf_b200_debug.h and built into a separate libvfnerf_b200_debug.so by the tests. */
 

@@ -74,11 +74,15 @@ def test_reference_error_behaviour(model):
         VFNerfConfig(rendering="splat")
     with pytest.raises(ValueError):
         VFNerfConfig(cos_sim_weights_anneal="anneal_fine")
-    model.train()
+    model.train()          # train mode is built (csrc/mlp_train.cu) and, like everything else, CUDA-only
     try:
-        with pytest.raises(NotImplementedError):
+        with pytest.raises(RuntimeError, match="CUDA"):
             model.vector_field_network(torch.zeros(4, 3))
+        model.set_precision("bf16")
+        with pytest.raises(NotImplementedError):       # batch statistics run on the fp32 layer-wise path only
+            model.render(pose, uv, K, 0)
     finally:
+        model.set_precision("fp32")
         model.eval()
 
 

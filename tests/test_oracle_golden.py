@@ -171,3 +171,44 @@ def test_supervision_oracle_reproduces_reference_golden():
     d = (torch.from_numpy(z["border_points"]) - c).norm(dim=1)
     assert (d >= far / 2 - radius - 1e-5).all() and (d <= far / 2 + 1e-5).all()
     assert ((torch.from_numpy(z["center_points"]) - c).norm(dim=1) <= radius + 1e-6).all()
+
+
+def test_train_mode_oracle_matches_reference_golden():
+    """Train mode: batch-statistic BatchNorm, Jacobian of column sums, directional derivatives,
+    running-statistics update and gradients of the restatement against what the LIVE reference produced in model.train()
+    (tests/golden/make_golden_train.py)."""
+    case, z = U.load_golden("train_small")
+    vf0 = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w_vf.")}
+    rn0 = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w_rn.")}
+    req = lambda sd: {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)   # noqa: E731
+                      for k, v in sd.items()}
+    vf, rn = req(vf0), req(rn0)
+    dn = {"beta": torch.tensor(0.5, requires_grad=True), "scale": torch.tensor(100.0, requires_grad=True),
+          "mean": torch.tensor(0.7, requires_grad=True)}
+    out = U.O.render_train(vf, rn, dn, U.oracle_cfg(case), U.t(z, "uv"), U.t(z, "pose"), U.t(z, "K"), U.t(z, "t_vals"),
+                           U.t(z, "U1"), U.t(z, "U2"), U.t(z, "U3"))
+    assert torch.equal(out["z_vals"], U.t(z, "ref_z_vals"))
+    for key, ref in (("normals", "ref_normals"), ("rgb", "ref_rgb"), ("depth", "ref_depth"), ("colors", "ref_colors")):
+        assert (out[key].detach() - U.t(z, ref)).abs().max().item() <= 2e-4, key
+    dd, dd_ref = out["directional_derivatives"], U.t(z, "ref_dir_derivs")
+    assert dd.shape == dd_ref.shape and ((dd - dd_ref).abs().max() / dd_ref.abs().max()).item() <= 2e-4
+    for tag, after in (("after_vf.", out["vf_sd_after"]), ("after_rn.", out["rn_sd_after"])):
+        for k in z.files:
+            if k.startswith(tag):
+                ref = torch.from_numpy(z[k])
+                if "num_batches" in k:
+                    assert int(after[k[len(tag):]]) == int(ref)
+                else:
+                    assert ((after[k[len(tag):]] - ref).abs().max() / ref.abs().max()).item() <= 1e-5, k
+    w = dict(U.LOSS_W, directional_derivatives=0.05)
+    loss = U.O.vf_loss(out["rgb"], out["depth"], out["normals"].reshape(-1, 3), U.t(z, "rgb_gt"), U.t(z, "depth_gt"), w, 0.5) + \
+        0.05 * dd.mean()
+    assert abs(loss.item() - float(z["ref_loss"])) < 2e-5
+    loss.backward()
+    for prefix, sd in (("g_vf.", vf), ("g_rn.", rn)):
+        for k, v in sd.items():
+            if isinstance(v, torch.Tensor) and v.requires_grad:
+                g = z[prefix + k]
+                got = np.zeros_like(g) if v.grad is None else v.grad.numpy()
+                # (Linear biases in front of a batch-statistics BatchNorm: mathematically zero, 1e-8 noise on both sides)
+                assert np.abs(got - g).max() / max(np.abs(g).max(), 1e-4) < 2e-3, k

@@ -15,7 +15,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libvfnerf_b200.so")
-SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "optim.cu", "mc_preprocess.cu", "host_rng.cu", "supervision.cu"]
+SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "mlp_simt.cu", "mlp_train.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "optim.cu", "mc_preprocess.cu", "host_rng.cu", "supervision.cu"]
 HEADERS = ["common.cuh", "host_plan.cuh", "mlp_tc.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "vfnerf_b200.h")]
 # test-only library (UMMA probes, micro-benchmarks, stash read-back): the product sources + tc_debug.cu, compiled with
 # -DVFNERF_DEBUG_EXPORTS; built on demand by the tests (tests/conftest.py: debug_lib), never loaded by the product
@@ -95,6 +95,12 @@ PROTOTYPES = {
     "vfnerf_composite_white": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "vfnerf_sphere_points": (_I, [_L, _P, _P, _P, _D, _D, C.POINTER(C.c_float), _I, _P, _P, _P]),
     "vfnerf_select_supervised": (_I, [_L, _P, C.POINTER(C.c_float), _F, _I, _P, _P, _P]),
+    "vfnerf_render_train_workspace_bytes": (_L, [_CFG, _DESC, _DESC]),
+    "vfnerf_render_train_fwd": (_I, [_CFG, _DESC, _P, _DESC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _OUT, _P, _F, _P, _L, _P]),
+    "vfnerf_render_train_bwd": (_I, [_CFG, _DESC, _P, _DESC, _P, _P, _OUT, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "vfnerf_vf_train_workspace_bytes": (_L, [_DESC, _L, _I]),
+    "vfnerf_vf_train_fwd": (_I, [_DESC, _P, _I, _I, _F, _F, _P, _L, _P, _L, _I, _P, _L, _P, _L, _P]),
+    "vfnerf_vf_train_bwd": (_I, [_DESC, _P, _I, _I, _L, _P, _L, _P, _L, _I, _P, _I, _P, _L, _P]),
 }
 
 DEBUG_PROTOTYPES = {

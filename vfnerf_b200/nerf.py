@@ -20,6 +20,10 @@ from .output import NerfOutput
 from .samplers import RangeFineSampler, UniformSampler, cpu_generator_rand_
 
 
+def c_is_nerf(config) -> bool:
+    return getattr(config, "rendering", "volsdf") == "nerf"
+
+
 class VectorFieldNerf:
     def __init__(self, config, precision: str = "fp32") -> None:
         """:param config: a VFNerfConfig (ours or the reference's own dataclass; only attributes are read).
@@ -246,12 +250,21 @@ class VectorFieldNerf:
             # vector_field_nerf.py:274-277 reads rgb_values_coarse before assignment
             raise UnboundLocalError("white=True is broken in the reference (SURVEY.md fact 2); call "
                                     "model.enable_reference_fix('white_background') for rgb += 1 - sum(weights)")
-        if self.vector_field_network.training or self.rendering_network.training:
-            # also reached with config.numerical_jacobian: train() then leaves the VF net in eval but still switches the
-            # colour net to batch statistics and asks for numerical directional derivatives (vector_field_nerf.py:84-101)
-            raise NotImplementedError("render() with a network in train() mode (batch-statistic BatchNorm, Jacobian / "
-                                      "directional derivatives) is SURVEY.md §8(f) rank 1; call model.eval() as the "
-                                      "reference trainer does (train/vector_field_nerf_train.py:140-141)")
+        train_mode = self.vector_field_network.training and self.rendering_network.training
+        if self.vector_field_network.training != self.rendering_network.training or \
+                (train_mode and getattr(self.config, "numerical_jacobian", False)):
+            # config.numerical_jacobian: train() leaves the VF net in eval but switches the colour net to batch statistics
+            # and asks for finite-difference directional derivatives (vector_field_nerf.py:84-101,262-263)
+            raise NotImplementedError("render() with only one network in train() mode / numerical_jacobian=True is not "
+                                      "built; model.train() (both networks, autograd Jacobian) and model.eval() are")
+        if train_mode:
+            if self.precision != "fp32":
+                raise NotImplementedError("train() mode (batch-statistic BatchNorm, Jacobian, directional derivatives) "
+                                          "runs on the fp32 layer-wise path: use precision='fp32', or model.eval() like "
+                                          "the reference trainer does when the directional-derivative weight is 0 "
+                                          "(train/vector_field_nerf_train.py:140-141)")
+            if white or c_is_nerf(self.config):
+                raise NotImplementedError("the white-background / nerf-rendering fixes are eval-mode options")
         if not getattr(self.config.rendering_net_config, "detach_normals", True):
             raise NotImplementedError("rendering_net_config.detach_normals=False: the backward kernels implement the shipped "
                                       "detach (rendering_network.py:76-77); gradients through the colour net's normal "
@@ -264,7 +277,8 @@ class VectorFieldNerf:
         if pose.shape[0] != R or intrinsics.shape[0] != R:
             raise ValueError("pose, pixels and intrinsics must have one row per ray")
         quat = pose.dim() == 2 and pose.shape[1] == 7
-        if self.graph_replay and z_vals_override is None and R > 0 and not white and not torch.is_grad_enabled():
+        if self.graph_replay and z_vals_override is None and R > 0 and not white and not torch.is_grad_enabled() \
+                and not train_mode:
             return self._render_replay(pose, pixels, intrinsics, quat, draws)
         cfg = self._render_cfg(R, quat, white)
         # host-side draws in the reference's order (ray_sampler.py:138, 292, 297), then H2D
@@ -294,7 +308,7 @@ class VectorFieldNerf:
         call = ops.RenderCall(cfg, self.vector_field_network, self.rendering_network, self.density,
                               pixels, pose, intrinsics, dev_(t_vals), dev_(U1), dev_(U2), dev_(U3),
                               z_override=dev_(z_vals_override), want_extras=True,
-                              want_ray_dirs=self.return_ray_dirs)
+                              want_ray_dirs=self.return_ray_dirs, train=train_mode)
         res = ops.render_call(call)
         rgb, depth, normals, colors, points, z_vals = res[:6]
         ray_dirs = res[6] if len(res) > 6 else None
@@ -302,7 +316,8 @@ class VectorFieldNerf:
         return NerfOutput(points_coarse=points, points_fine=None, coarse_normals=normals,
                           coarse_rgb_values=rgb, coarse_depth_map=depth, fine_normals=None,
                           fine_rgb_values=None, fine_depth_map=None, z_vals=z_vals,
-                          directional_derivtives=None, ray_dirs=ray_dirs, coarse_colors=colors,
+                          directional_derivtives=call.extras.get("directional_derivatives"), ray_dirs=ray_dirs,
+                          coarse_colors=colors,
                           weights=call.extras.get("weights"))
 
 

@@ -177,8 +177,9 @@ def _make_layers(dims: Sequence[Tuple[int, int]], batch_norm: bool, weight_norm:
 class VectorFieldNetwork(_ArenaOwner, nn.Module):
     """Drop-in for models/vector_field/vector_field_network.py:14-208 (eval-mode forward).
 
-    ``forward(points[P,3]) -> [P, 3 + feature_vector_dims]`` = tanh([v, feat]).  Training mode (BatchNorm
-    batch statistics + autograd Jacobian, :140-175) is SURVEY.md §8(f) rank 1 and raises.
+    ``forward(points[P,3]) -> [P, 3 + feature_vector_dims]`` = tanh([v, feat]); in train() mode (BatchNorm batch
+    statistics, :140-175) ``[P, 3 + feature_vector_dims + 9]`` with the flat autograd "Jacobian" appended
+    (csrc/mlp_train.cu, fp32 layer-wise path).
     """
 
     def __init__(self, config) -> None:
@@ -229,13 +230,10 @@ class VectorFieldNetwork(_ArenaOwner, nn.Module):
         return out[:, :3], out[:, 3:]
 
     def forward(self, points: torch.Tensor) -> torch.Tensor:
+        from .ops import vf_query, vf_query_train
         if self.training:
-            raise NotImplementedError(
-                "VectorFieldNetwork in train() mode (BatchNorm batch statistics + Jacobian, "
-                "vector_field_network.py:140-175) is not on the accelerated path; the reference trainer "
-                "runs the nets in eval() whenever the directional-derivative weight is 0 "
-                "(train/vector_field_nerf_train.py:140-141)")
-        from .ops import vf_query
+            # BatchNorm batch statistics + the autograd "Jacobian" (vector_field_network.py:140-175): [P, 3 + feat + 9]
+            return vf_query_train(self, points)
         return vf_query(self, points)
 
 

@@ -118,6 +118,86 @@ def vf_query(net, points: torch.Tensor, n_cols: Optional[int] = None) -> torch.T
     return _VFQuery.apply(net, points, n_cols, need_bwd, *params)
 
 
+BN_MOMENTUM = 0.1          # nn.BatchNorm1d default, vector_field_network.py:60 / rendering_network.py:52
+
+
+def _bump_batches_tracked(net, times: int = 1) -> None:
+    """nn.BatchNorm1d.forward in training mode advances num_batches_tracked; the C side updates the running statistics in
+    the arena, the int64 counters (not arena members) are advanced here with one foreach launch."""
+    counters = [layer[1].num_batches_tracked for layer in net.layers
+                if isinstance(layer, torch.nn.Sequential) and layer[1].num_batches_tracked is not None]
+    if counters:
+        torch._foreach_add_(counters, times)
+
+
+class _VFQueryTrain(torch.autograd.Function):
+    """VectorFieldNetwork.forward in train() mode (vector_field_network.py:140-175): [y, flat "Jacobian"]."""
+
+    @staticmethod
+    def forward(ctx, net, points, need_bwd, *params):
+        L = _lib.lib()
+        ar = net.arena()
+        dev = points.device
+        P = points.shape[0]
+        Do = ar.desc.out_dim[ar.desc.n_layers - 1]
+        if net.precision != "fp32":
+            raise NotImplementedError("train() mode (batch-statistic BatchNorm + Jacobian) runs on the fp32 layer-wise path: "
+                                      "build the model with precision='fp32'")
+        nbytes = L.vfnerf_vf_train_workspace_bytes(C.byref(ar.desc), P, net.multires)
+        if nbytes < 0:
+            _lib.check(1, "vfnerf_vf_train_workspace_bytes")
+        ws = _workspace(nbytes, dev)
+        out = torch.empty(P, Do + 9, dtype=torch.float32, device=dev)
+        with _on_device(dev):
+            _lib.check(L.vfnerf_vf_train_fwd(C.byref(ar.desc), ar.flat.data_ptr(), net.multires, net.skip_layer, 1e-5,
+                                             BN_MOMENTUM, points.data_ptr(), P, out.data_ptr(), Do + 9, Do,
+                                             out.data_ptr() + 4 * Do, Do + 9, ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
+                       "vfnerf_vf_train_fwd")
+        _bump_batches_tracked(net)
+        ctx.net, ctx.ws, ctx.P, ctx.Do = net, (ws if need_bwd else None), P, Do
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        L = _lib.lib()
+        net = ctx.net
+        ar = net.arena()
+        (out,) = ctx.saved_tensors
+        dev = out.device
+        Do = ctx.Do
+        if ctx.ws is None:
+            raise RuntimeError("backward through a train-mode VF query made under no_grad")
+        # gradients enter through the tanh outputs; the Jacobian columns carry none on any path of the reference (the
+        # trainer slices [:, :3], render() consumes the Jacobian under no_grad)
+        d_out = d_out.contiguous().float()
+        grad = torch.empty(ar.desc.arena_floats, dtype=torch.float32, device=dev)
+        with _on_device(dev):
+            _lib.check(L.vfnerf_vf_train_bwd(C.byref(ar.desc), ar.flat.data_ptr(), net.multires, net.skip_layer, ctx.P,
+                                             out.data_ptr(), Do + 9, d_out.data_ptr(), Do + 9, Do, grad.data_ptr(), 0,
+                                             ctx.ws.data_ptr(), ctx.ws.numel(), _stream_ptr(dev)), "vfnerf_vf_train_bwd")
+        ctx.ws = None
+        if ar.grad_flat is not None:
+            ar.grad_flat.add_(grad)
+            return (None, None, None) + (None,) * len(ar.params())
+        return (None, None, None) + tuple(ar.grad_views(grad))
+
+
+def vf_query_train(net, points: torch.Tensor) -> torch.Tensor:
+    """[P, 3 + feat + 9]: tanh outputs followed by cat(d sum(y0)/dx, d sum(y1)/dx, d sum(y2)/dx), the train-mode return
+    value of VectorFieldNetwork.forward (vector_field_network.py:146-173).  Normalises with the statistics of THIS batch
+    and folds them into the running statistics."""
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise ValueError(f"points must be [P,3], got {tuple(points.shape)}")
+    points = _require_cuda("points", points.detach())
+    ar = net.arena()
+    if ar.flat.device != points.device:
+        raise RuntimeError(f"network parameters are on {ar.flat.device}, points on {points.device}")
+    params = ar.params()
+    need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _VFQueryTrain.apply(net, points, need_bwd, *params)
+
+
 def mlp_points(vf_net, rn_net, points: torch.Tensor, ray_dirs: torch.Tensor, samples_per_ray: int,
                workspace: Optional[torch.Tensor] = None, repack: bool = True):
     """VF vectors and colours at ``points[P,3]`` seen along ``ray_dirs[P/samples_per_ray,3]`` -- the two-MLP evaluation
@@ -177,13 +257,14 @@ class RenderCall:
     """Everything one render() call needs besides the parameters (built by nerf.VectorFieldNerf)."""
 
     def __init__(self, cfg: _lib.RenderCfg, vf_net, rn_net, density, uv, pose, intrinsics, t_vals, U1, U2, U3,
-                 z_override=None, want_extras: bool = False, want_ray_dirs: bool = True):
+                 z_override=None, want_extras: bool = False, want_ray_dirs: bool = True, train: bool = False):
         self.cfg, self.vf_net, self.rn_net, self.density = cfg, vf_net, rn_net, density
         self.uv, self.pose, self.intrinsics, self.t_vals = uv, pose, intrinsics, t_vals
         self.U1, self.U2, self.U3, self.z_override = U1, U2, U3, z_override
         self.want_extras, self.want_ray_dirs = want_extras, want_ray_dirs
         self.extras = {}
         self.need_bwd = False
+        self.train = train          # batch-statistic BatchNorm + directional derivatives (csrc/mlp_train.cu)
 
 
 class _Render(torch.autograd.Function):
@@ -201,7 +282,10 @@ class _Render(torch.autograd.Function):
             cfg.flags |= _lib.FLAG_RECOMPUTE_COARSE
         if need_bwd and cfg.precision not in (_lib.PREC_FP32, _lib.PREC_BF16):
             raise RuntimeError("training (backward) runs on precision 'fp32' or 'bf16'")
-        nbytes = L.vfnerf_render_workspace_bytes(C.byref(cfg), C.byref(vf_ar.desc), C.byref(rn_ar.desc), int(need_bwd))
+        if call.train:
+            nbytes = L.vfnerf_render_train_workspace_bytes(C.byref(cfg), C.byref(vf_ar.desc), C.byref(rn_ar.desc))
+        else:
+            nbytes = L.vfnerf_render_workspace_bytes(C.byref(cfg), C.byref(vf_ar.desc), C.byref(rn_ar.desc), int(need_bwd))
         if nbytes < 0:
             _lib.check(1, "vfnerf_render_workspace_bytes")
         ws = _workspace(nbytes, dev)
@@ -219,14 +303,26 @@ class _Render(torch.autograd.Function):
         out = _lib.RenderOut(points.data_ptr(), normals.data_ptr(), rgb.data_ptr(), depth.data_ptr(),
                              z_vals.data_ptr(), _lib.ptr(ray_dirs), colors.data_ptr(), weights.data_ptr(),
                              _lib.ptr(z_c), _lib.ptr(w_c))
+        dd = None
         with _on_device(dev):
-            _lib.check(L.vfnerf_render_fwd(
-                C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),
-                dflat.data_ptr(), call.uv.data_ptr(), call.pose.data_ptr(), call.intrinsics.data_ptr(),
-                call.t_vals.data_ptr(), _lib.ptr(call.U1), _lib.ptr(call.U2), _lib.ptr(call.U3),
-                _lib.ptr(call.z_override), C.byref(out), ws.data_ptr(), ws.numel(), int(need_bwd), _stream_ptr(dev)),
-                "vfnerf_render_fwd")
-        call.extras = dict(weights=weights, z_coarse=z_c, weights_coarse=w_c)
+            if call.train:
+                dd = torch.empty(4 * R * cfg.n_coarse, **f32)
+                _lib.check(L.vfnerf_render_train_fwd(
+                    C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),
+                    dflat.data_ptr(), call.uv.data_ptr(), call.pose.data_ptr(), call.intrinsics.data_ptr(),
+                    call.t_vals.data_ptr(), _lib.ptr(call.U1), _lib.ptr(call.U2), _lib.ptr(call.U3),
+                    _lib.ptr(call.z_override), C.byref(out), dd.data_ptr(), BN_MOMENTUM, ws.data_ptr(), ws.numel(),
+                    _stream_ptr(dev)), "vfnerf_render_train_fwd")
+                _bump_batches_tracked(call.vf_net, 2)          # coarse pass + merged pass
+                _bump_batches_tracked(call.rn_net, 1)
+            else:
+                _lib.check(L.vfnerf_render_fwd(
+                    C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),
+                    dflat.data_ptr(), call.uv.data_ptr(), call.pose.data_ptr(), call.intrinsics.data_ptr(),
+                    call.t_vals.data_ptr(), _lib.ptr(call.U1), _lib.ptr(call.U2), _lib.ptr(call.U3),
+                    _lib.ptr(call.z_override), C.byref(out), ws.data_ptr(), ws.numel(), int(need_bwd), _stream_ptr(dev)),
+                    "vfnerf_render_fwd")
+        call.extras = dict(weights=weights, z_coarse=z_c, weights_coarse=w_c, directional_derivatives=dd)
         if need_bwd:
             ctx.call, ctx.ws, ctx.out_struct = call, ws, out
             ctx.keep = (points, z_vals, colors, normals, weights, ray_dirs, z_c, w_c)
@@ -256,12 +352,13 @@ class _Render(torch.autograd.Function):
         g_vf = torch.empty(vf_ar.desc.arena_floats, **f32)
         g_rn = torch.empty(rn_ar.desc.arena_floats, **f32)
         g_d = torch.empty(3, **f32)
+        bwd = L.vfnerf_render_train_bwd if call.train else L.vfnerf_render_bwd
         with _on_device(dev):
-            _lib.check(L.vfnerf_render_bwd(
+            _lib.check(bwd(
                 C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),
                 dflat.data_ptr(), C.byref(ctx.out_struct), d_rgb.data_ptr(), d_depth.data_ptr(), _lib.ptr(d_normals),
                 _lib.ptr(d_colors), g_vf.data_ptr(), g_rn.data_ptr(), g_d.data_ptr(), ctx.ws.data_ptr(),
-                ctx.ws.numel(), _stream_ptr(dev)), "vfnerf_render_bwd")
+                ctx.ws.numel(), _stream_ptr(dev)), "vfnerf_render_train_bwd" if call.train else "vfnerf_render_bwd")
         if DEBUG_KEEP_WORKSPACE:
             _debug_last.update(cfg=cfg, ws=ctx.ws, vf=vf_ar, rn=rn_ar)
         ctx.ws = ctx.keep = None
