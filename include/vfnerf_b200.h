@@ -36,6 +36,11 @@ extern "C" {
  *             cumprod) with the arguments in the function's own order (upstream passes (z_vals, density) swapped). */
 #define VFNERF_FLAG_WHITE_BG 2
 #define VFNERF_FLAG_NERF_WEIGHTS 4
+/* forward-only calls on the tensor-core paths: the workspace already holds the packed weight images of these arenas (an
+ * earlier vfnerf_render_fwd with the same workspace, cfg and network descriptions, parameters unchanged since) -- skip
+ * the re-tiling of the weights (2 launches, ~30 us).  Chunked evaluation loops render hundreds of 1024-ray chunks with
+ * one set of weights (evaluation/methods.py:510-530). */
+#define VFNERF_FLAG_WEIGHTS_PACKED 8
 #define VFNERF_MAX_SAMPLES 256 /* samples per ray (coarse + fine) handled by one warp */
 
 /* precision of the two MLPs */

@@ -37,6 +37,18 @@ def test_replay_equals_eager_call(built_lib, precision):
         rep2 = model.render(pose, uv, K, 0, draws=draws)
         assert torch.equal(rep2.coarse_rgb_values, eager2.coarse_rgb_values)
         assert not torch.equal(eager2.coarse_rgb_values, eager.coarse_rgb_values)
+        # ... and only then: with unchanged parameters the replay reuses the packed weight images (second capture)
+        g = next(iter(v for k, v in model._graphs.items() if k[0] == uv.shape[0]))
+        rep3 = model.render(pose, uv, K, 0, draws=draws)
+        assert torch.equal(rep3.coarse_rgb_values, eager2.coarse_rgb_values)
+        if precision != "fp32":
+            assert rep3.coarse_rgb_values.data_ptr() == g.out_packed.coarse_rgb_values.data_ptr()
+        # writes through .data are invisible to the version counters: the documented way out is invalidate_replay()
+        for p in model.rendering_network.parameters():
+            p.data.mul_(2.0)
+        model.invalidate_replay()
+        rep4 = model.render(pose, uv, K, 0, draws=draws)
+        assert torch.equal(rep4.coarse_rgb_values, eager.coarse_rgb_values)
 
 
 def test_replay_draws_follow_the_cpu_generator(built_lib):

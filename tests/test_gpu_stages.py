@@ -163,3 +163,48 @@ def test_sample_limit_is_an_error_not_a_crash(built_lib):
     st = built_lib.vfnerf_fine_sample(1, 200, 100, 0.0, 1.0, 0.3, 0, e.data_ptr(), e.data_ptr(), e.data_ptr(), e.data_ptr(),
                                       e.data_ptr(), e.data_ptr(), e.data_ptr(), e.data_ptr(), _stream())
     assert st != 0 and b"exceeds" in built_lib.vfnerf_last_error()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_fused_per_ray_kernels_equal_the_stage_kernels(built_lib, precision):
+    """render() runs the per-ray stages as three fused launches (csrc/render_fused.cu: ray head, coarse-to-fine, tail);
+    they share their device code with the stage entry points, so feeding the stage kernels render()'s own intermediate
+    results must reproduce its outputs: weights bit for bit, the composite to the last ulp of its FMA chain."""
+    case, z = U.load_golden("small_perturb" if precision == "fp32" else "full_perturb")
+    model = U.make_model(case, U.case_state(case, z), DEV, precision=precision)
+    uv, pose, K = (U.t(z, k).to(DEV) for k in ("uv", "pose", "K"))
+    draws = tuple(U.t(z, k).to(DEV) for k in ("U1", "U2", "U3"))
+    with torch.no_grad():
+        out = model.render(pose, uv, K, 0, draws=draws)
+    ex = model.last_extras
+    R, N = out.z_vals.shape
+    Nc = case["n_coarse"]
+    # a1 + a2: the head's coarse z values against the two stage kernels
+    d, rd, cam = (torch.empty(R, 3, device=DEV) for _ in range(3))
+    _lib.check(built_lib.vfnerf_ray_geometry(R, 0, uv.data_ptr(), pose.data_ptr(), K.data_ptr(), d.data_ptr(), rd.data_ptr(),
+                                             cam.data_ptr(), _stream()), "ray_geometry")
+    zc, pc = torch.empty(R, Nc, device=DEV), torch.empty(R, Nc, 3, device=DEV)
+    t_vals = U.t(z, "t_vals").to(DEV)
+    _lib.check(built_lib.vfnerf_coarse_sample(R, Nc, case["near"], case["far"], 1, t_vals.data_ptr(), draws[0].data_ptr(),
+                                              d.data_ptr(), cam.data_ptr(), zc.data_ptr(), pc.data_ptr(), _stream()), "coarse")
+    assert torch.equal(zc, ex["z_coarse"])
+    # a7: the fine sampler stage on render()'s coarse weights reproduces the merged z values and points
+    zf, pf = torch.empty(R, N, device=DEV), torch.empty(R, N, 3, device=DEV)
+    _lib.check(built_lib.vfnerf_fine_sample(R, Nc, N - Nc, case["near"], case["far"], case["fine_range"], 1, zc.data_ptr(),
+                                            ex["weights_coarse"].data_ptr(), draws[1].data_ptr(), draws[2].data_ptr(),
+                                            d.data_ptr(), cam.data_ptr(), zf.data_ptr(), pf.data_ptr(), _stream()), "fine")
+    assert torch.equal(zf, out.z_vals) and torch.equal(pf, out.points_coarse)
+    # a4-a6: the density stage on render()'s merged vectors reproduces its weights
+    cfg = model._render_cfg(R, False)
+    w = torch.empty(R, N, device=DEV)
+    nrm = out.coarse_normals.contiguous()
+    _lib.check(built_lib.vfnerf_density_weights(C.byref(cfg), N, model.density.flat().data_ptr(), nrm.data_ptr(), 3,
+                                                rd.data_ptr(), out.z_vals.data_ptr(), None, None, w.data_ptr(), _stream()),
+               "density_weights")
+    assert torch.equal(w, ex["weights"])
+    # a9
+    rgb, dep = torch.empty(R, 3, device=DEV), torch.empty(R, 1, device=DEV)
+    _lib.check(built_lib.vfnerf_composite(R, N, w.data_ptr(), out.coarse_colors.data_ptr(), out.z_vals.data_ptr(),
+                                          rgb.data_ptr(), dep.data_ptr(), _stream()), "composite")
+    assert (rgb - out.coarse_rgb_values).abs().max().item() <= 1e-6
+    assert (dep - out.coarse_depth_map).abs().max().item() <= 1e-6

@@ -15,8 +15,8 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libvfnerf_b200.so")
-SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "mlp_simt.cu", "mlp_train.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "optim.cu", "mc_preprocess.cu", "host_rng.cu", "supervision.cu"]
-HEADERS = ["common.cuh", "host_plan.cuh", "mlp_tc.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "vfnerf_b200.h")]
+SOURCES = ["api.cu", "geometry_sampler.cu", "density_composite.cu", "render_fused.cu", "mlp_simt.cu", "mlp_train.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "loss.cu", "optim.cu", "mc_preprocess.cu", "host_rng.cu", "supervision.cu"]
+HEADERS = ["common.cuh", "host_plan.cuh", "ray_ops.cuh", "mlp_tc.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "vfnerf_b200.h")]
 # test-only library (UMMA probes, micro-benchmarks, stash read-back): the product sources + tc_debug.cu, compiled with
 # -DVFNERF_DEBUG_EXPORTS; built on demand by the tests (tests/conftest.py: debug_lib), never loaded by the product
 DEBUG_LIB_PATH = os.path.join(HERE, "libvfnerf_b200_debug.so")
@@ -29,7 +29,7 @@ SQNORM_SCRATCH_FLOATS = 1024
 MAX_LAYERS = 16
 MAX_SAMPLES = 256
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
-FLAG_RECOMPUTE_COARSE, FLAG_WHITE_BG, FLAG_NERF_WEIGHTS = 1, 2, 4
+FLAG_RECOMPUTE_COARSE, FLAG_WHITE_BG, FLAG_NERF_WEIGHTS, FLAG_WEIGHTS_PACKED = 1, 2, 4, 8
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 
 

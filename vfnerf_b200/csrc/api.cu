@@ -257,9 +257,9 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
   float* z_c = out->z_coarse ? out->z_coarse : p.z_c;
   float* w_c = out->weights_coarse ? out->weights_coarse : p.w_c;
 
-  if (int e = launch_ray_geometry(p.R, cfg->pose_is_quat, uv, pose, intrinsics, p.directions, p.ray_dirs, p.cam_loc, s)) return e;
-  if (int e = launch_coarse_sample(p.R, p.Nc, cfg->near_, cfg->far_, cfg->perturb, t_vals, U1, p.directions,
-                                   p.cam_loc, z_c, p.pts_c, s)) return e;
+  // a1 + a2 in one launch (render_fused.cu)
+  if (int e = launch_ray_head(p.R, cfg->pose_is_quat, uv, pose, intrinsics, p.Nc, cfg->near_, cfg->far_, cfg->perturb, t_vals,
+                              U1, p.directions, p.ray_dirs, p.cam_loc, z_c, p.pts_c, s)) return e;
 
   if (cfg->precision == VFNERF_PREC_FP32) {
     if (int e = launch_fold_bn(*vf, vf_arena, cfg->bn_eps, p.vf.scale, p.vf.shift, s)) return e;
@@ -270,7 +270,8 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
       if (int e = vf_forward_fp32(*vf, vf_arena, p.vf, cfg->skip_layer, p.emb, p.Pc, p.normals_c, 3, 3, s)) return e;
     }
   } else {
-    if (int e = tc_prepare(*vf, vf_arena, rn, rn_arena, cfg->bn_eps, p.tc, s)) return e;
+    if (!(cfg->flags & VFNERF_FLAG_WEIGHTS_PACKED) || keep_for_backward)
+      if (int e = tc_prepare(*vf, vf_arena, rn, rn_arena, cfg->bn_eps, p.tc, s)) return e;
     if (p.reuse_coarse) {
       // both MLPs on the coarse points now: the merged pass moves these results instead of recomputing them
       if (int e = tc_forward(p.tc, keep_for_backward ? TC_MODE_RENDER_STASH : TC_MODE_RENDER, p.pts_c, nullptr, 0, 0, p.Pc,
@@ -280,15 +281,19 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
                              nullptr, 0, nullptr, s)) return e;
     }
   }
+  // ---- coarse weights -> argmax -> fine candidates -> merged, sorted z values and points (vector_field_nerf.py:266-287),
+  // one launch; a prescribed z (parity protocol) only needs its points
   if (!z_override) {
-    if (int e = launch_density_weights(*cfg, p.R, p.Nc, density_params, p.normals_c, 3, p.ray_dirs, z_c,
-                                       nullptr, nullptr, w_c, s)) return e;
+    if (int e = launch_coarse_to_fine(*cfg, p.R, p.Nc, p.Nf, density_params, p.normals_c, 3, p.ray_dirs, z_c, U2, U3,
+                                      p.directions, p.cam_loc, w_c, out->z_vals, out->points,
+                                      p.reuse_coarse ? p.src : nullptr, p.reuse_coarse ? p.pts_f : nullptr, s)) return e;
+  } else {
+    if (int e = launch_fine_sample(p.R, p.Nc, p.Nf, cfg->fine_near_, cfg->fine_far_, cfg->fine_range, cfg->perturb, z_c, w_c,
+                                   U2, U3, z_override, p.directions, p.cam_loc, out->z_vals, out->points, nullptr, nullptr,
+                                   s)) return e;
   }
-  // ---- fine sampling: merged, sorted z values and points (vector_field_nerf.py:284-287)
-  if (int e = launch_fine_sample(p.R, p.Nc, p.Nf, cfg->fine_near_, cfg->fine_far_, cfg->fine_range, cfg->perturb, z_c, w_c,
-                                 U2, U3, z_override, p.directions, p.cam_loc, out->z_vals, out->points,
-                                 p.reuse_coarse ? p.src : nullptr, p.reuse_coarse ? p.pts_f : nullptr, s)) return e;
   // ---- merged pass
+  const int white = (cfg->flags & VFNERF_FLAG_WHITE_BG) ? 1 : 0;
   if (cfg->precision == VFNERF_PREC_FP32) {
     if (int e = launch_color_input_head(out->points, p.ray_dirs, p.R, p.N, cfg->multires_view, p.cin, p.cin_ld,
                                         out->ray_dirs_rep, s)) return e;
@@ -296,32 +301,27 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
     if (int e = vf_embed_fp32(*vf, p.vf, cfg->multires, cfg->skip_layer, out->points, p.P, p.emb, s)) return e;
     if (int e = vf_forward_fp32(*vf, vf_arena, p.vf, cfg->skip_layer, p.emb, p.P, vf_out, p.cin_ld, 3 + p.F, s)) return e;
     if (int e = launch_copy_cols(vf_out, p.cin_ld, out->normals, 3, p.P, 3, s)) return e;
-    if (int e = launch_density_weights(*cfg, p.R, p.N, density_params, vf_out, p.cin_ld, p.ray_dirs, out->z_vals,
-                                       nullptr, nullptr, weights, s)) return e;
     if (int e = rn_forward_fp32(*rn, rn_arena, p.rn, p.cin, p.cin_ld, p.P, out->colors, s)) return e;
-  } else {
-    // one fused tcgen05 launch: VF MLP -> normals, colour MLP -> colours (features stay on chip)
-    if (out->ray_dirs_rep)
-      if (int e = launch_color_input_head(out->points, p.ray_dirs, p.R, p.N, cfg->multires_view, nullptr, 0,
-                                          out->ray_dirs_rep, s)) return e;
-    if (p.reuse_coarse) {
-      // the fine candidates are the only points not evaluated yet (the merged coarse points carry the same bits as
-      // the coarse sweep's, and the fused chain is a pure per-point function): evaluate them, then merge by `src`
-      if (int e = tc_forward(p.tc, keep_for_backward ? TC_MODE_RENDER_STASH : TC_MODE_RENDER, p.pts_f, nullptr, 0, 0,
-                             (int64_t)p.R * p.Nf, p.ray_dirs, p.Nf, p.normals_f, 3, nullptr, 0, p.colors_f, s,
-                             keep_for_backward ? p.Pc / 128 : 0)) return e;
-      if (int e = launch_merge_samples(p.R, p.Nc, p.Nf, p.src, p.normals_c, p.normals_f, out->normals, p.colors_c,
-                                       p.colors_f, out->colors, s)) return e;
-    } else {
-      if (int e = tc_forward(p.tc, keep_for_backward ? TC_MODE_RENDER_STASH : TC_MODE_RENDER, out->points, nullptr, 0, 0, p.P,
-                             p.ray_dirs, p.N, out->normals, 3, nullptr, 0, out->colors, s)) return e;
-    }
-    if (int e = launch_density_weights(*cfg, p.R, p.N, density_params, out->normals, 3, p.ray_dirs, out->z_vals,
-                                       nullptr, nullptr, weights, s)) return e;
+    // density -> weights -> composite in one launch
+    return launch_render_tail(*cfg, p.R, p.N, p.Nc, density_params, nullptr, vf_out, p.cin_ld, out->colors, p.ray_dirs,
+                              out->z_vals, nullptr, nullptr, weights, out->rgb, out->depth, nullptr, white, s);
   }
-  if (int e = launch_composite(p.R, p.N, weights, out->colors, out->z_vals, out->rgb, out->depth, s,
-                               (cfg->flags & VFNERF_FLAG_WHITE_BG) ? 1 : 0)) return e;
-  return 0;
+  // one fused tcgen05 launch: VF MLP -> normals, colour MLP -> colours (features stay on chip)
+  if (p.reuse_coarse) {
+    // the fine candidates are the only points not evaluated yet (the merged coarse points carry the same bits as
+    // the coarse sweep's, and the fused chain is a pure per-point function): evaluate them, then one launch gathers the
+    // per-candidate results into sample order by `src`, forms the weights and composites
+    if (int e = tc_forward(p.tc, keep_for_backward ? TC_MODE_RENDER_STASH : TC_MODE_RENDER, p.pts_f, nullptr, 0, 0,
+                           (int64_t)p.R * p.Nf, p.ray_dirs, p.Nf, p.normals_f, 3, nullptr, 0, p.colors_f, s,
+                           keep_for_backward ? p.Pc / 128 : 0)) return e;
+    return launch_render_tail(*cfg, p.R, p.N, p.Nc, density_params, p.src, p.normals_cf, 3, p.colors_cf, p.ray_dirs,
+                              out->z_vals, out->normals, out->colors, weights, out->rgb, out->depth, out->ray_dirs_rep,
+                              white, s);
+  }
+  if (int e = tc_forward(p.tc, keep_for_backward ? TC_MODE_RENDER_STASH : TC_MODE_RENDER, out->points, nullptr, 0, 0, p.P,
+                         p.ray_dirs, p.N, out->normals, 3, nullptr, 0, out->colors, s)) return e;
+  return launch_render_tail(*cfg, p.R, p.N, p.Nc, density_params, nullptr, out->normals, 3, out->colors, p.ray_dirs,
+                            out->z_vals, nullptr, nullptr, weights, out->rgb, out->depth, out->ray_dirs_rep, white, s);
 }
 
 int vfnerf_render_bwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, const float* vf_arena,

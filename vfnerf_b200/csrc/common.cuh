@@ -117,6 +117,19 @@ int launch_mc_emit(const float* pred, int N, const uint8_t* keep, const int64_t*
 
 int launch_smooth_vf(const float* in, float* tmp, float* out, int N, int k, const float* w_host, cudaStream_t s);
 
+// render_fused.cu: the per-ray stages fused around the MLP launches (same device code as the stage kernels)
+int launch_ray_head(int n_rays, int pose_is_quat, const float* uv, const float* pose, const float* K, int n_coarse,
+                    double near_, double far_, int perturb, const float* t_vals, const float* U1, float* directions,
+                    float* ray_dirs, float* cam_loc, float* z, float* points, cudaStream_t s);
+int launch_coarse_to_fine(const vfnerf_render_cfg& cfg, int n_rays, int n_coarse, int n_fine, const float* density_params,
+                          const float* normals_c, int64_t normals_ld, const float* ray_dirs, const float* z_c,
+                          const float* U2, const float* U3, const float* directions, const float* cam_loc, float* w_c,
+                          float* z, float* points, uint8_t* src, float* points_fine, cudaStream_t s);
+int launch_render_tail(const vfnerf_render_cfg& cfg, int n_rays, int n_samples, int n_coarse, const float* density_params,
+                       const uint8_t* src, const float* normals, int64_t normals_ld, const float* colors,
+                       const float* ray_dirs, const float* z, float* out_normals, float* out_colors, float* weights,
+                       float* rgb, float* depth, float* rep_dirs, int white, cudaStream_t s);
+
 // density_composite.cu
 int launch_density_weights(const vfnerf_render_cfg& cfg, int n_rays, int n_samples,
                            const float* density_params, const float* normals, int64_t normals_ld,

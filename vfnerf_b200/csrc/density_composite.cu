@@ -5,112 +5,9 @@
 // shared-memory stencil; transmittance is a chunked warp scan; all sums are warp shuffles.
 // HBM-bound: forward reads 12N+4N bytes/ray and writes 4N..12N; nothing is re-read.
 #include "common.cuh"
+#include "ray_ops.cuh"
 
 namespace vfn {
-
-constexpr int kRayWarps = 4;
-constexpr int kMaxPerLane = VFNERF_MAX_SAMPLES / 32;  // 8
-constexpr int kUS = 4;   // floats per staged unit vector (x, y, z, pad): one LDS.128 per stencil partner
-
-struct Laplace {
-  float beta, scale, mean;   // effective (clamped) parameters
-  float L0, Lp0, Lb0;        // cdf, d/dx and d/dbeta at the cutoff x0 = -0.5
-  __device__ __forceinline__ float cdf(float x) const {
-    float d = x - mean;
-    float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-    return scale * (0.5f + 0.5f * sg * (1.f - expf(-fabsf(d) / beta)));
-  }
-  __device__ __forceinline__ float dcdf_dx(float x) const {   // = -dcdf/dmean
-    return scale * 0.5f * expf(-fabsf(x - mean) / beta) / beta;
-  }
-  __device__ __forceinline__ float dcdf_dbeta(float x) const {
-    float d = x - mean, a = fabsf(d);
-    float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-    return scale * 0.5f * sg * (-expf(-a / beta) * a / (beta * beta));
-  }
-};
-
-// get_beta / get_scale / get_mean, density_functions.py:169-204; the cutoff is ALWAYS -0.5 because
-// Density.forward drops its cutoff argument (density_functions.py:20-34).
-__device__ __forceinline__ Laplace load_laplace(const vfnerf_render_cfg& cfg, const float* __restrict__ dp) {
-  Laplace l;
-  l.beta = fminf(fmaxf(dp[0], cfg.beta_lo), cfg.beta_hi);
-  l.scale = fmaxf(fabsf(dp[1]), cfg.scale_min);
-  l.mean = fminf(fmaxf(dp[2], cfg.mean_lo), cfg.mean_hi);
-  l.L0 = l.cdf(-0.5f);
-  l.Lp0 = l.dcdf_dx(-0.5f);
-  l.Lb0 = l.dcdf_dbeta(-0.5f);
-  return l;
-}
-
-struct Window {
-  int start, nb, lo, hi;     // band of centre indices j in [lo, hi) that get the full window
-  float coef;                // (1/W) / sum_i |1/W|, as the reference forms it in fp32
-};
-__device__ __forceinline__ Window make_window(int W, int N) {
-  Window w;
-  w.start = (W + 1) / 2 + 1;         // int((W + 1) / 2 + 1), functions.py:52
-  w.nb = w.start - 2;                // partners on each side besides j+1, functions.py:65
-  const int L = N - 1;
-  w.lo = w.start;
-  w.hi = L - w.start;
-  if (w.hi <= w.lo) { w.lo = 0; w.hi = 0; }
-  float wu = 1.0f / (float)W, nrm = 0.f;
-  for (int i = 0; i < W; ++i) nrm = __fadd_rn(nrm, wu);
-  w.coef = wu / nrm;
-  return w;
-}
-
-// Loads the N vectors of ray r, stores unit vectors (x / max(|x|, 1e-8), torch 2.x cosine_similarity)
-// and 1/max(|x|,1e-8) into shared memory.
-__device__ __forceinline__ void stage_unit_vectors(const float* __restrict__ nrm_row, int64_t ld, int N,
-                                                   int lane, float* su, float* sinv) {
-  for (int j = lane; j < N; j += 32) {
-    const float* p = nrm_row + (int64_t)j * ld;
-    float x = p[0], y = p[1], z = p[2];
-    float n = fmaxf(sqrtf(x * x + y * y + z * z), 1e-8f);
-    *reinterpret_cast<float4*>(su + kUS * j) = make_float4(x / n, y / n, z / n, 0.f);
-    if (sinv) sinv[j] = 1.f / n;
-  }
-}
-
-__device__ __forceinline__ float dot3(const float* a, const float* b) {
-  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
-}
-__device__ __forceinline__ float dot3(const float4& a, const float4& b) {
-  return a.x * b.x + a.y * b.y + a.z * b.z;
-}
-
-// windowed cosine c_j (functions.py:41-72 with the uniform weights of vector_field_nerf.py:453)
-__device__ __forceinline__ float window_cos(const float* su, int j, const Window& w) {
-  const float4* u4 = reinterpret_cast<const float4*>(su);
-  const float4 uj = u4[j];
-  float base = dot3(uj, u4[j + 1]);
-  if (j < w.lo || j >= w.hi) return base;
-  float c = base * w.coef;
-  if (w.nb == 5) {            // the shipped 11-tap window, unrolled (same order of operations as the loop below)
-#pragma unroll
-    for (int i = 1; i <= 5; ++i) {
-      c = c + dot3(uj, u4[j + 1 + i]) * w.coef;
-      c = c + dot3(uj, u4[j - i]) * w.coef;
-    }
-    return c;
-  }
-  for (int i = 1; i <= w.nb; ++i) {
-    c = c + dot3(uj, u4[j + 1 + i]) * w.coef;
-    c = c + dot3(uj, u4[j - i]) * w.coef;
-  }
-  return c;
-}
-
-__device__ __forceinline__ float warp_inclusive_prod(float v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    float t = __shfl_up_sync(kFull, v, o);
-    if (lane >= o) v *= t;
-  }
-  return v;
-}
 
 // ---------------------------------------------------------------------------------------------
 // forward: c, sigma, weights
@@ -130,46 +27,13 @@ density_weights_kernel(vfnerf_render_cfg cfg, int n_rays, int N, const float* __
   const Laplace lap = load_laplace(cfg, dparams);
   const Window win = make_window(cfg.window, N);
   stage_unit_vectors(normals + (int64_t)r * N * ld, ld, N, lane, su, nullptr);
-  float d[3] = {ray_dirs[3 * (int64_t)r], ray_dirs[3 * (int64_t)r + 1], ray_dirs[3 * (int64_t)r + 2]};
-  {
-    float n = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-8f);
-    d[0] /= n; d[1] /= n; d[2] /= n;
-  }
+  float d[3];
+  unit_dir(ray_dirs, r, d);
   __syncwarp();
-  const float* zr = z + (int64_t)r * N;
-  const bool nerf_w = (cfg.flags & VFNERF_FLAG_NERF_WEIGHTS) != 0;
-  float carry = 0.f, wsum = 0.f, pcarry = 1.f;
   float what[KP];
-#pragma unroll
-  for (int i = 0; i < KP; ++i) {
-    const int j = lane + 32 * i;
-    float E = 0.f, sg = 0.f;
-    if (j < N - 1) {
-      float c = window_cos(su, j, win);
-      float cdir = dot3(su + kUS * j, d);
-      sg = fmaxf(lap.cdf(-c) - lap.L0, 0.f);
-      if (cdir < cfg.dir_to_normal_th && c < 0.f) sg = 0.f;
-      E = (zr[j + 1] - zr[j]) * sg;
-      if (cosw) cosw[(int64_t)r * (N - 1) + j] = c;
-    }
-    if (j < N && sigma_out) sigma_out[(int64_t)r * N + j] = sg;
-    // exclusive prefix of the free energy over this 32-sample chunk, plus the carry of earlier chunks
-    float a = 1.f - expf(-E);
-    if (nerf_w) {
-      // nerf_volume_rendering (utils/rendering.py:98-119): inclusive cumprod of (1 - a + 1e-10)
-      const float pinc = warp_inclusive_prod((j < N) ? (1.f - a + 1e-10f) : 1.f, lane);
-      what[i] = (j < N) ? a * (pcarry * pinc) : 0.f;
-      pcarry *= __shfl_sync(kFull, pinc, 31);
-    } else {
-      float inc = warp_inclusive_scan(E, lane);
-      float T = expf(-(carry + inc - E));
-      what[i] = (j < N) ? a * T : 0.f;
-      carry += __shfl_sync(kFull, inc, 31);
-    }
-    wsum += what[i];
-  }
-  wsum = warp_sum(wsum);
-  const float inv = cfg.normalize ? 1.f / (wsum + 1e-5f) : 1.f;
+  const float inv = ray_weights<KP>(cfg, lap, win, su, d, z + (int64_t)r * N, N, lane,
+                                    cosw ? cosw + (int64_t)r * (N - 1) : nullptr,
+                                    sigma_out ? sigma_out + (int64_t)r * N : nullptr, what);
 #pragma unroll
   for (int i = 0; i < KP; ++i) {
     const int j = lane + 32 * i;

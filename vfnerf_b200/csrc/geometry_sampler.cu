@@ -5,6 +5,7 @@
 // sum here is an explicit round-to-nearest intrinsic (__fmul_rn/__fadd_rn/...): the compiler may not
 // contract them into FMAs.  HBM-bound byte work: one thread per output element, fully coalesced.
 #include "common.cuh"
+#include "ray_ops.cuh"
 
 namespace vfn {
 
@@ -17,52 +18,13 @@ __global__ void ray_geometry_kernel(int n_rays, int pose_is_quat, const float* _
                                     float* __restrict__ cam_loc) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rays) return;
-  float p[3][4];
-  if (pose_is_quat) {
-    const float* q7 = pose + (int64_t)r * 7;
-    float qr = q7[0], qi = q7[1], qj = q7[2], qk = q7[3];
-    float nq = fmaxf(sqrtf(qr * qr + qi * qi + qj * qj + qk * qk), 1e-12f);
-    qr /= nq; qi /= nq; qj /= nq; qk /= nq;
-    p[0][0] = 1.f - 2.f * (qj * qj + qk * qk); p[0][1] = 2.f * (qj * qi - qk * qr); p[0][2] = 2.f * (qi * qk + qr * qj);
-    p[1][0] = 2.f * (qj * qi + qk * qr); p[1][1] = 1.f - 2.f * (qi * qi + qk * qk); p[1][2] = 2.f * (qj * qk - qi * qr);
-    p[2][0] = 2.f * (qk * qi - qj * qr); p[2][1] = 2.f * (qj * qk + qi * qr); p[2][2] = 1.f - 2.f * (qi * qi + qj * qj);
-    p[0][3] = q7[4]; p[1][3] = q7[5]; p[2][3] = q7[6];
-  } else {
-    const float4* pm = reinterpret_cast<const float4*>(pose + (int64_t)r * 16);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      float4 row = __ldg(pm + i);
-      p[i][0] = row.x; p[i][1] = row.y; p[i][2] = row.z; p[i][3] = row.w;
-    }
-  }
-  const float* Kr = K + (int64_t)r * 16;
-  float fx = Kr[0], skew = Kr[1], cx = Kr[2], fy = Kr[5], cy = Kr[6];
-  float k011 = __ldg(K + 5);                                   // intrinsics[0,1,1] of the FIRST ray
-  float zc = (k011 > 0.f) ? 1.f : ((k011 < 0.f) ? -1.f : 0.f);  // ones * sign(.)
-  float za = fabsf(zc);
-  float u = uv[2 * (int64_t)r], v = uv[2 * (int64_t)r + 1];
-  // x = (u - cx + cy*skew/fy - skew*v/fy) / fx * |z| ; y = (v - cy) / fy * |z|
-  float t = __fsub_rn(u, cx);
-  t = __fadd_rn(t, __fdiv_rn(__fmul_rn(cy, skew), fy));
-  t = __fsub_rn(t, __fdiv_rn(__fmul_rn(skew, v), fy));
-  float x = __fmul_rn(__fdiv_rn(t, fx), za);
-  float y = __fmul_rn(__fdiv_rn(__fsub_rn(v, cy), fy), za);
-  float d[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    // bmm row: ((p0*x + p1*y) + p2*z) + p3*1, unfused (matches torch CPU bmm bit for bit)
-    float acc = __fmul_rn(p[i][0], x);
-    acc = __fadd_rn(acc, __fmul_rn(p[i][1], y));
-    acc = __fadd_rn(acc, __fmul_rn(p[i][2], zc));
-    acc = __fadd_rn(acc, __fmul_rn(p[i][3], 1.f));
-    d[i] = __fsub_rn(acc, p[i][3]);
-  }
-  float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]))), 1e-12f);
+  float d[3], rd[3], o[3];
+  ray_geometry_one(r, pose_is_quat, uv, pose, K, d, rd, o);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     directions[3 * (int64_t)r + i] = d[i];
-    ray_dirs[3 * (int64_t)r + i] = __fdiv_rn(d[i], nrm);
-    cam_loc[3 * (int64_t)r + i] = p[i][3];
+    ray_dirs[3 * (int64_t)r + i] = rd[i];
+    cam_loc[3 * (int64_t)r + i] = o[i];
   }
 }
 
@@ -88,16 +50,7 @@ __global__ void coarse_sample_kernel(int64_t total, int n_coarse, float nearf, f
   if (idx >= total) return;
   int64_t r = idx / n_coarse;
   int i = (int)(idx - r * n_coarse);
-  auto lin = [&](int k) {
-    float tk = __ldg(t_vals + k);
-    return __fadd_rn(__fmul_rn(nearf, __fsub_rn(1.f, tk)), __fmul_rn(farf, tk));
-  };
-  float zi = lin(i);
-  if (perturb) {
-    float lower = (i == 0) ? zi : __fmul_rn(0.5f, __fadd_rn(zi, lin(i - 1)));
-    float upper = (i == n_coarse - 1) ? zi : __fmul_rn(0.5f, __fadd_rn(lin(i + 1), zi));
-    zi = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), U1[idx]));
-  }
+  const float zi = coarse_z_one(i, n_coarse, nearf, farf, perturb, t_vals, U1, idx);
   z[idx] = zi;
   if (points) {
 #pragma unroll
@@ -116,71 +69,6 @@ int launch_coarse_sample(int n_rays, int n_coarse, double near_, double far_, in
       total, n_coarse, (float)near_, (float)far_, perturb, t_vals, U1, directions, cam_loc, z, points);
   VFN_LAUNCH_CHECK();
   return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Warp-level sort of cat(run A = s[0, na), run B = s[na, na + nb)) into t[0, na + nb), with the source index of every
-// output in ti.  Values are only moved, so the result equals torch.sort's values bit for bit.
-//  * fast path (both runs already ascending -- coarse z values are, and so is the fine ramp): merge by rank.  An element
-//    of A lands at (its index + number of B elements smaller than it), an element of B at (its index + number of A
-//    elements not larger than it): two binary searches per lane and sample instead of a full sort;
-//  * otherwise (the uniform "z_add" candidates, random inverse-CDF draws, NaNs): bitonic sort in place, then copy.
-// s / si need room for the next power of two >= na + nb (<= VFNERF_MAX_SAMPLES).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_sort_two_runs(float* s, uint8_t* si, float* t, uint8_t* ti, int na, int nb, int lane) {
-  const int N = na + nb;
-  bool ok = true;
-  for (int j = lane; j < N; j += 32)
-    if (j != 0 && j != na) ok = ok && (s[j - 1] <= s[j]);
-  if (__all_sync(kFull, ok)) {
-    // branch-free binary searches with a fixed trip count (log2 of the next power of two >= run length)
-    int pa = 1, pb = 1;
-    while (pa < na) pa <<= 1;
-    while (pb < nb) pb <<= 1;
-    for (int e = lane; e < N; e += 32) {
-      const float v = s[e];
-      int pos = 0;
-      if (e < na) {                       // number of B elements smaller than v (lower bound)
-        for (int st = pb; st > 0; st >>= 1) {
-          const int q = pos + st;
-          if (q <= nb && s[na + q - 1] < v) pos = q;
-        }
-        pos += e;
-      } else {                            // number of A elements not larger than v (upper bound)
-        for (int st = pa; st > 0; st >>= 1) {
-          const int q = pos + st;
-          if (q <= na && s[q - 1] <= v) pos = q;
-        }
-        pos += e - na;
-      }
-      t[pos] = v;
-      ti[pos] = (uint8_t)e;
-    }
-    __syncwarp();
-    return;
-  }
-  int P2 = 32;
-  while (P2 < N) P2 <<= 1;
-  for (int j = N + lane; j < P2; j += 32) s[j] = INFINITY;
-  for (int j = lane; j < P2; j += 32) si[j] = (uint8_t)j;
-  __syncwarp();
-  for (int k = 2; k <= P2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int q = lane; q < (P2 >> 1); q += 32) {
-        int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));   // index with bit j cleared
-        int hi = lo | j;
-        bool asc = (lo & k) == 0;
-        float a = s[lo], b = s[hi];
-        if ((a > b) == asc) {
-          s[lo] = b; s[hi] = a;
-          uint8_t ia = si[lo]; si[lo] = si[hi]; si[hi] = ia;
-        }
-      }
-      __syncwarp();
-    }
-  }
-  for (int j = lane; j < N; j += 32) { t[j] = s[j]; ti[j] = si[j]; }
-  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -208,8 +96,8 @@ fine_sample_kernel(int n_rays, int n_coarse, int n_fine, float nearf, float far_
   float* s = sbuf[wid];
   float* t = tbuf[wid];
   const int N = n_coarse + n_fine;
-  const float dx = directions[3 * (int64_t)r], dy = directions[3 * (int64_t)r + 1], dz = directions[3 * (int64_t)r + 2];
-  const float ox = cam_loc[3 * (int64_t)r], oy = cam_loc[3 * (int64_t)r + 1], oz = cam_loc[3 * (int64_t)r + 2];
+  const float dv[3] = {directions[3 * (int64_t)r], directions[3 * (int64_t)r + 1], directions[3 * (int64_t)r + 2]};
+  const float o[3] = {cam_loc[3 * (int64_t)r], cam_loc[3 * (int64_t)r + 1], cam_loc[3 * (int64_t)r + 2]};
   if (z_override) {
     for (int j = lane; j < N; j += 32) t[j] = z_override[(int64_t)r * N + j];
   } else {
@@ -220,58 +108,15 @@ fine_sample_kernel(int n_rays, int n_coarse, int n_fine, float nearf, float far_
       float w = w_coarse[(int64_t)r * n_coarse + j];
       if (w > best) { best = w; bi = j; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ob = __shfl_xor_sync(kFull, best, o);
-      int oi = __shfl_xor_sync(kFull, bi, o);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    if (bi == 0x7fffffff) bi = 0;  // all -inf / NaN rows: fall back to index 0 like an all-equal row
+    warp_argmax_first(best, bi);
     const float z_star = z_coarse[(int64_t)r * n_coarse + bi];
     for (int j = lane; j < n_coarse; j += 32) s[j] = z_coarse[(int64_t)r * n_coarse + j];
-    const float base = __fsub_rn(z_star, rangef);
-    auto ramp = [&](int i) { return __fadd_rn(base, __fmul_rn(stepf, (float)i)); };
-    for (int i = lane; i < n_fine; i += 32) {
-      float v;
-      if (bi > 0) {
-        v = ramp(i);
-        if (perturb) {
-          float lower = (i == 0) ? v : __fmul_rn(0.5f, __fadd_rn(v, ramp(i - 1)));
-          float upper = (i == n_fine - 1) ? v : __fmul_rn(0.5f, __fadd_rn(ramp(i + 1), v));
-          v = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), U2[(int64_t)r * n_fine + i]));
-        }
-      } else {
-        v = __fadd_rn(__fmul_rn(U3[(int64_t)r * n_fine + i], far_minus_near), nearf);
-      }
-      s[n_coarse + i] = v;
-    }
-    __syncwarp();
-    if (points_fine) {
-      // the fine candidates alone, in candidate order: the only points of this ray the MLPs have not seen yet
-      float* pf = points_fine + (int64_t)r * n_fine * 3;
-      for (int j = lane; j < n_fine; j += 32) {
-        const float zj = s[n_coarse + j];
-        pf[3 * j] = __fadd_rn(ox, __fmul_rn(zj, dx));
-        pf[3 * j + 1] = __fadd_rn(oy, __fmul_rn(zj, dy));
-        pf[3 * j + 2] = __fadd_rn(oz, __fmul_rn(zj, dz));
-      }
-      __syncwarp();
-    }
-    warp_sort_two_runs(s, sidx[wid], t, tidx[wid], n_coarse, n_fine, lane);
+    const FineCfg fc{n_coarse, n_fine, perturb, nearf, far_minus_near, rangef, stepf};
+    fine_candidates_sorted(fc, r, bi, z_star, U2, U3, o, dv, s, sidx[wid], t, tidx[wid], points_fine, lane);
     if (src) for (int j = lane; j < N; j += 32) src[(int64_t)r * N + j] = tidx[wid][j];
   }
   __syncwarp();
-  for (int j = lane; j < N; j += 32) z_out[(int64_t)r * N + j] = t[j];
-  if (points) {
-    // one sample per lane and iteration, three 12-byte-strided stores (a warp still writes one contiguous 384-byte span)
-    float* pr = points + (int64_t)r * N * 3;
-    for (int j = lane; j < N; j += 32) {
-      const float zj = t[j];
-      pr[3 * j] = __fadd_rn(ox, __fmul_rn(zj, dx));
-      pr[3 * j + 1] = __fadd_rn(oy, __fmul_rn(zj, dy));
-      pr[3 * j + 2] = __fadd_rn(oz, __fmul_rn(zj, dz));
-    }
-  }
+  write_merged_samples(t, N, r, o, dv, z_out, points, lane);
 }
 
 int launch_fine_sample(int n_rays, int n_coarse, int n_fine, double near_, double far_,

@@ -65,7 +65,10 @@ class VectorFieldNerf:
         # torch.no_grad() the whole forward is captured once per (ray count, sampler settings, precision) as a CUDA
         # graph and replayed -- per call the host then only copies the inputs into static buffers.  The NerfOutput of a
         # replayed call aliases static buffers that the NEXT render() call overwrites (the evaluation loop copies
-        # rgb / depth to the host right away); off by default for that reason.
+        # rgb / depth to the host right away); off by default for that reason.  The weight images are re-tiled only when
+        # the parameters changed since the previous replay, as seen by torch's version counters, load_state_dict and the
+        # library's own writers (ParamArena.version); after writing parameters through ``tensor.data`` call
+        # ``model.invalidate_replay()``.
         self.graph_replay = False
         self._graphs: dict = {}
         # Two paths of the reference's render() cannot execute upstream: white=True reads rgb before it is
@@ -236,7 +239,8 @@ class VectorFieldNerf:
         return cfg
 
     def render(self, pose: torch.Tensor, pixels: torch.Tensor, intrinsics: torch.Tensor, epoch: int,
-               white: bool = False, *, draws=None, z_vals_override: Optional[torch.Tensor] = None) -> NerfOutput:
+               white: bool = False, *, draws=None, z_vals_override: Optional[torch.Tensor] = None,
+               _workspace: Optional[torch.Tensor] = None, _weights_packed: bool = False) -> NerfOutput:
         """Same contract as vector_field_nerf.py:216-338.
 
         :param pose: [R,4,4] camera-to-world matrices or [R,7] (quaternion, translation), on the GPU.
@@ -308,7 +312,8 @@ class VectorFieldNerf:
         call = ops.RenderCall(cfg, self.vector_field_network, self.rendering_network, self.density,
                               pixels, pose, intrinsics, dev_(t_vals), dev_(U1), dev_(U2), dev_(U3),
                               z_override=dev_(z_vals_override), want_extras=True,
-                              want_ray_dirs=self.return_ray_dirs, train=train_mode)
+                              want_ray_dirs=self.return_ray_dirs, train=train_mode, workspace=_workspace,
+                              weights_packed=_weights_packed)
         res = ops.render_call(call)
         rgb, depth, normals, colors, points, z_vals = res[:6]
         ray_dirs = res[6] if len(res) > 6 else None
@@ -320,6 +325,10 @@ class VectorFieldNerf:
                           coarse_colors=colors,
                           weights=call.extras.get("weights"))
 
+
+    def invalidate_replay(self) -> None:
+        """Forget the captured render() graphs (and with them the packed weight images they reuse)."""
+        self._graphs.clear()
 
     # ---- CUDA-graph replay of the forward-only call (opt-in: self.graph_replay) ---------------------------------------
     def _replay_key(self, R: int, quat: bool, dev: torch.device):
@@ -363,7 +372,20 @@ class _RenderGraph:
         self._host = [[None if u is None else [torch.empty(u.shape, dtype=torch.float32).pin_memory(), None] for _ in range(4)]
                       for u in self.U]
         self._slot = 0
-        self.graph = torch.cuda.CUDAGraph()
+        # Two captures over ONE static workspace: `graph` re-tiles the weight images from the parameter arenas and renders,
+        # `graph_packed` renders with the images the workspace already holds.  replay() picks the first whenever the
+        # arenas' version changed since the last re-tiling (ParamArena.version) -- hundreds of chunks of one image then
+        # pay for the re-tiling once.
+        L = _lib.lib()
+        cfg = model._render_cfg(R, quat)
+        va, ra = model.vector_field_network.arena(), model.rendering_network.arena()
+        import ctypes as C
+        nbytes = L.vfnerf_render_workspace_bytes(C.byref(cfg), C.byref(va.desc), C.byref(ra.desc), 0)
+        if nbytes < 0:
+            _lib.check(1, "vfnerf_render_workspace_bytes")
+        self.ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
+        self.graph, self.graph_packed = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self._packed_version = None
         was = model.graph_replay
         model.graph_replay = False
         try:
@@ -371,12 +393,18 @@ class _RenderGraph:
             s.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(s), torch.no_grad():
                 for _ in range(2):      # lazy one-time work (kernel attributes, arenas, t_vals upload) outside the capture
-                    model.render(self.pose, self.pixels, self.intrinsics, 0, draws=tuple(self.U))
+                    model.render(self.pose, self.pixels, self.intrinsics, 0, draws=tuple(self.U), _workspace=self.ws)
             torch.cuda.current_stream(dev).wait_stream(s)
             torch.cuda.synchronize(dev)
             with torch.cuda.graph(self.graph), torch.no_grad():
-                self.out = model.render(self.pose, self.pixels, self.intrinsics, 0, draws=tuple(self.U))
+                self.out = model.render(self.pose, self.pixels, self.intrinsics, 0, draws=tuple(self.U), _workspace=self.ws)
             self.extras = model.last_extras
+            self.out_packed = self.extras_packed = None
+            if model.precision != "fp32":
+                with torch.cuda.graph(self.graph_packed), torch.no_grad():
+                    self.out_packed = model.render(self.pose, self.pixels, self.intrinsics, 0, draws=tuple(self.U),
+                                                   _workspace=self.ws, _weights_packed=True)
+                self.extras_packed = model.last_extras
         finally:
             model.graph_replay = was
 
@@ -408,6 +436,12 @@ class _RenderGraph:
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(self.dev))
                 ring[k][1] = ev
+        version = (m.vector_field_network.arena().version(), m.rendering_network.arena().version())
+        if self.out_packed is not None and version == self._packed_version:
+            self.graph_packed.replay()
+            m.last_extras = self.extras_packed
+            return self.out_packed
         self.graph.replay()
+        self._packed_version = version
         m.last_extras = self.extras
         return self.out

@@ -30,6 +30,7 @@ class ParamArena:
         self.slots: List[Tuple[str, torch.Tensor, int]] = []   # (kind, tensor, offset)
         self.grad_flat: Optional[torch.Tensor] = None           # flat gradient arena (optim.ArenaAdam), else None
         self.dirty = False                                      # set by the owner's _apply / load_state_dict overrides
+        self.generation = 0         # bumped by code that writes the arena behind torch's back (ArenaAdam, train-mode BN)
         self.rebuild()
 
     def _tensors(self):
@@ -132,6 +133,14 @@ class ParamArena:
 
     def params(self) -> List[nn.Parameter]:
         return [t for _, t, _ in self.slots if isinstance(t, nn.Parameter)]
+
+    def version(self):
+        """Changes whenever the arena's contents may have: torch's version counters of every member tensor (in-place
+        optimizer steps, load_state_dict, broadcasts), the storage address (re-flattening) and ``generation`` (writes by
+        the library itself).  Writes through ``tensor.data`` are invisible to it.  Used to skip re-packing the weight images
+        between CUDA-graph replays of render() (nerf._RenderGraph)."""
+        self.sync()
+        return (self.flat.data_ptr(), self.generation, self.flat._version, sum(t._version for _, t, _ in self.slots))
 
     def grad_views(self, grad_flat: torch.Tensor) -> List[torch.Tensor]:
         """Views of a gradient arena matching ``params()`` one to one."""

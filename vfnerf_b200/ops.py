@@ -154,6 +154,7 @@ class _VFQueryTrain(torch.autograd.Function):
                                              out.data_ptr() + 4 * Do, Do + 9, ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
                        "vfnerf_vf_train_fwd")
         _bump_batches_tracked(net)
+        ar.generation += 1             # running statistics updated in the arena by the library
         ctx.net, ctx.ws, ctx.P, ctx.Do = net, (ws if need_bwd else None), P, Do
         ctx.save_for_backward(out)
         return out
@@ -257,7 +258,8 @@ class RenderCall:
     """Everything one render() call needs besides the parameters (built by nerf.VectorFieldNerf)."""
 
     def __init__(self, cfg: _lib.RenderCfg, vf_net, rn_net, density, uv, pose, intrinsics, t_vals, U1, U2, U3,
-                 z_override=None, want_extras: bool = False, want_ray_dirs: bool = True, train: bool = False):
+                 z_override=None, want_extras: bool = False, want_ray_dirs: bool = True, train: bool = False,
+                 workspace: Optional[torch.Tensor] = None, weights_packed: bool = False):
         self.cfg, self.vf_net, self.rn_net, self.density = cfg, vf_net, rn_net, density
         self.uv, self.pose, self.intrinsics, self.t_vals = uv, pose, intrinsics, t_vals
         self.U1, self.U2, self.U3, self.z_override = U1, U2, U3, z_override
@@ -265,6 +267,9 @@ class RenderCall:
         self.extras = {}
         self.need_bwd = False
         self.train = train          # batch-statistic BatchNorm + directional derivatives (csrc/mlp_train.cu)
+        # a caller-owned workspace that outlives the call (CUDA-graph replay: the packed weight images stay in it), and
+        # the promise that it already holds them (include/vfnerf_b200.h: VFNERF_FLAG_WEIGHTS_PACKED)
+        self.workspace, self.weights_packed = workspace, weights_packed
 
 
 class _Render(torch.autograd.Function):
@@ -288,7 +293,12 @@ class _Render(torch.autograd.Function):
             nbytes = L.vfnerf_render_workspace_bytes(C.byref(cfg), C.byref(vf_ar.desc), C.byref(rn_ar.desc), int(need_bwd))
         if nbytes < 0:
             _lib.check(1, "vfnerf_render_workspace_bytes")
-        ws = _workspace(nbytes, dev)
+        if call.workspace is not None and not need_bwd and call.workspace.numel() >= nbytes:
+            ws = call.workspace
+            if call.weights_packed:
+                cfg.flags |= _lib.FLAG_WEIGHTS_PACKED
+        else:
+            ws = _workspace(nbytes, dev)
         f32 = dict(dtype=torch.float32, device=dev)
         points = torch.empty(R, N, 3, **f32)
         normals = torch.empty(R, N, 3, **f32)
@@ -315,6 +325,8 @@ class _Render(torch.autograd.Function):
                     _stream_ptr(dev)), "vfnerf_render_train_fwd")
                 _bump_batches_tracked(call.vf_net, 2)          # coarse pass + merged pass
                 _bump_batches_tracked(call.rn_net, 1)
+                vf_ar.generation += 1
+                rn_ar.generation += 1
             else:
                 _lib.check(L.vfnerf_render_fwd(
                     C.byref(cfg), C.byref(vf_ar.desc), vf_ar.flat.data_ptr(), C.byref(rn_ar.desc), rn_ar.flat.data_ptr(),

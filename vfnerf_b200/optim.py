@@ -177,6 +177,8 @@ class ArenaAdam(torch.optim.Optimizer):
             _lib.check(L.vfnerf_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _lib.ptr(mask), p.numel(),
                                           lr.data_ptr(), self._step.data_ptr(), float(b1), float(b2), float(g0["eps"]),
                                           float(g0["weight_decay"]), mn, self._sq.data_ptr(), gs, stream), "vfnerf_adam_step")
+        for ar in self._arenas:
+            ar.generation += 1         # the arenas changed behind torch's version counters
         return None
 
 
