@@ -68,7 +68,8 @@ def parse():
 def ncu_traffic(points_per_launch, precision):
     """dram__bytes_read.sum + dram__bytes_write.sum of the fused RENDER launch from the committed `ncu --set full` capture
     (profiles/run_render_points.py, same points per launch); None if no capture matches this launch."""
-    name = {"bf16": "r02_prof_render_bf16_raw.csv", "bf16x3": "r02_prof_render_bf16x3_raw.csv"}.get(precision)
+    name = {"bf16": "r02_prof_render_bf16_raw.csv", "bf16x3": "r02_prof_render_bf16x3_raw.csv",
+            "fp16f8": "r02_prof_render_fp16f8_raw.csv"}.get(precision)
     if name is None or points_per_launch != 65536 * (N_COARSE + N_FINE):
         return None, None
     path = os.path.join(ROOT, "profiles", name)
@@ -340,11 +341,11 @@ def main():
         s1k()
         resident_1024 = world * R / (timed(s1k, 1) * 1e-3)
         modes[head]["value_chunk_1024"] = resident_1024
-        if other:
-            so = make_step_resident(model_for(other), chunk)
+        for prec_o in ([other] if other else []) + (["fp16f8"] if head == "bf16x3" else []):
+            so = make_step_resident(model_for(prec_o), chunk)
             so()
             ms_o = timed(so, 2)
-            modes[other] = {"value": world * R / (ms_o * 1e-3), "unit": "rays/s", "ms_per_step": ms_o}
+            modes[prec_o] = {"value": world * R / (ms_o * 1e-3), "unit": "rays/s", "ms_per_step": ms_o}
 
     # ---- e2e: the reference-facing call render(pose, pixels, intrinsics, epoch) with HOST buffers, chunk by chunk like
     # evaluation/methods.py:516-530: per chunk H2D of uv/pose/K from pinned memory, the sampler draws on the CPU
@@ -698,7 +699,8 @@ def main():
         t_k = r0.elapsed_time(r1) * 1e-3 / reps
         ach = flop_pt * P / t_k / 1e12
         # FLOPs the tensor cores execute: the split-precision mode issues three MMAs per product of the 8 hidden VF layers
-        exe_pt = flop_pt + (2 * F_VF_HIDDEN if prec == "bf16x3" else 0)
+        # (fp16f8: one 16-bit MMA + two 8-bit MMAs at twice the rate = two 16-bit units per product)
+        exe_pt = flop_pt + (2 * F_VF_HIDDEN if prec == "bf16x3" else (F_VF_HIDDEN if prec == "fp16f8" else 0))
         traffic, traffic_src = ncu_traffic(P, prec)
         return {"bound": "tensor", "achieved": ach, "peak": peak_burst, "unit": "TFLOP/s", "frac": ach / peak_burst,
                 "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch", "traffic_source": traffic_src,
@@ -717,6 +719,11 @@ def main():
         modes[other]["note"] = ("plain bf16 operands: 5e-3 met only on a default-gain model; on the non-degenerate golden model "
                                 "normals differ from the reference by up to 0.13 (tests/test_gpu_tc.py)") if other == "bf16" else \
                                "split precision: <= 1e-3 against the reference goldens (tests/test_gpu_x3.py)"
+    if "fp16f8" in modes:
+        modes["fp16f8"]["roofline"] = kernel_roofline("fp16f8")
+        modes["fp16f8"]["note"] = ("fp16 product + two 8-bit remainder products per VF product (kind::f8f6f4): <= 2.5e-3 against "
+                                   "the reference goldens (measured 8e-4, tests/test_gpu_x3.py); executed_tflops counts the "
+                                   "8-bit MMAs as half a 16-bit unit each")
 
     line = {
         "metric": "render_fwd_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world,

@@ -27,7 +27,11 @@ int vfnerf_debug_umma2_m128_probe(const float* A, const float* B, float* dump, i
 /* Micro-benchmark: every CTA issues n_mma back-to-back tcgen05.mma (M=128, N, K=16) from one thread; CTA 0 writes
  * the elapsed SM cycles to cycles_dev[0].  mode 1 adds a tcgen05.commit after every second MMA. */
 int vfnerf_debug_umma_bench(int N, int n_mma, int mode, int n_ctas, long long* cycles_dev, void* stream);
-/* Same for tcgen05.mma.cta_group::2 (M=256, N=256): mode 0 no commits, 1 multicast commit per 4 MMAs, 2 leader-only commit */
+/* 2-CTA convention check for kind::f16 with fp16 operands (a_fmt = b_fmt = 2) and kind::f8f6f4 with 8-bit operands
+ * (0 = e4m3, 1 = e5m2; K multiple of 32): D[256,N] = round(A)[256,K] * round(B)[N,K]^T */
+int vfnerf_debug_umma2_alt_gemm(const float* A, const float* B, float* D, int N, int K, int a_fmt, int b_fmt, void* stream);
+/* Same for tcgen05.mma.cta_group::2 (M=256, N=256): mode 0 no commits, 1 multicast commit per 4 MMAs, 2 leader-only commit;
+ * +4: M = 128, +8: N = 128, +16: kind::f8f6f4 (K = 32 per instruction) */
 int vfnerf_debug_umma2_bench(int n_mma, int mode, int n_ctas, long long* cycles_dev, void* stream);
 /* Test support for the bf16 training path: after vfnerf_render_fwd(keep_for_backward = 1) [and vfnerf_render_bwd] on
  * `workspace`, convert activation-stash tensor `tensor` to row-major fp32 out[n_rays * n_samples, *n_cols].

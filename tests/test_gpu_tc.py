@@ -130,6 +130,27 @@ def test_umma_2cta_conventions(debug_lib, N, K):
     assert err <= 1e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("a_fmt,b_fmt", [(2, 2), (0, 1), (1, 0), (0, 0)])
+@pytest.mark.parametrize("N,K", [(256, 256), (224, 64), (64, 32)])
+def test_umma_fp16_and_8bit_operand_conventions(debug_lib, N, K, a_fmt, b_fmt):
+    """The operand kinds of the fp16 + fp8-remainder chain (precision "fp16f8"): kind::f16 with fp16 operands (format 2
+    here) and kind::f8f6f4 with e4m3 (0) / e5m2 (1) operands, K = 32 per instruction, 16 columns per 16-byte unit of the
+    K-slab.  Products of 8-bit operands are exact in fp32, so the result must equal the fp64 product of the rounded
+    operands up to fp32 accumulation."""
+    def rnd(x, fmt):
+        return x.half().float() if fmt == 2 else x.to(torch.float8_e5m2 if fmt else torch.float8_e4m3fn).float()
+    g = torch.Generator().manual_seed(N + K + 7 * a_fmt + b_fmt)
+    A = torch.randn(256, K, generator=g).to(DEV)
+    B = (torch.randn(N, K, generator=g) * 0.5).to(DEV)
+    D = torch.zeros(256, N, device=DEV)
+    _lib.check_debug(debug_lib.vfnerf_debug_umma2_alt_gemm(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, a_fmt, b_fmt,
+                                                     torch.cuda.current_stream().cuda_stream), "debug_umma2_alt_gemm")
+    torch.cuda.synchronize()
+    ref = rnd(A, a_fmt).double() @ rnd(B, b_fmt).double().T
+    err = (D.double() - ref).abs().max().item()
+    assert err <= 5e-6 * max(1.0, ref.abs().max().item()), err
+
+
 @pytest.mark.parametrize("N,K", [(256, 128), (48, 128), (256, 64), (96, 16)])
 def test_umma_mn_major_conventions(debug_lib, N, K):
     """Both operands MN-major (reduction index = row of the stashed [points, channels] tiles): the wgrad GEMM."""

@@ -1,5 +1,6 @@
-"""GPU: the split-precision tensor-core mode (precision="bf16x3": every VF product is three bf16 MMAs, colour net
-plain bf16) against the REFERENCE goldens and the CPU oracle -- never against this repo's own kernels.
+"""GPU: the split-precision tensor-core modes -- precision="bf16x3" (every VF product is three bf16 MMAs) and
+precision="fp16f8" (one fp16 MMA plus two 8-bit remainder MMAs per VF product, csrc/mlp_tc.cuh); colour net plain bf16 in
+both -- against the REFERENCE goldens and the CPU oracle, never against this repo's own kernels.
 
 This is the parity-carrying tcgen05 mode: BASELINE.json north_star asks for colour / depth / normals within 1e-3 abs
 (fp32-grade path) of the reference's render() on identical inputs; the goldens come from the live reference
@@ -14,8 +15,13 @@ DEV = "cuda"
 # north_star allows a bf16 tensor-core path 5e-3 abs.  This mode is held to the fp32 path's 1e-3 on every per-sample and
 # per-ray quantity in [0, 1] (normals, colours, rgb, weights); depth is a length in [0, far + range] = [0, 6.3] summed
 # from 128 weights, so the same weight error shows up 6x larger there: 2.5e-3 abs (4e-4 of the range).
-TOL = 1e-3
-TOL_DEPTH = 2.5e-3
+# fp16f8 carries ~2^-15 per product instead of ~2^-16.5 (8-bit remainders): held to HALF of north_star's bf16 tolerance.
+TOLS = {"bf16x3": (1e-3, 2.5e-3, 0.97), "fp16f8": (2.5e-3, 5e-3, 0.95)}
+
+
+@pytest.fixture(params=sorted(TOLS))
+def mode(request):
+    return request.param
 
 
 def _inputs(z):
@@ -30,13 +36,14 @@ def _oracle(case, z, st, draws, **kw):
 
 
 @pytest.mark.parametrize("name", ["full_det", "full_perturb"])
-def test_x3_render_matches_reference_golden(built_lib, name):
+def test_x3_render_matches_reference_golden(built_lib, name, mode):
+    TOL, TOL_DEPTH, PLACE = TOLS[mode]
     """Goldens in, goldens out: second pass conditioned on the reference's z values (SURVEY.md §8c protocol), every
     field compared with ref_* from the fixture at the fp32 tolerance; then the free-running call must place the fine
     samples exactly like the reference on >= 97 % of the rays."""
     case, z = U.load_golden(name)
     st = U.case_state(case, z)
-    model = U.make_model(case, st, DEV, precision="bf16x3")
+    model = U.make_model(case, st, DEV, precision=mode)
     uv, pose, K, draws = _inputs(z)
     z_ref = U.t(z, "ref_z_vals")
     with torch.no_grad():
@@ -54,12 +61,12 @@ def test_x3_render_matches_reference_golden(built_lib, name):
     dr = (out.coarse_rgb_values.cpu() - U.t(z, "ref_rgb"))[ok].abs().max().item()
     dd = (out.coarse_depth_map.cpu() - U.t(z, "ref_depth"))[ok].abs().max().item()
     dw = (out.weights.cpu() - ora["weights"])[ok].abs().max().item()
-    print(f"[{name}] bf16x3 vs reference golden: normals {dn:.2e} colors {dc:.2e} rgb {dr:.2e} depth {dd:.2e} weights {dw:.2e}")
+    print(f"[{name}] {mode} vs reference golden: normals {dn:.2e} colors {dc:.2e} rgb {dr:.2e} depth {dd:.2e} weights {dw:.2e}")
     assert dn <= TOL and dc <= TOL and dr <= TOL and dd <= TOL_DEPTH and dw <= TOL
     same = (free.z_vals.cpu() == z_ref).all(dim=1)
     rate = same.float().mean().item()
     print(f"[{name}] fine-sample placement identical to the reference on {100 * rate:.1f}% of rays")
-    assert rate >= 0.97
+    assert rate >= PLACE
     okf = same & ok
     assert torch.equal(free.points_coarse.cpu()[same], U.t(z, "ref_points")[same])
     assert (free.coarse_normals.cpu() - U.t(z, "ref_normals"))[same].abs().max().item() <= TOL
@@ -68,11 +75,12 @@ def test_x3_render_matches_reference_golden(built_lib, name):
     assert (free.coarse_colors.cpu().reshape(-1, N, 3) - U.t(z, "ref_colors").reshape(-1, N, 3))[same].abs().max().item() <= TOL
 
 
-def test_x3_render_1024_ray_chunk_against_oracle(built_lib):
+def test_x3_render_1024_ray_chunk_against_oracle(built_lib, mode):
+    TOL, TOL_DEPTH, PLACE = TOLS[mode]
     """BASELINE config 1 size (1024 rays, 64+64 samples, full-size nets) against the CPU oracle."""
     case, z = U.load_golden("full_perturb")
     st = U.case_state(case, z)
-    model = U.make_model(case, st, DEV, precision="bf16x3")
+    model = U.make_model(case, st, DEV, precision=mode)
     R = 1024
     uv, pose, K = U.S.synthetic_rays(R, seed=0, start=0, stride=797)
     draws = U.S.synthetic_draws(R, 64, 64, seed=99)
@@ -84,15 +92,15 @@ def test_x3_render_1024_ray_chunk_against_oracle(built_lib):
         model.recompute_coarse = True                  # the literal schedule of vector_field_nerf.py:252-312
         out3 = model.render(pose.to(DEV), uv.to(DEV), K.to(DEV), 0, draws=draws)
     same = (out.z_vals.cpu() == ora["z_vals"]).all(dim=1)
-    print(f"bf16x3: fine-sample placement identical to the oracle on {100 * same.float().mean().item():.2f}% of 1024 rays")
-    assert same.float().mean().item() >= 0.97
+    print(f"{mode}: fine-sample placement identical to the oracle on {100 * same.float().mean().item():.2f}% of 1024 rays")
+    assert same.float().mean().item() >= PLACE
     assert (ora["sigma"] > 0).float().mean().item() >= 0.05
     ok = U.discontinuity_guard(ora, case)
     dn = (out2.coarse_normals.cpu() - ora["normals"]).abs().max().item()
     dc = (out2.coarse_colors.cpu() - ora["colors"]).abs().max().item()
     dr = (out2.coarse_rgb_values.cpu() - ora["rgb"])[ok].abs().max().item()
     dd = (out2.coarse_depth_map.cpu() - ora["depth"])[ok].abs().max().item()
-    print(f"bf16x3 vs oracle, 1024 rays: normals {dn:.2e} colors {dc:.2e} rgb {dr:.2e} depth {dd:.2e}")
+    print(f"{mode} vs oracle, 1024 rays: normals {dn:.2e} colors {dc:.2e} rgb {dr:.2e} depth {dd:.2e}")
     assert dn <= TOL and dc <= TOL and dr <= TOL and dd <= TOL_DEPTH
     # coarse reuse (each unique point once) and the literal schedule give the same bits
     for f in ("z_vals", "coarse_rgb_values", "coarse_depth_map", "coarse_normals", "coarse_colors"):
@@ -100,12 +108,13 @@ def test_x3_render_1024_ray_chunk_against_oracle(built_lib):
 
 
 @pytest.mark.parametrize("P", [1, 127, 128, 129, 5000, 300 * 128 + 17])
-def test_x3_vf_query_matches_oracle(built_lib, P):
+def test_x3_vf_query_matches_oracle(built_lib, P, mode):
+    TOL, TOL_DEPTH, PLACE = TOLS[mode]
     """VF-only module call (vector + 256 features) on the non-degenerate model vs the oracle's VF MLP: tail tiles,
     odd tile counts, multi-tile CTAs."""
     case, z = U.load_golden("full_det")
     st = U.case_state(case, z)
-    model = U.make_model(case, st, DEV, precision="bf16x3")
+    model = U.make_model(case, st, DEV, precision=mode)
     g = torch.Generator().manual_seed(P)
     pts = (torch.rand(P, 3, generator=g) - 0.5) * 8
     from vfnerf_b200.ops import vf_query
@@ -114,19 +123,20 @@ def test_x3_vf_query_matches_oracle(built_lib, P):
         out = model.vector_field_network(pts.to(DEV)).cpu()
         v3 = vf_query(model.vector_field_network, pts.to(DEV), n_cols=3).cpu()
     err = (out - ref).abs()
-    print(f"P={P}: bf16x3 vs oracle  v max {err[:, :3].max().item():.2e} | feat max {err[:, 3:].max().item():.2e}")
+    print(f"P={P}: {mode} vs oracle  v max {err[:, :3].max().item():.2e} | feat max {err[:, 3:].max().item():.2e}")
     assert out.shape == ref.shape and torch.isfinite(out).all()
     assert torch.equal(v3, out[:, :3])
     assert err.max().item() <= TOL
 
 
-def test_x3_grid_query_matches_oracle(built_lib):
+def test_x3_grid_query_matches_oracle(built_lib, mode):
+    TOL, TOL_DEPTH, PLACE = TOLS[mode]
     """Marching-cubes grid query (mc_utils.py:88-104): in-kernel coordinates + VF chain vs the oracle on the
     reference's own coordinate formula."""
     from vfnerf_b200.grid_query import grid_query
     case, z = U.load_golden("full_det")
     st = U.case_state(case, z)
-    model = U.make_model(case, st, DEV, precision="bf16x3")
+    model = U.make_model(case, st, DEV, precision=mode)
     res = 40
     tr, ce = torch.tensor([0.5, -0.5, 0.5]), torch.tensor([0.1, 0.0, -0.2])
     out = grid_query(model.vector_field_network, res, 1.0, tr, ce, chunk=10000).cpu()
@@ -138,14 +148,15 @@ def test_x3_grid_query_matches_oracle(built_lib):
 
 
 @pytest.mark.parametrize("R,n_coarse,n_fine", [(3, 40, 24), (77, 64, 36), (1, 64, 64)])
-def test_x3_render_ragged_sample_counts(built_lib, R, n_coarse, n_fine):
+def test_x3_render_ragged_sample_counts(built_lib, R, n_coarse, n_fine, mode):
+    TOL, TOL_DEPTH, PLACE = TOLS[mode]
     """R*N not a multiple of the 128-point tile, odd tile counts, caller-mutated sample counts: vs the oracle."""
     case, z = U.load_golden("full_perturb")
     case = dict(case, n_coarse=n_coarse, n_fine=n_fine, max_samples=100)
     st = U.case_state(case, z)
     uv, pose, K = U.S.synthetic_rays(R, seed=0, start=11, stride=797)
     draws = U.S.synthetic_draws(R, n_coarse, n_fine, seed=7)
-    model = U.make_model(case, st, DEV, precision="bf16x3")
+    model = U.make_model(case, st, DEV, precision=mode)
     with torch.no_grad():
         ora = U.O.render(st["vf_net"], st["rendering_net"], st["density"], U.oracle_cfg(case), uv, pose, K,
                          torch.linspace(0., 1., n_coarse), *draws)
@@ -159,10 +170,11 @@ def test_x3_render_ragged_sample_counts(built_lib, R, n_coarse, n_fine):
         assert (out.coarse_depth_map.cpu() - ora["depth"])[ok].abs().max().item() <= TOL_DEPTH
 
 
-def test_x3_is_forward_only(built_lib):
+def test_x3_is_forward_only(built_lib, mode):
+    TOL, TOL_DEPTH, PLACE = TOLS[mode]
     """Training runs on bf16 / fp32: asking the split-precision mode for a backward must fail loudly."""
     case, z = U.load_golden("full_det")
-    model = U.make_model(case, U.case_state(case, z), DEV, precision="bf16x3")
+    model = U.make_model(case, U.case_state(case, z), DEV, precision=mode)
     uv, pose, K, draws = _inputs(z)
     with pytest.raises(RuntimeError):
         model.render(pose, uv, K, 0, draws=draws)

@@ -28,9 +28,9 @@ SQNORM_SCRATCH_FLOATS = 1024
 
 MAX_LAYERS = 16
 MAX_SAMPLES = 256
-PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_FP16F8 = 0, 1, 2, 3
 FLAG_RECOMPUTE_COARSE, FLAG_WHITE_BG, FLAG_NERF_WEIGHTS, FLAG_WEIGHTS_PACKED = 1, 2, 4, 8
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16f8": PREC_FP16F8}
 
 
 class MlpDesc(C.Structure):
@@ -108,6 +108,7 @@ DEBUG_PROTOTYPES = {
     "vfnerf_debug_umma_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "vfnerf_debug_umma_mn_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "vfnerf_debug_umma2_gemm": (_I, [_P, _P, _P, _I, _I, _P]),
+    "vfnerf_debug_umma2_alt_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "vfnerf_debug_umma2_m128_probe": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "vfnerf_debug_umma2_bench": (_I, [_I, _I, _I, _P, _P]),
     "vfnerf_debug_stash_read": (_I, [_P, _P, _P, _P, _I, _P, _P, _P]),

@@ -26,6 +26,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// split-precision tile variant of a precision (mlp_tc.cuh): 0 plain bf16, 1 bf16x3, 2 fp16 + fp8 remainders
+static int split_mode(int precision) {
+  return precision == VFNERF_PREC_BF16X3 ? 1 : (precision == VFNERF_PREC_FP16F8 ? 2 : 0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // fp32 MLP forward / backward (generic widths)
 // ---------------------------------------------------------------------------------------------
@@ -187,7 +192,7 @@ static int make_plan(const vfnerf_render_cfg& cfg, const vfnerf_mlp_desc& vf, co
     }
   } else {
     if (int e = tc_carve(c.base, c.off, cfg.multires, cfg.multires_view, cfg.skip_layer, vf, &rn, p.tc, p.P, keep,
-                         cfg.precision == VFNERF_PREC_BF16X3)) return e;
+                         split_mode(cfg.precision))) return e;
   }
   // Sized for every call (the workspace query does not know about z_override); used when it applies.  With a stash
   // (training) the two launches fill consecutive tile ranges of the same stash, so the coarse block must end on a tile
@@ -209,7 +214,7 @@ static int make_plan(const vfnerf_render_cfg& cfg, const vfnerf_mlp_desc& vf, co
 
 static int check_precision(const vfnerf_render_cfg& cfg) {
   VFN_REQUIRE(cfg.precision == VFNERF_PREC_FP32 || cfg.precision == VFNERF_PREC_BF16 ||
-              cfg.precision == VFNERF_PREC_BF16X3, "unknown precision %d", cfg.precision);
+              cfg.precision == VFNERF_PREC_BF16X3 || cfg.precision == VFNERF_PREC_FP16F8, "unknown precision %d", cfg.precision);
   return 0;
 }
 
@@ -429,7 +434,8 @@ static void make_vf_plan(const vfnerf_mlp_desc& vf, int64_t n, int multires, int
 }
 
 static int tc_precision(int precision, const char* who) {
-  VFN_REQUIRE(precision == VFNERF_PREC_BF16 || precision == VFNERF_PREC_BF16X3, "%s: unknown precision %d", who, precision);
+  VFN_REQUIRE(precision == VFNERF_PREC_BF16 || precision == VFNERF_PREC_BF16X3 || precision == VFNERF_PREC_FP16F8,
+              "%s: unknown precision %d", who, precision);
   return 0;
 }
 
@@ -450,7 +456,7 @@ int64_t vfnerf_vf_workspace_bytes(const vfnerf_mlp_desc* vf, int64_t n_points, i
     int64_t bytes = 0;
     int skip = -1;
     for (int l = 1; l < vf->n_layers; ++l) if (vf->in_dim[l] != vf->out_dim[l - 1]) skip = l;
-    if (vf_tc_plan(*vf, multires, skip, nullptr, plan, bytes, n_points, keep_for_backward, precision == VFNERF_PREC_BF16X3)) return -1;
+    if (vf_tc_plan(*vf, multires, skip, nullptr, plan, bytes, n_points, keep_for_backward, split_mode(precision))) return -1;
     return bytes + 1024;
   }
   VfPlan p;
@@ -474,7 +480,7 @@ int vfnerf_vf_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, int multires
     TcPlan plan;
     int64_t bytes = 0;
     if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes, n_points, keep_for_backward,
-                           precision == VFNERF_PREC_BF16X3)) return e;
+                           split_mode(precision))) return e;
     VFN_REQUIRE(workspace && workspace_bytes >= bytes, "vf_fwd: workspace too small");
     if (int e = tc_prepare(*vf, vf_arena, nullptr, nullptr, bn_eps, plan, s)) return e;
     const bool full = n_out_cols > 3;
@@ -507,15 +513,15 @@ int vfnerf_mlp_points_fwd(const vfnerf_mlp_desc* vf, const float* vf_arena, cons
                           int64_t n_points, float* normals, float* colors, void* workspace,
                           int64_t workspace_bytes, int repack, void* stream) {
   VFN_REQUIRE(vf && vf_arena && rn && rn_arena && points && ray_dirs && normals && colors, "mlp_points_fwd: null argument");
-  VFN_REQUIRE(precision == VFNERF_PREC_BF16 || precision == VFNERF_PREC_BF16X3,
-              "mlp_points_fwd: only the tensor-core paths (bf16, bf16x3) implement this entry");
+  VFN_REQUIRE(precision == VFNERF_PREC_BF16 || precision == VFNERF_PREC_BF16X3 || precision == VFNERF_PREC_FP16F8,
+              "mlp_points_fwd: only the tensor-core paths (bf16, bf16x3, fp16f8) implement this entry");
   if (int e = validate_vf(*vf, multires, skip_layer)) return e;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   DeviceGuard dev_guard(s);
   TcPlan plan;
   int64_t off = 0;
   if (int e = tc_carve(reinterpret_cast<char*>(workspace), off, multires, multires_view, skip_layer, *vf, rn, plan, 0, 0,
-                       precision == VFNERF_PREC_BF16X3)) return e;
+                       split_mode(precision))) return e;
   VFN_REQUIRE(workspace && workspace_bytes >= off, "mlp_points_fwd: workspace too small");
   if (repack)
     if (int e = tc_prepare(*vf, vf_arena, rn, rn_arena, bn_eps, plan, s)) return e;
@@ -574,7 +580,7 @@ int vfnerf_vf_grid_query(const vfnerf_mlp_desc* vf, const float* vf_arena, int m
     if (int e = tc_precision(precision, "grid_query")) return e;
     TcPlan plan;
     int64_t bytes = 0;
-    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes, 0, 0, precision == VFNERF_PREC_BF16X3)) return e;
+    if (int e = vf_tc_plan(*vf, multires, skip_layer, workspace, plan, bytes, 0, 0, split_mode(precision))) return e;
     VFN_REQUIRE(workspace && workspace_bytes >= bytes, "grid_query: workspace too small");
     if (int e = tc_prepare(*vf, vf_arena, nullptr, nullptr, bn_eps, plan, s)) return e;
     return tc_forward(plan, TC_MODE_V_ONLY, nullptr, &gs, res, i0, n_points, nullptr, 0, out, 3, nullptr, 0, nullptr, s);

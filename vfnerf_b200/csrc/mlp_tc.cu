@@ -22,6 +22,8 @@
 // group g of layer l's output is in shared memory, so they trail the epilogue by about one chunk.
 // Weights: 1.1 MB (VF) + 0.6 MB (colour) bf16, L2 resident, re-streamed per tile.
 #include <cstdlib>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "mlp_tc.cuh"
 #include "tc_common.cuh"
 
@@ -42,7 +44,7 @@ template <> struct Lay<true> {
 };
 template <bool kX3> constexpr size_t tc_smem_bytes() {
   return (size_t)Lay<kX3>::cols * kTileM * 2 + (size_t)kTcStages * Lay<kX3>::stage_bytes + 512 +
-         (size_t)kTcMaxSteps * kTcMaxChunks * 16 + 128 + (size_t)2 * 3 * 256 * 4;
+         (size_t)kTcTableSteps * kTcMaxChunks * 16 + 128 + (size_t)2 * 3 * 256 * 4;
 }
 static_assert(tc_smem_bytes<true>() <= 227 * 1024 && tc_smem_bytes<false>() <= 227 * 1024, "activation tile + ring exceed shared memory");
 constexpr int kTcThreads = 480;      // warp 0 producer, warp 1 MMA/relay, warps 2..9 epilogue, warps 10..13 prologue,
@@ -127,7 +129,8 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
           float sh = b;
           if (bn) sh = arena[d.beta_off[l] + row] + (b - arena[d.mean_off[l] + row]) * sc;
           sh *= st.post_scale;
-          const float hi = __bfloat162float(__float2bfloat16(sh));
+          if (prog.f8) sh *= 0.5f;                    // the ones-columns of this tile hold 2.0 (mlp_tc.cuh)
+          const float hi = st.a_f16 ? __half2float(__float2half_rn(sh)) : __bfloat162float(__float2bfloat16(sh));
           w = kin == 0 ? hi : sh - hi;
         }
       } else {
@@ -162,11 +165,28 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
       }
       w *= st.seg_wscale[sg];
     }
+    const bool f16 = st.a_f16 != 0;
+    if (split && st.seg_f8[sg]) {
+      // fp16 + fp8-remainder segment: the hi half is fp16(W); the lo half holds, per 16-column unit, e5m2(2^-8 W) in its
+      // first kc * N/2 bytes (multiplies the e4m3 remainders of the activations) and e4m3(2^12 (W - fp16(W))) in the next
+      // kc * N/2 (multiplies the e5m2 copies of the activations)
+      const float hi = __half2float(__float2half_rn(w));
+      if (!is_lo) {
+        *reinterpret_cast<__half*>(wpack + off) = __float2half_rn(w);
+      } else {
+        const int64_t lo_base = base + (int64_t)ci * span * nh * 2 + (int64_t)kc * nh * 2;
+        const int64_t o8 = lo_base + (int64_t)(kk / 16) * nh * 16 + nn * 16 + (kk & 15);
+        wpack[o8] = (uint8_t)__nv_cvt_float_to_fp8(w * (1.f / kF8ScaleLo), __NV_SATFINITE, __NV_E5M2);
+        wpack[o8 + (int64_t)kc * nh] = (uint8_t)__nv_cvt_float_to_fp8((w - hi) * kF8ScaleHi, __NV_SATFINITE, __NV_E4M3);
+      }
+      continue;
+    }
     if (split) {
-      const float hi = __bfloat162float(__float2bfloat16(w));
+      const float hi = f16 ? __half2float(__float2half_rn(w)) : __bfloat162float(__float2bfloat16(w));
       if (is_lo) w -= hi;
     }
-    *reinterpret_cast<__nv_bfloat16*>(wpack + off) = __float2bfloat16(w);
+    if (f16) *reinterpret_cast<__half*>(wpack + off) = __float2half_rn(w);
+    else *reinterpret_cast<__nv_bfloat16*>(wpack + off) = __float2bfloat16(w);
   }
 }
 
@@ -226,6 +246,16 @@ __device__ __forceinline__ void store_slab_f(uint8_t* s_act, int slab, int row, 
   uint4 u;
   u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
   u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(s_act + slab * (kTileM * 16) + row * 16) = u;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void store_slab_h(uint8_t* s_act, int slab, int row, const float* f) {     // fp16 variant
+  uint4 u;
+  u.x = pack_f16x2(f[0], f[1]); u.y = pack_f16x2(f[2], f[3]);
+  u.z = pack_f16x2(f[4], f[5]); u.w = pack_f16x2(f[6], f[7]);
   *reinterpret_cast<uint4*>(s_act + slab * (kTileM * 16) + row * 16) = u;
 }
 __device__ __forceinline__ void store_slab_u(uint8_t* s_act, int slab, int row, uint32_t a, uint32_t b, uint32_t c,
@@ -362,6 +392,19 @@ __device__ __forceinline__ void umma2_bf16_split_w(uint32_t tmem_d, uint32_t a_l
       "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
       "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma2_f8_split_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                 uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma2_commit_u32_w(uint32_t bar) {
   asm volatile(
       "{\n\t"
@@ -407,10 +450,11 @@ constexpr bool kTcProfile = false;
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
-template <bool kBwd, bool kStash, bool kX3>
+template <bool kBwd, bool kStash, bool kX3, bool kF8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcParams p) {
   static_assert(!kX3 || (!kBwd && !kStash), "the split-precision tile is built for the forward-only programs");
+  static_assert(!kF8 || kX3, "the fp16 + fp8-remainder chain uses the split-precision tile");
   using L = Lay<kX3>;
   // epilogue order of the split-precision tile (see the activation-store loop): all eight warps on one 64-column group
   // at a time.  -DVFN_X3_SERIAL_GROUPS=0 builds the plain tile's order (two groups per warp half) for A/B timing.
@@ -418,17 +462,23 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #define VFN_X3_SERIAL_GROUPS 1
 #endif
   constexpr bool kSerialGroups = kX3 && VFN_X3_SERIAL_GROUPS;
+  static_assert(!kF8 || kSerialGroups, "the fp8 hand-off writes 32 columns per warp and iteration");
+  // weight ring.  The stream from L2 is latency-bound (a slot is busy for its fill latency + its wait + its MMAs, whatever
+  // its size; profiles/r02_forward_kernel_experiments.md), so the fp16 + fp8 chain, whose MMAs are short, runs the same 48 KiB
+  // as six 8 KiB slots (32 K columns per chunk) instead of three 16 KiB ones
   constexpr int kStageBytes = L::stage_bytes;
+  constexpr int kStages = kTcStages;
+  static_assert(kStages * kStageBytes == kTcStages * L::stage_bytes, "ring size is part of tc_smem_bytes");
   const int kdbg = kTcProfile ? p.dbg : 0;   // experiment switches (VFNERF_TC_DBG) exist in profile builds only
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcProgram& prog = p.prog;
   uint8_t* s_act = smem;
   uint8_t* s_stage = smem + L::cols * (kTileM * 2);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kTcStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kStages * kStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kTcStages;
-  uint64_t* fullp = bars + 2 * kTcStages;      // leader only: "the peer's half of the chunk has landed"
-  uint64_t* acc_full = bars + 3 * kTcStages;
+  uint64_t* empty = bars + kStages;
+  uint64_t* fullp = bars + 2 * kStages;      // leader only: "the peer's half of the chunk has landed"
+  uint64_t* acc_full = bars + 3 * kStages;
   // one "accumulator complete" barrier per TMEM accumulator buffer: buffer b is committed once per two steps, and the
   // MMAs of step g+2 depend (through the column-group barriers) on every epilogue warp having finished step g+1, hence
   // having passed its wait for step g -- the issuer can never complete a phase twice before a slow warp has seen it
@@ -452,7 +502,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   //   w = bit 0: last chunk of the step; bits 8..: split-precision "hi" chunk -- distance (16-byte units) from the hi
   //       to the lo copy of the A columns: the chunk's MMAs are issued a second time on the lo copy
   uint4* s_chunks = reinterpret_cast<uint4*>(bars + 64);
-  int* s_nchunks = reinterpret_cast<int*>(s_chunks + kTcMaxSteps * kTcMaxChunks);
+  int* s_nchunks = reinterpret_cast<int*>(s_chunks + kTcTableSteps * kTcMaxChunks);
   // fp32 rows (and biases) of the two 3-wide output layers the epilogue warps evaluate on the CUDA cores (TcStep::dot)
   float* s_dotb = reinterpret_cast<float*>(s_nchunks + kTcMaxSteps);          // [8]: vector bias 3, colour bias 3
   float* s_dotw = reinterpret_cast<float*>(s_nchunks) + 32;                   // [2][3][256]
@@ -461,7 +511,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   const uint32_t rank = cluster_ctarank();
   if (threadIdx.x == 0) {
     // leader: a ring slot is full when its own bulk copy has landed AND the peer's relay has arrived
-    for (int i = 0; i < kTcStages; ++i) { mbar_init(&full[i], rank == 0 ? 2 : 1); mbar_init(&empty[i], 1); mbar_init(&fullp[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], rank == 0 ? 2 : 1); mbar_init(&empty[i], 1); mbar_init(&fullp[i], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     // 4 warps (one half of the epilogue warps, or the prologue warps) x 2 CTAs; the split-precision tile's column groups
     // are written by all 8 epilogue warps
@@ -490,11 +540,17 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         need &= (uint32_t)st.fresh_mask & ~seen;
         seen |= need;
         const uint32_t a_off = (uint32_t)(col >> 3) * ((kTileM * 16u) >> 4), bytes = (uint32_t)((st.N >> 1) * kc * 2);
-        const uint32_t dual = (lo && st.use_lo) ? ((uint32_t)(lo >> 3) * ((kTileM * 16u) >> 4)) << 8 : 0u;
+        const bool f8seg = kF8 && st.seg_f8[sg] != 0;
+        const uint32_t dual = (lo && st.use_lo && !f8seg) ? ((uint32_t)(lo >> 3) * ((kTileM * 16u) >> 4)) << 8 : 0u;
         s_chunks[si * kTcMaxChunks + nc++] = make_uint4(a_off, (uint32_t)kc | (need << 16), bytes | (src16 << 16), dual);
         src16 += bytes >> 4;
         if (lo) {              // the image holds W_lo right after W_hi whether or not this program uses it
-          if (st.use_lo) s_chunks[si * kTcMaxChunks + nc++] = make_uint4(a_off, (uint32_t)kc, bytes | (src16 << 16), 0u);
+          if (st.use_lo) {
+            // fp8 remainder chunk (w bit 1): x = the e4m3 copy of these columns in the lo region (16 columns per unit)
+            const uint32_t a8 = ((uint32_t)((st.seg_col0[sg] + lo) >> 3) + (uint32_t)(k0 >> 4)) * ((kTileM * 16u) >> 4);
+            s_chunks[si * kTcMaxChunks + nc++] = f8seg ? make_uint4(a8, (uint32_t)kc, bytes | (src16 << 16), 2u)
+                                                       : make_uint4(a_off, (uint32_t)kc, bytes | (src16 << 16), 0u);
+          }
           src16 += bytes >> 4;
         }
       }
@@ -510,7 +566,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kTileM) {
     // constant ones-columns [1, 1, 0, ...] that pick up the bias row of every weight image
     const int r = threadIdx.x - 64;
-    store_slab_u(s_act, L::ones / 8, r, 0x3F803F80u, 0u, 0u, 0u);
+    store_slab_u(s_act, L::ones / 8, r, kF8 ? 0x40004000u : 0x3F803F80u, 0u, 0u, 0u);   // kF8: 2.0 in bf16 AND fp16
     store_slab_u(s_act, L::ones / 8 + 1, r, 0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
   }
@@ -550,7 +606,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               mbar_arrive_expect_tx(&full[stage], bytes);
               bulk_g2s(s_stage + stage * kStageBytes, src + (size_t)(c.z >> 16) * 16, bytes, &full[stage]);
             }
-            if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
             if (c.w & 1u) break;
           }
         }
@@ -566,7 +622,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           for (int c = 0; c < nc; ++c) {
             mbar_wait(&full[stage], phase);           // my half of the chunk is in my shared memory
             mbar_arrive_remote(&full[stage], 0);      // second arrival on the leader's "slot full" barrier
-            if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -591,7 +647,9 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         for (int si = 0; si < prog.n_steps; ++si, ++gstep) {
           const TcStep& st = prog.s[si];
           bool first_mma = true;
-          const uint32_t idesc = make_idesc_bf16(2 * kTileM, st.N);
+          const uint32_t idesc = (kF8 && st.a_f16) ? make_idesc_f16(2 * kTileM, st.N) : make_idesc_bf16(2 * kTileM, st.N);
+          // 8-bit remainder products: e4m3 activations x e5m2 weights, then e5m2 activations x e4m3 weights
+          const uint32_t idesc8a = make_idesc_f8(2 * kTileM, st.N, 0, 1), idesc8b = make_idesc_f8(2 * kTileM, st.N, 1, 0);
           // descriptor halves: only the start-address field of the low words changes between MMAs
           const uint32_t desc_hi = (128u >> 4) | (1u << 14);                   // SBO = 128 B, version 1
           const uint32_t a_lo0 = ((act_base >> 4) & 0x3FFF) | (((kTileM * 16u) >> 4) << 16);
@@ -616,6 +674,10 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             nxt.x = __shfl_sync(0xffffffffu, nxt.x, 0); nxt.y = __shfl_sync(0xffffffffu, nxt.y, 0); nxt.w = __shfl_sync(0xffffffffu, nxt.w, 0);
             // the A columns of this chunk must have been (re)written: wait for their readiness barrier(s) (at most two)
             uint32_t need = (ck.y >> 16) & fresh;
+            // tcgen05.fence::after_thread_sync orders this thread's MMAs after what OTHER threads did to the activation tile
+            // and the accumulator (their stores + tcgen05.ld) before they arrived on a group barrier: needed after a
+            // group / hand-off wait, not after the weight ring's "slot full" (a bulk copy completing on an mbarrier)
+            const bool synced = need != 0 || accumulate == 0;
             if (need) {
               int b = __ffs(need) - 1;
               mbar_wait_u32(grp_u32 + 8u * b, (grp_par >> b) & 1u);
@@ -630,13 +692,33 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             TCK(t_grp);
             mbar_wait_u32(full_u32 + 8u * stage, phase);   // both halves of the weight chunk have landed
             TCK(t_full);
-            tc_fence_after_sync();
+            if (synced) tc_fence_after_sync();
             const uint32_t a_lo = a_lo0 + ck.x;
             const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kStageBytes >> 4);
             constexpr uint32_t a_kstep = 2u * ((kTileM * 16u) >> 4);
             const int kc = (int)(ck.y & 0xFFFFu);
             if (tl && first_mma) { p.dbg_buf[64 + si * 8 + 0] = clock64(); first_mma = false; }
-            if constexpr (kX3) {
+            if (kF8 && (ck.w & 2u)) {
+              // fp8 remainder chunk: K = 32 per instruction, two 16-column units of A and of B each.  First half of the
+              // slot: e5m2(2^-8 W) against the e4m3 remainders; second half: e4m3(2^12 W_lo) against the e5m2 copies,
+              // which sit 16 slabs after the remainders
+              const uint32_t b2 = b_lo + (((uint32_t)(st.N >> 1) * (uint32_t)kc) >> 4);
+              const uint32_t a2 = a_lo + 16u * ((kTileM * 16u) >> 4);
+              uint32_t j = 0;
+              if (kc == 64) {
+                umma2_f8_split_w(acc, a_lo, desc_hi, b_lo, desc_hi, idesc8a, 1u);
+                umma2_f8_split_w(acc, a_lo + a_kstep, desc_hi, b_lo + b_kstep, desc_hi, idesc8a, 1u);
+                umma2_f8_split_w(acc, a2, desc_hi, b2, desc_hi, idesc8b, 1u);
+                umma2_f8_split_w(acc, a2 + a_kstep, desc_hi, b2 + b_kstep, desc_hi, idesc8b, 1u);
+              } else {
+              for (int kk = 0; kk < kc; kk += 32, ++j)
+                umma2_f8_split_w(acc, a_lo + j * a_kstep, desc_hi, b_lo + j * b_kstep, desc_hi, idesc8a, 1u);
+              j = 0;
+              for (int kk = 0; kk < kc; kk += 32, ++j)
+                umma2_f8_split_w(acc, a2 + j * a_kstep, desc_hi, b2 + j * b_kstep, desc_hi, idesc8b, 1u);
+              }
+              umma2_commit_u32_w(empty_u32 + 8u * stage);
+            } else if constexpr (kX3) {
               // 16 KiB ring slots: at most 64 K columns per chunk.  A split-precision "hi" chunk multiplies W_hi with
               // the hi AND the lo copy of the A columns (the weights are fetched once for both products); the "lo"
               // chunk that follows multiplies W_lo with the hi copy.
@@ -684,7 +766,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               umma2_commit_u32_w(empty_u32 + 8u * stage);    // ring slot (in both CTAs) reusable once these MMAs have read it
             }
             accumulate = 1;
-            if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
             if (ck.w & 1u) break;
             ck = nxt; ++ckp;
           }
@@ -829,11 +911,16 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float v = emb[sl * 8 + j];
-              hi[j] = __bfloat162float(__float2bfloat16(v));
+              hi[j] = kF8 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16(v));
               lo[j] = v - hi[j];
             }
-            store_slab_f(s_act, L::emb0 / 8 + sl, row, hi);
-            store_slab_f(s_act, L::emb0 / 8 + nsl + sl, row, lo);
+            if (kF8) {
+              store_slab_h(s_act, L::emb0 / 8 + sl, row, hi);
+              store_slab_h(s_act, L::emb0 / 8 + nsl + sl, row, lo);
+            } else {
+              store_slab_f(s_act, L::emb0 / 8 + sl, row, hi);
+              store_slab_f(s_act, L::emb0 / 8 + nsl + sl, row, lo);
+            }
             if (st_on) {
               *stash_unit(p, p.sinfo.idx_emb0, tile, sl, row) =
                   make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
@@ -1122,7 +1209,36 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               if (second) tmem_ld32(acc + c0 + 32, vb);
               tmem_ld_wait();
               TCK(t_ld);
-              if constexpr (kX3) {
+              if (kF8 && st.a_f16 && !feat) {
+                // fp16 + fp8-remainder hand-off of a VF hidden layer: y = relu(acc) leaves as fp16(y) in the main columns,
+                // e4m3(2^8 (y - fp16(y))) and e5m2(2^-12 y) in the lo region (16 columns per 16-byte unit there)
+                const uint32_t* v = va;            // (kSerialGroups: 32 columns per warp and iteration)
+                uint32_t r8[8], h8[8];
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                  uint32_t hi[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float y0 = fmaxf(__uint_as_float(v[8 * sl + 2 * j]), 0.f), y1 = fmaxf(__uint_as_float(v[8 * sl + 2 * j + 1]), 0.f);
+                    const __half2 hh = __floats2half2_rn(y0, y1);
+                    hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                    const float2 hf2 = __half22float2(hh);
+                    const uint32_t lo8 = __nv_cvt_float2_to_fp8x2(make_float2((y0 - hf2.x) * kF8ScaleLo, (y1 - hf2.y) * kF8ScaleLo),
+                                                                  __NV_SATFINITE, __NV_E4M3);
+                    const uint32_t hi8 = __nv_cvt_float2_to_fp8x2(make_float2(y0 * (1.f / kF8ScaleHi), y1 * (1.f / kF8ScaleHi)),
+                                                                  __NV_SATFINITE, __NV_E5M2);
+                    const int e = 4 * sl + j;        // 16-bit pair e of the 32 columns -> half of 32-bit word e / 2
+                    if (e & 1) { r8[e >> 1] |= lo8 << 16; h8[e >> 1] |= hi8 << 16; }
+                    else { r8[e >> 1] = lo8; h8[e >> 1] = hi8; }
+                  }
+                  store_slab_u(s_act, (c0 >> 3) + sl, row, hi[0], hi[1], hi[2], hi[3]);
+                }
+                const int u8 = L::lo / 8 + (c0 >> 4);
+                store_slab_u(s_act, u8, row, r8[0], r8[1], r8[2], r8[3]);
+                store_slab_u(s_act, u8 + 1, row, r8[4], r8[5], r8[6], r8[7]);
+                store_slab_u(s_act, u8 + 16, row, h8[0], h8[1], h8[2], h8[3]);
+                store_slab_u(s_act, u8 + 17, row, h8[4], h8[5], h8[6], h8[7]);
+              } else if constexpr (kX3) {
                 // split-precision hand-off: y = relu(acc) leaves as hi = bf16(y) in the main columns and, for the VF
                 // layers, lo = bf16(y - hi) in the lo columns (same slab, kX3ColLo further on)
                 const bool out_lo = st.out_lo != 0;
@@ -1256,7 +1372,7 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
   const int E = 3 + 6 * multires, Epad = round16(E);
   const int L = vf.n_layers;
   VFN_REQUIRE(Epad <= 48 && multires <= kMaxRes && multires_view <= kMaxRes, "tensor-core path: embedding too wide");
-  VFN_REQUIRE(L >= 3 && L + (rn ? rn->n_layers - 1 : 0) <= kTcMaxSteps, "tensor-core path: too many layers");
+  VFN_REQUIRE(L >= 3 && L + (rn ? rn->n_layers - 1 : 0) <= kTcTableSteps, "tensor-core path: too many layers");
   VFN_REQUIRE(skip_layer < 0 || (skip_layer >= 2 && skip_layer < L - 1), "tensor-core path: skip_layer=%d unsupported", skip_layer);
   for (int l = 0; l < L; ++l) {
     const int want_in = (l == 0) ? E : 256;
@@ -1266,8 +1382,9 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
                 l, vf.in_dim[l], vf.out_dim[l]);
   }
   TcProgram pr{};
+  const int f8 = x3 == 2;
   auto layout = [&](TcProgram& q, int is_x3) {
-    q.x3 = is_x3;
+    q.x3 = is_x3 ? 1 : 0; q.f8 = is_x3 == 2;
     q.col_aux = is_x3 ? kX3ColAux : kColAux; q.col_skip = is_x3 ? -1 : kColSkip; q.col_ones = is_x3 ? kX3ColOnes : kColOnes;
     q.col_emb0 = is_x3 ? kX3ColEmb0 : kColEmb0; q.col_lo = is_x3 ? kX3ColLo : 0;
   };
@@ -1289,12 +1406,16 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
     TcStep& s = pr.s[ns];
     s = TcStep{};
     s.N = N; s.n_valid = n_valid; s.n_seg = nseg + (no_bias ? 0 : 1); s.K = 0;
-    for (int i = 0; i < kTcMaxSegs; ++i) { s.seg_lo[i] = 0; s.seg_wscale[i] = 1.f; }
+    for (int i = 0; i < kTcMaxSegs; ++i) { s.seg_lo[i] = 0; s.seg_wscale[i] = 1.f; s.seg_f8[i] = 0; }
     for (int i = 0; i < nseg; ++i) {
       s.seg_col0[i] = col0[i]; s.seg_k[i] = segk[i];
       s.seg_lo[i] = seglo ? seglo[i] : 0; s.seg_wscale[i] = segw ? segw[i] : 1.f;
+      // fp16 + fp8 remainders: the 256-wide main segments of the VF steps (the small embedding segments keep three
+      // 16-bit products, in fp16)
+      s.seg_f8[i] = (f8 && net == 0 && s.seg_lo[i] == kX3ColLo) ? 1 : 0;
       s.K += segk[i] * (s.seg_lo[i] ? 2 : 1);
     }
+    s.a_f16 = (f8 && net == 0) ? 1 : 0;
     if (!no_bias) { s.seg_col0[nseg] = pr.col_ones; s.seg_k[nseg] = 16; s.K += 16; }
     s.use_lo = seglo ? 1 : 0; s.out_lo = 0;
     s.no_bias = no_bias; s.stash_out = -1; s.mask_src = -1;
@@ -1381,6 +1502,16 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
       if (g < q.n_steps) q.s[g].pre_wait_mask |= 1 << kBarDot; else q.s[g - q.n_steps].dot_guard_next = 1;
     }
   };
+  for (int i = 0; i < ns; ++i)
+    for (int g = 0; g < pr.s[i].n_seg; ++g)
+      VFN_REQUIRE(!pr.s[i].seg_f8[g] || pr.s[i].seg_k[g] % 32 == 0, "tensor-core path (fp16f8): segment of %d columns is not a "
+                  "multiple of 32", pr.s[i].seg_k[g]);
+  for (int i = 0; i < ns; ++i) {
+    int nc = 0;
+    for (int g = 0; g < pr.s[i].n_seg; ++g)
+      nc += (pr.s[i].seg_k[g] + pr.s[i].chunk_k - 1) / pr.s[i].chunk_k * (pr.s[i].seg_lo[g] ? 2 : 1);
+    VFN_REQUIRE(nc <= kTcMaxChunks, "tensor-core path: step %d needs %d pipeline chunks (max %d)", i, nc, kTcMaxChunks);
+  }
   plan.render = pr;
   if (x3 && rn) plan.render.s[n_v].use_lo = 0;
   plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.render = 0; plan.vf_full.aux_step = -1;
@@ -1473,7 +1604,7 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
 
 int tc_carve(char* base, int64_t& off, int multires, int multires_view, int skip_layer,
              const vfnerf_mlp_desc& vf, const vfnerf_mlp_desc* rn, TcPlan& plan, int64_t n_points, int keep, int x3) {
-  VFN_REQUIRE(!(x3 && keep), "precision bf16x3 is forward-only: train with precision bf16 or fp32");
+  VFN_REQUIRE(!(x3 && keep), "precisions bf16x3 / fp16f8 are forward-only: train with precision bf16 or fp32");
   if (int e = build_programs(multires, multires_view, skip_layer, vf, rn, plan, x3)) return e;
   off = align_up(off, 1024);
   plan.wpack = base ? reinterpret_cast<uint8_t*>(base + off) : nullptr;
@@ -1570,14 +1701,16 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
     VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VFN_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VFN_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
   }
   const int64_t tiles = (n + kTileM - 1) / kTileM;
   const int64_t pairs = (tiles + 1) / 2;
   const int grid_x = 2 * (int)std::min<int64_t>(pairs, (int64_t)(num_sms[dev] / 2));
   if (p.prog.x3) {
-    VFN_REQUIRE(!is_bwd && !stashing, "tc_forward: precision bf16x3 is forward-only");
-    mlp_tc_kernel<false, false, true><<<grid_x, kTcThreads, tc_smem_bytes<true>(), s>>>(p);
+    VFN_REQUIRE(!is_bwd && !stashing, "tc_forward: precisions bf16x3 / fp16f8 are forward-only");
+    if (p.prog.f8) mlp_tc_kernel<false, false, true, true><<<grid_x, kTcThreads, tc_smem_bytes<true>(), s>>>(p);
+    else mlp_tc_kernel<false, false, true><<<grid_x, kTcThreads, tc_smem_bytes<true>(), s>>>(p);
   } else {
     const size_t smem = tc_smem_bytes<false>();
     if (is_bwd) mlp_tc_kernel<true, true, false><<<grid_x, kTcThreads, smem, s>>>(p);

@@ -6,7 +6,9 @@ namespace vfn {
 
 constexpr int kTcMaxSteps = 16;
 constexpr int kTcMaxSegs = 3;
-constexpr int kTcMaxChunks = 16;   // pipeline chunks per step (split-precision steps: hi + lo chunk per K range + bias)
+constexpr int kTcMaxChunks = 20;   // pipeline chunks per step (split-precision steps: hi + lo chunk per K range + bias)
+constexpr int kTcTableSteps = 13;  // steps of the longest program (render(): 8 + 1 + 4; its dgrad chain: 5 + 8) -- rows of the
+                                   // shared-memory chunk table
 
 // Activation-tile column map (bf16 columns of the 128-row A operand, K-slab layout, tc_common.cuh):
 //   [0,256)    main: current layer input / output (step 0 reads the hi/lo embedding from [0, 2*emb_pad))
@@ -25,6 +27,16 @@ constexpr int kColAux = 256, kColSkip = 304, kColOnes = 352, kColEmb0 = 368, kAc
 // embedding with its weights scaled by 1/sqrt(2).  The colour net stays plain bf16 (its error is 2e-4).
 //   [0,256) main hi | [256,304) aux | [304,320) ones | [320,416) emb0 hi|lo | [416,672) main lo
 constexpr int kX3ColAux = 256, kX3ColOnes = 304, kX3ColEmb0 = 320, kX3ColLo = 416, kX3ActCols = 672;
+// fp16 + fp8 remainders (VFNERF_PREC_FP16F8): the same tile, but a VF product is
+//   acc += A16 W16^T  +  e4m3(2^8 (A - A16)) e5m2(2^-8 W)^T  +  e5m2(2^-12 A) e4m3(2^12 (W - W16))^T
+// with A16 / W16 the fp16 roundings: one 16-bit MMA (K = 16) plus two 8-bit MMAs (kind::f8f6f4, K = 32 at the same issue
+// cost: profiles/probe_f8.py) per 16 K columns instead of three 16-bit ones -- 2 tensor-core units per product, not 3.
+// The remainders are 2^-12 of the product, so the 3-4 mantissa bits of the 8-bit formats leave ~2^-15 (measured against
+// the reference goldens: normals 9e-4 vs 2.7e-4 for bf16x3 and 1.4e-1 for bf16); the power-of-two scales keep both 8-bit
+// operands in their normal ranges (activations O(1), folded weights O(0.1)).  The lo columns [416,672) hold the two
+// 8-bit copies of the main columns: e4m3 remainders in slabs 0..15 (16 columns per 16-byte unit), e5m2 values in 16..31.
+// The ones-columns hold 2.0 -- the same bit pattern in bf16 and fp16 -- and the packed bias rows are halved.
+constexpr float kF8ScaleLo = 256.f, kF8ScaleHi = 4096.f;
 
 // One GEMM step of the fused chain: acc[128 x N] = sum over segments A[:, col0 : col0+k] * Wimg^T, then an epilogue.
 struct TcStep {
@@ -37,6 +49,9 @@ struct TcStep {
                               // this segment's A operand (0: plain segment).  The weight image then holds, per K chunk,
                               // the bf16 weights W_hi followed by the remainders W_lo
   float seg_wscale[kTcMaxSegs];   // extra factor on this segment's weights (skip-layer embedding columns: 1/sqrt(2))
+  int seg_f8[kTcMaxSegs];     // fp16 + fp8-remainder segment (VFNERF_PREC_FP16F8, below): the "lo" half of every chunk of the
+                              // weight image holds two 8-bit images instead of one 16-bit image
+  int a_f16;      // this step's 16-bit operands (activations, weights, bias pair) are fp16, not bf16
   int use_lo;     // this program issues the lo products of the split segments (0: only A_hi W_hi^T, e.g. the feature step
                   // inside render(), whose output is rounded to bf16 for the colour net anyway)
   int out_lo;     // epilogue also writes the lo copy of its output (the next step is a split-precision step)
@@ -103,6 +118,7 @@ struct TcProgram {
   int aux_step;     // index of the step that consumes the aux columns (-1: none)
   int bwd;          // 1: backward (dgrad) program of render() -- different prologue, no bias segments; 2: of the VF net alone
   int x3;           // split-precision tile layout (kX3Col*), 16 KiB ring slots
+  int f8;           // fp16 + fp8-remainder variant of the split-precision tile (implies x3)
   int emb0_last_step;   // the emb0 columns may be rewritten for the next tile once this step's MMAs have completed
   int dot_step[2];      // steps with TcStep::dot, in order (-1: none)
   int col_aux, col_skip, col_ones, col_emb0, col_lo;   // activation-tile layout of this program

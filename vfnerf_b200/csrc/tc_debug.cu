@@ -5,6 +5,8 @@
 // TEST-ONLY translation unit: part of libvfnerf_b200_debug.so (vfnerf_b200/_lib.py: build_debug), never of the product
 // library.  Declarations: include/vfnerf_b200_debug.h.
 #include "common.cuh"
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "tc_common.cuh"
 #include "../../include/vfnerf_b200_debug.h"
 
@@ -252,6 +254,82 @@ extern "C" int vfnerf_debug_umma2_gemm(const float* A, const float* B, float* D,
   return 0;
 }
 
+// ---- 2-CTA convention check for the other operand kinds the split-precision chain uses: kind::f16 with fp16 operands
+// (fmt 2) and kind::f8f6f4 with 8-bit operands (a_fmt / b_fmt: 0 = e4m3, 1 = e5m2; K = 32 per instruction).  Same data
+// placement as umma2_debug_kernel; the 8-bit K-slab holds 16 columns per 16-byte unit:
+//   byte(r, k) = (k / 16) * rows * 16 + r * 16 + (k % 16)
+namespace vfn {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+umma2_alt_debug_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K,
+                       int a_fmt, int b_fmt) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = cluster_ctarank();
+  const int Nh = N / 2;
+  const bool f16 = a_fmt == 2;
+  const int esz = f16 ? 2 : 1, per = 16 / esz;           // elements per 16-byte unit
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * K * esz;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  auto put = [&](uint8_t* base, int rows, int r, int k, float v, int fmt) {
+    uint8_t* q = base + (size_t)(k / per) * rows * 16 + r * 16 + (k % per) * esz;
+    if (f16) *reinterpret_cast<__half*>(q) = __float2half_rn(v);
+    else *q = (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, fmt ? __NV_E5M2 : __NV_E4M3);
+  };
+  for (int e = tid; e < 128 * K; e += 128) put(sA, 128, e / K, e % K, A[(int64_t)(rank * 128 + e / K) * K + e % K], a_fmt);
+  for (int e = tid; e < Nh * K; e += 128) put(sB, Nh, e / K, e % K, B[(int64_t)(rank * Nh + e / K) * K + e % K], b_fmt);
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = f16 ? make_idesc_f16(256, N) : make_idesc_f8(256, N, a_fmt, b_fmt);
+    const int kstep = f16 ? 16 : 32;                       // two 16-byte units per instruction either way
+    for (int k0 = 0; k0 < K; k0 += kstep) {
+      const uint64_t da = make_smem_desc(smem_u32(sA) + (k0 / per) * slab_bytes(128), slab_bytes(128), 128);
+      const uint64_t db = make_smem_desc(smem_u32(sB) + (k0 / per) * slab_bytes(Nh), slab_bytes(Nh), 128);
+      if (f16)
+        umma2_bf16_split_w1(tmem, (uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32), idesc, (uint32_t)(k0 > 0));
+      else
+        umma2_f8_split_w1(tmem, (uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32), idesc, (uint32_t)(k0 > 0));
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(int64_t)(rank * 128 + row) * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+}
+}  // namespace vfn
+
+extern "C" int vfnerf_debug_umma2_alt_gemm(const float* A, const float* B, float* D, int N, int K, int a_fmt, int b_fmt,
+                                           void* stream) {
+  using namespace vfn;
+  VFN_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256 && K % 32 == 0 && K >= 32 && K <= 256, "debug_umma2_alt_gemm: bad N/K");
+  VFN_REQUIRE((a_fmt == 2 && b_fmt == 2) || (a_fmt >= 0 && a_fmt <= 1 && b_fmt >= 0 && b_fmt <= 1), "debug_umma2_alt_gemm: formats");
+  size_t smem = (size_t)(128 + N / 2) * K * 2;
+  VFN_CHECK_CUDA(cudaFuncSetAttribute(umma2_alt_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma2_alt_debug_kernel<<<2, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(A, B, D, N, K, a_fmt, b_fmt);
+  VFN_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- layout probe: tcgen05.mma.cta_group::2 with M = 128 (64 rows per CTA).  Dumps all 128 TMEM lanes x 512 columns of
 // both CTAs so the test can see where the 64 x N accumulator of each CTA lands, and whether it can be placed at a lane
 // offset (two 64-row sub-tiles side by side in the lanes of the same columns).
@@ -358,7 +436,10 @@ umma2_bench_kernel(int n_mma, int mode, long long* out) {
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   if (rank == 0 && tid == 0) {
-    const uint32_t idesc = make_idesc_bf16((mode & 4) ? 128 : 256, (mode & 8) ? 128 : 256);   // mode bit 2: M = 128 (64 rows per CTA); bit 3: N = 128
+    const bool f8_all = (mode & 16) != 0;                                                    // mode bit 4: kind::f8f6f4 (e4m3 x e5m2, K = 32)
+    const uint32_t idesc_8 = make_idesc_f8((mode & 4) ? 128 : 256, (mode & 8) ? 128 : 256, 0, 1);
+    const uint32_t idesc_16 = (mode & 128) ? make_idesc_f16((mode & 4) ? 128 : 256, (mode & 8) ? 128 : 256)      // bit 7: fp16 operands
+                                           : make_idesc_bf16((mode & 4) ? 128 : 256, (mode & 8) ? 128 : 256);   // mode bit 2: M = 128 (64 rows per CTA); bit 3: N = 128
     const uint64_t da0 = make_smem_desc(smem_u32(smem), slab_bytes(128), 128);
     const uint64_t db0 = make_smem_desc(smem_u32(smem + 64 * 1024), slab_bytes(128), 128);
     const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32), a_lo0 = (uint32_t)da0, b_lo0 = (uint32_t)db0;
@@ -366,8 +447,14 @@ umma2_bench_kernel(int n_mma, int mode, long long* out) {
     long long t0 = clock64();
     for (int i = 0; i < n_mma; i += 4) {
       const uint32_t base = (uint32_t)((i >> 2) & 3) * 4u;
+      // mode bit 5: alternate the kind every 4 instructions (16-bit, 8-bit, 16-bit, ...); bit 6: every 16
+      const bool f8 = (mode & 32) ? (((i >> 2) & 1) != 0) : ((mode & 64) ? (((i >> 4) & 1) != 0) : f8_all);
+      const uint32_t idesc = f8 ? idesc_8 : idesc_16;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        if (f8)
+          umma2_f8_split_w1(tmem, a_lo0 + (base + j) * step, a_hi, b_lo0 + (base + j) * step, b_hi, idesc, (uint32_t)((i | j) > 0));
+        else
         asm volatile(
             "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
             "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"

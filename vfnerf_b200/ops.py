@@ -221,7 +221,7 @@ def mlp_points(vf_net, rn_net, points: torch.Tensor, ray_dirs: torch.Tensor, sam
     with _on_device(dev):
         _lib.check(L.vfnerf_mlp_points_fwd(C.byref(va.desc), va.flat.data_ptr(), C.byref(ra.desc), ra.flat.data_ptr(),
                                            vf_net.multires, rn_net.multires_view, vf_net.skip_layer, 1e-5,
-                                           _lib.PREC_BF16X3 if vf_net.precision == "bf16x3" else _lib.PREC_BF16,
+                                           _lib.PRECISIONS[vf_net.precision] if vf_net.precision != "fp32" else _lib.PREC_BF16,
                                            points.data_ptr(), ray_dirs.data_ptr(), int(samples_per_ray), P, normals.data_ptr(),
                                            colors.data_ptr(), workspace.data_ptr(), workspace.numel(), int(repack),
                                            _stream_ptr(dev)), "vfnerf_mlp_points_fwd")
