@@ -440,8 +440,10 @@ def main():
                              "normals": out.coarse_normals.reshape(-1, 3), "supervised_normals": None,
                              "directional_derivatives": None}, {"rgb": rgb_t, "depth": dep_t}, 0)[0]
 
-        def time_train(prec, n_tr, arena=False):
+        def time_train(prec, n_tr, arena=False, train_mode=False):
             tm = U.make_model(dict(CASE, perturb=True, dir_to_normal_th=-2.0), st, dev, precision=prec)
+            if train_mode:
+                tm.train()          # batch-statistic BatchNorm + Jacobian + directional derivatives (csrc/mlp_train.cu)
             if arena:
                 from vfnerf_b200 import optim as voptim
                 voptim.use_arena_optimizer(tm, max_norm=0.5)
@@ -468,6 +470,9 @@ def main():
                  "includes": "eager: render fwd + fused VFLoss + backward + (allreduce) + clip_grad_norm_ + Adam"}
         if train_prec != "fp32" and not args.no_extra:
             train["fp32_ms_per_step"] = time_train("fp32", 3)
+            # model.train(): what the reference trainer runs when the directional-derivative weight is non-zero
+            # (train/vector_field_nerf_train.py:140-141) -- fp32 layer-wise path, three extra reverse sweeps for the Jacobian
+            train["train_mode_fp32_ms_per_step"] = time_train("fp32", 3, train_mode=True)
         ms_ar = time_train(train_prec, 10, arena=True)
         train["arena_adam_eager"] = {"ms_per_step": ms_ar, "value": world * Rt / (ms_ar * 1e-3), "unit": "rays/s",
                                      "collective": "ONE ncclAllReduce(avg) over the single 3.2 MB gradient tensor (VF | colour | "
