@@ -162,3 +162,31 @@ def test_full_size_chunk_invariance_and_properties(built_lib, precision, R, chun
     assert (whole.coarse_depth_map >= 0).all() and (whole.coarse_depth_map <= case["far"] + case["fine_range"] + 1e-4).all()
     assert torch.isfinite(whole.coarse_normals).all() and (whole.coarse_normals.abs() <= 1).all()
     assert w_whole.sum().item() > 0          # the synthetic scene is not empty
+
+
+def test_render_empty_batch_and_maximum_sample_count(built_lib):
+    """Edge cases of the fused per-ray kernels (csrc/render_fused.cu): zero rays (a no-op that still returns correctly shaped
+    outputs), and 128 + 128 samples per ray -- VFNERF_MAX_SAMPLES, the 8-samples-per-lane instantiations -- vs the oracle."""
+    case, z = U.load_golden("small_perturb")
+    st = U.case_state(case, z)
+    model = U.make_model(case, st, DEV)
+    with torch.no_grad():
+        out = model.render(torch.zeros(0, 4, 4, device=DEV), torch.zeros(0, 2, device=DEV), torch.zeros(0, 4, 4, device=DEV), 0)
+    assert out.coarse_rgb_values.shape == (0, 3) and out.z_vals.shape[0] == 0 and out.coarse_normals.shape[0] == 0
+    big = dict(case, n_coarse=128, n_fine=128, max_samples=128)
+    model = U.make_model(big, st, DEV)
+    R = 37
+    uv, pose, K = U.S.synthetic_rays(R, seed=3, start=5, stride=1013)
+    draws = U.S.synthetic_draws(R, 128, 128, seed=21)
+    with torch.no_grad():
+        ora = U.O.render(st["vf_net"], st["rendering_net"], st["density"], U.oracle_cfg(big), uv, pose, K,
+                         torch.linspace(0., 1., 128), *draws)
+        out = model.render(pose.to(DEV), uv.to(DEV), K.to(DEV), 0, draws=draws)
+    assert out.z_vals.shape == (R, 256)
+    same = (out.z_vals.cpu() == ora["z_vals"]).all(dim=1)
+    assert same.float().mean().item() >= 0.9
+    ok = same & U.discontinuity_guard(ora, big)
+    assert torch.equal(out.points_coarse.cpu()[same], ora["points"][same])
+    assert (out.coarse_normals.cpu() - ora["normals"])[same].abs().max().item() <= 1e-3
+    assert (out.coarse_rgb_values.cpu() - ora["rgb"])[ok].abs().max().item() <= 1e-3
+    assert (out.coarse_depth_map.cpu() - ora["depth"])[ok].abs().max().item() <= 2e-3

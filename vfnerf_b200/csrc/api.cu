@@ -249,6 +249,7 @@ int vfnerf_render_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, c
   DeviceGuard dev_guard(s);
   RenderPlan p;
   if (int e = make_plan(*cfg, *vf, *rn, keep_for_backward, workspace, p, z_override != nullptr)) return e;
+  if (p.R == 0) return 0;          // an empty batch is a no-op (its output tensors have no storage to point at)
   VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "render_fwd: workspace %lld B < required %lld B",
               (long long)workspace_bytes, (long long)p.bytes);
   VFN_REQUIRE(out->points && out->normals && out->rgb && out->depth && out->z_vals && out->colors,

@@ -167,8 +167,8 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
     }
     const bool f16 = st.a_f16 != 0;
     if (split && st.seg_f8[sg]) {
-      // fp16 + fp8-remainder segment: the hi half is fp16(W); the lo half holds, per 16-column unit, e5m2(2^-8 W) in its
-      // first kc * N/2 bytes (multiplies the e4m3 remainders of the activations) and e4m3(2^12 (W - fp16(W))) in the next
+      // fp16 + fp8-remainder segment: the hi half is fp16(W); the lo half holds, per 16-column unit, e4m3(W) in its
+      // first kc * N/2 bytes (multiplies the e5m2 remainders of the activations) and e4m3(2^12 (W - fp16(W))) in the next
       // kc * N/2 (multiplies the e5m2 copies of the activations)
       const float hi = __half2float(__float2half_rn(w));
       if (!is_lo) {
@@ -176,7 +176,7 @@ __global__ void tc_pack_kernel(TcProgram prog, vfnerf_mlp_desc vf, const float* 
       } else {
         const int64_t lo_base = base + (int64_t)ci * span * nh * 2 + (int64_t)kc * nh * 2;
         const int64_t o8 = lo_base + (int64_t)(kk / 16) * nh * 16 + nn * 16 + (kk & 15);
-        wpack[o8] = (uint8_t)__nv_cvt_float_to_fp8(w * (1.f / kF8ScaleLo), __NV_SATFINITE, __NV_E5M2);
+        wpack[o8] = (uint8_t)__nv_cvt_float_to_fp8(w, __NV_SATFINITE, __NV_E4M3);
         wpack[o8 + (int64_t)kc * nh] = (uint8_t)__nv_cvt_float_to_fp8((w - hi) * kF8ScaleHi, __NV_SATFINITE, __NV_E4M3);
       }
       continue;
@@ -648,8 +648,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const TcStep& st = prog.s[si];
           bool first_mma = true;
           const uint32_t idesc = (kF8 && st.a_f16) ? make_idesc_f16(2 * kTileM, st.N) : make_idesc_bf16(2 * kTileM, st.N);
-          // 8-bit remainder products: e4m3 activations x e5m2 weights, then e5m2 activations x e4m3 weights
-          const uint32_t idesc8a = make_idesc_f8(2 * kTileM, st.N, 0, 1), idesc8b = make_idesc_f8(2 * kTileM, st.N, 1, 0);
+          // 8-bit remainder products: e5m2 activations (remainders, then scaled copies) x e4m3 weights
+          const uint32_t idesc8a = make_idesc_f8(2 * kTileM, st.N, 1, 0), idesc8b = idesc8a;
           // descriptor halves: only the start-address field of the low words changes between MMAs
           const uint32_t desc_hi = (128u >> 4) | (1u << 14);                   // SBO = 128 B, version 1
           const uint32_t a_lo0 = ((act_base >> 4) & 0x3FFF) | (((kTileM * 16u) >> 4) << 16);
@@ -700,7 +700,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             if (tl && first_mma) { p.dbg_buf[64 + si * 8 + 0] = clock64(); first_mma = false; }
             if (kF8 && (ck.w & 2u)) {
               // fp8 remainder chunk: K = 32 per instruction, two 16-column units of A and of B each.  First half of the
-              // slot: e5m2(2^-8 W) against the e4m3 remainders; second half: e4m3(2^12 W_lo) against the e5m2 copies,
+              // slot: e4m3(W) against the e5m2 remainders; second half: e4m3(2^12 W_lo) against the e5m2 copies,
               // which sit 16 slabs after the remainders
               const uint32_t b2 = b_lo + (((uint32_t)(st.N >> 1) * (uint32_t)kc) >> 4);
               const uint32_t a2 = a_lo + 16u * ((kTileM * 16u) >> 4);
@@ -1211,7 +1211,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               TCK(t_ld);
               if (kF8 && st.a_f16 && !feat) {
                 // fp16 + fp8-remainder hand-off of a VF hidden layer: y = relu(acc) leaves as fp16(y) in the main columns,
-                // e4m3(2^8 (y - fp16(y))) and e5m2(2^-12 y) in the lo region (16 columns per 16-byte unit there)
+                // e5m2(y - fp16(y)) and e5m2(2^-12 y) in the lo region (16 columns per 16-byte unit there)
                 const uint32_t* v = va;            // (kSerialGroups: 32 columns per warp and iteration)
                 uint32_t r8[8], h8[8];
 #pragma unroll
@@ -1223,8 +1223,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                     const __half2 hh = __floats2half2_rn(y0, y1);
                     hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
                     const float2 hf2 = __half22float2(hh);
-                    const uint32_t lo8 = __nv_cvt_float2_to_fp8x2(make_float2((y0 - hf2.x) * kF8ScaleLo, (y1 - hf2.y) * kF8ScaleLo),
-                                                                  __NV_SATFINITE, __NV_E4M3);
+                    const uint32_t lo8 = __nv_cvt_float2_to_fp8x2(make_float2(y0 - hf2.x, y1 - hf2.y), __NV_SATFINITE, __NV_E5M2);
                     const uint32_t hi8 = __nv_cvt_float2_to_fp8x2(make_float2(y0 * (1.f / kF8ScaleHi), y1 * (1.f / kF8ScaleHi)),
                                                                   __NV_SATFINITE, __NV_E5M2);
                     const int e = 4 * sl + j;        // 16-bit pair e of the 32 columns -> half of 32-bit word e / 2

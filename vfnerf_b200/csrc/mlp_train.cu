@@ -498,6 +498,7 @@ int vfnerf_render_train_fwd(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc*
   DeviceGuard dev_guard(s);
   TrainPlan p;
   if (int e = make_train_plan(*cfg, *vf, *rn, workspace, p)) return e;
+  if (p.R == 0) return 0;
   VFN_REQUIRE(workspace && workspace_bytes >= p.bytes, "render_train_fwd: workspace %lld B < required %lld B",
               (long long)workspace_bytes, (long long)p.bytes);
   VFN_REQUIRE(out->points && out->normals && out->rgb && out->depth && out->z_vals && out->colors,
