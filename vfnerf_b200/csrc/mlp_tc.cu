@@ -57,8 +57,20 @@ constexpr float kInvSqrt2 = 0.70710678118654752f;
 constexpr int kGroups = 9, kBarAux = 4, kBarSkip = 5, kBarEmb0 = 6, kBarAuxStatic = 7,
               kBarDot = 8;   // 8: the prologue warps have read the accumulator row of a TcStep::dot step (both CTAs)
 
+// One pipeline chunk of a step (= one weight-ring slot), as the producer and the MMA issuer see it:
+//   x = A start-address increment (16-byte units), y = K columns | readiness-barrier mask << 16,
+//   z = bytes of this CTA's half of the weight chunk | (its offset inside the step's half image / 16) << 16,
+//   w = bit 0: last chunk of the step; bit 1: fp8 remainder chunk; bits 8..: split-precision "hi" chunk -- distance
+//       (16-byte units) from the hi to the lo copy of the A columns: the chunk's MMAs are issued a second time on the lo copy
+struct TcChunk { uint32_t x, y, z, w; };
+
 struct TcParams {
   TcProgram prog;
+  // the chunk records of every step, built on the host (tc_chunk_records): the MMA-issuing warp reads them from the
+  // parameter constant bank with a warp-uniform index, so every descriptor word it forms lives in uniform registers and
+  // a tcgen05.mma costs it ~4 uniform-datapath instructions (from a shared-memory table + shuffles the compiler wrapped
+  // every MMA in ELECT / 8 x R2UR.BROADCAST: profiles/r02_forward_kernel_experiments.md, section 4)
+  TcChunk ctab[kTcTableSteps * kTcMaxChunks + 1];   // + 1: the issuer reads one record ahead
   const uint8_t* wpack;
   const float* points;
   int use_grid;
@@ -322,10 +334,9 @@ __device__ __forceinline__ uint2* gate_unit(const TcParams& p, int t, long long 
 }
 
 // readiness barriers (bit mask) that guard the 64-column chunk starting at activation-tile column `col`
-template <bool kX3>
-__device__ __forceinline__ uint32_t col_barriers(int col) {
+__host__ __device__ inline uint32_t col_barriers(bool x3, int col) {
   if (col < kColAux) return 1u << (col >> 6);
-  if (kX3) {
+  if (x3) {
     if (col < kX3ColOnes) return (1u << kBarAux) | (1u << kBarAuxStatic);
     if (col < kX3ColEmb0) return 0u;
     if (col < kX3ColLo) return 1u << kBarEmb0;
@@ -335,6 +346,43 @@ __device__ __forceinline__ uint32_t col_barriers(int col) {
   if (col < kColOnes) return 1u << kBarSkip;
   if (col < kColEmb0) return 0u;
   return 1u << kBarEmb0;
+}
+
+// The chunk records of step `si` (at most kTcMaxChunks): run by the host for TcParams::ctab (MMA issuer) and by one
+// thread per step inside the kernel for the shared-memory copy the weight producer and the relay lane walk.
+__host__ __device__ inline int tc_chunk_records(const TcProgram& prog, int si, TcChunk* out) {
+  const TcStep& st = prog.s[si];
+  const bool x3 = prog.x3 != 0, f8 = prog.f8 != 0;
+  constexpr uint32_t kSlabUnits = (kTileM * 16u) >> 4;     // 16-byte units per K-slab of the activation tile
+  uint32_t seen = 0, src16 = 0;
+  int nc = 0;
+  for (int sg = 0; sg < st.n_seg; ++sg) {
+    const int lo = st.seg_lo[sg];
+    for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
+      const int kc = (st.chunk_k < st.seg_k[sg] - k0) ? st.chunk_k : st.seg_k[sg] - k0;
+      const int col = st.seg_col0[sg] + k0;
+      uint32_t need = 0;
+      for (int cc = col; cc < col + kc; cc += 64) need |= col_barriers(x3, cc);
+      need &= (uint32_t)st.fresh_mask & ~seen;
+      seen |= need;
+      const uint32_t a_off = (uint32_t)(col >> 3) * kSlabUnits, bytes = (uint32_t)((st.N >> 1) * kc * 2);
+      const bool f8seg = f8 && st.seg_f8[sg] != 0;
+      const uint32_t dual = (lo && st.use_lo && !f8seg) ? ((uint32_t)(lo >> 3) * kSlabUnits) << 8 : 0u;
+      out[nc++] = TcChunk{a_off, (uint32_t)kc | (need << 16), bytes | (src16 << 16), dual};
+      src16 += bytes >> 4;
+      if (lo) {              // the image holds W_lo right after W_hi whether or not this program uses it
+        if (st.use_lo) {
+          // fp8 remainder chunk (w bit 1): x = the e5m2 remainders of these columns in the lo region (16 columns per unit)
+          const uint32_t a8 = ((uint32_t)((st.seg_col0[sg] + lo) >> 3) + (uint32_t)(k0 >> 4)) * kSlabUnits;
+          out[nc++] = f8seg ? TcChunk{a8, (uint32_t)kc, bytes | (src16 << 16), 2u}
+                            : TcChunk{a_off, (uint32_t)kc, bytes | (src16 << 16), 0u};
+        }
+        src16 += bytes >> 4;
+      }
+    }
+  }
+  out[nc - 1].w |= 1u;
+  return nc;
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -450,6 +498,15 @@ constexpr bool kTcProfile = false;
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
+#ifndef KS1
+#define KS1 kStash
+#endif
+#ifndef KS2
+#define KS2 kStash
+#endif
+#ifndef KS3
+#define KS3 kStash
+#endif
 template <bool kBwd, bool kStash, bool kX3, bool kF8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcParams p) {
@@ -527,36 +584,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   }
   if (threadIdx.x >= 256 && threadIdx.x < 256 + prog.n_steps) {
     const int si = threadIdx.x - 256;
-    const TcStep& st = prog.s[si];
-    uint32_t seen = 0, src16 = 0;
-    int nc = 0;
-    for (int sg = 0; sg < st.n_seg; ++sg) {
-      const int lo = st.seg_lo[sg];
-      for (int k0 = 0; k0 < st.seg_k[sg]; k0 += st.chunk_k) {
-        const int kc = min(st.chunk_k, st.seg_k[sg] - k0);
-        const int col = st.seg_col0[sg] + k0;
-        uint32_t need = 0;
-        for (int cc = col; cc < col + kc; cc += 64) need |= col_barriers<kX3>(cc);
-        need &= (uint32_t)st.fresh_mask & ~seen;
-        seen |= need;
-        const uint32_t a_off = (uint32_t)(col >> 3) * ((kTileM * 16u) >> 4), bytes = (uint32_t)((st.N >> 1) * kc * 2);
-        const bool f8seg = kF8 && st.seg_f8[sg] != 0;
-        const uint32_t dual = (lo && st.use_lo && !f8seg) ? ((uint32_t)(lo >> 3) * ((kTileM * 16u) >> 4)) << 8 : 0u;
-        s_chunks[si * kTcMaxChunks + nc++] = make_uint4(a_off, (uint32_t)kc | (need << 16), bytes | (src16 << 16), dual);
-        src16 += bytes >> 4;
-        if (lo) {              // the image holds W_lo right after W_hi whether or not this program uses it
-          if (st.use_lo) {
-            // fp8 remainder chunk (w bit 1): x = the e4m3 copy of these columns in the lo region (16 columns per unit)
-            const uint32_t a8 = ((uint32_t)((st.seg_col0[sg] + lo) >> 3) + (uint32_t)(k0 >> 4)) * ((kTileM * 16u) >> 4);
-            s_chunks[si * kTcMaxChunks + nc++] = f8seg ? make_uint4(a8, (uint32_t)kc, bytes | (src16 << 16), 2u)
-                                                       : make_uint4(a_off, (uint32_t)kc, bytes | (src16 << 16), 0u);
-          }
-          src16 += bytes >> 4;
-        }
-      }
-    }
-    s_chunks[si * kTcMaxChunks + nc - 1].w |= 1u;
-    s_nchunks[si] = nc;
+    s_nchunks[si] = tc_chunk_records(prog, si, reinterpret_cast<TcChunk*>(s_chunks + si * kTcMaxChunks));
   }
   if (!kBwd) {
     const float* dw = reinterpret_cast<const float*>(p.wpack + p.dot_off);
@@ -613,20 +641,6 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===================== peer CTA: relay lane =====================
-    if (lane == 0 && rank == 1) {
-      int stage = 0, phase = 0;
-      for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
-        for (int si = 0; si < prog.n_steps; ++si) {
-          const int nc = s_nchunks[si];
-          for (int c = 0; c < nc; ++c) {
-            mbar_wait(&full[stage], phase);           // my half of the chunk is in my shared memory
-            mbar_arrive_remote(&full[stage], 0);      // second arrival on the leader's "slot full" barrier
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
     // ===================== leader CTA: MMA issuer =====================
     // The WHOLE warp runs this loop (waits, chunk-table reads, descriptor arithmetic) in uniform control flow and only the
     // tcgen05 instructions themselves are issued by lane 0: the compiler then keeps the descriptor words in uniform
@@ -666,12 +680,13 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               grp_par ^= (1u << g);
             }
           }
-          const uint4* ckp = s_chunks + si * kTcMaxChunks;
-          uint4 ck = *ckp;
-          ck.x = __shfl_sync(0xffffffffu, ck.x, 0); ck.y = __shfl_sync(0xffffffffu, ck.y, 0); ck.w = __shfl_sync(0xffffffffu, ck.w, 0);
+          // chunk records come from the parameter constant bank with a warp-uniform index (TcParams::ctab): no
+          // shared-memory read, no shuffle, and everything derived from them stays in uniform registers
+          int cidx = si * kTcMaxChunks;
+          int ci = 0;                              // chunk number inside the step (profile builds: per-chunk stamps)
+          TcChunk ck = p.ctab[cidx];
           for (;;) {
-            uint4 nxt = ckp[1];                            // next chunk's facts arrive while this chunk's MMAs issue
-            nxt.x = __shfl_sync(0xffffffffu, nxt.x, 0); nxt.y = __shfl_sync(0xffffffffu, nxt.y, 0); nxt.w = __shfl_sync(0xffffffffu, nxt.w, 0);
+            const TcChunk nxt = p.ctab[cidx + 1];          // next chunk's facts arrive while this chunk's MMAs issue
             // the A columns of this chunk must have been (re)written: wait for their readiness barrier(s) (at most two)
             uint32_t need = (ck.y >> 16) & fresh;
             // tcgen05.fence::after_thread_sync orders this thread's MMAs after what OTHER threads did to the activation tile
@@ -690,8 +705,10 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               }
             }
             TCK(t_grp);
+            if (tl && si == 2 && ci < 10) p.dbg_buf[168 + 4 * ci + 0] = clock64();
             mbar_wait_u32(full_u32 + 8u * stage, phase);   // both halves of the weight chunk have landed
             TCK(t_full);
+            if (tl && si == 2 && ci < 10) p.dbg_buf[168 + 4 * ci + 1] = clock64();
             if (synced) tc_fence_after_sync();
             const uint32_t a_lo = a_lo0 + ck.x;
             const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kStageBytes >> 4);
@@ -702,7 +719,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               // fp8 remainder chunk: K = 32 per instruction, two 16-column units of A and of B each.  First half of the
               // slot: e4m3(W) against the e5m2 remainders; second half: e4m3(2^12 W_lo) against the e5m2 copies,
               // which sit 16 slabs after the remainders
-              const uint32_t b2 = b_lo + (((uint32_t)(st.N >> 1) * (uint32_t)kc) >> 4);
+              const uint32_t b2 = b_lo + ((b_kstep * (uint32_t)kc) >> 5);   // (N / 2) * kc bytes, from the register b_kstep lives in
               const uint32_t a2 = a_lo + 16u * ((kTileM * 16u) >> 4);
               uint32_t j = 0;
               if (kc == 64) {
@@ -766,9 +783,11 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               umma2_commit_u32_w(empty_u32 + 8u * stage);    // ring slot (in both CTAs) reusable once these MMAs have read it
             }
             accumulate = 1;
+            if (tl && si == 2 && ci < 10) { p.dbg_buf[168 + 4 * ci + 2] = clock64(); p.dbg_buf[168 + 4 * ci + 3] = ck.w; }
+            if (kTcProfile) ++ci;
             if (++stage == kStages) { stage = 0; phase ^= 1; }
             if (ck.w & 1u) break;
-            ck = nxt; ++ckp;
+            ck = nxt; ++cidx;
           }
           {
             umma2_commit_u32_w(smem_u32(&acc_full[gstep & 1]));      // accumulators complete -> epilogue warps of both CTAs
@@ -785,9 +804,41 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       TCK(t_issue);
       if (prof) { p.dbg_buf[0] = t_grp; p.dbg_buf[1] = t_full; p.dbg_buf[2] = t_issue; }
     }
+    // ===================== peer CTA: relay lane =====================
+    else if (kStash && lane == 0) {   // (inference variants: the relay runs in warp 14, see there)
+      int stage = 0, phase = 0;
+      for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
+        for (int si = 0; si < prog.n_steps; ++si) {
+          const int nc = s_nchunks[si];
+          for (int c = 0; c < nc; ++c) {
+            mbar_wait(&full[stage], phase);           // my half of the chunk is in my shared memory
+            mbar_arrive_remote(&full[stage], 0);      // second arrival on the leader's "slot full" barrier
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
   } else if (warp == 14) {
     // ===================== activation-stash store lane (training forward) =====================
-    if constexpr (kStash) {
+    if constexpr (!kStash) {
+      // inference variants: this warp has no stash to store, so its lane 0 is the peer CTA's relay lane.  (Side effect
+      // worth knowing: with this branch empty, ptxas stops treating the issuer warp's loop as converged and wraps every
+      // tcgen05.mma in ELECT + R2UR.BROADCAST again.)
+      if (lane == 0 && rank == 1) {
+      int stage = 0, phase = 0;
+      for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
+        for (int si = 0; si < prog.n_steps; ++si) {
+          const int nc = s_nchunks[si];
+          for (int c = 0; c < nc; ++c) {
+            mbar_wait(&full[stage], phase);           // my half of the chunk is in my shared memory
+            mbar_arrive_remote(&full[stage], 0);      // second arrival on the leader's "slot full" barrier
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+          }
+    }
+    if constexpr (KS1) {
       if (lane == 0) {
         uint32_t su = 0;
         for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
@@ -893,7 +944,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         const long long tile = tile_of(pair);
         const long long pi = tile * kTileM + row;
         const bool valid = pi < p.n_points;
-        const bool st_on = kStash && tile < num_tiles;
+        const bool st_on = KS2 && tile < num_tiles;
         float pt[3], emb[48];
         load_point(p, pi, valid, pt);
 #pragma unroll
@@ -954,7 +1005,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         const long long tile = tile_of(pair);
         const long long pi = tile * kTileM + row;
         const bool valid = pi < p.n_points;
-        const bool st_on = kStash && tile < num_tiles;
+        const bool st_on = KS2 && tile < num_tiles;
         float pt[3], a[40], d[3] = {0.f, 0.f, 0.f};
         load_point(p, pi, valid, pt);
 #pragma unroll
@@ -1034,7 +1085,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             // reader (the colour net's first layer of the previous tile) completed long ago
             const float a[8] = {nv[0], nv[1], nv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
             store_slab_f(s_act, L::aux / 8, rowd, a);
-            if (kStash && tile < num_tiles)
+            if (KS2 && tile < num_tiles)
               *stash_unit(p, p.sinfo.idx_aux, tile, 0, rowd) = make_uint4(pack_bf16x2(nv[0], nv[1]), pack_bf16x2(nv[2], 0.f), 0u, 0u);
             fence_proxy_async_smem();
             arrive_pro(kBarAux);           // matched by the colour net's first step
@@ -1173,8 +1224,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const bool feat = st.epi == TC_EPI_FEAT;
           const bool to_act = !feat || render;
           const int stN = st.N;
-          const bool st_on = kStash && st.stash_out >= 0 && tile < num_tiles;
-          const bool st_tile = kStash && st.stash_out >= 0 && to_act;     // this step's output leaves through warp 14
+          const bool st_on = KS3 && st.stash_out >= 0 && tile < num_tiles;
+          const bool st_tile = KS3 && st.stash_out >= 0 && to_act;     // this step's output leaves through warp 14
           // the last step of a program has no consumer in the activation tile: its output is only stashed (training)
           // and/or reduced to a 3-wide output by the prologue warps (TcStep::dot), and it must not arrive on the
           // column-group barriers (every arrival set is matched by exactly one wait of the MMA issuer)
@@ -1659,6 +1710,8 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
            : mode == TC_MODE_BWD ? plan.bwd : mode == TC_MODE_VF_BWD ? plan.bwd_vf : plan.v_only;
   p.wpack = is_bwd ? plan.wpack_bwd : plan.wpack;
   p.dot_off = plan.dot_off;
+  VFN_REQUIRE(p.prog.n_steps <= kTcTableSteps, "tc_forward: program of %d steps exceeds the chunk table", p.prog.n_steps);
+  for (int si = 0; si < p.prog.n_steps; ++si) tc_chunk_records(p.prog, si, p.ctab + si * kTcMaxChunks);
   if (stashing || is_bwd) {
     VFN_REQUIRE(plan.stash_buf, "tc_forward: this mode needs the training workspace (keep_for_backward)");
     p.stash = plan.stash_buf; p.sinfo = plan.stash;
@@ -1728,6 +1781,9 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
             tc, p.prog.n_steps, h[0] / tc, h[1] / tc, h[2] / tc, h[8] / tc, h[9] / tc, h[10] / tc, h[11] / tc, h[12] / tc,
             h[16] / tc, h[17] / tc, h[18] / tc, h[19] / tc, h[20] / tc);
     const long long base = h[64];
+    for (int ci = 0; ci < 10 && h[168 + 4 * ci]; ++ci)
+      fprintf(stderr, "[tc chunks] step 2 chunk %d (w=%lld): top->grp_done %6lld  full_done +%4lld  issued +%4lld\n", ci, h[168 + 4 * ci + 3],
+              h[168 + 4 * ci] - base, h[168 + 4 * ci + 1] - h[168 + 4 * ci], h[168 + 4 * ci + 2] - h[168 + 4 * ci + 1]);
 
 
     for (int si = 0; si < p.prog.n_steps && base; ++si) {
