@@ -390,14 +390,23 @@ def main():
             m.graph_replay = False
             return h2d, d2h
 
-        def time_e2e(m, ck, replay=False):
+        e2e_ms = {}
+
+        def time_e2e(m, ck, replay=False, key=None):
+            # one untimed image, then args.steps images timed ONE BY ONE (events + barrier + synchronize around each); the
+            # rate is taken from the median image and every per-image time is reported: this leg runs through the host
+            # (CPU generator, pinned staging, Python), where a single stall of the box -- seen once: one image at half
+            # rate between two normal runs -- would otherwise decide a figure measured on one image
             h2d, d2h = step_e2e(m, ck, replay)
-            ms2 = timed(lambda: step_e2e(m, ck, replay), 1)
-            return world * R / (ms2 * 1e-3), h2d, d2h
-        v_big, h2d, d2h = time_e2e(model, chunk)
-        v_1k, h2d_1k, d2h_1k = time_e2e(model, 1024, replay=True)
+            ms_all = sorted(timed(lambda: step_e2e(m, ck, replay), 1) for _ in range(max(1, args.steps)))
+            if key:
+                e2e_ms[key] = [round(x, 3) for x in ms_all]
+            return world * R / (ms_all[len(ms_all) // 2] * 1e-3), h2d, d2h
+        v_big, h2d, d2h = time_e2e(model, chunk, key="headline")
+        v_1k, h2d_1k, d2h_1k = time_e2e(model, 1024, replay=True, key="chunk_1024")
         e2e = {"value": v_big, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "chunk": chunk,
-               "precision": head,
+               "precision": head, "timing": "median of the per-image times listed in ms_per_image (one warm-up image first)",
+               "ms_per_image": e2e_ms,
                "value_chunk_1024": v_1k, "chunk_1024_over_headline": v_1k / v_big,
                "chunk_1024_note": "the reference's evaluation chunk size (evaluation/methods.py:516-530), each render() call a "
                                   "CUDA-graph replay (model.graph_replay); same H2D / draws / D2H per chunk"}
