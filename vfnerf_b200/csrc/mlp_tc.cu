@@ -722,7 +722,9 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               const uint32_t b2 = b_lo + ((b_kstep * (uint32_t)kc) >> 5);   // (N / 2) * kc bytes, from the register b_kstep lives in
               const uint32_t a2 = a_lo + 16u * ((kTileM * 16u) >> 4);
               uint32_t j = 0;
-              if (kc == 64) {
+              if (kTcProfile && (kdbg & 32)) {
+                // experiment: 8-bit MMAs not issued at all (garbage results): what a step costs without their tensor time
+              } else if (kc == 64) {
                 umma2_f8_split_w(acc, a_lo, desc_hi, b_lo, desc_hi, idesc8a, 1u);
                 umma2_f8_split_w(acc, a_lo + a_kstep, desc_hi, b_lo + b_kstep, desc_hi, idesc8a, 1u);
                 umma2_f8_split_w(acc, a2, desc_hi, b2, desc_hi, idesc8b, 1u);
@@ -734,6 +736,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               for (int kk = 0; kk < kc; kk += 32, ++j)
                 umma2_f8_split_w(acc, a2 + j * a_kstep, desc_hi, b2 + j * b_kstep, desc_hi, idesc8b, 1u);
               }
+              if (tl && si == 2 && ci < 10) p.dbg_buf[168 + 4 * ci + 3] = clock64();
               umma2_commit_u32_w(empty_u32 + 8u * stage);
             } else if constexpr (kX3) {
               // 16 KiB ring slots: at most 64 K columns per chunk.  A split-precision "hi" chunk multiplies W_hi with
@@ -764,6 +767,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                   }
                 }
               }
+              if (tl && si == 2 && ci < 10) p.dbg_buf[168 + 4 * ci + 3] = clock64();
               umma2_commit_u32_w(empty_u32 + 8u * stage);
             } else {
               if (kc == 128) {
@@ -780,10 +784,11 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                   ac = 1u; al += a_kstep; bl += b_kstep;
                 }
               }
+              if (tl && si == 2 && ci < 10) p.dbg_buf[168 + 4 * ci + 3] = clock64();
               umma2_commit_u32_w(empty_u32 + 8u * stage);    // ring slot (in both CTAs) reusable once these MMAs have read it
             }
             accumulate = 1;
-            if (tl && si == 2 && ci < 10) { p.dbg_buf[168 + 4 * ci + 2] = clock64(); p.dbg_buf[168 + 4 * ci + 3] = ck.w; }
+            if (tl && si == 2 && ci < 10) p.dbg_buf[168 + 4 * ci + 2] = clock64();
             if (kTcProfile) ++ci;
             if (++stage == kStages) { stage = 0; phase ^= 1; }
             if (ck.w & 1u) break;
@@ -1782,8 +1787,9 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
             h[16] / tc, h[17] / tc, h[18] / tc, h[19] / tc, h[20] / tc);
     const long long base = h[64];
     for (int ci = 0; ci < 10 && h[168 + 4 * ci]; ++ci)
-      fprintf(stderr, "[tc chunks] step 2 chunk %d (w=%lld): top->grp_done %6lld  full_done +%4lld  issued +%4lld\n", ci, h[168 + 4 * ci + 3],
-              h[168 + 4 * ci] - base, h[168 + 4 * ci + 1] - h[168 + 4 * ci], h[168 + 4 * ci + 2] - h[168 + 4 * ci + 1]);
+      fprintf(stderr, "[tc chunks] step 2 chunk %d: top->grp_done %6lld  full_done +%4lld  mmas issued +%4lld  commit +%4lld\n", ci,
+              h[168 + 4 * ci] - base, h[168 + 4 * ci + 1] - h[168 + 4 * ci], h[168 + 4 * ci + 3] - h[168 + 4 * ci + 1],
+              h[168 + 4 * ci + 2] - h[168 + 4 * ci + 3]);
 
 
     for (int si = 0; si < p.prog.n_steps && base; ++si) {

@@ -27,7 +27,7 @@ def c_is_nerf(config) -> bool:
 class VectorFieldNerf:
     def __init__(self, config, precision: str = "fp32") -> None:
         """:param config: a VFNerfConfig (ours or the reference's own dataclass; only attributes are read).
-        :param precision: "fp32" | "bf16" | "bf16x3" -- arithmetic of the two MLPs (include/vfnerf_b200.h)."""
+        :param precision: "fp32" | "bf16" | "bf16x3" | "fp16f8" -- arithmetic of the two MLPs (include/vfnerf_b200.h)."""
         self.config = config
         rs = config.ray_sampler_config
         self.vector_field_network = VectorFieldNetwork(config.vf_net_config)
