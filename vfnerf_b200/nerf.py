@@ -410,9 +410,16 @@ class _RenderGraph:
 
     def replay(self, pose, pixels, intrinsics, draws) -> NerfOutput:
         m = self.model
-        self.pose.copy_(pose, non_blocking=True)
-        self.pixels.copy_(pixels, non_blocking=True)
-        self.intrinsics.copy_(intrinsics, non_blocking=True)
+        srcs = [pose, pixels, intrinsics]
+        if all(t.is_cuda and t.dtype == torch.float32 and t.device == self.dev for t in srcs):
+            # one fused launch for the three input copies (a replayed 1024-ray call is a handful of launches in total)
+            torch._foreach_copy_([self.pose, self.pixels, self.intrinsics],
+                                 [pose.reshape(self.pose.shape), pixels.reshape(self.pixels.shape),
+                                  intrinsics.reshape(self.intrinsics.shape)], non_blocking=True)
+        else:
+            self.pose.copy_(pose, non_blocking=True)
+            self.pixels.copy_(pixels, non_blocking=True)
+            self.intrinsics.copy_(intrinsics, non_blocking=True)
         if draws is not None:
             for dst, src in zip(self.U, draws):
                 if dst is not None:
