@@ -43,8 +43,8 @@ template <> struct Lay<true> {
   static constexpr int stage_bytes = 16384;
 };
 template <bool kX3> constexpr size_t tc_smem_bytes() {
-  return (size_t)Lay<kX3>::cols * kTileM * 2 + (size_t)kTcStages * Lay<kX3>::stage_bytes + 512 +
-         (size_t)kTcTableSteps * kTcMaxChunks * 16 + 128 + (size_t)2 * 3 * 256 * 4;
+  return (size_t)Lay<kX3>::cols * kTileM * 2 + (size_t)kTcStages * Lay<kX3>::stage_bytes + 512 + 128 +
+         (size_t)2 * 3 * 256 * 4;
 }
 static_assert(tc_smem_bytes<true>() <= 227 * 1024 && tc_smem_bytes<false>() <= 227 * 1024, "activation tile + ring exceed shared memory");
 constexpr int kTcThreads = 480;      // warp 0 producer, warp 1 MMA/relay, warps 2..9 epilogue, warps 10..13 prologue,
@@ -71,6 +71,7 @@ struct TcParams {
   // a tcgen05.mma costs it ~4 uniform-datapath instructions (from a shared-memory table + shuffles the compiler wrapped
   // every MMA in ELECT / 8 x R2UR.BROADCAST: profiles/r02_forward_kernel_experiments.md, section 4)
   TcChunk ctab[kTcTableSteps * kTcMaxChunks + 1];   // + 1: the issuer reads one record ahead
+  int cnum[kTcTableSteps];                          // chunks per step (relay lane)
   const uint8_t* wpack;
   const float* points;
   int use_grid;
@@ -528,6 +529,9 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   static_assert(kStages * kStageBytes == kTcStages * L::stage_bytes, "ring size is part of tc_smem_bytes");
   const int kdbg = kTcProfile ? p.dbg : 0;   // experiment switches (VFNERF_TC_DBG) exist in profile builds only
   extern __shared__ __align__(1024) uint8_t smem[];
+  // launch-phase stamps of CTA 0 (profile builds, VFNERF_TC_DBG=64): entry, set-up done, first MMA, last step committed, exit
+  const bool stamp = kTcProfile && p.dbg_buf && blockIdx.x == 0 && threadIdx.x == 32;
+  if (stamp) p.dbg_buf[240] = clock64();
   const TcProgram& prog = p.prog;
   uint8_t* s_act = smem;
   uint8_t* s_stage = smem + L::cols * (kTileM * 2);
@@ -552,17 +556,12 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   // that does not observe EVERY phase of an mbarrier cannot tell the phase it wants from an older one of equal parity.
   uint64_t* dot_full = st_done + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dot_full + 1);
-  // chunk table: the single-lane producer / MMA-issuer loops must not chase per-chunk facts through the kernel
-  // parameters (dependent constant loads cost them ~500 cycles per chunk): everything a chunk needs is one LDS.128.
-  //   x = A start-address increment (16-byte units), y = K columns | readiness-barrier mask << 16,
-  //   z = bytes of this CTA's half of the weight chunk | (its offset inside the step's half image / 16) << 16,
-  //   w = bit 0: last chunk of the step; bits 8..: split-precision "hi" chunk -- distance (16-byte units) from the hi
-  //       to the lo copy of the A columns: the chunk's MMAs are issued a second time on the lo copy
-  uint4* s_chunks = reinterpret_cast<uint4*>(bars + 64);
-  int* s_nchunks = reinterpret_cast<int*>(s_chunks + kTcTableSteps * kTcMaxChunks);
+  // (the per-chunk facts of every step -- TcChunk records -- live in the kernel parameters, TcParams::ctab: the producer,
+  //  the relay lane and the MMA issuer read them from the constant bank with a warp-uniform index; rounds 1 and 2 built a
+  //  shared-memory copy here, 11 k cycles of set-up per launch)
   // fp32 rows (and biases) of the two 3-wide output layers the epilogue warps evaluate on the CUDA cores (TcStep::dot)
-  float* s_dotb = reinterpret_cast<float*>(s_nchunks + kTcMaxSteps);          // [8]: vector bias 3, colour bias 3
-  float* s_dotw = reinterpret_cast<float*>(s_nchunks) + 32;                   // [2][3][256]
+  float* s_dotb = reinterpret_cast<float*>(bars + 64);                        // [8]: vector bias 3, colour bias 3
+  float* s_dotw = s_dotb + 32;                                                // [2][3][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -582,10 +581,6 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x >= 256 && threadIdx.x < 256 + prog.n_steps) {
-    const int si = threadIdx.x - 256;
-    s_nchunks[si] = tc_chunk_records(prog, si, reinterpret_cast<TcChunk*>(s_chunks + si * kTcMaxChunks));
-  }
   if (!kBwd) {
     const float* dw = reinterpret_cast<const float*>(p.wpack + p.dot_off);
     for (int i = threadIdx.x; i < 2 * 3 * 256; i += kTcThreads) s_dotw[i] = __ldg(dw + i);
@@ -601,6 +596,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   tc_fence_before_sync();
   cluster_sync_all();                       // barriers of BOTH CTAs are initialised before any remote arrive / multicast
   tc_fence_after_sync();
+  if (stamp) p.dbg_buf[241] = clock64();
   const uint32_t tmem = *tmem_slot;
   const long long num_tiles = (p.n_points + kTileM - 1) / kTileM;
   // tiles are handed out in pairs: cluster c processes tile pairs c, c + n_clusters, ...; CTA `rank` takes tile 2*pair + rank
@@ -622,9 +618,11 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         for (int si = 0; si < prog.n_steps; ++si) {
           const TcStep& st = prog.s[si];
           const uint8_t* src = p.wpack + st.w_off + (int64_t)rank * (st.N >> 1) * st.K * 2;
-          const uint4* ck = s_chunks + si * kTcMaxChunks;
-          for (;; ++ck) {
-            const uint4 c = *ck;
+          // records from the parameter constant bank (host-built, TcParams::ctab), the next one fetched before the wait
+          int cidx = si * kTcMaxChunks;
+          TcChunk c = p.ctab[cidx];
+          for (;;) {
+            const TcChunk c_next = p.ctab[cidx + 1];
             const uint32_t bytes = c.z & 0xFFFFu;
             mbar_wait(&empty[stage], phase ^ 1);
             if (kdbg & 4) {
@@ -636,6 +634,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
             if (c.w & 1u) break;
+            c = c_next; ++cidx;
           }
         }
       }
@@ -715,6 +714,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             constexpr uint32_t a_kstep = 2u * ((kTileM * 16u) >> 4);
             const int kc = (int)(ck.y & 0xFFFFu);
             if (tl && first_mma) { p.dbg_buf[64 + si * 8 + 0] = clock64(); first_mma = false; }
+            if (prof && lane == 0 && gstep == 0 && ci == 0) p.dbg_buf[242] = clock64();
             if (kF8 && (ck.w & 2u)) {
               // fp8 remainder chunk: K = 32 per instruction, two 16-column units of A and of B each.  First half of the
               // slot: e4m3(W) against the e5m2 remainders; second half: e4m3(2^12 W_lo) against the e5m2 copies,
@@ -807,6 +807,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         }
       }
       TCK(t_issue);
+      if (prof && lane == 0) p.dbg_buf[243] = clock64();
       if (prof) { p.dbg_buf[0] = t_grp; p.dbg_buf[1] = t_full; p.dbg_buf[2] = t_issue; }
     }
     // ===================== peer CTA: relay lane =====================
@@ -814,7 +815,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       int stage = 0, phase = 0;
       for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
         for (int si = 0; si < prog.n_steps; ++si) {
-          const int nc = s_nchunks[si];
+          const int nc = p.cnum[si];
           for (int c = 0; c < nc; ++c) {
             mbar_wait(&full[stage], phase);           // my half of the chunk is in my shared memory
             mbar_arrive_remote(&full[stage], 0);      // second arrival on the leader's "slot full" barrier
@@ -833,7 +834,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       int stage = 0, phase = 0;
       for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
         for (int si = 0; si < prog.n_steps; ++si) {
-          const int nc = s_nchunks[si];
+          const int nc = p.cnum[si];
           for (int c = 0; c < nc; ++c) {
             mbar_wait(&full[stage], phase);           // my half of the chunk is in my shared memory
             mbar_arrive_remote(&full[stage], 0);      // second arrival on the leader's "slot full" barrier
@@ -1414,6 +1415,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   }
   tc_fence_before_sync();
   cluster_sync_all();                       // neither CTA may exit (or free TMEM) while its peer can still touch it
+  if (stamp) p.dbg_buf[244] = clock64();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
@@ -1716,7 +1718,7 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
   p.wpack = is_bwd ? plan.wpack_bwd : plan.wpack;
   p.dot_off = plan.dot_off;
   VFN_REQUIRE(p.prog.n_steps <= kTcTableSteps, "tc_forward: program of %d steps exceeds the chunk table", p.prog.n_steps);
-  for (int si = 0; si < p.prog.n_steps; ++si) tc_chunk_records(p.prog, si, p.ctab + si * kTcMaxChunks);
+  for (int si = 0; si < p.prog.n_steps; ++si) p.cnum[si] = tc_chunk_records(p.prog, si, p.ctab + si * kTcMaxChunks);
   if (stashing || is_bwd) {
     VFN_REQUIRE(plan.stash_buf, "tc_forward: this mode needs the training workspace (keep_for_backward)");
     p.stash = plan.stash_buf; p.sinfo = plan.stash;
@@ -1786,6 +1788,8 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
             tc, p.prog.n_steps, h[0] / tc, h[1] / tc, h[2] / tc, h[8] / tc, h[9] / tc, h[10] / tc, h[11] / tc, h[12] / tc,
             h[16] / tc, h[17] / tc, h[18] / tc, h[19] / tc, h[20] / tc);
     const long long base = h[64];
+    fprintf(stderr, "[tc launch] CTA 0 cycles from entry: set-up done %lld, first MMA %lld, last step issued %lld, exit %lld\n",
+            h[241] - h[240], h[242] - h[240], h[243] - h[240], h[244] - h[240]);
     for (int ci = 0; ci < 10 && h[168 + 4 * ci]; ++ci)
       fprintf(stderr, "[tc chunks] step 2 chunk %d: top->grp_done %6lld  full_done +%4lld  mmas issued +%4lld  commit +%4lld\n", ci,
               h[168 + 4 * ci] - base, h[168 + 4 * ci + 1] - h[168 + 4 * ci], h[168 + 4 * ci + 3] - h[168 + 4 * ci + 1],
