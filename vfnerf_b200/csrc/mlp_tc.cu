@@ -31,19 +31,20 @@ namespace vfn {
 using namespace tc;
 
 constexpr int kTileM = 128;
-constexpr int kTcStages = 3;
+// weight-ring depth: the split-precision tile's 16 KiB slots are refilled in ~1.1 k cycles (MMA completion -> `empty` -> bulk
+// copy from L2 -> relay) while a slot's four MMAs take 512: three slots bound the chunk rate at ~540 cycles, four do not
 // activation-tile layout and ring-slot size of the two tile formats (mlp_tc.cuh)
 template <bool kX3> struct Lay;
 template <> struct Lay<false> {
   static constexpr int aux = kColAux, skip = kColSkip, ones = kColOnes, emb0 = kColEmb0, lo = 0, cols = kActCols;
-  static constexpr int stage_bytes = 32768;
+  static constexpr int stage_bytes = 32768, stages = 3;
 };
 template <> struct Lay<true> {
   static constexpr int aux = kX3ColAux, skip = -1, ones = kX3ColOnes, emb0 = kX3ColEmb0, lo = kX3ColLo, cols = kX3ActCols;
-  static constexpr int stage_bytes = 16384;
+  static constexpr int stage_bytes = 16384, stages = 4;
 };
 template <bool kX3> constexpr size_t tc_smem_bytes() {
-  return (size_t)Lay<kX3>::cols * kTileM * 2 + (size_t)kTcStages * Lay<kX3>::stage_bytes + 512 + 128 +
+  return (size_t)Lay<kX3>::cols * kTileM * 2 + (size_t)Lay<kX3>::stages * Lay<kX3>::stage_bytes + 512 + 128 +
          (size_t)2 * 3 * 256 * 4;
 }
 static_assert(tc_smem_bytes<true>() <= 227 * 1024 && tc_smem_bytes<false>() <= 227 * 1024, "activation tile + ring exceed shared memory");
@@ -338,8 +339,7 @@ __device__ __forceinline__ uint2* gate_unit(const TcParams& p, int t, long long 
 __host__ __device__ inline uint32_t col_barriers(bool x3, int col) {
   if (col < kColAux) return 1u << (col >> 6);
   if (x3) {
-    if (col < kX3ColOnes) return (1u << kBarAux) | (1u << kBarAuxStatic);
-    if (col < kX3ColEmb0) return 0u;
+    if (col < kX3ColEmb0) return 0u;              // ones (the aux columns alias lo columns: TcStep::seg_bar names their barriers)
     if (col < kX3ColLo) return 1u << kBarEmb0;
     return 1u << ((col - kX3ColLo) >> 6);     // the lo copy of a group is published by the same arrival as its hi copy
   }
@@ -363,7 +363,9 @@ __host__ __device__ inline int tc_chunk_records(const TcProgram& prog, int si, T
       const int kc = (st.chunk_k < st.seg_k[sg] - k0) ? st.chunk_k : st.seg_k[sg] - k0;
       const int col = st.seg_col0[sg] + k0;
       uint32_t need = 0;
-      for (int cc = col; cc < col + kc; cc += 64) need |= col_barriers(x3, cc);
+      if (st.seg_bar[sg]) need = (uint32_t)st.seg_bar[sg];
+      else
+        for (int cc = col; cc < col + kc; cc += 64) need |= col_barriers(x3, cc);
       need &= (uint32_t)st.fresh_mask & ~seen;
       seen |= need;
       const uint32_t a_off = (uint32_t)(col >> 3) * kSlabUnits, bytes = (uint32_t)((st.N >> 1) * kc * 2);
@@ -525,8 +527,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
   // its size; profiles/r02_forward_kernel_experiments.md), so the fp16 + fp8 chain, whose MMAs are short, runs the same 48 KiB
   // as six 8 KiB slots (32 K columns per chunk) instead of three 16 KiB ones
   constexpr int kStageBytes = L::stage_bytes;
-  constexpr int kStages = kTcStages;
-  static_assert(kStages * kStageBytes == kTcStages * L::stage_bytes, "ring size is part of tc_smem_bytes");
+  constexpr int kStages = L::stages;
   const int kdbg = kTcProfile ? p.dbg : 0;   // experiment switches (VFNERF_TC_DBG) exist in profile builds only
   extern __shared__ __align__(1024) uint8_t smem[];
   // launch-phase stamps of CTA 0 (profile builds, VFNERF_TC_DBG=64): entry, set-up done, first MMA, last step committed, exit
@@ -1105,13 +1106,17 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       // per tile: [inputs A of the NEXT tile] -> vector dot -> [inputs B of the next tile] -> colour dot, so the next
       // tile's operands are in place long before its first MMA and no region is rewritten while it is still being read
       const int d_first = prog.dot_step[0], d_second = prog.dot_step[1];
-      if (pair0 < num_pairs) { prep_a(pair0, 0); if (prog.aux_step >= 0) prep_b(pair0, 0); }
+      // split-precision tile: the aux columns alias lo columns that are live until the last hidden VF layer's MMAs have
+      // completed, so part B is written for the CURRENT tile right after the vector dot step (which waits for exactly that)
+      constexpr bool kAuxLate = kX3;
+      if (pair0 < num_pairs) { prep_a(pair0, 0); if (!kAuxLate && prog.aux_step >= 0) prep_b(pair0, 0); }
       for (long long pair = pair0; pair < num_pairs; pair += pair_step, ++n) {
         const long long next = pair + pair_step;
         const uint32_t g0 = (uint32_t)n * (uint32_t)prog.n_steps;
         if (next < num_pairs) prep_a(next, n + 1);
         if (d_first >= 0) dot_step(d_first, g0 + d_first, pair);
-        if (next < num_pairs && prog.aux_step >= 0) prep_b(next, n + 1);
+        if (kAuxLate) { if (prog.aux_step >= 0) prep_b(pair, n); }
+        else if (next < num_pairs && prog.aux_step >= 0) prep_b(next, n + 1);
         if (d_second >= 0) dot_step(d_second, g0 + d_second, pair);
       }
     }
@@ -1289,11 +1294,13 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                   }
                   store_slab_u(s_act, (c0 >> 3) + sl, row, hi[0], hi[1], hi[2], hi[3]);
                 }
-                const int u8 = L::lo / 8 + (c0 >> 4);
-                store_slab_u(s_act, u8, row, r8[0], r8[1], r8[2], r8[3]);
-                store_slab_u(s_act, u8 + 1, row, r8[4], r8[5], r8[6], r8[7]);
-                store_slab_u(s_act, u8 + 16, row, h8[0], h8[1], h8[2], h8[3]);
-                store_slab_u(s_act, u8 + 17, row, h8[4], h8[5], h8[6], h8[7]);
+                if (st.out_lo) {       // (not for the last hidden layer inside render(): its lo columns hold the aux inputs)
+                  const int u8 = L::lo / 8 + (c0 >> 4);
+                  store_slab_u(s_act, u8, row, r8[0], r8[1], r8[2], r8[3]);
+                  store_slab_u(s_act, u8 + 1, row, r8[4], r8[5], r8[6], r8[7]);
+                  store_slab_u(s_act, u8 + 16, row, h8[0], h8[1], h8[2], h8[3]);
+                  store_slab_u(s_act, u8 + 17, row, h8[4], h8[5], h8[6], h8[7]);
+                }
               } else if constexpr (kX3) {
                 // split-precision hand-off: y = relu(acc) leaves as hi = bf16(y) in the main columns and, for the VF
                 // layers, lo = bf16(y - hi) in the lo columns (same slab, kX3ColLo further on)
@@ -1463,7 +1470,7 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
     TcStep& s = pr.s[ns];
     s = TcStep{};
     s.N = N; s.n_valid = n_valid; s.n_seg = nseg + (no_bias ? 0 : 1); s.K = 0;
-    for (int i = 0; i < kTcMaxSegs; ++i) { s.seg_lo[i] = 0; s.seg_wscale[i] = 1.f; s.seg_f8[i] = 0; }
+    for (int i = 0; i < kTcMaxSegs; ++i) { s.seg_lo[i] = 0; s.seg_wscale[i] = 1.f; s.seg_f8[i] = 0; s.seg_bar[i] = 0; }
     for (int i = 0; i < nseg; ++i) {
       s.seg_col0[i] = col0[i]; s.seg_k[i] = segk[i];
       s.seg_lo[i] = seglo ? seglo[i] : 0; s.seg_wscale[i] = segw ? segw[i] : 1.f;
@@ -1538,6 +1545,7 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
     const int c[2] = {0, pr.col_aux}, k[2] = {256, 48};
     pr.aux_step = ns;
     add(256, 256, 2, c, k, CK, TC_EPI_RELU, 0xF | (1 << kBarAux) | (1 << kBarAuxStatic), 1, 0, 0, 2, pr.small_w, 1.f);
+    if (x3) pr.s[ns - 1].seg_bar[1] = (1 << kBarAux) | (1 << kBarAuxStatic);   // aux columns alias lo columns (mlp_tc.cuh)
     for (int l = 1; l < Lr - 1; ++l) add(256, 256, 1, main0, k256, CK, TC_EPI_RELU, 0xF, 1, l, 0, 0, 0, 1.f);
     VFN_REQUIRE(Lr >= 2, "tensor-core path: the colour net needs a hidden layer");
     pr.s[ns - 1].dot = 2;         // the 3 colour rows: epilogue of the last hidden colour layer
@@ -1570,7 +1578,11 @@ static int build_programs(int multires, int multires_view, int skip_layer, const
     VFN_REQUIRE(nc <= kTcMaxChunks, "tensor-core path: step %d needs %d pipeline chunks (max %d)", i, nc, kTcMaxChunks);
   }
   plan.render = pr;
-  if (x3 && rn) plan.render.s[n_v].use_lo = 0;
+  if (x3 && rn) {
+    plan.render.s[n_v].use_lo = 0;
+    // ... so the last hidden layer writes no lo copy inside render(): its lo columns are the colour net's aux columns
+    plan.render.s[n_v - 1].out_lo = 0;
+  }
   plan.vf_full = pr; plan.vf_full.n_steps = n_full; plan.vf_full.render = 0; plan.vf_full.aux_step = -1;
   plan.v_only = pr; plan.v_only.n_steps = n_v; plan.v_only.render = 0; plan.v_only.aux_step = -1;
   set_guards(plan.render); set_guards(plan.vf_full); set_guards(plan.v_only);

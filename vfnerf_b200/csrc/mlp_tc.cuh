@@ -8,7 +8,7 @@ constexpr int kTcMaxSteps = 16;
 constexpr int kTcMaxSegs = 3;
 constexpr int kTcMaxChunks = 20;   // pipeline chunks per step (split-precision steps: hi + lo chunk per K range + bias)
 constexpr int kTcTableSteps = 13;  // steps of the longest program (render(): 8 + 1 + 4; its dgrad chain: 5 + 8) -- rows of the
-                                   // shared-memory chunk table
+                                   // chunk table in the kernel parameters (TcParams::ctab)
 
 // Activation-tile column map (bf16 columns of the 128-row A operand, K-slab layout, tc_common.cuh):
 //   [0,256)    main: current layer input / output (step 0 reads the hi/lo embedding from [0, 2*emb_pad))
@@ -25,8 +25,12 @@ constexpr int kColAux = 256, kColSkip = 304, kColOnes = 352, kColEmb0 = 368, kAc
 //   acc += A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T          (the A_lo W_lo term is below fp32 accumulation noise)
 // so the chain carries ~16 significant bits instead of 8.  No skip region: the skip layer reads the (hi | lo) layer-0
 // embedding with its weights scaled by 1/sqrt(2).  The colour net stays plain bf16 (its error is 2e-4).
-//   [0,256) main hi | [256,304) aux | [304,320) ones | [320,416) emb0 hi|lo | [416,672) main lo
-constexpr int kX3ColAux = 256, kX3ColOnes = 304, kX3ColEmb0 = 320, kX3ColLo = 416, kX3ActCols = 672;
+//   [0,256) main hi | [256,272) ones | [272,368) emb0 hi|lo | [368,624) main lo;  aux = [368,416), ALIASING the first 48 lo
+//   columns: the lo copies are dead once the last hidden VF layer's MMAs have completed (inside render() the feature step
+//   reads only the hi copy, and that layer's epilogue writes no lo copy), which is exactly when the prologue warps write the
+//   colour net's small inputs (normal, point, view embedding); the next tile's first epilogue rewrites the lo columns long
+//   after the colour net's first layer has read them.  The 12 KiB this saves are the fourth slot of the weight ring.
+constexpr int kX3ColOnes = 256, kX3ColEmb0 = 272, kX3ColLo = 368, kX3ColAux = kX3ColLo, kX3ActCols = 624;
 // fp16 + fp8 remainders (VFNERF_PREC_FP16F8): the same tile, but a VF product is
 //   acc += A16 W16^T  +  e5m2(A - A16) e4m3(W)^T  +  e5m2(2^-12 A) e4m3(2^12 (W - W16))^T
 // with A16 / W16 the fp16 roundings: one 16-bit MMA (K = 16) plus two 8-bit MMAs (kind::f8f6f4, K = 32 at the same issue
@@ -34,7 +38,7 @@ constexpr int kX3ColAux = 256, kX3ColOnes = 304, kX3ColEmb0 = 320, kX3ColLo = 41
 // The remainders are 2^-12 of the product, so the 3-4 mantissa bits of the 8-bit formats leave ~2^-15 (measured against
 // the reference goldens: normals 8e-4 vs 2.7e-4 for bf16x3 and 1.4e-1 for bf16).  The activation remainders (2^-12 of
 // O(1) activations) fit e5m2's range unscaled and the folded weights (O(0.1)) e4m3's; the weight remainders (2^-12 of the
-// weights) need the power-of-two scale, undone on the activation copy.  The lo columns [416,672) hold the two 8-bit copies
+// weights) need the power-of-two scale, undone on the activation copy.  The lo columns [368,624) hold the two 8-bit copies
 // of the main columns: e5m2 remainders in slabs 0..15 (16 columns per 16-byte unit), e5m2 scaled values in 16..31.
 // The ones-columns hold 2.0 -- the same bit pattern in bf16 and fp16 -- and the packed bias rows are halved.
 constexpr float kF8ScaleHi = 4096.f;
@@ -50,6 +54,8 @@ struct TcStep {
                               // this segment's A operand (0: plain segment).  The weight image then holds, per K chunk,
                               // the bf16 weights W_hi followed by the remainders W_lo
   float seg_wscale[kTcMaxSegs];   // extra factor on this segment's weights (skip-layer embedding columns: 1/sqrt(2))
+  int seg_bar[kTcMaxSegs];    // readiness barriers of this segment's columns given explicitly (0: derived from the columns) --
+                              // the split-precision tile's aux columns alias lo columns
   int seg_f8[kTcMaxSegs];     // fp16 + fp8-remainder segment (VFNERF_PREC_FP16F8, below): the "lo" half of every chunk of the
                               // weight image holds two 8-bit images instead of one 16-bit image
   int a_f16;      // this step's 16-bit operands (activations, weights, bias pair) are fp16, not bf16
