@@ -510,6 +510,9 @@ constexpr bool kTcProfile = false;
 #ifndef KS3
 #define KS3 kStash
 #endif
+// activation-tile stores of the split-precision epilogue (profile builds: VFNERF_TC_DBG bit 1 drops them -- garbage results --
+// to see what the epilogue's shared-memory writes cost the MMAs that run beside it)
+#define EPI_STORE(...) do { if (!(kTcProfile && (kdbg & 2))) store_slab_u(__VA_ARGS__); } while (0)
 template <bool kBwd, bool kStash, bool kX3, bool kF8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcParams p) {
@@ -1292,14 +1295,14 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                     if (e & 1) { r8[e >> 1] |= lo8 << 16; h8[e >> 1] |= hi8 << 16; }
                     else { r8[e >> 1] = lo8; h8[e >> 1] = hi8; }
                   }
-                  store_slab_u(s_act, (c0 >> 3) + sl, row, hi[0], hi[1], hi[2], hi[3]);
+                  EPI_STORE(s_act, (c0 >> 3) + sl, row, hi[0], hi[1], hi[2], hi[3]);
                 }
                 if (st.out_lo) {       // (not for the last hidden layer inside render(): its lo columns hold the aux inputs)
                   const int u8 = L::lo / 8 + (c0 >> 4);
-                  store_slab_u(s_act, u8, row, r8[0], r8[1], r8[2], r8[3]);
-                  store_slab_u(s_act, u8 + 1, row, r8[4], r8[5], r8[6], r8[7]);
-                  store_slab_u(s_act, u8 + 16, row, h8[0], h8[1], h8[2], h8[3]);
-                  store_slab_u(s_act, u8 + 17, row, h8[4], h8[5], h8[6], h8[7]);
+                  EPI_STORE(s_act, u8, row, r8[0], r8[1], r8[2], r8[3]);
+                  EPI_STORE(s_act, u8 + 1, row, r8[4], r8[5], r8[6], r8[7]);
+                  EPI_STORE(s_act, u8 + 16, row, h8[0], h8[1], h8[2], h8[3]);
+                  EPI_STORE(s_act, u8 + 17, row, h8[4], h8[5], h8[6], h8[7]);
                 }
               } else if constexpr (kX3) {
                 // split-precision hand-off: y = relu(acc) leaves as hi = bf16(y) in the main columns and, for the VF
@@ -1325,8 +1328,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                       }
                     }
                     const int slab = (c0 >> 3) + 4 * hf + sl;
-                    store_slab_u(s_act, slab, row, hi[0], hi[1], hi[2], hi[3]);
-                    if (out_lo) store_slab_u(s_act, slab + L::lo / 8, row, lo[0], lo[1], lo[2], lo[3]);
+                    EPI_STORE(s_act, slab, row, hi[0], hi[1], hi[2], hi[3]);
+                    if (out_lo) EPI_STORE(s_act, slab + L::lo / 8, row, lo[0], lo[1], lo[2], lo[3]);
                   }
                 }
               } else if (!(kdbg & 2)) {
