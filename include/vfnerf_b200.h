@@ -219,7 +219,7 @@ int vfnerf_adam_step(float* p, float* g, float* m, float* v, const uint8_t* mask
 /* ---- both MLPs on given points: the VF + colour evaluation of VectorFieldNerf.get_colors ---------------- */
 /* (vector_field_nerf.py:341-375 / the merged pass of render(), :292-321).  points [P,3]; ray_dirs [P/samples_per_ray,3]
  * unit view directions, one per ray; normals [P,3] = tanh VF vectors; colors [P,3] = sigmoid colour-net output.
- * One fused tcgen05 launch (bf16 precision only); repack != 0 re-tiles the weights first (needed after any
+ * One fused tcgen05 launch (tensor-core precisions only: bf16, bf16x3, fp16f8); repack != 0 re-tiles the weights first (needed after any
  * parameter update; 0 reuses the images already in `workspace`). */
 int64_t vfnerf_mlp_points_workspace_bytes(const vfnerf_mlp_desc* vf, const vfnerf_mlp_desc* rn, int multires,
                                           int multires_view, int skip_layer);

@@ -42,6 +42,15 @@ int vfnerf_debug_umma2_bench(int n_mma, int mode, int n_ctas, long long* cycles_
 int vfnerf_debug_stash_read(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, const vfnerf_mlp_desc* rn,
                             void* workspace, int tensor, float* out, int* n_cols, void* stream);
 
+/* Host only (no launch, no GPU): the per-chunk records the fused tensor-core kernel's MMA issuer / weight producer / relay
+ * lane read from the kernel parameters, for one program of the render() plan (0 render, 1 VF + features, 2 VF vector only,
+ * 3 dgrad chain of render() [keep_for_backward], 4 dgrad chain of the VF net).  records [n_steps][20][4] = {A offset,
+ * K columns | barrier mask << 16, bytes | offset/16 << 16, flags}; n_chunks [n_steps]; step_facts [n_steps][6] = {N, K,
+ * chunk_k, n_seg, fresh_mask, use_lo}. */
+int vfnerf_debug_chunk_table(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, const vfnerf_mlp_desc* rn,
+                             int keep_for_backward, int program, uint32_t* records, int* n_chunks, int* step_facts,
+                             int* n_steps);
+
 #ifdef __cplusplus
 }
 #endif

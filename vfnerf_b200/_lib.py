@@ -113,6 +113,7 @@ DEBUG_PROTOTYPES = {
     "vfnerf_debug_umma2_bench": (_I, [_I, _I, _I, _P, _P]),
     "vfnerf_debug_stash_read": (_I, [_P, _P, _P, _P, _I, _P, _P, _P]),
     "vfnerf_debug_umma_bench": (_I, [_I, _I, _I, _I, _P, _P]),
+    "vfnerf_debug_chunk_table": (_I, [_CFG, _DESC, _DESC, _I, _I, _P, _P, _P, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

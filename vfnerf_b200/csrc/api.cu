@@ -410,6 +410,16 @@ int vfnerf_debug_stash_read(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc*
   cudaFree(tmp);
   return e;
 }
+
+// host only: the chunk records behind one tensor-core program of the render() plan (no GPU needed)
+int vfnerf_debug_chunk_table(const vfnerf_render_cfg* cfg, const vfnerf_mlp_desc* vf, const vfnerf_mlp_desc* rn, int keep_for_backward,
+                             int program, uint32_t* records, int* n_chunks, int* step_facts, int* n_steps) {
+  VFN_REQUIRE(cfg && vf && rn && records && n_chunks && step_facts && n_steps, "chunk_table: null argument");
+  VFN_REQUIRE(cfg->precision != VFNERF_PREC_FP32, "chunk_table: tensor-core precisions only");
+  RenderPlan p;
+  if (int e = make_plan(*cfg, *vf, *rn, keep_for_backward, nullptr, p)) return e;
+  return tc_debug_chunk_table(p.tc, program, records, n_chunks, step_facts, n_steps);
+}
 #endif  // VFNERF_DEBUG_EXPORTS
 
 // ---- VF-only query -----------------------------------------------------------------------------

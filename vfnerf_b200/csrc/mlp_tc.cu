@@ -1702,6 +1702,26 @@ int tc_carve(char* base, int64_t& off, int multires, int multires_view, int skip
   return 0;
 }
 
+// test support (host only): the chunk records the MMA issuer, the weight producer and the relay lane will read for one
+// program of a plan -- records[step][chunk][4], n_chunks[step], step_facts[step][6] = N, K, chunk_k, n_seg, fresh_mask, use_lo
+int tc_debug_chunk_table(const TcPlan& plan, int program, uint32_t* records, int* n_chunks, int* step_facts, int* n_steps) {
+  const TcProgram& pr = program == 0 ? plan.render : program == 1 ? plan.vf_full : program == 2 ? plan.v_only
+                        : program == 3 ? plan.bwd : plan.bwd_vf;
+  *n_steps = pr.n_steps;
+  for (int si = 0; si < pr.n_steps; ++si) {
+    TcChunk rec[kTcMaxChunks];
+    n_chunks[si] = tc_chunk_records(pr, si, rec);
+    for (int c = 0; c < n_chunks[si]; ++c) {
+      uint32_t* o = records + ((size_t)si * kTcMaxChunks + c) * 4;
+      o[0] = rec[c].x; o[1] = rec[c].y; o[2] = rec[c].z; o[3] = rec[c].w;
+    }
+    const TcStep& st = pr.s[si];
+    int* f = step_facts + si * 6;
+    f[0] = st.N; f[1] = st.K; f[2] = st.chunk_k; f[3] = st.n_seg; f[4] = st.fresh_mask; f[5] = st.use_lo;
+  }
+  return 0;
+}
+
 int tc_prepare(const vfnerf_mlp_desc& vf, const float* vf_arena, const vfnerf_mlp_desc* rn,
                const float* rn_arena, float bn_eps, const TcPlan& plan, cudaStream_t s) {
   const TcProgram& pr = rn ? plan.render : plan.vf_full;

@@ -179,6 +179,9 @@ int tc_backward_vf(const TcPlan& plan, const vfnerf_mlp_desc& vf, const float* v
                    const float* out, int64_t out_ld, const float* d_out, int64_t d_ld, int n_out_cols, float* vf_grad,
                    int accumulate, cudaStream_t s);
 
+// test support (host only, no launch): the host-built chunk records of one program (0 render, 1 vf_full, 2 v_only, 3 dgrad
+// of render(), 4 dgrad of the VF net): records [n_steps][kTcMaxChunks][4], n_chunks [n_steps], step_facts [n_steps][6]
+int tc_debug_chunk_table(const TcPlan& plan, int program, uint32_t* records, int* n_chunks, int* step_facts, int* n_steps);
 // test support: convert one stash tensor (or, tensor == 1000, the two [n,3] output-layer gradients) to row-major fp32
 int tc_debug_stash_read(const TcPlan& plan, int tensor, int64_t n, float* out, int* n_cols, cudaStream_t s);
 
