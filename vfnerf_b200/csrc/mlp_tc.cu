@@ -1342,16 +1342,6 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                 for (int sl = 0; sl < 4; ++sl)
                   store_slab_u(s_act, (c0 >> 3) + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
-                uint32_t gate_lo = 0, gate_hi = 0;
-                const bool st_gate = st_on && !(kdbg & 16);   // experiment switch (the activations themselves leave via warp 14)
-                if (st_gate) {
-                  // gate bit e = "pre-activation of column c0 + e is not negative": one funnel shift per element
-                  // collects the fp32 sign bits (an exact zero passes the gate; its gradient contribution is zero or
-                  // belongs to a padded channel)
-#pragma unroll
-                  for (int j = 31; j >= 0; --j) gate_lo = __funnelshift_l(va[j], gate_lo, 1);
-                  gate_lo = ~gate_lo;
-                }
                 if (second) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
@@ -1361,14 +1351,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                   for (int sl = 0; sl < 4; ++sl)
                     store_slab_u(s_act, (c0 >> 3) + 4 + sl, row, pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
-                  if (st_gate) {
-#pragma unroll
-                    for (int j = 31; j >= 0; --j) gate_hi = __funnelshift_l(vb[j], gate_hi, 1);
-                    gate_hi = ~gate_hi;
-                  }
                 }
-                // the backward gates on the sign only: 8 bytes per row and 64-column group instead of 128
-                if (st_gate && !feat) *gate_unit(p, st.stash_out, tile, bg, row) = make_uint2(gate_lo, gate_hi);
               }
               TCK(t_math);
               fence_proxy_async_smem();
@@ -1376,6 +1359,25 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
               if (consumer) arrive_grp(bg);
               TCK(t_sig);
+              if constexpr (kStash && !kX3) {
+                // training forward: the ReLU gates of this group as bits, AFTER the group has been handed on (the next
+                // layer's MMAs wait for the arrival above, not for this).  Gate bit e = "pre-activation of column c0 + e is
+                // not negative": one funnel shift per element collects the fp32 sign bits (an exact zero passes the gate;
+                // its gradient contribution is zero or belongs to a padded channel).  The backward gates on the sign
+                // only: 8 bytes per row and 64-column group instead of 128.
+                if (st_on && !feat && !(kdbg & 16) && !(kdbg & 2)) {
+                  uint32_t gate_lo = 0, gate_hi = 0;
+#pragma unroll
+                  for (int j = 31; j >= 0; --j) gate_lo = __funnelshift_l(va[j], gate_lo, 1);
+                  gate_lo = ~gate_lo;
+                  if (second) {
+#pragma unroll
+                    for (int j = 31; j >= 0; --j) gate_hi = __funnelshift_l(vb[j], gate_hi, 1);
+                    gate_hi = ~gate_hi;
+                  }
+                  *gate_unit(p, st.stash_out, tile, bg, row) = make_uint2(gate_lo, gate_hi);
+                }
+              }
               if (tl && it == 0) p.dbg_buf[64 + si * 8 + 3 + 3 * h] = clock64();
               if (tl) p.dbg_buf[64 + si * 8 + 4 + 3 * h] = clock64();
             }
