@@ -613,6 +613,15 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       if (rank == 0) mbar_arrive(&grp[g]); else mbar_arrive_remote(&grp[g], 0);
     }
   };
+  // the same with the stash hand-shake of the training kernels folded in: ONE warp barrier, the arrival the MMA issuer is
+  // waiting for first, then "this group may be copied out" for warp 14
+  auto publish = [&](int g, bool to_issuer, uint64_t* st_ready_bar) {
+    __syncwarp();
+    if (lane == 0) {
+      if (to_issuer) { if (rank == 0) mbar_arrive(&grp[g]); else mbar_arrive_remote(&grp[g], 0); }
+      if (st_ready_bar) mbar_arrive(st_ready_bar);
+    }
+  };
 
   if (warp == 0) {
     // ===================== weight producer =====================
@@ -1178,10 +1187,9 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int it = 0; it < 2; ++it) {
             const int bg = 2 * it + h, c0 = bg * 64;
-            if (st_tile) mbar_wait(&st_done[bg], (su & 1) ^ 1);
             if (c0 >= stN) {
-              if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
-              if (hand_on) arrive_grp(bg);
+              if (st_tile) mbar_wait(&st_done[bg], (su & 1) ^ 1);
+              publish(bg, hand_on, st_tile ? &st_ready[bg] : nullptr);
               continue;
             }
             const bool second = c0 + 32 < stN;
@@ -1191,6 +1199,9 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               const int cb = c0 + 32 * half;
               uint32_t va[32];
               tmem_ld32(acc + cb, va);
+              // the bulk copy of this group's previous contents must have read them before they are overwritten: checked
+              // while the accumulator load is in flight
+              if (st_tile && half == 0) mbar_wait(&st_done[bg], (su & 1) ^ 1);
               uint4 yt[4];
               if (is_tanh) {
 #pragma unroll
@@ -1222,8 +1233,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             if (hand_on) {
               fence_proxy_async_smem();
               tc_fence_before_sync();
-              if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
-              arrive_grp(bg);
+              publish(bg, true, st_tile ? &st_ready[bg] : nullptr);
             }
           }
           if (st_tile) ++su;
@@ -1258,11 +1268,9 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             for (int it = 0; it < kIts; ++it) {
               const int bg = kSerialGroups ? it : 2 * it + h;
               const int c0 = kSerialGroups ? bg * 64 + 32 * h : bg * 64;
-              // the bulk copy of this group's previous contents (last stashed step) must have read them
-              if (st_tile) mbar_wait(&st_done[bg], (su & 1) ^ 1);
               if (c0 >= stN) {                                 // narrow layer: nothing to write, the barriers still count us
-                if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
-                if (consumer) arrive_grp(bg);
+                if (st_tile) mbar_wait(&st_done[bg], (su & 1) ^ 1);
+                publish(bg, consumer, st_tile ? &st_ready[bg] : nullptr);
                 continue;
               }
               // nothing leaves through the activation tile (inference: the last step only feeds the prologue warps' dot)
@@ -1270,10 +1278,15 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               const bool second = !kSerialGroups && c0 + 32 < stN;
               uint32_t va[32], vb[32];
               TCK(t_other);
+              if (tl && it == 0 && warp == 2) p.dbg_buf[64 + si * 8 + 5] = clock64();
               tmem_ld32(acc + c0, va);
               if (second) tmem_ld32(acc + c0 + 32, vb);
+              // the bulk copy of this group's previous contents (last stashed step) must have read them before they are
+              // overwritten: checked while the accumulator load is in flight
+              if (st_tile) mbar_wait(&st_done[bg], (su & 1) ^ 1);
               tmem_ld_wait();
               TCK(t_ld);
+              if (tl && it == 0 && warp == 2) p.dbg_buf[64 + si * 8 + 6] = clock64();
               if (kF8 && st.a_f16 && !feat) {
                 // fp16 + fp8-remainder hand-off of a VF hidden layer: y = relu(acc) leaves as fp16(y) in the main columns,
                 // e5m2(y - fp16(y)) and e5m2(2^-12 y) in the lo region (16 columns per 16-byte unit there)
@@ -1354,10 +1367,10 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                 }
               }
               TCK(t_math);
+              if (tl && it == 0 && warp == 2) p.dbg_buf[64 + si * 8 + 7] = clock64();
               fence_proxy_async_smem();
               tc_fence_before_sync();
-              if (st_tile) { __syncwarp(); if (lane == 0) mbar_arrive(&st_ready[bg]); }
-              if (consumer) arrive_grp(bg);
+              publish(bg, consumer, st_tile ? &st_ready[bg] : nullptr);
               TCK(t_sig);
               if constexpr (kStash && !kX3) {
                 // training forward: the ReLU gates of this group as bits, AFTER the group has been handed on (the next
@@ -1835,9 +1848,10 @@ int tc_forward(const TcPlan& plan, int mode, const float* points, const GridSpec
 
     for (int si = 0; si < p.prog.n_steps && base; ++si) {
       const long long* e = h + 64 + si * 8;
-      fprintf(stderr, "[tc timeline] step %2d: first_mma %6lld commit %6lld | h0: acc_seen %6lld first_arrive %6lld last_arrive %6lld | "
-              "h1: acc_seen %6lld first_arrive %6lld last_arrive %6lld\n", si, e[0] - base, e[1] - base, e[2] - base,
-              e[3] ? e[3] - base : 0, e[4] ? e[4] - base : 0, e[5] - base, e[6] ? e[6] - base : 0, e[7] ? e[7] - base : 0);
+      fprintf(stderr, "[tc timeline] step %2d: first_mma %6lld commit %6lld | acc_seen %6lld first_arrive %6lld last_arrive %6lld | "
+              "first group of warp 2: region free %6lld, tcgen05.ld done %6lld, converted + stored %6lld\n", si, e[0] - base, e[1] - base,
+              e[2] - base, e[3] ? e[3] - base : 0, e[4] ? e[4] - base : 0, e[5] ? e[5] - base : 0, e[6] ? e[6] - base : 0,
+              e[7] ? e[7] - base : 0);
     }
   }
 #endif
