@@ -1,26 +1,29 @@
-// Fused tensor-core MLP chain (VFNERF_PREC_BF16): the VF MLP (positional encoding -> 9 Linear+BN+ReLU
+// Fused tensor-core MLP chain (precisions bf16, bf16x3, fp16f8): the VF MLP (positional encoding -> 9 Linear+BN+ReLU
 // layers with skip -> tanh) and, in RENDER mode, the colour MLP (5 layers -> sigmoid) evaluated for a
-// tile of 128 points entirely on chip.  SURVEY.md §8 rows a3 + a8.
+// tile of 128 points entirely on chip.  SURVEY.md §8 rows a3 + a8.  DESIGN.md §4 is the long description.
 //
-// One CTA per SM, 320 threads, CTAs paired into clusters of two (tcgen05 cta_group::2): each CTA owns one
+// One CTA per SM, 480 threads, CTAs paired into clusters of two (tcgen05 cta_group::2): each CTA owns one
 // 128-point tile (its A operand and its TMEM accumulators) but only HALF of every weight chunk (N/2 output
 // channels); one MMA instruction of the leader drives both SMs' tensor cores with M = 256.  Per SM this halves
-// the shared-memory bytes moved per MMA (the limiter of the 1-CTA version, DESIGN.md §4) and the L2 traffic.
-//   warp 0      weight producer: one lane streams this CTA's half of each pre-tiled bf16 weight chunk (<= 16 KiB)
-//               from L2 into an 8-slot shared-memory ring with cp.async.bulk + mbarriers     (SASS UBLKCP)
-//   warp 1      leader CTA: MMA issuer -- one lane issues tcgen05.mma.cta_group::2 (M=256, N<=256, K=16, bf16 x
-//               bf16 -> fp32 in TMEM); tcgen05.commit (multicast) releases ring slots and publishes the
-//               accumulators in both CTAs (SASS UTCHMMA).  Peer CTA: relay lane that forwards "my half of the
-//               chunk has landed" to the leader with a remote mbarrier arrive
-//   warps 2..9  epilogue: tcgen05.ld the fp32 accumulator (one row per thread, 32 columns at a time),
-//               convert to bf16x2, ReLU / tanh on the packed pair, and write the NEXT layer's A operand
-//               straight into the activation tile in the K-slab UMMA layout -- activations never leave
-//               the SM.  The folded BatchNorm scale lives in the weights and the shift is a (hi, lo) bias
-//               row multiplied by a constant ones-column of A, so the epilogue has no per-channel operand.
-// Overlap inside the CTA: two 256-column TMEM accumulators (step s uses buffer s&1) and one "ready"
-// mbarrier per 32-column group of the activation tile; the MMAs of layer l+1 start on K chunk g as soon as
-// group g of layer l's output is in shared memory, so they trail the epilogue by about one chunk.
-// Weights: 1.1 MB (VF) + 0.6 MB (colour) bf16, L2 resident, re-streamed per tile.
+// the shared-memory bytes moved per MMA (the limiter of the 1-CTA version) and the L2 traffic.
+//   warp 0        weight producer: one lane streams this CTA's half of each pre-tiled weight chunk from L2 into the
+//                 shared-memory ring (3 x 32 KiB, split-precision tile: 4 x 16 KiB) with cp.async.bulk + mbarriers (UBLKCP)
+//   warp 1        leader CTA: MMA issuer -- the whole warp runs the loop on the uniform datapath (chunk records from the
+//                 kernel parameters), one elected lane issues tcgen05.mma.cta_group::2 (M=256, N<=256; bf16 / fp16 K=16,
+//                 8-bit K=32 -> fp32 in TMEM); tcgen05.commit (multicast) releases ring slots and publishes the
+//                 accumulators in both CTAs (SASS UTCHMMA / UTCQMMA)
+//   warps 2..9    epilogue: tcgen05.ld the fp32 accumulator (one row per thread, 32 columns at a time), ReLU / tanh,
+//                 conversion (bf16; bf16 hi + lo; fp16 + two 8-bit copies), and the NEXT layer's A operand written
+//                 straight into the activation tile in the K-slab UMMA layout -- activations never leave the SM.
+//                 The folded BatchNorm scale lives in the weights and the shift is a (hi, lo) bias row multiplied
+//                 by a constant ones-column of A, so the epilogue has no per-channel operand.
+//   warps 10..13  prologue, one tile ahead: positional encodings, colour-net side inputs; the two 3-wide output layers
+//                 (VF vector, colour) as fp32 CUDA-core dot products on the accumulator row
+//   warp 14       training: bulk-copies finished column groups to the activation stash; inference: the peer CTA's relay
+//                 lane ("my half of the chunk has landed" -> the leader's `full` barrier)
+// Overlap inside the CTA: two 256-column TMEM accumulators (step s uses buffer s&1) and one "ready" mbarrier per
+// 64-column group of the activation tile; the MMAs of layer l+1 start on K chunk g as soon as group g of layer l's
+// output is in shared memory.  Weights: 1.1 MB (VF) + 0.6 MB (colour) per 16-bit copy, L2 resident, re-streamed per tile.
 #include <cstdlib>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
@@ -501,15 +504,6 @@ constexpr bool kTcProfile = false;
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
-#ifndef KS1
-#define KS1 kStash
-#endif
-#ifndef KS2
-#define KS2 kStash
-#endif
-#ifndef KS3
-#define KS3 kStash
-#endif
 // activation-tile stores of the split-precision epilogue (profile builds: VFNERF_TC_DBG bit 1 drops them -- garbage results --
 // to see what the epilogue's shared-memory writes cost the MMAs that run beside it)
 #define EPI_STORE(...) do { if (!(kTcProfile && (kdbg & 2))) store_slab_u(__VA_ARGS__); } while (0)
@@ -857,7 +851,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
       }
           }
     }
-    if constexpr (KS1) {
+    if constexpr (kStash) {
       if (lane == 0) {
         uint32_t su = 0;
         for (long long pair = pair0; pair < num_pairs; pair += pair_step) {
@@ -963,7 +957,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         const long long tile = tile_of(pair);
         const long long pi = tile * kTileM + row;
         const bool valid = pi < p.n_points;
-        const bool st_on = KS2 && tile < num_tiles;
+        const bool st_on = kStash && tile < num_tiles;
         float pt[3], emb[48];
         load_point(p, pi, valid, pt);
 #pragma unroll
@@ -1024,7 +1018,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
         const long long tile = tile_of(pair);
         const long long pi = tile * kTileM + row;
         const bool valid = pi < p.n_points;
-        const bool st_on = KS2 && tile < num_tiles;
+        const bool st_on = kStash && tile < num_tiles;
         float pt[3], a[40], d[3] = {0.f, 0.f, 0.f};
         load_point(p, pi, valid, pt);
 #pragma unroll
@@ -1104,7 +1098,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
             // reader (the colour net's first layer of the previous tile) completed long ago
             const float a[8] = {nv[0], nv[1], nv[2], 0.f, 0.f, 0.f, 0.f, 0.f};
             store_slab_f(s_act, L::aux / 8, rowd, a);
-            if (KS2 && tile < num_tiles)
+            if (kStash && tile < num_tiles)
               *stash_unit(p, p.sinfo.idx_aux, tile, 0, rowd) = make_uint4(pack_bf16x2(nv[0], nv[1]), pack_bf16x2(nv[2], 0.f), 0u, 0u);
             fence_proxy_async_smem();
             arrive_pro(kBarAux);           // matched by the colour net's first step
@@ -1248,8 +1242,8 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const bool feat = st.epi == TC_EPI_FEAT;
           const bool to_act = !feat || render;
           const int stN = st.N;
-          const bool st_on = KS3 && st.stash_out >= 0 && tile < num_tiles;
-          const bool st_tile = KS3 && st.stash_out >= 0 && to_act;     // this step's output leaves through warp 14
+          const bool st_on = kStash && st.stash_out >= 0 && tile < num_tiles;
+          const bool st_tile = kStash && st.stash_out >= 0 && to_act;     // this step's output leaves through warp 14
           // the last step of a program has no consumer in the activation tile: its output is only stashed (training)
           // and/or reduced to a 3-wide output by the prologue warps (TcStep::dot), and it must not arrive on the
           // column-group barriers (every arrival set is matched by exactly one wait of the MMA issuer)
