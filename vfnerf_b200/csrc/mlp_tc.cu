@@ -1187,22 +1187,25 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               continue;
             }
             const bool second = c0 + 32 < stN;
+            // both 32-column halves of the group are loaded together (like the forward epilogue): one wait, not two
+            uint32_t vab[2][32];
+            tmem_ld32(acc + c0, vab[0]);
+            if (second) tmem_ld32(acc + c0 + 32, vab[1]);
+            // the bulk copy of this group's previous contents must have read them before they are overwritten: checked
+            // while the accumulator load is in flight
+            if (st_tile) mbar_wait(&st_done[bg], (su & 1) ^ 1);
+            tmem_ld_wait();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               if (half == 1 && !second) break;
               const int cb = c0 + 32 * half;
-              uint32_t va[32];
-              tmem_ld32(acc + cb, va);
-              // the bulk copy of this group's previous contents must have read them before they are overwritten: checked
-              // while the accumulator load is in flight
-              if (st_tile && half == 0) mbar_wait(&st_done[bg], (su & 1) ^ 1);
+              const uint32_t* va = vab[half];
               uint4 yt[4];
               if (is_tanh) {
 #pragma unroll
                 for (int sl = 0; sl < 4; ++sl)
                   yt[sl] = t_ok ? __ldg(stash_unit(p, st.mask_src, tile, (cb >> 3) + sl, row)) : make_uint4(0, 0, 0, 0);
               }
-              tmem_ld_wait();
               const uint32_t bits = gbits[it][half];
 #pragma unroll
               for (int sl = 0; sl < 4; ++sl) {
