@@ -48,7 +48,9 @@ extern "C" {
 #define VFNERF_PREC_BF16 1    /* tcgen05 bf16 x bf16 -> fp32 in TMEM (256-wide nets) -- 5e-3 contract       */
 #define VFNERF_PREC_BF16X3 2  /* tcgen05, hi/lo split operands, 3 MMAs per product -- fp32-class accuracy   */
 #define VFNERF_PREC_FP16F8 3  /* tcgen05, fp16 product + two 8-bit remainder products (kind::f8f6f4) per VF product:
-                               * 2 tensor-core units instead of 3, ~1e-3 on the reference goldens (forward only)  */
+                               * 2 tensor-core units instead of 3, ~1e-3 on the reference goldens (forward only).
+                               * Hidden VF activations and folded weights travel as fp16: they must stay below 65504
+                               * (any BatchNorm-ed net does); VFNERF_PREC_BF16X3 keeps fp32's range              */
 
 /* One MLP (Linear [+ BatchNorm1d in eval mode] per layer).  All parameters AND running statistics of
  * the network live in one contiguous fp32 "arena"; the offsets below are in floats.  -1 = absent.
