@@ -550,6 +550,25 @@ def main():
                 tf = A_train * n_r / (ms_k * 1e-3) / 1e12
                 ko[str(n_r)] = {"ms_per_step": ms_k, "rays_per_s": n_r / (ms_k * 1e-3), "algorithmic_tflops": tf,
                                 "frac_of_burst_bf16_peak": tf / peak_burst, "frac_of_sustained_bf16_peak": tf / peak_sust}
+            if "8192" in ko:
+                # the same step against its OTHER roof: DRAM bytes of the three big kernels from the committed ncu capture
+                # of an 8192-ray step (profiles/r02_prof_train_kernels_raw.csv: forward with stash x 2, dgrad chain, wgrad)
+                tr_path = os.path.join(ROOT, "profiles", "r02_prof_train_kernels_raw.csv")
+                if os.path.exists(tr_path):
+                    import csv
+                    rows = list(csv.reader(open(tr_path)))
+                    hdr, units = rows[0], rows[1]
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                    tot = 0.0
+                    for vals in rows[2:]:
+                        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                            i = hdr.index(key)
+                            tot += float(vals[i]) * scale[units[i]]
+                    gbs = tot / (ko["8192"]["ms_per_step"] * 1e-3) / 1e9
+                    ko["8192"]["hbm"] = {"traffic_bytes_per_step": tot, "achieved_gbs": gbs, "peak_gbs": pk["hbm_gbs"],
+                                         "frac_of_measured_hbm_peak": gbs / pk["hbm_gbs"],
+                                         "traffic_source": "profiles/r02_prof_train_kernels_raw.csv (ncu --set full: forward with "
+                                                           "stash x 2, dgrad chain, wgrad of one 8192-ray step)"}
             if ko:
                 train["kernels_only"] = dict(ko, note="fwd + loss gradient + bwd into the flat gradient buffers, CUDA-graph "
                                              "replay, median of 50 (a graph replay timed alone: the burst peak is the honest "
