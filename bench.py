@@ -797,9 +797,9 @@ def main():
     if hbm:
         line["hbm_kernels"] = hbm
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rps, med, threads = cpu_reference_rays_per_s(3, 1)
+        rps, med, threads = cpu_reference_rays_per_s(5, 2)      # median of >= 5 after 2 warm-ups
         line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": "3 timed renders of one 1024-ray chunk (median) after 1 warm-up, oracle port on host cores"}
+                                "sample": "5 timed renders of one 1024-ray chunk (median) after 2 warm-ups, oracle port on host cores"}
         try:
             g_rps, g_med, _ = cpu_reference_rays_per_s(5, 2, device=str(dev))
             line["cpu_baseline"]["gpu_eager_context"] = {
