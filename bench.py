@@ -454,7 +454,13 @@ def main():
                              "normals": out.coarse_normals.reshape(-1, 3), "supervised_normals": None,
                              "directional_derivatives": None}, {"rgb": rgb_t, "depth": dep_t}, 0)[0]
 
-        def time_train(prec, n_tr, arena=False, train_mode=False):
+        # supervision variant of config 3 (train/vector_field_nerf_train.py:180-216): (R * N) // 10 = 13 107
+        # border + 13 107 centre points through the VF-only module call, MSE against unit target directions
+        n_sup = 2 * ((Rt * (N_COARSE + N_FINE)) // 10)
+        sup_pts = (torch.rand(n_sup, 3, device=dev, generator=g2) - 0.5) * 6
+        sup_tgt = torch.nn.functional.normalize(torch.randn(n_sup, 3, device=dev, generator=g2), dim=1)
+
+        def time_train(prec, n_tr, arena=False, train_mode=False, supervised=False):
             tm = U.make_model(dict(CASE, perturb=True, dir_to_normal_th=-2.0), st, dev, precision=prec)
             if train_mode:
                 tm.train()          # batch-statistic BatchNorm + Jacobian + directional derivatives (csrc/mlp_train.cu)
@@ -464,7 +470,14 @@ def main():
 
             def train_step():
                 out = tm.render(poset, uvt, Kt, 0, draws=draws_t)
-                loss = vf_loss(out, rgb_gt, dep_gt)
+                if supervised:
+                    sup = tm.vector_field_network(sup_pts)[:, :3]
+                    loss = loss_mod({"rgb": out.coarse_rgb_values, "depth": out.coarse_depth_map,
+                                     "normals": out.coarse_normals.reshape(-1, 3), "supervised_normals": sup,
+                                     "directional_derivatives": None},
+                                    {"rgb": rgb_gt, "depth": dep_gt, "supervised_normals": sup_tgt}, 0)[0]
+                else:
+                    loss = vf_loss(out, rgb_gt, dep_gt)
                 tm.optimizer.zero_grad()
                 loss.backward()
                 if world > 1:
@@ -493,6 +506,13 @@ def main():
                                                    "density), issued when backward() returns" if world > 1 else None,
                                      "includes": "eager: render + fused VFLoss + backward + (allreduce of the flat gradient "
                                                  "arenas) + ArenaAdam (clip + Adam)"}
+
+        if train_prec == "bf16" and not args.no_extra:
+            ms_sup = time_train(train_prec, 10, arena=True, supervised=True)
+            train["arena_adam_eager_with_supervision"] = {
+                "ms_per_step": ms_sup, "supervision_points": n_sup, "value": world * Rt / (ms_sup * 1e-3), "unit": "rays/s",
+                "includes": "the eager ArenaAdam step + 2 x 13 107 supervision points through the VF-only module call (forward "
+                            "with stash + dgrad + wgrad accumulated into the same gradient arena) and the supervision MSE term"}
 
         # the same sequence captured once as a CUDA graph and replayed (vfnerf_b200/graphed.py), and -- SURVEY.md §8(d)
         # training protocol (i) -- the kernels alone: fwd + loss gradient + bwd into the flat gradient buffers,
