@@ -1237,16 +1237,20 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
           tc_fence_before_sync();
         } else {
         TCK(t_other);
+        // the step's facts are fetched from the parameter bank BEFORE the accumulator wait (the empty asm pins the loads
+        // there): behind it every cycle is hand-off time -- tensor-core idle time
+        const int st_epi = st.epi, st_n = st.N, st_stash = st.stash_out, st_outlo = st.out_lo, st_f16 = st.a_f16;
+        asm volatile("" ::"r"(st_epi), "r"(st_n), "r"(st_stash), "r"(st_outlo), "r"(st_f16));
         mbar_wait(&acc_full[gstep & 1], (gstep >> 1) & 1);
         TCK(t_acc);
         if (tl) p.dbg_buf[64 + si * 8 + 2 + 3 * h] = clock64();
         tc_fence_after_sync();
-        if (st.epi == TC_EPI_RELU || st.epi == TC_EPI_FEAT) {
-          const bool feat = st.epi == TC_EPI_FEAT;
+        if (st_epi == TC_EPI_RELU || st_epi == TC_EPI_FEAT) {
+          const bool feat = st_epi == TC_EPI_FEAT;
           const bool to_act = !feat || render;
-          const int stN = st.N;
-          const bool st_on = kStash && st.stash_out >= 0 && tile < num_tiles;
-          const bool st_tile = kStash && st.stash_out >= 0 && to_act;     // this step's output leaves through warp 14
+          const int stN = st_n;
+          const bool st_on = kStash && st_stash >= 0 && tile < num_tiles;
+          const bool st_tile = kStash && st_stash >= 0 && to_act;     // this step's output leaves through warp 14
           // the last step of a program has no consumer in the activation tile: its output is only stashed (training)
           // and/or reduced to a 3-wide output by the prologue warps (TcStep::dot), and it must not arrive on the
           // column-group barriers (every arrival set is matched by exactly one wait of the MMA issuer)
@@ -1284,7 +1288,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               tmem_ld_wait();
               TCK(t_ld);
               if (tl && it == 0 && warp == 2) p.dbg_buf[64 + si * 8 + 6] = clock64();
-              if (kF8 && st.a_f16 && !feat) {
+              if (kF8 && st_f16 && !feat) {
                 // fp16 + fp8-remainder hand-off of a VF hidden layer: y = relu(acc) leaves as fp16(y) in the main columns,
                 // e5m2(y - fp16(y)) and e5m2(2^-12 y) in the lo region (16 columns per 16-byte unit there)
                 const uint32_t* v = va;            // (kSerialGroups: 32 columns per warp and iteration)
@@ -1307,7 +1311,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
                   }
                   EPI_STORE(s_act, (c0 >> 3) + sl, row, hi[0], hi[1], hi[2], hi[3]);
                 }
-                if (st.out_lo) {       // (not for the last hidden layer inside render(): its lo columns hold the aux inputs)
+                if (st_outlo) {       // (not for the last hidden layer inside render(): its lo columns hold the aux inputs)
                   const int u8 = L::lo / 8 + (c0 >> 4);
                   EPI_STORE(s_act, u8, row, r8[0], r8[1], r8[2], r8[3]);
                   EPI_STORE(s_act, u8 + 1, row, r8[4], r8[5], r8[6], r8[7]);
@@ -1317,7 +1321,7 @@ mlp_tc_kernel(const __grid_constant__ TcParams p) {
               } else if constexpr (kX3) {
                 // split-precision hand-off: y = relu(acc) leaves as hi = bf16(y) in the main columns and, for the VF
                 // layers, lo = bf16(y - hi) in the lo columns (same slab, kX3ColLo further on)
-                const bool out_lo = st.out_lo != 0;
+                const bool out_lo = st_outlo != 0;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                   if (hf == 1 && !second) break;
